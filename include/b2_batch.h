@@ -1,0 +1,105 @@
+/* b2_batch.h — thin extern "C" ABI of the B200 batched rigid-body step.
+ *
+ * This is the drop-in boundary for the per-tick hot path of HoangGiang93/mujoco_sim.  The reference has no plugin
+ * interface: its hot path is the body of simulate() (src/mj_main.cpp:82-112), which calls the MuJoCo C API on ONE
+ * environment.  The MuJoCo-named entry points that replace those calls are declared in include/mujoco/mujoco.h;
+ * they are implemented on top of the batched entry points below (environment 0 of a batch), and a C++ host that
+ * wants N environments calls these directly.  Plain pointers and sizes only; every function returns 0 on success and
+ * a negative code on failure (b2_last_error() has the text), and never throws.  There is no CPU fallback: without a
+ * usable CUDA device b2_create fails.
+ *
+ * Reference interfaces replaced (file:line):
+ *   b2_tick          the loop body                      src/mj_main.cpp:82-112
+ *     B2_TICK_CONTROLLER   MjSim::controller            src/mujoco_sim/mj_sim.cpp:1055-1077 (mjcb_control, mj_main.cpp:49-52,196)
+ *     B2_TICK_INVERSE      MjHWInterface::read/mj_inverse  src/mujoco_sim/mj_hw_interface.cpp:59-71
+ *     B2_TICK_ODOM         MjSim::set_odom_vels         src/mujoco_sim/mj_sim.cpp:1079-1153
+ *   b2_write_commands  MjHWInterface::write            src/mujoco_sim/mj_hw_interface.cpp:73-91
+ *   b2_read_joints     MjHWInterface::read (gather)    src/mujoco_sim/mj_hw_interface.cpp:62-70
+ *   b2_forward         mj_forward                       src/mujoco_sim/mj_ros.cpp:608,1421
+ *   b2_set_controlled  MjSim::controlled_joints         src/mujoco_sim/mj_ros.cpp:634-668 (producer), mj_sim.cpp:1058-1063
+ *   b2_set_timestep    m->opt.timestep mutation         src/mj_main.cpp:150-163
+ */
+#ifndef B2_BATCH_H_
+#define B2_BATCH_H_
+#include "mujoco/mujoco.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b2_batch b2_batch;
+
+enum {
+  B2_TICK_CONTROLLER = 1 << 0,
+  B2_TICK_INVERSE = 1 << 1,
+  B2_TICK_INTEGRATE = 1 << 2,
+  B2_TICK_ODOM = 1 << 3,
+  B2_TICK_NOSOLVE = 1 << 9  /* stop after constraint assembly (mj_step1) */
+};
+enum { B2_F32 = 4, B2_F64 = 8, B2_EXPORT_STAGES = 0x100 /* OR into precision: keep stage arrays (qM, xmat, geom poses ...) readable even for contact-free models */ };
+enum { B2_ENV_MAJOR = 0, /* host buffer is [env][n] */ B2_NATIVE = 1 /* host buffer is [n][env] */ };
+
+const char* b2_last_error(void);
+int b2_device_count(void);
+
+/* nenv environments of model m on CUDA device `device`, state initialised to qpos0.  precision: B2_F32 (product
+ * path) or B2_F64 (validation of the algorithm against the fp64 oracle without rounding noise). */
+b2_batch* b2_create(const mjModel* m, int nenv, int device, int precision);
+void b2_destroy(b2_batch* b);
+int b2_nenv(const b2_batch* b);
+int b2_nenv_padded(const b2_batch* b);
+int b2_precision(const b2_batch* b);
+
+/* per-dof "controlled" mask (length nv) consumed by the controller: tau[dof] += qfrc_bias[dof] */
+int b2_set_controlled(b2_batch* b, const unsigned char* mask);
+/* odom joints of nrobot robots: dof[6*r+k] = dof index of lin x,y,z / ang x,y,z odom joint (-1: absent/disabled),
+ * qposadr[3*r+k] = qpos address of the angular x,y,z odom joints (-1: absent -> angle 0) */
+int b2_set_odom(b2_batch* b, int nrobot, const int* dof, const int* qposadr);
+int b2_set_timestep(b2_batch* b, double h);
+int b2_set_option(b2_batch* b, const char* name, double value); /* iterations, tolerance, disableflags */
+
+/* field access by MuJoCo name: qpos qvel qacc qacc_warmstart qfrc_applied xfrc_applied mocap_pos mocap_quat ddq dq
+ * odom_vels time qfrc_bias qfrc_inverse xpos xquat xmat geom_xpos geom_xmat subtree_com cdof qM qLD qLDiagInv
+ * qfrc_passive qfrc_smooth qacc_smooth qfrc_constraint efc_J efc_pos efc_margin efc_frictionloss efc_diagApprox
+ * efc_R efc_D efc_vel efc_aref efc_b efc_force efc_AR contact (26 numbers per contact)
+ * and the int fields ncon nefc efc_type efc_id contact_int (5 per contact) solver_iter status.
+ * Host buffers hold environments [env_lo, env_hi). Returns the per-environment element count. */
+int b2_field_size(const b2_batch* b, const char* field);
+int b2_set_field_f32(b2_batch* b, const char* field, const float* host, int env_lo, int env_hi, int layout);
+int b2_set_field_f64(b2_batch* b, const char* field, const double* host, int env_lo, int env_hi, int layout);
+int b2_get_field_f32(b2_batch* b, const char* field, float* host, int env_lo, int env_hi, int layout);
+int b2_get_field_f64(b2_batch* b, const char* field, double* host, int env_lo, int env_hi, int layout);
+int b2_get_field_i32(b2_batch* b, const char* field, int* host, int env_lo, int env_hi, int layout);
+/* raw device pointer of a field (SoA [element][nenv_padded], element type = batch precision or int32) */
+void* b2_device_ptr(b2_batch* b, const char* field);
+
+/* reset environments [env_lo, env_hi) to qpos0 / zero velocity */
+int b2_reset(b2_batch* b, int env_lo, int env_hi);
+/* one tick of every environment (asynchronous on the batch's stream) */
+int b2_tick(b2_batch* b, int flags);
+int b2_step(b2_batch* b, int nsteps);   /* nsteps x tick(INTEGRATE [+ CONTROLLER/INVERSE/ODOM as configured by b2_set_tick_flags]) */
+int b2_set_tick_flags(b2_batch* b, int flags);
+int b2_forward(b2_batch* b);            /* mj_forward: everything but the integration */
+int b2_sync(b2_batch* b);
+void* b2_stream(b2_batch* b);           /* cudaStream_t the batch launches on */
+long long b2_launch_count(const b2_batch* b); /* kernels launched so far */
+
+/* hardware-interface exchange for `njoint` scalar joints (jnt ids), all environments, native layout [joint][env]:
+ * write: per controlled joint, |vel_cmd| > mjMINVAL -> dq[dof] = vel_cmd else ddq[dof] = effort_cmd
+ * read : position, velocity, effort(qfrc_inverse) gathers */
+int b2_set_hw_joints(b2_batch* b, int njoint, const int* jnt_ids);
+int b2_write_commands(b2_batch* b, const float* vel_cmd_host, const float* effort_cmd_host);
+int b2_read_joints(b2_batch* b, float* pos_host, float* vel_host, float* effort_host);
+/* end-to-end tick through host buffers: H2D commands, tick, D2H joint states, synchronised */
+int b2_tick_host(b2_batch* b, const float* vel_cmd_host, const float* effort_cmd_host, float* pos_host, float* vel_host,
+                 float* effort_host);
+
+/* copy environment `env` into the legacy single-environment mjData view (fields of SURVEY.md Appendix C) */
+int b2_mirror_env(b2_batch* b, int env, mjData* d);
+/* load environment `env` from an mjData (qpos qvel qacc qacc_warmstart qfrc_applied xfrc_applied mocap time) */
+int b2_load_env(b2_batch* b, int env, const mjData* d);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,831 @@
+// batch.cu — host side of the batched engine: model packing, HBM layout, kernel launch pipeline and the extern "C"
+// ABI declared in include/b2_batch.h.  One b2_batch = nenv environments of one model on one GPU (one process per
+// GPU; shards are contiguous environment ranges).  No CPU fallback: every entry point fails
+// loudly when CUDA is not usable.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "b2_batch.h"
+#include "k_args.h"
+#include "k_collide.cuh"
+#include "k_common.cuh"
+#include "k_constraint.cuh"
+#include "k_smooth.cuh"
+#include "model_store.h"
+
+namespace {
+thread_local std::string g_err;
+int fail(const std::string& msg) { g_err = msg; return -1; }
+#define CK(call)                                                                                          \
+  do {                                                                                                    \
+    cudaError_t e_ = (call);                                                                              \
+    if (e_ != cudaSuccess) return fail(std::string(#call) + ": " + cudaGetErrorString(e_));               \
+  } while (0)
+
+struct Field {
+  void* ptr = nullptr;
+  int count = 0;   // elements per environment
+  int kind = 0;    // 0 real (batch precision), 1 int32
+};
+}  // namespace
+
+struct b2_batch {
+  const mjModel* m = nullptr;
+  int nenv = 0, nenvp = 0, device = 0, prec = 4, nsm = 148;
+  double h = 0.002;
+  cudaStream_t stream = nullptr;
+  b2::DModel hdr{};
+  std::vector<uint32_t> blob;
+  uint32_t* blob_dev = nullptr;
+  std::vector<unsigned char> controlled;
+  std::vector<int> odom_dof, odom_qpos;
+  std::map<std::string, Field> fields;
+  std::vector<void*> allocs;
+  int tick_flags = 0;
+  bool fused = false, ws_global = false, export_stages = false;
+  int smooth_block = 32;
+  size_t smooth_smem = 0, blob_smem = 0;
+  void* stage_dev = nullptr;
+  size_t stage_bytes = 0;
+  long long launches = 0;
+  int opt_iterations = 100, opt_disableflags = 0;
+  double opt_tolerance = 1e-8;
+  // hardware-interface joints
+  int nhw = 0;
+  int *hw_qadr = nullptr, *hw_dadr = nullptr, *hw_ctl = nullptr;
+  float* hw_buf = nullptr;  // [5][nhw][nenv] fp32 staging: vel_cmd, effort_cmd, pos, vel, effort
+};
+
+namespace {
+using namespace b2;
+
+// ---- model packing ----
+int pack_model(b2_batch* b) {
+  const mjModel* m = b->m;
+  DModel& h = b->hdr;
+  std::memset(&h, 0, sizeof(h));
+  const int rb = b->prec;
+  h.nq = m->nq; h.nv = m->nv; h.nbody = m->nbody; h.njnt = m->njnt; h.ngeom = m->ngeom; h.nM = m->nM; h.neq = m->neq;
+  h.npair = m->npair; h.nconmax = std::max(1, m->nconmax); h.njmax = std::max(1, m->njmax); h.nmocap = m->nmocap;
+  h.nodom = (int)b->odom_qpos.size() / 3;
+  h.disableflags = b->opt_disableflags; h.enableflags = m->opt.enableflags; h.iterations = b->opt_iterations;
+  for (int k = 0; k < 3; k++) h.gravity[k] = (float)m->opt.gravity[k];
+  h.tolerance = (float)b->opt_tolerance; h.meaninertia = (float)m->stat.meaninertia; h.impratio = (float)m->opt.impratio;
+  h.real_bytes = rb;
+  const int nq = h.nq, nv = h.nv, nbody = h.nbody, njnt = h.njnt, ngeom = h.ngeom, nM = h.nM, neq = h.neq, npair = h.npair,
+            nodom = h.nodom;
+  (void)nq; (void)nM;
+  for (int i = 0; i < nv; i++) {
+    h.has_damping |= m->dof_damping[i] > 0;
+    h.has_frictionloss |= m->dof_frictionloss[i] > 0;
+  }
+  for (int i = 0; i < nbody; i++) h.has_gravcomp |= m->body_gravcomp[i] != 0;
+  for (int j = 0; j < njnt; j++) { h.has_stiffness |= m->jnt_stiffness[j] != 0; h.has_limits |= m->jnt_limited[j] != 0; }
+  for (unsigned char c : b->controlled) h.has_controlled |= c != 0;
+
+  // offsets
+  const int header_words = (int)((sizeof(DModel) + 15) / 16 * 4);
+  int off = header_words;
+  auto place = [&](int n, bool real) {
+    if (real && rb == 8) off = (off + 1) & ~1;
+    const int o = off;
+    off += n * (real && rb == 8 ? 2 : 1);
+    return o;
+  };
+#define X(name, kind, count) h.o_##name = place((count), #kind[0] == 'F');
+  B2_MODEL_ARRAYS(X)
+#undef X
+  h.nwords = (off + 3) & ~3;
+  int ws = 0;
+#define X(name, count) h.w_##name = ws; ws += (count);
+  B2_WS_ARRAYS(X)
+#undef X
+  h.ws_slots = ws;
+
+  b->blob.assign(h.nwords, 0u);
+  std::memcpy(b->blob.data(), &h, sizeof(h));
+  // derived tables
+  std::vector<int> lastdof(nbody, -1);
+  for (int i = 1; i < nbody; i++) lastdof[i] = m->body_dofnum[i] > 0 ? m->body_dofadr[i] + m->body_dofnum[i] - 1 : lastdof[m->body_parentid[i]];
+  std::vector<int> ctl(nv, 0);
+  for (int i = 0; i < nv && i < (int)b->controlled.size(); i++) ctl[i] = b->controlled[i] ? 1 : 0;
+
+  auto put_int = [&](int o, const int* src, int n) { for (int i = 0; i < n; i++) b->blob[o + i] = (uint32_t)src[i]; };
+  auto put_real = [&](int o, const double* src, int n) {
+    if (rb == 8) std::memcpy(&b->blob[o], src, sizeof(double) * (size_t)n);
+    else for (int i = 0; i < n; i++) { float f = (float)src[i]; std::memcpy(&b->blob[o + i], &f, 4); }
+  };
+  auto fill = [&](const char* name, int o, int n, bool real) -> int {
+    if (n == 0) return 0;
+    if (!std::strcmp(name, "body_lastdof")) { put_int(o, lastdof.data(), n); return 0; }
+    if (!std::strcmp(name, "dof_controlled")) { put_int(o, ctl.data(), n); return 0; }
+    if (!std::strcmp(name, "odom_dof")) { put_int(o, b->odom_dof.data(), n); return 0; }
+    if (!std::strcmp(name, "odom_qpos")) { put_int(o, b->odom_qpos.data(), n); return 0; }
+    const void* p = nullptr;
+    int kind = 0;
+    const int cnt = b2::model_array(m, name, &p, &kind);
+    if (cnt < n || !p) return fail(std::string("pack_model: no source for '") + name + "'");
+    if (kind == 0) { if (!real) return fail(std::string("pack_model: kind mismatch for ") + name); put_real(o, (const double*)p, n); }
+    else if (kind == 1) { if (real) return fail(std::string("pack_model: kind mismatch for ") + name); put_int(o, (const int*)p, n); }
+    else if (kind == 2) { const unsigned char* s = (const unsigned char*)p; for (int i = 0; i < n; i++) b->blob[o + i] = s[i]; }
+    else return fail(std::string("pack_model: unsupported kind for ") + name);
+    return 0;
+  };
+#define X(name, kind, count) if (fill(#name, h.o_##name, (count), #kind[0] == 'F') < 0) return -1;
+  B2_MODEL_ARRAYS(X)
+#undef X
+  (void)neq; (void)npair; (void)nodom; (void)ngeom;
+  return 0;
+}
+
+int upload_model(b2_batch* b) {
+  if (pack_model(b) < 0) return -1;
+  if (!b->blob_dev) {
+    CK(cudaMalloc(&b->blob_dev, b->blob.size() * 4 + 64));
+  }
+  CK(cudaMemcpyAsync(b->blob_dev, b->blob.data(), b->blob.size() * 4, cudaMemcpyHostToDevice, b->stream));
+  CK(cudaStreamSynchronize(b->stream));
+  return 0;
+}
+
+int alloc_field(b2_batch* b, const char* name, long long count, int kind, void** out) {
+  const size_t esz = kind == 1 ? 4 : (size_t)b->prec;
+  const size_t bytes = std::max<size_t>(16, (size_t)count * b->nenvp * esz);
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) return fail(std::string("cudaMalloc(") + name + ", " + std::to_string(bytes) + " B): " + cudaGetErrorString(e));
+  CK(cudaMemsetAsync(p, 0, bytes, b->stream));
+  b->allocs.push_back(p);
+  Field f;
+  f.ptr = p; f.count = (int)count; f.kind = kind;
+  b->fields[name] = f;
+  if (out) *out = p;
+  return 0;
+}
+
+template <typename T>
+KArgs<T> make_args(b2_batch* b, int flags) {
+  KArgs<T> a;
+  std::memset(&a, 0, sizeof(a));
+  a.model = b->blob_dev;
+  a.nenv = b->nenv; a.nenvp = b->nenvp; a.flags = flags; a.ws_block = b->smooth_block; a.h = (T)b->h;
+  auto R = [&](const char* n) { auto it = b->fields.find(n); return it == b->fields.end() ? (T*)nullptr : (T*)it->second.ptr; };
+  auto I = [&](const char* n) { auto it = b->fields.find(n); return it == b->fields.end() ? (int*)nullptr : (int*)it->second.ptr; };
+  a.qpos = R("qpos"); a.qvel = R("qvel"); a.qacc = R("qacc"); a.qacc_warmstart = R("qacc_warmstart");
+  a.qfrc_applied = R("qfrc_applied"); a.xfrc_applied = R("xfrc_applied"); a.mocap_pos = R("mocap_pos"); a.mocap_quat = R("mocap_quat");
+  a.ddq = R("ddq"); a.dq = R("dq"); a.odom_vels = R("odom_vels"); a.time = R("time");
+  a.qfrc_bias = R("qfrc_bias"); a.qfrc_inverse = R("qfrc_inverse"); a.xpos = R("xpos"); a.xquat = R("xquat");
+  a.xmat = R("xmat"); a.geom_xpos = R("geom_xpos"); a.geom_xmat = R("geom_xmat"); a.subtree_com = R("subtree_com");
+  a.cdof = R("cdof"); a.qM = R("qM"); a.qLD = R("qLD"); a.qLDiagInv = R("qLDiagInv"); a.qfrc_passive = R("qfrc_passive");
+  a.qfrc_smooth = R("qfrc_smooth"); a.qacc_smooth = R("qacc_smooth"); a.qfrc_constraint = R("qfrc_constraint");
+  a.ws = R("_ws");
+  a.con = R("contact"); a.coni = I("contact_int"); a.ncon = I("ncon"); a.nefc = I("nefc"); a.efc_type = I("efc_type");
+  a.efc_id = I("efc_id"); a.efc_J = R("efc_J"); a.efc_pos = R("efc_pos"); a.efc_margin = R("efc_margin");
+  a.efc_frictionloss = R("efc_frictionloss"); a.efc_diagApprox = R("efc_diagApprox"); a.efc_R = R("efc_R"); a.efc_D = R("efc_D");
+  a.efc_KBI = R("efc_KBI"); a.efc_vel = R("efc_vel"); a.efc_aref = R("efc_aref"); a.efc_b = R("efc_b"); a.efc_force = R("efc_force");
+  a.efc_MiJT = R("efc_MiJT"); a.efc_AR = R("efc_AR"); a.solver_iter = I("solver_iter"); a.status = I("status");
+  return a;
+}
+
+template <typename T, int BLOCK>
+int launch_smooth(b2_batch* b, const KArgs<T>& a, int grid) {
+  static bool attr_set[8] = {false};
+  int dev = b->device & 7;
+  if (!attr_set[dev]) {
+    CK(cudaFuncSetAttribute(k_smooth<T, BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set[dev] = true;
+  }
+  k_smooth<T, BLOCK><<<grid, BLOCK, b->smooth_smem, b->stream>>>(a);
+  b->launches++;
+  return 0;
+}
+
+template <typename T>
+int run_tick(b2_batch* b, int flags) {
+  int kf = 0;
+  if (flags & B2_TICK_CONTROLLER) kf |= B2F_CONTROLLER;
+  if (flags & B2_TICK_INVERSE) kf |= B2F_INVERSE;
+  if (flags & B2_TICK_INTEGRATE) kf |= B2F_INTEGRATE;
+  if ((flags & B2_TICK_ODOM) && b->hdr.nodom > 0) kf |= B2F_ODOM;
+  if (b->fused) kf |= B2F_FUSED;
+  if (b->ws_global) kf |= B2F_WS_GLOBAL;
+  if (b->tick_flags & (1 << 30)) kf |= B2F_XFRC;  // set once xfrc_applied has been written
+  if (b->export_stages) kf |= B2F_EXPORT;
+  KArgs<T> a = make_args<T>(b, kf);
+  const int ntiles = b->nenvp / b->smooth_block;
+  const int per_sm = std::max<size_t>(1, (227 * 1024) / std::max<size_t>(1, b->smooth_smem));
+  const int grid = std::max(1, std::min(ntiles, b->nsm * per_sm));
+  int rc;
+  switch (b->smooth_block) {
+    case 128: rc = launch_smooth<T, 128>(b, a, grid); break;
+    case 64: rc = launch_smooth<T, 64>(b, a, grid); break;
+    default: rc = launch_smooth<T, 32>(b, a, grid); break;
+  }
+  if (rc < 0) return rc;
+  if (!b->fused) {
+    constexpr int BL = 128;
+    const int nt = b->nenvp / BL;
+    const int g2 = std::max(1, std::min(nt, b->nsm * 4));
+    const size_t sm = b->blob_smem;
+    k_collide<T, BL><<<g2, BL, sm, b->stream>>>(a);
+    k_make_constraint<T, BL><<<g2, BL, sm, b->stream>>>(a);
+    b->launches += 2;
+    if (!(flags & B2_TICK_NOSOLVE)) {
+      k_project<T, BL><<<g2, BL, sm, b->stream>>>(a);
+      k_pgs<T, BL><<<g2, BL, sm, b->stream>>>(a);
+      k_integrate<T, BL><<<g2, BL, sm, b->stream>>>(a);
+      b->launches += 3;
+    }
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int tick_dispatch(b2_batch* b, int flags) {
+  CK(cudaSetDevice(b->device));
+  return b->prec == 8 ? run_tick<double>(b, flags) : run_tick<float>(b, flags);
+}
+
+// ---- host <-> device field transfer with layout / precision conversion ----
+template <typename H, typename D>
+__global__ void k_scatter_field(D* dev, const H* host, int count, int nenvp, int env_lo, int n, int layout) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)count * n) return;
+  const int i = (int)(idx / n), e = (int)(idx % n);  // consecutive threads -> consecutive environments
+  const H v = layout == B2_NATIVE ? host[(long long)i * n + e] : host[(long long)e * count + i];
+  dev[(long long)i * nenvp + env_lo + e] = (D)v;
+}
+template <typename H, typename D>
+__global__ void k_gather_field(const D* dev, H* host, int count, int nenvp, int env_lo, int n, int layout) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)count * n) return;
+  const int i = (int)(idx / n), e = (int)(idx % n);
+  const H v = (H)dev[(long long)i * nenvp + env_lo + e];
+  if (layout == B2_NATIVE) host[(long long)i * n + e] = v; else host[(long long)e * count + i] = v;
+}
+
+int ensure_stage(b2_batch* b, size_t bytes) {
+  if (bytes <= b->stage_bytes) return 0;
+  if (b->stage_dev) cudaFree(b->stage_dev);
+  b->stage_dev = nullptr;
+  b->stage_bytes = 0;
+  CK(cudaMalloc(&b->stage_dev, bytes));
+  b->stage_bytes = bytes;
+  return 0;
+}
+
+template <typename H>
+int set_field(b2_batch* b, const char* name, const H* host, int lo, int hi, int layout) {
+  if (!b) return fail("null batch");
+  CK(cudaSetDevice(b->device));
+  auto it = b->fields.find(name);
+  if (it == b->fields.end()) return fail(std::string("unknown field '") + name + "'");
+  const Field& f = it->second;
+  if (lo < 0 || hi > b->nenv || lo >= hi) return fail("bad environment range");
+  if (f.kind != 0) return fail(std::string("field '") + name + "' is an int field");
+  const int n = hi - lo;
+  const size_t bytes = (size_t)f.count * n * sizeof(H);
+  if (bytes == 0) return f.count;
+  if (ensure_stage(b, bytes) < 0) return -1;
+  CK(cudaMemcpyAsync(b->stage_dev, host, bytes, cudaMemcpyHostToDevice, b->stream));
+  const long long tot = (long long)f.count * n;
+  const int th = 256, bl = (int)((tot + th - 1) / th);
+  if (b->prec == 8) k_scatter_field<H, double><<<bl, th, 0, b->stream>>>((double*)f.ptr, (const H*)b->stage_dev, f.count, b->nenvp, lo, n, layout);
+  else k_scatter_field<H, float><<<bl, th, 0, b->stream>>>((float*)f.ptr, (const H*)b->stage_dev, f.count, b->nenvp, lo, n, layout);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(b->stream));
+  if (!std::strcmp(name, "xfrc_applied")) b->tick_flags |= (1 << 30);
+  return f.count;
+}
+
+template <typename H>
+int get_field(b2_batch* b, const char* name, H* host, int lo, int hi, int layout, int want_kind) {
+  if (!b) return fail("null batch");
+  CK(cudaSetDevice(b->device));
+  auto it = b->fields.find(name);
+  if (it == b->fields.end()) return fail(std::string("unknown field '") + name + "'");
+  const Field& f = it->second;
+  if (lo < 0 || hi > b->nenv || lo >= hi) return fail("bad environment range");
+  if (f.kind != want_kind) return fail(std::string("field '") + name + "' has a different element kind");
+  const int n = hi - lo;
+  const size_t bytes = (size_t)f.count * n * sizeof(H);
+  if (bytes == 0) return f.count;
+  if (ensure_stage(b, bytes) < 0) return -1;
+  const long long tot = (long long)f.count * n;
+  const int th = 256, bl = (int)((tot + th - 1) / th);
+  if (f.kind == 1) k_gather_field<H, int><<<bl, th, 0, b->stream>>>((const int*)f.ptr, (H*)b->stage_dev, f.count, b->nenvp, lo, n, layout);
+  else if (b->prec == 8) k_gather_field<H, double><<<bl, th, 0, b->stream>>>((const double*)f.ptr, (H*)b->stage_dev, f.count, b->nenvp, lo, n, layout);
+  else k_gather_field<H, float><<<bl, th, 0, b->stream>>>((const float*)f.ptr, (H*)b->stage_dev, f.count, b->nenvp, lo, n, layout);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(host, b->stage_dev, bytes, cudaMemcpyDeviceToHost, b->stream));
+  CK(cudaStreamSynchronize(b->stream));
+  return f.count;
+}
+
+template <typename D>
+__global__ void k_reset(D* qpos, D* qvel, D* qacc, D* qws, D* qapp, D* time, const uint32_t* model, int nenvp, int lo, int hi) {
+  const DModel* h = reinterpret_cast<const DModel*>(model);
+  const int e = lo + blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= hi) return;
+  const D* q0 = reinterpret_cast<const D*>(model + h->o_qpos0);
+  for (int i = 0; i < h->nq; i++) qpos[(long long)i * nenvp + e] = q0[i];
+  for (int i = 0; i < h->nv; i++) {
+    qvel[(long long)i * nenvp + e] = 0; qacc[(long long)i * nenvp + e] = 0; qws[(long long)i * nenvp + e] = 0; qapp[(long long)i * nenvp + e] = 0;
+  }
+  time[e] = 0;
+}
+
+// MjHWInterface::write (src/mujoco_sim/mj_hw_interface.cpp:73-91) for every environment
+template <typename D>
+__global__ void k_hw_write(D* ddq, D* dq, const float* vel_cmd, const float* eff_cmd, const int* dadr, const int* ctl, int nhw,
+                           int nenv, int nenvp) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)nhw * nenv) return;
+  const int j = (int)(idx / nenv), e = (int)(idx % nenv);
+  if (!ctl[j]) return;
+  const float v = vel_cmd[idx];
+  const int d = dadr[j];
+  if (fabsf(v) > 1e-15f) dq[(long long)d * nenvp + e] = (D)v;
+  else ddq[(long long)d * nenvp + e] = (D)eff_cmd[idx];
+}
+// MjHWInterface::read gathers (src/mujoco_sim/mj_hw_interface.cpp:62-70)
+template <typename D>
+__global__ void k_hw_read(const D* qpos, const D* qvel, const D* qfrc_inverse, float* pos, float* vel, float* eff, const int* qadr,
+                          const int* dadr, int nhw, int nenv, int nenvp) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)nhw * nenv) return;
+  const int j = (int)(idx / nenv), e = (int)(idx % nenv);
+  pos[idx] = (float)qpos[(long long)qadr[j] * nenvp + e];
+  vel[idx] = (float)qvel[(long long)dadr[j] * nenvp + e];
+  eff[idx] = (float)qfrc_inverse[(long long)dadr[j] * nenvp + e];
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* b2_last_error(void) { return g_err.c_str(); }
+
+int b2_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+b2_batch* b2_create(const mjModel* m, int nenv, int device, int precision) {
+  if (!m) { fail("b2_create: null model"); return nullptr; }
+  if (nenv < 1) { fail("b2_create: nenv must be >= 1"); return nullptr; }
+  const bool export_stages = (precision & B2_EXPORT_STAGES) != 0;
+  precision &= ~B2_EXPORT_STAGES;
+  if (precision != B2_F32 && precision != B2_F64) { fail("b2_create: precision must be B2_F32 or B2_F64"); return nullptr; }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    fail(std::string("b2_create: no usable CUDA device (") + cudaGetErrorString(e) + "); this engine has no CPU fallback");
+    cudaGetLastError();
+    return nullptr;
+  }
+  if (device < 0 || device >= ndev) { fail("b2_create: bad device index"); return nullptr; }
+  if (cudaSetDevice(device) != cudaSuccess) { fail("b2_create: cudaSetDevice failed"); return nullptr; }
+  auto* b = new b2_batch();
+  b->m = m; b->nenv = nenv; b->nenvp = (nenv + 127) / 128 * 128; b->device = device; b->prec = precision;
+  b->h = m->opt.timestep;
+  b->opt_iterations = m->opt.iterations; b->opt_tolerance = m->opt.tolerance; b->opt_disableflags = m->opt.disableflags;
+  b->controlled.assign(m->nv, 0);
+  b->export_stages = export_stages;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) b->nsm = prop.multiProcessorCount;
+  auto bail = [&](const char* what) -> b2_batch* {
+    if (g_err.empty()) fail(what);
+    b2_destroy(b);
+    return nullptr;
+  };
+  if (cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess) return bail("cudaStreamCreate failed");
+  if (upload_model(b) < 0) return bail("upload_model failed");
+
+  const int nq = m->nq, nv = m->nv, nb = m->nbody, ng = m->ngeom, nM = m->nM;
+  // does the model have any constraint source?  If not the smooth kernel integrates by itself (one launch per tick).
+  bool any_pair = false;
+  for (int p = 0; p < m->npair; p++)
+    any_pair |= pair_supported(m->geom_type[m->pair_geom1[p]], m->geom_type[m->pair_geom2[p]]);
+  bool any_lim = false, any_fl = false;
+  for (int j = 0; j < m->njnt; j++) any_lim |= m->jnt_limited[j] != 0;
+  for (int i = 0; i < nv; i++) any_fl |= m->dof_frictionloss[i] > 0;
+  b->fused = (m->opt.disableflags & mjDSBL_CONSTRAINT) || !(any_pair || any_lim || any_fl || m->neq > 0);
+
+  struct Spec { const char* name; long long count; int kind; };
+  std::vector<Spec> specs = {
+      {"qpos", nq, 0}, {"qvel", nv, 0}, {"qacc", nv, 0}, {"qacc_warmstart", nv, 0}, {"qfrc_applied", nv, 0},
+      {"xfrc_applied", 6 * nb, 0}, {"mocap_pos", 3 * std::max(1, m->nmocap), 0}, {"mocap_quat", 4 * std::max(1, m->nmocap), 0},
+      {"ddq", nv, 0}, {"dq", nv, 0}, {"odom_vels", 6, 0}, {"time", 1, 0}, {"qfrc_bias", nv, 0}, {"qfrc_inverse", nv, 0},
+      {"xpos", 3 * nb, 0}, {"xquat", 4 * nb, 0}, {"status", 1, 1}, {"solver_iter", 1, 1}, {"ncon", 1, 1}, {"nefc", 1, 1}};
+  if (!b->fused || b->export_stages) {
+    std::vector<Spec> more = {
+        {"xmat", 9 * nb, 0}, {"geom_xpos", 3 * std::max(1, ng), 0}, {"geom_xmat", 9 * std::max(1, ng), 0}, {"subtree_com", 3 * nb, 0},
+        {"cdof", 6 * nv, 0}, {"qM", nM, 0}, {"qLD", nM, 0}, {"qLDiagInv", nv, 0}, {"qfrc_passive", nv, 0}, {"qfrc_smooth", nv, 0},
+        {"qacc_smooth", nv, 0}, {"qfrc_constraint", nv, 0}};
+    specs.insert(specs.end(), more.begin(), more.end());
+  }
+  if (!b->fused) {
+    const long long njmax = b->hdr.njmax, ncm = b->hdr.nconmax;
+    std::vector<Spec> more = {
+        {"contact", CF_NFLOAT * ncm, 0}, {"contact_int", CI_NINT * ncm, 1},
+        {"efc_type", njmax, 1}, {"efc_id", njmax, 1}, {"efc_J", njmax * nv, 0}, {"efc_pos", njmax, 0}, {"efc_margin", njmax, 0},
+        {"efc_frictionloss", njmax, 0}, {"efc_diagApprox", njmax, 0}, {"efc_R", njmax, 0}, {"efc_D", njmax, 0}, {"efc_KBI", 3 * njmax, 0},
+        {"efc_vel", njmax, 0}, {"efc_aref", njmax, 0}, {"efc_b", njmax, 0}, {"efc_force", njmax, 0}, {"efc_MiJT", njmax * nv, 0},
+        {"efc_AR", njmax * njmax, 0}};
+    specs.insert(specs.end(), more.begin(), more.end());
+  }
+  for (auto& s : specs)
+    if (alloc_field(b, s.name, s.count, s.kind, nullptr) < 0) return bail("alloc failed");
+
+  // shared-memory budget of the smooth kernel: 16 B barrier + model blob + workspace[ws_slots][BLOCK]
+  b->blob_smem = 16 + (size_t)b->hdr.nwords * 4;
+  const size_t budget = 200 * 1024;
+  int block = 0;
+  for (int cand : {128, 64, 32}) {
+    const size_t need = b->blob_smem + (size_t)b->hdr.ws_slots * cand * precision;
+    if (need > budget) continue;
+    if (!block) block = cand;
+    // prefer a smaller CTA when the batch cannot fill the SMs with the larger one
+    if (b->nenvp / block < b->nsm && cand < block) block = cand;
+  }
+  if (block) {
+    b->smooth_block = block;
+    b->smooth_smem = b->blob_smem + (size_t)b->hdr.ws_slots * block * precision;
+    b->ws_global = false;
+  } else {
+    b->smooth_block = 128;
+    b->smooth_smem = b->blob_smem;
+    b->ws_global = true;
+    if (alloc_field(b, "_ws", b->hdr.ws_slots, 0, nullptr) < 0) return bail("alloc failed");
+  }
+  if (b->blob_smem > 48 * 1024) {
+    // the constraint-pipeline kernels stage the same blob
+    bool ok = true;
+    if (precision == 8) {
+      ok &= cudaFuncSetAttribute(k_collide<double, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->blob_smem) == cudaSuccess;
+      ok &= cudaFuncSetAttribute(k_make_constraint<double, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->blob_smem) == cudaSuccess;
+      ok &= cudaFuncSetAttribute(k_project<double, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->blob_smem) == cudaSuccess;
+      ok &= cudaFuncSetAttribute(k_pgs<double, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->blob_smem) == cudaSuccess;
+      ok &= cudaFuncSetAttribute(k_integrate<double, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->blob_smem) == cudaSuccess;
+    } else {
+      ok &= cudaFuncSetAttribute(k_collide<float, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->blob_smem) == cudaSuccess;
+      ok &= cudaFuncSetAttribute(k_make_constraint<float, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->blob_smem) == cudaSuccess;
+      ok &= cudaFuncSetAttribute(k_project<float, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->blob_smem) == cudaSuccess;
+      ok &= cudaFuncSetAttribute(k_pgs<float, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->blob_smem) == cudaSuccess;
+      ok &= cudaFuncSetAttribute(k_integrate<float, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->blob_smem) == cudaSuccess;
+    }
+    if (!ok) return bail("cudaFuncSetAttribute failed");
+  }
+  if (b2_reset(b, 0, nenv) < 0) return bail("reset failed");
+  // padded environments also start from qpos0 so that they stay finite
+  if (b->nenvp > nenv) {
+    const int th = 128, n = b->nenvp - nenv;
+    if (precision == 8)
+      k_reset<double><<<(n + th - 1) / th, th, 0, b->stream>>>((double*)b->fields["qpos"].ptr, (double*)b->fields["qvel"].ptr, (double*)b->fields["qacc"].ptr,
+          (double*)b->fields["qacc_warmstart"].ptr, (double*)b->fields["qfrc_applied"].ptr, (double*)b->fields["time"].ptr, b->blob_dev, b->nenvp, nenv, b->nenvp);
+    else
+      k_reset<float><<<(n + th - 1) / th, th, 0, b->stream>>>((float*)b->fields["qpos"].ptr, (float*)b->fields["qvel"].ptr, (float*)b->fields["qacc"].ptr,
+          (float*)b->fields["qacc_warmstart"].ptr, (float*)b->fields["qfrc_applied"].ptr, (float*)b->fields["time"].ptr, b->blob_dev, b->nenvp, nenv, b->nenvp);
+  }
+  // mocap bodies start at their authored pose
+  if (m->nmocap > 0) {
+    std::vector<double> mp(3 * (size_t)m->nmocap), mq(4 * (size_t)m->nmocap);
+    for (int i = 0; i < m->nbody; i++) {
+      const int id = m->body_mocapid[i];
+      if (id < 0) continue;
+      for (int k = 0; k < 3; k++) mp[3 * id + k] = m->body_pos[3 * i + k];
+      for (int k = 0; k < 4; k++) mq[4 * id + k] = m->body_quat[4 * i + k];
+    }
+    std::vector<double> hp((size_t)nenv * mp.size()), hq((size_t)nenv * mq.size());
+    for (int e2 = 0; e2 < nenv; e2++) {
+      std::copy(mp.begin(), mp.end(), hp.begin() + (size_t)e2 * mp.size());
+      std::copy(mq.begin(), mq.end(), hq.begin() + (size_t)e2 * mq.size());
+    }
+    if (set_field<double>(b, "mocap_pos", hp.data(), 0, nenv, B2_ENV_MAJOR) < 0) return bail("mocap init failed");
+    if (set_field<double>(b, "mocap_quat", hq.data(), 0, nenv, B2_ENV_MAJOR) < 0) return bail("mocap init failed");
+  }
+  if (cudaStreamSynchronize(b->stream) != cudaSuccess) return bail("stream sync failed");
+  b->tick_flags = B2_TICK_INTEGRATE;
+  return b;
+}
+
+void b2_destroy(b2_batch* b) {
+  if (!b) return;
+  cudaSetDevice(b->device);
+  if (b->stream) cudaStreamSynchronize(b->stream);
+  for (void* p : b->allocs) cudaFree(p);
+  if (b->blob_dev) cudaFree(b->blob_dev);
+  if (b->stage_dev) cudaFree(b->stage_dev);
+  if (b->hw_qadr) cudaFree(b->hw_qadr);
+  if (b->hw_dadr) cudaFree(b->hw_dadr);
+  if (b->hw_ctl) cudaFree(b->hw_ctl);
+  if (b->hw_buf) cudaFree(b->hw_buf);
+  if (b->stream) cudaStreamDestroy(b->stream);
+  delete b;
+}
+
+int b2_nenv(const b2_batch* b) { return b ? b->nenv : -1; }
+int b2_nenv_padded(const b2_batch* b) { return b ? b->nenvp : -1; }
+int b2_precision(const b2_batch* b) { return b ? b->prec : -1; }
+
+int b2_set_controlled(b2_batch* b, const unsigned char* mask) {
+  if (!b || !mask) return fail("b2_set_controlled: null argument");
+  CK(cudaSetDevice(b->device));
+  b->controlled.assign(mask, mask + b->m->nv);
+  if (upload_model(b) < 0) return -1;
+  if (b->nhw > 0) {  // refresh the per-joint controlled flags
+    std::vector<int> dadr(b->nhw), ctl(b->nhw);
+    CK(cudaMemcpy(dadr.data(), b->hw_dadr, sizeof(int) * b->nhw, cudaMemcpyDeviceToHost));
+    for (int j = 0; j < b->nhw; j++) ctl[j] = b->controlled[dadr[j]] ? 1 : 0;
+    CK(cudaMemcpy(b->hw_ctl, ctl.data(), sizeof(int) * b->nhw, cudaMemcpyHostToDevice));
+  }
+  return 0;
+}
+
+int b2_set_odom(b2_batch* b, int nrobot, const int* dof, const int* qposadr) {
+  if (!b || nrobot < 0 || (nrobot > 0 && (!dof || !qposadr))) return fail("b2_set_odom: bad argument");
+  CK(cudaSetDevice(b->device));
+  b->odom_dof.assign(dof, dof + 6 * nrobot);
+  b->odom_qpos.assign(qposadr, qposadr + 3 * nrobot);
+  // the blob grows: reallocate it
+  if (b->blob_dev) { cudaFree(b->blob_dev); b->blob_dev = nullptr; }
+  if (upload_model(b) < 0) return -1;
+  // odom_vels holds 6 numbers per robot
+  auto it = b->fields.find("odom_vels");
+  if (it != b->fields.end() && it->second.count < 6 * nrobot) {
+    if (alloc_field(b, "odom_vels", 6 * nrobot, 0, nullptr) < 0) return -1;
+  }
+  b->blob_smem = 16 + (size_t)b->hdr.nwords * 4;
+  if (!b->ws_global) b->smooth_smem = b->blob_smem + (size_t)b->hdr.ws_slots * b->smooth_block * b->prec;
+  else b->smooth_smem = b->blob_smem;
+  return 0;
+}
+
+int b2_set_timestep(b2_batch* b, double h) {
+  if (!b || !(h > 0)) return fail("b2_set_timestep: bad argument");
+  b->h = h;
+  return 0;
+}
+
+int b2_set_option(b2_batch* b, const char* name, double value) {
+  if (!b || !name) return fail("b2_set_option: null argument");
+  CK(cudaSetDevice(b->device));
+  if (!std::strcmp(name, "iterations")) b->opt_iterations = (int)value;
+  else if (!std::strcmp(name, "tolerance")) b->opt_tolerance = value;
+  else if (!std::strcmp(name, "disableflags")) b->opt_disableflags = (int)value;
+  else return fail(std::string("b2_set_option: unknown option '") + name + "'");
+  return upload_model(b);
+}
+
+int b2_field_size(const b2_batch* b, const char* field) {
+  if (!b || !field) return fail("b2_field_size: null argument");
+  auto it = b->fields.find(field);
+  if (it == b->fields.end()) return fail(std::string("unknown field '") + field + "'");
+  return it->second.count;
+}
+int b2_set_field_f32(b2_batch* b, const char* f, const float* h, int lo, int hi, int layout) { return set_field<float>(b, f, h, lo, hi, layout); }
+int b2_set_field_f64(b2_batch* b, const char* f, const double* h, int lo, int hi, int layout) { return set_field<double>(b, f, h, lo, hi, layout); }
+int b2_get_field_f32(b2_batch* b, const char* f, float* h, int lo, int hi, int layout) { return get_field<float>(b, f, h, lo, hi, layout, 0); }
+int b2_get_field_f64(b2_batch* b, const char* f, double* h, int lo, int hi, int layout) { return get_field<double>(b, f, h, lo, hi, layout, 0); }
+int b2_get_field_i32(b2_batch* b, const char* f, int* h, int lo, int hi, int layout) { return get_field<int>(b, f, h, lo, hi, layout, 1); }
+
+void* b2_device_ptr(b2_batch* b, const char* field) {
+  if (!b || !field) { fail("b2_device_ptr: null argument"); return nullptr; }
+  auto it = b->fields.find(field);
+  if (it == b->fields.end()) { fail(std::string("unknown field '") + field + "'"); return nullptr; }
+  return it->second.ptr;
+}
+
+int b2_reset(b2_batch* b, int lo, int hi) {
+  if (!b || lo < 0 || hi > b->nenv || lo >= hi) return fail("b2_reset: bad range");
+  CK(cudaSetDevice(b->device));
+  const int th = 128, n = hi - lo;
+  auto P = [&](const char* nm) { return b->fields[nm].ptr; };
+  if (b->prec == 8)
+    k_reset<double><<<(n + th - 1) / th, th, 0, b->stream>>>((double*)P("qpos"), (double*)P("qvel"), (double*)P("qacc"), (double*)P("qacc_warmstart"),
+                                                            (double*)P("qfrc_applied"), (double*)P("time"), b->blob_dev, b->nenvp, lo, hi);
+  else
+    k_reset<float><<<(n + th - 1) / th, th, 0, b->stream>>>((float*)P("qpos"), (float*)P("qvel"), (float*)P("qacc"), (float*)P("qacc_warmstart"),
+                                                           (float*)P("qfrc_applied"), (float*)P("time"), b->blob_dev, b->nenvp, lo, hi);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int b2_tick(b2_batch* b, int flags) {
+  if (!b) return fail("b2_tick: null batch");
+  return tick_dispatch(b, flags);
+}
+int b2_set_tick_flags(b2_batch* b, int flags) {
+  if (!b) return fail("null batch");
+  b->tick_flags = (b->tick_flags & (1 << 30)) | (flags & ~(1 << 30));
+  return 0;
+}
+int b2_step(b2_batch* b, int nsteps) {
+  if (!b) return fail("b2_step: null batch");
+  for (int s = 0; s < nsteps; s++)
+    if (tick_dispatch(b, (b->tick_flags & ~(1 << 30)) | B2_TICK_INTEGRATE) < 0) return -1;
+  return 0;
+}
+int b2_forward(b2_batch* b) {
+  if (!b) return fail("b2_forward: null batch");
+  return tick_dispatch(b, 0);
+}
+int b2_sync(b2_batch* b) {
+  if (!b) return fail("b2_sync: null batch");
+  CK(cudaSetDevice(b->device));
+  CK(cudaStreamSynchronize(b->stream));
+  return 0;
+}
+void* b2_stream(b2_batch* b) { return b ? (void*)b->stream : nullptr; }
+long long b2_launch_count(const b2_batch* b) { return b ? b->launches : -1; }
+
+int b2_set_hw_joints(b2_batch* b, int njoint, const int* jnt_ids) {
+  if (!b || njoint < 1 || !jnt_ids) return fail("b2_set_hw_joints: bad argument");
+  CK(cudaSetDevice(b->device));
+  std::vector<int> qadr(njoint), dadr(njoint), ctl(njoint);
+  for (int j = 0; j < njoint; j++) {
+    const int id = jnt_ids[j];
+    if (id < 0 || id >= b->m->njnt) return fail("b2_set_hw_joints: joint id out of range");
+    if (b->m->jnt_type[id] != mjJNT_HINGE && b->m->jnt_type[id] != mjJNT_SLIDE) return fail("b2_set_hw_joints: only scalar joints");
+    qadr[j] = b->m->jnt_qposadr[id];
+    dadr[j] = b->m->jnt_dofadr[id];
+    ctl[j] = b->controlled[dadr[j]] ? 1 : 0;
+  }
+  for (int** p : {&b->hw_qadr, &b->hw_dadr, &b->hw_ctl}) { if (*p) cudaFree(*p); *p = nullptr; }
+  if (b->hw_buf) { cudaFree(b->hw_buf); b->hw_buf = nullptr; }
+  CK(cudaMalloc(&b->hw_qadr, sizeof(int) * njoint));
+  CK(cudaMalloc(&b->hw_dadr, sizeof(int) * njoint));
+  CK(cudaMalloc(&b->hw_ctl, sizeof(int) * njoint));
+  CK(cudaMalloc(&b->hw_buf, sizeof(float) * 5 * (size_t)njoint * b->nenv));
+  CK(cudaMemcpy(b->hw_qadr, qadr.data(), sizeof(int) * njoint, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(b->hw_dadr, dadr.data(), sizeof(int) * njoint, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(b->hw_ctl, ctl.data(), sizeof(int) * njoint, cudaMemcpyHostToDevice));
+  b->nhw = njoint;
+  return 0;
+}
+
+static int hw_write_async(b2_batch* b, const float* vel, const float* eff) {
+  if (!b->nhw) return fail("b2_write_commands: call b2_set_hw_joints first");
+  const size_t n = (size_t)b->nhw * b->nenv;
+  float* dv = b->hw_buf;
+  float* de = b->hw_buf + n;
+  CK(cudaMemcpyAsync(dv, vel, n * 4, cudaMemcpyHostToDevice, b->stream));
+  CK(cudaMemcpyAsync(de, eff, n * 4, cudaMemcpyHostToDevice, b->stream));
+  const int th = 256, bl = (int)((n + th - 1) / th);
+  if (b->prec == 8) k_hw_write<double><<<bl, th, 0, b->stream>>>((double*)b->fields["ddq"].ptr, (double*)b->fields["dq"].ptr, dv, de, b->hw_dadr, b->hw_ctl, b->nhw, b->nenv, b->nenvp);
+  else k_hw_write<float><<<bl, th, 0, b->stream>>>((float*)b->fields["ddq"].ptr, (float*)b->fields["dq"].ptr, dv, de, b->hw_dadr, b->hw_ctl, b->nhw, b->nenv, b->nenvp);
+  b->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+static int hw_read_async(b2_batch* b, float* pos, float* vel, float* eff) {
+  if (!b->nhw) return fail("b2_read_joints: call b2_set_hw_joints first");
+  const size_t n = (size_t)b->nhw * b->nenv;
+  float *dp = b->hw_buf + 2 * n, *dv = b->hw_buf + 3 * n, *de = b->hw_buf + 4 * n;
+  const int th = 256, bl = (int)((n + th - 1) / th);
+  if (b->prec == 8) k_hw_read<double><<<bl, th, 0, b->stream>>>((const double*)b->fields["qpos"].ptr, (const double*)b->fields["qvel"].ptr, (const double*)b->fields["qfrc_inverse"].ptr, dp, dv, de, b->hw_qadr, b->hw_dadr, b->nhw, b->nenv, b->nenvp);
+  else k_hw_read<float><<<bl, th, 0, b->stream>>>((const float*)b->fields["qpos"].ptr, (const float*)b->fields["qvel"].ptr, (const float*)b->fields["qfrc_inverse"].ptr, dp, dv, de, b->hw_qadr, b->hw_dadr, b->nhw, b->nenv, b->nenvp);
+  b->launches++;
+  CK(cudaGetLastError());
+  if (pos) CK(cudaMemcpyAsync(pos, dp, n * 4, cudaMemcpyDeviceToHost, b->stream));
+  if (vel) CK(cudaMemcpyAsync(vel, dv, n * 4, cudaMemcpyDeviceToHost, b->stream));
+  if (eff) CK(cudaMemcpyAsync(eff, de, n * 4, cudaMemcpyDeviceToHost, b->stream));
+  return 0;
+}
+
+int b2_write_commands(b2_batch* b, const float* vel, const float* eff) {
+  if (!b || !vel || !eff) return fail("b2_write_commands: null argument");
+  CK(cudaSetDevice(b->device));
+  if (hw_write_async(b, vel, eff) < 0) return -1;
+  CK(cudaStreamSynchronize(b->stream));
+  return 0;
+}
+int b2_read_joints(b2_batch* b, float* pos, float* vel, float* eff) {
+  if (!b) return fail("b2_read_joints: null batch");
+  CK(cudaSetDevice(b->device));
+  if (hw_read_async(b, pos, vel, eff) < 0) return -1;
+  CK(cudaStreamSynchronize(b->stream));
+  return 0;
+}
+
+// One control tick as the reference's loop body sees it (src/mj_main.cpp:82-112), with host buffers:
+// write(commands of the previous update) -> step1 + controller -> read (mj_inverse) -> step2 -> odom; joint states out.
+// Note on order: the reference reads the joint state between mj_step1 and mj_step2 (pre-integration qpos/qvel,
+// qfrc_inverse of this tick); the gather here returns qfrc_inverse of this tick and the post-integration qpos/qvel,
+// i.e. exactly what read() of the NEXT tick would return for positions and velocities.
+int b2_tick_host(b2_batch* b, const float* vel, const float* eff, float* pos, float* velo, float* effo) {
+  if (!b || !vel || !eff) return fail("b2_tick_host: null argument");
+  CK(cudaSetDevice(b->device));
+  if (hw_write_async(b, vel, eff) < 0) return -1;
+  if (tick_dispatch(b, (b->tick_flags & ~(1 << 30)) | B2_TICK_INTEGRATE | B2_TICK_CONTROLLER | B2_TICK_INVERSE) < 0) return -1;
+  if (hw_read_async(b, pos, velo, effo) < 0) return -1;
+  CK(cudaStreamSynchronize(b->stream));
+  return 0;
+}
+
+int b2_mirror_env(b2_batch* b, int env, mjData* d) {
+  if (!b || !d || env < 0 || env >= b->nenv) return fail("b2_mirror_env: bad argument");
+  const mjModel* m = b->m;
+  auto G = [&](const char* name, double* dst, int n) -> int {
+    if (n <= 0 || !dst) return 0;
+    auto it = b->fields.find(name);
+    if (it == b->fields.end()) return 0;
+    if (it->second.count < n) return fail(std::string("b2_mirror_env: size mismatch for ") + name);
+    std::vector<double> tmp(it->second.count);
+    if (get_field<double>(b, name, tmp.data(), env, env + 1, B2_ENV_MAJOR, 0) < 0) return -1;
+    std::copy(tmp.begin(), tmp.begin() + n, dst);
+    return 0;
+  };
+  const int nq = m->nq, nv = m->nv, nb = m->nbody, ng = m->ngeom;
+  if (G("qpos", d->qpos, nq) < 0 || G("qvel", d->qvel, nv) < 0 || G("qacc", d->qacc, nv) < 0 ||
+      G("qacc_warmstart", d->qacc_warmstart, nv) < 0 || G("qfrc_applied", d->qfrc_applied, nv) < 0 ||
+      G("qfrc_bias", d->qfrc_bias, nv) < 0 || G("qfrc_inverse", d->qfrc_inverse, nv) < 0 || G("xpos", d->xpos, 3 * nb) < 0 ||
+      G("xquat", d->xquat, 4 * nb) < 0 || G("xmat", d->xmat, 9 * nb) < 0 || G("geom_xpos", d->geom_xpos, 3 * ng) < 0 ||
+      G("geom_xmat", d->geom_xmat, 9 * ng) < 0 || G("qM", d->qM, m->nM) < 0 || G("qfrc_passive", d->qfrc_passive, nv) < 0 ||
+      G("qfrc_constraint", d->qfrc_constraint, nv) < 0 || G("qacc_smooth", d->qacc_smooth, nv) < 0 ||
+      G("qfrc_smooth", d->qfrc_smooth, nv) < 0 || G("subtree_com", d->subtree_com, 3 * nb) < 0 || G("cdof", d->cdof, 6 * nv) < 0)
+    return -1;
+  double t = 0;
+  if (get_field<double>(b, "time", &t, env, env + 1, B2_ENV_MAJOR, 0) < 0) return -1;
+  d->time = t;
+  int v = 0;
+  if (get_field<int>(b, "ncon", &v, env, env + 1, B2_ENV_MAJOR, 1) < 0) return -1;
+  d->ncon = b->fused ? 0 : v;
+  if (get_field<int>(b, "nefc", &v, env, env + 1, B2_ENV_MAJOR, 1) < 0) return -1;
+  d->nefc = b->fused ? 0 : v;
+  if (get_field<int>(b, "solver_iter", &v, env, env + 1, B2_ENV_MAJOR, 1) < 0) return -1;
+  d->solver_iter = v;
+  if (!b->fused && d->ncon > 0) {
+    std::vector<double> cf((size_t)CF_NFLOAT * b->hdr.nconmax);
+    std::vector<int> ci((size_t)CI_NINT * b->hdr.nconmax);
+    if (get_field<double>(b, "contact", cf.data(), env, env + 1, B2_ENV_MAJOR, 0) < 0) return -1;
+    if (get_field<int>(b, "contact_int", ci.data(), env, env + 1, B2_ENV_MAJOR, 1) < 0) return -1;
+    const int ncm = b->hdr.nconmax;
+    for (int c = 0; c < d->ncon && c < m->nconmax; c++) {
+      mjContact& k = d->contact[c];
+      k.dist = cf[(size_t)CF_DIST * ncm + c];
+      for (int i = 0; i < 3; i++) k.pos[i] = cf[(size_t)(CF_POS + i) * ncm + c];
+      for (int i = 0; i < 9; i++) k.frame[i] = cf[(size_t)(CF_FRAME + i) * ncm + c];
+      k.includemargin = cf[(size_t)CF_INCLUDEMARGIN * ncm + c];
+      for (int i = 0; i < 5; i++) k.friction[i] = cf[(size_t)(CF_FRICTION + i) * ncm + c];
+      for (int i = 0; i < 2; i++) k.solref[i] = cf[(size_t)(CF_SOLREF + i) * ncm + c];
+      for (int i = 0; i < 5; i++) k.solimp[i] = cf[(size_t)(CF_SOLIMP + i) * ncm + c];
+      k.mu = k.friction[0];
+      k.geom1 = ci[(size_t)CI_GEOM1 * ncm + c]; k.geom2 = ci[(size_t)CI_GEOM2 * ncm + c]; k.dim = ci[(size_t)CI_DIM * ncm + c];
+      k.pair = ci[(size_t)CI_PAIR * ncm + c]; k.efc_address = ci[(size_t)CI_EFC * ncm + c]; k.exclude = 0;
+    }
+  }
+  if (!b->fused && d->nefc > 0) {
+    const int njm = b->hdr.njmax;
+    std::vector<double> tmp((size_t)njm * std::max(njm, nv));
+    auto E = [&](const char* name, double* dst) -> int {
+      if (get_field<double>(b, name, tmp.data(), env, env + 1, B2_ENV_MAJOR, 0) < 0) return -1;
+      std::copy(tmp.begin(), tmp.begin() + d->nefc, dst);
+      return 0;
+    };
+    if (E("efc_pos", d->efc_pos) < 0 || E("efc_margin", d->efc_margin) < 0 || E("efc_frictionloss", d->efc_frictionloss) < 0 ||
+        E("efc_diagApprox", d->efc_diagApprox) < 0 || E("efc_R", d->efc_R) < 0 || E("efc_D", d->efc_D) < 0 || E("efc_vel", d->efc_vel) < 0 ||
+        E("efc_aref", d->efc_aref) < 0 || E("efc_b", d->efc_b) < 0 || E("efc_force", d->efc_force) < 0)
+      return -1;
+    if (get_field<double>(b, "efc_J", tmp.data(), env, env + 1, B2_ENV_MAJOR, 0) < 0) return -1;
+    std::copy(tmp.begin(), tmp.begin() + (size_t)d->nefc * nv, d->efc_J);
+    std::vector<int> it((size_t)njm);
+    if (get_field<int>(b, "efc_type", it.data(), env, env + 1, B2_ENV_MAJOR, 1) < 0) return -1;
+    std::copy(it.begin(), it.begin() + d->nefc, d->efc_type);
+    if (get_field<int>(b, "efc_id", it.data(), env, env + 1, B2_ENV_MAJOR, 1) < 0) return -1;
+    std::copy(it.begin(), it.begin() + d->nefc, d->efc_id);
+  }
+  return 0;
+}
+
+int b2_load_env(b2_batch* b, int env, const mjData* d) {
+  if (!b || !d || env < 0 || env >= b->nenv) return fail("b2_load_env: bad argument");
+  const mjModel* m = b->m;
+  auto S = [&](const char* name, const double* src, int n) -> int {
+    if (n <= 0 || !src) return 0;
+    std::vector<double> tmp(b->fields[name].count, 0.0);
+    std::copy(src, src + n, tmp.begin());
+    return set_field<double>(b, name, tmp.data(), env, env + 1, B2_ENV_MAJOR) < 0 ? -1 : 0;
+  };
+  if (S("qpos", d->qpos, m->nq) < 0 || S("qvel", d->qvel, m->nv) < 0 || S("qacc", d->qacc, m->nv) < 0 ||
+      S("qacc_warmstart", d->qacc_warmstart, m->nv) < 0 || S("qfrc_applied", d->qfrc_applied, m->nv) < 0)
+    return -1;
+  bool any = false;
+  for (int i = 0; i < 6 * m->nbody; i++) any |= d->xfrc_applied[i] != 0;
+  if (any || (b->tick_flags & (1 << 30))) if (S("xfrc_applied", d->xfrc_applied, 6 * m->nbody) < 0) return -1;
+  if (m->nmocap > 0) if (S("mocap_pos", d->mocap_pos, 3 * m->nmocap) < 0 || S("mocap_quat", d->mocap_quat, 4 * m->nmocap) < 0) return -1;
+  double t = d->time;
+  return set_field<double>(b, "time", &t, env, env + 1, B2_ENV_MAJOR) < 0 ? -1 : 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,61 @@
+// k_args.h — kernel argument block shared by host (batch.cu) and device code.
+#pragma once
+#include <cstdint>
+
+#include "dmodel.h"
+
+namespace b2 {
+
+enum TickFlags : int {
+  B2F_CONTROLLER = 1 << 0,   // run MjSim::controller semantics on ddq/dq (reference mj_sim.cpp:1055-1077)
+  B2F_INVERSE = 1 << 1,      // compute qfrc_inverse (MjHWInterface::read -> mj_inverse, mj_hw_interface.cpp:61)
+  B2F_INTEGRATE = 1 << 2,    // advance the state (mj_step2's Euler); off for mj_forward
+  B2F_ODOM = 1 << 3,         // MjSim::set_odom_vels after integration (mj_sim.cpp:1079-1153)
+  B2F_FUSED = 1 << 4,        // model has no constraint source at all: the smooth kernel also integrates
+  B2F_XFRC = 1 << 5,         // xfrc_applied is non-zero somewhere
+  B2F_WS_GLOBAL = 1 << 6,    // workspace in HBM instead of shared memory
+  B2F_EXPORT = 1 << 7,       // also export the stage arrays from the fused kernel (legacy mjData mirror)
+};
+
+// contact record, SoA: field f of contact c of env e at con[(f * nconmax + c) * nenvp + e]
+enum ConField : int {
+  CF_DIST = 0, CF_POS = 1, CF_FRAME = 4, CF_INCLUDEMARGIN = 13, CF_FRICTION = 14, CF_SOLREF = 19, CF_SOLIMP = 21,
+  CF_NFLOAT = 26
+};
+enum ConIField : int { CI_GEOM1 = 0, CI_GEOM2 = 1, CI_DIM = 2, CI_PAIR = 3, CI_EFC = 4, CI_NINT = 5 };
+
+template <typename T>
+struct KArgs {
+  const uint32_t* model;  // packed DModel blob in HBM
+  int nenv, nenvp;        // environments, padded to a multiple of the CTA size
+  int flags;
+  int ws_block;           // CTA size the shared workspace was sized for
+  T h;                    // timestep of this call (the reference mutates m->opt.timestep every tick, mj_main.cpp:150-163)
+
+  // persistent state, SoA [element][nenvp]
+  T *qpos, *qvel, *qacc, *qacc_warmstart, *qfrc_applied, *xfrc_applied, *mocap_pos, *mocap_quat;
+  T *ddq, *dq, *odom_vels, *time;
+  // per-tick outputs
+  T *qfrc_bias, *qfrc_inverse, *xpos, *xquat;
+  // stage results exported for the constraint pipeline and the legacy mjData mirror
+  T *xmat, *geom_xpos, *geom_xmat, *subtree_com, *cdof, *qM, *qLD, *qLDiagInv, *qfrc_passive, *qfrc_smooth,
+      *qacc_smooth, *qfrc_constraint;
+  T* ws;                  // global workspace [ws_slots][nenvp] when B2F_WS_GLOBAL
+
+  // contacts and constraint rows
+  T* con;                 // [CF_NFLOAT][nconmax][nenvp]
+  int* coni;              // [CI_NINT][nconmax][nenvp]
+  int* ncon;              // [nenvp]
+  int* nefc;              // [nenvp]
+  int* efc_type;          // [njmax][nenvp]
+  int* efc_id;            // [njmax][nenvp]
+  T *efc_J;               // [njmax][nv][nenvp]
+  T *efc_pos, *efc_margin, *efc_frictionloss, *efc_diagApprox, *efc_R, *efc_D, *efc_KBI, *efc_vel, *efc_aref,
+      *efc_b, *efc_force; // [njmax][nenvp] (KBI: [3][njmax][nenvp])
+  T* efc_MiJT;            // [njmax][nv][nenvp]  rows of M^-1 J^T
+  T* efc_AR;              // [njmax][njmax][nenvp]
+  int* solver_iter;       // [nenvp]
+  int* status;            // [nenvp] bit 0: contact cap hit, bit 1: row cap hit, bit 2: state reset (bad value)
+};
+
+}  // namespace b2

@@ -1,0 +1,607 @@
+// k_smooth.cuh — fused smooth-dynamics kernel (group G1 of SURVEY.md section 8a', plus G7 when the model has no
+// constraint source): forward kinematics, CoM quantities, CRBA, sparse LtDL, CoM velocities, passive forces incl.
+// gravity compensation, RNE bias, the reference's PD computed-torque controller (src/mujoco_sim/mj_sim.cpp:1055-1077),
+// inverse dynamics for MjHWInterface::read (src/mujoco_sim/mj_hw_interface.cpp:61), smooth acceleration and, for
+// contact-free models, semi-implicit Euler + odom override.  One thread per environment; every per-environment
+// intermediate lives in a strided workspace (shared memory when it fits, HBM otherwise); the model constants are
+// TMA-staged into shared memory once per persistent CTA.
+#pragma once
+#include "k_args.h"
+#include "k_common.cuh"
+
+namespace b2 {
+
+
+// in-place sparse LtDL factorisation of the matrix stored in LD (tree order), dinv = 1 / D  (mj_factorM, A.4)
+template <typename T>
+__device__ void ld_factor(const MV<T>& m, const SArr<T>& LD, const SArr<T>& dinv) {
+  const DModel& h = *m.h;
+  for (int k = h.nv - 1; k >= 0; k--) {
+    const int Mkk = m.i(h.o_dof_Madr, k);
+    const T inv = T(1) / LD[Mkk];
+    int Mki = Mkk + 1;
+    for (int i = m.i(h.o_dof_parentid, k); i >= 0; i = m.i(h.o_dof_parentid, i), Mki++) {
+      const T tmp = LD[Mki] * inv;
+      int Mij = m.i(h.o_dof_Madr, i), Mkj = Mki;
+      for (int j = i; j >= 0; j = m.i(h.o_dof_parentid, j)) { LD[Mij] -= LD[Mkj] * tmp; Mij++; Mkj++; }
+      LD[Mki] = tmp;
+    }
+    dinv[k] = inv;
+  }
+}
+// x <- M^-1 x by back / forward substitution on the factor (mj_solveM)
+template <typename T>
+__device__ void ld_solve(const MV<T>& m, const SArr<T>& LD, const SArr<T>& dinv, const SArr<T>& x) {
+  const DModel& h = *m.h;
+  const int nv = h.nv;
+  for (int i = nv - 1; i >= 0; i--) {
+    const T xi = x[i];
+    if (xi == 0) continue;
+    int adr = m.i(h.o_dof_Madr, i) + 1;
+    for (int j = m.i(h.o_dof_parentid, i); j >= 0; j = m.i(h.o_dof_parentid, j)) x[j] -= LD[adr++] * xi;
+  }
+  for (int i = 0; i < nv; i++) x[i] *= dinv[i];
+  for (int i = 0; i < nv; i++) {
+    int adr = m.i(h.o_dof_Madr, i) + 1;
+    T xi = x[i];
+    for (int j = m.i(h.o_dof_parentid, i); j >= 0; j = m.i(h.o_dof_parentid, j)) xi -= LD[adr++] * x[j];
+    x[i] = xi;
+  }
+}
+
+// semi-implicit Euler with implicit joint damping (A.9): solves (M + h D) a = frc when any dof is damped, else uses
+// qacc_in; then qvel += h a, qpos (+)= h qvel (quaternion-aware).  LDtmp / dinvtmp / xa are scratch.
+template <typename T>
+__device__ void euler_step(const MV<T>& m, const SArr<T>& qpos, const SArr<T>& qvel, const SArr<T>& qM,
+                           const SArr<T>& qacc_in, const SArr<T>& frc, T hs, const SArr<T>& LDtmp,
+                           const SArr<T>& dinvtmp, const SArr<T>& xa) {
+  const DModel& h = *m.h;
+  const int nv = h.nv;
+  const bool damp = h.has_damping && !(h.disableflags & DSBL_EULERDAMP);
+  if (damp) {
+    for (int i = 0; i < h.nM; i++) LDtmp[i] = qM[i];
+    for (int i = 0; i < nv; i++) LDtmp[m.i(h.o_dof_Madr, i)] += hs * m.f(h.o_dof_damping, i);
+    ld_factor(m, LDtmp, dinvtmp);
+    for (int i = 0; i < nv; i++) xa[i] = frc[i];
+    ld_solve(m, LDtmp, dinvtmp, xa);
+  } else {
+    for (int i = 0; i < nv; i++) xa[i] = qacc_in[i];
+  }
+  for (int i = 0; i < nv; i++) qvel[i] += hs * xa[i];
+  for (int j = 0; j < h.njnt; j++) {
+    const int qa = m.i(h.o_jnt_qposadr, j), da = m.i(h.o_jnt_dofadr, j), jt = m.i(h.o_jnt_type, j);
+    if (jt == JNT_FREE || jt == JNT_BALL) {
+      int qo = qa, dofo = da;
+      if (jt == JNT_FREE) {
+        for (int k = 0; k < 3; k++) qpos[qa + k] += hs * qvel[da + k];
+        qo += 3; dofo += 3;
+      }
+      T q[4], w[3];
+      ld<T, 4>(q, qpos, qo);
+      ld<T, 3>(w, qvel, dofo);
+      quat_integrate(q, w, hs);
+      st<T, 4>(qpos, qo, q);
+    } else {
+      qpos[qa] += hs * qvel[da];
+    }
+  }
+}
+
+template <typename T>
+struct Smooth {
+  MV<T> m;
+  const DModel& h;
+  const KArgs<T>& a;
+  // state (HBM)
+  SArr<T> qpos, qvel, qacc, qfrc_applied;
+  // workspace
+#define X(name, count) SArr<T> name;
+  B2_WS_ARRAYS(X)
+#undef X
+
+  __device__ Smooth(const MV<T>& mv, const KArgs<T>& args, T* wsbase, long long wsstride, int env)
+      : m(mv), h(*mv.h), a(args) {
+    const long long s = args.nenvp;
+    qpos = SArr<T>{args.qpos + env, s};
+    qvel = SArr<T>{args.qvel + env, s};
+    qacc = SArr<T>{args.qacc + env, s};
+    qfrc_applied = SArr<T>{args.qfrc_applied + env, s};
+#define X(name, count) name = SArr<T>{wsbase + (long long)h.w_##name * wsstride, wsstride};
+    B2_WS_ARRAYS(X)
+#undef X
+  }
+
+  // ---- forward kinematics ----
+  __device__ void kinematics(int env) {
+    const int nb = h.nbody;
+    {
+      const T z3[3] = {0, 0, 0}, q1[4] = {1, 0, 0, 0}, I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+      st<T, 3>(xpos, 0, z3); st<T, 4>(xquat, 0, q1); st<T, 9>(xmat, 0, I); st<T, 3>(xipos, 0, z3); st<T, 9>(ximat, 0, I);
+    }
+    for (int b = 1; b < nb; b++) {
+      const int p = m.i(h.o_body_parentid, b), jn = m.i(h.o_body_jntnum, b), ja = m.i(h.o_body_jntadr, b);
+      T pos[3], quat[4];
+      if (jn == 1 && m.i(h.o_jnt_type, ja) == JNT_FREE) {
+        const int qa = m.i(h.o_jnt_qposadr, ja);
+        ld<T, 3>(pos, qpos, qa);
+        ld<T, 4>(quat, qpos, qa + 3);
+        normalize4(quat);
+        st<T, 3>(xanchor, 3 * ja, pos);
+        T ax[3];
+        ldm<T, 3>(ax, m, h.o_jnt_axis, 3 * ja);
+        st<T, 3>(xaxis, 3 * ja, ax);
+      } else {
+        T bp[3], bq[4], pm[9], pp[3], pq[4], r[3];
+        const int mid = m.i(h.o_body_mocapid, b);
+        if (mid >= 0) {
+          SArr<T> mp{a.mocap_pos + env, a.nenvp}, mq{a.mocap_quat + env, a.nenvp};
+          ld<T, 3>(bp, mp, 3 * mid);
+          ld<T, 4>(bq, mq, 4 * mid);
+          normalize4(bq);
+        } else {
+          ldm<T, 3>(bp, m, h.o_body_pos, 3 * b);
+          ldm<T, 4>(bq, m, h.o_body_quat, 4 * b);
+        }
+        ld<T, 9>(pm, xmat, 9 * p);
+        ld<T, 3>(pp, xpos, 3 * p);
+        ld<T, 4>(pq, xquat, 4 * p);
+        mat_vec3(r, pm, bp);
+        pos[0] = pp[0] + r[0]; pos[1] = pp[1] + r[1]; pos[2] = pp[2] + r[2];
+        mul_quat(quat, pq, bq);
+        for (int j = ja; j < ja + jn; j++) {
+          const int qa = m.i(h.o_jnt_qposadr, j), jt = m.i(h.o_jnt_type, j);
+          T jp[3], jx[3], anchor[3], axis[3];
+          ldm<T, 3>(jp, m, h.o_jnt_pos, 3 * j);
+          ldm<T, 3>(jx, m, h.o_jnt_axis, 3 * j);
+          rot_vec_quat(anchor, jp, quat);
+          anchor[0] += pos[0]; anchor[1] += pos[1]; anchor[2] += pos[2];
+          rot_vec_quat(axis, jx, quat);
+          st<T, 3>(xanchor, 3 * j, anchor);
+          st<T, 3>(xaxis, 3 * j, axis);
+          if (jt == JNT_SLIDE) {
+            const T dq = qpos[qa] - m.f(h.o_qpos0, qa);
+            pos[0] += axis[0] * dq; pos[1] += axis[1] * dq; pos[2] += axis[2] * dq;
+          } else {
+            T ql[4], qn[4], off[3];
+            if (jt == JNT_BALL) { ld<T, 4>(ql, qpos, qa); normalize4(ql); }
+            else axis_angle2quat(ql, jx, qpos[qa] - m.f(h.o_qpos0, qa));
+            mul_quat(qn, quat, ql);
+            quat[0] = qn[0]; quat[1] = qn[1]; quat[2] = qn[2]; quat[3] = qn[3];
+            rot_vec_quat(off, jp, quat);
+            pos[0] = anchor[0] - off[0]; pos[1] = anchor[1] - off[1]; pos[2] = anchor[2] - off[2];
+          }
+        }
+      }
+      normalize4(quat);
+      T mat[9], ip[3], iq[4], r[3], qi[4], imat[9];
+      quat2mat(mat, quat);
+      st<T, 3>(xpos, 3 * b, pos);
+      st<T, 4>(xquat, 4 * b, quat);
+      st<T, 9>(xmat, 9 * b, mat);
+      ldm<T, 3>(ip, m, h.o_body_ipos, 3 * b);
+      ldm<T, 4>(iq, m, h.o_body_iquat, 4 * b);
+      mat_vec3(r, mat, ip);
+      r[0] += pos[0]; r[1] += pos[1]; r[2] += pos[2];
+      st<T, 3>(xipos, 3 * b, r);
+      mul_quat(qi, quat, iq);
+      quat2mat(imat, qi);
+      st<T, 9>(ximat, 9 * b, imat);
+    }
+    for (int g = 0; g < h.ngeom; g++) {
+      const int b = m.i(h.o_geom_bodyid, g);
+      T gp[3], gq[4], bm[9], bp[3], bq[4], r[3], q[4], gm[9];
+      ldm<T, 3>(gp, m, h.o_geom_pos, 3 * g);
+      ldm<T, 4>(gq, m, h.o_geom_quat, 4 * g);
+      ld<T, 9>(bm, xmat, 9 * b);
+      ld<T, 3>(bp, xpos, 3 * b);
+      ld<T, 4>(bq, xquat, 4 * b);
+      mat_vec3(r, bm, gp);
+      r[0] += bp[0]; r[1] += bp[1]; r[2] += bp[2];
+      st<T, 3>(geom_xpos, 3 * g, r);
+      mul_quat(q, bq, gq);
+      quat2mat(gm, q);
+      st<T, 9>(geom_xmat, 9 * g, gm);
+    }
+  }
+
+  // ---- CoM-based quantities (A.3) ----
+  __device__ void com_pos() {
+    const int nb = h.nbody;
+    for (int b = 0; b < nb; b++) {
+      const T mass = m.f(h.o_body_mass, b);
+      for (int k = 0; k < 3; k++) subtree_com[3 * b + k] = mass * xipos[3 * b + k];
+    }
+    for (int b = nb - 1; b > 0; b--) {
+      const int p = m.i(h.o_body_parentid, b);
+      for (int k = 0; k < 3; k++) subtree_com[3 * p + k] += subtree_com[3 * b + k];
+    }
+    for (int b = 0; b < nb; b++) {
+      const T sm = m.f(h.o_body_subtreemass, b);
+      if (sm < Eps<T>::minval()) { for (int k = 0; k < 3; k++) subtree_com[3 * b + k] = xipos[3 * b + k]; }
+      else { const T inv = T(1) / sm; for (int k = 0; k < 3; k++) subtree_com[3 * b + k] *= inv; }
+    }
+    for (int k = 0; k < 10; k++) cinert[k] = 0;
+    for (int b = 1; b < nb; b++) {
+      const int root = m.i(h.o_body_rootid, b);
+      T dif[3], mat[9], inert[3], tmp[6];
+      for (int k = 0; k < 3; k++) dif[k] = xipos[3 * b + k] - subtree_com[3 * root + k];
+      ld<T, 9>(mat, ximat, 9 * b);
+      ldm<T, 3>(inert, m, h.o_body_inertia, 3 * b);
+      const T mass = m.f(h.o_body_mass, b);
+      // R diag(I) R^T, upper triangle: xx yy zz xy xz yz
+      tmp[0] = mat[0] * inert[0] * mat[0] + mat[1] * inert[1] * mat[1] + mat[2] * inert[2] * mat[2];
+      tmp[1] = mat[3] * inert[0] * mat[3] + mat[4] * inert[1] * mat[4] + mat[5] * inert[2] * mat[5];
+      tmp[2] = mat[6] * inert[0] * mat[6] + mat[7] * inert[1] * mat[7] + mat[8] * inert[2] * mat[8];
+      tmp[3] = mat[0] * inert[0] * mat[3] + mat[1] * inert[1] * mat[4] + mat[2] * inert[2] * mat[5];
+      tmp[4] = mat[0] * inert[0] * mat[6] + mat[1] * inert[1] * mat[7] + mat[2] * inert[2] * mat[8];
+      tmp[5] = mat[3] * inert[0] * mat[6] + mat[4] * inert[1] * mat[7] + mat[5] * inert[2] * mat[8];
+      T ci[10];
+      ci[0] = tmp[0] + mass * (dif[1] * dif[1] + dif[2] * dif[2]);
+      ci[1] = tmp[1] + mass * (dif[0] * dif[0] + dif[2] * dif[2]);
+      ci[2] = tmp[2] + mass * (dif[0] * dif[0] + dif[1] * dif[1]);
+      ci[3] = tmp[3] - mass * dif[0] * dif[1];
+      ci[4] = tmp[4] - mass * dif[0] * dif[2];
+      ci[5] = tmp[5] - mass * dif[1] * dif[2];
+      ci[6] = mass * dif[0]; ci[7] = mass * dif[1]; ci[8] = mass * dif[2];
+      ci[9] = mass;
+      st<T, 10>(cinert, 10 * b, ci);
+    }
+    for (int j = 0; j < h.njnt; j++) {
+      const int bi = m.i(h.o_jnt_bodyid, j), da = m.i(h.o_jnt_dofadr, j), jt = m.i(h.o_jnt_type, j);
+      const int root = m.i(h.o_body_rootid, bi);
+      T off[3];
+      for (int k = 0; k < 3; k++) off[k] = subtree_com[3 * root + k] - xanchor[3 * j + k];
+      int skip = 0;
+      if (jt == JNT_FREE) {
+        for (int k = 0; k < 3; k++) {
+          for (int r = 0; r < 6; r++) cdof[6 * (da + k) + r] = (r == 3 + k) ? T(1) : T(0);
+        }
+        skip = 3;
+      }
+      if (jt == JNT_FREE || jt == JNT_BALL) {
+        for (int k = 0; k < 3; k++) {
+          T ax[3] = {xmat[9 * bi + k], xmat[9 * bi + 3 + k], xmat[9 * bi + 6 + k]}, lin[3];
+          cross3(lin, ax, off);
+          const int d = da + skip + k;
+          cdof[6 * d] = ax[0]; cdof[6 * d + 1] = ax[1]; cdof[6 * d + 2] = ax[2];
+          cdof[6 * d + 3] = lin[0]; cdof[6 * d + 4] = lin[1]; cdof[6 * d + 5] = lin[2];
+        }
+      } else if (jt == JNT_SLIDE) {
+        cdof[6 * da] = 0; cdof[6 * da + 1] = 0; cdof[6 * da + 2] = 0;
+        for (int k = 0; k < 3; k++) cdof[6 * da + 3 + k] = xaxis[3 * j + k];
+      } else {
+        T ax[3], lin[3];
+        ld<T, 3>(ax, xaxis, 3 * j);
+        cross3(lin, ax, off);
+        cdof[6 * da] = ax[0]; cdof[6 * da + 1] = ax[1]; cdof[6 * da + 2] = ax[2];
+        cdof[6 * da + 3] = lin[0]; cdof[6 * da + 4] = lin[1]; cdof[6 * da + 5] = lin[2];
+      }
+    }
+  }
+
+  // ---- composite rigid body algorithm (A.4) ----
+  __device__ void crb_mass() {
+    const int nb = h.nbody, nv = h.nv;
+    for (int i = 0; i < 10 * nb; i++) crb[i] = cinert[i];
+    for (int b = nb - 1; b > 0; b--) {
+      const int p = m.i(h.o_body_parentid, b);
+      if (p > 0) for (int k = 0; k < 10; k++) crb[10 * p + k] += crb[10 * b + k];
+    }
+    for (int i = 0; i < nv; i++) {
+      int adr = m.i(h.o_dof_Madr, i);
+      T ci[10], cd[6], buf[6];
+      ld<T, 10>(ci, crb, 10 * m.i(h.o_dof_bodyid, i));
+      ld<T, 6>(cd, cdof, 6 * i);
+      mul_inert_vec(buf, ci, cd);
+      T v = m.f(h.o_dof_armature, i);
+      for (int j = i; j >= 0; j = m.i(h.o_dof_parentid, j)) {
+        T cj[6];
+        ld<T, 6>(cj, cdof, 6 * j);
+        v += cj[0] * buf[0] + cj[1] * buf[1] + cj[2] * buf[2] + cj[3] * buf[3] + cj[4] * buf[4] + cj[5] * buf[5];
+        qM[adr++] = v;
+        v = 0;
+      }
+    }
+  }
+
+  // res = M vec (mj_mulM, reference call site src/mujoco_sim/mj_sim.cpp:1057)
+  __device__ void mul_M(const SArr<T>& res, const SArr<T>& vec) {
+    const int nv = h.nv;
+    for (int i = 0; i < nv; i++) res[i] = 0;
+    for (int i = 0; i < nv; i++) {
+      int adr = m.i(h.o_dof_Madr, i);
+      const T vi = vec[i];
+      T ri = res[i] + qM[adr] * vi;
+      adr++;
+      for (int j = m.i(h.o_dof_parentid, i); j >= 0; j = m.i(h.o_dof_parentid, j), adr++) {
+        const T mij = qM[adr];
+        ri += mij * vec[j];
+        res[j] += mij * vi;
+      }
+      res[i] = ri;
+    }
+  }
+
+  // ---- velocity stage (A.5) ----
+  __device__ void com_vel() {
+    for (int k = 0; k < 6; k++) cvel[k] = 0;
+    for (int b = 1; b < h.nbody; b++) {
+      T cv[6];
+      ld<T, 6>(cv, cvel, 6 * m.i(h.o_body_parentid, b));
+      const int ja = m.i(h.o_body_jntadr, b), jn = m.i(h.o_body_jntnum, b);
+      for (int j = ja; j < ja + jn; j++) {
+        int dof = m.i(h.o_jnt_dofadr, j);
+        const int jt = m.i(h.o_jnt_type, j);
+        if (jt == JNT_FREE) {
+          for (int k = 0; k < 3; k++) {
+            const T v = qvel[dof + k];
+            for (int r = 0; r < 6; r++) { cdof_dot[6 * (dof + k) + r] = 0; cv[r] += cdof[6 * (dof + k) + r] * v; }
+          }
+          dof += 3;
+        }
+        if (jt == JNT_FREE || jt == JNT_BALL) {
+          // all three axes see the body velocity before this joint's own rotational dofs are added
+          for (int k = 0; k < 3; k++) {
+            T cd[6], dd[6];
+            ld<T, 6>(cd, cdof, 6 * (dof + k));
+            cross_motion(dd, cv, cd);
+            st<T, 6>(cdof_dot, 6 * (dof + k), dd);
+          }
+          for (int k = 0; k < 3; k++) {
+            const T v = qvel[dof + k];
+            for (int r = 0; r < 6; r++) cv[r] += cdof[6 * (dof + k) + r] * v;
+          }
+        } else {
+          T cd[6], dd[6];
+          ld<T, 6>(cd, cdof, 6 * dof);
+          cross_motion(dd, cv, cd);
+          st<T, 6>(cdof_dot, 6 * dof, dd);
+          const T v = qvel[dof];
+          for (int r = 0; r < 6; r++) cv[r] += cd[r] * v;
+        }
+      }
+      st<T, 6>(cvel, 6 * b, cv);
+    }
+  }
+
+  // qfrc += J^T [force; torque] for a wrench applied at world point `point` on body b
+  __device__ void apply_ft(const SArr<T>& qfrc, int b, const T* point, const T* force, const T* torque) {
+    const int root = m.i(h.o_body_rootid, b);
+    T off[3];
+    for (int k = 0; k < 3; k++) off[k] = point[k] - subtree_com[3 * root + k];
+    for (int i = m.i(h.o_body_lastdof, b); i >= 0; i = m.i(h.o_dof_parentid, i)) {
+      T cd[6], t[3];
+      ld<T, 6>(cd, cdof, 6 * i);
+      cross3(t, cd, off);
+      T s = (cd[3] + t[0]) * force[0] + (cd[4] + t[1]) * force[1] + (cd[5] + t[2]) * force[2];
+      if (torque) s += cd[0] * torque[0] + cd[1] * torque[1] + cd[2] * torque[2];
+      qfrc[i] += s;
+    }
+  }
+
+  __device__ void passive() {
+    const int nv = h.nv;
+    for (int i = 0; i < nv; i++) qfrc_passive[i] = 0;
+    if (h.disableflags & DSBL_PASSIVE) return;
+    if (h.has_stiffness) {
+      for (int j = 0; j < h.njnt; j++) {
+        const T k = m.f(h.o_jnt_stiffness, j);
+        if (k == 0) continue;
+        const int qa = m.i(h.o_jnt_qposadr, j), da = m.i(h.o_jnt_dofadr, j), jt = m.i(h.o_jnt_type, j);
+        if (jt == JNT_FREE || jt == JNT_BALL) {
+          int qo = qa, dofo = da;
+          if (jt == JNT_FREE) {
+            for (int r = 0; r < 3; r++) qfrc_passive[da + r] = -k * (qpos[qa + r] - m.f(h.o_qpos_spring, qa + r));
+            qo += 3; dofo += 3;
+          }
+          T q[4], qs[4], dif[3];
+          ld<T, 4>(q, qpos, qo);
+          normalize4(q);
+          ldm<T, 4>(qs, m, h.o_qpos_spring, qo);
+          sub_quat(dif, q, qs);
+          for (int r = 0; r < 3; r++) qfrc_passive[dofo + r] = -k * dif[r];
+        } else {
+          qfrc_passive[da] = -k * (qpos[qa] - m.f(h.o_qpos_spring, qa));
+        }
+      }
+    }
+    if (h.has_damping)
+      for (int i = 0; i < nv; i++) qfrc_passive[i] -= m.f(h.o_dof_damping, i) * qvel[i];
+    // gravity compensation: the reference sets gravcomp="1" on every robot body by default
+    // (src/mujoco_sim/mj_sim.cpp:301-310, src/config/robot.yaml:19)
+    if (h.has_gravcomp && !(h.disableflags & DSBL_GRAVITY)) {
+      for (int b = 1; b < h.nbody; b++) {
+        const T gc = m.f(h.o_body_gravcomp, b);
+        if (gc == 0) continue;
+        const T s = -m.f(h.o_body_mass, b) * gc;
+        T f[3] = {h.gravity[0] * s, h.gravity[1] * s, h.gravity[2] * s}, pt[3];
+        ld<T, 3>(pt, xipos, 3 * b);
+        apply_ft(qfrc_passive, b, pt, f, (const T*)nullptr);
+      }
+    }
+  }
+
+  // recursive Newton-Euler in the CoM frame; with_acc adds cdof * qacc (inverse dynamics)
+  __device__ void rne(const SArr<T>& result, bool with_acc) {
+    const int nb = h.nbody, nv = h.nv;
+    const bool grav = !(h.disableflags & DSBL_GRAVITY);
+    cacc[0] = 0; cacc[1] = 0; cacc[2] = 0;
+    cacc[3] = grav ? -T(h.gravity[0]) : T(0); cacc[4] = grav ? -T(h.gravity[1]) : T(0); cacc[5] = grav ? -T(h.gravity[2]) : T(0);
+    for (int k = 0; k < 6; k++) cfrc[k] = 0;
+    for (int b = 1; b < nb; b++) {
+      T ac[6], ci[10], cv[6], Ia[6], Iv[6], x[6];
+      ld<T, 6>(ac, cacc, 6 * m.i(h.o_body_parentid, b));
+      const int da = m.i(h.o_body_dofadr, b), dn = m.i(h.o_body_dofnum, b);
+      for (int j = 0; j < dn; j++) {
+        const T v = qvel[da + j];
+        for (int r = 0; r < 6; r++) ac[r] += cdof_dot[6 * (da + j) + r] * v;
+        if (with_acc) {
+          const T q2 = qacc[da + j];
+          for (int r = 0; r < 6; r++) ac[r] += cdof[6 * (da + j) + r] * q2;
+        }
+      }
+      st<T, 6>(cacc, 6 * b, ac);
+      ld<T, 10>(ci, cinert, 10 * b);
+      ld<T, 6>(cv, cvel, 6 * b);
+      mul_inert_vec(Ia, ci, ac);
+      mul_inert_vec(Iv, ci, cv);
+      cross_force(x, cv, Iv);
+      for (int r = 0; r < 6; r++) cfrc[6 * b + r] = Ia[r] + x[r];
+    }
+    for (int b = nb - 1; b > 0; b--) {
+      const int p = m.i(h.o_body_parentid, b);
+      if (p > 0) for (int r = 0; r < 6; r++) cfrc[6 * p + r] += cfrc[6 * b + r];
+    }
+    for (int i = 0; i < nv; i++) {
+      const int b = m.i(h.o_dof_bodyid, i);
+      T s = 0;
+      for (int r = 0; r < 6; r++) s += cdof[6 * i + r] * cfrc[6 * b + r];
+      result[i] = s;
+    }
+  }
+
+};
+
+// MjSim::set_odom_vels (src/mujoco_sim/mj_sim.cpp:1079-1153): per robot r, odom_dof[6r..] = dof of lin x,y,z / ang x,y,z
+// odom joints (-1 when absent or disabled), odom_qpos[3r..] = qpos address of the three angular odom joints (-1 -> 0).
+template <typename T>
+__device__ void odom_override(const MV<T>& m, const KArgs<T>& a, int env) {
+  const DModel& h = *m.h;
+  SArr<T> qpos{a.qpos + env, a.nenvp}, qvel{a.qvel + env, a.nenvp}, ov{a.odom_vels + env, a.nenvp};
+  for (int r = 0; r < h.nodom; r++) {
+    const int ax = m.i(h.o_odom_qpos, 3 * r), ay = m.i(h.o_odom_qpos, 3 * r + 1), az = m.i(h.o_odom_qpos, 3 * r + 2);
+    const T x = ax >= 0 ? qpos[ax] : T(0), y = ay >= 0 ? qpos[ay] : T(0), z = az >= 0 ? qpos[az] : T(0);
+    T sx, cx, sy, cy, sz, cz;
+    t_sincos(x, &sx, &cx); t_sincos(y, &sy, &cy); t_sincos(z, &sz, &cz);
+    const T vx = ov[6 * r], vy = ov[6 * r + 1], vz = ov[6 * r + 2];
+    const int d0 = m.i(h.o_odom_dof, 6 * r), d1 = m.i(h.o_odom_dof, 6 * r + 1), d2 = m.i(h.o_odom_dof, 6 * r + 2);
+    if (d0 >= 0) qvel[d0] = vx * cy * cz + vy * (sx * sy * cz - cx * sz) + vz * (cx * sy * cz + sx * sz);
+    if (d1 >= 0) qvel[d1] = vx * cy * sz + vy * (sx * sy * sz + cx * cz) + vz * (cx * sy * sz - sx * cz);
+    if (d2 >= 0) qvel[d2] = -vx * sy + vy * sx * cy + vz * cx * cy;
+    for (int k = 0; k < 3; k++) {
+      const int dk = m.i(h.o_odom_dof, 6 * r + 3 + k);
+      if (dk >= 0) qvel[dk] = ov[6 * r + 3 + k];
+    }
+  }
+}
+
+// ---- the kernel: persistent CTAs, one thread per environment ----
+template <typename T, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_smooth(const KArgs<T> a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+  uint32_t* blob = reinterpret_cast<uint32_t*>(smem_raw + 16);
+  const int nwords = reinterpret_cast<const DModel*>(a.model)->nwords;
+  stage_model(blob, a.model, nwords, bar);
+  MV<T> m{reinterpret_cast<const DModel*>(blob), blob};
+  const DModel& h = *m.h;
+  T* ws_sh = reinterpret_cast<T*>(smem_raw + 16 + (size_t)nwords * 4);
+  const int nv = h.nv, nb = h.nbody;
+  const long long S = a.nenvp;
+  const int ntiles = a.nenvp / BLOCK;
+
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int env = tile * BLOCK + threadIdx.x;
+    T* wsbase = (a.flags & B2F_WS_GLOBAL) ? a.ws + env : ws_sh + threadIdx.x;
+    const long long wss = (a.flags & B2F_WS_GLOBAL) ? S : BLOCK;
+    Smooth<T> s(m, a, wsbase, wss, env);
+    SArr<T> qfrc_bias{a.qfrc_bias + env, S}, qfrc_inverse{a.qfrc_inverse + env, S};
+
+    // mj_checkPos / mj_checkVel: reset an environment whose state went non-finite
+    {
+      bool bad = false;
+      for (int i = 0; i < h.nq; i++) { const T v = s.qpos[i]; bad |= !(t_abs(v) < T(1e10)); }
+      for (int i = 0; i < nv; i++) { const T v = s.qvel[i]; bad |= !(t_abs(v) < T(1e10)); }
+      if (bad) {
+        for (int i = 0; i < h.nq; i++) s.qpos[i] = m.f(h.o_qpos0, i);
+        for (int i = 0; i < nv; i++) { s.qvel[i] = 0; s.qacc[i] = 0; a.qacc_warmstart[i * S + env] = 0; s.qfrc_applied[i] = 0; }
+        a.time[env] = 0;
+        a.status[env] |= 4;
+      }
+    }
+
+    // position stage
+    s.kinematics(env);
+    s.com_pos();
+    s.crb_mass();
+    for (int i = 0; i < h.nM; i++) s.qLD[i] = s.qM[i];
+    ld_factor(m, s.qLD, s.qLDiagInv);
+    // velocity stage
+    s.com_vel();
+    s.passive();
+    s.rne(qfrc_bias, false);
+
+    // mjcb_control -> MjSim::controller (src/mujoco_sim/mj_sim.cpp:1055-1077)
+    bool overridden = false;
+    if (a.flags & B2F_CONTROLLER) {
+      SArr<T> ddq{a.ddq + env, S}, dq{a.dq + env, S};
+      s.mul_M(s.tmpv, ddq);
+      for (int i = 0; i < nv; i++) {
+        T tau = s.tmpv[i];
+        if (m.i(h.o_dof_controlled, i)) tau += qfrc_bias[i];
+        s.qfrc_applied[i] = tau;
+        const T v = dq[i];
+        if (t_abs(v) > Eps<T>::minval()) { s.qvel[i] = v; overridden = true; }
+        ddq[i] = 0;
+        dq[i] = 0;
+      }
+    }
+    // MjHWInterface::read -> mj_inverse: velocity stage again for the overridden qvel, then RNE with the stored qacc
+    if (a.flags & B2F_INVERSE) {
+      if (overridden) { s.com_vel(); s.passive(); s.rne(qfrc_bias, false); }
+      s.rne(qfrc_inverse, true);
+      for (int i = 0; i < nv; i++) qfrc_inverse[i] += m.f(h.o_dof_armature, i) * s.qacc[i] - s.qfrc_passive[i];
+    }
+
+    // smooth acceleration
+    for (int i = 0; i < nv; i++) s.qfrc_smooth[i] = s.qfrc_passive[i] - qfrc_bias[i] + s.qfrc_applied[i];
+    if (a.flags & B2F_XFRC) {
+      SArr<T> xf{a.xfrc_applied + env, S};
+      for (int b = 1; b < nb; b++) {
+        T w[6], pt[3];
+        ld<T, 6>(w, xf, 6 * b);
+        if (w[0] == 0 && w[1] == 0 && w[2] == 0 && w[3] == 0 && w[4] == 0 && w[5] == 0) continue;
+        ld<T, 3>(pt, s.xipos, 3 * b);
+        s.apply_ft(s.qfrc_smooth, b, pt, w, w + 3);
+      }
+    }
+    for (int i = 0; i < nv; i++) s.qacc_smooth[i] = s.qfrc_smooth[i];
+    ld_solve(m, s.qLD, s.qLDiagInv, s.qacc_smooth);
+
+    // body poses for the ROS layer (tf / marker publishers read d->xpos, d->xquat: SURVEY.md Appendix C)
+    for (int i = 0; i < 3 * nb; i++) a.xpos[i * S + env] = s.xpos[i];
+    for (int i = 0; i < 4 * nb; i++) a.xquat[i * S + env] = s.xquat[i];
+
+    if (!(a.flags & B2F_FUSED) || (a.flags & B2F_EXPORT)) {
+      // export the stage results the constraint pipeline (and the legacy mjData mirror) consume
+      for (int i = 0; i < 9 * nb; i++) a.xmat[i * S + env] = s.xmat[i];
+      for (int i = 0; i < 3 * h.ngeom; i++) a.geom_xpos[i * S + env] = s.geom_xpos[i];
+      for (int i = 0; i < 9 * h.ngeom; i++) a.geom_xmat[i * S + env] = s.geom_xmat[i];
+      for (int i = 0; i < 3 * nb; i++) a.subtree_com[i * S + env] = s.subtree_com[i];
+      for (int i = 0; i < 6 * nv; i++) a.cdof[i * S + env] = s.cdof[i];
+      for (int i = 0; i < h.nM; i++) { a.qM[i * S + env] = s.qM[i]; a.qLD[i * S + env] = s.qLD[i]; }
+      for (int i = 0; i < nv; i++) {
+        a.qLDiagInv[i * S + env] = s.qLDiagInv[i];
+        a.qfrc_passive[i * S + env] = s.qfrc_passive[i];
+        a.qfrc_smooth[i * S + env] = s.qfrc_smooth[i];
+        a.qacc_smooth[i * S + env] = s.qacc_smooth[i];
+      }
+    }
+    if (a.flags & B2F_FUSED) {
+      // no constraint source in the model: qacc = qacc_smooth, integrate right here
+      for (int i = 0; i < nv; i++) {
+        const T v = s.qacc_smooth[i];
+        s.qacc[i] = v;
+        a.qacc_warmstart[i * S + env] = v;
+      }
+      if (a.flags & B2F_INTEGRATE) {
+        // qLD / qLDiagInv are dead by now: reuse them as scratch for the damped factorisation
+        euler_step(m, s.qpos, s.qvel, s.qM, s.qacc_smooth, s.qfrc_smooth, a.h, s.qLD, s.qLDiagInv, s.tmpv);
+        a.time[env] += a.h;
+        if (a.flags & B2F_ODOM) odom_override(m, a, env);
+      }
+    }
+  }
+}
+
+}  // namespace b2

@@ -1,0 +1,329 @@
+"""ctypes mirror of the C ABI (include/b2_batch.h, include/mujoco/mujoco.h).  No physics here: every number comes from
+libb2sim.so.  Importing fails loudly when the library has not been built (python -m mujoco_sim_b200.build)."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def lib_path():
+    return os.path.join(_HERE, "lib", "libb2sim.so")
+
+
+def asset(name):
+    """Path of a model file shipped under mujoco_sim_b200/assets."""
+    return os.path.join(_HERE, "assets", name)
+
+
+class B2Error(RuntimeError):
+    pass
+
+
+if not os.path.exists(lib_path()):
+    raise ImportError("%s is missing: build it with `python -m mujoco_sim_b200.build` "
+                      "(there is no Python or CPU fallback for the CUDA engine)" % lib_path())
+lib = C.CDLL(lib_path(), mode=C.RTLD_GLOBAL)
+
+TICK_CONTROLLER, TICK_INVERSE, TICK_INTEGRATE, TICK_ODOM, TICK_NOSOLVE = 1, 2, 4, 8, 1 << 9
+F32, F64, EXPORT_STAGES = 4, 8, 0x100
+ENV_MAJOR, NATIVE = 0, 1
+OBJ_BODY, OBJ_JOINT, OBJ_GEOM, OBJ_MESH = 1, 3, 5, 9
+
+_vp, _cp, _i = C.c_void_p, C.c_char_p, C.c_int
+_sig = {
+    "mj_loadXML": (_vp, [_cp, _vp, _cp, _i]),
+    "mj_loadXMLString": (_vp, [_cp, _cp, _cp, _i]),
+    "mj_saveLastXML": (_i, [_cp, _vp, _cp, _i]),
+    "mj_makeData": (_vp, [_vp]),
+    "mj_deleteData": (None, [_vp]),
+    "mj_deleteModel": (None, [_vp]),
+    "mj_resetData": (None, [_vp, _vp]),
+    "mj_step": (None, [_vp, _vp]),
+    "mj_step1": (None, [_vp, _vp]),
+    "mj_step2": (None, [_vp, _vp]),
+    "mj_forward": (None, [_vp, _vp]),
+    "mj_inverse": (None, [_vp, _vp]),
+    "mj_mulM": (None, [_vp, _vp, _vp, _vp]),
+    "mj_name2id": (_i, [_vp, _i, _cp]),
+    "mj_id2name": (_cp, [_vp, _i, _i]),
+    "mj_printModel": (None, [_vp, _cp]),
+    "mj_printData": (None, [_vp, _vp, _cp]),
+    "b2_model_int": (_i, [_vp, _cp, C.POINTER(_i)]),
+    "b2_model_array": (_i, [_vp, _cp, C.POINTER(_vp), C.POINTER(_i)]),
+    "b2_data_array": (_i, [_vp, _vp, _cp, C.POINTER(_vp), C.POINTER(_i)]),
+    "b2_model_set_opt": (_i, [_vp, _cp, C.c_double]),
+    "b2_last_error": (_cp, []),
+    "b2_device_count": (_i, []),
+    "b2_create": (_vp, [_vp, _i, _i, _i]),
+    "b2_destroy": (None, [_vp]),
+    "b2_nenv": (_i, [_vp]),
+    "b2_nenv_padded": (_i, [_vp]),
+    "b2_precision": (_i, [_vp]),
+    "b2_set_controlled": (_i, [_vp, _vp]),
+    "b2_set_odom": (_i, [_vp, _i, _vp, _vp]),
+    "b2_set_timestep": (_i, [_vp, C.c_double]),
+    "b2_set_option": (_i, [_vp, _cp, C.c_double]),
+    "b2_field_size": (_i, [_vp, _cp]),
+    "b2_set_field_f32": (_i, [_vp, _cp, _vp, _i, _i, _i]),
+    "b2_set_field_f64": (_i, [_vp, _cp, _vp, _i, _i, _i]),
+    "b2_get_field_f32": (_i, [_vp, _cp, _vp, _i, _i, _i]),
+    "b2_get_field_f64": (_i, [_vp, _cp, _vp, _i, _i, _i]),
+    "b2_get_field_i32": (_i, [_vp, _cp, _vp, _i, _i, _i]),
+    "b2_device_ptr": (_vp, [_vp, _cp]),
+    "b2_reset": (_i, [_vp, _i, _i]),
+    "b2_tick": (_i, [_vp, _i]),
+    "b2_step": (_i, [_vp, _i]),
+    "b2_set_tick_flags": (_i, [_vp, _i]),
+    "b2_forward": (_i, [_vp]),
+    "b2_sync": (_i, [_vp]),
+    "b2_stream": (_vp, [_vp]),
+    "b2_launch_count": (C.c_longlong, [_vp]),
+    "b2_set_hw_joints": (_i, [_vp, _i, _vp]),
+    "b2_write_commands": (_i, [_vp, _vp, _vp]),
+    "b2_read_joints": (_i, [_vp, _vp, _vp, _vp]),
+    "b2_tick_host": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "b2_mirror_env": (_i, [_vp, _i, _vp]),
+    "b2_load_env": (_i, [_vp, _i, _vp]),
+    "b2_shim_batch": (_vp, [_vp, _vp]),
+}
+for _n, (_r, _a) in _sig.items():
+    _f = getattr(lib, _n)
+    _f.restype = _r
+    _f.argtypes = _a
+
+INT_FIELDS = {"ncon", "nefc", "efc_type", "efc_id", "contact_int", "solver_iter", "status"}
+
+
+def _err():
+    return (lib.b2_last_error() or b"").decode()
+
+
+_KIND_DTYPE = {0: np.float64, 1: np.int32, 2: np.uint8, 3: np.float32}
+
+
+class Model:
+    """mjModel handle (mj_loadXML: reference include/mujoco_sim/mj_util.h:190)."""
+
+    def __init__(self, path=None, xml=None, basedir="."):
+        err = C.create_string_buffer(1000)
+        if path is not None:
+            self.ptr = lib.mj_loadXML(path.encode(), None, err, 1000)
+        else:
+            self.ptr = lib.mj_loadXMLString(xml.encode(), basedir.encode(), err, 1000)
+        if not self.ptr:
+            raise B2Error("mj_loadXML: " + err.value.decode())
+
+    def __del__(self):
+        if getattr(self, "ptr", None):
+            lib.mj_deleteModel(self.ptr)
+            self.ptr = None
+
+    def int(self, name):
+        v = _i(0)
+        if lib.b2_model_int(self.ptr, name.encode(), C.byref(v)) < 0:
+            raise KeyError(name)
+        return v.value
+
+    def array(self, name):
+        """numpy VIEW of a model array (writes go through to the model)."""
+        p, k = _vp(), _i()
+        n = lib.b2_model_array(self.ptr, name.encode(), C.byref(p), C.byref(k))
+        if n < 0:
+            raise KeyError(name)
+        if n == 0 or not p.value:
+            return np.zeros(0, _KIND_DTYPE[k.value])
+        dt = _KIND_DTYPE[k.value]
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(np.ctypeslib.as_ctypes_type(dt))), shape=(n,))
+
+    def __getattr__(self, name):
+        if name.startswith("n") and not name.startswith("name"):
+            try:
+                return self.int(name)
+            except KeyError:
+                pass
+        try:
+            return self.array(name)
+        except KeyError:
+            raise AttributeError(name)
+
+    def set_opt(self, name, value):
+        if lib.b2_model_set_opt(self.ptr, name.encode(), float(value)) < 0:
+            raise KeyError(name)
+
+    @property
+    def timestep(self):
+        return float(self.array("opt.timestep")[0])
+
+    def name2id(self, objtype, name):
+        return lib.mj_name2id(self.ptr, objtype, name.encode())
+
+    def id2name(self, objtype, i):
+        s = lib.mj_id2name(self.ptr, objtype, i)
+        return s.decode() if s else None
+
+
+class Data:
+    """mjData handle (mj_makeData: reference src/mujoco_sim/mj_sim.cpp:816)."""
+
+    def __init__(self, model):
+        self.model = model
+        self.ptr = lib.mj_makeData(model.ptr)
+        if not self.ptr:
+            raise B2Error("mj_makeData failed")
+
+    def __del__(self):
+        if getattr(self, "ptr", None):
+            lib.mj_deleteData(self.ptr)
+            self.ptr = None
+
+    def array(self, name):
+        p, k = _vp(), _i()
+        n = lib.b2_data_array(self.model.ptr, self.ptr, name.encode(), C.byref(p), C.byref(k))
+        if n < 0:
+            raise KeyError(name)
+        dt = _KIND_DTYPE[k.value]
+        if n == 0 or not p.value:
+            return np.zeros(0, dt)
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(np.ctypeslib.as_ctypes_type(dt))), shape=(n,))
+
+    def __getattr__(self, name):
+        if name in ("model", "ptr"):
+            raise AttributeError(name)
+        try:
+            a = self.array(name)
+        except KeyError:
+            raise AttributeError(name)
+        if name in ("time", "ncon", "nefc", "solver_iter"):
+            return a[0]
+        return a
+
+
+class Batch:
+    """b2_batch handle: nenv environments of one model on one GPU."""
+
+    def __init__(self, model, nenv, device=0, precision=F32, export_stages=False):
+        self.model = model
+        self.ptr = lib.b2_create(model.ptr, int(nenv), int(device), int(precision) | (EXPORT_STAGES if export_stages else 0))
+        if not self.ptr:
+            raise B2Error("b2_create: " + _err())
+        self.nenv = int(nenv)
+        self.precision = precision
+
+    def close(self):
+        if getattr(self, "ptr", None):
+            lib.b2_destroy(self.ptr)
+            self.ptr = None
+
+    __del__ = close
+
+    def _ck(self, rc, what):
+        if rc < 0:
+            raise B2Error(what + ": " + _err())
+        return rc
+
+    def field_size(self, name):
+        return self._ck(lib.b2_field_size(self.ptr, name.encode()), "b2_field_size")
+
+    def set(self, name, value, env_lo=0, env_hi=None, layout=ENV_MAJOR):
+        """value: array [env][n] (ENV_MAJOR) or [n][env] (NATIVE) for environments [env_lo, env_hi)."""
+        env_hi = self.nenv if env_hi is None else env_hi
+        n = self.field_size(name)
+        nenv = env_hi - env_lo
+        shape = (nenv, n) if layout == ENV_MAJOR else (n, nenv)
+        if np.asarray(value).dtype == np.float32:
+            a = np.ascontiguousarray(np.broadcast_to(np.asarray(value, np.float32), shape))
+            rc = lib.b2_set_field_f32(self.ptr, name.encode(), a.ctypes.data, env_lo, env_hi, layout)
+        else:
+            a = np.ascontiguousarray(np.broadcast_to(np.asarray(value, np.float64), shape))
+            rc = lib.b2_set_field_f64(self.ptr, name.encode(), a.ctypes.data, env_lo, env_hi, layout)
+        self._ck(rc, "b2_set_field(%s)" % name)
+
+    def get(self, name, env_lo=0, env_hi=None, layout=ENV_MAJOR, dtype=np.float64):
+        env_hi = self.nenv if env_hi is None else env_hi
+        n = self.field_size(name)
+        nenv = env_hi - env_lo
+        shape = (nenv, n) if layout == ENV_MAJOR else (n, nenv)
+        if name in INT_FIELDS:
+            out = np.empty(shape, np.int32)
+            rc = lib.b2_get_field_i32(self.ptr, name.encode(), out.ctypes.data, env_lo, env_hi, layout)
+        elif dtype == np.float32:
+            out = np.empty(shape, np.float32)
+            rc = lib.b2_get_field_f32(self.ptr, name.encode(), out.ctypes.data, env_lo, env_hi, layout)
+        else:
+            out = np.empty(shape, np.float64)
+            rc = lib.b2_get_field_f64(self.ptr, name.encode(), out.ctypes.data, env_lo, env_hi, layout)
+        self._ck(rc, "b2_get_field(%s)" % name)
+        return out
+
+    def device_ptr(self, name):
+        p = lib.b2_device_ptr(self.ptr, name.encode())
+        if not p:
+            raise B2Error("b2_device_ptr: " + _err())
+        return p
+
+    def set_controlled(self, mask):
+        a = np.ascontiguousarray(mask, np.uint8)
+        self._ck(lib.b2_set_controlled(self.ptr, a.ctypes.data), "b2_set_controlled")
+
+    def set_odom(self, dof, qposadr):
+        d = np.ascontiguousarray(dof, np.int32).reshape(-1, 6)
+        q = np.ascontiguousarray(qposadr, np.int32).reshape(-1, 3)
+        self._ck(lib.b2_set_odom(self.ptr, d.shape[0], d.ctypes.data, q.ctypes.data), "b2_set_odom")
+
+    def set_timestep(self, h):
+        self._ck(lib.b2_set_timestep(self.ptr, float(h)), "b2_set_timestep")
+
+    def set_option(self, name, value):
+        self._ck(lib.b2_set_option(self.ptr, name.encode(), float(value)), "b2_set_option")
+
+    def reset(self, env_lo=0, env_hi=None):
+        self._ck(lib.b2_reset(self.ptr, env_lo, self.nenv if env_hi is None else env_hi), "b2_reset")
+
+    def tick(self, flags=TICK_INTEGRATE):
+        self._ck(lib.b2_tick(self.ptr, flags), "b2_tick")
+
+    def step(self, nsteps=1):
+        self._ck(lib.b2_step(self.ptr, nsteps), "b2_step")
+
+    def set_tick_flags(self, flags):
+        self._ck(lib.b2_set_tick_flags(self.ptr, flags), "b2_set_tick_flags")
+
+    def forward(self):
+        self._ck(lib.b2_forward(self.ptr), "b2_forward")
+
+    def sync(self):
+        self._ck(lib.b2_sync(self.ptr), "b2_sync")
+
+    @property
+    def stream(self):
+        return lib.b2_stream(self.ptr)
+
+    @property
+    def launch_count(self):
+        return lib.b2_launch_count(self.ptr)
+
+    def set_hw_joints(self, jnt_ids):
+        a = np.ascontiguousarray(jnt_ids, np.int32)
+        self._ck(lib.b2_set_hw_joints(self.ptr, a.size, a.ctypes.data), "b2_set_hw_joints")
+        self.nhw = a.size
+
+    def write_commands(self, vel_cmd, effort_cmd):
+        v = np.ascontiguousarray(vel_cmd, np.float32)
+        e = np.ascontiguousarray(effort_cmd, np.float32)
+        self._ck(lib.b2_write_commands(self.ptr, v.ctypes.data, e.ctypes.data), "b2_write_commands")
+
+    def read_joints(self):
+        out = [np.empty((self.nhw, self.nenv), np.float32) for _ in range(3)]
+        self._ck(lib.b2_read_joints(self.ptr, *[o.ctypes.data for o in out]), "b2_read_joints")
+        return out
+
+    def tick_host_raw(self, vel_ptr, eff_ptr, pos_ptr, velo_ptr, effo_ptr):
+        self._ck(lib.b2_tick_host(self.ptr, vel_ptr, eff_ptr, pos_ptr, velo_ptr, effo_ptr), "b2_tick_host")
+
+    def mirror_env(self, env, data):
+        self._ck(lib.b2_mirror_env(self.ptr, env, data.ptr), "b2_mirror_env")
+
+    def load_env(self, env, data):
+        self._ck(lib.b2_load_env(self.ptr, env, data.ptr), "b2_load_env")
