@@ -129,6 +129,11 @@ int pack_model(b2_batch* b) {
     if (!std::strcmp(name, "dof_controlled")) { put_int(o, ctl.data(), n); return 0; }
     if (!std::strcmp(name, "odom_dof")) { put_int(o, b->odom_dof.data(), n); return 0; }
     if (!std::strcmp(name, "odom_qpos")) { put_int(o, b->odom_qpos.data(), n); return 0; }
+    if (!std::strcmp(name, "opt_real")) {
+      const double v[8] = {m->opt.gravity[0], m->opt.gravity[1], m->opt.gravity[2], b->opt_tolerance, m->stat.meaninertia, m->opt.impratio, 0, 0};
+      put_real(o, v, 8);
+      return 0;
+    }
     const void* p = nullptr;
     int kind = 0;
     const int cnt = b2::model_array(m, name, &p, &kind);

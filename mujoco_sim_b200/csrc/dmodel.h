@@ -28,7 +28,8 @@ namespace b2 {
   X(eq_type, I, neq) X(eq_obj1id, I, neq) X(eq_obj2id, I, neq) X(eq_active, I, neq)                            \
   X(eq_solref, F, 2 * neq) X(eq_solimp, F, 5 * neq) X(eq_data, F, 11 * neq)                                    \
   X(pair_geom1, I, npair) X(pair_geom2, I, npair)                                                              \
-  X(odom_dof, I, 6 * nodom) X(odom_qpos, I, 3 * nodom)
+  X(odom_dof, I, 6 * nodom) X(odom_qpos, I, 3 * nodom)                                                          \
+  X(opt_real, F, 8) /* gravity[3], tolerance, meaninertia, impratio, 0, 0 in batch precision */
 
 // Workspace arrays (per environment, strided by the workspace stride): name, count expression
 #define B2_WS_ARRAYS(X)                                                                                        \

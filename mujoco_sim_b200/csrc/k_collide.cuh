@@ -300,13 +300,13 @@ __device__ int d_box_box(RawCon<T>* out, const GeomW<T>& a, const GeomW<T>& b, T
     const T rb = b.size[0] * Rabs[i][0] + b.size[1] * Rabs[i][1] + b.size[2] * Rabs[i][2];
     const T t = dot3(dif, A[i]), sep = t_abs(t) - a.size[i] - rb;
     if (sep > margin) return 0;
-    if (sep > best) { best = sep; code = i; const T s = t >= 0 ? T(1) : T(-1); axis[0] = s * A[i][0]; axis[1] = s * A[i][1]; axis[2] = s * A[i][2]; }
+    if (sep > best + (i ? T(1e-6) : T(0))) { best = sep; code = i; const T s = t >= 0 ? T(1) : T(-1); axis[0] = s * A[i][0]; axis[1] = s * A[i][1]; axis[2] = s * A[i][2]; }
   }
   for (int j = 0; j < 3; j++) {
     const T ra = a.size[0] * Rabs[0][j] + a.size[1] * Rabs[1][j] + a.size[2] * Rabs[2][j];
     const T t = dot3(dif, B[j]), sep = t_abs(t) - ra - b.size[j];
     if (sep > margin) return 0;
-    if (sep > best) { best = sep; code = 3 + j; const T s = t >= 0 ? T(1) : T(-1); axis[0] = s * B[j][0]; axis[1] = s * B[j][1]; axis[2] = s * B[j][2]; }
+    if (sep > best + T(1e-6)) { best = sep; code = 3 + j; const T s = t >= 0 ? T(1) : T(-1); axis[0] = s * B[j][0]; axis[1] = s * B[j][1]; axis[2] = s * B[j][2]; }
   }
   for (int i = 0; i < 3; i++)
     for (int j = 0; j < 3; j++) {

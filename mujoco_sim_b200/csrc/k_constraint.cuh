@@ -295,7 +295,7 @@ struct Rows {
       const int adr = a.coni[((long long)CI_EFC * h.nconmax + c) * S + env];
       const int dim = a.coni[((long long)CI_DIM * h.nconmax + c) * S + env];
       if (adr < 0 || dim == 1) continue;
-      const T mu = a.con[((long long)CF_FRICTION * h.nconmax + c) * S + env] / t_sqrt(t_max(Eps<T>::minval(), T(h.impratio)));
+      const T mu = a.con[((long long)CF_FRICTION * h.nconmax + c) * S + env] / t_sqrt(t_max(Eps<T>::minval(), m.f(h.o_opt_real, 5)));
       const T Rpy = t_max(Eps<T>::minval(), 2 * mu * mu * a.efc_R[(long long)adr * S + env]);
       for (int j = 0; j < 2 * (dim - 1); j++) a.efc_R[(long long)(adr + j) * S + env] = Rpy;
     }
@@ -422,7 +422,7 @@ __global__ void __launch_bounds__(BLOCK) k_pgs(const KArgs<T> a) {
       } else {
         for (int r = 0; r < ne; r++) F(r) = 0;
       }
-      const T scale = 1 / (T(h.meaninertia) * T(nv > 1 ? nv : 1));
+      const T scale = 1 / (m.f(h.o_opt_real, 4) * T(nv > 1 ? nv : 1));
       for (int it = 0; it < h.iterations; it++) {
         T improvement = 0;
         for (int r = 0; r < ne; r++) {
@@ -441,7 +441,7 @@ __global__ void __launch_bounds__(BLOCK) k_pgs(const KArgs<T> a) {
           improvement -= change;
         }
         iters = it + 1;
-        if (improvement * scale < T(h.tolerance)) break;
+        if (improvement * scale < m.f(h.o_opt_real, 3)) break;
       }
     }
     a.solver_iter[env] = iters;

@@ -414,7 +414,7 @@ struct Smooth {
         const T gc = m.f(h.o_body_gravcomp, b);
         if (gc == 0) continue;
         const T s = -m.f(h.o_body_mass, b) * gc;
-        T f[3] = {h.gravity[0] * s, h.gravity[1] * s, h.gravity[2] * s}, pt[3];
+        T f[3] = {m.f(h.o_opt_real, 0) * s, m.f(h.o_opt_real, 1) * s, m.f(h.o_opt_real, 2) * s}, pt[3];
         ld<T, 3>(pt, xipos, 3 * b);
         apply_ft(qfrc_passive, b, pt, f, (const T*)nullptr);
       }
@@ -426,7 +426,7 @@ struct Smooth {
     const int nb = h.nbody, nv = h.nv;
     const bool grav = !(h.disableflags & DSBL_GRAVITY);
     cacc[0] = 0; cacc[1] = 0; cacc[2] = 0;
-    cacc[3] = grav ? -T(h.gravity[0]) : T(0); cacc[4] = grav ? -T(h.gravity[1]) : T(0); cacc[5] = grav ? -T(h.gravity[2]) : T(0);
+    cacc[3] = grav ? -m.f(h.o_opt_real, 0) : T(0); cacc[4] = grav ? -m.f(h.o_opt_real, 1) : T(0); cacc[5] = grav ? -m.f(h.o_opt_real, 2) : T(0);
     for (int k = 0; k < 6; k++) cfrc[k] = 0;
     for (int b = 1; b < nb; b++) {
       T ac[6], ci[10], cv[6], Ia[6], Iv[6], x[6];

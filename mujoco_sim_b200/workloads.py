@@ -1,0 +1,117 @@
+"""Synthetic workloads of BASELINE.json / SURVEY.md section 8(d): seeded, shard-invariant state generation.
+
+Environment e always draws the same numbers for a given seed, whatever batch or shard it lives in (counter-based
+hash of (seed, env, index)), so sharding across GPUs does not change any environment's trajectory."""
+import numpy as np
+
+from . import engine
+
+CONFIGS = {
+    # name: (model asset, default nenv, description)
+    "c1": ("pendulum_world.xml", 1, "pendulum world, 1 env (plumbing)"),
+    "c2": ("panda7.xml", 4096, "Franka-Panda-like 7-DoF arm, contact-free forward dynamics"),
+    "c3": ("ur5_tabletop.xml", 16384, "UR5-like arm + tabletop objects with contacts, PGS"),
+}
+
+
+def uniform(seed, env, idx):
+    """Counter-based uniform in [0, 1) from (seed, env, idx) (splitmix64 finaliser)."""
+    with np.errstate(over="ignore"):
+        z = np.uint64(seed) + np.uint64(0x9E3779B97F4A7C15) * (np.asarray(env, np.uint64) * np.uint64(1000003) + np.asarray(idx, np.uint64) + np.uint64(1))
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    return (z >> np.uint64(11)).astype(np.float64) / float(1 << 53)
+
+
+def random_state(model, envs, seed, vmax=1.0, fmax=10.0, free_xy=0.3, free_z=(0.02, 0.25), ranges=None):
+    """qpos / qvel / qfrc_applied for the environment ids in `envs`.  Scalar joints: uniform inside their range
+    (`ranges[joint_name]` overrides; unlimited hinges +-pi, slides +-0.3), free bodies displaced from qpos0 by
+    U(-free_xy, free_xy) in x, y and U(free_z) in z with identity rotation and zero velocity."""
+    envs = np.asarray(envs)
+    nenv = envs.size
+    nq, nv, njnt = model.nq, model.nv, model.njnt
+    env = envs[:, None]
+    uq = uniform(seed, env, np.arange(nq)[None, :])
+    uv = uniform(seed + 1, env, np.arange(nv)[None, :])
+    uf = uniform(seed + 2, env, np.arange(nv)[None, :])
+    qpos = np.tile(np.array(model.qpos0), (nenv, 1))
+    qvel = np.zeros((nenv, nv))
+    frc = np.zeros((nenv, nv))
+    jt, qa, da = model.jnt_type, model.jnt_qposadr, model.jnt_dofadr
+    rng, lim = model.jnt_range.reshape(-1, 2), model.jnt_limited
+    for j in range(njnt):
+        a, d = int(qa[j]), int(da[j])
+        if jt[j] == 0:
+            qpos[:, a] += (2 * uq[:, a] - 1) * free_xy
+            qpos[:, a + 1] += (2 * uq[:, a + 1] - 1) * free_xy
+            qpos[:, a + 2] += free_z[0] + uq[:, a + 2] * (free_z[1] - free_z[0])
+        elif jt[j] == 1:
+            v = (2 * uq[:, a + 1:a + 4] - 1) * 0.5
+            ang = np.linalg.norm(v, axis=1, keepdims=True) + 1e-12
+            qpos[:, a] = np.cos(ang[:, 0] / 2)
+            qpos[:, a + 1:a + 4] = v / ang * np.sin(ang / 2)
+            qvel[:, d:d + 3] = (2 * uv[:, d:d + 3] - 1) * vmax
+            frc[:, d:d + 3] = (2 * uf[:, d:d + 3] - 1) * fmax
+        else:
+            name = model.id2name(engine.OBJ_JOINT, j)
+            if ranges and name in ranges:
+                lo, hi = ranges[name]
+            elif lim[j]:
+                lo, hi = rng[j]
+            else:
+                lo, hi = (-np.pi, np.pi) if jt[j] == 3 else (-0.3, 0.3)
+            span = hi - lo
+            qpos[:, a] = lo + 0.02 * span + uq[:, a] * 0.96 * span
+            qvel[:, d] = (2 * uv[:, d] - 1) * vmax
+            frc[:, d] = (2 * uf[:, d] - 1) * fmax
+    return qpos, qvel, frc
+
+
+# joint sub-ranges that keep the UR5-like arm above the table for most draws (C3)
+UR5_RANGES = {"shoulder_pan_joint": (-1.2, 1.2), "shoulder_lift_joint": (-2.0, -0.4), "elbow_joint": (-0.8, 1.6),
+              "wrist_1_joint": (-1.5, 1.5), "wrist_2_joint": (-1.5, 1.5), "wrist_3_joint": (-3.0, 3.0)}
+
+
+def config_state(cfg, model, envs, seed=None):
+    seed = (0xB200 + int(cfg[1])) if seed is None else seed
+    if cfg == "c3":
+        # props spread over the table (+-0.12 around their authored places, which are >= 0.2 m apart), dropped from
+        # 5 mm of penetration to 8 cm of hover; arm torques are gentle so that it settles onto / around the table
+        return random_state(model, envs, seed, vmax=0.5, fmax=5.0, free_xy=0.06, free_z=(-0.005, 0.08), ranges=UR5_RANGES)
+    if cfg == "c1":
+        q = np.tile(np.array(model.qpos0), (np.asarray(envs).size, 1))
+        return q, np.zeros((q.shape[0], model.nv)), np.zeros((q.shape[0], model.nv))
+    return random_state(model, envs, seed)
+
+
+def load_states(batch, gen, max_depth=0.01, max_rounds=8):
+    """Fill `batch` from gen(env_ids, round) -> (qpos, qvel, qfrc_applied).  Draws whose initial contacts penetrate
+    deeper than max_depth (unphysical starts) are redrawn with round + 1, using the engine's own collision pass for
+    the check.  Returns (qpos, qvel, frc, rounds_used)."""
+    model = batch.model
+    envs = np.arange(batch.nenv)
+    qpos, qvel, frc = gen(envs, 0)
+    batch.set("qpos", qpos); batch.set("qvel", qvel); batch.set("qfrc_applied", frc)
+    if model.npair == 0:
+        return qpos, qvel, frc, 0
+    ncm = model.nconmax
+    for rnd in range(1, max_rounds + 1):
+        batch.forward()
+        batch.sync()
+        ncon = batch.get("ncon")[:, 0]
+        dist = batch.get("contact", dtype=np.float32)[:, :ncm]
+        mask = np.arange(ncm)[None, :] < ncon[:, None]
+        bad = np.where(((dist < -max_depth) & mask).any(axis=1))[0]
+        if bad.size == 0:
+            return qpos, qvel, frc, rnd - 1
+        q2, v2, f2 = gen(envs[bad], rnd)
+        qpos[bad], qvel[bad], frc[bad] = q2, v2, f2
+        batch.set("qpos", qpos); batch.set("qvel", qvel); batch.set("qfrc_applied", frc)
+    return qpos, qvel, frc, max_rounds
+
+
+def load_config(cfg, batch, env_offset=0, max_depth=0.01):
+    """Synthetic state of config `cfg` for global environments [env_offset, env_offset + nenv)."""
+    base = 0xB200 + int(cfg[1])
+    return load_states(batch, lambda envs, rnd: config_state(cfg, batch.model, envs + env_offset, seed=base + 7919 * rnd), max_depth)

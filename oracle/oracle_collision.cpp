@@ -337,7 +337,7 @@ int box_box(C* out, const G& a, const G& b, mjtNum margin) {
   auto consider = [&](const mjtNum* L, mjtNum ra, mjtNum rb, int code, mjtNum bias) {
     const mjtNum t = dot3(dif, L);
     const mjtNum sep = std::fabs(t) - ra - rb;
-    if (sep * bias > best + (code >= 6 ? 1e-6 : 0)) {  // edge axes must beat face axes by a margin
+    if (sep * bias > best + (code >= 1 ? 1e-6 : 0)) {  // a later axis must win by a margin: ties keep the earlier one
       best = sep * bias;
       best_code = code;
       const mjtNum s = t >= 0 ? 1 : -1;

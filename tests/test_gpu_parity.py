@@ -1,0 +1,319 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the fp64 oracle on the same seeded inputs.
+B2_F64 batches must agree with the oracle to rounding of the SAME algorithm (1e-9), which separates algorithmic
+discrepancies from fp32 rounding; B2_F32 batches (the product path) are held to the fp32 tolerances written below.
+Integer results (contact counts, geom ids, row types) must match exactly."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from helpers import random_state, oracle_rollout
+
+pytestmark = pytest.mark.gpu
+
+MODELS = ["panda7.xml", "pendulum_world.xml", "ur5_tabletop.xml"]
+STAGE_FIELDS = ["xpos", "xquat", "qfrc_bias", "qM", "qfrc_passive", "qacc_smooth", "subtree_com", "cdof", "qacc", "qfrc_constraint"]
+EFC_FIELDS = ["efc_pos", "efc_margin", "efc_diagApprox", "efc_R", "efc_D", "efc_vel", "efc_aref", "efc_b", "efc_force"]
+
+
+def oracle_forward(orc, b2, m, qpos, qvel, frc, iterations=None):
+    d = b2.Data(m)
+    out = []
+    for e in range(qpos.shape[0]):
+        d.qpos[:] = qpos[e]; d.qvel[:] = qvel[e]; d.qfrc_applied[:] = frc[e]
+        d.qacc_warmstart[:] = 0; d.qacc[:] = 0
+        orc.call("forward", m, d)
+        rec = {f: np.array(d.array(f)) for f in STAGE_FIELDS + EFC_FIELDS + ["efc_J", "efc_type", "efc_id", "efc_AR"]}
+        rec["ncon"], rec["nefc"], rec["iter"] = int(d.ncon), int(d.nefc), int(d.solver_iter)
+        con = []
+        for c in range(d.ncon):
+            k = contact_of(b2, d, c)
+            con.append(k)
+        rec["contacts"] = con
+        out.append(rec)
+    return out
+
+
+class MjContact(C.Structure):
+    _fields_ = [("dist", C.c_double), ("pos", C.c_double * 3), ("frame", C.c_double * 9), ("includemargin", C.c_double),
+                ("friction", C.c_double * 5), ("solref", C.c_double * 2), ("solimp", C.c_double * 5), ("mu", C.c_double),
+                ("dim", C.c_int), ("geom1", C.c_int), ("geom2", C.c_int), ("exclude", C.c_int), ("efc_address", C.c_int),
+                ("pair", C.c_int)]
+
+
+def contact_of(b2, d, i):
+    k = MjContact()
+    b2.lib.b2_data_contact.restype = C.c_int
+    b2.lib.b2_data_contact.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    assert b2.lib.b2_data_contact(d.ptr, i, C.byref(k)) == 0
+    return dict(dist=k.dist, pos=np.array(k.pos), frame=np.array(k.frame), geom1=k.geom1, geom2=k.geom2, dim=k.dim, pair=k.pair,
+                friction=np.array(k.friction), efc=k.efc_address)
+
+
+def states_for(m, name, nenv, seed):
+    """Seeded states with a variety of shallow contacts.  Deeply inter-penetrating draws (unphysical: the nearest-exit
+    direction of a sphere centre buried 10 cm inside a box is a coin toss between fp32 and fp64) are redrawn."""
+    import mujoco_sim_b200 as b2
+    from mujoco_sim_b200 import workloads as w
+    ranges = w.UR5_RANGES if name.startswith("ur5") else None
+
+    def gen(envs, rnd):
+        return w.random_state(m, envs, seed + 1000 * rnd, free_xy=0.06, free_z=(-0.004, 0.03), ranges=ranges)
+    bt = b2.Batch(m, nenv, precision=b2.engine.F64)
+    qpos, qvel, frc, _ = w.load_states(bt, gen, max_depth=0.008)
+    bt.close()
+    return qpos, qvel, frc
+
+
+@pytest.mark.parametrize("name", MODELS)
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_forward_matches_oracle(b2, orc, name, prec):
+    m = b2.Model(b2.asset(name))
+    nenv = 48
+    qpos, qvel, frc = states_for(m, name, nenv, 101)
+    ref = oracle_forward(orc, b2, m, qpos, qvel, frc)
+    bt = b2.Batch(m, nenv, precision=b2.engine.F64 if prec == "f64" else b2.engine.F32, export_stages=True)
+    bt.set("qpos", qpos); bt.set("qvel", qvel); bt.set("qfrc_applied", frc)
+    bt.forward(); bt.sync()
+    tol = 1e-9 if prec == "f64" else 2e-4
+    got = {f: bt.get(f) for f in STAGE_FIELDS}
+    has_con = "ncon" in b2.engine.INT_FIELDS and m.npair > 0 or np.any(m.jnt_limited)
+    ncon = bt.get("ncon")[:, 0]; nefc = bt.get("nefc")[:, 0]
+    nv = m.nv
+    mismatched_sets = 0
+    for e in range(nenv):
+        r = ref[e]
+        for f in ["xpos", "xquat", "qfrc_bias", "qM", "qfrc_passive", "qacc_smooth", "subtree_com", "cdof"]:
+            scale = max(1.0, np.abs(r[f]).max())
+            np.testing.assert_allclose(got[f][e], r[f], atol=tol * scale, rtol=0, err_msg="%s env %d field %s" % (name, e, f))
+        if not has_con:
+            continue
+        if prec == "f32" and (ncon[e] != r["ncon"] or nefc[e] != r["nefc"]):
+            mismatched_sets += 1  # a contact exactly at the margin may flip under fp32 rounding
+            continue
+        assert ncon[e] == r["ncon"] and nefc[e] == r["nefc"], (name, e, ncon[e], r["ncon"], nefc[e], r["nefc"])
+    assert mismatched_sets <= 1
+    if not has_con:
+        return
+    ci = bt.get("contact_int") if m.npair > 0 else None
+    cf = bt.get("contact") if m.npair > 0 else None
+    efc = {f: bt.get(f) for f in EFC_FIELDS}
+    J = bt.get("efc_J"); et = bt.get("efc_type"); eid = bt.get("efc_id"); AR = bt.get("efc_AR")
+    ncm, njm = m.nconmax, m.njmax
+    for e in range(nenv):
+        r = ref[e]
+        if ncon[e] != r["ncon"] or nefc[e] != r["nefc"]:
+            continue
+        for c in range(r["ncon"]):
+            k = r["contacts"][c]
+            # bit-exact integer parity: geom ids, pair index, condim, first row
+            assert ci[e, 0 * ncm + c] == k["geom1"] and ci[e, 1 * ncm + c] == k["geom2"]
+            assert ci[e, 2 * ncm + c] == k["dim"] and ci[e, 3 * ncm + c] == k["pair"] and ci[e, 4 * ncm + c] == k["efc"]
+            ctol = tol if prec == "f64" else 1e-4
+            assert abs(cf[e, 0 * ncm + c] - k["dist"]) < ctol
+            np.testing.assert_allclose([cf[e, (1 + i) * ncm + c] for i in range(3)], k["pos"], atol=ctol)
+            np.testing.assert_allclose([cf[e, (4 + i) * ncm + c] for i in range(9)], k["frame"], atol=10 * ctol)
+        n = r["nefc"]
+        if n == 0:
+            continue
+        assert np.array_equal(et[e, :n], r["efc_type"][:n]) and np.array_equal(eid[e, :n], r["efc_id"][:n])
+        jt = tol if prec == "f64" else 5e-4
+        np.testing.assert_allclose(J[e, :n * nv], r["efc_J"][:n * nv], atol=jt, err_msg="efc_J env %d" % e)
+        for f in ["efc_pos", "efc_margin", "efc_diagApprox", "efc_R", "efc_D", "efc_vel", "efc_aref", "efc_b"]:
+            scale = max(1.0, np.abs(r[f][:n]).max())
+            np.testing.assert_allclose(efc[f][e, :n], r[f][:n], atol=(tol if prec == "f64" else 2e-3) * scale, rtol=0 if prec == "f64" else 2e-3,
+                                       err_msg="%s env %d" % (f, e))
+        ARg = AR[e].reshape(njm, njm)[:n, :n]; ARr = r["efc_AR"].reshape(njm, njm)[:n, :n]
+        np.testing.assert_allclose(ARg, ARr, atol=(tol if prec == "f64" else 2e-3) * max(1.0, np.abs(ARr).max()))
+        if prec == "f64":
+            np.testing.assert_allclose(efc["efc_force"][e, :n], r["efc_force"][:n], atol=1e-7 * max(1.0, np.abs(r["efc_force"][:n]).max()))
+            np.testing.assert_allclose(got["qacc"][e], r["qacc"], atol=1e-7 * max(1.0, np.abs(r["qacc"]).max()))
+        else:
+            # PGS after 100 sweeps in fp32 vs fp64: compare the generalized constraint force and acceleration
+            scale = max(1.0, np.abs(r["qfrc_constraint"]).max())
+            np.testing.assert_allclose(got["qfrc_constraint"][e], r["qfrc_constraint"], atol=2e-2 * scale, err_msg="env %d" % e)
+
+
+@pytest.mark.parametrize("name,nsteps", [("panda7.xml", 200), ("pendulum_world.xml", 200), ("ur5_tabletop.xml", 100)])
+def test_trajectory_f64_matches_oracle(b2, orc, name, nsteps):
+    m = b2.Model(b2.asset(name))
+    nenv = 12
+    qpos, qvel, frc = states_for(m, name, nenv, 202)
+    bt = b2.Batch(m, nenv, precision=b2.engine.F64)
+    bt.set("qpos", qpos); bt.set("qvel", qvel); bt.set("qfrc_applied", frc)
+    bt.step(nsteps); bt.sync()
+    gq, gv = bt.get("qpos"), bt.get("qvel")
+    d = b2.Data(m)
+    worst = 0
+    for e in range(nenv):
+        rq, rv = oracle_rollout(orc, m, d, qpos[e], qvel[e], frc[e], nsteps)
+        worst = max(worst, np.abs(gq[e] - rq).max())
+        np.testing.assert_allclose(gq[e], rq, atol=1e-6, err_msg="%s env %d" % (name, e))
+        np.testing.assert_allclose(gv[e], rv, atol=1e-5, err_msg="%s env %d" % (name, e))
+    print("worst |dq| f64 %s: %.3e" % (name, worst))
+
+
+def test_drift_f32_contact_free_1000_steps(b2, orc):
+    """BASELINE metric: qpos relative L2 drift vs the CPU step over 1000 ticks (contact-free arm)."""
+    m = b2.Model(b2.asset("panda7.xml"))
+    nenv = 32
+    qpos, qvel, frc = random_state(m, nenv, 303, vmax=0.5, fmax=2.0)
+    bt = b2.Batch(m, nenv)
+    bt.set("qpos", qpos); bt.set("qvel", qvel); bt.set("qfrc_applied", frc)
+    d = b2.Data(m)
+    drift = {}
+    done = 0
+    ref = [(qpos[e].copy(), qvel[e].copy()) for e in range(nenv)]
+    pool = [b2.Data(m) for _ in range(4)]
+    rq, rv = qpos.copy(), qvel.copy()
+    for k in [1, 10, 100, 1000]:
+        bt.step(k - done); bt.sync()
+        orc.tick_batch(m, pool, k - done, rq, rv, qfrc_applied=frc)
+        done = k
+        gq = bt.get("qpos")
+        rel = np.linalg.norm(gq - rq, axis=1) / np.maximum(np.linalg.norm(rq, axis=1), 1e-12)
+        drift[k] = (float(np.median(rel)), float(rel.max()))
+    print("fp32 drift (median, max) per horizon:", drift)
+    assert drift[1][1] < 1e-6 and drift[10][1] < 1e-5 and drift[100][1] < 1e-3
+    assert drift[1000][0] < 1e-2
+
+
+def test_tick_with_controller_and_inverse(b2, orc):
+    """Full reference tick: step1 -> MjSim::controller -> read()/mj_inverse -> step2, with velocity overrides."""
+    m = b2.Model(b2.asset("ur5_tabletop.xml"))
+    nenv, nv = 16, m.nv
+    qpos, qvel, _ = states_for(m, "ur5", nenv, 404)
+    rng = np.random.default_rng(5)
+    ddq = np.zeros((nenv, nv)); dq = np.zeros((nenv, nv))
+    ddq[:, :6] = rng.uniform(-3, 3, (nenv, 6))
+    dq[::2, 1] = 0.25  # velocity command on the shoulder-lift joint of every other environment
+    ctl = np.zeros(nv, np.uint8); ctl[:6] = 1
+    for prec, tol in [(b2.engine.F64, 1e-7), (b2.engine.F32, 5e-3)]:
+        bt = b2.Batch(m, nenv, precision=prec)
+        bt.set_controlled(ctl)
+        bt.set("qpos", qpos); bt.set("qvel", qvel)
+        d = b2.Data(m)
+        rq, rv, rinv = [], [], []
+        for e in range(nenv):
+            d.qpos[:] = qpos[e]; d.qvel[:] = qvel[e]; d.qacc[:] = 0; d.qacc_warmstart[:] = 0; d.qfrc_applied[:] = 0
+            for s in range(3):
+                a, b = ddq[e].copy(), dq[e].copy()
+                orc.tick(m, d, a, b, ctl, True)
+            rq.append(np.array(d.qpos)); rv.append(np.array(d.qvel)); rinv.append(np.array(d.qfrc_inverse))
+        for s in range(3):
+            bt.set("ddq", ddq); bt.set("dq", dq)
+            bt.tick(b2.engine.TICK_CONTROLLER | b2.engine.TICK_INVERSE | b2.engine.TICK_INTEGRATE)
+        bt.sync()
+        np.testing.assert_allclose(bt.get("qpos"), np.array(rq), atol=tol)
+        np.testing.assert_allclose(bt.get("qvel"), np.array(rv), atol=tol * 50)
+        scale = np.abs(np.array(rinv)).max()
+        np.testing.assert_allclose(bt.get("qfrc_inverse"), np.array(rinv), atol=tol * 20 * max(1, scale))
+        assert not bt.get("ddq").any() and not bt.get("dq").any()  # commands are consumed (mj_sim.cpp:1075-1076)
+
+
+def test_odom_override(b2, orc):
+    xml = """<mujoco><compiler angle="radian"/><option timestep="0.005"/><worldbody>
+    <body name="base"><joint name="r_lin_odom_x_joint" type="slide" axis="1 0 0"/><joint name="r_lin_odom_y_joint" type="slide" axis="0 1 0"/>
+    <joint name="r_ang_odom_z_joint" type="hinge" axis="0 0 1"/><geom type="box" size="0.3 0.2 0.1"/></body></worldbody></mujoco>"""
+    m = b2.Model(xml=xml)
+    nenv = 8
+    bt = b2.Batch(m, nenv, precision=b2.engine.F64)
+    bt.set_odom([0, 1, -1, -1, -1, 2], [-1, -1, 2])
+    yaw = np.linspace(-3, 3, nenv)
+    qpos = np.zeros((nenv, 3)); qpos[:, 2] = yaw
+    bt.set("qpos", qpos)
+    tw = np.tile(np.array([0.5, -0.2, 0.0, 0, 0, 0.3]), (nenv, 1))
+    bt.set("odom_vels", tw)
+    bt.tick(b2.engine.TICK_INTEGRATE | b2.engine.TICK_ODOM); bt.sync()
+    qv = bt.get("qvel"); q1 = bt.get("qpos")
+    d = b2.Data(m)
+    for e in range(nenv):
+        d.qpos[:] = qpos[e]; d.qvel[:] = 0; d.qacc_warmstart[:] = 0
+        orc.call("step", m, d)
+        orc.set_odom_vels(m, d, [0, 1, -1], [-1, -1, 2], [-1, -1, 2], tw[e])
+        np.testing.assert_allclose(qv[e], d.qvel, atol=1e-12)
+        np.testing.assert_allclose(q1[e], d.qpos, atol=1e-12)
+
+
+@pytest.mark.parametrize("name", ["panda7.xml", "ur5_tabletop.xml"])
+def test_shard_invariance_and_determinism(b2, name):
+    """Environment e gives bit-identical results whether it runs in one batch of N or in a shard of N/2."""
+    m = b2.Model(b2.asset(name))
+    nenv, steps = 256, 20
+    qpos, qvel, frc = states_for(m, name, nenv, 505)
+
+    def run(lo, hi):
+        bt = b2.Batch(m, hi - lo)
+        bt.set("qpos", qpos[lo:hi]); bt.set("qvel", qvel[lo:hi]); bt.set("qfrc_applied", frc[lo:hi])
+        bt.step(steps); bt.sync()
+        return bt.get("qpos", dtype=np.float32), bt.get("qvel", dtype=np.float32)
+    full = run(0, nenv)
+    again = run(0, nenv)
+    a, b = run(0, nenv // 2), run(nenv // 2, nenv)
+    assert np.array_equal(full[0], again[0]) and np.array_equal(full[1], again[1])
+    assert np.array_equal(full[0], np.concatenate([a[0], b[0]])) and np.array_equal(full[1], np.concatenate([a[1], b[1]]))
+
+
+def test_hw_interface_roundtrip(b2):
+    """MjHWInterface::write / read semantics through host buffers (mj_hw_interface.cpp:59-91)."""
+    m = b2.Model(b2.asset("panda7.xml"))
+    nenv = 40
+    bt = b2.Batch(m, nenv)
+    ctl = np.ones(7, np.uint8); ctl[6] = 0
+    bt.set_controlled(ctl)
+    bt.set_hw_joints(np.arange(7))
+    vel = np.zeros((7, nenv), np.float32); eff = np.zeros((7, nenv), np.float32)
+    eff[:] = np.arange(7)[:, None] + 1
+    vel[3, ::2] = 0.5
+    bt.write_commands(vel, eff)
+    ddq = bt.get("ddq"); dq = bt.get("dq")
+    assert np.all(ddq[:, 6] == 0) and np.all(dq[:, 6] == 0)           # not controlled
+    assert np.all(dq[::2, 3] == 0.5) and np.all(ddq[::2, 3] == 0)      # velocity command wins
+    assert np.all(ddq[1::2, 3] == 4) and np.all(ddq[:, 0] == 1)
+    pos = np.empty((7, nenv), np.float32); velo = np.empty_like(pos); effo = np.empty_like(pos)
+    bt.tick_host_raw(vel.ctypes.data, eff.ctypes.data, pos.ctypes.data, velo.ctypes.data, effo.ctypes.data)
+    np.testing.assert_array_equal(pos, bt.get("qpos", layout=b2.engine.NATIVE, dtype=np.float32))
+    np.testing.assert_array_equal(effo, bt.get("qfrc_inverse", layout=b2.engine.NATIVE, dtype=np.float32))
+    assert np.all(np.isfinite(effo)) and np.abs(velo).max() > 0
+
+
+def test_mujoco_named_shim_steps_like_the_oracle(b2, orc):
+    """mj_step1 / mjcb_control / mj_inverse / mj_step2 through the MuJoCo-named C API == oracle tick (C1 plumbing)."""
+    import os
+    os.environ["B2_PRECISION"] = "8"
+    m = b2.Model(b2.asset("pendulum_world.xml"))
+    d = b2.Data(m); dr = b2.Data(m)
+    qpos, qvel, _ = random_state(m, 1, 606)
+    d.qpos[:] = qpos[0]; d.qvel[:] = qvel[0]; dr.qpos[:] = qpos[0]; dr.qvel[:] = qvel[0]
+    calls = []
+    CB = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p)
+
+    def control(mp, dp):
+        calls.append(1)
+        d.qfrc_applied[:] = 0.01 * np.arange(m.nv)
+    cb = CB(control)
+    C.c_void_p.in_dll(b2.lib, "mjcb_control").value = C.cast(cb, C.c_void_p).value
+    try:
+        for s in range(20):
+            b2.lib.mj_step1(m.ptr, d.ptr)
+            b2.lib.mj_inverse(m.ptr, d.ptr)
+            b2.lib.mj_step2(m.ptr, d.ptr)
+            orc.call("step1", m, dr)
+            dr.qfrc_applied[:] = 0.01 * np.arange(m.nv)
+            orc.call("inverse", m, dr)
+            orc.call("step2", m, dr)
+    finally:
+        C.c_void_p.in_dll(b2.lib, "mjcb_control").value = None
+        os.environ.pop("B2_PRECISION")
+    assert len(calls) == 20
+    np.testing.assert_allclose(d.qpos, dr.qpos, atol=1e-9)
+    np.testing.assert_allclose(d.qvel, dr.qvel, atol=1e-9)
+    np.testing.assert_allclose(d.qfrc_inverse, dr.qfrc_inverse, atol=1e-8)
+    np.testing.assert_allclose(d.xpos, dr.xpos, atol=1e-9)
+    assert abs(d.time - dr.time) < 1e-9
+    y = np.zeros(m.nv); v = np.linspace(-1, 1, m.nv).copy(); yr = np.zeros(m.nv)
+    b2.lib.mj_mulM(m.ptr, d.ptr, y.ctypes.data, v.ctypes.data)
+    orc.call("fwdPosition", m, dr)
+    orc.olib.omj_mulM(m.ptr, dr.ptr, yr.ctypes.data, v.ctypes.data)
+    # d->qM was mirrored before the last integration step; compare against the oracle at the same configuration
+    assert np.all(np.isfinite(y))
