@@ -1,0 +1,299 @@
+#!/usr/bin/env python
+"""bench.py — env-steps/s of the batched rigid-body tick (BASELINE.json metric) on N B200 GPUs of one node.
+
+  python bench.py --gpus N --steps K --warmup W [--config c2|c3] [--nenv E] [--impl reference]
+
+One "step" = one control tick (write -> mj_step1 + controller -> read/mj_inverse -> mj_step2, reference
+src/mj_main.cpp:82-112) of every environment of the batch.  N > 1 is launched by torchrun, one rank per GPU; the
+environments shard across ranks with no data-path collective, torch.distributed (NCCL) is
+used only for the barriers and the max-over-ranks reduction of the device time.  Rank 0 prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC, UNIT = "env_steps_per_sec", "env-steps/s"
+SETTLE_TICKS = {"c1": 0, "c2": 0, "c3": 150}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def b_alg(model, ncon_mean):
+    """Algorithmic HBM bytes per env-step, fp32 SoA:
+    read {qpos, qvel, qfrc_applied, qacc_warmstart, ddq, dq} + write {qpos, qvel, qacc, qacc_warmstart, qfrc_bias,
+    qfrc_inverse} = 2 nq + 8 nv floats, + write {xpos, xquat} = 7 nbody floats, + 72 B per contact."""
+    return 4 * (2 * model.nq + 8 * model.nv + 7 * model.nbody) + 72.0 * ncon_mean
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu):
+        self.gpu, self.rows, self.proc = gpu, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_reference(cfg, nenv_sample, steps, warmup, threads=None):
+    """The reference's CPU path for this tick, restated by the fp64 oracle (libmujoco is not available: SURVEY 8c),
+    on `threads` host threads (default: all).  Returns (env-steps/s, threads used, description)."""
+    import mujoco_sim_b200 as b2
+    from mujoco_sim_b200 import workloads as w
+    from oracle import pyoracle as orc
+    asset = w.CONFIGS[cfg][0]
+    m = b2.Model(b2.asset(asset))
+    threads = threads or os.cpu_count() or 1
+    threads = max(1, min(threads, nenv_sample))
+    pool = [b2.Data(m) for _ in range(threads)]
+    qpos, qvel, frc = w.config_state(cfg, m, np.arange(nenv_sample))
+    qpos = np.ascontiguousarray(qpos); qvel = np.ascontiguousarray(qvel)
+    ws = np.zeros((nenv_sample, m.nv))
+    ddq = np.ascontiguousarray(0.1 * frc)
+    dq = np.zeros((nenv_sample, m.nv))
+    ctl = np.ones(m.nv, np.uint8)
+    settle = SETTLE_TICKS[cfg]
+    if settle:
+        orc.tick_batch(m, pool, settle, qpos, qvel, ws, None, ddq, dq, ctl, True)
+    if warmup:
+        orc.tick_batch(m, pool, warmup, qpos, qvel, ws, None, ddq, dq, ctl, True)
+    t0 = time.perf_counter()
+    used = orc.tick_batch(m, pool, steps, qpos, qvel, ws, None, ddq, dq, ctl, True)
+    dt = time.perf_counter() - t0
+    return nenv_sample * steps / dt, used, dt
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--config", default=os.environ.get("B2_BENCH_CONFIG", "c2"), choices=["c2", "c3"])
+    ap.add_argument("--nenv", type=int, default=0, help="environments per GPU (default: the config's)")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-flush", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    from mujoco_sim_b200 import workloads as w
+    asset, nenv_default, desc = w.CONFIGS[args.config]
+    nenv = args.nenv or nenv_default
+
+    if args.impl == "reference":
+        # the reference arm: the CPU tick on the box's host cores, rank 0 only
+        if rank != 0:
+            return
+        sample = nenv  # the whole batch per step: the CPU tick is fast enough for the full configuration
+        val, used, dt = cpu_reference(args.config, sample, args.steps, args.warmup)
+        out = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+               "data": "synthetic",
+               "config": {"workload": "%s: %s" % (args.config, desc), "model": asset, "envs_per_step": sample, "timestep": 0.005,
+                          "tick": "step1+controller+inverse+step2"},
+               "cpu_baseline": {"value": val, "unit": UNIT, "cores": used, "kind": "port",
+                                "sample": "%d envs x %d ticks of the same workload; fp64 oracle restatement of MuJoCo 2.3.7 semantics (libmujoco unavailable)" % (sample, args.steps)},
+               "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(out))
+        return
+
+    import torch
+    import mujoco_sim_b200 as b2
+    if not torch.cuda.is_available() or b2.lib.b2_device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device (the engine has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    m = b2.Model(b2.asset(asset))
+    bt = b2.Batch(m, nenv, device=local_rank, precision=b2.engine.F32)
+    env_offset = rank * nenv  # contiguous shards of one global batch
+    w.load_config(args.config, bt, env_offset=env_offset)
+    nv = m.nv
+    # every scalar joint is a ros_control joint; all of them are "controlled" (PD computed-torque on every joint)
+    jt = np.array(m.jnt_type)
+    hw = np.where(jt >= 2)[0].astype(np.int32)
+    ctl = np.zeros(nv, np.uint8)
+    ctl[np.array(m.jnt_dofadr)[hw]] = 1
+    bt.set_controlled(ctl)
+    bt.set_hw_joints(hw)
+    nhw = hw.size
+    # commands: desired accelerations ddq = 0.1 * (the config's random torques) on the controlled joints, no velocity commands
+    _, _, frc = w.config_state(args.config, m, np.arange(env_offset, env_offset + nenv))
+    eff_cmd = torch.from_numpy(np.ascontiguousarray((0.1 * frc[:, np.array(m.jnt_dofadr)[hw]]).T.astype(np.float32))).pin_memory()
+    vel_cmd = torch.zeros((nhw, nenv), dtype=torch.float32).pin_memory()
+    pos_o = torch.empty((nhw, nenv), dtype=torch.float32).pin_memory()
+    vel_o = torch.empty_like(pos_o).pin_memory()
+    eff_o = torch.empty_like(pos_o).pin_memory()
+    host_args = (vel_cmd.data_ptr(), eff_cmd.data_ptr(), pos_o.data_ptr(), vel_o.data_ptr(), eff_o.data_ptr())
+    bt.tick_host_raw(*host_args)  # uploads the commands once: they stay resident for the device-timed loop
+
+    stream = torch.cuda.ExternalStream(bt.stream, device=torch.device("cuda", local_rank))
+    flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def do_flush():
+        if flush is not None:
+            with torch.cuda.stream(stream):
+                flush.fill_(1)  # 256 MiB > 126 MB L2: evicts the batch state between timed steps
+
+    # settle (contacts form) + warm-up, untimed
+    for _ in range(SETTLE_TICKS[args.config] + args.warmup):
+        bt.tick_resident()
+    bt.sync()
+    ncon_mean = float(bt.get("ncon").mean()) if m.npair > 0 else 0.0
+    nefc_mean = float(bt.get("nefc").mean())
+
+    # ---- device-timed region: K steps, inputs resident in HBM, CUDA events on the launching stream ----
+    K = args.steps
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    sampler = ClockSampler(local_rank)
+    l0 = bt.launch_count
+    barrier(); torch.cuda.synchronize(); bt.sync()
+    sampler.start()
+    bt.profile_begin(K)
+    for k in range(K):
+        do_flush()
+        with torch.cuda.stream(stream):
+            starts[k].record()
+        bt.tick_resident()
+        with torch.cuda.stream(stream):
+            ends[k].record()
+    bt.sync(); torch.cuda.synchronize()
+    nprof, slot_ms = bt.profile_end()
+    clocks = sampler.stop()
+    barrier()
+    launches = bt.launch_count - l0
+    dev_ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
+    t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    max_ms = float(t.item())
+
+    # ---- end to end: the same tick through the C ABI with HOST buffers (H2D commands, D2H joint states) ----
+    e2e_s = 0.0
+    barrier()
+    for k in range(K):
+        do_flush()
+        bt.sync()
+        t0 = time.perf_counter()
+        bt.tick_host_raw(*host_args)
+        e2e_s += time.perf_counter() - t0
+    t2 = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    e2e_max = float(t2.item())
+    _ = float(pos_o.sum())  # the result is read on the host
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    total_envs = nenv * world
+    value = total_envs * K / (max_ms * 1e-3)
+    peak, peak_src = peaks()
+    # dominant kernel = the slot with the largest device time
+    kern = {k: v for k, v in slot_ms.items() if k not in ("hw_write", "hw_read")}
+    dom = max(kern, key=kern.get)
+    dom_ms = kern[dom] / max(1, nprof)
+    balg = b_alg(m, ncon_mean)
+    achieved = balg * nenv / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic_%s.json" % args.config)
+    if os.path.exists(tp):
+        try:
+            with open(tp) as f:
+                traffic = json.load(f).get(dom)
+        except Exception:
+            traffic = None
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
+        "ms_per_step": max_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "%s: %s" % (args.config, desc), "model": asset, "envs_per_gpu": nenv, "envs_total": total_envs,
+                   "timestep": 0.005, "tick": "write+step1+controller+inverse+step2+read", "mean_ncon": ncon_mean, "mean_nefc": nefc_mean,
+                   "l2": "flushed before every timed step (256 MiB fill)" if flush is not None else "not flushed",
+                   "solver": "PGS, %d iterations max" % int(m.int("opt.iterations"))},
+        "roofline": {"bound": "hbm", "kernel": "k_" + dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_env_step": balg,
+                     "kernel_ms": dom_ms, "kernel_share_of_step": kern[dom] / max(1e-12, sum(slot_ms.values())),
+                     "kernel_ms_all": {k: v / max(1, nprof) for k, v in slot_ms.items()}},
+        "e2e": {"value": total_envs * K / e2e_max, "unit": UNIT, "h2d_bytes_per_step": int(2 * nhw * nenv * 4 * world),
+                "d2h_bytes_per_step": int(3 * nhw * nenv * 4 * world), "ms_per_step": 1e3 * e2e_max / K},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+    }
+    if not args.no_cpu_baseline and world == 1:
+        sample = {"c2": 4096, "c3": 2048}[args.config]
+        csteps = {"c2": 2000, "c3": 1500}[args.config]  # about 10 s of CPU work on 8 cores
+        val, used, dt = cpu_reference(args.config, sample, csteps, 3)
+        out["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": used, "kind": "port",
+                               "sample": "%d envs x %d ticks of the same workload in %.1f s; fp64 oracle restatement of MuJoCo 2.3.7 semantics "
+                                         "(libmujoco is not available)" % (sample, csteps, dt)}
+    print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -94,6 +94,15 @@ int b2_read_joints(b2_batch* b, float* pos_host, float* vel_host, float* effort_
 int b2_tick_host(b2_batch* b, const float* vel_cmd_host, const float* effort_cmd_host, float* pos_host, float* vel_host,
                  float* effort_host);
 
+/* the same control tick with the command buffers of the last upload re-issued from HBM and the joint states left in
+ * HBM: no host<->device traffic, asynchronous (throughput with resident inputs) */
+int b2_tick_resident(b2_batch* b);
+
+/* per-kernel device timing with CUDA events on the batch's stream: profile up to max_ticks ticks, then read the summed
+ * milliseconds per kernel slot {hw_write, smooth, collide, make_constraint, project, pgs, integrate, hw_read} */
+int b2_profile_begin(b2_batch* b, int max_ticks);
+int b2_profile_end(b2_batch* b, double* ms_per_slot, int nslot);
+
 /* copy environment `env` into the legacy single-environment mjData view (fields of SURVEY.md Appendix C) */
 int b2_mirror_env(b2_batch* b, int env, mjData* d);
 /* load environment `env` from an mjData (qpos qvel qacc qacc_warmstart qfrc_applied xfrc_applied mocap time) */

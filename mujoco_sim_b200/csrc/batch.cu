@@ -62,7 +62,21 @@ struct b2_batch {
   int nhw = 0;
   int *hw_qadr = nullptr, *hw_dadr = nullptr, *hw_ctl = nullptr;
   float* hw_buf = nullptr;  // [5][nhw][nenv] fp32 staging: vel_cmd, effort_cmd, pos, vel, effort
+  // per-kernel CUDA-event profiling (b2_profile_begin / b2_profile_end)
+  std::vector<cudaEvent_t> prof_ev;  // [max_ticks][B2_NSLOT + 1]
+  std::vector<unsigned> prof_mask;   // which boundary events of each tick were recorded
+  int prof_max = 0, prof_n = 0;
+  bool prof_on = false;
+  int prof_tick_open = -1;
 };
+
+enum { SLOT_HW_WRITE = 0, SLOT_SMOOTH, SLOT_COLLIDE, SLOT_MAKE, SLOT_PROJECT, SLOT_PGS, SLOT_INTEGRATE, SLOT_HW_READ, B2_NSLOT };
+// record the boundary event that precedes kernel slot `slot` of the tick being profiled
+static inline void prof_mark(b2_batch* b, int slot) {
+  if (!b->prof_on || b->prof_tick_open < 0) return;
+  cudaEventRecord(b->prof_ev[(size_t)b->prof_tick_open * (B2_NSLOT + 1) + slot], b->stream);
+  b->prof_mask[b->prof_tick_open] |= 1u << slot;
+}
 
 namespace {
 using namespace b2;
@@ -229,6 +243,7 @@ int run_tick(b2_batch* b, int flags) {
   const int per_sm = std::max<size_t>(1, (227 * 1024) / std::max<size_t>(1, b->smooth_smem));
   const int grid = std::max(1, std::min(ntiles, b->nsm * per_sm));
   int rc;
+  prof_mark(b, SLOT_SMOOTH);
   switch (b->smooth_block) {
     case 128: rc = launch_smooth<T, 128>(b, a, grid); break;
     case 64: rc = launch_smooth<T, 64>(b, a, grid); break;
@@ -240,23 +255,47 @@ int run_tick(b2_batch* b, int flags) {
     const int nt = b->nenvp / BL;
     const int g2 = std::max(1, std::min(nt, b->nsm * 4));
     const size_t sm = b->blob_smem;
+    prof_mark(b, SLOT_COLLIDE);
     k_collide<T, BL><<<g2, BL, sm, b->stream>>>(a);
+    prof_mark(b, SLOT_MAKE);
     k_make_constraint<T, BL><<<g2, BL, sm, b->stream>>>(a);
     b->launches += 2;
     if (!(flags & B2_TICK_NOSOLVE)) {
+      prof_mark(b, SLOT_PROJECT);
       k_project<T, BL><<<g2, BL, sm, b->stream>>>(a);
+      prof_mark(b, SLOT_PGS);
       k_pgs<T, BL><<<g2, BL, sm, b->stream>>>(a);
+      prof_mark(b, SLOT_INTEGRATE);
       k_integrate<T, BL><<<g2, BL, sm, b->stream>>>(a);
       b->launches += 3;
     }
   }
+  prof_mark(b, SLOT_HW_READ);
   CK(cudaGetLastError());
   return 0;
 }
 
+// a profiled tick records B2_NSLOT + 1 boundary events; slots that do not run collapse to zero duration
+static bool prof_open(b2_batch* b) {
+  if (!b->prof_on || b->prof_tick_open >= 0 || b->prof_n >= b->prof_max) return false;
+  b->prof_tick_open = b->prof_n;
+  return true;
+}
+static void prof_close(b2_batch* b) {
+  if (b->prof_tick_open < 0) return;
+  cudaEventRecord(b->prof_ev[(size_t)b->prof_tick_open * (B2_NSLOT + 1) + B2_NSLOT], b->stream);
+  b->prof_mask[b->prof_tick_open] |= 1u << B2_NSLOT;
+  b->prof_tick_open = -1;
+  b->prof_n++;
+}
+
 int tick_dispatch(b2_batch* b, int flags) {
   CK(cudaSetDevice(b->device));
-  return b->prec == 8 ? run_tick<double>(b, flags) : run_tick<float>(b, flags);
+  const bool mine = prof_open(b);
+  if (mine) prof_mark(b, SLOT_HW_WRITE);
+  const int rc = b->prec == 8 ? run_tick<double>(b, flags) : run_tick<float>(b, flags);
+  if (mine) prof_close(b);
+  return rc;
 }
 
 // ---- host <-> device field transfer with layout / precision conversion ----
@@ -535,6 +574,7 @@ void b2_destroy(b2_batch* b) {
   if (b->hw_dadr) cudaFree(b->hw_dadr);
   if (b->hw_ctl) cudaFree(b->hw_ctl);
   if (b->hw_buf) cudaFree(b->hw_buf);
+  for (cudaEvent_t e : b->prof_ev) cudaEventDestroy(e);
   if (b->stream) cudaStreamDestroy(b->stream);
   delete b;
 }
@@ -684,8 +724,9 @@ static int hw_write_async(b2_batch* b, const float* vel, const float* eff) {
   const size_t n = (size_t)b->nhw * b->nenv;
   float* dv = b->hw_buf;
   float* de = b->hw_buf + n;
-  CK(cudaMemcpyAsync(dv, vel, n * 4, cudaMemcpyHostToDevice, b->stream));
-  CK(cudaMemcpyAsync(de, eff, n * 4, cudaMemcpyHostToDevice, b->stream));
+  // NULL host pointers: the command buffers already resident in HBM (from the previous upload) are re-issued
+  if (vel) CK(cudaMemcpyAsync(dv, vel, n * 4, cudaMemcpyHostToDevice, b->stream));
+  if (eff) CK(cudaMemcpyAsync(de, eff, n * 4, cudaMemcpyHostToDevice, b->stream));
   const int th = 256, bl = (int)((n + th - 1) / th);
   if (b->prec == 8) k_hw_write<double><<<bl, th, 0, b->stream>>>((double*)b->fields["ddq"].ptr, (double*)b->fields["dq"].ptr, dv, de, b->hw_dadr, b->hw_ctl, b->nhw, b->nenv, b->nenvp);
   else k_hw_write<float><<<bl, th, 0, b->stream>>>((float*)b->fields["ddq"].ptr, (float*)b->fields["dq"].ptr, dv, de, b->hw_dadr, b->hw_ctl, b->nhw, b->nenv, b->nenvp);
@@ -723,19 +764,69 @@ int b2_read_joints(b2_batch* b, float* pos, float* vel, float* eff) {
   return 0;
 }
 
-// One control tick as the reference's loop body sees it (src/mj_main.cpp:82-112), with host buffers:
-// write(commands of the previous update) -> step1 + controller -> read (mj_inverse) -> step2 -> odom; joint states out.
+// One control tick as the reference's loop body sees it (src/mj_main.cpp:82-112):
+// write(commands) -> step1 + controller -> read (mj_inverse) -> step2 -> odom; joint states out.
 // Note on order: the reference reads the joint state between mj_step1 and mj_step2 (pre-integration qpos/qvel,
 // qfrc_inverse of this tick); the gather here returns qfrc_inverse of this tick and the post-integration qpos/qvel,
 // i.e. exactly what read() of the NEXT tick would return for positions and velocities.
+static int tick_hw(b2_batch* b, const float* vel, const float* eff, float* pos, float* velo, float* effo, bool sync) {
+  CK(cudaSetDevice(b->device));
+  const bool mine = prof_open(b);
+  if (mine) prof_mark(b, SLOT_HW_WRITE);
+  int rc = hw_write_async(b, vel, eff);
+  if (rc == 0) rc = tick_dispatch(b, (b->tick_flags & ~(1 << 30)) | B2_TICK_INTEGRATE | B2_TICK_CONTROLLER | B2_TICK_INVERSE);
+  if (rc == 0) rc = hw_read_async(b, pos, velo, effo);
+  if (mine) prof_close(b);
+  if (rc < 0) return rc;
+  if (sync) CK(cudaStreamSynchronize(b->stream));
+  return 0;
+}
+// host buffers in, host buffers out, synchronised (the end-to-end path)
 int b2_tick_host(b2_batch* b, const float* vel, const float* eff, float* pos, float* velo, float* effo) {
   if (!b || !vel || !eff) return fail("b2_tick_host: null argument");
+  return tick_hw(b, vel, eff, pos, velo, effo, true);
+}
+// same tick with the commands already resident in HBM and the joint states left in HBM (asynchronous)
+int b2_tick_resident(b2_batch* b) {
+  if (!b) return fail("b2_tick_resident: null batch");
+  return tick_hw(b, nullptr, nullptr, nullptr, nullptr, nullptr, false);
+}
+
+int b2_profile_begin(b2_batch* b, int max_ticks) {
+  if (!b || max_ticks < 1) return fail("b2_profile_begin: bad argument");
   CK(cudaSetDevice(b->device));
-  if (hw_write_async(b, vel, eff) < 0) return -1;
-  if (tick_dispatch(b, (b->tick_flags & ~(1 << 30)) | B2_TICK_INTEGRATE | B2_TICK_CONTROLLER | B2_TICK_INVERSE) < 0) return -1;
-  if (hw_read_async(b, pos, velo, effo) < 0) return -1;
-  CK(cudaStreamSynchronize(b->stream));
+  const size_t need = (size_t)max_ticks * (B2_NSLOT + 1);
+  while (b->prof_ev.size() < need) {
+    cudaEvent_t e;
+    CK(cudaEventCreate(&e));
+    b->prof_ev.push_back(e);
+  }
+  b->prof_mask.assign(max_ticks, 0u);
+  b->prof_max = max_ticks; b->prof_n = 0; b->prof_on = true; b->prof_tick_open = -1;
   return 0;
+}
+// ms[slot] = summed device time of kernel slot over the profiled ticks (slots: hw_write, smooth, collide,
+// make_constraint, project, pgs, integrate, hw_read); returns the number of ticks profiled
+int b2_profile_end(b2_batch* b, double* ms, int nslot) {
+  if (!b || !ms) return fail("b2_profile_end: null argument");
+  CK(cudaSetDevice(b->device));
+  CK(cudaStreamSynchronize(b->stream));
+  b->prof_on = false;
+  for (int s = 0; s < nslot; s++) ms[s] = 0;
+  for (int t = 0; t < b->prof_n; t++) {
+    // boundary events that were not recorded this tick are skipped by walking to the next recorded one
+    const size_t base = (size_t)t * (B2_NSLOT + 1);
+    int prev = -1;
+    for (int s = 0; s <= B2_NSLOT; s++) {
+      if (!(b->prof_mask[t] & (1u << s))) continue;
+      if (prev >= 0 && prev < nslot) {
+        float dt = 0;
+        if (cudaEventElapsedTime(&dt, b->prof_ev[base + prev], b->prof_ev[base + s]) == cudaSuccess) ms[prev] += dt; else cudaGetLastError();
+      }
+      prev = s;
+    }
+  }
+  return b->prof_n;
 }
 
 int b2_mirror_env(b2_batch* b, int env, mjData* d) {

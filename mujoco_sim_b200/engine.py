@@ -84,6 +84,9 @@ _sig = {
     "b2_write_commands": (_i, [_vp, _vp, _vp]),
     "b2_read_joints": (_i, [_vp, _vp, _vp, _vp]),
     "b2_tick_host": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "b2_tick_resident": (_i, [_vp]),
+    "b2_profile_begin": (_i, [_vp, _i]),
+    "b2_profile_end": (_i, [_vp, _vp, _i]),
     "b2_mirror_env": (_i, [_vp, _i, _vp]),
     "b2_load_env": (_i, [_vp, _i, _vp]),
     "b2_shim_batch": (_vp, [_vp, _vp]),
@@ -321,6 +324,20 @@ class Batch:
 
     def tick_host_raw(self, vel_ptr, eff_ptr, pos_ptr, velo_ptr, effo_ptr):
         self._ck(lib.b2_tick_host(self.ptr, vel_ptr, eff_ptr, pos_ptr, velo_ptr, effo_ptr), "b2_tick_host")
+
+    def tick_resident(self):
+        self._ck(lib.b2_tick_resident(self.ptr), "b2_tick_resident")
+
+    PROFILE_SLOTS = ["hw_write", "smooth", "collide", "make_constraint", "project", "pgs", "integrate", "hw_read"]
+
+    def profile_begin(self, max_ticks):
+        self._ck(lib.b2_profile_begin(self.ptr, int(max_ticks)), "b2_profile_begin")
+
+    def profile_end(self):
+        """-> (ticks profiled, {slot: summed ms})"""
+        ms = np.zeros(len(self.PROFILE_SLOTS))
+        n = self._ck(lib.b2_profile_end(self.ptr, ms.ctypes.data, ms.size), "b2_profile_end")
+        return n, dict(zip(self.PROFILE_SLOTS, ms.tolist()))
 
     def mirror_env(self, env, data):
         self._ck(lib.b2_mirror_env(self.ptr, env, data.ptr), "b2_mirror_env")
