@@ -51,6 +51,7 @@ struct b2_batch {
   std::vector<void*> allocs;
   int tick_flags = 0;
   bool fused = false, ws_global = false, export_stages = false;
+  int wp = 16, epl = 2;  // solver team: 8 lanes x epl elements cover the compact row width
   int smooth_block = 32;
   size_t smooth_smem = 0, blob_smem = 0;
   void* stage_dev = nullptr;
@@ -81,6 +82,12 @@ static inline void prof_mark(b2_batch* b, int slot) {
 namespace {
 using namespace b2;
 
+// last dof on the chain from body i to the world (-1: the body is welded to the world)
+int lastdof_of(const mjModel* m, int i) {
+  while (i > 0 && m->body_dofnum[i] == 0) i = m->body_parentid[i];
+  return i > 0 ? m->body_dofadr[i] + m->body_dofnum[i] - 1 : -1;
+}
+
 // ---- model packing ----
 int pack_model(b2_batch* b) {
   const mjModel* m = b->m;
@@ -90,6 +97,23 @@ int pack_model(b2_batch* b) {
   h.nq = m->nq; h.nv = m->nv; h.nbody = m->nbody; h.njnt = m->njnt; h.ngeom = m->ngeom; h.nM = m->nM; h.neq = m->neq;
   h.npair = m->npair; h.nconmax = std::max(1, m->nconmax); h.njmax = std::max(1, m->njmax); h.nmocap = m->nmocap;
   h.nodom = (int)b->odom_qpos.size() / 3;
+  // kinematic trees: children of the world that carry dofs somewhere below them; their dofs are contiguous
+  std::vector<int> body_tree(m->nbody, -1), dof_tree(m->nv, -1), tree_adr, tree_num;
+  {
+    std::vector<int> root_tree(m->nbody, -1);
+    for (int d = 0; d < m->nv; d++) {
+      const int root = m->body_rootid[m->dof_bodyid[d]];
+      if (root_tree[root] < 0) { root_tree[root] = (int)tree_adr.size(); tree_adr.push_back(d); tree_num.push_back(0); }
+      dof_tree[d] = root_tree[root];
+      tree_num[root_tree[root]] = d - tree_adr[root_tree[root]] + 1;
+    }
+    for (int i = 1; i < m->nbody; i++) body_tree[i] = lastdof_of(m, i) >= 0 ? root_tree[m->body_rootid[i]] : -1;
+    std::vector<int> sz(tree_num);
+    std::sort(sz.begin(), sz.end(), [](int x, int y) { return x > y; });
+    h.ntree = (int)tree_adr.size();
+    h.wmax = std::max(1, (sz.size() > 0 ? sz[0] : 0) + (sz.size() > 1 ? sz[1] : 0));
+  }
+  const int ntree = h.ntree;
   h.disableflags = b->opt_disableflags; h.enableflags = m->opt.enableflags; h.iterations = b->opt_iterations;
   for (int k = 0; k < 3; k++) h.gravity[k] = (float)m->opt.gravity[k];
   h.tolerance = (float)b->opt_tolerance; h.meaninertia = (float)m->stat.meaninertia; h.impratio = (float)m->opt.impratio;
@@ -143,6 +167,10 @@ int pack_model(b2_batch* b) {
     if (!std::strcmp(name, "dof_controlled")) { put_int(o, ctl.data(), n); return 0; }
     if (!std::strcmp(name, "odom_dof")) { put_int(o, b->odom_dof.data(), n); return 0; }
     if (!std::strcmp(name, "odom_qpos")) { put_int(o, b->odom_qpos.data(), n); return 0; }
+    if (!std::strcmp(name, "body_treeid")) { put_int(o, body_tree.data(), n); return 0; }
+    if (!std::strcmp(name, "dof_treeid")) { put_int(o, dof_tree.data(), n); return 0; }
+    if (!std::strcmp(name, "tree_dofadr")) { put_int(o, tree_adr.data(), n); return 0; }
+    if (!std::strcmp(name, "tree_dofnum")) { put_int(o, tree_num.data(), n); return 0; }
     if (!std::strcmp(name, "opt_real")) {
       const double v[8] = {m->opt.gravity[0], m->opt.gravity[1], m->opt.gravity[2], b->opt_tolerance, m->stat.meaninertia, m->opt.impratio, 0, 0};
       put_real(o, v, 8);
@@ -161,7 +189,7 @@ int pack_model(b2_batch* b) {
 #define X(name, kind, count) if (fill(#name, h.o_##name, (count), #kind[0] == 'F') < 0) return -1;
   B2_MODEL_ARRAYS(X)
 #undef X
-  (void)neq; (void)npair; (void)nodom; (void)ngeom;
+  (void)neq; (void)npair; (void)nodom; (void)ngeom; (void)ntree;
   return 0;
 }
 
@@ -207,10 +235,10 @@ KArgs<T> make_args(b2_batch* b, int flags) {
   a.qfrc_smooth = R("qfrc_smooth"); a.qacc_smooth = R("qacc_smooth"); a.qfrc_constraint = R("qfrc_constraint");
   a.ws = R("_ws");
   a.con = R("contact"); a.coni = I("contact_int"); a.ncon = I("ncon"); a.nefc = I("nefc"); a.efc_type = I("efc_type");
-  a.efc_id = I("efc_id"); a.efc_J = R("efc_J"); a.efc_pos = R("efc_pos"); a.efc_margin = R("efc_margin");
+  a.efc_id = I("efc_id"); a.efc_tree = I("efc_tree"); a.efc_J = R("efc_J"); a.efc_pos = R("efc_pos"); a.efc_margin = R("efc_margin");
   a.efc_frictionloss = R("efc_frictionloss"); a.efc_diagApprox = R("efc_diagApprox"); a.efc_R = R("efc_R"); a.efc_D = R("efc_D");
   a.efc_KBI = R("efc_KBI"); a.efc_vel = R("efc_vel"); a.efc_aref = R("efc_aref"); a.efc_b = R("efc_b"); a.efc_force = R("efc_force");
-  a.efc_MiJT = R("efc_MiJT"); a.efc_AR = R("efc_AR"); a.solver_iter = I("solver_iter"); a.status = I("status");
+  a.efc_ARdiag = R("efc_ARdiag"); a.efc_rows = R("efc_rows"); a.efc_meta = R("efc_meta"); a.wp = b->wp; a.solver_iter = I("solver_iter"); a.status = I("status");
   return a;
 }
 
@@ -235,6 +263,7 @@ int run_tick(b2_batch* b, int flags) {
   if (flags & B2_TICK_INTEGRATE) kf |= B2F_INTEGRATE;
   if ((flags & B2_TICK_ODOM) && b->hdr.nodom > 0) kf |= B2F_ODOM;
   if (b->fused) kf |= B2F_FUSED;
+  if (flags & B2_TICK_NOSOLVE) kf |= B2F_NOSOLVE;
   if (b->ws_global) kf |= B2F_WS_GLOBAL;
   if (b->tick_flags & (1 << 30)) kf |= B2F_XFRC;  // set once xfrc_applied has been written
   if (b->export_stages) kf |= B2F_EXPORT;
@@ -258,16 +287,22 @@ int run_tick(b2_batch* b, int flags) {
     prof_mark(b, SLOT_COLLIDE);
     k_collide<T, BL><<<g2, BL, sm, b->stream>>>(a);
     prof_mark(b, SLOT_MAKE);
-    k_make_constraint<T, BL><<<g2, BL, sm, b->stream>>>(a);
+    k_make_constraint<T, BL><<<g2, BL, sm + (size_t)2 * b->wp * (BL + 1) * sizeof(T), b->stream>>>(a);
     b->launches += 2;
     if (!(flags & B2_TICK_NOSOLVE)) {
-      prof_mark(b, SLOT_PROJECT);
-      k_project<T, BL><<<g2, BL, sm, b->stream>>>(a);
       prof_mark(b, SLOT_PGS);
-      k_pgs<T, BL><<<g2, BL, sm, b->stream>>>(a);
+      const size_t smp = sm + ((size_t)2 * (b->hdr.nv + 4) + b->hdr.njmax) * (BL / 8) * sizeof(T);
+      const int ngroups = b->nenvp / (BL / 8);
+      const int g3 = std::max(1, std::min(ngroups, b->nsm * 8));
+      switch (b->epl) {
+        case 2: k_pgs_team<T, 2, BL><<<g3, BL, smp, b->stream>>>(a); break;
+        case 4: k_pgs_team<T, 4, BL><<<g3, BL, smp, b->stream>>>(a); break;
+        case 8: k_pgs_team<T, 8, BL><<<g3, BL, smp, b->stream>>>(a); break;
+        default: k_pgs_team<T, 16, BL><<<g3, BL, smp, b->stream>>>(a); break;
+      }
       prof_mark(b, SLOT_INTEGRATE);
       k_integrate<T, BL><<<g2, BL, sm, b->stream>>>(a);
-      b->launches += 3;
+      b->launches += 2;
     }
   }
   prof_mark(b, SLOT_HW_READ);
@@ -350,10 +385,44 @@ int set_field(b2_batch* b, const char* name, const H* host, int lo, int hi, int 
   return f.count;
 }
 
+// legacy dense views (mjData.efc_J is [nefc][nv], efc_AR is [nefc][njmax]) are expanded on demand from the compact rows
+template <typename T>
+int expand_dense(b2_batch* b, const char* name) {
+  if (b->fused) return fail(std::string("field '") + name + "' does not exist for a model without constraints");
+  KArgs<T> a = make_args<T>(b, 0);
+  const long long njmax = b->hdr.njmax, nv = b->hdr.nv;
+  auto ensure = [&](const char* n, long long count) -> T* {
+    auto it = b->fields.find(n);
+    if (it == b->fields.end()) { if (alloc_field(b, n, count, 0, nullptr) < 0) return nullptr; it = b->fields.find(n); }
+    return (T*)it->second.ptr;
+  };
+  T* Jd = ensure("efc_J_dense", njmax * nv);
+  if (!Jd) return -1;
+  const int th = 128, bl = (b->nenvp + th - 1) / th;
+  k_expand_rows<T><<<bl, th, 0, b->stream>>>(a, 0, Jd);
+  if (!std::strcmp(name, "efc_AR") || !std::strcmp(name, "efc_B_dense")) {
+    T* Bd = ensure("efc_B_dense", njmax * nv);
+    if (!Bd) return -1;
+    k_expand_rows<T><<<bl, th, 0, b->stream>>>(a, 1, Bd);
+    if (!std::strcmp(name, "efc_AR")) {
+      T* AR = ensure("efc_AR", njmax * njmax);
+      if (!AR) return -1;
+      k_dense_AR<T><<<bl, th, 0, b->stream>>>(a, Jd, Bd, AR);
+    }
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+
 template <typename H>
-int get_field(b2_batch* b, const char* name, H* host, int lo, int hi, int layout, int want_kind) {
+int get_field(b2_batch* b, const char* name_in, H* host, int lo, int hi, int layout, int want_kind) {
   if (!b) return fail("null batch");
   CK(cudaSetDevice(b->device));
+  const char* name = name_in;
+  if (!std::strcmp(name, "efc_J") || !std::strcmp(name, "efc_AR") || !std::strcmp(name, "efc_B_dense")) {
+    if ((b->prec == 8 ? expand_dense<double>(b, name) : expand_dense<float>(b, name)) < 0) return -1;
+    if (!std::strcmp(name, "efc_J")) name = "efc_J_dense";
+  }
   auto it = b->fields.find(name);
   if (it == b->fields.end()) return fail(std::string("unknown field '") + name + "'");
   const Field& f = it->second;
@@ -465,6 +534,10 @@ b2_batch* b2_create(const mjModel* m, int nenv, int device, int precision) {
   for (int i = 0; i < nv; i++) any_fl |= m->dof_frictionloss[i] > 0;
   b->fused = (m->opt.disableflags & mjDSBL_CONSTRAINT) || !(any_pair || any_lim || any_fl || m->neq > 0);
 
+  b->epl = 2;
+  while (8 * b->epl < b->hdr.wmax) b->epl *= 2;
+  if (b->epl > 16) return bail("model too wide for the solver team (more than 128 dofs in two trees)");
+  b->wp = 8 * b->epl;
   struct Spec { const char* name; long long count; int kind; };
   std::vector<Spec> specs = {
       {"qpos", nq, 0}, {"qvel", nv, 0}, {"qacc", nv, 0}, {"qacc_warmstart", nv, 0}, {"qfrc_applied", nv, 0},
@@ -482,10 +555,10 @@ b2_batch* b2_create(const mjModel* m, int nenv, int device, int precision) {
     const long long njmax = b->hdr.njmax, ncm = b->hdr.nconmax;
     std::vector<Spec> more = {
         {"contact", CF_NFLOAT * ncm, 0}, {"contact_int", CI_NINT * ncm, 1},
-        {"efc_type", njmax, 1}, {"efc_id", njmax, 1}, {"efc_J", njmax * nv, 0}, {"efc_pos", njmax, 0}, {"efc_margin", njmax, 0},
+        {"efc_type", njmax, 1}, {"efc_id", njmax, 1}, {"efc_tree", 2 * njmax, 1}, {"efc_J", njmax * b->hdr.wmax, 0}, {"efc_pos", njmax, 0}, {"efc_margin", njmax, 0},
         {"efc_frictionloss", njmax, 0}, {"efc_diagApprox", njmax, 0}, {"efc_R", njmax, 0}, {"efc_D", njmax, 0}, {"efc_KBI", 3 * njmax, 0},
-        {"efc_vel", njmax, 0}, {"efc_aref", njmax, 0}, {"efc_b", njmax, 0}, {"efc_force", njmax, 0}, {"efc_MiJT", njmax * nv, 0},
-        {"efc_AR", njmax * njmax, 0}};
+        {"efc_vel", njmax, 0}, {"efc_aref", njmax, 0}, {"efc_b", njmax, 0}, {"efc_force", njmax, 0}, {"efc_ARdiag", njmax, 0},
+        {"efc_rows", njmax * 2 * b->wp, 0}, {"efc_meta", njmax * 8, 0}};
     specs.insert(specs.end(), more.begin(), more.end());
   }
   for (auto& s : specs)
@@ -512,21 +585,22 @@ b2_batch* b2_create(const mjModel* m, int nenv, int device, int precision) {
     b->ws_global = true;
     if (alloc_field(b, "_ws", b->hdr.ws_slots, 0, nullptr) < 0) return bail("alloc failed");
   }
-  if (b->blob_smem > 48 * 1024) {
-    // the constraint-pipeline kernels stage the same blob
+  {
+    // the constraint-pipeline kernels stage the same blob; row assembly and the solver add their shared vectors
+    const int need1 = (int)b->blob_smem;
+    const int need2 = (int)(b->blob_smem + (size_t)2 * b->wp * 129 * precision);
+    const int need3 = (int)(b->blob_smem + ((size_t)2 * (nv + 4) + b->hdr.njmax) * 16 * precision);
+    if (need2 > 227 * 1024 || need3 > 227 * 1024) return bail("model too large for the constraint kernels' shared memory");
     bool ok = true;
+    auto SA = [&](const void* fn, int need) { ok &= cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(need, 48 * 1024)) == cudaSuccess; };
     if (precision == 8) {
-      ok &= cudaFuncSetAttribute(k_collide<double, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->blob_smem) == cudaSuccess;
-      ok &= cudaFuncSetAttribute(k_make_constraint<double, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->blob_smem) == cudaSuccess;
-      ok &= cudaFuncSetAttribute(k_project<double, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->blob_smem) == cudaSuccess;
-      ok &= cudaFuncSetAttribute(k_pgs<double, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->blob_smem) == cudaSuccess;
-      ok &= cudaFuncSetAttribute(k_integrate<double, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->blob_smem) == cudaSuccess;
+      SA((const void*)k_collide<double, 128>, need1); SA((const void*)k_make_constraint<double, 128>, need2); SA((const void*)k_integrate<double, 128>, need1);
+      SA((const void*)k_pgs_team<double, 2, 128>, need3); SA((const void*)k_pgs_team<double, 4, 128>, need3);
+      SA((const void*)k_pgs_team<double, 8, 128>, need3); SA((const void*)k_pgs_team<double, 16, 128>, need3);
     } else {
-      ok &= cudaFuncSetAttribute(k_collide<float, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->blob_smem) == cudaSuccess;
-      ok &= cudaFuncSetAttribute(k_make_constraint<float, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->blob_smem) == cudaSuccess;
-      ok &= cudaFuncSetAttribute(k_project<float, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->blob_smem) == cudaSuccess;
-      ok &= cudaFuncSetAttribute(k_pgs<float, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->blob_smem) == cudaSuccess;
-      ok &= cudaFuncSetAttribute(k_integrate<float, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->blob_smem) == cudaSuccess;
+      SA((const void*)k_collide<float, 128>, need1); SA((const void*)k_make_constraint<float, 128>, need2); SA((const void*)k_integrate<float, 128>, need1);
+      SA((const void*)k_pgs_team<float, 2, 128>, need3); SA((const void*)k_pgs_team<float, 4, 128>, need3);
+      SA((const void*)k_pgs_team<float, 8, 128>, need3); SA((const void*)k_pgs_team<float, 16, 128>, need3);
     }
     if (!ok) return bail("cudaFuncSetAttribute failed");
   }
@@ -634,6 +708,8 @@ int b2_set_option(b2_batch* b, const char* name, double value) {
 
 int b2_field_size(const b2_batch* b, const char* field) {
   if (!b || !field) return fail("b2_field_size: null argument");
+  if (!b->fused && !std::strcmp(field, "efc_J")) return b->hdr.njmax * b->hdr.nv;            // dense legacy view
+  if (!b->fused && !std::strcmp(field, "efc_AR")) return b->hdr.njmax * b->hdr.njmax;
   auto it = b->fields.find(field);
   if (it == b->fields.end()) return fail(std::string("unknown field '") + field + "'");
   return it->second.count;

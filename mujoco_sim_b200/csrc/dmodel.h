@@ -29,6 +29,7 @@ namespace b2 {
   X(eq_solref, F, 2 * neq) X(eq_solimp, F, 5 * neq) X(eq_data, F, 11 * neq)                                    \
   X(pair_geom1, I, npair) X(pair_geom2, I, npair)                                                              \
   X(odom_dof, I, 6 * nodom) X(odom_qpos, I, 3 * nodom)                                                          \
+  X(body_treeid, I, nbody) X(dof_treeid, I, nv) X(tree_dofadr, I, ntree) X(tree_dofnum, I, ntree)              \
   X(opt_real, F, 8) /* gravity[3], tolerance, meaninertia, impratio, 0, 0 in batch precision */
 
 // Workspace arrays (per environment, strided by the workspace stride): name, count expression
@@ -42,6 +43,8 @@ namespace b2 {
 struct DModel {
   // sizes
   int nq, nv, nbody, njnt, ngeom, nM, neq, npair, nconmax, njmax, nmocap, nodom;
+  int ntree, wmax;  // kinematic trees with dofs; widest compact constraint row (dofs of the two largest trees)
+  int pad3[2];
   int disableflags, enableflags, iterations, nwords;  // nwords: blob size in 32-bit words (multiple of 4)
   int has_damping, has_gravcomp, has_stiffness, has_limits, has_frictionloss, has_controlled, has_xfrc, pad0;
   float gravity[3];

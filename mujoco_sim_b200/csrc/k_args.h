@@ -14,7 +14,8 @@ enum TickFlags : int {
   B2F_FUSED = 1 << 4,        // model has no constraint source at all: the smooth kernel also integrates
   B2F_XFRC = 1 << 5,         // xfrc_applied is non-zero somewhere
   B2F_WS_GLOBAL = 1 << 6,    // workspace in HBM instead of shared memory
-  B2F_EXPORT = 1 << 7,       // also export the stage arrays from the fused kernel (legacy mjData mirror)
+  B2F_EXPORT = 1 << 7,
+  B2F_NOSOLVE = 1 << 8,      // stop after constraint assembly (mj_step1)       // also export the stage arrays from the fused kernel (legacy mjData mirror)
 };
 
 // contact record, SoA: field f of contact c of env e at con[(f * nconmax + c) * nenvp + e]
@@ -49,11 +50,14 @@ struct KArgs {
   int* nefc;              // [nenvp]
   int* efc_type;          // [njmax][nenvp]
   int* efc_id;            // [njmax][nenvp]
-  T *efc_J;               // [njmax][nv][nenvp]
+  int* efc_tree;          // [njmax][2][nenvp] kinematic trees of the row (-1: none)
+  T *efc_J;               // [njmax][wmax][nenvp] compact rows (k_constraint.cuh)
   T *efc_pos, *efc_margin, *efc_frictionloss, *efc_diagApprox, *efc_R, *efc_D, *efc_KBI, *efc_vel, *efc_aref,
       *efc_b, *efc_force; // [njmax][nenvp] (KBI: [3][njmax][nenvp])
-  T* efc_MiJT;            // [njmax][nv][nenvp]  rows of M^-1 J^T
-  T* efc_AR;              // [njmax][njmax][nenvp]
+  T* efc_ARdiag;          // [njmax][nenvp] diagonal of J M^-1 J^T + R
+  T* efc_rows;            // [nenvp][njmax][2 wp] environment-major solver slab: J compact | M^-1 J^T compact
+  T* efc_meta;            // [nenvp][njmax][8]   {R, aref, diag(AR), frictionloss, type, tree1, tree2, b}
+  int wp;                 // padded compact row width: 8 * EPL of the solver team
   int* solver_iter;       // [nenvp]
   int* status;            // [nenvp] bit 0: contact cap hit, bit 1: row cap hit, bit 2: state reset (bad value)
 };

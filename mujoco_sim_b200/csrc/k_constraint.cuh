@@ -1,5 +1,13 @@
 // k_constraint.cuh — constraint rows (equality, friction loss, limits, pyramidal contacts), impedance / reference
-// acceleration, projection AR = J M^-1 J^T + R, the PGS solve and the final integrate kernel
+// acceleration, projection B = M^-1 J^T (+ diag(AR)), the PGS solve fused with the integrate stage.
+//
+// Row storage is COMPACT: the mass matrix is block diagonal over kinematic trees and a constraint row touches at
+// most two trees (contact between two bodies, joint equality, limit, friction loss), so row r keeps only the dofs of
+// trees (t1, t2): element k < n1 is dof s1 + k, element k >= n1 is dof s2 + k - n1, width <= DModel.wmax.
+// J and B = M^-1 J^T share that layout; [row][k][env] in HBM (env fastest: coalesced for one thread per environment).
+// PGS runs in acceleration space: with a = qacc_smooth + sum_r f_r B_r the Gauss-Seidel residual of row r is
+// J_r a - aref_r + R_r f_r, identical to AR_r f + b_r of the dual formulation but O(width) instead of O(nefc) per row
+// and without ever forming the nefc x nefc matrix (which is still available on demand for the legacy efc_AR field).
 // (rows s6, s7(aref), s11, s12, s13, s14 of SURVEY.md section 8a').  Row order and formulas follow MuJoCo's published
 // constraint model; the reference reaches them only through mj_step1 / mj_step2 / mj_inverse
 // (src/mj_main.cpp:83,108; src/mujoco_sim/mj_hw_interface.cpp:61).
@@ -30,6 +38,21 @@ __device__ T impedance(const T* solimp, T pos, T margin) {
   return dmin + y * (dmax - dmin);
 }
 
+
+struct Seg { int s1, n1, s2, n2; };
+
+template <typename T>
+__device__ __forceinline__ Seg seg_of(const MV<T>& m, int t1, int t2) {
+  const DModel& h = *m.h;
+  Seg g{0, 0, 0, 0};
+  if (t1 >= 0) { g.s1 = m.i(h.o_tree_dofadr, t1); g.n1 = m.i(h.o_tree_dofnum, t1); }
+  if (t2 >= 0) { g.s2 = m.i(h.o_tree_dofadr, t2); g.n2 = m.i(h.o_tree_dofnum, t2); }
+  return g;
+}
+// compact position of dof i in a row with segments g (i must lie in one of them)
+__device__ __forceinline__ int seg_pos(const Seg& g, int i) { return (i >= g.s1 && i < g.s1 + g.n1) ? i - g.s1 : g.n1 + i - g.s2; }
+__device__ __forceinline__ int seg_dof(const Seg& g, int k) { return k < g.n1 ? g.s1 + k : g.s2 + k - g.n1; }
+
 template <typename T>
 struct Rows {
   MV<T> m;
@@ -39,19 +62,26 @@ struct Rows {
   long long S;
   int nefc = 0;
   __device__ Rows(const MV<T>& mv, const KArgs<T>& args, int e) : m(mv), h(*mv.h), a(args), env(e), S(args.nenvp) {}
-  __device__ __forceinline__ T& J(int r, int i) const { return a.efc_J[((long long)r * h.nv + i) * S + env]; }
+  __device__ __forceinline__ T& Jc(int r, int k) const { return a.efc_J[((long long)r * h.wmax + k) * S + env]; }
   __device__ __forceinline__ T cdof(int i, int k) const { return a.cdof[(6 * i + k) * S + env]; }
 
-  // start a new zero row; returns its index or -1 when njmax is exhausted
-  __device__ int open(int type, int id, T pos, T margin, T frictionloss) {
+  // start a new zero row over trees (t1, t2); returns its index or -1 when njmax is exhausted
+  __device__ int open(int type, int id, T pos, T margin, T frictionloss, int t1, int t2, Seg* gout) {
     if (nefc >= h.njmax) { a.status[env] |= 2; return -1; }
+    if (t1 < 0) { t1 = t2; t2 = -1; }
+    if (t1 == t2) t2 = -1;
+    if (t2 >= 0 && t2 < t1) { const int t = t1; t1 = t2; t2 = t; }
     const int r = nefc++;
-    for (int i = 0; i < h.nv; i++) J(r, i) = 0;
+    const Seg g = seg_of(m, t1, t2);
+    for (int k = 0; k < g.n1 + g.n2; k++) Jc(r, k) = 0;
+    a.efc_tree[((long long)2 * r) * S + env] = t1;
+    a.efc_tree[((long long)2 * r + 1) * S + env] = t2;
     a.efc_type[(long long)r * S + env] = type;
     a.efc_id[(long long)r * S + env] = id;
     a.efc_pos[(long long)r * S + env] = pos;
     a.efc_margin[(long long)r * S + env] = margin;
     a.efc_frictionloss[(long long)r * S + env] = frictionloss;
+    if (gout) *gout = g;
     return r;
   }
 
@@ -70,13 +100,14 @@ struct Rows {
   }
 
   // rows [r0, r0 + 3) += sign * translational Jacobian of body b at point (world axes)
-  __device__ void add_jacp(int r0, int b, const T* point, T sign) {
+  __device__ void add_jacp(int r0, const Seg& g, int b, const T* point, T sign) {
     T off[3];
     point_off(b, point, off);
     for (int i = m.i(h.o_body_lastdof, b); i >= 0; i = m.i(h.o_dof_parentid, i)) {
       T jp[3], jr[3];
       jac_col(i, off, jp, jr);
-      for (int k = 0; k < 3; k++) J(r0 + k, i) += sign * jp[k];
+      const int k = seg_pos(g, i);
+      for (int c = 0; c < 3; c++) Jc(r0 + c, k) += sign * jp[c];
     }
   }
 
@@ -86,6 +117,7 @@ struct Rows {
       if (!m.i(h.o_eq_active, q)) continue;
       const int type = m.i(h.o_eq_type, q), o1 = m.i(h.o_eq_obj1id, q), o2 = m.i(h.o_eq_obj2id, q);
       const T* data = m.fp(h.o_eq_data) + 11 * q;
+      Seg g;
       if (type == EQ_JOINT) {
         const int qa1 = m.i(h.o_jnt_qposadr, o1), da1 = m.i(h.o_jnt_dofadr, o1);
         const T pos = a.qpos[qa1 * S + env] - m.f(h.o_qpos0, qa1);
@@ -98,12 +130,13 @@ struct Rows {
           ref = data[0] + dif * (data[1] + dif * (data[2] + dif * (data[3] + dif * data[4])));
           deriv = data[1] + dif * (2 * data[2] + dif * (3 * data[3] + dif * 4 * data[4]));
         }
-        const int r = open(CN_EQUALITY, q, pos - ref, 0, 0);
+        const int r = open(CN_EQUALITY, q, pos - ref, 0, 0, m.i(h.o_dof_treeid, da1), da2 >= 0 ? m.i(h.o_dof_treeid, da2) : -1, &g);
         if (r < 0) continue;
-        if (da2 >= 0) J(r, da2) = -deriv;
-        J(r, da1) = 1;
+        if (da2 >= 0) Jc(r, seg_pos(g, da2)) = -deriv;
+        Jc(r, seg_pos(g, da1)) = 1;
       } else {
         const bool weld = type == EQ_WELD;
+        const int t1 = m.i(h.o_body_treeid, o1), t2 = m.i(h.o_body_treeid, o2);
         T a1[3], a2[3], p1[3], p2[3], m1[9], m2[9];
         for (int k = 0; k < 3; k++) { a1[k] = weld ? data[3 + k] : data[k]; a2[k] = weld ? data[k] : data[3 + k]; }
         for (int k = 0; k < 9; k++) { m1[k] = a.xmat[(9 * o1 + k) * S + env]; m2[k] = a.xmat[(9 * o2 + k) * S + env]; }
@@ -111,10 +144,10 @@ struct Rows {
         mat_vec3(p2, m2, a2);
         for (int k = 0; k < 3; k++) { p1[k] += a.xpos[(3 * o1 + k) * S + env]; p2[k] += a.xpos[(3 * o2 + k) * S + env]; }
         int r0 = -1;
-        for (int k = 0; k < 3; k++) { const int r = open(CN_EQUALITY, q, p1[k] - p2[k], 0, 0); if (k == 0) r0 = r; }
+        for (int k = 0; k < 3; k++) { const int r = open(CN_EQUALITY, q, p1[k] - p2[k], 0, 0, t1, t2, &g); if (k == 0) r0 = r; }
         if (r0 < 0 || nefc - r0 < 3) continue;
-        add_jacp(r0, o1, p1, T(1));
-        add_jacp(r0, o2, p2, T(-1));
+        add_jacp(r0, g, o1, p1, T(1));
+        add_jacp(r0, g, o2, p2, T(-1));
         if (weld) {
           const T ts = data[10];
           T q1[4], q2n[4], q1r[4], qe[4];
@@ -123,17 +156,18 @@ struct Rows {
           mul_quat(q1r, q1, data + 6);
           mul_quat(qe, q2n, q1r);
           int rr = -1;
-          for (int k = 0; k < 3; k++) { const int r = open(CN_EQUALITY, q, ts * qe[1 + k], 0, 0); if (k == 0) rr = r; }
+          for (int k = 0; k < 3; k++) { const int r = open(CN_EQUALITY, q, ts * qe[1 + k], 0, 0, t1, t2, &g); if (k == 0) rr = r; }
           if (rr < 0 || nefc - rr < 3) continue;
           for (int side = 0; side < 2; side++) {
             const int b = side ? o2 : o1;
             const T sg = side ? T(-1) : T(1);
             for (int i = m.i(h.o_body_lastdof, b); i >= 0; i = m.i(h.o_dof_parentid, i)) {
               const T w[4] = {0, cdof(i, 0), cdof(i, 1), cdof(i, 2)};
-              T t1[4], t2[4];
-              mul_quat(t1, q2n, w);
-              mul_quat(t2, t1, q1r);
-              for (int k = 0; k < 3; k++) J(rr + k, i) += sg * T(0.5) * ts * t2[1 + k];
+              T t1q[4], t2q[4];
+              mul_quat(t1q, q2n, w);
+              mul_quat(t2q, t1q, q1r);
+              const int kk = seg_pos(g, i);
+              for (int k = 0; k < 3; k++) Jc(rr + k, kk) += sg * T(0.5) * ts * t2q[1 + k];
             }
           }
         }
@@ -146,8 +180,9 @@ struct Rows {
     for (int i = 0; i < h.nv; i++) {
       const T fl = m.f(h.o_dof_frictionloss, i);
       if (fl <= 0) continue;
-      const int r = open(CN_FRICTION_DOF, i, 0, 0, fl);
-      if (r >= 0) J(r, i) = 1;
+      Seg g;
+      const int r = open(CN_FRICTION_DOF, i, 0, 0, fl, m.i(h.o_dof_treeid, i), -1, &g);
+      if (r >= 0) Jc(r, seg_pos(g, i)) = 1;
     }
   }
 
@@ -157,13 +192,14 @@ struct Rows {
       if (!m.i(h.o_jnt_limited, j)) continue;
       const int qa = m.i(h.o_jnt_qposadr, j), da = m.i(h.o_jnt_dofadr, j), jt = m.i(h.o_jnt_type, j);
       const T margin = m.f(h.o_jnt_margin, j);
+      Seg g;
       if (jt == JNT_SLIDE || jt == JNT_HINGE) {
         const T value = a.qpos[qa * S + env];
         for (int side = -1; side <= 1; side += 2) {
           const T dist = side * (m.f(h.o_jnt_range, 2 * j + (side + 1) / 2) - value);
           if (dist < margin) {
-            const int r = open(CN_LIMIT_JOINT, j, dist, margin, 0);
-            if (r >= 0) J(r, da) = T(-side);
+            const int r = open(CN_LIMIT_JOINT, j, dist, margin, 0, m.i(h.o_dof_treeid, da), -1, &g);
+            if (r >= 0) Jc(r, seg_pos(g, da)) = T(-side);
           }
         }
       } else if (jt == JNT_BALL) {
@@ -178,8 +214,8 @@ struct Rows {
         if (angle < 0) { angle = -angle; ax[0] = -ax[0]; ax[1] = -ax[1]; ax[2] = -ax[2]; }
         const T dist = t_max(m.f(h.o_jnt_range, 2 * j), m.f(h.o_jnt_range, 2 * j + 1)) - angle;
         if (dist < margin) {
-          const int r = open(CN_LIMIT_JOINT, j, dist, margin, 0);
-          if (r >= 0) for (int k = 0; k < 3; k++) J(r, da + k) = -ax[k];
+          const int r = open(CN_LIMIT_JOINT, j, dist, margin, 0, m.i(h.o_dof_treeid, da), -1, &g);
+          if (r >= 0) for (int k = 0; k < 3; k++) Jc(r, seg_pos(g, da + k)) = -ax[k];
         }
       }
     }
@@ -200,8 +236,10 @@ struct Rows {
       const T dist = F(CF_DIST), im = F(CF_INCLUDEMARGIN);
       const int nrow = dim == 1 ? 1 : 2 * (dim - 1);
       const int first = nefc;
-      for (int k = 0; k < nrow; k++) open(dim == 1 ? CN_CONTACT_FRICTIONLESS : CN_CONTACT_PYRAMIDAL, c, dist, im, 0);
-      if (nefc - first < nrow) { nefc = first; I(CI_EFC) = -1; continue; }  // did not fit: drop the whole contact
+      if (first + nrow > h.njmax) { a.status[env] |= 2; I(CI_EFC) = -1; continue; }  // kept whole or dropped whole
+      Seg g;
+      const int t1 = m.i(h.o_body_treeid, b1), t2 = m.i(h.o_body_treeid, b2);
+      for (int k = 0; k < nrow; k++) open(dim == 1 ? CN_CONTACT_FRICTIONLESS : CN_CONTACT_PYRAMIDAL, c, dist, im, 0, t1, t2, &g);
       I(CI_EFC) = first;
       for (int side = 0; side < 2; side++) {
         const int b = side ? b2 : b1;
@@ -213,12 +251,13 @@ struct Rows {
           jac_col(i, off, jp, jr);
           mat_vec3(fp, frame, jp);  // rows of frame: normal, tangent1, tangent2
           mat_vec3(fr, frame, jr);
-          if (dim == 1) { J(first, i) += sg * fp[0]; continue; }
+          const int kk = seg_pos(g, i);
+          if (dim == 1) { Jc(first, kk) += sg * fp[0]; continue; }
           for (int k = 1; k < dim; k++) {
             const T dir = k < 3 ? fp[k] : fr[k - 3];
             const T mu = fri[k - 1];
-            J(first + 2 * k - 2, i) += sg * (fp[0] + mu * dir);
-            J(first + 2 * k - 1, i) += sg * (fp[0] - mu * dir);
+            Jc(first + 2 * k - 2, kk) += sg * (fp[0] + mu * dir);
+            Jc(first + 2 * k - 1, kk) += sg * (fp[0] - mu * dir);
           }
         }
       }
@@ -299,16 +338,6 @@ struct Rows {
       const T Rpy = t_max(Eps<T>::minval(), 2 * mu * mu * a.efc_R[(long long)adr * S + env]);
       for (int j = 0; j < 2 * (dim - 1); j++) a.efc_R[(long long)(adr + j) * S + env] = Rpy;
     }
-    for (int r = 0; r < nefc; r++) {
-      const long long o = (long long)r * S + env;
-      a.efc_D[o] = 1 / a.efc_R[o];
-      T vel = 0;
-      for (int i = 0; i < h.nv; i++) vel += J(r, i) * a.qvel[i * S + env];
-      a.efc_vel[o] = vel;
-      const T K = a.efc_KBI[((long long)0 * h.njmax + r) * S + env], B = a.efc_KBI[((long long)1 * h.njmax + r) * S + env];
-      const T imp = a.efc_KBI[((long long)2 * h.njmax + r) * S + env];
-      a.efc_aref[o] = -B * vel - K * imp * (a.efc_pos[o] - a.efc_margin[o]);
-    }
   }
 };
 
@@ -336,10 +365,23 @@ __device__ __forceinline__ T primal_force(int type, T jar, T D, T R, T fl) {
   const int ntiles = a.nenvp / BLOCK;                                                \
   (void)S; (void)h;
 
-// K4: rows + impedance + aref, b = J qacc_smooth - aref, and (for mj_inverse) qfrc_inverse -= J^T f(qacc_prev)
+// Row slab for the solver, environment-major: row r of environment e is 2 * wp contiguous numbers
+// [J compact (wp) | B = M^-1 J^T compact (wp)] at efc_rows[(e * njmax + r) * 2 wp], plus an 8-number record
+// {R, aref, diag(AR), frictionloss, type, tree1, tree2, b} at efc_meta[(e * njmax + r) * 8].  One 8-lane team of the
+// solver streams these rows with 8/16-byte vector loads; for wp = 16 (C3) a row is exactly one 128-byte line.
+enum { META_R = 0, META_AREF, META_DIAG, META_FL, META_TYPE, META_T1, META_T2, META_B, META_N };
+
+// K4 + K5 fused: rows, impedance, then per row: vel, aref, b = J qacc_smooth - aref, B_r = M^-1 J_r^T by sparse
+// back-substitution inside the row's tree blocks (in shared memory), diag(AR)_r = J_r B_r + R_r, and (for mj_inverse)
+// qfrc_inverse -= J^T f(qacc_prev).  Finished rows leave through a shared-memory transpose so that every global store
+// of the slab is a full coalesced line.
 template <typename T, int BLOCK>
 __global__ void __launch_bounds__(BLOCK) k_make_constraint(const KArgs<T> a) {
   B2_KERNEL_PROLOGUE
+  const int WP = a.wp;
+  constexpr int LDS = BLOCK + 1;  // +1: conflict-free both for per-thread columns and for the transposed row reads
+  T* rowsh = reinterpret_cast<T*>(smem_raw + 16 + (size_t)nwords * 4);  // [2 * WP][LDS]
+  const int lane = threadIdx.x & 31, wbase = threadIdx.x & ~31;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int env = tile * BLOCK + threadIdx.x;
     Rows<T> rows(m, a, env);
@@ -350,132 +392,267 @@ __global__ void __launch_bounds__(BLOCK) k_make_constraint(const KArgs<T> a) {
       rows.contacts();
       rows.finish();
     }
-    const int ne = rows.nefc, nv = h.nv;
+    const int ne = rows.nefc, W = h.wmax;
     a.nefc[env] = ne;
-    for (int r = 0; r < ne; r++) {
-      const long long o = (long long)r * S + env;
-      T js = 0, jq = 0;
-      for (int i = 0; i < nv; i++) {
-        const T j = rows.J(r, i);
-        js += j * a.qacc_smooth[i * S + env];
-        jq += j * a.qacc[i * S + env];
-      }
-      const T aref = a.efc_aref[o];
-      a.efc_b[o] = js - aref;
-      if (a.flags & B2F_INVERSE) {
-        const T f = primal_force(a.efc_type[o], jq - aref, a.efc_D[o], a.efc_R[o], a.efc_frictionloss[o]);
-        if (f != 0) for (int i = 0; i < nv; i++) a.qfrc_inverse[i * S + env] -= rows.J(r, i) * f;
-      }
-    }
-  }
-}
-
-// K5: rows of M^-1 J^T by sparse back-substitution, then AR = J (M^-1 J^T) + diag(R)   (FFMA version)
-template <typename T, int BLOCK>
-__global__ void __launch_bounds__(BLOCK) k_project(const KArgs<T> a) {
-  B2_KERNEL_PROLOGUE
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int env = tile * BLOCK + threadIdx.x;
-    const int ne = a.nefc[env], nv = h.nv, ld = h.njmax;
     SArr<T> LD{a.qLD + env, S}, dinv{a.qLDiagInv + env, S};
-    for (int r = 0; r < ne; r++) {
-      SArr<T> x{a.efc_MiJT + (long long)r * nv * S + env, S};
-      for (int i = 0; i < nv; i++) x[i] = a.efc_J[((long long)r * nv + i) * S + env];
-      ld_solve(m, LD, dinv, x);
-    }
-    for (int r = 0; r < ne; r++)
-      for (int c = 0; c <= r; c++) {
-        T v = 0;
-        for (int i = 0; i < nv; i++) v += a.efc_J[((long long)r * nv + i) * S + env] * a.efc_MiJT[((long long)c * nv + i) * S + env];
-        if (c == r) v += a.efc_R[(long long)r * S + env];
-        a.efc_AR[((long long)r * ld + c) * S + env] = v;
-        a.efc_AR[((long long)c * ld + r) * S + env] = v;
+    SArr<T> Jr{rowsh + threadIdx.x, LDS}, Br{rowsh + (size_t)WP * LDS + threadIdx.x, LDS};
+    int nemax = ne;
+    for (int o = 16; o > 0; o >>= 1) nemax = max(nemax, __shfl_xor_sync(0xffffffffu, nemax, o));
+    for (int r = 0; r < nemax; r++) {
+      T R = 0, aref = 0, dg = 0, fl = 0, bb = 0;
+      int type = 0, t1 = -1, t2 = -1;
+      if (r < ne) {
+        const long long o = (long long)r * S + env;
+        t1 = a.efc_tree[((long long)2 * r) * S + env]; t2 = a.efc_tree[((long long)2 * r + 1) * S + env];
+        const Seg g = seg_of(m, t1, t2);
+        const int w = g.n1 + g.n2;
+        T vel = 0, js = 0, jq = 0;
+        for (int k = 0; k < w; k++) {
+          const T j = a.efc_J[((long long)r * W + k) * S + env];
+          const long long d = (long long)seg_dof(g, k) * S + env;
+          vel += j * a.qvel[d];
+          js += j * a.qacc_smooth[d];
+          jq += j * a.qacc[d];
+          Jr[k] = j;
+          Br[k] = j;
+        }
+        for (int k = w; k < WP; k++) { Jr[k] = 0; Br[k] = 0; }
+        const T K = a.efc_KBI[((long long)0 * h.njmax + r) * S + env], Bd = a.efc_KBI[((long long)1 * h.njmax + r) * S + env];
+        const T imp = a.efc_KBI[((long long)2 * h.njmax + r) * S + env];
+        R = a.efc_R[o];
+        const T D = 1 / R;
+        aref = -Bd * vel - K * imp * (a.efc_pos[o] - a.efc_margin[o]);
+        type = a.efc_type[o];
+        fl = a.efc_frictionloss[o];
+        bb = js - aref;
+        a.efc_D[o] = D;
+        a.efc_vel[o] = vel;
+        a.efc_aref[o] = aref;
+        a.efc_b[o] = bb;
+        if (a.flags & B2F_INVERSE) {
+          const T f = primal_force(type, jq - aref, D, R, fl);
+          if (f != 0) for (int k = 0; k < w; k++) a.qfrc_inverse[(long long)seg_dof(g, k) * S + env] -= Jr[k] * f;
+        }
+        // B_r = M^-1 J_r^T, one tree block at a time (M is block diagonal over trees)
+        for (int sgm = 0; sgm < 2; sgm++) {
+          const int lo = sgm ? g.s2 : g.s1, n = sgm ? g.n2 : g.n1, base = sgm ? g.n1 : 0;
+          if (n == 0) continue;
+          for (int i = lo + n - 1; i >= lo; i--) {
+            const T xi = Br[base + i - lo];
+            if (xi == 0) continue;
+            int adr = m.i(h.o_dof_Madr, i) + 1;
+            for (int j = m.i(h.o_dof_parentid, i); j >= 0; j = m.i(h.o_dof_parentid, j)) Br[base + j - lo] -= LD[adr++] * xi;
+          }
+          for (int i = lo; i < lo + n; i++) Br[base + i - lo] *= dinv[i];
+          for (int i = lo; i < lo + n; i++) {
+            int adr = m.i(h.o_dof_Madr, i) + 1;
+            T xi = Br[base + i - lo];
+            for (int j = m.i(h.o_dof_parentid, i); j >= 0; j = m.i(h.o_dof_parentid, j)) xi -= LD[adr++] * Br[base + j - lo];
+            Br[base + i - lo] = xi;
+          }
+        }
+        dg = R;
+        for (int k = 0; k < w; k++) dg += Jr[k] * Br[k];
+        a.efc_ARdiag[o] = dg;
       }
+      // ---- transpose out: lanes cooperate on one environment's row at a time (coalesced line stores) ----
+      __syncwarp();
+      for (int e = 0; e < 32; e++) {
+        const int ne_e = __shfl_sync(0xffffffffu, ne, e);
+        // the meta record of environment e is assembled from lane e's registers
+        const T mR = __shfl_sync(0xffffffffu, R, e), mA = __shfl_sync(0xffffffffu, aref, e), mD = __shfl_sync(0xffffffffu, dg, e);
+        const T mF = __shfl_sync(0xffffffffu, fl, e), mB = __shfl_sync(0xffffffffu, bb, e);
+        const int mT = __shfl_sync(0xffffffffu, type, e), m1 = __shfl_sync(0xffffffffu, t1, e), m2 = __shfl_sync(0xffffffffu, t2, e);
+        if (r >= ne_e) continue;
+        const long long env_e = (long long)tile * BLOCK + wbase + e;
+        T* dst = a.efc_rows + (env_e * h.njmax + r) * (2 * WP);
+        for (int l = lane; l < 2 * WP; l += 32) dst[l] = rowsh[(size_t)l * LDS + wbase + e];
+        if (lane < META_N) {
+          T v;
+          switch (lane) {
+            case META_R: v = mR; break;
+            case META_AREF: v = mA; break;
+            case META_DIAG: v = mD; break;
+            case META_FL: v = mF; break;
+            case META_TYPE: v = (T)mT; break;
+            case META_T1: v = (T)m1; break;
+            case META_T2: v = (T)m2; break;
+            default: v = mB;
+          }
+          a.efc_meta[(env_e * h.njmax + r) * META_N + lane] = v;
+        }
+      }
+      __syncwarp();
+    }
   }
 }
 
-// K6: projected Gauss-Seidel on the dual (A.8), warm-started from qacc_warmstart
-template <typename T, int BLOCK>
-__global__ void __launch_bounds__(BLOCK) k_pgs(const KArgs<T> a) {
+template <typename T, int N> struct alignas(sizeof(T) * N) VecN { T v[N]; };
+
+// K6: projected Gauss-Seidel (A.8) in acceleration space.  An 8-lane team owns one environment (4 per warp): lane l
+// holds elements [l * EPL, (l + 1) * EPL) of the current row of J and B, the running acceleration and the forces live
+// in shared memory, rows stream from the slab one ahead of their use.
+template <typename T, int EPL, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_pgs_team(const KArgs<T> a) {
   B2_KERNEL_PROLOGUE
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int env = tile * BLOCK + threadIdx.x;
-    const int ne = a.nefc[env], nv = h.nv, ld = h.njmax;
+  (void)ntiles;
+  constexpr int TEAM = 8, EPB = BLOCK / TEAM;  // environments per CTA
+  constexpr int WP = TEAM * EPL;
+  const int nv = h.nv, njmax = h.njmax;
+  const int nvs = nv + 4;  // stride of the per-environment vectors (skews the teams over the banks)
+  T* accsh = reinterpret_cast<T*>(smem_raw + 16 + (size_t)nwords * 4);  // [EPB][nvs] running acceleration
+  T* tmpsh = accsh + (size_t)EPB * nvs;                                   // [EPB][nvs] M^-1 J^T f, later qfrc_constraint
+  T* fsh = tmpsh + (size_t)EPB * nvs;                                     // [EPB][njmax] forces
+  const int team = threadIdx.x / TEAM, l = threadIdx.x % TEAM;
+  const unsigned tmask = 0xffu << ((threadIdx.x & 31) & ~7);
+  T* acc = accsh + (size_t)team * nvs;
+  T* tmp = tmpsh + (size_t)team * nvs;
+  T* f = fsh + (size_t)team * njmax;
+  const int ngroups = (a.nenvp + EPB - 1) / EPB;
+  const T tol = m.f(h.o_opt_real, 3), scale = 1 / (m.f(h.o_opt_real, 4) * T(nv > 1 ? nv : 1));
+
+  auto team_sum = [&](T v) {
+    v += __shfl_xor_sync(tmask, v, 4);
+    v += __shfl_xor_sync(tmask, v, 2);
+    v += __shfl_xor_sync(tmask, v, 1);
+    return v;
+  };
+  for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+    const long long env = (long long)grp * EPB + team;  // nenvp is a multiple of 128 >= EPB: always in range
+    const int ne = a.nefc[env];
+    const T* rowp = a.efc_rows + env * njmax * (2 * WP);
+    const T* metap = a.efc_meta + env * njmax * META_N;
     int iters = 0;
+    // dof index of this lane's elements for a row with trees (t1, t2); -1 for padding
+    auto dofs_of = [&](int t1, int t2, int* d) {
+      const Seg g = seg_of(m, t1, t2);
+#pragma unroll
+      for (int k = 0; k < EPL; k++) { const int kk = l * EPL + k; d[k] = kk < g.n1 + g.n2 ? seg_dof(g, kk) : -1; }
+    };
+    auto load_row = [&](int r, VecN<T, EPL>& J, VecN<T, EPL>& B, VecN<T, META_N>& M) {
+      J = *reinterpret_cast<const VecN<T, EPL>*>(rowp + (size_t)r * 2 * WP + l * EPL);
+      B = *reinterpret_cast<const VecN<T, EPL>*>(rowp + (size_t)r * 2 * WP + WP + l * EPL);
+      M = *reinterpret_cast<const VecN<T, META_N>*>(metap + (size_t)r * META_N);
+    };
+    for (int i = l; i < nv; i += TEAM) { acc[i] = a.qacc_warmstart[(long long)i * S + env]; tmp[i] = 0; }
+    __syncwarp(tmask);
     if (ne > 0) {
-      auto AR = [&](int r, int c) -> T { return a.efc_AR[((long long)r * ld + c) * S + env]; };
-      auto F = [&](int r) -> T& { return a.efc_force[(long long)r * S + env]; };
-      if (!(h.disableflags & DSBL_WARMSTART)) {
+      VecN<T, EPL> J, B;
+      VecN<T, META_N> M;
+      int d[EPL];
+      // ---- warm start: forces implied by qacc_warmstart (held in acc), kept only if their dual cost is negative ----
+      bool warm = !(h.disableflags & DSBL_WARMSTART);
+      if (warm) {
         for (int r = 0; r < ne; r++) {
-          const long long o = (long long)r * S + env;
-          T jw = 0;
-          for (int i = 0; i < nv; i++) jw += a.efc_J[((long long)r * nv + i) * S + env] * a.qacc_warmstart[i * S + env];
-          F(r) = primal_force(a.efc_type[o], jw - a.efc_aref[o], a.efc_D[o], a.efc_R[o], a.efc_frictionloss[o]);
+          load_row(r, J, B, M);
+          dofs_of((int)M.v[META_T1], (int)M.v[META_T2], d);
+          T p = 0;
+#pragma unroll
+          for (int k = 0; k < EPL; k++) if (d[k] >= 0) p += J.v[k] * acc[d[k]];
+          const T jw = team_sum(p);
+          const T R = M.v[META_R];
+          const T fr = primal_force((int)M.v[META_TYPE], jw - M.v[META_AREF], 1 / R, R, M.v[META_FL]);
+          if (l == 0) f[r] = fr;
+          if (fr != 0) {
+#pragma unroll
+            for (int k = 0; k < EPL; k++) if (d[k] >= 0) tmp[d[k]] += fr * B.v[k];
+          }
+          __syncwarp(tmask);
         }
         T cost = 0;
         for (int r = 0; r < ne; r++) {
-          T Af = 0;
-          for (int c = 0; c < ne; c++) Af += AR(r, c) * F(c);
-          cost += F(r) * (T(0.5) * Af + a.efc_b[(long long)r * S + env]);
+          const T fr = f[r];
+          if (fr == 0) continue;
+          load_row(r, J, B, M);
+          dofs_of((int)M.v[META_T1], (int)M.v[META_T2], d);
+          T p = 0;
+#pragma unroll
+          for (int k = 0; k < EPL; k++) if (d[k] >= 0) p += J.v[k] * tmp[d[k]];
+          const T Af = team_sum(p) + M.v[META_R] * fr;
+          cost += fr * (T(0.5) * Af + M.v[META_B]);
         }
-        if (cost > 0) for (int r = 0; r < ne; r++) F(r) = 0;
-      } else {
-        for (int r = 0; r < ne; r++) F(r) = 0;
+        if (cost > 0) warm = false;
       }
-      const T scale = 1 / (m.f(h.o_opt_real, 4) * T(nv > 1 ? nv : 1));
+      __syncwarp(tmask);
+      if (warm) {
+        for (int i = l; i < nv; i += TEAM) acc[i] = a.qacc_smooth[(long long)i * S + env] + tmp[i];
+      } else {
+        for (int i = l; i < nv; i += TEAM) acc[i] = a.qacc_smooth[(long long)i * S + env];
+        for (int r = l; r < ne; r += TEAM) f[r] = 0;
+      }
+      __syncwarp(tmask);
+      // ---- Gauss-Seidel sweeps; the next row is fetched while the current one is processed ----
       for (int it = 0; it < h.iterations; it++) {
         T improvement = 0;
+        VecN<T, EPL> Jn, Bn;
+        VecN<T, META_N> Mn;
+        load_row(0, Jn, Bn, Mn);
         for (int r = 0; r < ne; r++) {
-          const long long o = (long long)r * S + env;
-          T res = a.efc_b[o];
-          for (int c = 0; c < ne; c++) res += AR(r, c) * F(c);
-          const T Arr = AR(r, r), old = F(r);
-          T f = old - res / Arr;
-          const int type = a.efc_type[o];
-          if (type == CN_FRICTION_DOF) { const T fl = a.efc_frictionloss[o]; f = t_min(fl, t_max(-fl, f)); }
-          else if (type != CN_EQUALITY) f = t_max(T(0), f);
-          const T delta = f - old;
+          J = Jn; B = Bn; M = Mn;
+          if (r + 1 < ne) load_row(r + 1, Jn, Bn, Mn);
+          dofs_of((int)M.v[META_T1], (int)M.v[META_T2], d);
+          T p = 0;
+#pragma unroll
+          for (int k = 0; k < EPL; k++) if (d[k] >= 0) p += J.v[k] * acc[d[k]];
+          const T old = f[r];
+          const T res = team_sum(p) + M.v[META_R] * old - M.v[META_AREF];
+          const T Arr = M.v[META_DIAG];
+          T fn = old - res / Arr;
+          const int type = (int)M.v[META_TYPE];
+          if (type == CN_FRICTION_DOF) { const T flv = M.v[META_FL]; fn = t_min(flv, t_max(-flv, fn)); }
+          else if (type != CN_EQUALITY) fn = t_max(T(0), fn);
+          const T delta = fn - old;
           const T change = T(0.5) * delta * delta * Arr + delta * res;
-          if (change > T(1e-10)) continue;
-          F(r) = f;
-          improvement -= change;
+          if (delta != 0 && !(change > T(1e-10))) {
+            if (l == 0) f[r] = fn;
+            improvement -= change;
+#pragma unroll
+            for (int k = 0; k < EPL; k++) if (d[k] >= 0) acc[d[k]] += delta * B.v[k];
+          }
+          __syncwarp(tmask);
         }
         iters = it + 1;
-        if (improvement * scale < m.f(h.o_opt_real, 3)) break;
+        if (improvement * scale < tol) break;
       }
+      // ---- qfrc_constraint = J^T f ----
+      for (int i = l; i < nv; i += TEAM) tmp[i] = 0;
+      __syncwarp(tmask);
+      for (int r = 0; r < ne; r++) {
+        const T fr = f[r];
+        if (l == 0) a.efc_force[(long long)r * S + env] = fr;
+        if (fr == 0) continue;
+        load_row(r, J, B, M);
+        dofs_of((int)M.v[META_T1], (int)M.v[META_T2], d);
+#pragma unroll
+        for (int k = 0; k < EPL; k++) if (d[k] >= 0) tmp[d[k]] += J.v[k] * fr;
+        __syncwarp(tmask);
+      }
+    } else {
+      for (int i = l; i < nv; i += TEAM) acc[i] = a.qacc_smooth[(long long)i * S + env];
     }
-    a.solver_iter[env] = iters;
+    __syncwarp(tmask);
+    for (int i = l; i < nv; i += TEAM) {
+      const T v = acc[i];
+      a.qacc[(long long)i * S + env] = v;
+      a.qacc_warmstart[(long long)i * S + env] = v;
+      a.qfrc_constraint[(long long)i * S + env] = tmp[i];
+    }
+    if (l == 0) a.solver_iter[env] = iters;
+    __syncwarp(tmask);
   }
 }
 
-// G7: qfrc_constraint = J^T f, qacc = qacc_smooth + M^-1 qfrc_constraint, warm start, Euler, odom override
+// G7: mj_checkAcc, semi-implicit Euler with implicit damping, odom override (one thread per environment)
 template <typename T, int BLOCK>
 __global__ void __launch_bounds__(BLOCK) k_integrate(const KArgs<T> a) {
   B2_KERNEL_PROLOGUE
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int env = tile * BLOCK + threadIdx.x;
-    const int ne = a.nefc[env], nv = h.nv;
-    SArr<T> qfc{a.qfrc_constraint + env, S}, qacc{a.qacc + env, S}, LD{a.qLD + env, S}, dinv{a.qLDiagInv + env, S};
-    for (int i = 0; i < nv; i++) qfc[i] = 0;
-    for (int r = 0; r < ne; r++) {
-      const T f = a.efc_force[(long long)r * S + env];
-      if (f == 0) continue;
-      for (int i = 0; i < nv; i++) qfc[i] += a.efc_J[((long long)r * nv + i) * S + env] * f;
-    }
-    if (ne > 0) {
-      for (int i = 0; i < nv; i++) qacc[i] = qfc[i];
-      ld_solve(m, LD, dinv, qacc);
-      for (int i = 0; i < nv; i++) qacc[i] += a.qacc_smooth[i * S + env];
-    } else {
-      for (int i = 0; i < nv; i++) qacc[i] = a.qacc_smooth[i * S + env];
-    }
+    const int nv = h.nv;
+    SArr<T> qacc{a.qacc + env, S};
     bool bad = false;
-    for (int i = 0; i < nv; i++) {
-      const T v = qacc[i];
-      bad |= !(t_abs(v) < T(1e10));
-      a.qacc_warmstart[i * S + env] = v;
-    }
-    if (bad) {  // mj_checkAcc: reset instead of integrating garbage
+    for (int i = 0; i < nv; i++) bad |= !(t_abs(qacc[i]) < T(1e10));
+    if (bad) {  // reset instead of integrating garbage
       for (int i = 0; i < h.nq; i++) a.qpos[i * S + env] = m.f(h.o_qpos0, i);
       for (int i = 0; i < nv; i++) { a.qvel[i * S + env] = 0; qacc[i] = 0; a.qacc_warmstart[i * S + env] = 0; a.qfrc_applied[i * S + env] = 0; }
       a.time[env] = 0;
@@ -483,15 +660,51 @@ __global__ void __launch_bounds__(BLOCK) k_integrate(const KArgs<T> a) {
       continue;
     }
     if (a.flags & B2F_INTEGRATE) {
-      SArr<T> qpos{a.qpos + env, S}, qvel{a.qvel + env, S}, qM{a.qM + env, S}, frc{a.qfrc_smooth + env, S};
-      // total force for the implicit-damping solve; qLD / qLDiagInv / efc_MiJT row 0 are free to be reused as scratch
-      for (int i = 0; i < nv; i++) frc[i] += qfc[i];
-      SArr<T> xa{a.qfrc_passive + env, S};
+      SArr<T> qpos{a.qpos + env, S}, qvel{a.qvel + env, S}, qM{a.qM + env, S}, LD{a.qLD + env, S}, dinv{a.qLDiagInv + env, S};
+      SArr<T> frc{a.qfrc_smooth + env, S}, xa{a.qacc_smooth + env, S};
+      // qfrc_smooth becomes the total force of the implicit-damping solve; qLD / qLDiagInv / qacc_smooth are dead after
+      // the solver and serve as scratch for the damped factorisation
+      if (h.has_damping) for (int i = 0; i < nv; i++) frc[i] += a.qfrc_constraint[i * S + env];
       euler_step(m, qpos, qvel, qM, qacc, frc, a.h, LD, dinv, xa);
       a.time[env] += a.h;
       if (a.flags & B2F_ODOM) odom_override(m, a, env);
     }
   }
+}
+
+// on-demand expansions for the legacy dense fields: efc_J [njmax][nv] and efc_AR [njmax][njmax], one thread per env
+template <typename T>
+__global__ void k_expand_rows(const KArgs<T> a, int which /* 0: J, 1: B */, T* dst /* [njmax * nv][nenvp] */) {
+  const DModel* h = reinterpret_cast<const DModel*>(a.model);
+  const uint32_t* w = a.model;
+  const int env = blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= a.nenvp) return;
+  const long long S = a.nenvp;
+  const int ne = a.nefc[env], nv = h->nv, WP = a.wp;
+  for (int r = 0; r < h->njmax; r++) {
+    for (int i = 0; i < nv; i++) dst[((long long)r * nv + i) * S + env] = 0;
+    if (r >= ne) continue;
+    const int t1 = a.efc_tree[((long long)2 * r) * S + env], t2 = a.efc_tree[((long long)2 * r + 1) * S + env];
+    Seg g{0, 0, 0, 0};
+    if (t1 >= 0) { g.s1 = (int)w[h->o_tree_dofadr + t1]; g.n1 = (int)w[h->o_tree_dofnum + t1]; }
+    if (t2 >= 0) { g.s2 = (int)w[h->o_tree_dofadr + t2]; g.n2 = (int)w[h->o_tree_dofnum + t2]; }
+    const T* row = a.efc_rows + ((long long)env * h->njmax + r) * (2 * WP) + (which ? WP : 0);
+    for (int k = 0; k < g.n1 + g.n2; k++) dst[((long long)r * nv + seg_dof(g, k)) * S + env] = row[k];
+  }
+}
+template <typename T>
+__global__ void k_dense_AR(const KArgs<T> a, const T* Jd, const T* Bd, T* AR /* [njmax * njmax][nenvp] */) {
+  const DModel* h = reinterpret_cast<const DModel*>(a.model);
+  const int env = blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= a.nenvp) return;
+  const long long S = a.nenvp;
+  const int ne = a.nefc[env], nv = h->nv, ld = h->njmax;
+  for (int r = 0; r < ne; r++)
+    for (int c = 0; c < ne; c++) {
+      T v = (r == c) ? a.efc_R[(long long)r * S + env] : T(0);
+      for (int i = 0; i < nv; i++) v += Jd[((long long)r * nv + i) * S + env] * Bd[((long long)c * nv + i) * S + env];
+      AR[((long long)r * ld + c) * S + env] = v;
+    }
 }
 
 }  // namespace b2
