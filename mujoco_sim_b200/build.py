@@ -16,7 +16,7 @@ ORACLE_LIB = os.path.join(ORACLE_DIR, "liboracle.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 CXX = os.environ.get("CXX", "g++")
 
-LIB_SOURCES = ["batch.cu", "shim_step.cpp", "shim_host.cpp", "mjcf_compile.cpp", "set0.cpp", "model_store.cpp"]
+LIB_SOURCES = ["batch.cu", "chain_f32.cu", "chain_f64.cu", "shim_step.cpp", "shim_host.cpp", "mjcf_compile.cpp", "set0.cpp", "model_store.cpp"]
 ORACLE_SOURCES = ["oracle_smooth.cpp", "oracle_collision.cpp", "oracle_constraint.cpp", "oracle_top.cpp"]
 
 
@@ -43,6 +43,7 @@ def build_lib(force=False, verbose_ptxas=False):
     os.makedirs(objdir, exist_ok=True)
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
     objs, relink = [], force or not os.path.exists(LIB)
+    jobs = []
     for s in LIB_SOURCES:
         src = os.path.join(CSRC, s)
         obj = os.path.join(objdir, s + ".o")
@@ -53,8 +54,12 @@ def build_lib(force=False, verbose_ptxas=False):
                    "-I" + os.path.join(ROOT, "include"), "-I" + CSRC, "-o", obj, src]
             if verbose_ptxas and s.endswith(".cu"):
                 cmd.insert(1, "-Xptxas=-v")
-            _run(cmd)
-            relink = True
+            jobs.append(cmd)
+    if jobs:
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
+            list(ex.map(_run, jobs))
+        relink = True
     if relink or _newer(LIB, objs):
         _run([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs)
     return LIB

@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -14,6 +15,7 @@
 #include <vector>
 
 #include "b2_batch.h"
+#include "batch_internal.h"
 #include "k_args.h"
 #include "k_collide.cuh"
 #include "k_common.cuh"
@@ -21,55 +23,20 @@
 #include "k_smooth.cuh"
 #include "model_store.h"
 
-namespace {
+namespace b2 {
 thread_local std::string g_err;
-int fail(const std::string& msg) { g_err = msg; return -1; }
+int set_error(const std::string& msg) { g_err = msg; return -1; }
+}  // namespace b2
+
+namespace {
+using b2::Field;
+int fail(const std::string& msg) { return b2::set_error(msg); }
 #define CK(call)                                                                                          \
   do {                                                                                                    \
     cudaError_t e_ = (call);                                                                              \
     if (e_ != cudaSuccess) return fail(std::string(#call) + ": " + cudaGetErrorString(e_));               \
   } while (0)
-
-struct Field {
-  void* ptr = nullptr;
-  int count = 0;   // elements per environment
-  int kind = 0;    // 0 real (batch precision), 1 int32
-};
 }  // namespace
-
-struct b2_batch {
-  const mjModel* m = nullptr;
-  int nenv = 0, nenvp = 0, device = 0, prec = 4, nsm = 148;
-  double h = 0.002;
-  cudaStream_t stream = nullptr;
-  b2::DModel hdr{};
-  std::vector<uint32_t> blob;
-  uint32_t* blob_dev = nullptr;
-  std::vector<unsigned char> controlled;
-  std::vector<int> odom_dof, odom_qpos;
-  std::map<std::string, Field> fields;
-  std::vector<void*> allocs;
-  int tick_flags = 0;
-  bool fused = false, ws_global = false, export_stages = false;
-  int wp = 16, epl = 2;  // solver team: 8 lanes x epl elements cover the compact row width
-  int smooth_block = 32;
-  size_t smooth_smem = 0, blob_smem = 0;
-  void* stage_dev = nullptr;
-  size_t stage_bytes = 0;
-  long long launches = 0;
-  int opt_iterations = 100, opt_disableflags = 0;
-  double opt_tolerance = 1e-8;
-  // hardware-interface joints
-  int nhw = 0;
-  int *hw_qadr = nullptr, *hw_dadr = nullptr, *hw_ctl = nullptr;
-  float* hw_buf = nullptr;  // [5][nhw][nenv] fp32 staging: vel_cmd, effort_cmd, pos, vel, effort
-  // per-kernel CUDA-event profiling (b2_profile_begin / b2_profile_end)
-  std::vector<cudaEvent_t> prof_ev;  // [max_ticks][B2_NSLOT + 1]
-  std::vector<unsigned> prof_mask;   // which boundary events of each tick were recorded
-  int prof_max = 0, prof_n = 0;
-  bool prof_on = false;
-  int prof_tick_open = -1;
-};
 
 enum { SLOT_HW_WRITE = 0, SLOT_SMOOTH, SLOT_COLLIDE, SLOT_MAKE, SLOT_PROJECT, SLOT_PGS, SLOT_INTEGRATE, SLOT_HW_READ, B2_NSLOT };
 // record the boundary event that precedes kernel slot `slot` of the tick being profiled
@@ -239,20 +206,27 @@ KArgs<T> make_args(b2_batch* b, int flags) {
   a.efc_frictionloss = R("efc_frictionloss"); a.efc_diagApprox = R("efc_diagApprox"); a.efc_R = R("efc_R"); a.efc_D = R("efc_D");
   a.efc_KBI = R("efc_KBI"); a.efc_vel = R("efc_vel"); a.efc_aref = R("efc_aref"); a.efc_b = R("efc_b"); a.efc_force = R("efc_force");
   a.efc_ARdiag = R("efc_ARdiag"); a.efc_rows = R("efc_rows"); a.efc_meta = R("efc_meta"); a.wp = b->wp; a.solver_iter = I("solver_iter"); a.status = I("status");
+  a.pending = I("_pending"); a.tick = b->tick;
   return a;
 }
 
-template <typename T, int BLOCK>
+template <typename T, int BLOCK, typename P>
 int launch_smooth(b2_batch* b, const KArgs<T>& a, int grid) {
   static bool attr_set[8] = {false};
   int dev = b->device & 7;
   if (!attr_set[dev]) {
-    CK(cudaFuncSetAttribute(k_smooth<T, BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CK(cudaFuncSetAttribute(k_smooth<T, BLOCK, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set[dev] = true;
   }
-  k_smooth<T, BLOCK><<<grid, BLOCK, b->smooth_smem, b->stream>>>(a);
+  k_smooth<T, BLOCK, P><<<grid, BLOCK, b->smooth_smem, b->stream>>>(a);
   b->launches++;
   return 0;
+}
+
+template <typename T>
+int launch_chain(b2_batch* b, const KArgs<T>& a, int grid) {
+  if constexpr (sizeof(T) == 4) return launch_chain_f32(b, a, grid);
+  else return launch_chain_f64(b, a, grid);
 }
 
 template <typename T>
@@ -265,6 +239,8 @@ int run_tick(b2_batch* b, int flags) {
   if (b->fused) kf |= B2F_FUSED;
   if (flags & B2_TICK_NOSOLVE) kf |= B2F_NOSOLVE;
   if (b->ws_global) kf |= B2F_WS_GLOBAL;
+  if (b->fusable) kf |= B2F_FUSABLE;
+  b->tick++;
   if (b->tick_flags & (1 << 30)) kf |= B2F_XFRC;  // set once xfrc_applied has been written
   if (b->export_stages) kf |= B2F_EXPORT;
   KArgs<T> a = make_args<T>(b, kf);
@@ -273,10 +249,11 @@ int run_tick(b2_batch* b, int flags) {
   const int grid = std::max(1, std::min(ntiles, b->nsm * per_sm));
   int rc;
   prof_mark(b, SLOT_SMOOTH);
-  switch (b->smooth_block) {
-    case 128: rc = launch_smooth<T, 128>(b, a, grid); break;
-    case 64: rc = launch_smooth<T, 64>(b, a, grid); break;
-    default: rc = launch_smooth<T, 32>(b, a, grid); break;
+  if (b->chain_n > 0) rc = launch_chain<T>(b, a, grid);
+  else switch (b->smooth_block) {
+    case 128: rc = launch_smooth<T, 128, GenericP>(b, a, grid); break;
+    case 64: rc = launch_smooth<T, 64, GenericP>(b, a, grid); break;
+    default: rc = launch_smooth<T, 32, GenericP>(b, a, grid); break;
   }
   if (rc < 0) return rc;
   if (!b->fused) {
@@ -285,10 +262,10 @@ int run_tick(b2_batch* b, int flags) {
     const int g2 = std::max(1, std::min(nt, b->nsm * 4));
     const size_t sm = b->blob_smem;
     prof_mark(b, SLOT_COLLIDE);
-    k_collide<T, BL><<<g2, BL, sm, b->stream>>>(a);
+    if (b->m->npair > 0) { k_collide<T, BL><<<g2, BL, sm, b->stream>>>(a); b->launches++; }
     prof_mark(b, SLOT_MAKE);
-    k_make_constraint<T, BL><<<g2, BL, sm + (size_t)2 * b->wp * (BL + 1) * sizeof(T), b->stream>>>(a);
-    b->launches += 2;
+    k_make_constraint<T, BL><<<g2, BL, sm + (size_t)(2 * b->wp + 8) * (BL + 1) * sizeof(T), b->stream>>>(a);
+    b->launches += 1;
     if (!(flags & B2_TICK_NOSOLVE)) {
       prof_mark(b, SLOT_PGS);
       const size_t smp = sm + ((size_t)2 * (b->hdr.nv + 4) + b->hdr.njmax) * (BL / 8) * sizeof(T);
@@ -485,7 +462,7 @@ __global__ void k_hw_read(const D* qpos, const D* qvel, const D* qfrc_inverse, f
 
 extern "C" {
 
-const char* b2_last_error(void) { return g_err.c_str(); }
+const char* b2_last_error(void) { return b2::g_err.c_str(); }
 
 int b2_device_count(void) {
   int n = 0;
@@ -517,7 +494,7 @@ b2_batch* b2_create(const mjModel* m, int nenv, int device, int precision) {
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) b->nsm = prop.multiProcessorCount;
   auto bail = [&](const char* what) -> b2_batch* {
-    if (g_err.empty()) fail(what);
+    if (b2::g_err.empty()) fail(what);
     b2_destroy(b);
     return nullptr;
   };
@@ -533,6 +510,20 @@ b2_batch* b2_create(const mjModel* m, int nenv, int device, int precision) {
   for (int j = 0; j < m->njnt; j++) any_lim |= m->jnt_limited[j] != 0;
   for (int i = 0; i < nv; i++) any_fl |= m->dof_frictionloss[i] > 0;
   b->fused = (m->opt.disableflags & mjDSBL_CONSTRAINT) || !(any_pair || any_lim || any_fl || m->neq > 0);
+  bool ball_lim = false;
+  for (int j = 0; j < m->njnt; j++) ball_lim |= m->jnt_limited[j] && m->jnt_type[j] == mjJNT_BALL;
+  b->fusable = !b->fused && !any_pair && !any_fl && m->neq == 0 && !ball_lim;
+  // serial chain of scalar joints?
+  {
+    bool chain = m->nbody >= 2 && m->nv == m->nbody - 1 && m->njnt == m->nbody - 1 && m->nq == m->nv && m->nmocap == 0;
+    for (int i = 1; i < m->nbody && chain; i++)
+      chain = m->body_parentid[i] == i - 1 && m->body_jntnum[i] == 1 && m->body_jntadr[i] == i - 1 && m->body_dofadr[i] == i - 1 &&
+              (m->jnt_type[i - 1] == mjJNT_HINGE || m->jnt_type[i - 1] == mjJNT_SLIDE);
+    const int n = m->nbody - 1;
+    const bool have = have_chain_kernel(n, precision);
+    b->chain_n = (chain && have && !getenv("B2_NO_CHAIN")) ? n : 0;
+    b->chain_variant = getenv("B2_CHAIN_VARIANT") ? atoi(getenv("B2_CHAIN_VARIANT")) : 0;
+  }
 
   b->epl = 2;
   while (8 * b->epl < b->hdr.wmax) b->epl *= 2;
@@ -543,7 +534,7 @@ b2_batch* b2_create(const mjModel* m, int nenv, int device, int precision) {
       {"qpos", nq, 0}, {"qvel", nv, 0}, {"qacc", nv, 0}, {"qacc_warmstart", nv, 0}, {"qfrc_applied", nv, 0},
       {"xfrc_applied", 6 * nb, 0}, {"mocap_pos", 3 * std::max(1, m->nmocap), 0}, {"mocap_quat", 4 * std::max(1, m->nmocap), 0},
       {"ddq", nv, 0}, {"dq", nv, 0}, {"odom_vels", 6, 0}, {"time", 1, 0}, {"qfrc_bias", nv, 0}, {"qfrc_inverse", nv, 0},
-      {"xpos", 3 * nb, 0}, {"xquat", 4 * nb, 0}, {"status", 1, 1}, {"solver_iter", 1, 1}, {"ncon", 1, 1}, {"nefc", 1, 1}};
+      {"xpos", 3 * nb, 0}, {"xquat", 4 * nb, 0}, {"_pending", 1, 1}, {"status", 1, 1}, {"solver_iter", 1, 1}, {"ncon", 1, 1}, {"nefc", 1, 1}};
   if (!b->fused || b->export_stages) {
     std::vector<Spec> more = {
         {"xmat", 9 * nb, 0}, {"geom_xpos", 3 * std::max(1, ng), 0}, {"geom_xmat", 9 * std::max(1, ng), 0}, {"subtree_com", 3 * nb, 0},
@@ -575,7 +566,12 @@ b2_batch* b2_create(const mjModel* m, int nenv, int device, int precision) {
     // prefer a smaller CTA when the batch cannot fill the SMs with the larger one
     if (b->nenvp / block < b->nsm && cand < block) block = cand;
   }
-  if (block) {
+  if (b->chain_n > 0) {
+    // register-resident chain kernel: shared memory holds the model blob only
+    b->smooth_block = (precision == 8 || b->nenvp / 128 < 2 * b->nsm) ? 32 : 128;
+    b->smooth_smem = b->blob_smem;
+    b->ws_global = false;
+  } else if (block) {
     b->smooth_block = block;
     b->smooth_smem = b->blob_smem + (size_t)b->hdr.ws_slots * block * precision;
     b->ws_global = false;
@@ -588,7 +584,7 @@ b2_batch* b2_create(const mjModel* m, int nenv, int device, int precision) {
   {
     // the constraint-pipeline kernels stage the same blob; row assembly and the solver add their shared vectors
     const int need1 = (int)b->blob_smem;
-    const int need2 = (int)(b->blob_smem + (size_t)2 * b->wp * 129 * precision);
+    const int need2 = (int)(b->blob_smem + (size_t)(2 * b->wp + 8) * 129 * precision);
     const int need3 = (int)(b->blob_smem + ((size_t)2 * (nv + 4) + b->hdr.njmax) * 16 * precision);
     if (need2 > 227 * 1024 || need3 > 227 * 1024) return bail("model too large for the constraint kernels' shared memory");
     bool ok = true;

@@ -1,0 +1,65 @@
+// batch_internal.h — host-side state of a batch, shared by the translation units that launch kernels.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "b2_batch.h"
+#include "dmodel.h"
+#include "k_args.h"
+
+namespace b2 {
+struct Field {
+  void* ptr = nullptr;
+  int count = 0;   // elements per environment
+  int kind = 0;    // 0 real (batch precision), 1 int32
+};
+int set_error(const std::string& msg);  // stores the text for b2_last_error(), returns -1
+}  // namespace b2
+
+struct b2_batch {
+  const mjModel* m = nullptr;
+  int nenv = 0, nenvp = 0, device = 0, prec = 4, nsm = 148;
+  double h = 0.002;
+  cudaStream_t stream = nullptr;
+  b2::DModel hdr{};
+  std::vector<uint32_t> blob;
+  uint32_t* blob_dev = nullptr;
+  std::vector<unsigned char> controlled;
+  std::vector<int> odom_dof, odom_qpos;
+  std::map<std::string, b2::Field> fields;
+  std::vector<void*> allocs;
+  int tick_flags = 0;
+  bool fused = false, ws_global = false, export_stages = false;
+  int chain_n = 0;       // > 0: the model is a serial chain of chain_n scalar joints (ChainP<chain_n> kernels)
+  int chain_variant = 0; // register budget variant of the chain kernel (B2_CHAIN_VARIANT)
+  bool fusable = false;  // joint limits are the only constraint source
+  int tick = 0;
+  int wp = 16, epl = 2;  // solver team: 8 lanes x epl elements cover the compact row width
+  int smooth_block = 32;
+  size_t smooth_smem = 0, blob_smem = 0;
+  void* stage_dev = nullptr;
+  size_t stage_bytes = 0;
+  long long launches = 0;
+  int opt_iterations = 100, opt_disableflags = 0;
+  double opt_tolerance = 1e-8;
+  // hardware-interface joints
+  int nhw = 0;
+  int *hw_qadr = nullptr, *hw_dadr = nullptr, *hw_ctl = nullptr;
+  float* hw_buf = nullptr;  // [5][nhw][nenv] fp32 staging: vel_cmd, effort_cmd, pos, vel, effort
+  // per-kernel CUDA-event profiling (b2_profile_begin / b2_profile_end)
+  std::vector<cudaEvent_t> prof_ev;  // [max_ticks][B2_NSLOT + 1]
+  std::vector<unsigned> prof_mask;   // which boundary events of each tick were recorded
+  int prof_max = 0, prof_n = 0;
+  bool prof_on = false;
+  int prof_tick_open = -1;
+};
+
+namespace b2 {
+// serial-chain kernels live in their own translation units (chain_f32.cu / chain_f64.cu): they are the slowest to compile
+int launch_chain_f32(b2_batch* b, const KArgs<float>& a, int grid);
+int launch_chain_f64(b2_batch* b, const KArgs<double>& a, int grid);
+bool have_chain_kernel(int n, int precision);
+}  // namespace b2

@@ -1,0 +1,29 @@
+// chain_f64.cu — fp64 instantiations of the register-resident serial-chain smooth kernel (k_smooth.cuh, ChainP<N>).
+#include <cuda_runtime.h>
+
+#include "batch_internal.h"
+#include "k_smooth.cuh"
+
+namespace b2 {
+namespace {
+template <typename T, int BLOCK, typename P>
+int launch(b2_batch* b, const KArgs<T>& a, int grid) {
+  static bool attr_set[8] = {false};
+  const int dev = b->device & 7;
+  if (!attr_set[dev]) {
+    if (cudaFuncSetAttribute(k_smooth<T, BLOCK, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess)
+      return set_error("cudaFuncSetAttribute(k_smooth chain) failed");
+    attr_set[dev] = true;
+  }
+  k_smooth<T, BLOCK, P><<<grid, BLOCK, b->smooth_smem, b->stream>>>(a);
+  b->launches++;
+  return 0;
+}
+}  // namespace
+
+int launch_chain_f64(b2_batch* b, const KArgs<double>& a, int grid) {
+  if (b->chain_n == 7) return launch<double, 32, ChainP<7>>(b, a, grid);
+  return set_error("no fp64 chain kernel for this chain length");
+}
+
+}  // namespace b2

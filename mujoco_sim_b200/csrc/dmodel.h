@@ -37,8 +37,7 @@ namespace b2 {
   X(xpos, 3 * nbody) X(xquat, 4 * nbody) X(xmat, 9 * nbody) X(xipos, 3 * nbody) X(ximat, 9 * nbody)            \
   X(xanchor, 3 * njnt) X(xaxis, 3 * njnt) X(subtree_com, 3 * nbody) X(cinert, 10 * nbody) X(crb, 10 * nbody)   \
   X(cdof, 6 * nv) X(cvel, 6 * nbody) X(cdof_dot, 6 * nv) X(cacc, 6 * nbody) X(cfrc, 6 * nbody)                 \
-  X(qM, nM) X(qLD, nM) X(qLDiagInv, nv) X(qfrc_passive, nv) X(qfrc_smooth, nv) X(qacc_smooth, nv)              \
-  X(qfrc_constraint, nv) X(tmpv, nv) X(geom_xpos, 3 * ngeom) X(geom_xmat, 9 * ngeom)
+  X(qM, nM) X(qLD, nM) X(qLDiagInv, nv) X(qfrc_passive, nv) X(qfrc_smooth, nv) X(qacc_smooth, nv) X(tmpv, nv)
 
 struct DModel {
   // sizes

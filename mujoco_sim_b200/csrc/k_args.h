@@ -15,7 +15,9 @@ enum TickFlags : int {
   B2F_XFRC = 1 << 5,         // xfrc_applied is non-zero somewhere
   B2F_WS_GLOBAL = 1 << 6,    // workspace in HBM instead of shared memory
   B2F_EXPORT = 1 << 7,
-  B2F_NOSOLVE = 1 << 8,      // stop after constraint assembly (mj_step1)       // also export the stage arrays from the fused kernel (legacy mjData mirror)
+  B2F_NOSOLVE = 1 << 8,      // stop after constraint assembly (mj_step1)
+  B2F_FUSABLE = 1 << 9,      // joint limits are the only constraint source: environments without an active limit are
+                             // integrated by the smooth kernel (status bit 8) and skipped by the constraint pipeline       // also export the stage arrays from the fused kernel (legacy mjData mirror)
 };
 
 // contact record, SoA: field f of contact c of env e at con[(f * nconmax + c) * nenvp + e]
@@ -59,7 +61,10 @@ struct KArgs {
   T* efc_meta;            // [nenvp][njmax][8]   {R, aref, diag(AR), frictionloss, type, tree1, tree2, b}
   int wp;                 // padded compact row width: 8 * EPL of the solver team
   int* solver_iter;       // [nenvp]
-  int* status;            // [nenvp] bit 0: contact cap hit, bit 1: row cap hit, bit 2: state reset (bad value)
+  int* status;            // [nenvp] bit 0: contact cap hit, bit 1: row cap hit, bit 2: state reset (bad value),
+                          //         bit 3: integrated by the smooth kernel this tick (B2F_FUSABLE)
+  int* pending;           // [2] environments that need the constraint pipeline, by tick parity (B2F_FUSABLE)
+  int tick;               // tick counter of this launch
 };
 
 }  // namespace b2

@@ -192,11 +192,11 @@ template <typename T> __device__ __forceinline__ void cross_force(T* res, const 
   res[3] = c[0]; res[4] = c[1]; res[5] = c[2];
 }
 
-template <typename T, int N> __device__ __forceinline__ void ld(T* r, const SArr<T>& a, int base) {
+template <typename T, int N, typename A> __device__ __forceinline__ void ld(T* r, const A& a, int base) {
 #pragma unroll
   for (int k = 0; k < N; k++) r[k] = a[base + k];
 }
-template <typename T, int N> __device__ __forceinline__ void st(const SArr<T>& a, int base, const T* r) {
+template <typename T, int N, typename A> __device__ __forceinline__ void st(const A& a, int base, const T* r) {
 #pragma unroll
   for (int k = 0; k < N; k++) a[base + k] = r[k];
 }

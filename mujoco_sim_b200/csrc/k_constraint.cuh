@@ -354,6 +354,7 @@ __device__ __forceinline__ T primal_force(int type, T jar, T D, T R, T fl) {
 }
 
 #define B2_KERNEL_PROLOGUE                                                           \
+  if ((a.flags & B2F_FUSABLE) && a.pending[a.tick & 1] == 0) return;                 \
   extern __shared__ __align__(16) unsigned char smem_raw[];                          \
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);                             \
   uint32_t* blob = reinterpret_cast<uint32_t*>(smem_raw + 16);                       \
@@ -380,12 +381,13 @@ __global__ void __launch_bounds__(BLOCK) k_make_constraint(const KArgs<T> a) {
   B2_KERNEL_PROLOGUE
   const int WP = a.wp;
   constexpr int LDS = BLOCK + 1;  // +1: conflict-free both for per-thread columns and for the transposed row reads
-  T* rowsh = reinterpret_cast<T*>(smem_raw + 16 + (size_t)nwords * 4);  // [2 * WP][LDS]
+  T* rowsh = reinterpret_cast<T*>(smem_raw + 16 + (size_t)nwords * 4);  // [2 * WP + META_N][LDS]: J | B | meta
   const int lane = threadIdx.x & 31, wbase = threadIdx.x & ~31;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int env = tile * BLOCK + threadIdx.x;
     Rows<T> rows(m, a, env);
-    if (!(h.disableflags & DSBL_CONSTRAINT)) {
+    const bool done = (a.flags & B2F_FUSABLE) && (a.status[env] & 8);  // already integrated by the smooth kernel
+    if (!(h.disableflags & DSBL_CONSTRAINT) && !done) {
       rows.equality();
       rows.friction_loss();
       rows.limits();
@@ -393,7 +395,7 @@ __global__ void __launch_bounds__(BLOCK) k_make_constraint(const KArgs<T> a) {
       rows.finish();
     }
     const int ne = rows.nefc, W = h.wmax;
-    a.nefc[env] = ne;
+    if (!done) a.nefc[env] = ne;
     SArr<T> LD{a.qLD + env, S}, dinv{a.qLDiagInv + env, S};
     SArr<T> Jr{rowsh + threadIdx.x, LDS}, Br{rowsh + (size_t)WP * LDS + threadIdx.x, LDS};
     int nemax = ne;
@@ -456,30 +458,21 @@ __global__ void __launch_bounds__(BLOCK) k_make_constraint(const KArgs<T> a) {
         a.efc_ARdiag[o] = dg;
       }
       // ---- transpose out: lanes cooperate on one environment's row at a time (coalesced line stores) ----
+      {
+        SArr<T> Mr{rowsh + (size_t)2 * WP * LDS + threadIdx.x, LDS};
+        Mr[META_R] = R; Mr[META_AREF] = aref; Mr[META_DIAG] = dg; Mr[META_FL] = fl;
+        Mr[META_TYPE] = (T)type; Mr[META_T1] = (T)t1; Mr[META_T2] = (T)t2; Mr[META_B] = bb;
+      }
       __syncwarp();
-      for (int e = 0; e < 32; e++) {
-        const int ne_e = __shfl_sync(0xffffffffu, ne, e);
-        // the meta record of environment e is assembled from lane e's registers
-        const T mR = __shfl_sync(0xffffffffu, R, e), mA = __shfl_sync(0xffffffffu, aref, e), mD = __shfl_sync(0xffffffffu, dg, e);
-        const T mF = __shfl_sync(0xffffffffu, fl, e), mB = __shfl_sync(0xffffffffu, bb, e);
-        const int mT = __shfl_sync(0xffffffffu, type, e), m1 = __shfl_sync(0xffffffffu, t1, e), m2 = __shfl_sync(0xffffffffu, t2, e);
-        if (r >= ne_e) continue;
+      const unsigned live = __ballot_sync(0xffffffffu, r < ne);
+      for (unsigned rem = live; rem; rem &= rem - 1) {
+        const int e = __ffs(rem) - 1;
         const long long env_e = (long long)tile * BLOCK + wbase + e;
         T* dst = a.efc_rows + (env_e * h.njmax + r) * (2 * WP);
-        for (int l = lane; l < 2 * WP; l += 32) dst[l] = rowsh[(size_t)l * LDS + wbase + e];
-        if (lane < META_N) {
-          T v;
-          switch (lane) {
-            case META_R: v = mR; break;
-            case META_AREF: v = mA; break;
-            case META_DIAG: v = mD; break;
-            case META_FL: v = mF; break;
-            case META_TYPE: v = (T)mT; break;
-            case META_T1: v = (T)m1; break;
-            case META_T2: v = (T)m2; break;
-            default: v = mB;
-          }
-          a.efc_meta[(env_e * h.njmax + r) * META_N + lane] = v;
+        T* dstm = a.efc_meta + (env_e * h.njmax + r) * META_N;
+        for (int l = lane; l < 2 * WP + META_N; l += 32) {
+          const T v = rowsh[(size_t)l * LDS + wbase + e];
+          if (l < 2 * WP) dst[l] = v; else dstm[l - 2 * WP] = v;
         }
       }
       __syncwarp();
@@ -519,6 +512,7 @@ __global__ void __launch_bounds__(BLOCK) k_pgs_team(const KArgs<T> a) {
   };
   for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
     const long long env = (long long)grp * EPB + team;  // nenvp is a multiple of 128 >= EPB: always in range
+    if ((a.flags & B2F_FUSABLE) && (a.status[env] & 8)) continue;  // integrated by the smooth kernel (team-uniform)
     const int ne = a.nefc[env];
     const T* rowp = a.efc_rows + env * njmax * (2 * WP);
     const T* metap = a.efc_meta + env * njmax * META_N;
@@ -649,6 +643,7 @@ __global__ void __launch_bounds__(BLOCK) k_integrate(const KArgs<T> a) {
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int env = tile * BLOCK + threadIdx.x;
     const int nv = h.nv;
+    if ((a.flags & B2F_FUSABLE) && (a.status[env] & 8)) continue;
     SArr<T> qacc{a.qacc + env, S};
     bool bad = false;
     for (int i = 0; i < nv; i++) bad |= !(t_abs(qacc[i]) < T(1e10));
@@ -665,7 +660,7 @@ __global__ void __launch_bounds__(BLOCK) k_integrate(const KArgs<T> a) {
       // qfrc_smooth becomes the total force of the implicit-damping solve; qLD / qLDiagInv / qacc_smooth are dead after
       // the solver and serve as scratch for the damped factorisation
       if (h.has_damping) for (int i = 0; i < nv; i++) frc[i] += a.qfrc_constraint[i * S + env];
-      euler_step(m, qpos, qvel, qM, qacc, frc, a.h, LD, dinv, xa);
+      euler_step<GenericP>(m, qpos, qvel, qM, qacc, frc, a.h, LD, dinv, xa);
       a.time[env] += a.h;
       if (a.flags & B2F_ODOM) odom_override(m, a, env);
     }

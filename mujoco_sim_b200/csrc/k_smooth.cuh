@@ -1,76 +1,87 @@
-// k_smooth.cuh — fused smooth-dynamics kernel (group G1 of SURVEY.md section 8a', plus G7 when the model has no
-// constraint source): forward kinematics, CoM quantities, CRBA, sparse LtDL, CoM velocities, passive forces incl.
-// gravity compensation, RNE bias, the reference's PD computed-torque controller (src/mujoco_sim/mj_sim.cpp:1055-1077),
+// k_smooth.cuh — fused smooth-dynamics kernel (group G1 of SURVEY.md section 8a', plus G7 when no constraint is
+// active): forward kinematics, CoM quantities, CRBA, sparse LtDL, CoM velocities, passive forces incl. gravity
+// compensation, RNE bias, the reference's PD computed-torque controller (src/mujoco_sim/mj_sim.cpp:1055-1077),
 // inverse dynamics for MjHWInterface::read (src/mujoco_sim/mj_hw_interface.cpp:61), smooth acceleration and, for
-// contact-free models, semi-implicit Euler + odom override.  One thread per environment; every per-environment
-// intermediate lives in a strided workspace (shared memory when it fits, HBM otherwise); the model constants are
-// TMA-staged into shared memory once per persistent CTA.
+// environments without active constraints, semi-implicit Euler + odom override.  One thread per environment; the
+// model constants are TMA-staged into shared memory once per persistent CTA.  The same source is compiled under the
+// two policies of k_policy.cuh (generic tree tables + strided workspace, or compile-time serial chain in registers).
 #pragma once
 #include "k_args.h"
 #include "k_common.cuh"
+#include "k_policy.cuh"
 
 namespace b2 {
 
-
 // in-place sparse LtDL factorisation of the matrix stored in LD (tree order), dinv = 1 / D  (mj_factorM, A.4)
-template <typename T>
-__device__ void ld_factor(const MV<T>& m, const SArr<T>& LD, const SArr<T>& dinv) {
-  const DModel& h = *m.h;
-  for (int k = h.nv - 1; k >= 0; k--) {
-    const int Mkk = m.i(h.o_dof_Madr, k);
+template <typename P, typename T, typename A1, typename A2>
+__device__ __forceinline__ void ld_factor(const MV<T>& m, const A1& LD, const A2& dinv) {
+#pragma unroll(P::UNROLL)
+  for (int k = P::nv(m) - 1; k >= 0; k--) {
+    const int Mkk = P::dof_Madr(m, k);
     const T inv = T(1) / LD[Mkk];
     int Mki = Mkk + 1;
-    for (int i = m.i(h.o_dof_parentid, k); i >= 0; i = m.i(h.o_dof_parentid, i), Mki++) {
+#pragma unroll(P::UNROLL)
+    for (int i = P::dof_parentid(m, k); i >= 0; i = P::dof_parentid(m, i), Mki++) {
       const T tmp = LD[Mki] * inv;
-      int Mij = m.i(h.o_dof_Madr, i), Mkj = Mki;
-      for (int j = i; j >= 0; j = m.i(h.o_dof_parentid, j)) { LD[Mij] -= LD[Mkj] * tmp; Mij++; Mkj++; }
+      int Mij = P::dof_Madr(m, i), Mkj = Mki;
+#pragma unroll(P::UNROLL)
+      for (int j = i; j >= 0; j = P::dof_parentid(m, j)) { LD[Mij] -= LD[Mkj] * tmp; Mij++; Mkj++; }
       LD[Mki] = tmp;
     }
     dinv[k] = inv;
   }
 }
 // x <- M^-1 x by back / forward substitution on the factor (mj_solveM)
-template <typename T>
-__device__ void ld_solve(const MV<T>& m, const SArr<T>& LD, const SArr<T>& dinv, const SArr<T>& x) {
-  const DModel& h = *m.h;
-  const int nv = h.nv;
+template <typename P, typename T, typename A1, typename A2, typename A3>
+__device__ __forceinline__ void ld_solve(const MV<T>& m, const A1& LD, const A2& dinv, const A3& x) {
+  const int nv = P::nv(m);
+#pragma unroll(P::UNROLL)
   for (int i = nv - 1; i >= 0; i--) {
     const T xi = x[i];
-    if (xi == 0) continue;
-    int adr = m.i(h.o_dof_Madr, i) + 1;
-    for (int j = m.i(h.o_dof_parentid, i); j >= 0; j = m.i(h.o_dof_parentid, j)) x[j] -= LD[adr++] * xi;
+    if (!P::STATIC && xi == 0) continue;
+    int adr = P::dof_Madr(m, i) + 1;
+#pragma unroll(P::UNROLL)
+    for (int j = P::dof_parentid(m, i); j >= 0; j = P::dof_parentid(m, j)) x[j] -= LD[adr++] * xi;
   }
+#pragma unroll(P::UNROLL)
   for (int i = 0; i < nv; i++) x[i] *= dinv[i];
+#pragma unroll(P::UNROLL)
   for (int i = 0; i < nv; i++) {
-    int adr = m.i(h.o_dof_Madr, i) + 1;
+    int adr = P::dof_Madr(m, i) + 1;
     T xi = x[i];
-    for (int j = m.i(h.o_dof_parentid, i); j >= 0; j = m.i(h.o_dof_parentid, j)) xi -= LD[adr++] * x[j];
+#pragma unroll(P::UNROLL)
+    for (int j = P::dof_parentid(m, i); j >= 0; j = P::dof_parentid(m, j)) xi -= LD[adr++] * x[j];
     x[i] = xi;
   }
 }
 
 // semi-implicit Euler with implicit joint damping (A.9): solves (M + h D) a = frc when any dof is damped, else uses
 // qacc_in; then qvel += h a, qpos (+)= h qvel (quaternion-aware).  LDtmp / dinvtmp / xa are scratch.
-template <typename T>
-__device__ void euler_step(const MV<T>& m, const SArr<T>& qpos, const SArr<T>& qvel, const SArr<T>& qM,
-                           const SArr<T>& qacc_in, const SArr<T>& frc, T hs, const SArr<T>& LDtmp,
-                           const SArr<T>& dinvtmp, const SArr<T>& xa) {
+template <typename P, typename T, typename AQ, typename AV, typename AM, typename AA, typename AF, typename AL, typename AD, typename AX>
+__device__ __forceinline__ void euler_step(const MV<T>& m, const AQ& qpos, const AV& qvel, const AM& qM, const AA& qacc_in,
+                                           const AF& frc, T hs, const AL& LDtmp, const AD& dinvtmp, const AX& xa) {
   const DModel& h = *m.h;
-  const int nv = h.nv;
+  const int nv = P::nv(m);
   const bool damp = h.has_damping && !(h.disableflags & DSBL_EULERDAMP);
   if (damp) {
-    for (int i = 0; i < h.nM; i++) LDtmp[i] = qM[i];
-    for (int i = 0; i < nv; i++) LDtmp[m.i(h.o_dof_Madr, i)] += hs * m.f(h.o_dof_damping, i);
-    ld_factor(m, LDtmp, dinvtmp);
+#pragma unroll(P::UNROLL)
+    for (int i = 0; i < P::nM(m); i++) LDtmp[i] = qM[i];
+#pragma unroll(P::UNROLL)
+    for (int i = 0; i < nv; i++) LDtmp[P::dof_Madr(m, i)] += hs * m.f(h.o_dof_damping, i);
+    ld_factor<P>(m, LDtmp, dinvtmp);
+#pragma unroll(P::UNROLL)
     for (int i = 0; i < nv; i++) xa[i] = frc[i];
-    ld_solve(m, LDtmp, dinvtmp, xa);
+    ld_solve<P>(m, LDtmp, dinvtmp, xa);
   } else {
+#pragma unroll(P::UNROLL)
     for (int i = 0; i < nv; i++) xa[i] = qacc_in[i];
   }
+#pragma unroll(P::UNROLL)
   for (int i = 0; i < nv; i++) qvel[i] += hs * xa[i];
-  for (int j = 0; j < h.njnt; j++) {
-    const int qa = m.i(h.o_jnt_qposadr, j), da = m.i(h.o_jnt_dofadr, j), jt = m.i(h.o_jnt_type, j);
-    if (jt == JNT_FREE || jt == JNT_BALL) {
+#pragma unroll(P::UNROLL)
+  for (int j = 0; j < P::njnt(m); j++) {
+    const int qa = P::jnt_qposadr(m, j), da = P::jnt_dofadr(m, j), jt = P::jnt_type(m, j);
+    if (!P::STATIC && (jt == JNT_FREE || jt == JNT_BALL)) {
       int qo = qa, dofo = da;
       if (jt == JNT_FREE) {
         for (int k = 0; k < 3; k++) qpos[qa + k] += hs * qvel[da + k];
@@ -87,42 +98,56 @@ __device__ void euler_step(const MV<T>& m, const SArr<T>& qpos, const SArr<T>& q
   }
 }
 
-template <typename T>
+template <typename T, typename P>
 struct Smooth {
+  static constexpr int nbody = P::NBODY, njnt = P::NJNT, nv = P::NV, nM = P::NM, nq = P::NQ;
   MV<T> m;
   const DModel& h;
   const KArgs<T>& a;
-  // state (HBM)
-  SArr<T> qpos, qvel, qacc, qfrc_applied;
-  // workspace
-#define X(name, count) SArr<T> name;
+  // state: views of the HBM arrays (GenericP) or thread-private copies loaded once (ChainP)
+  typename P::template Arr<T, nq> qpos;
+  typename P::template Arr<T, nv> qvel, qacc, qfrc_applied, qfrc_bias;
+#define X(name, count) typename P::template Arr<T, (count)> name;
   B2_WS_ARRAYS(X)
 #undef X
 
-  __device__ Smooth(const MV<T>& mv, const KArgs<T>& args, T* wsbase, long long wsstride, int env)
+  __device__ __forceinline__ Smooth(const MV<T>& mv, const KArgs<T>& args, T* wsbase, long long wsstride, int env)
       : m(mv), h(*mv.h), a(args) {
     const long long s = args.nenvp;
-    qpos = SArr<T>{args.qpos + env, s};
-    qvel = SArr<T>{args.qvel + env, s};
-    qacc = SArr<T>{args.qacc + env, s};
-    qfrc_applied = SArr<T>{args.qfrc_applied + env, s};
+    if constexpr (!P::STATIC) {
+      qpos = SArr<T>{args.qpos + env, s};
+      qvel = SArr<T>{args.qvel + env, s};
+      qacc = SArr<T>{args.qacc + env, s};
+      qfrc_applied = SArr<T>{args.qfrc_applied + env, s};
+      qfrc_bias = SArr<T>{args.qfrc_bias + env, s};
 #define X(name, count) name = SArr<T>{wsbase + (long long)h.w_##name * wsstride, wsstride};
-    B2_WS_ARRAYS(X)
+      B2_WS_ARRAYS(X)
 #undef X
+    } else {
+#pragma unroll
+      for (int i = 0; i < nq; i++) qpos[i] = args.qpos[i * s + env];
+#pragma unroll
+      for (int i = 0; i < nv; i++) {
+        qvel[i] = args.qvel[i * s + env];
+        qacc[i] = args.qacc[i * s + env];
+        qfrc_applied[i] = args.qfrc_applied[i * s + env];
+      }
+    }
   }
 
   // ---- forward kinematics ----
-  __device__ void kinematics(int env) {
-    const int nb = h.nbody;
+  __device__ __forceinline__ void kinematics(int env) {
+    const int nb = P::nbody(m);
     {
       const T z3[3] = {0, 0, 0}, q1[4] = {1, 0, 0, 0}, I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
       st<T, 3>(xpos, 0, z3); st<T, 4>(xquat, 0, q1); st<T, 9>(xmat, 0, I); st<T, 3>(xipos, 0, z3); st<T, 9>(ximat, 0, I);
     }
+#pragma unroll(P::UNROLL)
     for (int b = 1; b < nb; b++) {
-      const int p = m.i(h.o_body_parentid, b), jn = m.i(h.o_body_jntnum, b), ja = m.i(h.o_body_jntadr, b);
+      const int p = P::body_parentid(m, b), jn = P::body_jntnum(m, b), ja = P::body_jntadr(m, b);
       T pos[3], quat[4];
-      if (jn == 1 && m.i(h.o_jnt_type, ja) == JNT_FREE) {
-        const int qa = m.i(h.o_jnt_qposadr, ja);
+      if (!P::STATIC && jn == 1 && P::jnt_type(m, ja) == JNT_FREE) {
+        const int qa = P::jnt_qposadr(m, ja);
         ld<T, 3>(pos, qpos, qa);
         ld<T, 4>(quat, qpos, qa + 3);
         normalize4(quat);
@@ -132,7 +157,7 @@ struct Smooth {
         st<T, 3>(xaxis, 3 * ja, ax);
       } else {
         T bp[3], bq[4], pm[9], pp[3], pq[4], r[3];
-        const int mid = m.i(h.o_body_mocapid, b);
+        const int mid = P::body_mocapid(m, b);
         if (mid >= 0) {
           SArr<T> mp{a.mocap_pos + env, a.nenvp}, mq{a.mocap_quat + env, a.nenvp};
           ld<T, 3>(bp, mp, 3 * mid);
@@ -148,8 +173,9 @@ struct Smooth {
         mat_vec3(r, pm, bp);
         pos[0] = pp[0] + r[0]; pos[1] = pp[1] + r[1]; pos[2] = pp[2] + r[2];
         mul_quat(quat, pq, bq);
+#pragma unroll(P::UNROLL)
         for (int j = ja; j < ja + jn; j++) {
-          const int qa = m.i(h.o_jnt_qposadr, j), jt = m.i(h.o_jnt_type, j);
+          const int qa = P::jnt_qposadr(m, j), jt = P::jnt_type(m, j);
           T jp[3], jx[3], anchor[3], axis[3];
           ldm<T, 3>(jp, m, h.o_jnt_pos, 3 * j);
           ldm<T, 3>(jx, m, h.o_jnt_axis, 3 * j);
@@ -163,7 +189,7 @@ struct Smooth {
             pos[0] += axis[0] * dq; pos[1] += axis[1] * dq; pos[2] += axis[2] * dq;
           } else {
             T ql[4], qn[4], off[3];
-            if (jt == JNT_BALL) { ld<T, 4>(ql, qpos, qa); normalize4(ql); }
+            if (!P::STATIC && jt == JNT_BALL) { ld<T, 4>(ql, qpos, qa); normalize4(ql); }
             else axis_angle2quat(ql, jx, qpos[qa] - m.f(h.o_qpos0, qa));
             mul_quat(qn, quat, ql);
             quat[0] = qn[0]; quat[1] = qn[1]; quat[2] = qn[2]; quat[3] = qn[3];
@@ -187,42 +213,51 @@ struct Smooth {
       quat2mat(imat, qi);
       st<T, 9>(ximat, 9 * b, imat);
     }
+  }
+
+  // geom frames go straight to HBM (consumed by the collision kernel and the ROS marker publishers); the body frames
+  // are re-read from their exported HBM copies because the body index of a geom is a run-time value
+  __device__ void geoms(int env) {
+    const long long S = a.nenvp;
     for (int g = 0; g < h.ngeom; g++) {
       const int b = m.i(h.o_geom_bodyid, g);
       T gp[3], gq[4], bm[9], bp[3], bq[4], r[3], q[4], gm[9];
       ldm<T, 3>(gp, m, h.o_geom_pos, 3 * g);
       ldm<T, 4>(gq, m, h.o_geom_quat, 4 * g);
-      ld<T, 9>(bm, xmat, 9 * b);
-      ld<T, 3>(bp, xpos, 3 * b);
-      ld<T, 4>(bq, xquat, 4 * b);
+      for (int k = 0; k < 9; k++) bm[k] = a.xmat[(9 * b + k) * S + env];
+      for (int k = 0; k < 3; k++) bp[k] = a.xpos[(3 * b + k) * S + env];
+      for (int k = 0; k < 4; k++) bq[k] = a.xquat[(4 * b + k) * S + env];
       mat_vec3(r, bm, gp);
-      r[0] += bp[0]; r[1] += bp[1]; r[2] += bp[2];
-      st<T, 3>(geom_xpos, 3 * g, r);
+      for (int k = 0; k < 3; k++) a.geom_xpos[(3 * g + k) * S + env] = bp[k] + r[k];
       mul_quat(q, bq, gq);
       quat2mat(gm, q);
-      st<T, 9>(geom_xmat, 9 * g, gm);
+      for (int k = 0; k < 9; k++) a.geom_xmat[(9 * g + k) * S + env] = gm[k];
     }
   }
 
   // ---- CoM-based quantities (A.3) ----
-  __device__ void com_pos() {
-    const int nb = h.nbody;
+  __device__ __forceinline__ void com_pos() {
+    const int nb = P::nbody(m);
+#pragma unroll(P::UNROLL)
     for (int b = 0; b < nb; b++) {
       const T mass = m.f(h.o_body_mass, b);
       for (int k = 0; k < 3; k++) subtree_com[3 * b + k] = mass * xipos[3 * b + k];
     }
+#pragma unroll(P::UNROLL)
     for (int b = nb - 1; b > 0; b--) {
-      const int p = m.i(h.o_body_parentid, b);
+      const int p = P::body_parentid(m, b);
       for (int k = 0; k < 3; k++) subtree_com[3 * p + k] += subtree_com[3 * b + k];
     }
+#pragma unroll(P::UNROLL)
     for (int b = 0; b < nb; b++) {
       const T sm = m.f(h.o_body_subtreemass, b);
       if (sm < Eps<T>::minval()) { for (int k = 0; k < 3; k++) subtree_com[3 * b + k] = xipos[3 * b + k]; }
       else { const T inv = T(1) / sm; for (int k = 0; k < 3; k++) subtree_com[3 * b + k] *= inv; }
     }
     for (int k = 0; k < 10; k++) cinert[k] = 0;
+#pragma unroll(P::UNROLL)
     for (int b = 1; b < nb; b++) {
-      const int root = m.i(h.o_body_rootid, b);
+      const int root = P::body_rootid(m, b);
       T dif[3], mat[9], inert[3], tmp[6];
       for (int k = 0; k < 3; k++) dif[k] = xipos[3 * b + k] - subtree_com[3 * root + k];
       ld<T, 9>(mat, ximat, 9 * b);
@@ -246,19 +281,19 @@ struct Smooth {
       ci[9] = mass;
       st<T, 10>(cinert, 10 * b, ci);
     }
-    for (int j = 0; j < h.njnt; j++) {
-      const int bi = m.i(h.o_jnt_bodyid, j), da = m.i(h.o_jnt_dofadr, j), jt = m.i(h.o_jnt_type, j);
-      const int root = m.i(h.o_body_rootid, bi);
+#pragma unroll(P::UNROLL)
+    for (int j = 0; j < P::njnt(m); j++) {
+      const int bi = P::jnt_bodyid(m, j), da = P::jnt_dofadr(m, j), jt = P::jnt_type(m, j);
+      const int root = P::body_rootid(m, bi);
       T off[3];
       for (int k = 0; k < 3; k++) off[k] = subtree_com[3 * root + k] - xanchor[3 * j + k];
-      int skip = 0;
-      if (jt == JNT_FREE) {
-        for (int k = 0; k < 3; k++) {
-          for (int r = 0; r < 6; r++) cdof[6 * (da + k) + r] = (r == 3 + k) ? T(1) : T(0);
+      if (!P::STATIC && (jt == JNT_FREE || jt == JNT_BALL)) {
+        int skip = 0;
+        if (jt == JNT_FREE) {
+          for (int k = 0; k < 3; k++)
+            for (int r = 0; r < 6; r++) cdof[6 * (da + k) + r] = (r == 3 + k) ? T(1) : T(0);
+          skip = 3;
         }
-        skip = 3;
-      }
-      if (jt == JNT_FREE || jt == JNT_BALL) {
         for (int k = 0; k < 3; k++) {
           T ax[3] = {xmat[9 * bi + k], xmat[9 * bi + 3 + k], xmat[9 * bi + 6 + k]}, lin[3];
           cross3(lin, ax, off);
@@ -280,21 +315,25 @@ struct Smooth {
   }
 
   // ---- composite rigid body algorithm (A.4) ----
-  __device__ void crb_mass() {
-    const int nb = h.nbody, nv = h.nv;
+  __device__ __forceinline__ void crb_mass() {
+    const int nb = P::nbody(m), nvv = P::nv(m);
+#pragma unroll(P::UNROLL)
     for (int i = 0; i < 10 * nb; i++) crb[i] = cinert[i];
+#pragma unroll(P::UNROLL)
     for (int b = nb - 1; b > 0; b--) {
-      const int p = m.i(h.o_body_parentid, b);
+      const int p = P::body_parentid(m, b);
       if (p > 0) for (int k = 0; k < 10; k++) crb[10 * p + k] += crb[10 * b + k];
     }
-    for (int i = 0; i < nv; i++) {
-      int adr = m.i(h.o_dof_Madr, i);
+#pragma unroll(P::UNROLL)
+    for (int i = 0; i < nvv; i++) {
+      int adr = P::dof_Madr(m, i);
       T ci[10], cd[6], buf[6];
-      ld<T, 10>(ci, crb, 10 * m.i(h.o_dof_bodyid, i));
+      ld<T, 10>(ci, crb, 10 * P::dof_bodyid(m, i));
       ld<T, 6>(cd, cdof, 6 * i);
       mul_inert_vec(buf, ci, cd);
       T v = m.f(h.o_dof_armature, i);
-      for (int j = i; j >= 0; j = m.i(h.o_dof_parentid, j)) {
+#pragma unroll(P::UNROLL)
+      for (int j = i; j >= 0; j = P::dof_parentid(m, j)) {
         T cj[6];
         ld<T, 6>(cj, cdof, 6 * j);
         v += cj[0] * buf[0] + cj[1] * buf[1] + cj[2] * buf[2] + cj[3] * buf[3] + cj[4] * buf[4] + cj[5] * buf[5];
@@ -305,15 +344,19 @@ struct Smooth {
   }
 
   // res = M vec (mj_mulM, reference call site src/mujoco_sim/mj_sim.cpp:1057)
-  __device__ void mul_M(const SArr<T>& res, const SArr<T>& vec) {
-    const int nv = h.nv;
-    for (int i = 0; i < nv; i++) res[i] = 0;
-    for (int i = 0; i < nv; i++) {
-      int adr = m.i(h.o_dof_Madr, i);
+  template <typename AR, typename AV>
+  __device__ __forceinline__ void mul_M(const AR& res, const AV& vec) {
+    const int nvv = P::nv(m);
+#pragma unroll(P::UNROLL)
+    for (int i = 0; i < nvv; i++) res[i] = 0;
+#pragma unroll(P::UNROLL)
+    for (int i = 0; i < nvv; i++) {
+      int adr = P::dof_Madr(m, i);
       const T vi = vec[i];
       T ri = res[i] + qM[adr] * vi;
       adr++;
-      for (int j = m.i(h.o_dof_parentid, i); j >= 0; j = m.i(h.o_dof_parentid, j), adr++) {
+#pragma unroll(P::UNROLL)
+      for (int j = P::dof_parentid(m, i); j >= 0; j = P::dof_parentid(m, j), adr++) {
         const T mij = qM[adr];
         ri += mij * vec[j];
         res[j] += mij * vi;
@@ -323,23 +366,25 @@ struct Smooth {
   }
 
   // ---- velocity stage (A.5) ----
-  __device__ void com_vel() {
+  __device__ __forceinline__ void com_vel() {
     for (int k = 0; k < 6; k++) cvel[k] = 0;
-    for (int b = 1; b < h.nbody; b++) {
+#pragma unroll(P::UNROLL)
+    for (int b = 1; b < P::nbody(m); b++) {
       T cv[6];
-      ld<T, 6>(cv, cvel, 6 * m.i(h.o_body_parentid, b));
-      const int ja = m.i(h.o_body_jntadr, b), jn = m.i(h.o_body_jntnum, b);
+      ld<T, 6>(cv, cvel, 6 * P::body_parentid(m, b));
+      const int ja = P::body_jntadr(m, b), jn = P::body_jntnum(m, b);
+#pragma unroll(P::UNROLL)
       for (int j = ja; j < ja + jn; j++) {
-        int dof = m.i(h.o_jnt_dofadr, j);
-        const int jt = m.i(h.o_jnt_type, j);
-        if (jt == JNT_FREE) {
-          for (int k = 0; k < 3; k++) {
-            const T v = qvel[dof + k];
-            for (int r = 0; r < 6; r++) { cdof_dot[6 * (dof + k) + r] = 0; cv[r] += cdof[6 * (dof + k) + r] * v; }
+        int dof = P::jnt_dofadr(m, j);
+        const int jt = P::jnt_type(m, j);
+        if (!P::STATIC && (jt == JNT_FREE || jt == JNT_BALL)) {
+          if (jt == JNT_FREE) {
+            for (int k = 0; k < 3; k++) {
+              const T v = qvel[dof + k];
+              for (int r = 0; r < 6; r++) { cdof_dot[6 * (dof + k) + r] = 0; cv[r] += cdof[6 * (dof + k) + r] * v; }
+            }
+            dof += 3;
           }
-          dof += 3;
-        }
-        if (jt == JNT_FREE || jt == JNT_BALL) {
           // all three axes see the body velocity before this joint's own rotational dofs are added
           for (int k = 0; k < 3; k++) {
             T cd[6], dd[6];
@@ -365,11 +410,13 @@ struct Smooth {
   }
 
   // qfrc += J^T [force; torque] for a wrench applied at world point `point` on body b
-  __device__ void apply_ft(const SArr<T>& qfrc, int b, const T* point, const T* force, const T* torque) {
-    const int root = m.i(h.o_body_rootid, b);
+  template <typename AQ>
+  __device__ __forceinline__ void apply_ft(const AQ& qfrc, int b, const T* point, const T* force, const T* torque) {
+    const int root = P::body_rootid(m, b);
     T off[3];
     for (int k = 0; k < 3; k++) off[k] = point[k] - subtree_com[3 * root + k];
-    for (int i = m.i(h.o_body_lastdof, b); i >= 0; i = m.i(h.o_dof_parentid, i)) {
+#pragma unroll(P::UNROLL)
+    for (int i = P::body_lastdof(m, b); i >= 0; i = P::dof_parentid(m, i)) {
       T cd[6], t[3];
       ld<T, 6>(cd, cdof, 6 * i);
       cross3(t, cd, off);
@@ -379,16 +426,18 @@ struct Smooth {
     }
   }
 
-  __device__ void passive() {
-    const int nv = h.nv;
-    for (int i = 0; i < nv; i++) qfrc_passive[i] = 0;
+  __device__ __forceinline__ void passive() {
+    const int nvv = P::nv(m);
+#pragma unroll(P::UNROLL)
+    for (int i = 0; i < nvv; i++) qfrc_passive[i] = 0;
     if (h.disableflags & DSBL_PASSIVE) return;
     if (h.has_stiffness) {
-      for (int j = 0; j < h.njnt; j++) {
+#pragma unroll(P::UNROLL)
+      for (int j = 0; j < P::njnt(m); j++) {
         const T k = m.f(h.o_jnt_stiffness, j);
         if (k == 0) continue;
-        const int qa = m.i(h.o_jnt_qposadr, j), da = m.i(h.o_jnt_dofadr, j), jt = m.i(h.o_jnt_type, j);
-        if (jt == JNT_FREE || jt == JNT_BALL) {
+        const int qa = P::jnt_qposadr(m, j), da = P::jnt_dofadr(m, j), jt = P::jnt_type(m, j);
+        if (!P::STATIC && (jt == JNT_FREE || jt == JNT_BALL)) {
           int qo = qa, dofo = da;
           if (jt == JNT_FREE) {
             for (int r = 0; r < 3; r++) qfrc_passive[da + r] = -k * (qpos[qa + r] - m.f(h.o_qpos_spring, qa + r));
@@ -405,12 +454,15 @@ struct Smooth {
         }
       }
     }
-    if (h.has_damping)
-      for (int i = 0; i < nv; i++) qfrc_passive[i] -= m.f(h.o_dof_damping, i) * qvel[i];
+    if (h.has_damping) {
+#pragma unroll(P::UNROLL)
+      for (int i = 0; i < nvv; i++) qfrc_passive[i] -= m.f(h.o_dof_damping, i) * qvel[i];
+    }
     // gravity compensation: the reference sets gravcomp="1" on every robot body by default
     // (src/mujoco_sim/mj_sim.cpp:301-310, src/config/robot.yaml:19)
     if (h.has_gravcomp && !(h.disableflags & DSBL_GRAVITY)) {
-      for (int b = 1; b < h.nbody; b++) {
+#pragma unroll(P::UNROLL)
+      for (int b = 1; b < P::nbody(m); b++) {
         const T gc = m.f(h.o_body_gravcomp, b);
         if (gc == 0) continue;
         const T s = -m.f(h.o_body_mass, b) * gc;
@@ -422,16 +474,19 @@ struct Smooth {
   }
 
   // recursive Newton-Euler in the CoM frame; with_acc adds cdof * qacc (inverse dynamics)
-  __device__ void rne(const SArr<T>& result, bool with_acc) {
-    const int nb = h.nbody, nv = h.nv;
+  template <typename AR>
+  __device__ __forceinline__ void rne(const AR& result, bool with_acc) {
+    const int nb = P::nbody(m), nvv = P::nv(m);
     const bool grav = !(h.disableflags & DSBL_GRAVITY);
     cacc[0] = 0; cacc[1] = 0; cacc[2] = 0;
     cacc[3] = grav ? -m.f(h.o_opt_real, 0) : T(0); cacc[4] = grav ? -m.f(h.o_opt_real, 1) : T(0); cacc[5] = grav ? -m.f(h.o_opt_real, 2) : T(0);
     for (int k = 0; k < 6; k++) cfrc[k] = 0;
+#pragma unroll(P::UNROLL)
     for (int b = 1; b < nb; b++) {
       T ac[6], ci[10], cv[6], Ia[6], Iv[6], x[6];
-      ld<T, 6>(ac, cacc, 6 * m.i(h.o_body_parentid, b));
-      const int da = m.i(h.o_body_dofadr, b), dn = m.i(h.o_body_dofnum, b);
+      ld<T, 6>(ac, cacc, 6 * P::body_parentid(m, b));
+      const int da = P::body_dofadr(m, b), dn = P::body_dofnum(m, b);
+#pragma unroll(P::UNROLL)
       for (int j = 0; j < dn; j++) {
         const T v = qvel[da + j];
         for (int r = 0; r < 6; r++) ac[r] += cdof_dot[6 * (da + j) + r] * v;
@@ -448,18 +503,19 @@ struct Smooth {
       cross_force(x, cv, Iv);
       for (int r = 0; r < 6; r++) cfrc[6 * b + r] = Ia[r] + x[r];
     }
+#pragma unroll(P::UNROLL)
     for (int b = nb - 1; b > 0; b--) {
-      const int p = m.i(h.o_body_parentid, b);
+      const int p = P::body_parentid(m, b);
       if (p > 0) for (int r = 0; r < 6; r++) cfrc[6 * p + r] += cfrc[6 * b + r];
     }
-    for (int i = 0; i < nv; i++) {
-      const int b = m.i(h.o_dof_bodyid, i);
+#pragma unroll(P::UNROLL)
+    for (int i = 0; i < nvv; i++) {
+      const int b = P::dof_bodyid(m, i);
       T s = 0;
       for (int r = 0; r < 6; r++) s += cdof[6 * i + r] * cfrc[6 * b + r];
       result[i] = s;
     }
   }
-
 };
 
 // MjSim::set_odom_vels (src/mujoco_sim/mj_sim.cpp:1079-1153): per robot r, odom_dof[6r..] = dof of lin x,y,z / ang x,y,z
@@ -486,7 +542,7 @@ __device__ void odom_override(const MV<T>& m, const KArgs<T>& a, int env) {
 }
 
 // ---- the kernel: persistent CTAs, one thread per environment ----
-template <typename T, int BLOCK>
+template <typename T, int BLOCK, typename P>
 __global__ void __launch_bounds__(BLOCK) k_smooth(const KArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
@@ -496,25 +552,34 @@ __global__ void __launch_bounds__(BLOCK) k_smooth(const KArgs<T> a) {
   MV<T> m{reinterpret_cast<const DModel*>(blob), blob};
   const DModel& h = *m.h;
   T* ws_sh = reinterpret_cast<T*>(smem_raw + 16 + (size_t)nwords * 4);
-  const int nv = h.nv, nb = h.nbody;
+  const int nv = P::nv(m), nb = P::nbody(m), nq = P::nq(m), nM = P::nM(m);
   const long long S = a.nenvp;
   const int ntiles = a.nenvp / BLOCK;
+  // the "environments that still need the constraint pipeline" counter of the NEXT tick is cleared one tick ahead
+  if ((a.flags & B2F_FUSABLE) && blockIdx.x == 0 && threadIdx.x == 0) a.pending[(a.tick + 1) & 1] = 0;
 
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int env = tile * BLOCK + threadIdx.x;
     T* wsbase = (a.flags & B2F_WS_GLOBAL) ? a.ws + env : ws_sh + threadIdx.x;
     const long long wss = (a.flags & B2F_WS_GLOBAL) ? S : BLOCK;
-    Smooth<T> s(m, a, wsbase, wss, env);
-    SArr<T> qfrc_bias{a.qfrc_bias + env, S}, qfrc_inverse{a.qfrc_inverse + env, S};
+    Smooth<T, P> s(m, a, wsbase, wss, env);
+    SArr<T> qfrc_inverse{a.qfrc_inverse + env, S};
 
     // mj_checkPos / mj_checkVel: reset an environment whose state went non-finite
     {
       bool bad = false;
-      for (int i = 0; i < h.nq; i++) { const T v = s.qpos[i]; bad |= !(t_abs(v) < T(1e10)); }
+#pragma unroll(P::UNROLL)
+      for (int i = 0; i < nq; i++) { const T v = s.qpos[i]; bad |= !(t_abs(v) < T(1e10)); }
+#pragma unroll(P::UNROLL)
       for (int i = 0; i < nv; i++) { const T v = s.qvel[i]; bad |= !(t_abs(v) < T(1e10)); }
       if (bad) {
-        for (int i = 0; i < h.nq; i++) s.qpos[i] = m.f(h.o_qpos0, i);
-        for (int i = 0; i < nv; i++) { s.qvel[i] = 0; s.qacc[i] = 0; a.qacc_warmstart[i * S + env] = 0; s.qfrc_applied[i] = 0; }
+#pragma unroll(P::UNROLL)
+        for (int i = 0; i < nq; i++) { const T q0 = m.f(h.o_qpos0, i); s.qpos[i] = q0; a.qpos[i * S + env] = q0; }
+#pragma unroll(P::UNROLL)
+        for (int i = 0; i < nv; i++) {
+          s.qvel[i] = 0; s.qacc[i] = 0; s.qfrc_applied[i] = 0;
+          a.qvel[i * S + env] = 0; a.qacc[i * S + env] = 0; a.qacc_warmstart[i * S + env] = 0; a.qfrc_applied[i * S + env] = 0;
+        }
         a.time[env] = 0;
         a.status[env] |= 4;
       }
@@ -524,39 +589,54 @@ __global__ void __launch_bounds__(BLOCK) k_smooth(const KArgs<T> a) {
     s.kinematics(env);
     s.com_pos();
     s.crb_mass();
-    for (int i = 0; i < h.nM; i++) s.qLD[i] = s.qM[i];
-    ld_factor(m, s.qLD, s.qLDiagInv);
+#pragma unroll(P::UNROLL)
+    for (int i = 0; i < nM; i++) s.qLD[i] = s.qM[i];
+    ld_factor<P>(m, s.qLD, s.qLDiagInv);
     // velocity stage
     s.com_vel();
     s.passive();
-    s.rne(qfrc_bias, false);
+    s.rne(s.qfrc_bias, false);
 
     // mjcb_control -> MjSim::controller (src/mujoco_sim/mj_sim.cpp:1055-1077)
     bool overridden = false;
     if (a.flags & B2F_CONTROLLER) {
-      SArr<T> ddq{a.ddq + env, S}, dq{a.dq + env, S};
+      typename P::template Arr<T, P::NV> ddq;
+      if constexpr (!P::STATIC) ddq = SArr<T>{a.ddq + env, S};
+      else {
+#pragma unroll
+        for (int i = 0; i < P::NV; i++) ddq[i] = a.ddq[i * S + env];
+      }
       s.mul_M(s.tmpv, ddq);
+#pragma unroll(P::UNROLL)
       for (int i = 0; i < nv; i++) {
         T tau = s.tmpv[i];
-        if (m.i(h.o_dof_controlled, i)) tau += qfrc_bias[i];
+        if (P::dof_controlled(m, i)) tau += s.qfrc_bias[i];
         s.qfrc_applied[i] = tau;
-        const T v = dq[i];
+        if (P::STATIC) a.qfrc_applied[i * S + env] = tau;
+        const T v = a.dq[i * S + env];
         if (t_abs(v) > Eps<T>::minval()) { s.qvel[i] = v; overridden = true; }
-        ddq[i] = 0;
-        dq[i] = 0;
+        a.ddq[i * S + env] = 0;
+        a.dq[i * S + env] = 0;
       }
     }
     // MjHWInterface::read -> mj_inverse: velocity stage again for the overridden qvel, then RNE with the stored qacc
     if (a.flags & B2F_INVERSE) {
-      if (overridden) { s.com_vel(); s.passive(); s.rne(qfrc_bias, false); }
-      s.rne(qfrc_inverse, true);
-      for (int i = 0; i < nv; i++) qfrc_inverse[i] += m.f(h.o_dof_armature, i) * s.qacc[i] - s.qfrc_passive[i];
+      if (overridden) { s.com_vel(); s.passive(); s.rne(s.qfrc_bias, false); }
+      s.rne(s.tmpv, true);
+#pragma unroll(P::UNROLL)
+      for (int i = 0; i < nv; i++) qfrc_inverse[i] = s.tmpv[i] + m.f(h.o_dof_armature, i) * s.qacc[i] - s.qfrc_passive[i];
+    }
+    if (P::STATIC) {
+#pragma unroll(P::UNROLL)
+      for (int i = 0; i < nv; i++) a.qfrc_bias[i * S + env] = s.qfrc_bias[i];
     }
 
     // smooth acceleration
-    for (int i = 0; i < nv; i++) s.qfrc_smooth[i] = s.qfrc_passive[i] - qfrc_bias[i] + s.qfrc_applied[i];
+#pragma unroll(P::UNROLL)
+    for (int i = 0; i < nv; i++) s.qfrc_smooth[i] = s.qfrc_passive[i] - s.qfrc_bias[i] + s.qfrc_applied[i];
     if (a.flags & B2F_XFRC) {
       SArr<T> xf{a.xfrc_applied + env, S};
+#pragma unroll(P::UNROLL)
       for (int b = 1; b < nb; b++) {
         T w[6], pt[3];
         ld<T, 6>(w, xf, 6 * b);
@@ -565,40 +645,80 @@ __global__ void __launch_bounds__(BLOCK) k_smooth(const KArgs<T> a) {
         s.apply_ft(s.qfrc_smooth, b, pt, w, w + 3);
       }
     }
+#pragma unroll(P::UNROLL)
     for (int i = 0; i < nv; i++) s.qacc_smooth[i] = s.qfrc_smooth[i];
-    ld_solve(m, s.qLD, s.qLDiagInv, s.qacc_smooth);
+    ld_solve<P>(m, s.qLD, s.qLDiagInv, s.qacc_smooth);
 
     // body poses for the ROS layer (tf / marker publishers read d->xpos, d->xquat: SURVEY.md Appendix C)
+#pragma unroll(P::UNROLL)
     for (int i = 0; i < 3 * nb; i++) a.xpos[i * S + env] = s.xpos[i];
+#pragma unroll(P::UNROLL)
     for (int i = 0; i < 4 * nb; i++) a.xquat[i * S + env] = s.xquat[i];
 
-    if (!(a.flags & B2F_FUSED) || (a.flags & B2F_EXPORT)) {
+    // does this environment need the constraint pipeline this tick?
+    bool pipeline = !(a.flags & B2F_FUSED);
+    if (a.flags & B2F_FUSABLE) {
+      // joint limits are the model's only constraint source: the pipeline runs only for environments with an active one
+      pipeline = false;
+      if (!(h.disableflags & (DSBL_LIMIT | DSBL_CONSTRAINT))) {
+#pragma unroll(P::UNROLL)
+        for (int j = 0; j < P::njnt(m); j++) {
+          if (!P::jnt_limited(m, j)) continue;
+          const T q = s.qpos[P::jnt_qposadr(m, j)], mg = m.f(h.o_jnt_margin, j);
+          pipeline |= (q - m.f(h.o_jnt_range, 2 * j) < mg) || (m.f(h.o_jnt_range, 2 * j + 1) - q < mg);
+        }
+      }
+      a.nefc[env] = 0;
+      a.status[env] = (a.status[env] & 7) | (pipeline ? 0 : 8);
+      const unsigned vote = __ballot_sync(__activemask(), pipeline);
+      if (vote && (int)(threadIdx.x & 31) == __ffs(vote) - 1) atomicAdd(&a.pending[a.tick & 1], __popc(vote));
+    }
+
+    if (pipeline || (a.flags & B2F_EXPORT)) {
       // export the stage results the constraint pipeline (and the legacy mjData mirror) consume
+#pragma unroll(P::UNROLL)
       for (int i = 0; i < 9 * nb; i++) a.xmat[i * S + env] = s.xmat[i];
-      for (int i = 0; i < 3 * h.ngeom; i++) a.geom_xpos[i * S + env] = s.geom_xpos[i];
-      for (int i = 0; i < 9 * h.ngeom; i++) a.geom_xmat[i * S + env] = s.geom_xmat[i];
+#pragma unroll(P::UNROLL)
       for (int i = 0; i < 3 * nb; i++) a.subtree_com[i * S + env] = s.subtree_com[i];
+#pragma unroll(P::UNROLL)
       for (int i = 0; i < 6 * nv; i++) a.cdof[i * S + env] = s.cdof[i];
-      for (int i = 0; i < h.nM; i++) { a.qM[i * S + env] = s.qM[i]; a.qLD[i * S + env] = s.qLD[i]; }
+#pragma unroll(P::UNROLL)
+      for (int i = 0; i < nM; i++) { a.qM[i * S + env] = s.qM[i]; a.qLD[i * S + env] = s.qLD[i]; }
+#pragma unroll(P::UNROLL)
       for (int i = 0; i < nv; i++) {
         a.qLDiagInv[i * S + env] = s.qLDiagInv[i];
         a.qfrc_passive[i * S + env] = s.qfrc_passive[i];
         a.qfrc_smooth[i * S + env] = s.qfrc_smooth[i];
         a.qacc_smooth[i * S + env] = s.qacc_smooth[i];
       }
+      s.geoms(env);
+      if (P::STATIC && overridden) {
+#pragma unroll(P::UNROLL)
+        for (int i = 0; i < nv; i++) a.qvel[i * S + env] = s.qvel[i];
+      }
     }
-    if (a.flags & B2F_FUSED) {
-      // no constraint source in the model: qacc = qacc_smooth, integrate right here
+    if (!pipeline) {
+      // no active constraint: qacc = qacc_smooth, integrate right here
+#pragma unroll(P::UNROLL)
       for (int i = 0; i < nv; i++) {
         const T v = s.qacc_smooth[i];
-        s.qacc[i] = v;
+        a.qacc[i * S + env] = v;
         a.qacc_warmstart[i * S + env] = v;
       }
       if (a.flags & B2F_INTEGRATE) {
         // qLD / qLDiagInv are dead by now: reuse them as scratch for the damped factorisation
-        euler_step(m, s.qpos, s.qvel, s.qM, s.qacc_smooth, s.qfrc_smooth, a.h, s.qLD, s.qLDiagInv, s.tmpv);
+        euler_step<P>(m, s.qpos, s.qvel, s.qM, s.qacc_smooth, s.qfrc_smooth, a.h, s.qLD, s.qLDiagInv, s.tmpv);
+        if (P::STATIC) {
+#pragma unroll(P::UNROLL)
+          for (int i = 0; i < nq; i++) a.qpos[i * S + env] = s.qpos[i];
+#pragma unroll(P::UNROLL)
+          for (int i = 0; i < nv; i++) a.qvel[i * S + env] = s.qvel[i];
+        }
         a.time[env] += a.h;
         if (a.flags & B2F_ODOM) odom_override(m, a, env);
+      } else if (P::STATIC && overridden) {
+#pragma unroll(P::UNROLL)
+        for (int i = 0; i < nv; i++) a.qvel[i * S + env] = s.qvel[i];
       }
     }
   }
