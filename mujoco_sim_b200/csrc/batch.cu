@@ -522,7 +522,9 @@ b2_batch* b2_create(const mjModel* m, int nenv, int device, int precision) {
     const int n = m->nbody - 1;
     const bool have = have_chain_kernel(n, precision);
     b->chain_n = (chain && have && !getenv("B2_NO_CHAIN")) ? n : 0;
-    b->chain_variant = getenv("B2_CHAIN_VARIANT") ? atoi(getenv("B2_CHAIN_VARIANT")) : 0;
+    // register budget of the chain kernel: 230 registers (best single-warp latency) for batches that cannot fill the
+    // SMs, 128 registers (16 warps / SM) for large ones; measured in profiles/r01_chain_variants.txt
+    b->chain_variant = getenv("B2_CHAIN_VARIANT") ? atoi(getenv("B2_CHAIN_VARIANT")) : (b->nenvp >= 32768 ? 2 : 0);
   }
 
   b->epl = 2;

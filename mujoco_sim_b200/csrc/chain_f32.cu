@@ -6,22 +6,24 @@
 
 namespace b2 {
 namespace {
-template <typename T, int BLOCK, typename P>
+template <typename T, int BLOCK, typename P, int MINB = 1>
 int launch(b2_batch* b, const KArgs<T>& a, int grid) {
   static bool attr_set[8] = {false};
   const int dev = b->device & 7;
   if (!attr_set[dev]) {
-    if (cudaFuncSetAttribute(k_smooth<T, BLOCK, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess)
+    if (cudaFuncSetAttribute(k_smooth<T, BLOCK, P, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess)
       return set_error("cudaFuncSetAttribute(k_smooth chain) failed");
     attr_set[dev] = true;
   }
-  k_smooth<T, BLOCK, P><<<grid, BLOCK, b->smooth_smem, b->stream>>>(a);
+  k_smooth<T, BLOCK, P, MINB><<<grid, BLOCK, b->smooth_smem, b->stream>>>(a);
   b->launches++;
   return 0;
 }
 }  // namespace
 
 int launch_chain_f32(b2_batch* b, const KArgs<float>& a, int grid) {
+  if (b->chain_n == 7 && b->chain_variant == 1) return b->smooth_block == 32 ? launch<float, 32, ChainP<7>, 12>(b, a, grid) : launch<float, 128, ChainP<7>, 3>(b, a, grid);
+  if (b->chain_n == 7 && b->chain_variant == 2) return b->smooth_block == 32 ? launch<float, 32, ChainP<7>, 16>(b, a, grid) : launch<float, 128, ChainP<7>, 4>(b, a, grid);
   if (b->chain_n == 7) return b->smooth_block == 32 ? launch<float, 32, ChainP<7>>(b, a, grid) : launch<float, 128, ChainP<7>>(b, a, grid);
   if (b->chain_n == 6) return b->smooth_block == 32 ? launch<float, 32, ChainP<6>>(b, a, grid) : launch<float, 128, ChainP<6>>(b, a, grid);
   return set_error("no fp32 chain kernel for this chain length");

@@ -542,8 +542,8 @@ __device__ void odom_override(const MV<T>& m, const KArgs<T>& a, int env) {
 }
 
 // ---- the kernel: persistent CTAs, one thread per environment ----
-template <typename T, int BLOCK, typename P>
-__global__ void __launch_bounds__(BLOCK) k_smooth(const KArgs<T> a) {
+template <typename T, int BLOCK, typename P, int MINB = 1>
+__global__ void __launch_bounds__(BLOCK, MINB) k_smooth(const KArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
   uint32_t* blob = reinterpret_cast<uint32_t*>(smem_raw + 16);
@@ -622,9 +622,11 @@ __global__ void __launch_bounds__(BLOCK) k_smooth(const KArgs<T> a) {
     // MjHWInterface::read -> mj_inverse: velocity stage again for the overridden qvel, then RNE with the stored qacc
     if (a.flags & B2F_INVERSE) {
       if (overridden) { s.com_vel(); s.passive(); s.rne(s.qfrc_bias, false); }
-      s.rne(s.tmpv, true);
+      // RNE is affine in the acceleration: RNE(q, v, a) + armature a = M a + bias, so the second tree pass of
+      // mj_inverse collapses to one sparse mat-vec with the CRBA matrix already at hand
+      s.mul_M(s.tmpv, s.qacc);
 #pragma unroll(P::UNROLL)
-      for (int i = 0; i < nv; i++) qfrc_inverse[i] = s.tmpv[i] + m.f(h.o_dof_armature, i) * s.qacc[i] - s.qfrc_passive[i];
+      for (int i = 0; i < nv; i++) qfrc_inverse[i] = s.tmpv[i] + s.qfrc_bias[i] - s.qfrc_passive[i];
     }
     if (P::STATIC) {
 #pragma unroll(P::UNROLL)

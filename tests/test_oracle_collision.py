@@ -1,0 +1,145 @@
+"""Analytic pins of the oracle's narrow phase: each case places two primitives so that distance, normal and contact
+point are known in closed form (conventions of SURVEY.md A.6: dist < 0 penetration, normal from geom1 to geom2, geom1
+has the lower geom type, pos at the midpoint)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+
+class MjContact(C.Structure):
+    _fields_ = [("dist", C.c_double), ("pos", C.c_double * 3), ("frame", C.c_double * 9), ("includemargin", C.c_double),
+                ("friction", C.c_double * 5), ("solref", C.c_double * 2), ("solimp", C.c_double * 5), ("mu", C.c_double),
+                ("dim", C.c_int), ("geom1", C.c_int), ("geom2", C.c_int), ("exclude", C.c_int), ("efc_address", C.c_int),
+                ("pair", C.c_int)]
+
+
+def contacts(b2, orc, body_xml, qpos=None):
+    xml = "<mujoco><compiler angle='radian'/><option gravity='0 0 0'/><worldbody>%s</worldbody></mujoco>" % body_xml
+    m = b2.Model(xml=xml)
+    d = b2.Data(m)
+    if qpos is not None:
+        d.qpos[:] = qpos
+    orc.call("kinematics", m, d)
+    orc.call("collision", m, d)
+    b2.lib.b2_data_contact.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    out = []
+    for i in range(d.ncon):
+        k = MjContact()
+        assert b2.lib.b2_data_contact(d.ptr, i, C.byref(k)) == 0
+        out.append((k.dist, np.array(k.pos), np.array(k.frame[:3]), k.geom1, k.geom2, k.dim))
+    return out
+
+
+def free(name, geom, pos):
+    return "<body name='%s' pos='%s'><freejoint/>%s</body>" % (name, pos, geom)
+
+
+def test_sphere_sphere(b2, orc):
+    c = contacts(b2, orc, free("a", "<geom size='0.1'/>", "0 0 0") + free("b", "<geom size='0.2'/>", "0.25 0 0"))
+    assert len(c) == 1
+    dist, pos, n, g1, g2, dim = c[0]
+    assert abs(dist + 0.05) < 1e-12 and np.allclose(n, [1, 0, 0]) and np.allclose(pos, [0.075, 0, 0]) and dim == 3
+    assert not contacts(b2, orc, free("a", "<geom size='0.1'/>", "0 0 0") + free("b", "<geom size='0.2'/>", "0.31 0 0"))
+
+
+def test_plane_sphere_capsule_box_cylinder(b2, orc):
+    floor = "<geom type='plane' size='0 0 1'/>"
+    c = contacts(b2, orc, floor + free("s", "<geom size='0.1'/>", "0 0 0.09"))
+    assert len(c) == 1 and abs(c[0][0] + 0.01) < 1e-12 and np.allclose(c[0][2], [0, 0, 1]) and np.allclose(c[0][1], [0, 0, -0.005])
+    assert c[0][3] == 0 and c[0][4] == 1                       # plane first
+    # lying capsule: two end-sphere contacts, first tangent along the capsule axis
+    c = contacts(b2, orc, floor + free("c", "<geom type='capsule' size='0.05 0.2' quat='0.7071067811865476 0 0.7071067811865476 0'/>", "0 0 0.04"))
+    assert len(c) == 2 and all(abs(k[0] + 0.01) < 1e-9 for k in c)
+    assert sorted(round(k[1][0], 6) for k in c) == [-0.2, 0.2]
+    # box resting flat: four corner contacts
+    c = contacts(b2, orc, floor + free("b", "<geom type='box' size='0.1 0.2 0.05'/>", "0 0 0.049"))
+    assert len(c) == 4 and all(abs(k[0] + 0.001) < 1e-12 for k in c)
+    assert sorted((round(k[1][0], 6), round(k[1][1], 6)) for k in c) == [(-0.1, -0.2), (-0.1, 0.2), (0.1, -0.2), (0.1, 0.2)]
+    # upright cylinder: rim contacts all at the same depth, spread around the rim
+    c = contacts(b2, orc, floor + free("y", "<geom type='cylinder' size='0.1 0.15'/>", "0 0 0.148"))
+    assert len(c) >= 3 and all(abs(k[0] + 0.002) < 1e-9 for k in c)
+    r = [np.hypot(k[1][0], k[1][1]) for k in c]
+    assert np.allclose(r, 0.1, atol=1e-9)
+    # tilted cylinder touches with one rim point only
+    c = contacts(b2, orc, floor + free("y", "<geom type='cylinder' size='0.1 0.15' euler='0 0.5 0'/>", "0 0 0.17"))
+    assert len(c) == 1 and c[0][0] < 0
+
+
+def test_sphere_box_face_edge_corner_and_inside(b2, orc):
+    box = free("b", "<geom type='box' size='0.1 0.2 0.3'/>", "0 0 0")
+    # face
+    c = contacts(b2, orc, free("s", "<geom size='0.05'/>", "0.14 0.05 0.1") + box)
+    assert len(c) == 1 and abs(c[0][0] + 0.01) < 1e-12 and np.allclose(c[0][2], [-1, 0, 0])   # from the sphere toward the box
+    # edge (x and y faces): distance to the edge line
+    c = contacts(b2, orc, free("s", "<geom size='0.05'/>", "0.13 0.23 0.0") + box)
+    assert len(c) == 1 and abs(c[0][0] - (np.hypot(0.03, 0.03) - 0.05)) < 1e-12
+    # corner
+    c = contacts(b2, orc, free("s", "<geom size='0.05'/>", "0.12 0.22 0.32") + box)
+    assert len(c) == 1 and abs(c[0][0] - (np.sqrt(3) * 0.02 - 0.05)) < 1e-12
+    # centre inside the box: exits through the nearest face (+x here)
+    c = contacts(b2, orc, free("s", "<geom size='0.05'/>", "0.08 0 0") + box)
+    assert len(c) == 1 and abs(c[0][0] + 0.07) < 1e-12 and np.allclose(c[0][2], [-1, 0, 0])
+
+
+def test_sphere_cylinder_side_and_cap(b2, orc):
+    cyl = free("y", "<geom type='cylinder' size='0.1 0.2'/>", "0 0 0")
+    c = contacts(b2, orc, free("s", "<geom size='0.05'/>", "0.14 0 0.05") + cyl)
+    assert len(c) == 1 and abs(c[0][0] + 0.01) < 1e-12 and np.allclose(c[0][2], [-1, 0, 0])
+    c = contacts(b2, orc, free("s", "<geom size='0.05'/>", "0.03 0 0.24") + cyl)
+    assert len(c) == 1 and abs(c[0][0] + 0.01) < 1e-12 and np.allclose(c[0][2], [0, 0, -1])
+    c = contacts(b2, orc, free("s", "<geom size='0.05'/>", "0.13 0 0.23") + cyl)          # rim
+    assert len(c) == 1 and abs(c[0][0] - (np.hypot(0.03, 0.03) - 0.05)) < 1e-12
+
+
+def test_capsule_capsule_crossed_and_parallel(b2, orc):
+    a = free("a", "<geom type='capsule' size='0.05 0.3'/>", "0 0 0")
+    b = free("b", "<geom type='capsule' size='0.05 0.3' quat='0.7071067811865476 0.7071067811865476 0 0'/>", "0.09 0 0")
+    c = contacts(b2, orc, a + b)
+    assert len(c) == 1 and abs(c[0][0] + 0.01) < 1e-9 and np.allclose(c[0][2], [1, 0, 0], atol=1e-9)
+    b = free("b", "<geom type='capsule' size='0.05 0.2'/>", "0.09 0 0.05")
+    c = contacts(b2, orc, a + b)
+    assert len(c) == 2 and all(abs(k[0] + 0.01) < 1e-9 for k in c)
+    assert sorted(round(k[1][2], 6) for k in c) == [-0.15, 0.25]
+
+
+def test_capsule_box(b2, orc):
+    box = free("b", "<geom type='box' size='0.2 0.2 0.1'/>", "0 0 0")
+    # capsule lying flat on the top face: contacts at both ends (and the nearest point in between is dropped as a duplicate)
+    cap = free("c", "<geom type='capsule' size='0.05 0.1' quat='0.7071067811865476 0 0.7071067811865476 0'/>", "0 0 0.14")
+    c = contacts(b2, orc, cap + box)
+    assert 2 <= len(c) <= 3 and all(abs(k[0] + 0.01) < 1e-6 for k in c) and all(np.allclose(k[2], [0, 0, -1], atol=1e-6) for k in c)
+    # capsule standing on the face: one contact under the lower end
+    cap = free("c", "<geom type='capsule' size='0.05 0.1'/>", "0.05 0 0.245")
+    c = contacts(b2, orc, cap + box)
+    assert len(c) == 1 and abs(c[0][0] + 0.005) < 1e-6 and np.allclose(c[0][1][:2], [0.05, 0], atol=1e-6)
+
+
+def test_box_box_face_and_edge(b2, orc):
+    a = free("a", "<geom type='box' size='0.2 0.2 0.1'/>", "0 0 0")
+    b = free("b", "<geom type='box' size='0.05 0.05 0.05'/>", "0.05 0.02 0.148")
+    c = contacts(b2, orc, a + b)
+    assert len(c) == 4 and all(abs(k[0] + 0.002) < 1e-9 for k in c) and all(np.allclose(k[2], [0, 0, 1]) for k in c)
+    assert sorted((round(k[1][0], 6), round(k[1][1], 6)) for k in c) == [(0.0, -0.03), (0.0, 0.07), (0.1, -0.03), (0.1, 0.07)]
+    # overhanging small box: the incident face is clipped by the reference face
+    b = free("b", "<geom type='box' size='0.05 0.05 0.05'/>", "0.22 0 0.148")
+    c = contacts(b2, orc, a + b)
+    assert len(c) == 4 and max(k[1][0] for k in c) <= 0.2 + 1e-9
+    # two boxes rotated 45 degrees about different axes touching edge to edge: a single contact
+    a = free("a", "<geom type='box' size='0.1 0.1 0.1' euler='0.7853981633974483 0 0'/>", "0 0 0")
+    b = free("b", "<geom type='box' size='0.1 0.1 0.1' euler='0 0.7853981633974483 0'/>", "0 0 0.28")
+    c = contacts(b2, orc, a + b)
+    assert len(c) == 1 and abs(c[0][0] - (0.28 - 2 * 0.1 * np.sqrt(2))) < 1e-9 and np.allclose(np.abs(c[0][2]), [0, 0, 1], atol=1e-9)
+
+
+def test_contact_parameter_mixing(b2, orc):
+    """condim = max, friction = element-wise max (floor of the reference: condim 4, friction 2 0.05 0.01; world/empty.xml:12)."""
+    floor = "<geom type='plane' size='0 0 1' condim='4' friction='2 0.05 0.01'/>"
+    xml = "<mujoco><worldbody>%s%s</worldbody></mujoco>" % (floor, free("s", "<geom size='0.1'/>", "0 0 0.09"))
+    m = b2.Model(xml=xml); d = b2.Data(m)
+    orc.call("kinematics", m, d); orc.call("collision", m, d)
+    k = MjContact()
+    b2.lib.b2_data_contact.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    assert b2.lib.b2_data_contact(d.ptr, 0, C.byref(k)) == 0
+    assert k.dim == 4 and list(k.friction) == [2, 2, 0.05, 0.01, 0.01]
+    assert list(k.solref) == [0.02, 1] and list(k.solimp) == [0.9, 0.95, 0.001, 0.5, 2]
