@@ -160,7 +160,9 @@ int pack_model(b2_batch* b) {
   return 0;
 }
 
+void drop_graphs(b2_batch* b);
 int upload_model(b2_batch* b) {
+  drop_graphs(b);  // kernel arguments / constants may change
   if (pack_model(b) < 0) return -1;
   if (!b->blob_dev) {
     CK(cudaMalloc(&b->blob_dev, b->blob.size() * 4 + 64));
@@ -171,6 +173,7 @@ int upload_model(b2_batch* b) {
 }
 
 int alloc_field(b2_batch* b, const char* name, long long count, int kind, void** out) {
+  drop_graphs(b);
   const size_t esz = kind == 1 ? 4 : (size_t)b->prec;
   const size_t bytes = std::max<size_t>(16, (size_t)count * b->nenvp * esz);
   void* p = nullptr;
@@ -206,7 +209,7 @@ KArgs<T> make_args(b2_batch* b, int flags) {
   a.efc_frictionloss = R("efc_frictionloss"); a.efc_diagApprox = R("efc_diagApprox"); a.efc_R = R("efc_R"); a.efc_D = R("efc_D");
   a.efc_KBI = R("efc_KBI"); a.efc_vel = R("efc_vel"); a.efc_aref = R("efc_aref"); a.efc_b = R("efc_b"); a.efc_force = R("efc_force");
   a.efc_ARdiag = R("efc_ARdiag"); a.efc_rows = R("efc_rows"); a.efc_meta = R("efc_meta"); a.wp = b->wp; a.solver_iter = I("solver_iter"); a.status = I("status");
-  a.pending = I("_pending"); a.tick = b->tick;
+  a.pending = I("_pending");
   return a;
 }
 
@@ -229,6 +232,10 @@ int launch_chain(b2_batch* b, const KArgs<T>& a, int grid) {
   else return launch_chain_f64(b, a, grid);
 }
 
+int hw_write_async(b2_batch* b, const float* vel, const float* eff);
+int hw_read_async(b2_batch* b, float* pos, float* vel, float* eff);
+enum { B2_TICK_HW = 1 << 20 };  // internal: run k_hw_write / k_hw_read around the tick kernels
+
 template <typename T>
 int run_tick(b2_batch* b, int flags) {
   int kf = 0;
@@ -240,14 +247,16 @@ int run_tick(b2_batch* b, int flags) {
   if (flags & B2_TICK_NOSOLVE) kf |= B2F_NOSOLVE;
   if (b->ws_global) kf |= B2F_WS_GLOBAL;
   if (b->fusable) kf |= B2F_FUSABLE;
-  b->tick++;
   if (b->tick_flags & (1 << 30)) kf |= B2F_XFRC;  // set once xfrc_applied has been written
   if (b->export_stages) kf |= B2F_EXPORT;
   KArgs<T> a = make_args<T>(b, kf);
   const int ntiles = b->nenvp / b->smooth_block;
-  const int per_sm = std::max<size_t>(1, (227 * 1024) / std::max<size_t>(1, b->smooth_smem));
+  int per_sm = (int)std::max<size_t>(1, (227 * 1024) / std::max<size_t>(1, b->smooth_smem));
+  if (getenv("B2_SMOOTH_CTAS_PER_SM")) per_sm = std::max(1, atoi(getenv("B2_SMOOTH_CTAS_PER_SM")));
   const int grid = std::max(1, std::min(ntiles, b->nsm * per_sm));
   int rc;
+  if (flags & B2_TICK_HW) { if (hw_write_async(b, nullptr, nullptr) < 0) return -1; }
+  if (b->fusable) CK(cudaMemsetAsync(a.pending, 0, sizeof(int), b->stream));
   prof_mark(b, SLOT_SMOOTH);
   if (b->chain_n > 0) rc = launch_chain<T>(b, a, grid);
   else switch (b->smooth_block) {
@@ -283,6 +292,7 @@ int run_tick(b2_batch* b, int flags) {
     }
   }
   prof_mark(b, SLOT_HW_READ);
+  if (flags & B2_TICK_HW) { if (hw_read_async(b, nullptr, nullptr, nullptr) < 0) return -1; }
   CK(cudaGetLastError());
   return 0;
 }
@@ -301,13 +311,58 @@ static void prof_close(b2_batch* b) {
   b->prof_n++;
 }
 
+int tick_eager(b2_batch* b, int flags) { return b->prec == 8 ? run_tick<double>(b, flags) : run_tick<float>(b, flags); }
+
+// The kernel sequence of one tick is launch-bound for small batches (seven launches of a few microseconds each), so it
+// is captured once per (flags, timestep) into a CUDA graph and replayed with a single launch.  The first tick of a key
+// runs eagerly (it also sets the function attributes), the second is captured, later ones replay.  Per-kernel event
+// profiling (b2_profile_begin) and B2_NO_GRAPH=1 use the eager path.
 int tick_dispatch(b2_batch* b, int flags) {
   CK(cudaSetDevice(b->device));
-  const bool mine = prof_open(b);
-  if (mine) prof_mark(b, SLOT_HW_WRITE);
-  const int rc = b->prec == 8 ? run_tick<double>(b, flags) : run_tick<float>(b, flags);
-  if (mine) prof_close(b);
-  return rc;
+  if (b->prof_on || !b->use_graph) {
+    const bool mine = prof_open(b);
+    if (mine) prof_mark(b, SLOT_HW_WRITE);
+    const int rc = tick_eager(b, flags);
+    if (mine) prof_close(b);
+    return rc;
+  }
+  float hf = (float)b->h;
+  uint32_t hb;
+  std::memcpy(&hb, &hf, 4);
+  const unsigned long long key = ((unsigned long long)(unsigned)(flags | (b->tick_flags & (1 << 30))) << 32) | hb;
+  auto it = b->graphs.find(key);
+  if (it == b->graphs.end()) {  // first use: eager
+    b->graphs[key] = b2_batch::GraphEntry{};
+    return tick_eager(b, flags);
+  }
+  b2_batch::GraphEntry& g = it->second;
+  if (!g.exec) {  // second use: capture
+    const long long l0 = b->launches;
+    CK(cudaStreamBeginCapture(b->stream, cudaStreamCaptureModeThreadLocal));
+    const int rc = tick_eager(b, flags);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(b->stream, &graph);
+    if (rc < 0 || e != cudaSuccess || !graph) {
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      b->use_graph = false;  // capture is not possible here: stay on the eager path
+      b->launches = l0;
+      return tick_eager(b, flags);
+    }
+    g.kernels = (int)(b->launches - l0);
+    b->launches = l0;
+    const cudaError_t e2 = cudaGraphInstantiate(&g.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e2 != cudaSuccess) { g.exec = nullptr; b->use_graph = false; cudaGetLastError(); return tick_eager(b, flags); }
+  }
+  CK(cudaGraphLaunch(g.exec, b->stream));
+  b->launches += g.kernels;
+  return 0;
+}
+
+void drop_graphs(b2_batch* b) {
+  for (auto& kv : b->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  b->graphs.clear();
 }
 
 // ---- host <-> device field transfer with layout / precision conversion ----
@@ -491,6 +546,7 @@ b2_batch* b2_create(const mjModel* m, int nenv, int device, int precision) {
   b->opt_iterations = m->opt.iterations; b->opt_tolerance = m->opt.tolerance; b->opt_disableflags = m->opt.disableflags;
   b->controlled.assign(m->nv, 0);
   b->export_stages = export_stages;
+  b->use_graph = !getenv("B2_NO_GRAPH");
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) b->nsm = prop.multiProcessorCount;
   auto bail = [&](const char* what) -> b2_batch* {
@@ -561,7 +617,9 @@ b2_batch* b2_create(const mjModel* m, int nenv, int device, int precision) {
   b->blob_smem = 16 + (size_t)b->hdr.nwords * 4;
   const size_t budget = 200 * 1024;
   int block = 0;
-  for (int cand : {128, 64, 32}) {
+  // a shared-memory workspace pays off only when at least two warps fit on an SM; below that the L2-resident HBM
+  // workspace with four warps per SM is faster (measured on C3: 0.63 ms vs 0.95 ms, profiles/r01_ncu_c3_summary.txt)
+  for (int cand : {128, 64}) {
     const size_t need = b->blob_smem + (size_t)b->hdr.ws_slots * cand * precision;
     if (need > budget) continue;
     if (!block) block = cand;
@@ -647,6 +705,7 @@ void b2_destroy(b2_batch* b) {
   if (b->hw_ctl) cudaFree(b->hw_ctl);
   if (b->hw_buf) cudaFree(b->hw_buf);
   for (cudaEvent_t e : b->prof_ev) cudaEventDestroy(e);
+  drop_graphs(b);
   if (b->stream) cudaStreamDestroy(b->stream);
   delete b;
 }
@@ -771,6 +830,7 @@ long long b2_launch_count(const b2_batch* b) { return b ? b->launches : -1; }
 int b2_set_hw_joints(b2_batch* b, int njoint, const int* jnt_ids) {
   if (!b || njoint < 1 || !jnt_ids) return fail("b2_set_hw_joints: bad argument");
   CK(cudaSetDevice(b->device));
+  drop_graphs(b);
   std::vector<int> qadr(njoint), dadr(njoint), ctl(njoint);
   for (int j = 0; j < njoint; j++) {
     const int id = jnt_ids[j];
@@ -793,7 +853,9 @@ int b2_set_hw_joints(b2_batch* b, int njoint, const int* jnt_ids) {
   return 0;
 }
 
-static int hw_write_async(b2_batch* b, const float* vel, const float* eff) {
+}  // extern "C"
+namespace {
+int hw_write_async(b2_batch* b, const float* vel, const float* eff) {
   if (!b->nhw) return fail("b2_write_commands: call b2_set_hw_joints first");
   const size_t n = (size_t)b->nhw * b->nenv;
   float* dv = b->hw_buf;
@@ -808,7 +870,7 @@ static int hw_write_async(b2_batch* b, const float* vel, const float* eff) {
   CK(cudaGetLastError());
   return 0;
 }
-static int hw_read_async(b2_batch* b, float* pos, float* vel, float* eff) {
+int hw_read_async(b2_batch* b, float* pos, float* vel, float* eff) {
   if (!b->nhw) return fail("b2_read_joints: call b2_set_hw_joints first");
   const size_t n = (size_t)b->nhw * b->nenv;
   float *dp = b->hw_buf + 2 * n, *dv = b->hw_buf + 3 * n, *de = b->hw_buf + 4 * n;
@@ -822,6 +884,9 @@ static int hw_read_async(b2_batch* b, float* pos, float* vel, float* eff) {
   if (eff) CK(cudaMemcpyAsync(eff, de, n * 4, cudaMemcpyDeviceToHost, b->stream));
   return 0;
 }
+
+}  // namespace
+extern "C" {
 
 int b2_write_commands(b2_batch* b, const float* vel, const float* eff) {
   if (!b || !vel || !eff) return fail("b2_write_commands: null argument");
@@ -845,13 +910,15 @@ int b2_read_joints(b2_batch* b, float* pos, float* vel, float* eff) {
 // i.e. exactly what read() of the NEXT tick would return for positions and velocities.
 static int tick_hw(b2_batch* b, const float* vel, const float* eff, float* pos, float* velo, float* effo, bool sync) {
   CK(cudaSetDevice(b->device));
-  const bool mine = prof_open(b);
-  if (mine) prof_mark(b, SLOT_HW_WRITE);
-  int rc = hw_write_async(b, vel, eff);
-  if (rc == 0) rc = tick_dispatch(b, (b->tick_flags & ~(1 << 30)) | B2_TICK_INTEGRATE | B2_TICK_CONTROLLER | B2_TICK_INVERSE);
-  if (rc == 0) rc = hw_read_async(b, pos, velo, effo);
-  if (mine) prof_close(b);
-  if (rc < 0) return rc;
+  if (!b->nhw) return fail("b2_tick_host: call b2_set_hw_joints first");
+  const size_t n = (size_t)b->nhw * b->nenv;
+  const int flags = (b->tick_flags & ~(1 << 30)) | B2_TICK_INTEGRATE | B2_TICK_CONTROLLER | B2_TICK_INVERSE | B2_TICK_HW;
+  if (vel) CK(cudaMemcpyAsync(b->hw_buf, vel, n * 4, cudaMemcpyHostToDevice, b->stream));
+  if (eff) CK(cudaMemcpyAsync(b->hw_buf + n, eff, n * 4, cudaMemcpyHostToDevice, b->stream));
+  if (tick_dispatch(b, flags) < 0) return -1;   // k_hw_write -> tick kernels -> k_hw_read (one graph launch)
+  if (pos) CK(cudaMemcpyAsync(pos, b->hw_buf + 2 * n, n * 4, cudaMemcpyDeviceToHost, b->stream));
+  if (velo) CK(cudaMemcpyAsync(velo, b->hw_buf + 3 * n, n * 4, cudaMemcpyDeviceToHost, b->stream));
+  if (effo) CK(cudaMemcpyAsync(effo, b->hw_buf + 4 * n, n * 4, cudaMemcpyDeviceToHost, b->stream));
   if (sync) CK(cudaStreamSynchronize(b->stream));
   return 0;
 }

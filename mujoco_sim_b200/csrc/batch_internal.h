@@ -36,7 +36,9 @@ struct b2_batch {
   int chain_n = 0;       // > 0: the model is a serial chain of chain_n scalar joints (ChainP<chain_n> kernels)
   int chain_variant = 0; // register budget variant of the chain kernel (B2_CHAIN_VARIANT)
   bool fusable = false;  // joint limits are the only constraint source
-  int tick = 0;
+  bool use_graph = true;  // replay the tick's kernel sequence as a CUDA graph (B2_NO_GRAPH=1 disables)
+  struct GraphEntry { cudaGraphExec_t exec = nullptr; int kernels = 0; };
+  std::map<unsigned long long, GraphEntry> graphs;  // keyed by (tick flags, timestep)
   int wp = 16, epl = 2;  // solver team: 8 lanes x epl elements cover the compact row width
   int smooth_block = 32;
   size_t smooth_smem = 0, blob_smem = 0;

@@ -63,8 +63,8 @@ struct KArgs {
   int* solver_iter;       // [nenvp]
   int* status;            // [nenvp] bit 0: contact cap hit, bit 1: row cap hit, bit 2: state reset (bad value),
                           //         bit 3: integrated by the smooth kernel this tick (B2F_FUSABLE)
-  int* pending;           // [2] environments that need the constraint pipeline, by tick parity (B2F_FUSABLE)
-  int tick;               // tick counter of this launch
+  int* pending;           // [1] environments that need the constraint pipeline this tick (B2F_FUSABLE); cleared by a
+                          //     memset node in front of the smooth kernel
 };
 
 }  // namespace b2

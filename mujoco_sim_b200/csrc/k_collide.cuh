@@ -444,7 +444,7 @@ __device__ void load_geom(GeomW<T>& g, const MV<T>& m, const KArgs<T>& a, int gi
 
 template <typename T, int BLOCK>
 __global__ void __launch_bounds__(BLOCK) k_collide(const KArgs<T> a) {
-  if ((a.flags & B2F_FUSABLE) && a.pending[a.tick & 1] == 0) return;
+  if ((a.flags & B2F_FUSABLE) && a.pending[0] == 0) return;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
   uint32_t* blob = reinterpret_cast<uint32_t*>(smem_raw + 16);

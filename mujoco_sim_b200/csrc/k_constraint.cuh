@@ -354,7 +354,7 @@ __device__ __forceinline__ T primal_force(int type, T jar, T D, T R, T fl) {
 }
 
 #define B2_KERNEL_PROLOGUE                                                           \
-  if ((a.flags & B2F_FUSABLE) && a.pending[a.tick & 1] == 0) return;                 \
+  if ((a.flags & B2F_FUSABLE) && a.pending[0] == 0) return;                 \
   extern __shared__ __align__(16) unsigned char smem_raw[];                          \
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);                             \
   uint32_t* blob = reinterpret_cast<uint32_t*>(smem_raw + 16);                       \

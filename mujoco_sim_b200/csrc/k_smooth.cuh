@@ -555,8 +555,6 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_smooth(const KArgs<T> a) {
   const int nv = P::nv(m), nb = P::nbody(m), nq = P::nq(m), nM = P::nM(m);
   const long long S = a.nenvp;
   const int ntiles = a.nenvp / BLOCK;
-  // the "environments that still need the constraint pipeline" counter of the NEXT tick is cleared one tick ahead
-  if ((a.flags & B2F_FUSABLE) && blockIdx.x == 0 && threadIdx.x == 0) a.pending[(a.tick + 1) & 1] = 0;
 
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int env = tile * BLOCK + threadIdx.x;
@@ -673,7 +671,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_smooth(const KArgs<T> a) {
       a.nefc[env] = 0;
       a.status[env] = (a.status[env] & 7) | (pipeline ? 0 : 8);
       const unsigned vote = __ballot_sync(__activemask(), pipeline);
-      if (vote && (int)(threadIdx.x & 31) == __ffs(vote) - 1) atomicAdd(&a.pending[a.tick & 1], __popc(vote));
+      if (vote && (int)(threadIdx.x & 31) == __ffs(vote) - 1) atomicAdd(&a.pending[0], __popc(vote));
     }
 
     if (pipeline || (a.flags & B2F_EXPORT)) {
