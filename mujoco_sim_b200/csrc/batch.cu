@@ -256,6 +256,16 @@ int run_tick(b2_batch* b, int flags) {
   const int grid = std::max(1, std::min(ntiles, b->nsm * per_sm));
   int rc;
   if (flags & B2_TICK_HW) { if (hw_write_async(b, nullptr, nullptr) < 0) return -1; }
+  if (b->chain_single && !(kf & B2F_XFRC)) {
+    // limit-only serial chain: one kernel does the whole tick (k_chain.cuh)
+    prof_mark(b, SLOT_SMOOTH);
+    if constexpr (sizeof(T) == 4) rc = launch_chain1_f32(b, a, grid); else rc = launch_chain1_f64(b, a, grid);
+    if (rc < 0) return rc;
+    prof_mark(b, SLOT_HW_READ);
+    if (flags & B2_TICK_HW) { if (hw_read_async(b, nullptr, nullptr, nullptr) < 0) return -1; }
+    CK(cudaGetLastError());
+    return 0;
+  }
   if (b->fusable) CK(cudaMemsetAsync(a.pending, 0, sizeof(int), b->stream));
   prof_mark(b, SLOT_SMOOTH);
   if (b->chain_n > 0) rc = launch_chain<T>(b, a, grid);
@@ -578,9 +588,9 @@ b2_batch* b2_create(const mjModel* m, int nenv, int device, int precision) {
     const int n = m->nbody - 1;
     const bool have = have_chain_kernel(n, precision);
     b->chain_n = (chain && have && !getenv("B2_NO_CHAIN")) ? n : 0;
-    // register budget of the chain kernel: 230 registers (best single-warp latency) for batches that cannot fill the
-    // SMs, 128 registers (16 warps / SM) for large ones; measured in profiles/r01_chain_variants.txt
-    b->chain_variant = getenv("B2_CHAIN_VARIANT") ? atoi(getenv("B2_CHAIN_VARIANT")) : (b->nenvp >= 32768 ? 2 : 0);
+    // large batches: 128-thread CTAs, 2 per SM at 255 registers (variant 1) beat 4 per SM at 128 registers
+    // (profiles/r01_chain_variants.txt)
+    b->chain_variant = getenv("B2_CHAIN_VARIANT") ? atoi(getenv("B2_CHAIN_VARIANT")) : 1;
   }
 
   b->epl = 2;

@@ -35,6 +35,7 @@ struct b2_batch {
   bool fused = false, ws_global = false, export_stages = false;
   int chain_n = 0;       // > 0: the model is a serial chain of chain_n scalar joints (ChainP<chain_n> kernels)
   int chain_variant = 0; // register budget variant of the chain kernel (B2_CHAIN_VARIANT)
+  bool chain_single = false;  // limit-only chain: the whole tick runs in k_chain (unless xfrc_applied is in use)
   bool fusable = false;  // joint limits are the only constraint source
   bool use_graph = true;  // replay the tick's kernel sequence as a CUDA graph (B2_NO_GRAPH=1 disables)
   struct GraphEntry { cudaGraphExec_t exec = nullptr; int kernels = 0; };
@@ -64,4 +65,7 @@ namespace b2 {
 int launch_chain_f32(b2_batch* b, const KArgs<float>& a, int grid);
 int launch_chain_f64(b2_batch* b, const KArgs<double>& a, int grid);
 bool have_chain_kernel(int n, int precision);
+// the whole tick of a limit-only serial chain in one kernel (k_chain.cuh, chain1_f32.cu / chain1_f64.cu)
+int launch_chain1_f32(b2_batch* b, const KArgs<float>& a, int grid);
+int launch_chain1_f64(b2_batch* b, const KArgs<double>& a, int grid);
 }  // namespace b2

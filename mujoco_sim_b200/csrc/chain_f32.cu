@@ -22,10 +22,10 @@ int launch(b2_batch* b, const KArgs<T>& a, int grid) {
 }  // namespace
 
 int launch_chain_f32(b2_batch* b, const KArgs<float>& a, int grid) {
-  if (b->chain_n == 7 && b->chain_variant == 1) return b->smooth_block == 32 ? launch<float, 32, ChainP<7>, 12>(b, a, grid) : launch<float, 128, ChainP<7>, 3>(b, a, grid);
-  if (b->chain_n == 7 && b->chain_variant == 2) return b->smooth_block == 32 ? launch<float, 32, ChainP<7>, 16>(b, a, grid) : launch<float, 128, ChainP<7>, 4>(b, a, grid);
-  if (b->chain_n == 7) return b->smooth_block == 32 ? launch<float, 32, ChainP<7>>(b, a, grid) : launch<float, 128, ChainP<7>>(b, a, grid);
-  if (b->chain_n == 6) return b->smooth_block == 32 ? launch<float, 32, ChainP<6>>(b, a, grid) : launch<float, 128, ChainP<6>>(b, a, grid);
+  // CTA of 32 threads / 230 registers for batches that cannot fill the SMs, 128 threads / 128 registers otherwise
+  // (profiles/r01_chain_variants.txt)
+  if (b->chain_n == 7) return b->smooth_block == 32 ? launch<float, 32, ChainP<7>>(b, a, grid) : launch<float, 128, ChainP<7>, 4>(b, a, grid);
+  if (b->chain_n == 6) return b->smooth_block == 32 ? launch<float, 32, ChainP<6>>(b, a, grid) : launch<float, 128, ChainP<6>, 4>(b, a, grid);
   return set_error("no fp32 chain kernel for this chain length");
 }
 bool have_chain_kernel(int n, int precision) { return precision == 4 ? (n == 6 || n == 7) : n == 7; }
