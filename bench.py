@@ -189,12 +189,11 @@ def main():
     bt.tick_host_raw(*host_args)  # uploads the commands once: they stay resident for the device-timed loop
 
     stream = torch.cuda.ExternalStream(bt.stream, device=torch.device("cuda", local_rank))
-    flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    flush = not args.no_flush
 
     def do_flush():
-        if flush is not None:
-            with torch.cuda.stream(stream):
-                flush.fill_(1)  # 256 MiB > 126 MB L2: evicts the batch state between timed steps
+        if flush:
+            bt.l2_flush(256 << 20)  # 256 MiB memset on the batch's stream > 126 MB L2: evicts the state between timed steps
 
     # settle (contacts form) + warm-up, untimed
     for _ in range(SETTLE_TICKS[args.config] + args.warmup):
@@ -213,11 +212,9 @@ def main():
     sampler.start()
     for k in range(K):
         do_flush()
-        with torch.cuda.stream(stream):
-            starts[k].record()
+        starts[k].record(stream)
         bt.tick_resident()          # one CUDA-graph launch: k_hw_write -> tick kernels -> k_hw_read
-        with torch.cuda.stream(stream):
-            ends[k].record()
+        ends[k].record(stream)
     bt.sync(); torch.cuda.synchronize()
     # per-kernel device time: the same K ticks again, launched eagerly with CUDA events between the kernels
     bt.profile_begin(K)
@@ -277,7 +274,7 @@ def main():
         "ms_per_step": max_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "%s: %s" % (args.config, desc), "model": asset, "envs_per_gpu": nenv, "envs_total": total_envs,
                    "timestep": 0.005, "tick": "write+step1+controller+inverse+step2+read", "mean_ncon": ncon_mean, "mean_nefc": nefc_mean,
-                   "l2": "flushed before every timed step (256 MiB fill)" if flush is not None else "not flushed",
+                   "l2": "flushed before every timed step (256 MiB memset)" if flush else "not flushed",
                    "solver": "PGS, %d iterations max" % int(m.int("opt.iterations"))},
         "roofline": {"bound": "hbm", "kernel": "k_" + dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_env_step": balg,

@@ -98,6 +98,9 @@ int b2_tick_host(b2_batch* b, const float* vel_cmd_host, const float* effort_cmd
  * HBM: no host<->device traffic, asynchronous (throughput with resident inputs) */
 int b2_tick_resident(b2_batch* b);
 
+/* benchmarking aid: write `bytes` of scratch on the batch's stream so that the state leaves the L2 between timed steps */
+int b2_l2_flush(b2_batch* b, long long bytes);
+
 /* per-kernel device timing with CUDA events on the batch's stream: profile up to max_ticks ticks, then read the summed
  * milliseconds per kernel slot {hw_write, smooth, collide, make_constraint, project, pgs, integrate, hw_read} */
 int b2_profile_begin(b2_batch* b, int max_ticks);

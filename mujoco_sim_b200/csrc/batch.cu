@@ -590,6 +590,7 @@ b2_batch* b2_create(const mjModel* m, int nenv, int device, int precision) {
     b->chain_n = (chain && have && !getenv("B2_NO_CHAIN")) ? n : 0;
     // large batches: 128-thread CTAs, 2 per SM at 255 registers (variant 1) beat 4 per SM at 128 registers
     // (profiles/r01_chain_variants.txt)
+    b->chain_single = b->chain_n > 0 && (b->fusable || b->fused) && !b->export_stages && !getenv("B2_NO_CHAIN1");
     b->chain_variant = getenv("B2_CHAIN_VARIANT") ? atoi(getenv("B2_CHAIN_VARIANT")) : 1;
   }
 
@@ -714,6 +715,7 @@ void b2_destroy(b2_batch* b) {
   if (b->hw_dadr) cudaFree(b->hw_dadr);
   if (b->hw_ctl) cudaFree(b->hw_ctl);
   if (b->hw_buf) cudaFree(b->hw_buf);
+  if (b->flush_buf) cudaFree(b->flush_buf);
   for (cudaEvent_t e : b->prof_ev) cudaEventDestroy(e);
   drop_graphs(b);
   if (b->stream) cudaStreamDestroy(b->stream);
@@ -941,6 +943,20 @@ int b2_tick_host(b2_batch* b, const float* vel, const float* eff, float* pos, fl
 int b2_tick_resident(b2_batch* b) {
   if (!b) return fail("b2_tick_resident: null batch");
   return tick_hw(b, nullptr, nullptr, nullptr, nullptr, nullptr, false);
+}
+
+// write `bytes` of scratch on the batch's stream: evicts the batch state from the 126 MB L2 between timed steps
+int b2_l2_flush(b2_batch* b, long long bytes) {
+  if (!b || bytes <= 0) return fail("b2_l2_flush: bad argument");
+  CK(cudaSetDevice(b->device));
+  if ((size_t)bytes > b->flush_bytes) {
+    if (b->flush_buf) cudaFree(b->flush_buf);
+    b->flush_buf = nullptr; b->flush_bytes = 0;
+    CK(cudaMalloc(&b->flush_buf, (size_t)bytes));
+    b->flush_bytes = (size_t)bytes;
+  }
+  CK(cudaMemsetAsync(b->flush_buf, 1, (size_t)bytes, b->stream));
+  return 0;
 }
 
 int b2_profile_begin(b2_batch* b, int max_ticks) {

@@ -43,6 +43,8 @@ struct b2_batch {
   int wp = 16, epl = 2;  // solver team: 8 lanes x epl elements cover the compact row width
   int smooth_block = 32;
   size_t smooth_smem = 0, blob_smem = 0;
+  void* flush_buf = nullptr;
+  size_t flush_bytes = 0;
   void* stage_dev = nullptr;
   size_t stage_bytes = 0;
   long long launches = 0;

@@ -85,6 +85,7 @@ _sig = {
     "b2_read_joints": (_i, [_vp, _vp, _vp, _vp]),
     "b2_tick_host": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "b2_tick_resident": (_i, [_vp]),
+    "b2_l2_flush": (_i, [_vp, C.c_longlong]),
     "b2_profile_begin": (_i, [_vp, _i]),
     "b2_profile_end": (_i, [_vp, _vp, _i]),
     "b2_mirror_env": (_i, [_vp, _i, _vp]),
@@ -327,6 +328,9 @@ class Batch:
 
     def tick_resident(self):
         self._ck(lib.b2_tick_resident(self.ptr), "b2_tick_resident")
+
+    def l2_flush(self, nbytes=256 << 20):
+        self._ck(lib.b2_l2_flush(self.ptr, int(nbytes)), "b2_l2_flush")
 
     PROFILE_SLOTS = ["hw_write", "smooth", "collide", "make_constraint", "project", "pgs", "integrate", "hw_read"]
 

@@ -379,3 +379,26 @@ def test_collision_zoo_contacts_match_oracle(b2, orc):
                 np.testing.assert_allclose([cf[e, (4 + i) * ncm + c] for i in range(3)], k["frame"][:3], atol=tol * 100)
         assert flips <= nenv // 16, flips
         bt.close()
+
+
+def test_limit_only_chain_runs_as_one_kernel_per_tick(b2):
+    """C2 path: the whole tick of a limit-only serial chain is ONE kernel (k_chain); the hardware-interface scatter /
+    gather add two small ones.  Guards against silently falling back to the six-kernel pipeline."""
+    m = b2.Model(b2.asset("panda7.xml"))
+    bt = b2.Batch(m, 256)
+    l0 = bt.launch_count
+    bt.step(10); bt.sync()
+    assert bt.launch_count - l0 == 10
+    bt.set_controlled(np.ones(7, np.uint8)); bt.set_hw_joints(np.arange(7))
+    z = np.zeros((7, 256), np.float32); o = [np.empty((7, 256), np.float32) for _ in range(3)]
+    l0 = bt.launch_count
+    for _ in range(5):
+        bt.tick_host_raw(z.ctypes.data, z.ctypes.data, *[x.ctypes.data for x in o])
+    assert bt.launch_count - l0 == 15
+    # joints driven into their limits are handled inside the same kernel: positions stay within range + tolerance
+    qpos = np.tile(np.array(m.jnt_range.reshape(-1, 2)[:, 1]) - 0.01, (256, 1))
+    bt.set("qpos", qpos); bt.set("qvel", np.full((256, 7), 2.0))
+    bt.step(200); bt.sync()
+    q = bt.get("qpos")
+    hi = m.jnt_range.reshape(-1, 2)[:, 1]
+    assert np.all(q < hi + 0.05) and bt.get("nefc").max() >= 1
