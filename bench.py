@@ -275,8 +275,8 @@ def main():
         "config": {"workload": "%s: %s" % (args.config, desc), "model": asset, "envs_per_gpu": nenv, "envs_total": total_envs,
                    "timestep": 0.005, "tick": "write+step1+controller+inverse+step2+read", "mean_ncon": ncon_mean, "mean_nefc": nefc_mean,
                    "l2": "flushed before every timed step (256 MiB memset)" if flush else "not flushed",
-                   "solver": "PGS, %d iterations max" % int(m.int("opt.iterations"))},
-        "roofline": {"bound": "hbm", "kernel": "k_" + dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                   "solver": "PGS, %d iterations max" % int(m.int("opt.iterations")), "kernels": bt.path_name},
+        "roofline": {"bound": "hbm", "kernel": (bt.path_name.split("+")[0] if dom == "smooth" else {"pgs": "k_pgs_team"}.get(dom, "k_" + dom)), "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_env_step": balg,
                      "kernel_timing": "CUDA events between the kernels, same K ticks re-run eagerly right after the graph-replayed timed loop",
                      "kernel_ms": dom_ms, "kernel_share_of_step": kern[dom] / max(1e-12, sum(slot_ms.values())),

@@ -1,30 +1,22 @@
-import sys, time; sys.path.insert(0,'/root/repo')
-import numpy as np, torch, mujoco_sim_b200 as b2
-from mujoco_sim_b200 import workloads as w
-for nenv in [4096, 262144]:
-    m = b2.Model(b2.asset("panda7.xml"))
-    bt = b2.Batch(m, nenv)
-    w.load_config("c2", bt)
-    hw = np.arange(7, dtype=np.int32); bt.set_controlled(np.ones(7, np.uint8)); bt.set_hw_joints(hw)
-    vel = np.zeros((7, nenv), np.float32); eff = np.zeros((7, nenv), np.float32)
-    pos = np.empty_like(vel); v2 = np.empty_like(vel); e2 = np.empty_like(vel)
-    bt.tick_host_raw(vel.ctypes.data, eff.ctypes.data, pos.ctypes.data, v2.ctypes.data, e2.ctypes.data)
-    stream = torch.cuda.ExternalStream(bt.stream)
-    buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    big = torch.empty(64 << 20, dtype=torch.float32, device="cuda")
-    def flush_fill():
-        with torch.cuda.stream(stream): buf.fill_(1)
-    def flush_memset(): bt.l2_flush(256 << 20)
-    def flush_read():
-        with torch.cuda.stream(stream): big.sum()
-    def flush_none(): pass
-    for name, fl in [("none", flush_none), ("torch_fill", flush_fill), ("memset", flush_memset), ("read_sum", flush_read), ("torch_fill", flush_fill)]:
-        for _ in range(5): fl(); bt.tick_resident()
-        bt.sync()
-        K = 40
-        st = [torch.cuda.Event(enable_timing=True) for _ in range(K)]; en = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
-        for k in range(K):
-            fl(); st[k].record(stream); bt.tick_resident(); en[k].record(stream)
-        bt.sync(); torch.cuda.synchronize()
-        ts = np.array([s.elapsed_time(e) for s, e in zip(st, en)])
-        print(nenv, name, "mean %.4f ms  median %.4f  min %.4f  max %.4f" % (ts.mean(), np.median(ts), ts.min(), ts.max()), flush=True)
+import sys, os, json, subprocess; sys.path.insert(0,'/root/repo')
+import numpy as np, mujoco_sim_b200 as b2
+from oracle import pyoracle as orc
+model = b2.asset("mobile_arm.xml")
+def oracle(nticks):
+    m = b2.Model(model); d = b2.Data(m); nv = m.nv; arm=[3,4,5]
+    ctl = np.zeros(nv, np.uint8); ctl[arm]=1; ddq=np.zeros(nv); dq=np.zeros(nv); eff=np.zeros(3)
+    for t in range(nticks):
+        orc.call("step1", m, d); orc.controller(m, d, ddq, dq, ctl); orc.call("inverse", m, d)
+        eff = np.array(d.qfrc_inverse)[arm]; q, qd = np.array(d.qpos)[arm], np.array(d.qvel)[arm]
+        for i in range(3):
+            vcmd = 0.2 if (i == 1 and t % 10 == 3) else 0.0
+            if abs(vcmd) > 1e-15: dq[arm[i]] = vcmd
+            else: ddq[arm[i]] = 20.0 * (0.3 * (i + 1) - q[i]) - 4.0 * qd[i]
+        orc.call("step2", m, d)
+        orc.set_odom_vels(m, d, [0, 1, -1], [-1, -1, 2], [-1, -1, 2], [0.4, -0.1, 0, 0, 0, 0.3])
+    return eff, np.array(d.qacc), np.array(d.qfrc_passive)[arm], np.array(d.qfrc_bias)[arm]
+for n in [1, 2, 3, 4, 5, 6, 10]:
+    res = subprocess.run(["tests/_compat/compat_tick", model, str(n)], capture_output=True, text=True, env=dict(os.environ, B2_PRECISION="8"))
+    got = json.loads(res.stdout.strip().splitlines()[-1])
+    e, qa, pas, bias = oracle(n)
+    print(n, "gpu", np.round(got["effort"], 6), "oracle", np.round(e, 6))

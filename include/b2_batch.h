@@ -46,6 +46,7 @@ int b2_device_count(void);
  * path) or B2_F64 (validation of the algorithm against the fp64 oracle without rounding noise). */
 b2_batch* b2_create(const mjModel* m, int nenv, int device, int precision);
 void b2_destroy(b2_batch* b);
+const char* b2_path_name(const b2_batch* b); /* kernels a tick launches, e.g. "k_chain<7>" */
 int b2_nenv(const b2_batch* b);
 int b2_nenv_padded(const b2_batch* b);
 int b2_precision(const b2_batch* b);

@@ -722,6 +722,17 @@ void b2_destroy(b2_batch* b) {
   delete b;
 }
 
+// which kernels a tick of this batch launches (for reports): "k_chain<N>", "k_smooth<ChainP<N>>+pipeline",
+// "k_smooth<GenericP>" (no constraint source) or "k_smooth<GenericP>+pipeline"
+const char* b2_path_name(const b2_batch* b) {
+  static thread_local char buf[64];
+  if (!b) return "";
+  if (b->chain_single) std::snprintf(buf, sizeof(buf), "k_chain<%d>", b->chain_n);
+  else if (b->chain_n > 0) std::snprintf(buf, sizeof(buf), "k_smooth<ChainP<%d>>%s", b->chain_n, b->fused ? "" : "+pipeline");
+  else std::snprintf(buf, sizeof(buf), "k_smooth<GenericP>%s", b->fused ? "" : "+pipeline");
+  return buf;
+}
+
 int b2_nenv(const b2_batch* b) { return b ? b->nenv : -1; }
 int b2_nenv_padded(const b2_batch* b) { return b ? b->nenvp : -1; }
 int b2_precision(const b2_batch* b) { return b ? b->prec : -1; }

@@ -697,7 +697,13 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_smooth(const KArgs<T> a) {
         for (int i = 0; i < nv; i++) a.qvel[i * S + env] = s.qvel[i];
       }
     }
-    if (!pipeline) {
+    if (!pipeline && (a.flags & B2F_NOSOLVE)) {
+      // mj_step1 leaves qacc alone (MjHWInterface::read needs the previous tick's); only a velocity override is kept
+      if (P::STATIC && overridden) {
+#pragma unroll(P::UNROLL)
+        for (int i = 0; i < nv; i++) a.qvel[i * S + env] = s.qvel[i];
+      }
+    } else if (!pipeline) {
       // no active constraint: qacc = qacc_smooth, integrate right here
 #pragma unroll(P::UNROLL)
       for (int i = 0; i < nv; i++) {

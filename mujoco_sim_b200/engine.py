@@ -58,6 +58,7 @@ _sig = {
     "b2_device_count": (_i, []),
     "b2_create": (_vp, [_vp, _i, _i, _i]),
     "b2_destroy": (None, [_vp]),
+    "b2_path_name": (_cp, [_vp]),
     "b2_nenv": (_i, [_vp]),
     "b2_nenv_padded": (_i, [_vp]),
     "b2_precision": (_i, [_vp]),
@@ -299,6 +300,10 @@ class Batch:
 
     def sync(self):
         self._ck(lib.b2_sync(self.ptr), "b2_sync")
+
+    @property
+    def path_name(self):
+        return (lib.b2_path_name(self.ptr) or b"").decode()
 
     @property
     def stream(self):
