@@ -186,7 +186,7 @@ def main():
     vel_o = torch.empty_like(pos_o).pin_memory()
     eff_o = torch.empty_like(pos_o).pin_memory()
     host_args = (vel_cmd.data_ptr(), eff_cmd.data_ptr(), pos_o.data_ptr(), vel_o.data_ptr(), eff_o.data_ptr())
-    bt.tick_host_raw(*host_args)  # uploads the commands once: they stay resident for the device-timed loop
+    bt.write_commands(vel_cmd.numpy(), eff_cmd.numpy())  # uploads the commands once: they stay resident in HBM for the device-timed loop
 
     stream = torch.cuda.ExternalStream(bt.stream, device=torch.device("cuda", local_rank))
     flush = not args.no_flush

@@ -161,6 +161,7 @@ int pack_model(b2_batch* b) {
 }
 
 void drop_graphs(b2_batch* b);
+int tick_eager(b2_batch* b, int flags);
 int upload_model(b2_batch* b) {
   drop_graphs(b);  // kernel arguments / constants may change
   if (pack_model(b) < 0) return -1;
@@ -210,6 +211,8 @@ KArgs<T> make_args(b2_batch* b, int flags) {
   a.efc_KBI = R("efc_KBI"); a.efc_vel = R("efc_vel"); a.efc_aref = R("efc_aref"); a.efc_b = R("efc_b"); a.efc_force = R("efc_force");
   a.efc_ARdiag = R("efc_ARdiag"); a.efc_rows = R("efc_rows"); a.efc_meta = R("efc_meta"); a.wp = b->wp; a.solver_iter = I("solver_iter"); a.status = I("status");
   a.pending = I("_pending");
+  a.hw_vel = b->io_in[0]; a.hw_eff = b->io_in[1];
+  a.hw_pos = b->io_out[0]; a.hw_velo = b->io_out[1]; a.hw_effo = b->io_out[2];
   return a;
 }
 
@@ -232,8 +235,9 @@ int launch_chain(b2_batch* b, const KArgs<T>& a, int grid) {
   else return launch_chain_f64(b, a, grid);
 }
 
-int hw_write_async(b2_batch* b, const float* vel, const float* eff);
-int hw_read_async(b2_batch* b, float* pos, float* vel, float* eff);
+void io_default(b2_batch* b);
+int hw_write_async(b2_batch* b);  // k_hw_write from b->io_in
+int hw_read_async(b2_batch* b);   // k_hw_read into b->io_out
 enum { B2_TICK_HW = 1 << 20 };  // internal: run k_hw_write / k_hw_read around the tick kernels
 
 template <typename T>
@@ -249,20 +253,24 @@ int run_tick(b2_batch* b, int flags) {
   if (b->fusable) kf |= B2F_FUSABLE;
   if (b->tick_flags & (1 << 30)) kf |= B2F_XFRC;  // set once xfrc_applied has been written
   if (b->export_stages) kf |= B2F_EXPORT;
+  const bool single = b->chain_single && !(kf & B2F_XFRC);
+  // k_chain does the hardware-interface exchange itself when the hardware joints are exactly the chain's dofs
+  const bool hwio = single && (flags & B2_TICK_HW) && b->hw_identity && (kf & B2F_CONTROLLER) && !(kf & B2F_ODOM) && !getenv("B2_NO_HWIO");
+  if (hwio) kf |= B2F_HWIO;
   KArgs<T> a = make_args<T>(b, kf);
   const int ntiles = b->nenvp / b->smooth_block;
   int per_sm = (int)std::max<size_t>(1, (227 * 1024) / std::max<size_t>(1, b->smooth_smem));
   if (getenv("B2_SMOOTH_CTAS_PER_SM")) per_sm = std::max(1, atoi(getenv("B2_SMOOTH_CTAS_PER_SM")));
   const int grid = std::max(1, std::min(ntiles, b->nsm * per_sm));
   int rc;
-  if (flags & B2_TICK_HW) { if (hw_write_async(b, nullptr, nullptr) < 0) return -1; }
-  if (b->chain_single && !(kf & B2F_XFRC)) {
+  if ((flags & B2_TICK_HW) && !hwio) { if (hw_write_async(b) < 0) return -1; }
+  if (single) {
     // limit-only serial chain: one kernel does the whole tick (k_chain.cuh)
     prof_mark(b, SLOT_SMOOTH);
     if constexpr (sizeof(T) == 4) rc = launch_chain1_f32(b, a, grid); else rc = launch_chain1_f64(b, a, grid);
     if (rc < 0) return rc;
     prof_mark(b, SLOT_HW_READ);
-    if (flags & B2_TICK_HW) { if (hw_read_async(b, nullptr, nullptr, nullptr) < 0) return -1; }
+    if ((flags & B2_TICK_HW) && !hwio) { if (hw_read_async(b) < 0) return -1; }
     CK(cudaGetLastError());
     return 0;
   }
@@ -302,7 +310,7 @@ int run_tick(b2_batch* b, int flags) {
     }
   }
   prof_mark(b, SLOT_HW_READ);
-  if (flags & B2_TICK_HW) { if (hw_read_async(b, nullptr, nullptr, nullptr) < 0) return -1; }
+  if (flags & B2_TICK_HW) { if (hw_read_async(b) < 0) return -1; }
   CK(cudaGetLastError());
   return 0;
 }
@@ -339,7 +347,14 @@ int tick_dispatch(b2_batch* b, int flags) {
   float hf = (float)b->h;
   uint32_t hb;
   std::memcpy(&hb, &hf, 4);
-  const unsigned long long key = ((unsigned long long)(unsigned)(flags | (b->tick_flags & (1 << 30))) << 32) | hb;
+  // a tick that is a single kernel gains nothing from a graph
+  if ((flags & B2_TICK_HW) && b->chain_single && b->hw_identity && !(b->tick_flags & (1 << 30))) return tick_eager(b, flags);
+  unsigned long long ph = 0;  // the exchange buffers are baked into the captured kernel arguments
+  if (flags & B2_TICK_HW)
+    for (const void* p : {(const void*)b->io_in[0], (const void*)b->io_in[1], (const void*)b->io_out[0], (const void*)b->io_out[1], (const void*)b->io_out[2]})
+      ph = ph * 0x9E3779B97F4A7C15ull + (unsigned long long)(uintptr_t)p;
+  const std::pair<unsigned long long, unsigned long long> key{((unsigned long long)(unsigned)(flags | (b->tick_flags & (1 << 30))) << 32) | hb, ph};
+  if (b->graphs.size() > 32) drop_graphs(b);
   auto it = b->graphs.find(key);
   if (it == b->graphs.end()) {  // first use: eager
     b->graphs[key] = b2_batch::GraphEntry{};
@@ -716,6 +731,7 @@ void b2_destroy(b2_batch* b) {
   if (b->hw_ctl) cudaFree(b->hw_ctl);
   if (b->hw_buf) cudaFree(b->hw_buf);
   if (b->flush_buf) cudaFree(b->flush_buf);
+  for (auto& kv : b->registered) cudaHostUnregister(const_cast<void*>(kv.first));
   for (cudaEvent_t e : b->prof_ev) cudaEventDestroy(e);
   drop_graphs(b);
   if (b->stream) cudaStreamDestroy(b->stream);
@@ -873,55 +889,91 @@ int b2_set_hw_joints(b2_batch* b, int njoint, const int* jnt_ids) {
   CK(cudaMemcpy(b->hw_dadr, dadr.data(), sizeof(int) * njoint, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(b->hw_ctl, ctl.data(), sizeof(int) * njoint, cudaMemcpyHostToDevice));
   b->nhw = njoint;
+  b->hw_identity = njoint == b->m->nv;
+  for (int j = 0; j < njoint && b->hw_identity; j++) b->hw_identity = qadr[j] == j && dadr[j] == j;
+  io_default(b);
   return 0;
 }
 
 }  // extern "C"
 namespace {
-int hw_write_async(b2_batch* b, const float* vel, const float* eff) {
+void io_default(b2_batch* b) {  // the exchange runs on the HBM staging buffers
+  const size_t n = (size_t)b->nhw * b->nenv;
+  b->io_in[0] = b->hw_buf; b->io_in[1] = b->hw_buf + n;
+  b->io_out[0] = b->hw_buf + 2 * n; b->io_out[1] = b->hw_buf + 3 * n; b->io_out[2] = b->hw_buf + 4 * n;
+}
+int hw_write_async(b2_batch* b) {
   if (!b->nhw) return fail("b2_write_commands: call b2_set_hw_joints first");
   const size_t n = (size_t)b->nhw * b->nenv;
-  float* dv = b->hw_buf;
-  float* de = b->hw_buf + n;
-  // NULL host pointers: the command buffers already resident in HBM (from the previous upload) are re-issued
-  if (vel) CK(cudaMemcpyAsync(dv, vel, n * 4, cudaMemcpyHostToDevice, b->stream));
-  if (eff) CK(cudaMemcpyAsync(de, eff, n * 4, cudaMemcpyHostToDevice, b->stream));
   const int th = 256, bl = (int)((n + th - 1) / th);
-  if (b->prec == 8) k_hw_write<double><<<bl, th, 0, b->stream>>>((double*)b->fields["ddq"].ptr, (double*)b->fields["dq"].ptr, dv, de, b->hw_dadr, b->hw_ctl, b->nhw, b->nenv, b->nenvp);
-  else k_hw_write<float><<<bl, th, 0, b->stream>>>((float*)b->fields["ddq"].ptr, (float*)b->fields["dq"].ptr, dv, de, b->hw_dadr, b->hw_ctl, b->nhw, b->nenv, b->nenvp);
+  if (b->prec == 8) k_hw_write<double><<<bl, th, 0, b->stream>>>((double*)b->fields["ddq"].ptr, (double*)b->fields["dq"].ptr, b->io_in[0], b->io_in[1], b->hw_dadr, b->hw_ctl, b->nhw, b->nenv, b->nenvp);
+  else k_hw_write<float><<<bl, th, 0, b->stream>>>((float*)b->fields["ddq"].ptr, (float*)b->fields["dq"].ptr, b->io_in[0], b->io_in[1], b->hw_dadr, b->hw_ctl, b->nhw, b->nenv, b->nenvp);
   b->launches++;
   CK(cudaGetLastError());
   return 0;
 }
-int hw_read_async(b2_batch* b, float* pos, float* vel, float* eff) {
+int hw_read_async(b2_batch* b) {
   if (!b->nhw) return fail("b2_read_joints: call b2_set_hw_joints first");
   const size_t n = (size_t)b->nhw * b->nenv;
-  float *dp = b->hw_buf + 2 * n, *dv = b->hw_buf + 3 * n, *de = b->hw_buf + 4 * n;
   const int th = 256, bl = (int)((n + th - 1) / th);
-  if (b->prec == 8) k_hw_read<double><<<bl, th, 0, b->stream>>>((const double*)b->fields["qpos"].ptr, (const double*)b->fields["qvel"].ptr, (const double*)b->fields["qfrc_inverse"].ptr, dp, dv, de, b->hw_qadr, b->hw_dadr, b->nhw, b->nenv, b->nenvp);
-  else k_hw_read<float><<<bl, th, 0, b->stream>>>((const float*)b->fields["qpos"].ptr, (const float*)b->fields["qvel"].ptr, (const float*)b->fields["qfrc_inverse"].ptr, dp, dv, de, b->hw_qadr, b->hw_dadr, b->nhw, b->nenv, b->nenvp);
+  if (b->prec == 8) k_hw_read<double><<<bl, th, 0, b->stream>>>((const double*)b->fields["qpos"].ptr, (const double*)b->fields["qvel"].ptr, (const double*)b->fields["qfrc_inverse"].ptr, b->io_out[0], b->io_out[1], b->io_out[2], b->hw_qadr, b->hw_dadr, b->nhw, b->nenv, b->nenvp);
+  else k_hw_read<float><<<bl, th, 0, b->stream>>>((const float*)b->fields["qpos"].ptr, (const float*)b->fields["qvel"].ptr, (const float*)b->fields["qfrc_inverse"].ptr, b->io_out[0], b->io_out[1], b->io_out[2], b->hw_qadr, b->hw_dadr, b->nhw, b->nenv, b->nenvp);
   b->launches++;
   CK(cudaGetLastError());
-  if (pos) CK(cudaMemcpyAsync(pos, dp, n * 4, cudaMemcpyDeviceToHost, b->stream));
-  if (vel) CK(cudaMemcpyAsync(vel, dv, n * 4, cudaMemcpyDeviceToHost, b->stream));
-  if (eff) CK(cudaMemcpyAsync(eff, de, n * 4, cudaMemcpyDeviceToHost, b->stream));
   return 0;
+}
+
+// Device-accessible alias of a caller buffer, or nullptr when it has to be staged.  Device memory and pinned host memory
+// (cudaHostAlloc / cudaHostRegister) are used in place: the kernels read the commands and write the joint states over
+// PCIe themselves, which removes five staging copies from the control tick.  Pageable host memory is pinned once with
+// cudaHostRegister and remembered (B2_NO_ZEROCOPY=1 turns all of this off).
+float* device_alias(b2_batch* b, const void* host, size_t bytes) {
+  static const bool off = getenv("B2_NO_ZEROCOPY") != nullptr;
+  if (off || !host) return nullptr;
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  if (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) return (float*)const_cast<void*>(host);
+  if (at.type == cudaMemoryTypeHost) return (float*)at.devicePointer;
+  auto it = b->registered.find(host);
+  if (it == b->registered.end() || it->second < bytes) {
+    if (it != b->registered.end()) { cudaHostUnregister(const_cast<void*>(host)); b->registered.erase(it); }
+    if (cudaHostRegister(const_cast<void*>(host), bytes, cudaHostRegisterMapped | cudaHostRegisterPortable) != cudaSuccess) {
+      cudaGetLastError();
+      return nullptr;
+    }
+    b->registered[host] = bytes;
+  }
+  void* dp = nullptr;
+  if (cudaHostGetDevicePointer(&dp, const_cast<void*>(host), 0) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return (float*)dp;
 }
 
 }  // namespace
 extern "C" {
 
+// upload the command buffers into the HBM staging area and apply them (MjHWInterface::write for every environment)
 int b2_write_commands(b2_batch* b, const float* vel, const float* eff) {
   if (!b || !vel || !eff) return fail("b2_write_commands: null argument");
   CK(cudaSetDevice(b->device));
-  if (hw_write_async(b, vel, eff) < 0) return -1;
+  if (!b->nhw) return fail("b2_write_commands: call b2_set_hw_joints first");
+  const size_t n = (size_t)b->nhw * b->nenv;
+  io_default(b);
+  CK(cudaMemcpyAsync(b->hw_buf, vel, n * 4, cudaMemcpyDefault, b->stream));
+  CK(cudaMemcpyAsync(b->hw_buf + n, eff, n * 4, cudaMemcpyDefault, b->stream));
+  if (hw_write_async(b) < 0) return -1;
   CK(cudaStreamSynchronize(b->stream));
   return 0;
 }
 int b2_read_joints(b2_batch* b, float* pos, float* vel, float* eff) {
   if (!b) return fail("b2_read_joints: null batch");
   CK(cudaSetDevice(b->device));
-  if (hw_read_async(b, pos, vel, eff) < 0) return -1;
+  if (!b->nhw) return fail("b2_read_joints: call b2_set_hw_joints first");
+  const size_t n = (size_t)b->nhw * b->nenv;
+  io_default(b);
+  if (hw_read_async(b) < 0) return -1;
+  if (pos) CK(cudaMemcpyAsync(pos, b->io_out[0], n * 4, cudaMemcpyDefault, b->stream));
+  if (vel) CK(cudaMemcpyAsync(vel, b->io_out[1], n * 4, cudaMemcpyDefault, b->stream));
+  if (eff) CK(cudaMemcpyAsync(eff, b->io_out[2], n * 4, cudaMemcpyDefault, b->stream));
   CK(cudaStreamSynchronize(b->stream));
   return 0;
 }
@@ -936,12 +988,24 @@ static int tick_hw(b2_batch* b, const float* vel, const float* eff, float* pos, 
   if (!b->nhw) return fail("b2_tick_host: call b2_set_hw_joints first");
   const size_t n = (size_t)b->nhw * b->nenv;
   const int flags = (b->tick_flags & ~(1 << 30)) | B2_TICK_INTEGRATE | B2_TICK_CONTROLLER | B2_TICK_INVERSE | B2_TICK_HW;
-  if (vel) CK(cudaMemcpyAsync(b->hw_buf, vel, n * 4, cudaMemcpyHostToDevice, b->stream));
-  if (eff) CK(cudaMemcpyAsync(b->hw_buf + n, eff, n * 4, cudaMemcpyHostToDevice, b->stream));
-  if (tick_dispatch(b, flags) < 0) return -1;   // k_hw_write -> tick kernels -> k_hw_read (one graph launch)
-  if (pos) CK(cudaMemcpyAsync(pos, b->hw_buf + 2 * n, n * 4, cudaMemcpyDeviceToHost, b->stream));
-  if (velo) CK(cudaMemcpyAsync(velo, b->hw_buf + 3 * n, n * 4, cudaMemcpyDeviceToHost, b->stream));
-  if (effo) CK(cudaMemcpyAsync(effo, b->hw_buf + 4 * n, n * 4, cudaMemcpyDeviceToHost, b->stream));
+  io_default(b);
+  // buffers that are not device-accessible in place go through the HBM staging area
+  const float* in[2] = {vel, eff};
+  float* out[3] = {pos, velo, effo};
+  float* stage_out[3] = {nullptr, nullptr, nullptr};
+  for (int k = 0; k < 2; k++) {
+    if (!in[k]) continue;  // resident: the staging buffer of the last upload is re-issued
+    if (const float* d = device_alias(b, in[k], n * 4)) b->io_in[k] = d;
+    else CK(cudaMemcpyAsync(b->hw_buf + k * n, in[k], n * 4, cudaMemcpyHostToDevice, b->stream));
+  }
+  for (int k = 0; k < 3; k++) {
+    if (!out[k]) continue;
+    if (float* d = device_alias(b, out[k], n * 4)) b->io_out[k] = d;
+    else stage_out[k] = b->hw_buf + (2 + k) * n;
+  }
+  if (tick_dispatch(b, flags) < 0) return -1;
+  for (int k = 0; k < 3; k++)
+    if (stage_out[k]) CK(cudaMemcpyAsync(out[k], stage_out[k], n * 4, cudaMemcpyDeviceToHost, b->stream));
   if (sync) CK(cudaStreamSynchronize(b->stream));
   return 0;
 }
@@ -950,7 +1014,7 @@ int b2_tick_host(b2_batch* b, const float* vel, const float* eff, float* pos, fl
   if (!b || !vel || !eff) return fail("b2_tick_host: null argument");
   return tick_hw(b, vel, eff, pos, velo, effo, true);
 }
-// same tick with the commands already resident in HBM and the joint states left in HBM (asynchronous)
+// same tick with the commands already resident in HBM (b2_write_commands) and the joint states left in HBM (asynchronous)
 int b2_tick_resident(b2_batch* b) {
   if (!b) return fail("b2_tick_resident: null batch");
   return tick_hw(b, nullptr, nullptr, nullptr, nullptr, nullptr, false);

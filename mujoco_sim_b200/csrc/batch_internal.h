@@ -39,7 +39,7 @@ struct b2_batch {
   bool fusable = false;  // joint limits are the only constraint source
   bool use_graph = true;  // replay the tick's kernel sequence as a CUDA graph (B2_NO_GRAPH=1 disables)
   struct GraphEntry { cudaGraphExec_t exec = nullptr; int kernels = 0; };
-  std::map<unsigned long long, GraphEntry> graphs;  // keyed by (tick flags, timestep)
+  std::map<std::pair<unsigned long long, unsigned long long>, GraphEntry> graphs;  // keyed by (tick flags, timestep; exchange buffers)
   int wp = 16, epl = 2;  // solver team: 8 lanes x epl elements cover the compact row width
   int smooth_block = 32;
   size_t smooth_smem = 0, blob_smem = 0;
@@ -54,6 +54,12 @@ struct b2_batch {
   int nhw = 0;
   int *hw_qadr = nullptr, *hw_dadr = nullptr, *hw_ctl = nullptr;
   float* hw_buf = nullptr;  // [5][nhw][nenv] fp32 staging: vel_cmd, effort_cmd, pos, vel, effort
+  bool hw_identity = false; // hardware joint j is dof j for every dof (lets k_chain do the exchange itself)
+  // buffers the exchange of the tick being launched reads / writes: the hw_buf slots, or device-accessible aliases of the
+  // caller's host buffers (pinned / registered memory is read and written in place over PCIe, no staging copies)
+  const float* io_in[2] = {nullptr, nullptr};
+  float* io_out[3] = {nullptr, nullptr, nullptr};
+  std::map<const void*, size_t> registered;  // host ranges this batch pinned with cudaHostRegister
   // per-kernel CUDA-event profiling (b2_profile_begin / b2_profile_end)
   std::vector<cudaEvent_t> prof_ev;  // [max_ticks][B2_NSLOT + 1]
   std::vector<unsigned> prof_mask;   // which boundary events of each tick were recorded

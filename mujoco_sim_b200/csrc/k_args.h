@@ -17,7 +17,9 @@ enum TickFlags : int {
   B2F_EXPORT = 1 << 7,
   B2F_NOSOLVE = 1 << 8,      // stop after constraint assembly (mj_step1)
   B2F_FUSABLE = 1 << 9,      // joint limits are the only constraint source: environments without an active limit are
-                             // integrated by the smooth kernel (status bit 8) and skipped by the constraint pipeline       // also export the stage arrays from the fused kernel (legacy mjData mirror)
+                             // integrated by the smooth kernel (status bit 8) and skipped by the constraint pipeline
+  B2F_HWIO = 1 << 10,        // k_chain also does MjHWInterface::write / read (hardware joint j == dof j): commands are read
+                             // from, and joint states written to, the hw_* buffers (HBM or mapped host memory)
 };
 
 // contact record, SoA: field f of contact c of env e at con[(f * nconmax + c) * nenvp + e]
@@ -63,6 +65,9 @@ struct KArgs {
   int* solver_iter;       // [nenvp]
   int* status;            // [nenvp] bit 0: contact cap hit, bit 1: row cap hit, bit 2: state reset (bad value),
                           //         bit 3: integrated by the smooth kernel this tick (B2F_FUSABLE)
+  // hardware-interface exchange, native layout [joint][nenv] fp32; HBM staging or mapped (zero-copy) host memory
+  const float *hw_vel, *hw_eff;
+  float *hw_pos, *hw_velo, *hw_effo;
   int* pending;           // [1] environments that need the constraint pipeline this tick (B2F_FUSABLE); cleared by a
                           //     memset node in front of the smooth kernel
 };

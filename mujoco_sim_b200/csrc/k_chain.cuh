@@ -45,6 +45,23 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_chain(const KArgs<T> a) {
       q[i] = a.qpos[i * S + env]; v[i] = a.qvel[i * S + env]; qa[i] = a.qacc[i * S + env]; fa[i] = a.qfrc_applied[i * S + env];
       bad |= !(t_abs(q[i]) < T(1e10)) || !(t_abs(v[i]) < T(1e10));
     }
+    // commands of the hardware interface: issued first so that a zero-copy read over PCIe overlaps the position stage
+    const bool hwio = (a.flags & B2F_HWIO) && env < a.nenv;
+    float hwv[N], hwe[N];
+    if (hwio) {
+#pragma unroll
+      for (int i = 0; i < N; i++) { hwv[i] = a.hw_vel[(long long)i * a.nenv + env]; hwe[i] = a.hw_eff[(long long)i * a.nenv + env]; }
+    }
+    // MjHWInterface::read gathers (src/mujoco_sim/mj_hw_interface.cpp:62-70)
+    auto hw_out = [&](const T* qo, const T* vo, const T* fo) {
+      if (!hwio) return;
+#pragma unroll
+      for (int i = 0; i < N; i++) {
+        a.hw_pos[(long long)i * a.nenv + env] = (float)qo[i];
+        a.hw_velo[(long long)i * a.nenv + env] = (float)vo[i];
+        a.hw_effo[(long long)i * a.nenv + env] = (float)fo[i];
+      }
+    };
     if (bad) {  // mj_checkPos / mj_checkVel
 #pragma unroll
       for (int i = 0; i < N; i++) {
@@ -230,16 +247,23 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_chain(const KArgs<T> a) {
     // ---- mjcb_control -> MjSim::controller (src/mujoco_sim/mj_sim.cpp:1055-1077) ----
     bool overridden = false;
     if (a.flags & B2F_CONTROLLER) {
-      T ddq[N], tau[N];
+      T ddq[N], dqc[N], tau[N];
 #pragma unroll
-      for (int i = 0; i < N; i++) ddq[i] = a.ddq[i * S + env];
+      for (int i = 0; i < N; i++) { ddq[i] = a.ddq[i * S + env]; dqc[i] = a.dq[i * S + env]; }
+      if (hwio) {  // MjHWInterface::write (src/mujoco_sim/mj_hw_interface.cpp:73-91), hardware joint i == dof i
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+          if (!m.i(h.o_dof_controlled, i)) continue;
+          if (fabsf(hwv[i]) > 1e-15f) dqc[i] = (T)hwv[i]; else ddq[i] = (T)hwe[i];
+        }
+      }
       mul_M(tau, ddq);
 #pragma unroll
       for (int i = 0; i < N; i++) {
         if (m.i(h.o_dof_controlled, i)) tau[i] += bias[i];
         fa[i] = tau[i];
         a.qfrc_applied[i * S + env] = tau[i];
-        const T dv = a.dq[i * S + env];
+        const T dv = dqc[i];
         if (t_abs(dv) > Eps<T>::minval()) { v[i] = dv; overridden = true; }
         a.ddq[i * S + env] = 0;
         a.dq[i * S + env] = 0;
@@ -249,6 +273,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_chain(const KArgs<T> a) {
 #pragma unroll
     for (int i = 0; i < N; i++) a.qfrc_bias[i * S + env] = bias[i];
     T finv[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) finv[i] = 0;
     if (a.flags & B2F_INVERSE) {
       // RNE(q, v, a) + armature a = M a + bias  (see k_smooth.cuh)
       mul_M(finv, qa);
@@ -414,6 +440,12 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_chain(const KArgs<T> a) {
       }
       a.time[env] = 0;
       a.status[env] |= 4;
+      if (hwio) {
+        T q0[N], z[N];
+#pragma unroll
+        for (int i = 0; i < N; i++) { q0[i] = m.f(h.o_qpos0, i); z[i] = 0; }
+        hw_out(q0, z, finv);
+      }
       continue;
     }
 #pragma unroll
@@ -444,6 +476,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_chain(const KArgs<T> a) {
 #pragma unroll
       for (int i = 0; i < N; i++) a.qvel[i * S + env] = v[i];
     }
+    hw_out(q, v, finv);
   }
 }
 
