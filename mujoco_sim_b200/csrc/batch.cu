@@ -175,6 +175,7 @@ int upload_model(b2_batch* b) {
 
 int alloc_field(b2_batch* b, const char* name, long long count, int kind, void** out) {
   drop_graphs(b);
+  b->args_valid = false;
   const size_t esz = kind == 1 ? 4 : (size_t)b->prec;
   const size_t bytes = std::max<size_t>(16, (size_t)count * b->nenvp * esz);
   void* p = nullptr;
@@ -190,11 +191,12 @@ int alloc_field(b2_batch* b, const char* name, long long count, int kind, void**
 }
 
 template <typename T>
-KArgs<T> make_args(b2_batch* b, int flags) {
+KArgs<T> build_args(b2_batch* b) {
   KArgs<T> a;
   std::memset(&a, 0, sizeof(a));
   a.model = b->blob_dev;
-  a.nenv = b->nenv; a.nenvp = b->nenvp; a.flags = flags; a.ws_block = b->smooth_block; a.h = (T)b->h;
+  a.model_words = b->hdr.nwords;
+  a.nenv = b->nenv; a.nenvp = b->nenvp;
   auto R = [&](const char* n) { auto it = b->fields.find(n); return it == b->fields.end() ? (T*)nullptr : (T*)it->second.ptr; };
   auto I = [&](const char* n) { auto it = b->fields.find(n); return it == b->fields.end() ? (int*)nullptr : (int*)it->second.ptr; };
   a.qpos = R("qpos"); a.qvel = R("qvel"); a.qacc = R("qacc"); a.qacc_warmstart = R("qacc_warmstart");
@@ -211,6 +213,20 @@ KArgs<T> make_args(b2_batch* b, int flags) {
   a.efc_KBI = R("efc_KBI"); a.efc_vel = R("efc_vel"); a.efc_aref = R("efc_aref"); a.efc_b = R("efc_b"); a.efc_force = R("efc_force");
   a.efc_ARdiag = R("efc_ARdiag"); a.efc_rows = R("efc_rows"); a.efc_meta = R("efc_meta"); a.wp = b->wp; a.solver_iter = I("solver_iter"); a.status = I("status");
   a.pending = I("_pending");
+  return a;
+}
+// the field pointers are looked up by name once per (re)allocation, not once per tick
+template <typename T>
+KArgs<T> make_args(b2_batch* b, int flags) {
+  if (!b->args_valid) {
+    b->args_f = build_args<float>(b);
+    b->args_d = build_args<double>(b);
+    b->args_valid = true;
+  }
+  KArgs<T> a;
+  if constexpr (sizeof(T) == 4) a = b->args_f; else a = b->args_d;
+  a.model = b->blob_dev; a.model_words = b->hdr.nwords;
+  a.flags = flags; a.ws_block = b->smooth_block; a.h = (T)b->h; a.wp = b->wp;
   a.hw_vel = b->io_in[0]; a.hw_eff = b->io_in[1];
   a.hw_pos = b->io_out[0]; a.hw_velo = b->io_out[1]; a.hw_effo = b->io_out[2];
   return a;
@@ -267,7 +283,8 @@ int run_tick(b2_batch* b, int flags) {
   if (single) {
     // limit-only serial chain: one kernel does the whole tick (k_chain.cuh)
     prof_mark(b, SLOT_SMOOTH);
-    if constexpr (sizeof(T) == 4) rc = launch_chain1_f32(b, a, grid); else rc = launch_chain1_f64(b, a, grid);
+    if (b->chain_team) { if constexpr (sizeof(T) == 4) rc = launch_chain_team_f32(b, a); else rc = launch_chain_team_f64(b, a); }
+    else if constexpr (sizeof(T) == 4) rc = launch_chain1_f32(b, a, grid); else rc = launch_chain1_f64(b, a, grid);
     if (rc < 0) return rc;
     prof_mark(b, SLOT_HW_READ);
     if ((flags & B2_TICK_HW) && !hwio) { if (hw_read_async(b) < 0) return -1; }
@@ -607,6 +624,10 @@ b2_batch* b2_create(const mjModel* m, int nenv, int device, int precision) {
     // (profiles/r01_chain_variants.txt)
     b->chain_single = b->chain_n > 0 && (b->fusable || b->fused) && !b->export_stages && !getenv("B2_NO_CHAIN1");
     b->chain_variant = getenv("B2_CHAIN_VARIANT") ? atoi(getenv("B2_CHAIN_VARIANT")) : 1;
+    // below ~16 k environments one thread per environment leaves the SMs latency-bound on a single instruction stream:
+    // an 8-lane team per environment shortens the dependent chain (k_chain_team.cuh)
+    b->chain_team = b->chain_single && (n == 6 || (n == 7 && precision == 4) || n == 7) &&
+                    (getenv("B2_CHAIN_TEAM") ? atoi(getenv("B2_CHAIN_TEAM")) != 0 : b->nenvp <= 16384);
   }
 
   b->epl = 2;
@@ -743,7 +764,7 @@ void b2_destroy(b2_batch* b) {
 const char* b2_path_name(const b2_batch* b) {
   static thread_local char buf[64];
   if (!b) return "";
-  if (b->chain_single) std::snprintf(buf, sizeof(buf), "k_chain<%d>", b->chain_n);
+  if (b->chain_single) std::snprintf(buf, sizeof(buf), b->chain_team ? "k_chain_team<%d>" : "k_chain<%d>", b->chain_n);
   else if (b->chain_n > 0) std::snprintf(buf, sizeof(buf), "k_smooth<ChainP<%d>>%s", b->chain_n, b->fused ? "" : "+pipeline");
   else std::snprintf(buf, sizeof(buf), "k_smooth<GenericP>%s", b->fused ? "" : "+pipeline");
   return buf;
@@ -993,14 +1014,18 @@ static int tick_hw(b2_batch* b, const float* vel, const float* eff, float* pos, 
   const float* in[2] = {vel, eff};
   float* out[3] = {pos, velo, effo};
   float* stage_out[3] = {nullptr, nullptr, nullptr};
+  auto alias = [&](int slot, const void* host) -> float* {
+    if (b->alias_host[slot] != host) { b->alias_host[slot] = host; b->alias_dev[slot] = device_alias(b, host, n * 4); }
+    return b->alias_dev[slot];
+  };
   for (int k = 0; k < 2; k++) {
     if (!in[k]) continue;  // resident: the staging buffer of the last upload is re-issued
-    if (const float* d = device_alias(b, in[k], n * 4)) b->io_in[k] = d;
+    if (const float* d = alias(k, in[k])) b->io_in[k] = d;
     else CK(cudaMemcpyAsync(b->hw_buf + k * n, in[k], n * 4, cudaMemcpyHostToDevice, b->stream));
   }
   for (int k = 0; k < 3; k++) {
     if (!out[k]) continue;
-    if (float* d = device_alias(b, out[k], n * 4)) b->io_out[k] = d;
+    if (float* d = alias(2 + k, out[k])) b->io_out[k] = d;
     else stage_out[k] = b->hw_buf + (2 + k) * n;
   }
   if (tick_dispatch(b, flags) < 0) return -1;

@@ -35,6 +35,7 @@ struct b2_batch {
   bool fused = false, ws_global = false, export_stages = false;
   int chain_n = 0;       // > 0: the model is a serial chain of chain_n scalar joints (ChainP<chain_n> kernels)
   int chain_variant = 0; // register budget variant of the chain kernel (B2_CHAIN_VARIANT)
+  bool chain_team = false;    // ... with an 8-lane team per environment (small batches: latency-bound otherwise)
   bool chain_single = false;  // limit-only chain: the whole tick runs in k_chain (unless xfrc_applied is in use)
   bool fusable = false;  // joint limits are the only constraint source
   bool use_graph = true;  // replay the tick's kernel sequence as a CUDA graph (B2_NO_GRAPH=1 disables)
@@ -60,6 +61,13 @@ struct b2_batch {
   const float* io_in[2] = {nullptr, nullptr};
   float* io_out[3] = {nullptr, nullptr, nullptr};
   std::map<const void*, size_t> registered;  // host ranges this batch pinned with cudaHostRegister
+  // device aliases of the caller buffers seen by the last b2_tick_host (the control loop passes the same ones every tick)
+  const void* alias_host[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  float* alias_dev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  // kernel argument block, rebuilt only after a field (re)allocation
+  b2::KArgs<float> args_f{};
+  b2::KArgs<double> args_d{};
+  bool args_valid = false;
   // per-kernel CUDA-event profiling (b2_profile_begin / b2_profile_end)
   std::vector<cudaEvent_t> prof_ev;  // [max_ticks][B2_NSLOT + 1]
   std::vector<unsigned> prof_mask;   // which boundary events of each tick were recorded
@@ -76,4 +84,7 @@ bool have_chain_kernel(int n, int precision);
 // the whole tick of a limit-only serial chain in one kernel (k_chain.cuh, chain1_f32.cu / chain1_f64.cu)
 int launch_chain1_f32(b2_batch* b, const KArgs<float>& a, int grid);
 int launch_chain1_f64(b2_batch* b, const KArgs<double>& a, int grid);
+// the same tick with an 8-lane team per environment (k_chain_team.cuh): small batches
+int launch_chain_team_f32(b2_batch* b, const KArgs<float>& a);
+int launch_chain_team_f64(b2_batch* b, const KArgs<double>& a);
 }  // namespace b2

@@ -32,6 +32,7 @@ enum ConIField : int { CI_GEOM1 = 0, CI_GEOM2 = 1, CI_DIM = 2, CI_PAIR = 3, CI_E
 template <typename T>
 struct KArgs {
   const uint32_t* model;  // packed DModel blob in HBM
+  int model_words;        // its size in 32-bit words (so that the TMA staging copy needs no dependent header load)
   int nenv, nenvp;        // environments, padded to a multiple of the CTA size
   int flags;
   int ws_block;           // CTA size the shared workspace was sized for

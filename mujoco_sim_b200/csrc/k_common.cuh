@@ -37,21 +37,24 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 
 // One elected thread issues a single TMA bulk copy (cp.async.bulk, SASS: UBLKCP) of the model blob HBM -> shared
 // memory and every thread of the CTA waits on the mbarrier transaction count.
-__device__ __forceinline__ void stage_model(uint32_t* dst, const uint32_t* src, int nwords, uint64_t* bar) {
+// Split form: stage_model_issue starts the copy, stage_model_wait blocks until it has landed, so that a kernel can put
+// its first global loads in flight in between.
+__device__ __forceinline__ void stage_model_issue(uint32_t* dst, const uint32_t* src, int nwords, uint64_t* bar) {
   const uint32_t bytes = (uint32_t)nwords * 4u;
   const uint32_t bar_a = smem_u32(bar);
   if (threadIdx.x == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes) : "memory");
     // bulk copies are limited in size per instruction only by the smem capacity; the blob is < 64 KB
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
                  "l"(src), "r"(bytes), "r"(bar_a)
                  : "memory");
   }
+}
+__device__ __forceinline__ void stage_model_wait(uint64_t* bar) {
+  const uint32_t bar_a = smem_u32(bar);
+  __syncthreads();   // the barrier initialisation by thread 0 is visible to every waiter
   uint32_t done = 0;
   while (!done) {
     asm volatile(
@@ -60,6 +63,10 @@ __device__ __forceinline__ void stage_model(uint32_t* dst, const uint32_t* src, 
         : "r"(bar_a)
         : "memory");
   }
+}
+__device__ __forceinline__ void stage_model(uint32_t* dst, const uint32_t* src, int nwords, uint64_t* bar) {
+  stage_model_issue(dst, src, nwords, bar);
+  stage_model_wait(bar);
 }
 
 // ---------- small math (registers) ----------

@@ -446,3 +446,46 @@ def test_hw_exchange_fused_zero_copy_equals_staged_kernels(b2):
     for x, y, z in zip(r_p, r_g, r_s):
         assert np.array_equal(x, z) and np.array_equal(y, z)
     assert np.abs(r_p[0]).max() > 0 and np.all(np.isfinite(r_p[2]))
+
+
+@pytest.mark.parametrize("prec", ["f32", "f64"])
+def test_chain_team_kernel_matches_thread_per_env_kernel(b2, prec):
+    """k_chain_team (8-lane team per environment, shuffle scans) against k_chain (one thread per environment) on the same
+    states, free motion and joints driven into their limits: identical limit-row sets and iteration counts, states equal
+    to rounding (sums along the chain are associated pairwise in the team kernel)."""
+    import os
+    m = b2.Model(b2.asset("panda7.xml"))
+    nenv = 200
+    qpos, qvel, frc = random_state(m, nenv, 4242)
+    hi = m.jnt_range.reshape(-1, 2)[:, 1]
+    qpos[::2] = hi - 0.02          # half of the environments run into the upper limits
+    qvel[::2] = 1.5
+    P = b2.engine.F32 if prec == "f32" else b2.engine.F64
+    out = {}
+    for team in ("0", "1"):
+        os.environ["B2_CHAIN_TEAM"] = team
+        try:
+            bt = b2.Batch(m, nenv, precision=P)
+        finally:
+            os.environ.pop("B2_CHAIN_TEAM", None)
+        assert bt.path_name == ("k_chain_team<7>" if team == "1" else "k_chain<7>")
+        bt.set("qpos", qpos); bt.set("qvel", qvel); bt.set("qfrc_applied", frc)
+        bt.set_tick_flags(b2.engine.TICK_INVERSE)
+        hist = []
+        for _ in range(60):
+            bt.step(1)
+            hist.append((bt.get("nefc").copy(), bt.get("solver_iter").copy()))
+        out[team] = (bt.get("qpos", dtype=np.float64), bt.get("qvel", dtype=np.float64), bt.get("qacc", dtype=np.float64),
+                     bt.get("qfrc_inverse", dtype=np.float64), bt.get("qfrc_bias", dtype=np.float64), bt.get("xpos", dtype=np.float64),
+                     bt.get("xquat", dtype=np.float64), hist)
+        bt.close()
+    a, b = out["0"], out["1"]
+    assert max(h[0].max() for h in a[7]) >= 1                      # limits really were active
+    rtol = 1e-3 if prec == "f32" else 1e-9    # 60 ticks in and out of joint limits amplify fp32 rounding
+    same_rows = sum(int(np.array_equal(x[0], y[0])) for x, y in zip(a[7], b[7]))
+    assert same_rows >= (60 if prec == "f64" else 57), same_rows     # an fp32 ulp may move a limit activation by a tick
+    if prec == "f64":
+        assert all(np.array_equal(x[1], y[1]) for x, y in zip(a[7], b[7]))
+    for k in range(7):
+        scale = max(1.0, float(np.abs(a[k]).max()))
+        assert np.abs(a[k] - b[k]).max() <= rtol * scale * (50 if k in (2, 3) and prec == "f32" else 1), (k, np.abs(a[k] - b[k]).max(), scale)
