@@ -38,6 +38,9 @@ int fail(const std::string& msg) { return b2::set_error(msg); }
   } while (0)
 }  // namespace
 
+#ifndef PGS_MINB
+#define PGS_MINB 16
+#endif
 enum { SLOT_HW_WRITE = 0, SLOT_SMOOTH, SLOT_COLLIDE, SLOT_MAKE, SLOT_PROJECT, SLOT_PGS, SLOT_INTEGRATE, SLOT_HW_READ, B2_NSLOT };
 // record the boundary event that precedes kernel slot `slot` of the tick being profiled
 static inline void prof_mark(b2_batch* b, int slot) {
@@ -211,7 +214,7 @@ KArgs<T> build_args(b2_batch* b) {
   a.efc_id = I("efc_id"); a.efc_tree = I("efc_tree"); a.efc_J = R("efc_J"); a.efc_pos = R("efc_pos"); a.efc_margin = R("efc_margin");
   a.efc_frictionloss = R("efc_frictionloss"); a.efc_diagApprox = R("efc_diagApprox"); a.efc_R = R("efc_R"); a.efc_D = R("efc_D");
   a.efc_KBI = R("efc_KBI"); a.efc_vel = R("efc_vel"); a.efc_aref = R("efc_aref"); a.efc_b = R("efc_b"); a.efc_force = R("efc_force");
-  a.efc_ARdiag = R("efc_ARdiag"); a.efc_rows = R("efc_rows"); a.efc_meta = R("efc_meta"); a.wp = b->wp; a.solver_iter = I("solver_iter"); a.status = I("status");
+  a.efc_ARdiag = R("efc_ARdiag"); a.efc_blocks = R("efc_blocks"); a.efc_nwords = I("efc_nwords"); a.env_order = I("env_order"); a.solver_iter = I("solver_iter"); a.status = I("status");
   a.pending = I("_pending");
   return a;
 }
@@ -227,9 +230,46 @@ KArgs<T> make_args(b2_batch* b, int flags) {
   if constexpr (sizeof(T) == 4) a = b->args_f; else a = b->args_d;
   a.model = b->blob_dev; a.model_words = b->hdr.nwords;
   a.flags = flags; a.ws_block = b->smooth_block; a.h = (T)b->h; a.wp = b->wp;
+  a.block_capw = b->block_capw; a.stage_cap = b->stage_cap;
   a.hw_vel = b->io_in[0]; a.hw_eff = b->io_in[1];
   a.hw_pos = b->io_out[0]; a.hw_velo = b->io_out[1]; a.hw_effo = b->io_out[2];
   return a;
+}
+
+// shared-memory budgets of the constraint-pipeline kernels (they stage the same model blob; row assembly and the solver
+// add their own vectors); redone whenever the blob changes size
+int configure_constraint_kernels(b2_batch* b) {
+  if (b->fused) return 0;
+    // the constraint-pipeline kernels stage the same blob; row assembly and the solver add their shared vectors
+    const int need1 = (int)b->blob_smem;
+    // row assembly: one record column per thread; 128-thread CTAs when that fits, else 32
+    b->make_block = b->blob_smem + (size_t)b->rec_max * 129 * b->prec <= 200 * 1024 ? 128 : 32;
+    const int need2 = (int)(b->blob_smem + (size_t)b->rec_max * (b->make_block + 1) * b->prec);
+    // solver: per environment 2 (b->hdr.nv + 4) + njmax words of vectors plus the staged records; sized for ~4 CTAs per SM
+    const int epb = 128 / b->pgs_lanes;
+    const long long fixed = (long long)b->blob_smem + ((long long)2 * (b->hdr.nv + 4) + b->hdr.njmax) * epb * b->prec;
+    // staging an environment's records in shared memory lost to plain L1-cached streaming once the records became compact
+    // (profiles/r01_pgs_variants.txt): off unless asked for
+    long long cap = getenv("B2_PGS_STAGE") ? atoi(getenv("B2_PGS_STAGE")) : 0;
+    cap = std::max(0LL, std::min<long long>(cap, b->block_capw)) & ~3LL;
+    if (fixed + cap * epb * b->prec > 227 * 1024) cap = 0;
+    b->stage_cap = (int)cap;
+    const int need3 = (int)(fixed + cap * epb * b->prec);
+    if (need2 > 227 * 1024 || need3 > 227 * 1024) return fail("model too large for the constraint kernels' shared memory");
+    b->pgs_ctas_per_sm = std::max(1, std::min(16, (int)(227 * 1024 / std::max(1, need3 + 1024))));
+    bool ok = true;
+    auto SA = [&](const void* fn, int need) { ok &= cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(need, 48 * 1024)) == cudaSuccess; };
+    if (b->prec == 8) {
+      SA((const void*)k_collide<double, 128>, need1); SA((const void*)k_integrate<double, 128>, need1);
+      SA((const void*)k_make_constraint<double, 128>, need2); SA((const void*)k_make_constraint<double, 32>, need2);
+      SA((const void*)k_pgs_block<double, 4, 32, PGS_MINB>, need3); SA((const void*)k_pgs_block<double, 8, 32, PGS_MINB>, need3);
+    } else {
+      SA((const void*)k_collide<float, 128>, need1); SA((const void*)k_integrate<float, 128>, need1);
+      SA((const void*)k_make_constraint<float, 128>, need2); SA((const void*)k_make_constraint<float, 32>, need2);
+      SA((const void*)k_pgs_block<float, 4, 32, PGS_MINB>, need3); SA((const void*)k_pgs_block<float, 8, 32, PGS_MINB>, need3);
+    }
+    if (!ok) return fail("cudaFuncSetAttribute failed");
+  return 0;
 }
 
 template <typename T, int BLOCK, typename P>
@@ -308,19 +348,21 @@ int run_tick(b2_batch* b, int flags) {
     prof_mark(b, SLOT_COLLIDE);
     if (b->m->npair > 0) { k_collide<T, BL><<<g2, BL, sm, b->stream>>>(a); b->launches++; }
     prof_mark(b, SLOT_MAKE);
-    k_make_constraint<T, BL><<<g2, BL, sm + (size_t)(2 * b->wp + 8) * (BL + 1) * sizeof(T), b->stream>>>(a);
+    if (b->make_block == 128) k_make_constraint<T, 128><<<g2, 128, sm + (size_t)b->rec_max * 129 * sizeof(T), b->stream>>>(a);
+    else k_make_constraint<T, 32><<<std::max(1, std::min(b->nenvp / 32, b->nsm * 8)), 32, sm + (size_t)b->rec_max * 33 * sizeof(T), b->stream>>>(a);
     b->launches += 1;
     if (!(flags & B2_TICK_NOSOLVE)) {
       prof_mark(b, SLOT_PGS);
-      const size_t smp = sm + ((size_t)2 * (b->hdr.nv + 4) + b->hdr.njmax) * (BL / 8) * sizeof(T);
-      const int ngroups = b->nenvp / (BL / 8);
-      const int g3 = std::max(1, std::min(ngroups, b->nsm * 8));
-      switch (b->epl) {
-        case 2: k_pgs_team<T, 2, BL><<<g3, BL, smp, b->stream>>>(a); break;
-        case 4: k_pgs_team<T, 4, BL><<<g3, BL, smp, b->stream>>>(a); break;
-        case 8: k_pgs_team<T, 8, BL><<<g3, BL, smp, b->stream>>>(a); break;
-        default: k_pgs_team<T, 16, BL><<<g3, BL, smp, b->stream>>>(a); break;
-      }
+      k_order_envs<256, 1024><<<1, 1024, 0, b->stream>>>(a.nefc, a.efc_nwords, a.env_order, b->nenvp, std::max(4, b->block_capw / 256), a.pending, b->fusable ? 1 : 0);
+      b->launches += 1;
+      // one warp per CTA and one CTA per group of environments: the hardware scheduler balances the very uneven
+      // per-environment work (contact counts) dynamically
+      constexpr int PB = 32;
+      const int epb = PB / b->pgs_lanes;
+      const size_t smp = ((size_t)2 * (b->hdr.nv + 4) + b->hdr.njmax + b->stage_cap) * epb * sizeof(T);
+      const int g3 = b->nenvp / epb;
+      if (b->pgs_lanes == 4) k_pgs_block<T, 4, PB, PGS_MINB><<<g3, PB, smp, b->stream>>>(a);
+      else k_pgs_block<T, 8, PB, PGS_MINB><<<g3, PB, smp, b->stream>>>(a);
       prof_mark(b, SLOT_INTEGRATE);
       k_integrate<T, BL><<<g2, BL, sm, b->stream>>>(a);
       b->launches += 2;
@@ -630,10 +672,17 @@ b2_batch* b2_create(const mjModel* m, int nenv, int device, int precision) {
                     (getenv("B2_CHAIN_TEAM") ? atoi(getenv("B2_CHAIN_TEAM")) != 0 : b->nenvp <= 16384);
   }
 
-  b->epl = 2;
-  while (8 * b->epl < b->hdr.wmax) b->epl *= 2;
-  if (b->epl > 16) return bail("model too wide for the solver team (more than 128 dofs in two trees)");
-  b->wp = 8 * b->epl;
+  b->epl = 2; b->wp = 16;  // (legacy fields of the row-slab solver; unused)
+  {
+    // block records (k_constraint.cuh): slab capacity per environment and the largest single record
+    int nbmax = 1;
+    for (int g = 0; g < m->ngeom; g++) nbmax = std::max(nbmax, m->geom_condim[g]);
+    nbmax = std::min(nbmax, 6);
+    b->block_capw = block_capacity(b->hdr.njmax, b->hdr.wmax);
+    b->rec_max = block_max_words(nbmax, b->hdr.wmax);
+    b->pgs_lanes = getenv("B2_PGS_LANES") ? atoi(getenv("B2_PGS_LANES")) : 8;
+    if (b->pgs_lanes != 4) b->pgs_lanes = 8;
+  }
   struct Spec { const char* name; long long count; int kind; };
   std::vector<Spec> specs = {
       {"qpos", nq, 0}, {"qvel", nv, 0}, {"qacc", nv, 0}, {"qacc_warmstart", nv, 0}, {"qfrc_applied", nv, 0},
@@ -654,7 +703,7 @@ b2_batch* b2_create(const mjModel* m, int nenv, int device, int precision) {
         {"efc_type", njmax, 1}, {"efc_id", njmax, 1}, {"efc_tree", 2 * njmax, 1}, {"efc_J", njmax * b->hdr.wmax, 0}, {"efc_pos", njmax, 0}, {"efc_margin", njmax, 0},
         {"efc_frictionloss", njmax, 0}, {"efc_diagApprox", njmax, 0}, {"efc_R", njmax, 0}, {"efc_D", njmax, 0}, {"efc_KBI", 3 * njmax, 0},
         {"efc_vel", njmax, 0}, {"efc_aref", njmax, 0}, {"efc_b", njmax, 0}, {"efc_force", njmax, 0}, {"efc_ARdiag", njmax, 0},
-        {"efc_rows", njmax * 2 * b->wp, 0}, {"efc_meta", njmax * 8, 0}};
+        {"efc_blocks", b->block_capw, 0}, {"efc_nwords", 1, 1}, {"env_order", 1, 1}};
     specs.insert(specs.end(), more.begin(), more.end());
   }
   for (auto& s : specs)
@@ -688,25 +737,7 @@ b2_batch* b2_create(const mjModel* m, int nenv, int device, int precision) {
     b->ws_global = true;
     if (alloc_field(b, "_ws", b->hdr.ws_slots, 0, nullptr) < 0) return bail("alloc failed");
   }
-  {
-    // the constraint-pipeline kernels stage the same blob; row assembly and the solver add their shared vectors
-    const int need1 = (int)b->blob_smem;
-    const int need2 = (int)(b->blob_smem + (size_t)(2 * b->wp + 8) * 129 * precision);
-    const int need3 = (int)(b->blob_smem + ((size_t)2 * (nv + 4) + b->hdr.njmax) * 16 * precision);
-    if (need2 > 227 * 1024 || need3 > 227 * 1024) return bail("model too large for the constraint kernels' shared memory");
-    bool ok = true;
-    auto SA = [&](const void* fn, int need) { ok &= cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(need, 48 * 1024)) == cudaSuccess; };
-    if (precision == 8) {
-      SA((const void*)k_collide<double, 128>, need1); SA((const void*)k_make_constraint<double, 128>, need2); SA((const void*)k_integrate<double, 128>, need1);
-      SA((const void*)k_pgs_team<double, 2, 128>, need3); SA((const void*)k_pgs_team<double, 4, 128>, need3);
-      SA((const void*)k_pgs_team<double, 8, 128>, need3); SA((const void*)k_pgs_team<double, 16, 128>, need3);
-    } else {
-      SA((const void*)k_collide<float, 128>, need1); SA((const void*)k_make_constraint<float, 128>, need2); SA((const void*)k_integrate<float, 128>, need1);
-      SA((const void*)k_pgs_team<float, 2, 128>, need3); SA((const void*)k_pgs_team<float, 4, 128>, need3);
-      SA((const void*)k_pgs_team<float, 8, 128>, need3); SA((const void*)k_pgs_team<float, 16, 128>, need3);
-    }
-    if (!ok) return bail("cudaFuncSetAttribute failed");
-  }
+  if (configure_constraint_kernels(b) < 0) return bail("constraint kernel configuration failed");
   if (b2_reset(b, 0, nenv) < 0) return bail("reset failed");
   // padded environments also start from qpos0 so that they stay finite
   if (b->nenvp > nenv) {
@@ -804,6 +835,7 @@ int b2_set_odom(b2_batch* b, int nrobot, const int* dof, const int* qposadr) {
   b->blob_smem = 16 + (size_t)b->hdr.nwords * 4;
   if (!b->ws_global) b->smooth_smem = b->blob_smem + (size_t)b->hdr.ws_slots * b->smooth_block * b->prec;
   else b->smooth_smem = b->blob_smem;
+  if (configure_constraint_kernels(b) < 0) return -1;
   return 0;
 }
 

@@ -41,7 +41,14 @@ struct b2_batch {
   bool use_graph = true;  // replay the tick's kernel sequence as a CUDA graph (B2_NO_GRAPH=1 disables)
   struct GraphEntry { cudaGraphExec_t exec = nullptr; int kernels = 0; };
   std::map<std::pair<unsigned long long, unsigned long long>, GraphEntry> graphs;  // keyed by (tick flags, timestep; exchange buffers)
-  int wp = 16, epl = 2;  // solver team: 8 lanes x epl elements cover the compact row width
+  int wp = 16, epl = 2;  // (legacy)
+  // block records of the constraint pipeline (k_constraint.cuh)
+  int block_capw = 0;    // words of efc_blocks per environment
+  int rec_max = 0;       // largest single record (words): sizes the assembly kernel's shared-memory columns
+  int make_block = 128;  // CTA size of k_make_constraint
+  int pgs_lanes = 8;     // lanes per environment in k_pgs_block
+  int stage_cap = 0;     // words of records per environment staged in shared memory by the solver
+  int pgs_ctas_per_sm = 4;
   int smooth_block = 32;
   size_t smooth_smem = 0, blob_smem = 0;
   void* flush_buf = nullptr;

@@ -56,13 +56,16 @@ struct KArgs {
   int* efc_type;          // [njmax][nenvp]
   int* efc_id;            // [njmax][nenvp]
   int* efc_tree;          // [njmax][2][nenvp] kinematic trees of the row (-1: none)
-  T *efc_J;               // [njmax][wmax][nenvp] compact rows (k_constraint.cuh)
+  T *efc_J;               // [njmax][wmax][nenvp] compact rows (k_constraint.cuh); a contact's first condim rows hold its base directions
   T *efc_pos, *efc_margin, *efc_frictionloss, *efc_diagApprox, *efc_R, *efc_D, *efc_KBI, *efc_vel, *efc_aref,
       *efc_b, *efc_force; // [njmax][nenvp] (KBI: [3][njmax][nenvp])
   T* efc_ARdiag;          // [njmax][nenvp] diagonal of J M^-1 J^T + R
-  T* efc_rows;            // [nenvp][njmax][2 wp] environment-major solver slab: J compact | M^-1 J^T compact
-  T* efc_meta;            // [nenvp][njmax][8]   {R, aref, diag(AR), frictionloss, type, tree1, tree2, b}
-  int wp;                 // padded compact row width: 8 * EPL of the solver team
+  T* efc_blocks;          // [nenvp][block_capw] environment-major block records streamed by the solver (k_constraint.cuh)
+  int* efc_nwords;        // [nenvp] words of efc_blocks in use
+  int* env_order;         // [nenvp] visit order of the solver (k_order_envs)
+  int block_capw;         // words of efc_blocks per environment
+  int stage_cap;          // words of an environment's records the solver keeps in shared memory
+  int wp;                 // (unused) padded compact row width
   int* solver_iter;       // [nenvp]
   int* status;            // [nenvp] bit 0: contact cap hit, bit 1: row cap hit, bit 2: state reset (bad value),
                           //         bit 3: integrated by the smooth kernel this tick (B2F_FUSABLE)

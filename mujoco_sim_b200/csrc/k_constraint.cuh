@@ -12,6 +12,7 @@
 // constraint model; the reference reaches them only through mj_step1 / mj_step2 / mj_inverse
 // (src/mj_main.cpp:83,108; src/mujoco_sim/mj_hw_interface.cpp:61).
 #pragma once
+#include <type_traits>
 #include "k_args.h"
 #include "k_common.cuh"
 #include "k_smooth.cuh"
@@ -252,13 +253,12 @@ struct Rows {
           mat_vec3(fp, frame, jp);  // rows of frame: normal, tangent1, tangent2
           mat_vec3(fr, frame, jr);
           const int kk = seg_pos(g, i);
-          if (dim == 1) { Jc(first, kk) += sg * fp[0]; continue; }
-          for (int k = 1; k < dim; k++) {
-            const T dir = k < 3 ? fp[k] : fr[k - 3];
-            const T mu = fri[k - 1];
-            Jc(first + 2 * k - 2, kk) += sg * (fp[0] + mu * dir);
-            Jc(first + 2 * k - 1, kk) += sg * (fp[0] - mu * dir);
-          }
+          // rows first .. first + dim - 1 hold the BASE directions of the contact: normal, tangent 1, tangent 2, torsion,
+          // rolling 1, rolling 2 (unscaled); pyramid row 2 (k - 1) + s is base 0 +/- friction[k - 1] * base k and is never
+          // materialised on the hot path (k_make_constraint works on the dim base rows, the legacy efc_J view is expanded
+          // on demand)
+          Jc(first, kk) += sg * fp[0];
+          for (int k = 1; k < dim; k++) Jc(first + k, kk) += sg * (k < 3 ? fp[k] : fr[k - 3]);
         }
       }
     }
@@ -366,23 +366,69 @@ __device__ __forceinline__ T primal_force(int type, T jar, T D, T R, T fl) {
   const int ntiles = a.nenvp / BLOCK;                                                \
   (void)S; (void)h;
 
-// Row slab for the solver, environment-major: row r of environment e is 2 * wp contiguous numbers
-// [J compact (wp) | B = M^-1 J^T compact (wp)] at efc_rows[(e * njmax + r) * 2 wp], plus an 8-number record
-// {R, aref, diag(AR), frictionloss, type, tree1, tree2, b} at efc_meta[(e * njmax + r) * 8].  One 8-lane team of the
-// solver streams these rows with 8/16-byte vector loads; for wp = 16 (C3) a row is exactly one 128-byte line.
-enum { META_R = 0, META_AREF, META_DIAG, META_FL, META_TYPE, META_T1, META_T2, META_B, META_N };
+template <typename T, int N> struct alignas(sizeof(T) * N) VecN { T v[N]; };
 
-// K4 + K5 fused: rows, impedance, then per row: vel, aref, b = J qacc_smooth - aref, B_r = M^-1 J_r^T by sparse
-// back-substitution inside the row's tree blocks (in shared memory), diag(AR)_r = J_r B_r + R_r, and (for mj_inverse)
-// qfrc_inverse -= J^T f(qacc_prev).  Finished rows leave through a shared-memory transpose so that every global store
-// of the slab is a full coalesced line.
+// ---- block records: what the solver streams -----------------------------------------------------------------------
+// A BLOCK is one scalar row (equality, friction loss, limit, frictionless contact: nb = 1) or one pyramidal contact
+// (nb = condim base directions, nrow = 2 (nb - 1) solver rows J_0 +/- mu_k J_k).  Environment e owns the word range
+// efc_blocks[e * capw, e * capw + efc_nwords[e]) (environment-major: a team streams its own environment), block after
+// block in row order:
+//   [0] code = type + 16 nb + 256 nrow   [1] s1   [2] n1 + 1024 w   [3] s2   [4] R   [5] frictionloss   [6] len   [7] row0
+//   aref[nrow]  Arr[nrow]  1/Arr[nrow]  b[nrow]            (Arr = J_r M^-1 J_r^T + R, b = J_r qacc_smooth - aref_r)
+//   mu[nb - 1]  ARu[nrow (nrow - 1) / 2]                   (nb > 1: J_r M^-1 J_s^T for the pyramid rows r < s of the contact,
+//                                                           packed by rows: what relaxing row r does to the later rows)
+//   (pad to a multiple of 4)  J[nb][wq]  B[nb][wq]         (compact over the block's trees, wq = w rounded up to 4)
+// Keeping the base directions instead of the pyramid rows makes a contact 2-3x smaller than its rows, needs nb instead
+// of 2 (nb - 1) products with M^-1, and lets the solver update a whole contact from nb dot products (k_pgs_block).
+enum { BH_CODE = 0, BH_S1, BH_N1W, BH_S2, BH_R, BH_FL, BH_LEN, BH_ROW0, BH_N };
+struct BlockShape {
+  int type, nb, nrow, s1, n1, s2, w, wq, oAref, oArr, oiA, ob, oMu, oA, oJ, oB, len;
+  __host__ __device__ void layout() {
+    wq = (w + 3) & ~3;
+    oAref = BH_N; oArr = oAref + nrow; oiA = oArr + nrow; ob = oiA + nrow; oMu = ob + nrow;
+    oA = oMu + (nb > 1 ? nb - 1 : 0);
+    oJ = (oA + (nb > 1 ? nrow * (nrow - 1) / 2 : 0) + 3) & ~3;
+    oB = oJ + nb * wq;
+    len = oB + nb * wq;
+  }
+  __host__ __device__ int dof(int e) const { return e < n1 ? s1 + e : s2 + e - n1; }
+  // position of (r, s), r < s, in the packed strict upper triangle
+  __host__ __device__ int aru(int r, int s) const { return oA + r * (2 * nrow - r - 1) / 2 + (s - r - 1); }
+};
+// integers ride in the records as bit patterns (fp32: no conversion on the solver's critical path) / exact values (fp64)
+__device__ __forceinline__ float enc_int(int v, float) { return __int_as_float(v); }
+__device__ __forceinline__ double enc_int(int v, double) { return (double)v; }
+__device__ __forceinline__ int dec_int(float v) { return __float_as_int(v); }
+__device__ __forceinline__ int dec_int(double v) { return (int)v; }
+template <typename T>
+__device__ __forceinline__ BlockShape block_shape(const T* rec) {
+  BlockShape s;
+  const int code = dec_int(rec[BH_CODE]), n1w = dec_int(rec[BH_N1W]);
+  s.type = code & 15; s.nb = (code >> 4) & 15; s.nrow = code >> 8;
+  s.s1 = dec_int(rec[BH_S1]); s.n1 = n1w & 1023; s.w = n1w >> 10; s.s2 = dec_int(rec[BH_S2]);
+  s.layout();
+  return s;
+}
+// words one environment can need: every row as a single-row block is the worst case
+__host__ __device__ inline int block_capacity(int njmax, int wmax) { return njmax * (BH_N + 4 + 2 * ((wmax + 3) & ~3)); }
+__host__ __device__ inline int block_max_words(int nbmax, int wmax) {
+  BlockShape s{};
+  s.nb = nbmax; s.nrow = nbmax > 1 ? 2 * (nbmax - 1) : 1; s.w = wmax;
+  s.layout();
+  return s.len;
+}
+
+// K4 + K5 fused: rows, impedance, then per BLOCK: vel, aref, b, B = M^-1 J^T of the base directions by sparse
+// back-substitution inside the block's trees (in shared memory), the local matrix A, diag(AR) per row, and (for
+// mj_inverse) qfrc_inverse -= J^T f(qacc_prev).  A finished record leaves through a shared-memory transpose so that
+// every global store of the slab is a coalesced run.
 template <typename T, int BLOCK>
 __global__ void __launch_bounds__(BLOCK) k_make_constraint(const KArgs<T> a) {
   B2_KERNEL_PROLOGUE
-  const int WP = a.wp;
-  constexpr int LDS = BLOCK + 1;  // +1: conflict-free both for per-thread columns and for the transposed row reads
-  T* rowsh = reinterpret_cast<T*>(smem_raw + 16 + (size_t)nwords * 4);  // [2 * WP + META_N][LDS]: J | B | meta
+  constexpr int LDS = BLOCK + 1;  // +1: conflict-free both for per-thread columns and for the transposed reads
+  T* recsh = reinterpret_cast<T*>(smem_raw + 16 + (size_t)nwords * 4);  // [recmax][LDS]: one record per thread (column)
   const int lane = threadIdx.x & 31, wbase = threadIdx.x & ~31;
+  const int capw = a.block_capw;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int env = tile * BLOCK + threadIdx.x;
     Rows<T> rows(m, a, env);
@@ -397,241 +443,434 @@ __global__ void __launch_bounds__(BLOCK) k_make_constraint(const KArgs<T> a) {
     const int ne = rows.nefc, W = h.wmax;
     if (!done) a.nefc[env] = ne;
     SArr<T> LD{a.qLD + env, S}, dinv{a.qLDiagInv + env, S};
-    SArr<T> Jr{rowsh + threadIdx.x, LDS}, Br{rowsh + (size_t)WP * LDS + threadIdx.x, LDS};
-    int nemax = ne;
-    for (int o = 16; o > 0; o >>= 1) nemax = max(nemax, __shfl_xor_sync(0xffffffffu, nemax, o));
-    for (int r = 0; r < nemax; r++) {
-      T R = 0, aref = 0, dg = 0, fl = 0, bb = 0;
-      int type = 0, t1 = -1, t2 = -1;
-      if (r < ne) {
+    SArr<T> rec{recsh + threadIdx.x, LDS};
+    int r = 0, woff = 0;
+    while (__any_sync(0xffffffffu, r < ne)) {
+      BlockShape bs{};
+      const bool have = r < ne;
+      if (have) {
         const long long o = (long long)r * S + env;
-        t1 = a.efc_tree[((long long)2 * r) * S + env]; t2 = a.efc_tree[((long long)2 * r + 1) * S + env];
-        const Seg g = seg_of(m, t1, t2);
-        const int w = g.n1 + g.n2;
-        T vel = 0, js = 0, jq = 0;
-        for (int k = 0; k < w; k++) {
-          const T j = a.efc_J[((long long)r * W + k) * S + env];
-          const long long d = (long long)seg_dof(g, k) * S + env;
-          vel += j * a.qvel[d];
-          js += j * a.qacc_smooth[d];
-          jq += j * a.qacc[d];
-          Jr[k] = j;
-          Br[k] = j;
+        bs.type = a.efc_type[o];
+        const int id = a.efc_id[o];
+        bs.nb = 1; bs.nrow = 1;
+        T fri[5] = {0, 0, 0, 0, 0};
+        if (bs.type == CN_CONTACT_PYRAMIDAL) {
+          bs.nb = a.coni[((long long)CI_DIM * h.nconmax + id) * S + env];
+          bs.nrow = 2 * (bs.nb - 1);
+          for (int k = 0; k < 5; k++) fri[k] = a.con[((long long)(CF_FRICTION + k) * h.nconmax + id) * S + env];
         }
-        for (int k = w; k < WP; k++) { Jr[k] = 0; Br[k] = 0; }
-        const T K = a.efc_KBI[((long long)0 * h.njmax + r) * S + env], Bd = a.efc_KBI[((long long)1 * h.njmax + r) * S + env];
-        const T imp = a.efc_KBI[((long long)2 * h.njmax + r) * S + env];
-        R = a.efc_R[o];
-        const T D = 1 / R;
-        aref = -Bd * vel - K * imp * (a.efc_pos[o] - a.efc_margin[o]);
-        type = a.efc_type[o];
-        fl = a.efc_frictionloss[o];
-        bb = js - aref;
-        a.efc_D[o] = D;
-        a.efc_vel[o] = vel;
-        a.efc_aref[o] = aref;
-        a.efc_b[o] = bb;
+        const Seg g = seg_of(m, a.efc_tree[((long long)2 * r) * S + env], a.efc_tree[((long long)2 * r + 1) * S + env]);
+        bs.s1 = g.s1; bs.n1 = g.n1; bs.s2 = g.s2; bs.w = g.n1 + g.n2;
+        bs.layout();
+        const int w = bs.w, wq = bs.wq, nb = bs.nb;
+        T vel[6], js[6], jq[6];
+        for (int k = 0; k < nb; k++) {
+          T v0 = 0, s0 = 0, q0 = 0;
+          for (int e = 0; e < w; e++) {
+            const T j = a.efc_J[((long long)(r + k) * W + e) * S + env];
+            const long long d = (long long)bs.dof(e) * S + env;
+            v0 += j * a.qvel[d]; s0 += j * a.qacc_smooth[d]; q0 += j * a.qacc[d];
+            rec[bs.oJ + k * wq + e] = j;
+            rec[bs.oB + k * wq + e] = j;
+          }
+          for (int e = w; e < wq; e++) { rec[bs.oJ + k * wq + e] = 0; rec[bs.oB + k * wq + e] = 0; }
+          vel[k] = v0; js[k] = s0; jq[k] = q0;
+          // B_k = M^-1 J_k^T, one tree at a time (M is block diagonal over trees)
+          for (int sgm = 0; sgm < 2; sgm++) {
+            const int lo = sgm ? g.s2 : g.s1, n = sgm ? g.n2 : g.n1, base = bs.oB + k * wq + (sgm ? g.n1 : 0);
+            if (n == 0) continue;
+            for (int i = lo + n - 1; i >= lo; i--) {
+              const T xi = rec[base + i - lo];
+              if (xi == 0) continue;
+              int adr = m.i(h.o_dof_Madr, i) + 1;
+              for (int j = m.i(h.o_dof_parentid, i); j >= 0; j = m.i(h.o_dof_parentid, j)) rec[base + j - lo] -= LD[adr++] * xi;
+            }
+            for (int i = lo; i < lo + n; i++) rec[base + i - lo] *= dinv[i];
+            for (int i = lo; i < lo + n; i++) {
+              int adr = m.i(h.o_dof_Madr, i) + 1;
+              T xi = rec[base + i - lo];
+              for (int j = m.i(h.o_dof_parentid, i); j >= 0; j = m.i(h.o_dof_parentid, j)) xi -= LD[adr++] * rec[base + j - lo];
+              rec[base + i - lo] = xi;
+            }
+          }
+        }
+        // local matrix A = J_base B_base^T (symmetric), then the couplings between the pyramid rows
+        T A[6][6];
+        for (int k = 0; k < nb; k++)
+          for (int c = k; c < nb; c++) {
+            T s0 = 0;
+            for (int e = 0; e < w; e++) s0 += rec[bs.oJ + k * wq + e] * rec[bs.oB + c * wq + e];
+            A[k][c] = s0; A[c][k] = s0;
+          }
+        T A0[6], Ad[6];   // A[0][k] and A[k][k]: all the pyramid rows' diagonals need
+        for (int k = 0; k < nb; k++) { A0[k] = A[0][k]; Ad[k] = A[k][k]; }
+        if (nb > 1)
+          for (int r1 = 0; r1 < bs.nrow; r1++)
+            for (int r2 = r1 + 1; r2 < bs.nrow; r2++) {
+              const int k1 = r1 / 2 + 1, k2 = r2 / 2 + 1;
+              const T m1 = (r1 & 1) ? -fri[k1 - 1] : fri[k1 - 1], m2 = (r2 & 1) ? -fri[k2 - 1] : fri[k2 - 1];
+              rec[bs.aru(r1, r2)] = A[0][0] + m2 * A[0][k2] + m1 * (A[k1][0] + m2 * A[k1][k2]);
+            }
+        for (int k = 1; k < nb; k++) rec[bs.oMu + k - 1] = fri[k - 1];
+        const T R = a.efc_R[o], D = 1 / R, fl = a.efc_frictionloss[o];
+        T dsum[6] = {0, 0, 0, 0, 0, 0};
+        for (int rr = 0; rr < bs.nrow; rr++) {
+          const long long orr = (long long)(r + rr) * S + env;
+          const int k = nb > 1 ? rr / 2 + 1 : 0;
+          const T sm = nb > 1 ? ((rr & 1) ? -fri[k - 1] : fri[k - 1]) : T(0);
+          const T velr = vel[0] + sm * vel[k], jsr = js[0] + sm * js[k], jqr = jq[0] + sm * jq[k];
+          const T K = a.efc_KBI[((long long)0 * h.njmax + r + rr) * S + env], Bd = a.efc_KBI[((long long)1 * h.njmax + r + rr) * S + env];
+          const T imp = a.efc_KBI[((long long)2 * h.njmax + r + rr) * S + env];
+          const T aref = -Bd * velr - K * imp * (a.efc_pos[orr] - a.efc_margin[orr]);
+          const T Arr = (nb > 1 ? A0[0] + 2 * sm * A0[k] + sm * sm * Ad[k] : A0[0]) + R;
+          const T bb = jsr - aref;
+          a.efc_D[orr] = D; a.efc_vel[orr] = velr; a.efc_aref[orr] = aref; a.efc_b[orr] = bb; a.efc_ARdiag[orr] = Arr;
+          rec[bs.oAref + rr] = aref; rec[bs.oArr + rr] = Arr; rec[bs.oiA + rr] = 1 / Arr; rec[bs.ob + rr] = bb;
+          if (a.flags & B2F_INVERSE) {
+            const T f = primal_force(bs.type, jqr - aref, D, R, fl);
+            dsum[0] += f;
+            if (nb > 1) dsum[k] += sm * f;
+          }
+        }
         if (a.flags & B2F_INVERSE) {
-          const T f = primal_force(type, jq - aref, D, R, fl);
-          if (f != 0) for (int k = 0; k < w; k++) a.qfrc_inverse[(long long)seg_dof(g, k) * S + env] -= Jr[k] * f;
-        }
-        // B_r = M^-1 J_r^T, one tree block at a time (M is block diagonal over trees)
-        for (int sgm = 0; sgm < 2; sgm++) {
-          const int lo = sgm ? g.s2 : g.s1, n = sgm ? g.n2 : g.n1, base = sgm ? g.n1 : 0;
-          if (n == 0) continue;
-          for (int i = lo + n - 1; i >= lo; i--) {
-            const T xi = Br[base + i - lo];
-            if (xi == 0) continue;
-            int adr = m.i(h.o_dof_Madr, i) + 1;
-            for (int j = m.i(h.o_dof_parentid, i); j >= 0; j = m.i(h.o_dof_parentid, j)) Br[base + j - lo] -= LD[adr++] * xi;
-          }
-          for (int i = lo; i < lo + n; i++) Br[base + i - lo] *= dinv[i];
-          for (int i = lo; i < lo + n; i++) {
-            int adr = m.i(h.o_dof_Madr, i) + 1;
-            T xi = Br[base + i - lo];
-            for (int j = m.i(h.o_dof_parentid, i); j >= 0; j = m.i(h.o_dof_parentid, j)) xi -= LD[adr++] * Br[base + j - lo];
-            Br[base + i - lo] = xi;
+          for (int e = 0; e < w; e++) {
+            T s0 = 0;
+            for (int k = 0; k < nb; k++) s0 += dsum[k] * rec[bs.oJ + k * wq + e];
+            if (s0 != 0) a.qfrc_inverse[(long long)bs.dof(e) * S + env] -= s0;
           }
         }
-        dg = R;
-        for (int k = 0; k < w; k++) dg += Jr[k] * Br[k];
-        a.efc_ARdiag[o] = dg;
+        for (int q = bs.oA + (nb > 1 ? bs.nrow * (bs.nrow - 1) / 2 : 0); q < bs.oJ; q++) rec[q] = 0;
+        rec[BH_CODE] = enc_int(bs.type + 16 * nb + 256 * bs.nrow, T());
+        rec[BH_S1] = enc_int(bs.s1, T()); rec[BH_N1W] = enc_int(bs.n1 + 1024 * w, T()); rec[BH_S2] = enc_int(bs.s2, T());
+        rec[BH_R] = R; rec[BH_FL] = fl; rec[BH_LEN] = enc_int(bs.len, T()); rec[BH_ROW0] = enc_int(r, T());
       }
-      // ---- transpose out: lanes cooperate on one environment's row at a time (coalesced line stores) ----
-      {
-        SArr<T> Mr{rowsh + (size_t)2 * WP * LDS + threadIdx.x, LDS};
-        Mr[META_R] = R; Mr[META_AREF] = aref; Mr[META_DIAG] = dg; Mr[META_FL] = fl;
-        Mr[META_TYPE] = (T)type; Mr[META_T1] = (T)t1; Mr[META_T2] = (T)t2; Mr[META_B] = bb;
-      }
+      // ---- transpose out: the lanes of the warp write one environment's record at a time (coalesced runs) ----
       __syncwarp();
-      const unsigned live = __ballot_sync(0xffffffffu, r < ne);
-      for (unsigned rem = live; rem; rem &= rem - 1) {
+      const int mylen = have ? bs.len : 0;
+      for (unsigned rem = __ballot_sync(0xffffffffu, have); rem; rem &= rem - 1) {
         const int e = __ffs(rem) - 1;
-        const long long env_e = (long long)tile * BLOCK + wbase + e;
-        T* dst = a.efc_rows + (env_e * h.njmax + r) * (2 * WP);
-        T* dstm = a.efc_meta + (env_e * h.njmax + r) * META_N;
-        for (int l = lane; l < 2 * WP + META_N; l += 32) {
-          const T v = rowsh[(size_t)l * LDS + wbase + e];
-          if (l < 2 * WP) dst[l] = v; else dstm[l - 2 * WP] = v;
-        }
+        const int len_e = __shfl_sync(0xffffffffu, mylen, e), off_e = __shfl_sync(0xffffffffu, woff, e);
+        T* dst = a.efc_blocks + ((long long)tile * BLOCK + wbase + e) * capw + off_e;
+        for (int q = lane; q < len_e; q += 32) dst[q] = recsh[(size_t)q * LDS + wbase + e];
       }
       __syncwarp();
+      if (have) { woff += bs.len; r += bs.nrow; }
+    }
+    if (!done) a.efc_nwords[env] = woff;
+  }
+}
+
+// One Gauss-Seidel visit of a block.  NBW is a WARP-uniform upper bound of the block's base directions (the teams of a
+// warp relax different blocks at the same time: running all of them through one instruction stream, padded rows
+// predicated off, keeps the warp converged where a switch on the block's own shape would serialise the teams).
+// Everything the visit needs is fetched up front; after the nb dot products v_r = J_r . acc of the pyramid rows is
+// tracked through the relaxation with the packed couplings ARu, so a row costs ~7 dependent operations.
+template <typename T, int NBW, int LANES>
+__device__ __forceinline__ void pgs_visit(const T* __restrict__ rec, const BlockShape& bs, T* acc, T* f, int l, T& improvement) {
+  // called by ALL lanes of the warp (full-mask shuffles of width LANES); a team without a block passes nb = nrow = w = 0
+  constexpr int NROWW = NBW > 1 ? 2 * (NBW - 1) : 1;
+  const int wq = bs.wq, w = bs.w, nb = bs.nb, nrow = bs.nrow;
+  const bool have = nrow > 0;
+  const int row0 = have ? dec_int(rec[BH_ROW0]) : 0;
+  const T R = have ? rec[BH_R] : T(0);
+  // admissible interval of the forces of this block
+  const T big = T(3.0e38);
+  const T flv = have ? rec[BH_FL] : T(0);
+  const T lo = bs.type == CN_EQUALITY ? -big : (bs.type == CN_FRICTION_DOF ? -flv : T(0));
+  const T hi = bs.type == CN_FRICTION_DOF ? flv : big;
+  T aref[NROWW], Arr[NROWW], iA[NROWW], fo[NROWW], mu[NBW > 1 ? NBW - 1 : 1];
+#pragma unroll
+  for (int r = 0; r < NROWW; r++) {
+    const bool on = r < nrow;
+    aref[r] = on ? rec[bs.oAref + r] : T(0); Arr[r] = on ? rec[bs.oArr + r] : T(0); iA[r] = on ? rec[bs.oiA + r] : T(0);
+    fo[r] = on ? f[row0 + r] : T(0);
+  }
+#pragma unroll
+  for (int k = 0; k < NBW - 1; k++) mu[k] = k < nb - 1 ? rec[bs.oMu + k] : T(0);
+  T cpl[NROWW > 1 ? NROWW * (NROWW - 1) / 2 : 1];   // couplings (r, s), r < s, in this function's own static packing
+  if (NBW > 1) {
+    int q = 0;
+#pragma unroll
+    for (int r = 0; r < NROWW; r++)
+#pragma unroll
+      for (int c = r + 1; c < NROWW; c++, q++) cpl[q] = c < nrow ? rec[bs.aru(r, c)] : T(0);
+  }
+  T u[NBW];
+#pragma unroll
+  for (int k = 0; k < NBW; k++) u[k] = 0;
+  for (int e = l; e < w; e += LANES) {
+    const T xv = acc[bs.dof(e)];
+#pragma unroll
+    for (int k = 0; k < NBW; k++) if (k < nb) u[k] += rec[bs.oJ + k * wq + e] * xv;
+  }
+#pragma unroll
+  for (int o = LANES / 2; o > 0; o >>= 1) {
+#pragma unroll
+    for (int k = 0; k < NBW; k++) u[k] += __shfl_xor_sync(0xffffffffu, u[k], o, LANES);
+  }
+  T v[NROWW], dl[NROWW];
+  if (NBW == 1) v[0] = u[0];
+  else {
+#pragma unroll
+    for (int r = 0; r < NROWW; r++) v[r] = nb > 1 ? u[0] + ((r & 1) ? -mu[r / 2] : mu[r / 2]) * u[r / 2 + 1] : u[0];
+  }
+  bool any = false;
+  {
+    int q = 0;
+#pragma unroll
+    for (int r = 0; r < NROWW; r++) {
+      const T res = v[r] + (R * fo[r] - aref[r]);
+      const T fn = t_min(hi, t_max(lo, fo[r] - res * iA[r]));
+      T delta = fn - fo[r];
+      const T change = T(0.5) * delta * delta * Arr[r] + delta * res;
+      const bool ok = r < nrow && delta != 0 && !(change > T(1e-10));
+      delta = ok ? delta : T(0);
+      improvement -= ok ? change : T(0);
+      fo[r] = ok ? fn : fo[r];
+      any |= ok;
+      dl[r] = delta;
+#pragma unroll
+      for (int c = r + 1; c < NROWW; c++, q++) v[c] += delta * cpl[q];
+    }
+  }
+  if (any) {
+#pragma unroll
+    for (int r = 0; r < NROWW; r++) if (r < nrow && l == r % LANES) f[row0 + r] = fo[r];
+    T d[NBW];
+    d[0] = dl[0];
+#pragma unroll
+    for (int r = 1; r < NROWW; r++) d[0] += dl[r];
+#pragma unroll
+    for (int k = 1; k < NBW; k++) d[k] = mu[k - 1] * (dl[2 * k - 2] - dl[2 * k - 1]);
+    for (int e = l; e < w; e += LANES) {
+      T s0 = 0;
+#pragma unroll
+      for (int k = 0; k < NBW; k++) if (k < nb) s0 += d[k] * rec[bs.oB + k * wq + e];
+      acc[bs.dof(e)] += s0;
     }
   }
 }
 
-template <typename T, int N> struct alignas(sizeof(T) * N) VecN { T v[N]; };
+// Visit order of the solver: environments sorted by descending record volume (a counting sort over NB bins of
+// words / BINW, one CTA; the order inside a bin is whatever the atomics give, which affects scheduling only).
+template <int NBIN, int THREADS>
+__global__ void __launch_bounds__(THREADS) k_order_envs(const int* __restrict__ nefc, const int* __restrict__ nwords, int* __restrict__ order,
+                                                        int nenvp, int binw, const int* pending, int use_pending) {
+  if (use_pending && pending[0] == 0) return;
+  __shared__ int hist[NBIN], start[NBIN];
+  for (int i = threadIdx.x; i < NBIN; i += THREADS) hist[i] = 0;
+  __syncthreads();
+  auto bin_of = [&](int e) { const int w = nefc[e] > 0 ? nwords[e] : 0; const int b = w / binw; return NBIN - 1 - (b < NBIN ? b : NBIN - 1); };
+  for (int e = threadIdx.x; e < nenvp; e += THREADS) atomicAdd(&hist[bin_of(e)], 1);
+  __syncthreads();
+  if (threadIdx.x == 0) { int s0 = 0; for (int i = 0; i < NBIN; i++) { start[i] = s0; s0 += hist[i]; } }
+  __syncthreads();
+  for (int e = threadIdx.x; e < nenvp; e += THREADS) order[atomicAdd(&start[bin_of(e)], 1)] = e;
+}
 
-// K6: projected Gauss-Seidel (A.8) in acceleration space.  An 8-lane team owns one environment (4 per warp): lane l
-// holds elements [l * EPL, (l + 1) * EPL) of the current row of J and B, the running acceleration and the forces live
-// in shared memory, rows stream from the slab one ahead of their use.
-template <typename T, int EPL, int BLOCK>
-__global__ void __launch_bounds__(BLOCK) k_pgs_team(const KArgs<T> a) {
-  B2_KERNEL_PROLOGUE
-  (void)ntiles;
-  constexpr int TEAM = 8, EPB = BLOCK / TEAM;  // environments per CTA
-  constexpr int WP = TEAM * EPL;
-  const int nv = h.nv, njmax = h.njmax;
+// K6: projected Gauss-Seidel (A.8) in acceleration space, one BLOCK at a time.  A team of LANES lanes owns one
+// environment; the running acceleration and the forces live in shared memory, and so do the first `stage_cap` words of
+// the environment's records (copied once, read `iterations` times; anything beyond is streamed from the slab).  Per
+// visit of a contact: u_k = J_k . acc for its nb base directions (lane-strided products + a team reduction), then the
+// contact's 2 (nb - 1) pyramid rows are relaxed in order on the local nb x nb matrix A (u is updated by columns of A
+// after every row, which is exactly what the row-by-row sweep over J_r = J_0 +/- mu_k J_k would have seen), and the
+// acceleration is corrected once by the accumulated force changes.  Same iterates as the row-by-row dual PGS.
+template <typename T, int LANES, int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) k_pgs_block(const KArgs<T> a) {
+  if ((a.flags & B2F_FUSABLE) && a.pending[0] == 0) return;
+  // the solver needs a handful of scalars of the model, not the staged blob: read them from the header in HBM (cached)
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const DModel& h = *reinterpret_cast<const DModel*>(a.model);
+  MV<T> m{&h, a.model};
+  const long long S = a.nenvp;
+  constexpr int EPB = BLOCK / LANES;  // environments per CTA
+  const int nv = h.nv, njmax = h.njmax, capw = a.block_capw, cap = a.stage_cap;
   const int nvs = nv + 4;  // stride of the per-environment vectors (skews the teams over the banks)
-  T* accsh = reinterpret_cast<T*>(smem_raw + 16 + (size_t)nwords * 4);  // [EPB][nvs] running acceleration
+  T* accsh = reinterpret_cast<T*>(smem_raw);                             // [EPB][nvs] running acceleration
   T* tmpsh = accsh + (size_t)EPB * nvs;                                   // [EPB][nvs] M^-1 J^T f, later qfrc_constraint
   T* fsh = tmpsh + (size_t)EPB * nvs;                                     // [EPB][njmax] forces
-  const int team = threadIdx.x / TEAM, l = threadIdx.x % TEAM;
-  const unsigned tmask = 0xffu << ((threadIdx.x & 31) & ~7);
+  T* stsh = fsh + (size_t)EPB * njmax;                                    // [EPB][cap] staged records
+  const int team = threadIdx.x / LANES, l = threadIdx.x % LANES;
+  const unsigned tmask = (LANES == 32 ? 0xffffffffu : ((1u << LANES) - 1u)) << ((threadIdx.x & 31) & ~(LANES - 1));
   T* acc = accsh + (size_t)team * nvs;
   T* tmp = tmpsh + (size_t)team * nvs;
   T* f = fsh + (size_t)team * njmax;
+  T* st = stsh + (size_t)team * cap;
   const int ngroups = (a.nenvp + EPB - 1) / EPB;
   const T tol = m.f(h.o_opt_real, 3), scale = 1 / (m.f(h.o_opt_real, 4) * T(nv > 1 ? nv : 1));
 
   auto team_sum = [&](T v) {
-    v += __shfl_xor_sync(tmask, v, 4);
-    v += __shfl_xor_sync(tmask, v, 2);
-    v += __shfl_xor_sync(tmask, v, 1);
+#pragma unroll
+    for (int o = LANES / 2; o > 0; o >>= 1) v += __shfl_xor_sync(tmask, v, o);
     return v;
   };
   for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
-    const long long env = (long long)grp * EPB + team;  // nenvp is a multiple of 128 >= EPB: always in range
-    if ((a.flags & B2F_FUSABLE) && (a.status[env] & 8)) continue;  // integrated by the smooth kernel (team-uniform)
-    const int ne = a.nefc[env];
-    const T* rowp = a.efc_rows + env * njmax * (2 * WP);
-    const T* metap = a.efc_meta + env * njmax * META_N;
+    // environments are visited in the order of k_order_envs: most constraint words first, so that the longest serial
+    // chains start at once and the teams of a warp carry similar loads (nenvp is a multiple of 128 >= EPB: in range)
+    const long long env = a.env_order[(long long)grp * EPB + team];
+    // integrated by the smooth kernel already (team-uniform): such a team only keeps the warp's collectives company
+    const bool skip = (a.flags & B2F_FUSABLE) && (a.status[env] & 8);
+    const int ne = skip ? 0 : a.nefc[env], nw = ne > 0 ? a.efc_nwords[env] : 0;
+    const T* slab = a.efc_blocks + env * capw;
     int iters = 0;
-    // dof index of this lane's elements for a row with trees (t1, t2); -1 for padding
-    auto dofs_of = [&](int t1, int t2, int* d) {
-      const Seg g = seg_of(m, t1, t2);
-#pragma unroll
-      for (int k = 0; k < EPL; k++) { const int kk = l * EPL + k; d[k] = kk < g.n1 + g.n2 ? seg_dof(g, kk) : -1; }
-    };
-    auto load_row = [&](int r, VecN<T, EPL>& J, VecN<T, EPL>& B, VecN<T, META_N>& M) {
-      J = *reinterpret_cast<const VecN<T, EPL>*>(rowp + (size_t)r * 2 * WP + l * EPL);
-      B = *reinterpret_cast<const VecN<T, EPL>*>(rowp + (size_t)r * 2 * WP + WP + l * EPL);
-      M = *reinterpret_cast<const VecN<T, META_N>*>(metap + (size_t)r * META_N);
-    };
-    for (int i = l; i < nv; i += TEAM) { acc[i] = a.qacc_warmstart[(long long)i * S + env]; tmp[i] = 0; }
+    // stage the leading records (16-byte copies: capw, cap and every record length are multiples of 4 words)
+    {
+      const int nst = nw < cap ? nw : cap;
+      constexpr int VW = 16 / (int)sizeof(T);
+      using V = VecN<T, VW>;
+      for (int q = l * VW; q < nst; q += LANES * VW) *reinterpret_cast<V*>(st + q) = *reinterpret_cast<const V*>(slab + q);
+    }
+    for (int i = l; i < nv; i += LANES) { acc[i] = a.qacc_warmstart[(long long)i * S + env]; tmp[i] = 0; }
     __syncwarp(tmask);
+    // record at word offset off: from shared memory when it was staged whole, else from the slab
+    auto rec_at = [&](int off) -> const T* {
+      if (off + BH_N <= cap) { const int len = dec_int(st[off + BH_LEN]); if (off + len <= cap) return st + off; }
+      return slab + off;
+    };
+    // u[k] = J_k . x for the nb base directions of a block
+    auto base_dots = [&](const T* rec, const BlockShape& bs, const T* x, T* u) {
+#pragma unroll
+      for (int k = 0; k < 6; k++) u[k] = 0;
+      for (int e = l; e < bs.w; e += LANES) {
+        const T xv = x[bs.dof(e)];
+#pragma unroll
+        for (int k = 0; k < 6; k++) if (k < bs.nb) u[k] += rec[bs.oJ + k * bs.wq + e] * xv;
+      }
+#pragma unroll
+      for (int k = 0; k < 6; k++) if (k < bs.nb) u[k] = team_sum(u[k]);
+    };
+    // x += sum_k d[k] X_k  (X = J or B rows of the block)
+    auto base_axpy = [&](const T* rec, const BlockShape& bs, int oX, const T* d, T* x) {
+      for (int e = l; e < bs.w; e += LANES) {
+        T s0 = 0;
+#pragma unroll
+        for (int k = 0; k < 6; k++) if (k < bs.nb) s0 += d[k] * rec[oX + k * bs.wq + e];
+        x[bs.dof(e)] += s0;
+      }
+    };
     if (ne > 0) {
-      VecN<T, EPL> J, B;
-      VecN<T, META_N> M;
-      int d[EPL];
       // ---- warm start: forces implied by qacc_warmstart (held in acc), kept only if their dual cost is negative ----
       bool warm = !(h.disableflags & DSBL_WARMSTART);
       if (warm) {
-        for (int r = 0; r < ne; r++) {
-          load_row(r, J, B, M);
-          dofs_of((int)M.v[META_T1], (int)M.v[META_T2], d);
-          T p = 0;
-#pragma unroll
-          for (int k = 0; k < EPL; k++) if (d[k] >= 0) p += J.v[k] * acc[d[k]];
-          const T jw = team_sum(p);
-          const T R = M.v[META_R];
-          const T fr = primal_force((int)M.v[META_TYPE], jw - M.v[META_AREF], 1 / R, R, M.v[META_FL]);
-          if (l == 0) f[r] = fr;
-          if (fr != 0) {
-#pragma unroll
-            for (int k = 0; k < EPL; k++) if (d[k] >= 0) tmp[d[k]] += fr * B.v[k];
+        for (int off = 0; off < nw;) {
+          const T* rec = rec_at(off);
+          const BlockShape bs = block_shape(rec);
+          T u[6], d[6] = {0, 0, 0, 0, 0, 0};
+          base_dots(rec, bs, acc, u);
+          const int row0 = dec_int(rec[BH_ROW0]);
+          const T R = rec[BH_R];
+          bool any = false;
+          for (int rr = 0; rr < bs.nrow; rr++) {
+            const int k = bs.nb > 1 ? rr / 2 + 1 : 0;
+            const T sm = bs.nb > 1 ? ((rr & 1) ? -rec[bs.oMu + k - 1] : rec[bs.oMu + k - 1]) : T(0);
+            const T fr = primal_force(bs.type, u[0] + sm * u[k] - rec[bs.oAref + rr], 1 / R, R, rec[BH_FL]);
+            if (l == 0) f[row0 + rr] = fr;
+            if (fr != 0) { any = true; d[0] += fr; if (bs.nb > 1) d[k] += sm * fr; }
           }
+          if (any) base_axpy(rec, bs, bs.oB, d, tmp);
           __syncwarp(tmask);
+          off += bs.len;
         }
         T cost = 0;
-        for (int r = 0; r < ne; r++) {
-          const T fr = f[r];
-          if (fr == 0) continue;
-          load_row(r, J, B, M);
-          dofs_of((int)M.v[META_T1], (int)M.v[META_T2], d);
-          T p = 0;
-#pragma unroll
-          for (int k = 0; k < EPL; k++) if (d[k] >= 0) p += J.v[k] * tmp[d[k]];
-          const T Af = team_sum(p) + M.v[META_R] * fr;
-          cost += fr * (T(0.5) * Af + M.v[META_B]);
+        for (int off = 0; off < nw;) {
+          const T* rec = rec_at(off);
+          const BlockShape bs = block_shape(rec);
+          const int row0 = dec_int(rec[BH_ROW0]);
+          bool any = false;
+          for (int rr = 0; rr < bs.nrow; rr++) any |= f[row0 + rr] != 0;
+          if (any) {
+            T u[6];
+            base_dots(rec, bs, tmp, u);
+            for (int rr = 0; rr < bs.nrow; rr++) {
+              const T fr = f[row0 + rr];
+              if (fr == 0) continue;
+              const int k = bs.nb > 1 ? rr / 2 + 1 : 0;
+              const T sm = bs.nb > 1 ? ((rr & 1) ? -rec[bs.oMu + k - 1] : rec[bs.oMu + k - 1]) : T(0);
+              const T Af = u[0] + sm * u[k] + rec[BH_R] * fr;
+              cost += fr * (T(0.5) * Af + rec[bs.ob + rr]);
+            }
+          }
+          off += bs.len;
         }
         if (cost > 0) warm = false;
       }
       __syncwarp(tmask);
       if (warm) {
-        for (int i = l; i < nv; i += TEAM) acc[i] = a.qacc_smooth[(long long)i * S + env] + tmp[i];
+        for (int i = l; i < nv; i += LANES) acc[i] = a.qacc_smooth[(long long)i * S + env] + tmp[i];
       } else {
-        for (int i = l; i < nv; i += TEAM) acc[i] = a.qacc_smooth[(long long)i * S + env];
-        for (int r = l; r < ne; r += TEAM) f[r] = 0;
+        for (int i = l; i < nv; i += LANES) acc[i] = a.qacc_smooth[(long long)i * S + env];
+        for (int r = l; r < ne; r += LANES) f[r] = 0;
       }
       __syncwarp(tmask);
-      // ---- Gauss-Seidel sweeps; the next row is fetched while the current one is processed ----
+    }
+    // ---- Gauss-Seidel sweeps over the blocks: every lane of the warp takes part in every visit (a team that has run
+    //      out of blocks, converged, or has no constraint at all relaxes an empty block), so the loop is warp-uniform,
+    //      the shuffles use the full mask and the teams never serialise ----
+    {
+      bool done = ne <= 0;
       for (int it = 0; it < h.iterations; it++) {
+        if (__all_sync(0xffffffffu, done)) break;
         T improvement = 0;
-        VecN<T, EPL> Jn, Bn;
-        VecN<T, META_N> Mn;
-        load_row(0, Jn, Bn, Mn);
-        for (int r = 0; r < ne; r++) {
-          J = Jn; B = Bn; M = Mn;
-          if (r + 1 < ne) load_row(r + 1, Jn, Bn, Mn);
-          dofs_of((int)M.v[META_T1], (int)M.v[META_T2], d);
-          T p = 0;
-#pragma unroll
-          for (int k = 0; k < EPL; k++) if (d[k] >= 0) p += J.v[k] * acc[d[k]];
-          const T old = f[r];
-          const T res = team_sum(p) + M.v[META_R] * old - M.v[META_AREF];
-          const T Arr = M.v[META_DIAG];
-          T fn = old - res / Arr;
-          const int type = (int)M.v[META_TYPE];
-          if (type == CN_FRICTION_DOF) { const T flv = M.v[META_FL]; fn = t_min(flv, t_max(-flv, fn)); }
-          else if (type != CN_EQUALITY) fn = t_max(T(0), fn);
-          const T delta = fn - old;
-          const T change = T(0.5) * delta * delta * Arr + delta * res;
-          if (delta != 0 && !(change > T(1e-10))) {
-            if (l == 0) f[r] = fn;
-            improvement -= change;
-#pragma unroll
-            for (int k = 0; k < EPL; k++) if (d[k] >= 0) acc[d[k]] += delta * B.v[k];
+        int off = 0;
+        while (true) {
+          const bool have = !done && off < nw;
+          if (!__any_sync(0xffffffffu, have)) break;
+          const T* rec = slab + (have ? off : 0);
+          BlockShape bs{};
+          if (have) {
+            bs = block_shape(rec);
+            // pull the next record (or, at the end of a sweep, the first) towards L1 while this one is relaxed
+            const int nxt = off + bs.len < nw ? off + bs.len : 0;
+            const int pq = nxt + l * (128 / (int)sizeof(T));
+            if (pq < nw && l < 5) asm volatile("prefetch.global.L1 [%0];" ::"l"(slab + pq));
           }
-          __syncwarp(tmask);
+          const int nbw = __reduce_max_sync(0xffffffffu, bs.nb);
+          if (nbw <= 1) pgs_visit<T, 1, LANES>(rec, bs, acc, f, l, improvement);
+          else if (nbw <= 3) pgs_visit<T, 3, LANES>(rec, bs, acc, f, l, improvement);
+          else if (nbw <= 4) pgs_visit<T, 4, LANES>(rec, bs, acc, f, l, improvement);
+          else pgs_visit<T, 6, LANES>(rec, bs, acc, f, l, improvement);
+          __syncwarp();
+          off += bs.len;
         }
-        iters = it + 1;
-        if (improvement * scale < tol) break;
+        if (!done) { iters = it + 1; if (improvement * scale < tol) done = true; }
       }
+    }
+    if (ne > 0) {
       // ---- qfrc_constraint = J^T f ----
-      for (int i = l; i < nv; i += TEAM) tmp[i] = 0;
+      for (int i = l; i < nv; i += LANES) tmp[i] = 0;
       __syncwarp(tmask);
-      for (int r = 0; r < ne; r++) {
-        const T fr = f[r];
-        if (l == 0) a.efc_force[(long long)r * S + env] = fr;
-        if (fr == 0) continue;
-        load_row(r, J, B, M);
-        dofs_of((int)M.v[META_T1], (int)M.v[META_T2], d);
-#pragma unroll
-        for (int k = 0; k < EPL; k++) if (d[k] >= 0) tmp[d[k]] += J.v[k] * fr;
+      for (int off = 0; off < nw;) {
+        const T* rec = rec_at(off);
+        const BlockShape bs = block_shape(rec);
+        const int row0 = dec_int(rec[BH_ROW0]);
+        T d[6] = {0, 0, 0, 0, 0, 0};
+        bool any = false;
+        for (int rr = 0; rr < bs.nrow; rr++) {
+          const T fr = f[row0 + rr];
+          if (l == 0) a.efc_force[(long long)(row0 + rr) * S + env] = fr;
+          if (fr == 0) continue;
+          const int k = bs.nb > 1 ? rr / 2 + 1 : 0;
+          any = true;
+          d[0] += fr;
+          if (bs.nb > 1) d[k] += ((rr & 1) ? -rec[bs.oMu + k - 1] : rec[bs.oMu + k - 1]) * fr;
+        }
+        if (any) base_axpy(rec, bs, bs.oJ, d, tmp);
         __syncwarp(tmask);
+        off += bs.len;
       }
     } else {
-      for (int i = l; i < nv; i += TEAM) acc[i] = a.qacc_smooth[(long long)i * S + env];
+      for (int i = l; i < nv; i += LANES) acc[i] = a.qacc_smooth[(long long)i * S + env];
     }
     __syncwarp(tmask);
-    for (int i = l; i < nv; i += TEAM) {
-      const T v = acc[i];
-      a.qacc[(long long)i * S + env] = v;
-      a.qacc_warmstart[(long long)i * S + env] = v;
-      a.qfrc_constraint[(long long)i * S + env] = tmp[i];
+    if (!skip) {
+      for (int i = l; i < nv; i += LANES) {
+        const T v = acc[i];
+        a.qacc[(long long)i * S + env] = v;
+        a.qacc_warmstart[(long long)i * S + env] = v;
+        a.qfrc_constraint[(long long)i * S + env] = tmp[i];
+      }
+      if (l == 0) a.solver_iter[env] = iters;
     }
-    if (l == 0) a.solver_iter[env] = iters;
     __syncwarp(tmask);
   }
 }
@@ -667,24 +906,31 @@ __global__ void __launch_bounds__(BLOCK) k_integrate(const KArgs<T> a) {
   }
 }
 
-// on-demand expansions for the legacy dense fields: efc_J [njmax][nv] and efc_AR [njmax][njmax], one thread per env
+// on-demand expansions for the legacy dense fields: efc_J [njmax][nv] (pyramid rows rebuilt from the base directions of
+// the block records) and efc_AR [njmax][njmax], one thread per env
 template <typename T>
 __global__ void k_expand_rows(const KArgs<T> a, int which /* 0: J, 1: B */, T* dst /* [njmax * nv][nenvp] */) {
   const DModel* h = reinterpret_cast<const DModel*>(a.model);
-  const uint32_t* w = a.model;
   const int env = blockIdx.x * blockDim.x + threadIdx.x;
   if (env >= a.nenvp) return;
   const long long S = a.nenvp;
-  const int ne = a.nefc[env], nv = h->nv, WP = a.wp;
-  for (int r = 0; r < h->njmax; r++) {
+  const int ne = a.nefc[env], nv = h->nv;
+  for (int r = 0; r < h->njmax; r++)
     for (int i = 0; i < nv; i++) dst[((long long)r * nv + i) * S + env] = 0;
-    if (r >= ne) continue;
-    const int t1 = a.efc_tree[((long long)2 * r) * S + env], t2 = a.efc_tree[((long long)2 * r + 1) * S + env];
-    Seg g{0, 0, 0, 0};
-    if (t1 >= 0) { g.s1 = (int)w[h->o_tree_dofadr + t1]; g.n1 = (int)w[h->o_tree_dofnum + t1]; }
-    if (t2 >= 0) { g.s2 = (int)w[h->o_tree_dofadr + t2]; g.n2 = (int)w[h->o_tree_dofnum + t2]; }
-    const T* row = a.efc_rows + ((long long)env * h->njmax + r) * (2 * WP) + (which ? WP : 0);
-    for (int k = 0; k < g.n1 + g.n2; k++) dst[((long long)r * nv + seg_dof(g, k)) * S + env] = row[k];
+  if (ne <= 0) return;
+  const int nw = a.efc_nwords[env];
+  const T* slab = a.efc_blocks + (long long)env * a.block_capw;
+  for (int off = 0; off < nw;) {
+    const T* rec = slab + off;
+    const BlockShape bs = block_shape(rec);
+    const int row0 = dec_int(rec[BH_ROW0]), oX = which ? bs.oB : bs.oJ;
+    for (int rr = 0; rr < bs.nrow; rr++) {
+      const int k = bs.nb > 1 ? rr / 2 + 1 : 0;
+      const T sm = bs.nb > 1 ? ((rr & 1) ? -rec[bs.oMu + k - 1] : rec[bs.oMu + k - 1]) : T(0);
+      for (int e = 0; e < bs.w; e++)
+        dst[((long long)(row0 + rr) * nv + bs.dof(e)) * S + env] = rec[oX + e] + (bs.nb > 1 ? sm * rec[oX + k * bs.wq + e] : T(0));
+    }
+    off += bs.len;
   }
 }
 template <typename T>
