@@ -122,6 +122,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true")
+    ap.add_argument("--gather-obs", action="store_true",
+                    help="N > 1: add the optional per-tick NCCL all-gather of observations (SURVEY.md 8e) to the timed region; "
+                         "off by default because the path itself has no exchange step (environments are independent)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -190,6 +193,19 @@ def main():
 
     stream = torch.cuda.ExternalStream(bt.stream, device=torch.device("cuda", local_rank))
     flush = not args.no_flush
+    # the one exchange of the control tick: every rank receives every shard's [qpos | qvel] (fp32).  The
+    # pack is a kernel of the engine; the all-gather is NCCL over NVLink on the batch's own stream.
+    gather = dist is not None and args.gather_obs
+    nobs = m.nq + m.nv
+    if gather:
+        obs_local = torch.empty((nobs, nenv), dtype=torch.float32, device="cuda")
+        obs_all = torch.empty((world, nobs, nenv), dtype=torch.float32, device="cuda")
+
+    def exchange():
+        if gather:
+            bt.pack_obs(obs_local.data_ptr())
+            with torch.cuda.stream(stream):
+                dist.all_gather_into_tensor(obs_all, obs_local)
 
     def do_flush():
         if flush:
@@ -213,7 +229,8 @@ def main():
     for k in range(K):
         do_flush()
         starts[k].record(stream)
-        bt.tick_resident()          # one CUDA-graph launch: k_hw_write -> tick kernels -> k_hw_read
+        bt.tick_resident()          # the tick kernels (one launch for a limit-only chain, else a CUDA-graph replay)
+        exchange()
         ends[k].record(stream)
     bt.sync(); torch.cuda.synchronize()
     # per-kernel device time: the same K ticks again, launched eagerly with CUDA events between the kernels
@@ -240,6 +257,9 @@ def main():
         bt.sync()
         t0 = time.perf_counter()
         bt.tick_host_raw(*host_args)
+        if gather:
+            exchange()
+            stream.synchronize()
         e2e_s += time.perf_counter() - t0
     t2 = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if dist is not None:
@@ -275,8 +295,9 @@ def main():
         "config": {"workload": "%s: %s" % (args.config, desc), "model": asset, "envs_per_gpu": nenv, "envs_total": total_envs,
                    "timestep": 0.005, "tick": "write+step1+controller+inverse+step2+read", "mean_ncon": ncon_mean, "mean_nefc": nefc_mean,
                    "l2": "flushed before every timed step (256 MiB memset)" if flush else "not flushed",
-                   "solver": "PGS, %d iterations max" % int(m.int("opt.iterations")), "kernels": bt.path_name},
-        "roofline": {"bound": "hbm", "kernel": (bt.path_name.split("+")[0] if dom == "smooth" else {"pgs": "k_pgs_team"}.get(dom, "k_" + dom)), "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                   "solver": "PGS, %d iterations max" % int(m.int("opt.iterations")), "kernels": bt.path_name,
+                   "obs_allgather": ("NCCL all_gather of [qpos|qvel] fp32, %d B per rank per tick, inside the timed region" % (4 * nobs * nenv)) if gather else "none: shards are independent, no data-path collective"},
+        "roofline": {"bound": "hbm", "kernel": (bt.path_name.split("+")[0] if dom == "smooth" else {"pgs": "k_pgs_block"}.get(dom, "k_" + dom)), "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_env_step": balg,
                      "kernel_timing": "CUDA events between the kernels, same K ticks re-run eagerly right after the graph-replayed timed loop",
                      "kernel_ms": dom_ms, "kernel_share_of_step": kern[dom] / max(1e-12, sum(slot_ms.values())),

@@ -99,6 +99,12 @@ int b2_tick_host(b2_batch* b, const float* vel_cmd_host, const float* effort_cmd
  * HBM: no host<->device traffic, asynchronous (throughput with resident inputs) */
 int b2_tick_resident(b2_batch* b);
 
+/* observation exchange ("at most one all-gather of observations per control tick"): pack
+ * [qpos | qvel] of every environment of this shard as fp32, native layout [nq + nv][nenv], into the DEVICE buffer
+ * obs_dev ((nq + nv) * nenv floats) on the batch's stream.  The collective itself is the caller's: one process per GPU,
+ * ncclAllGather / torch.distributed.all_gather_into_tensor of that buffer on the same stream (bench.py does exactly that). */
+int b2_pack_obs(b2_batch* b, float* obs_dev);
+
 /* benchmarking aid: write `bytes` of scratch on the batch's stream so that the state leaves the L2 between timed steps */
 int b2_l2_flush(b2_batch* b, long long bytes);
 

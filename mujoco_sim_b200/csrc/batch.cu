@@ -572,6 +572,15 @@ __global__ void k_reset(D* qpos, D* qvel, D* qacc, D* qws, D* qapp, D* time, con
   time[e] = 0;
 }
 
+// observation pack for the per-tick all-gather: dst[(i) * nenv + e] = (i < nq ? qpos[i] : qvel[i - nq]) of environment e
+template <typename D>
+__global__ void k_pack_obs(const D* __restrict__ qpos, const D* __restrict__ qvel, float* __restrict__ dst, int nq, int nv, int nenv, int nenvp) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)(nq + nv) * nenv) return;
+  const int i = (int)(idx / nenv), e = (int)(idx % nenv);
+  dst[idx] = (float)(i < nq ? qpos[(long long)i * nenvp + e] : qvel[(long long)(i - nq) * nenvp + e]);
+}
+
 // MjHWInterface::write (src/mujoco_sim/mj_hw_interface.cpp:73-91) for every environment
 template <typename D>
 __global__ void k_hw_write(D* ddq, D* dq, const float* vel_cmd, const float* eff_cmd, const int* dadr, const int* ctl, int nhw,
@@ -1075,6 +1084,24 @@ int b2_tick_host(b2_batch* b, const float* vel, const float* eff, float* pos, fl
 int b2_tick_resident(b2_batch* b) {
   if (!b) return fail("b2_tick_resident: null batch");
   return tick_hw(b, nullptr, nullptr, nullptr, nullptr, nullptr, false);
+}
+
+int b2_pack_obs(b2_batch* b, float* obs_dev) {
+  if (!b || !obs_dev) return fail("b2_pack_obs: null argument");
+  CK(cudaSetDevice(b->device));
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, obs_dev) != cudaSuccess || (at.type != cudaMemoryTypeDevice && at.type != cudaMemoryTypeManaged)) {
+    cudaGetLastError();
+    return fail("b2_pack_obs: obs_dev must be device memory");
+  }
+  const int nq = b->m->nq, nv = b->m->nv;
+  const long long tot = (long long)(nq + nv) * b->nenv;
+  const int th = 256, bl = (int)((tot + th - 1) / th);
+  if (b->prec == 8) k_pack_obs<double><<<bl, th, 0, b->stream>>>((const double*)b->fields["qpos"].ptr, (const double*)b->fields["qvel"].ptr, obs_dev, nq, nv, b->nenv, b->nenvp);
+  else k_pack_obs<float><<<bl, th, 0, b->stream>>>((const float*)b->fields["qpos"].ptr, (const float*)b->fields["qvel"].ptr, obs_dev, nq, nv, b->nenv, b->nenvp);
+  b->launches++;
+  CK(cudaGetLastError());
+  return 0;
 }
 
 // write `bytes` of scratch on the batch's stream: evicts the batch state from the 126 MB L2 between timed steps

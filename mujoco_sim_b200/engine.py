@@ -1,5 +1,5 @@
 """ctypes mirror of the C ABI (include/b2_batch.h, include/mujoco/mujoco.h).  No physics here: every number comes from
-libb2sim.so.  Importing fails loudly when the library has not been built (python -m mujoco_sim_b200.build)."""
+libb2sim.so.  Importing fails loudly when the library has not been built (python mujoco_sim_b200/build.py)."""
 import ctypes as C
 import os
 
@@ -22,7 +22,7 @@ class B2Error(RuntimeError):
 
 
 if not os.path.exists(lib_path()):
-    raise ImportError("%s is missing: build it with `python -m mujoco_sim_b200.build` "
+    raise ImportError("%s is missing: build it with `python mujoco_sim_b200/build.py` "
                       "(there is no Python or CPU fallback for the CUDA engine)" % lib_path())
 lib = C.CDLL(lib_path(), mode=C.RTLD_GLOBAL)
 
@@ -86,6 +86,7 @@ _sig = {
     "b2_read_joints": (_i, [_vp, _vp, _vp, _vp]),
     "b2_tick_host": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "b2_tick_resident": (_i, [_vp]),
+    "b2_pack_obs": (_i, [_vp, _vp]),
     "b2_l2_flush": (_i, [_vp, C.c_longlong]),
     "b2_profile_begin": (_i, [_vp, _i]),
     "b2_profile_end": (_i, [_vp, _vp, _i]),
@@ -330,6 +331,10 @@ class Batch:
 
     def tick_host_raw(self, vel_ptr, eff_ptr, pos_ptr, velo_ptr, effo_ptr):
         self._ck(lib.b2_tick_host(self.ptr, vel_ptr, eff_ptr, pos_ptr, velo_ptr, effo_ptr), "b2_tick_host")
+
+    def pack_obs(self, dev_ptr):
+        """[qpos | qvel] as fp32 [nq + nv][nenv] into a device buffer (the payload of the per-tick all-gather)."""
+        self._ck(lib.b2_pack_obs(self.ptr, dev_ptr), "b2_pack_obs")
 
     def tick_resident(self):
         self._ck(lib.b2_tick_resident(self.ptr), "b2_tick_resident")

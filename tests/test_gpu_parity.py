@@ -489,3 +489,21 @@ def test_chain_team_kernel_matches_thread_per_env_kernel(b2, prec):
     for k in range(7):
         scale = max(1.0, float(np.abs(a[k]).max()))
         assert np.abs(a[k] - b[k]).max() <= rtol * scale * (50 if k in (2, 3) and prec == "f32" else 1), (k, np.abs(a[k] - b[k]).max(), scale)
+
+
+def test_pack_obs_is_the_state_in_native_layout(b2):
+    """b2_pack_obs: the payload of the per-tick observation all-gather is [qpos | qvel] as fp32 [nq + nv][nenv]."""
+    import torch
+    m = b2.Model(b2.asset("ur5_tabletop.xml"))
+    nenv = 70
+    bt = b2.Batch(m, nenv)
+    qpos, qvel, _ = random_state(m, nenv, 9)
+    bt.set("qpos", qpos); bt.set("qvel", qvel)
+    bt.step(3)
+    obs = torch.zeros((m.nq + m.nv, nenv), dtype=torch.float32, device="cuda")
+    bt.pack_obs(obs.data_ptr()); bt.sync()
+    ref = np.concatenate([bt.get("qpos", layout=b2.engine.NATIVE, dtype=np.float32), bt.get("qvel", layout=b2.engine.NATIVE, dtype=np.float32)])
+    assert np.array_equal(obs.cpu().numpy(), ref)
+    with pytest.raises(b2.B2Error, match="device memory"):
+        bt.pack_obs(np.zeros(4, np.float32).ctypes.data)
+    bt.close()
