@@ -23,7 +23,7 @@ if ROOT not in sys.path:
 import numpy as np  # noqa: E402
 
 METRIC, UNIT = "env_steps_per_sec", "env-steps/s"
-SETTLE_TICKS = {"c1": 0, "c2": 0, "c3": 150}
+SETTLE_TICKS = {"c1": 0, "c2": 0, "c3": 150, "c4": 150}
 
 
 def peaks():
@@ -98,18 +98,70 @@ def cpu_reference(cfg, nenv_sample, steps, warmup, threads=None):
     qpos, qvel, frc = w.config_state(cfg, m, np.arange(nenv_sample))
     qpos = np.ascontiguousarray(qpos); qvel = np.ascontiguousarray(qvel)
     ws = np.zeros((nenv_sample, m.nv))
-    ddq = np.ascontiguousarray(0.1 * frc)
+    hw, ctl, kp, kd = w.control_spec(cfg, m)
+    dadr = np.array(m.jnt_dofadr)[hw]
+    ddq = np.zeros((nenv_sample, m.nv))
+    ddq[:, dadr] = w.commands(cfg, m, np.arange(nenv_sample))
     dq = np.zeros((nenv_sample, m.nv))
-    ctl = np.ones(m.nv, np.uint8)
+    pd = {}
+    if kp is not None:
+        kpv, kdv = np.zeros(m.nv), np.zeros(m.nv)
+        kpv[dadr], kdv[dadr] = kp, kd
+        pd = {"pd_kp": kpv, "pd_kd": kdv}
     settle = SETTLE_TICKS[cfg]
     if settle:
-        orc.tick_batch(m, pool, settle, qpos, qvel, ws, None, ddq, dq, ctl, True)
+        orc.tick_batch(m, pool, settle, qpos, qvel, ws, None, ddq, dq, ctl, True, **pd)
     if warmup:
-        orc.tick_batch(m, pool, warmup, qpos, qvel, ws, None, ddq, dq, ctl, True)
+        orc.tick_batch(m, pool, warmup, qpos, qvel, ws, None, ddq, dq, ctl, True, **pd)
     t0 = time.perf_counter()
-    used = orc.tick_batch(m, pool, steps, qpos, qvel, ws, None, ddq, dq, ctl, True)
+    used = orc.tick_batch(m, pool, steps, qpos, qvel, ws, None, ddq, dq, ctl, True, **pd)
     dt = time.perf_counter() - t0
     return nenv_sample * steps / dt, used, dt
+
+
+def drift_report(cfg, nenv=64, horizons=(1, 10, 100, 1000)):
+    """BASELINE metric, second part: relative L2 drift of qpos (fp32 CUDA tick vs the fp64 CPU oracle) from identical
+    states, median and max over `nenv` environments, plus the fraction of environments whose contact COUNT still
+    agrees (trajectories stop being comparable once the contact sets differ).  Part of the cpu_baseline leg: the oracle
+    is the checker here, not the thing measured."""
+    import mujoco_sim_b200 as b2
+    from mujoco_sim_b200 import workloads as w
+    from oracle import pyoracle as orc
+    m = b2.Model(b2.asset(w.CONFIGS[cfg][0]))
+    bt = b2.Batch(m, nenv)
+    qpos, qvel, frc, _ = w.load_config(cfg, bt)
+    rq, rv, rf = (np.ascontiguousarray(x, np.float64).copy() for x in (qpos, qvel, frc))
+    ws = np.zeros((nenv, m.nv))
+    pool = [b2.Data(m) for _ in range(min(16, os.cpu_count() or 1, nenv))]
+    probe = b2.Data(m)
+    out = {"envs": nenv, "ticks": list(horizons), "median": [], "max": [], "ncon_equal_frac": []}
+    done = 0
+    for k in horizons:
+        bt.step(k - done); bt.sync()
+        orc.tick_batch(m, pool, k - done, rq, rv, ws, rf)
+        done = k
+        gq = bt.get("qpos")
+        rel = np.linalg.norm(gq - rq, axis=1) / np.maximum(np.linalg.norm(rq, axis=1), 1e-12)
+        out["median"].append(float(np.median(rel))); out["max"].append(float(rel.max()))
+        if m.npair > 0:
+            gn = bt.get("ncon")[:, 0]
+            rn = np.zeros(nenv, int)
+            for e in range(nenv):   # contact count of the oracle state: one position stage per environment
+                probe.qpos[:] = rq[e]; probe.qvel[:] = rv[e]
+                orc.call("fwdPosition", m, probe)
+                rn[e] = probe.ncon
+            # the batch holds the contacts of the tick it just ran (the state one tick earlier): re-run the position stage
+            # on the current state (mj_forward), with the solver's warm start put back so the trajectory is not perturbed
+            keep = [(f, bt.get(f)) for f in ("qacc", "qacc_warmstart")]
+            bt.forward(); bt.sync()
+            gn = bt.get("ncon")[:, 0]
+            for f, v in keep:
+                bt.set(f, v)
+            out["ncon_equal_frac"].append(float((gn == rn).mean()))
+        else:
+            out["ncon_equal_frac"].append(1.0)
+    bt.close()
+    return out
 
 
 def main():
@@ -117,7 +169,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--config", default=os.environ.get("B2_BENCH_CONFIG", "c2"), choices=["c2", "c3"])
+    ap.add_argument("--config", default=os.environ.get("B2_BENCH_CONFIG", "c2"), choices=["c2", "c3", "c4"])
     ap.add_argument("--nenv", type=int, default=0, help="environments per GPU (default: the config's)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -172,18 +224,15 @@ def main():
     bt = b2.Batch(m, nenv, device=local_rank, precision=b2.engine.F32)
     env_offset = rank * nenv  # contiguous shards of one global batch
     w.load_config(args.config, bt, env_offset=env_offset)
-    nv = m.nv
-    # every scalar joint is a ros_control joint; all of them are "controlled" (PD computed-torque on every joint)
-    jt = np.array(m.jnt_type)
-    hw = np.where(jt >= 2)[0].astype(np.int32)
-    ctl = np.zeros(nv, np.uint8)
-    ctl[np.array(m.jnt_dofadr)[hw]] = 1
+    # hardware joints, controlled dofs, PD gains and the command buffer of the config (workloads.control_spec)
+    hw, ctl, kp, kd = w.control_spec(args.config, m)
     bt.set_controlled(ctl)
     bt.set_hw_joints(hw)
+    if kp is not None:
+        bt.set_pd(kp, kd)
     nhw = hw.size
-    # commands: desired accelerations ddq = 0.1 * (the config's random torques) on the controlled joints, no velocity commands
-    _, _, frc = w.config_state(args.config, m, np.arange(env_offset, env_offset + nenv))
-    eff_cmd = torch.from_numpy(np.ascontiguousarray((0.1 * frc[:, np.array(m.jnt_dofadr)[hw]]).T.astype(np.float32))).pin_memory()
+    cmd = w.commands(args.config, m, np.arange(env_offset, env_offset + nenv))
+    eff_cmd = torch.from_numpy(np.ascontiguousarray(cmd.T.astype(np.float32))).pin_memory()
     vel_cmd = torch.zeros((nhw, nenv), dtype=torch.float32).pin_memory()
     pos_o = torch.empty((nhw, nenv), dtype=torch.float32).pin_memory()
     vel_o = torch.empty_like(pos_o).pin_memory()
@@ -293,7 +342,7 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
         "ms_per_step": max_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "%s: %s" % (args.config, desc), "model": asset, "envs_per_gpu": nenv, "envs_total": total_envs,
-                   "timestep": 0.005, "tick": "write+step1+controller+inverse+step2+read", "mean_ncon": ncon_mean, "mean_nefc": nefc_mean,
+                   "timestep": 0.005, "tick": "write+step1+controller+inverse+step2+read" + (" with device-side PD (kp 200, kd 50) on %d arm joints" % nhw if kp is not None else ""), "mean_ncon": ncon_mean, "mean_nefc": nefc_mean,
                    "l2": "flushed before every timed step (256 MiB memset)" if flush else "not flushed",
                    "solver": "PGS, %d iterations max" % int(m.int("opt.iterations")), "kernels": bt.path_name,
                    "obs_allgather": ("NCCL all_gather of [qpos|qvel] fp32, %d B per rank per tick, inside the timed region" % (4 * nobs * nenv)) if gather else "none: shards are independent, no data-path collective"},
@@ -308,9 +357,10 @@ def main():
         "clocks": clocks,
     }
     if not args.no_cpu_baseline and world == 1:
-        sample = {"c2": 4096, "c3": 2048}[args.config]
-        csteps = {"c2": 2000, "c3": 1500}[args.config]  # about 10 s of CPU work on 8 cores
+        sample = {"c2": 4096, "c3": 2048, "c4": 1024}[args.config]
+        csteps = {"c2": 2000, "c3": 1500, "c4": 1000}[args.config]  # about 10 s of CPU work on 8 cores
         val, used, dt = cpu_reference(args.config, sample, csteps, 3)
+        out["drift"] = drift_report(args.config)
         out["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": used, "kind": "port",
                                "sample": "%d envs x %d ticks of the same workload in %.1f s; fp64 oracle restatement of MuJoCo 2.3.7 semantics "
                                          "(libmujoco is not available)" % (sample, csteps, dt)}

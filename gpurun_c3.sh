@@ -1,4 +1,2 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -4
-for lanes in 8 4; do
-B2_PGS_LANES=$lanes python bench.py --config c3 --no-cpu-baseline --steps 10 2>&1 | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); k=d['roofline']['kernel_ms_all']; print('lanes $lanes', round(d['value']/1e6,3), 'M/s', round(d['ms_per_step'],3), {x: round(v,3) for x,v in k.items() if v>0})"
-done
+python -m pytest tests -m gpu -x -q 2>&1 | tail -15
+python bench.py --config c4 --steps 10 2>&1 | tail -1

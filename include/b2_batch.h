@@ -91,6 +91,12 @@ long long b2_launch_count(const b2_batch* b); /* kernels launched so far */
 int b2_set_hw_joints(b2_batch* b, int njoint, const int* jnt_ids);
 int b2_write_commands(b2_batch* b, const float* vel_cmd_host, const float* effort_cmd_host);
 int b2_read_joints(b2_batch* b, float* pos_host, float* vel_host, float* effort_host);
+/* device-side PD stage in front of write(): with gains set (kp, kd per hardware joint; NULL, NULL switches it off) the
+ * effort-command buffer carries position TARGETS q* and the command consumed by write() becomes
+ * kp (q* - q) - kd qdot, evaluated per environment on the GPU.  This is what the reference's ros_control PID
+ * controllers compute on the host for its single environment (gains: model/ontology/box/box.yaml:5-13; the result is
+ * read as a desired acceleration, src/mujoco_sim/mj_hw_interface.cpp:73-91). */
+int b2_set_pd(b2_batch* b, const float* kp, const float* kd);
 /* end-to-end tick through host buffers: H2D commands, tick, D2H joint states, synchronised */
 int b2_tick_host(b2_batch* b, const float* vel_cmd_host, const float* effort_cmd_host, float* pos_host, float* vel_host,
                  float* effort_host);

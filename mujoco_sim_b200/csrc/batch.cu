@@ -233,6 +233,7 @@ KArgs<T> make_args(b2_batch* b, int flags) {
   a.block_capw = b->block_capw; a.stage_cap = b->stage_cap;
   a.hw_vel = b->io_in[0]; a.hw_eff = b->io_in[1];
   a.hw_pos = b->io_out[0]; a.hw_velo = b->io_out[1]; a.hw_effo = b->io_out[2];
+  a.hw_kp = b->hw_kp; a.hw_kd = b->hw_kd;
   return a;
 }
 
@@ -584,15 +585,17 @@ __global__ void k_pack_obs(const D* __restrict__ qpos, const D* __restrict__ qve
 // MjHWInterface::write (src/mujoco_sim/mj_hw_interface.cpp:73-91) for every environment
 template <typename D>
 __global__ void k_hw_write(D* ddq, D* dq, const float* vel_cmd, const float* eff_cmd, const int* dadr, const int* ctl, int nhw,
-                           int nenv, int nenvp) {
+                           int nenv, int nenvp, const D* qpos, const D* qvel, const int* qadr, const float* kp, const float* kd) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)nhw * nenv) return;
   const int j = (int)(idx / nenv), e = (int)(idx % nenv);
   if (!ctl[j]) return;
   const float v = vel_cmd[idx];
   const int d = dadr[j];
-  if (fabsf(v) > 1e-15f) dq[(long long)d * nenvp + e] = (D)v;
-  else ddq[(long long)d * nenvp + e] = (D)eff_cmd[idx];
+  if (fabsf(v) > 1e-15f) { dq[(long long)d * nenvp + e] = (D)v; return; }
+  D cmd = (D)eff_cmd[idx];
+  if (kp) cmd = (D)kp[j] * (cmd - qpos[(long long)qadr[j] * nenvp + e]) - (D)kd[j] * qvel[(long long)d * nenvp + e];  // PD stage (b2_set_pd)
+  ddq[(long long)d * nenvp + e] = cmd;
 }
 // MjHWInterface::read gathers (src/mujoco_sim/mj_hw_interface.cpp:62-70)
 template <typename D>
@@ -791,6 +794,8 @@ void b2_destroy(b2_batch* b) {
   if (b->hw_dadr) cudaFree(b->hw_dadr);
   if (b->hw_ctl) cudaFree(b->hw_ctl);
   if (b->hw_buf) cudaFree(b->hw_buf);
+  if (b->hw_kp) cudaFree(b->hw_kp);
+  if (b->hw_kd) cudaFree(b->hw_kd);
   if (b->flush_buf) cudaFree(b->flush_buf);
   for (auto& kv : b->registered) cudaHostUnregister(const_cast<void*>(kv.first));
   for (cudaEvent_t e : b->prof_ev) cudaEventDestroy(e);
@@ -943,6 +948,8 @@ int b2_set_hw_joints(b2_batch* b, int njoint, const int* jnt_ids) {
   }
   for (int** p : {&b->hw_qadr, &b->hw_dadr, &b->hw_ctl}) { if (*p) cudaFree(*p); *p = nullptr; }
   if (b->hw_buf) { cudaFree(b->hw_buf); b->hw_buf = nullptr; }
+  if (b->hw_kp) { cudaFree(b->hw_kp); b->hw_kp = nullptr; }
+  if (b->hw_kd) { cudaFree(b->hw_kd); b->hw_kd = nullptr; }
   CK(cudaMalloc(&b->hw_qadr, sizeof(int) * njoint));
   CK(cudaMalloc(&b->hw_dadr, sizeof(int) * njoint));
   CK(cudaMalloc(&b->hw_ctl, sizeof(int) * njoint));
@@ -968,8 +975,8 @@ int hw_write_async(b2_batch* b) {
   if (!b->nhw) return fail("b2_write_commands: call b2_set_hw_joints first");
   const size_t n = (size_t)b->nhw * b->nenv;
   const int th = 256, bl = (int)((n + th - 1) / th);
-  if (b->prec == 8) k_hw_write<double><<<bl, th, 0, b->stream>>>((double*)b->fields["ddq"].ptr, (double*)b->fields["dq"].ptr, b->io_in[0], b->io_in[1], b->hw_dadr, b->hw_ctl, b->nhw, b->nenv, b->nenvp);
-  else k_hw_write<float><<<bl, th, 0, b->stream>>>((float*)b->fields["ddq"].ptr, (float*)b->fields["dq"].ptr, b->io_in[0], b->io_in[1], b->hw_dadr, b->hw_ctl, b->nhw, b->nenv, b->nenvp);
+  if (b->prec == 8) k_hw_write<double><<<bl, th, 0, b->stream>>>((double*)b->fields["ddq"].ptr, (double*)b->fields["dq"].ptr, b->io_in[0], b->io_in[1], b->hw_dadr, b->hw_ctl, b->nhw, b->nenv, b->nenvp, (const double*)b->fields["qpos"].ptr, (const double*)b->fields["qvel"].ptr, b->hw_qadr, b->hw_kp, b->hw_kd);
+  else k_hw_write<float><<<bl, th, 0, b->stream>>>((float*)b->fields["ddq"].ptr, (float*)b->fields["dq"].ptr, b->io_in[0], b->io_in[1], b->hw_dadr, b->hw_ctl, b->nhw, b->nenv, b->nenvp, (const float*)b->fields["qpos"].ptr, (const float*)b->fields["qvel"].ptr, b->hw_qadr, b->hw_kp, b->hw_kd);
   b->launches++;
   CK(cudaGetLastError());
   return 0;
@@ -1012,6 +1019,23 @@ float* device_alias(b2_batch* b, const void* host, size_t bytes) {
 
 }  // namespace
 extern "C" {
+
+int b2_set_pd(b2_batch* b, const float* kp, const float* kd) {
+  if (!b) return fail("b2_set_pd: null batch");
+  CK(cudaSetDevice(b->device));
+  if (!b->nhw) return fail("b2_set_pd: call b2_set_hw_joints first");
+  drop_graphs(b);
+  CK(cudaStreamSynchronize(b->stream));
+  if (b->hw_kp) { cudaFree(b->hw_kp); b->hw_kp = nullptr; }
+  if (b->hw_kd) { cudaFree(b->hw_kd); b->hw_kd = nullptr; }
+  if (!kp && !kd) return 0;
+  if (!kp || !kd) return fail("b2_set_pd: kp and kd must both be given (or both NULL)");
+  CK(cudaMalloc(&b->hw_kp, sizeof(float) * b->nhw));
+  CK(cudaMalloc(&b->hw_kd, sizeof(float) * b->nhw));
+  CK(cudaMemcpy(b->hw_kp, kp, sizeof(float) * b->nhw, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(b->hw_kd, kd, sizeof(float) * b->nhw, cudaMemcpyHostToDevice));
+  return 0;
+}
 
 // upload the command buffers into the HBM staging area and apply them (MjHWInterface::write for every environment)
 int b2_write_commands(b2_batch* b, const float* vel, const float* eff) {

@@ -62,6 +62,7 @@ struct b2_batch {
   int nhw = 0;
   int *hw_qadr = nullptr, *hw_dadr = nullptr, *hw_ctl = nullptr;
   float* hw_buf = nullptr;  // [5][nhw][nenv] fp32 staging: vel_cmd, effort_cmd, pos, vel, effort
+  float *hw_kp = nullptr, *hw_kd = nullptr;  // [nhw] device-side PD gains (b2_set_pd)
   bool hw_identity = false; // hardware joint j is dof j for every dof (lets k_chain do the exchange itself)
   // buffers the exchange of the tick being launched reads / writes: the hw_buf slots, or device-accessible aliases of the
   // caller's host buffers (pinned / registered memory is read and written in place over PCIe, no staging copies)

@@ -72,6 +72,7 @@ struct KArgs {
   // hardware-interface exchange, native layout [joint][nenv] fp32; HBM staging or mapped (zero-copy) host memory
   const float *hw_vel, *hw_eff;
   float *hw_pos, *hw_velo, *hw_effo;
+  const float *hw_kp, *hw_kd;   // [nhw] PD gains (b2_set_pd): hw_eff holds position targets when non-null
   int* pending;           // [1] environments that need the constraint pipeline this tick (B2F_FUSABLE); cleared by a
                           //     memset node in front of the smooth kernel
 };

@@ -254,7 +254,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_chain(const KArgs<T> a) {
 #pragma unroll
         for (int i = 0; i < N; i++) {
           if (!m.i(h.o_dof_controlled, i)) continue;
-          if (fabsf(hwv[i]) > 1e-15f) dqc[i] = (T)hwv[i]; else ddq[i] = (T)hwe[i];
+          if (fabsf(hwv[i]) > 1e-15f) dqc[i] = (T)hwv[i];
+          else ddq[i] = a.hw_kp ? (T)a.hw_kp[i] * ((T)hwe[i] - q[i]) - (T)a.hw_kd[i] * v[i] : (T)hwe[i];   // PD stage (b2_set_pd)
         }
       }
       mul_M(tau, ddq);

@@ -350,7 +350,8 @@ __global__ void __launch_bounds__(BLOCK) k_chain_team(const KArgs<T> a) {
         __syncthreads();
         if (ctl && env < a.nenv) {
           const float hwv = hwsh[l * EPB + (threadIdx.x >> 3)], hwe = hwsh[(8 + l) * EPB + (threadIdx.x >> 3)];
-          if (fabsf(hwv) > 1e-15f) dqc = (T)hwv; else ddq = (T)hwe;
+          if (fabsf(hwv) > 1e-15f) dqc = (T)hwv;
+          else ddq = a.hw_kp ? (T)a.hw_kp[l] * ((T)hwe - q) - (T)a.hw_kd[l] * v : (T)hwe;   // PD stage (b2_set_pd)
         }
       }
       T tau = mul_M(ddq);

@@ -87,6 +87,7 @@ _sig = {
     "b2_tick_host": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "b2_tick_resident": (_i, [_vp]),
     "b2_pack_obs": (_i, [_vp, _vp]),
+    "b2_set_pd": (_i, [_vp, _vp, _vp]),
     "b2_l2_flush": (_i, [_vp, C.c_longlong]),
     "b2_profile_begin": (_i, [_vp, _i]),
     "b2_profile_end": (_i, [_vp, _vp, _i]),
@@ -331,6 +332,15 @@ class Batch:
 
     def tick_host_raw(self, vel_ptr, eff_ptr, pos_ptr, velo_ptr, effo_ptr):
         self._ck(lib.b2_tick_host(self.ptr, vel_ptr, eff_ptr, pos_ptr, velo_ptr, effo_ptr), "b2_tick_host")
+
+    def set_pd(self, kp=None, kd=None):
+        """Device-side PD stage: the effort-command buffer then carries position targets (b2_set_pd)."""
+        if kp is None:
+            self._ck(lib.b2_set_pd(self.ptr, None, None), "b2_set_pd")
+            return
+        kp = np.ascontiguousarray(np.broadcast_to(np.asarray(kp, np.float32), (self.nhw,)))
+        kd = np.ascontiguousarray(np.broadcast_to(np.asarray(kd, np.float32), (self.nhw,)))
+        self._ck(lib.b2_set_pd(self.ptr, kp.ctypes.data, kd.ctypes.data), "b2_set_pd")
 
     def pack_obs(self, dev_ptr):
         """[qpos | qvel] as fp32 [nq + nv][nenv] into a device buffer (the payload of the per-tick all-gather)."""

@@ -11,7 +11,43 @@ CONFIGS = {
     "c1": ("pendulum_world.xml", 1, "pendulum world, 1 env (plumbing)"),
     "c2": ("panda7.xml", 4096, "Franka-Panda-like 7-DoF arm, contact-free forward dynamics"),
     "c3": ("ur5_tabletop.xml", 16384, "UR5-like arm + tabletop objects with contacts, PGS"),
+    "c4": ("pr2_like.xml", 8192, "PR2-shaped dual-arm robot (49 dofs, mimic-joint equalities, limits, wheel contacts) + PD computed-torque control"),
 }
+
+PR2_ARM_JOINTS = ["%s_%s_joint" % (s, j) for s in ("l", "r") for j in
+                  ("shoulder_pan", "shoulder_lift", "upper_arm_roll", "elbow_flex", "forearm_roll", "wrist_flex", "wrist_roll")]
+
+
+def control_spec(cfg, model):
+    """(hardware joint ids, per-dof controlled mask, kp, kd) of a config's control tick.  c2 / c3: every scalar joint is
+    a ros_control joint commanded with a desired acceleration.  c4: the 14 arm joints under PD computed-torque control,
+    ddq = 200 (q* - q) - 50 qdot (gains of the reference's PID config, model/ontology/box/box.yaml:5-13, i = 0)."""
+    jt = np.array(model.jnt_type)
+    if cfg == "c4":
+        hw = np.array([model.name2id(engine.OBJ_JOINT, n) for n in PR2_ARM_JOINTS], np.int32)
+        kp, kd = np.full(hw.size, 200.0, np.float32), np.full(hw.size, 50.0, np.float32)
+    else:
+        hw = np.where(jt >= 2)[0].astype(np.int32)
+        kp = kd = None
+    ctl = np.zeros(model.nv, np.uint8)
+    ctl[np.array(model.jnt_dofadr)[hw]] = 1
+    return hw, ctl, kp, kd
+
+
+def commands(cfg, model, envs):
+    """Effort-command buffer [nenv][nhw] of the config: desired accelerations 0.1 * (the config's random torques) for
+    c2 / c3, position targets (mid-range +- 0.3 rad) for the PD-controlled arms of c4."""
+    hw, _, kp, _ = control_spec(cfg, model)
+    dadr = np.array(model.jnt_dofadr)[hw]
+    if kp is None:
+        _, _, frc = config_state(cfg, model, envs)
+        return 0.1 * frc[:, dadr]
+    envs = np.asarray(envs)
+    rng = np.array(model.jnt_range).reshape(-1, 2)[hw]
+    lim = np.array(model.jnt_limited)[hw] != 0
+    mid = np.where(lim, 0.5 * (rng[:, 0] + rng[:, 1]), 0.0)
+    u = uniform(0xB204 + 99, envs[:, None], np.arange(hw.size)[None, :])
+    return mid[None, :] + (2 * u - 1) * 0.3
 
 
 def uniform(seed, env, idx):
@@ -79,6 +115,23 @@ def config_state(cfg, model, envs, seed=None):
         # props spread over the table (+-0.12 around their authored places, which are >= 0.2 m apart), dropped from
         # 5 mm of penetration to 8 cm of hover; arm torques are gentle so that it settles onto / around the table
         return random_state(model, envs, seed, vmax=0.5, fmax=5.0, free_xy=0.06, free_z=(-0.005, 0.08), ranges=UR5_RANGES)
+    if cfg == "c4":
+        # the robot is dropped onto its wheels from 0-25 cm at a random place / heading; arms near mid-range, everything
+        # else at its authored pose (the gripper couplings are satisfied there); at rest
+        envs = np.asarray(envs)
+        nenv = envs.size
+        q = np.tile(np.array(model.qpos0), (nenv, 1))
+        u = uniform(seed, envs[:, None], np.arange(model.nq)[None, :])
+        q[:, 0] += (2 * u[:, 0] - 1); q[:, 1] += (2 * u[:, 1] - 1); q[:, 2] += 0.25 * u[:, 2]
+        yaw = (2 * u[:, 3] - 1) * np.pi
+        q[:, 3] = np.cos(yaw / 2); q[:, 4:6] = 0; q[:, 6] = np.sin(yaw / 2)
+        rngs = np.array(model.jnt_range).reshape(-1, 2)
+        for n in PR2_ARM_JOINTS:
+            j = model.name2id(engine.OBJ_JOINT, n)
+            a = int(model.jnt_qposadr[j])
+            mid = 0.5 * (rngs[j, 0] + rngs[j, 1]) if model.jnt_limited[j] else 0.0
+            q[:, a] = mid + (2 * u[:, a] - 1) * 0.2
+        return q, np.zeros((nenv, model.nv)), np.zeros((nenv, model.nv))
     if cfg == "c1":
         q = np.tile(np.array(model.qpos0), (np.asarray(envs).size, 1))
         return q, np.zeros((q.shape[0], model.nv)), np.zeros((q.shape[0], model.nv))

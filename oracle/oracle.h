@@ -66,6 +66,9 @@ void omj_tick(const mjModel* m, mjData* d, mjtNum* ddq, mjtNum* dq, const mjtByt
 int omj_tick_batch(const mjModel* m, mjData** pool, int npool, int nenv, int nsteps, mjtNum* qpos, mjtNum* qvel,
                    mjtNum* qacc_warmstart, const mjtNum* qfrc_applied, const mjtNum* ddq, const mjtNum* dq,
                    const mjtByte* controlled, int do_inverse, mjtNum* qfrc_inverse_out);
+int omj_tick_batch_pd(const mjModel* m, mjData** pool, int npool, int nenv, int nsteps, mjtNum* qpos, mjtNum* qvel,
+                   mjtNum* qacc_warmstart, const mjtNum* qfrc_applied, const mjtNum* ddq, const mjtNum* dq,
+                   const mjtByte* controlled, int do_inverse, mjtNum* qfrc_inverse_out, const mjtNum* pd_kp, const mjtNum* pd_kd);
 
 #ifdef __cplusplus
 }

@@ -91,9 +91,12 @@ void omj_tick(const mjModel* m, mjData* d, mjtNum* ddq, mjtNum* dq, const mjtByt
   omj_step2(m, d);
 }
 
-int omj_tick_batch(const mjModel* m, mjData** pool, int npool, int nenv, int nsteps, mjtNum* qpos, mjtNum* qvel,
-                   mjtNum* qacc_warmstart, const mjtNum* qfrc_applied, const mjtNum* ddq, const mjtNum* dq,
-                   const mjtByte* controlled, int do_inverse, mjtNum* qfrc_inverse_out) {
+// pd_kp / pd_kd ([nv], optional): dofs with a non-zero gain take ddq as a position TARGET and are commanded
+// kp (target - q) - kd qdot every tick — what the reference's ros_control PID controllers feed into write()
+// (gains: model/ontology/box/box.yaml:5-13); mirrors b2_set_pd of the CUDA engine.
+int omj_tick_batch_pd(const mjModel* m, mjData** pool, int npool, int nenv, int nsteps, mjtNum* qpos, mjtNum* qvel,
+                      mjtNum* qacc_warmstart, const mjtNum* qfrc_applied, const mjtNum* ddq, const mjtNum* dq,
+                      const mjtByte* controlled, int do_inverse, mjtNum* qfrc_inverse_out, const mjtNum* pd_kp, const mjtNum* pd_kd) {
   const int nq = m->nq, nv = m->nv;
   const int used = std::max(1, std::min(npool, nenv));
   auto work = [&](int tid) {
@@ -113,6 +116,12 @@ int omj_tick_batch(const mjModel* m, mjData** pool, int npool, int nenv, int nst
         if (ctl) {  // the same command is re-issued every tick (write() runs every tick in the reference)
           copy(c_ddq.data(), ddq + (size_t)e * nv, nv);
           copy(c_dq.data(), dq + (size_t)e * nv, nv);
+          if (pd_kp && pd_kd)
+            for (int i = 0; i < nv; i++) {
+              if (pd_kp[i] == 0 && pd_kd[i] == 0) continue;
+              const int j = m->dof_jntid[i];
+              c_ddq[i] = pd_kp[i] * (c_ddq[i] - d->qpos[m->jnt_qposadr[j]]) - pd_kd[i] * d->qvel[i];
+            }
         }
         omj_tick(m, d, ctl ? c_ddq.data() : nullptr, ctl ? c_dq.data() : nullptr, controlled, do_inverse);
       }
@@ -127,4 +136,11 @@ int omj_tick_batch(const mjModel* m, mjData** pool, int npool, int nenv, int nst
   for (int t = 0; t < used; t++) th.emplace_back(work, t);
   for (auto& t : th) t.join();
   return used;
+}
+
+int omj_tick_batch(const mjModel* m, mjData** pool, int npool, int nenv, int nsteps, mjtNum* qpos, mjtNum* qvel,
+                   mjtNum* qacc_warmstart, const mjtNum* qfrc_applied, const mjtNum* ddq, const mjtNum* dq,
+                   const mjtByte* controlled, int do_inverse, mjtNum* qfrc_inverse_out) {
+  return omj_tick_batch_pd(m, pool, npool, nenv, nsteps, qpos, qvel, qacc_warmstart, qfrc_applied, ddq, dq, controlled, do_inverse,
+                           qfrc_inverse_out, nullptr, nullptr);
 }

@@ -8,7 +8,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liboracle.so")
 if not os.path.exists(LIB_PATH):
-    raise ImportError(LIB_PATH + " is missing: build it with `python -m mujoco_sim_b200.build`")
+    raise ImportError(LIB_PATH + " is missing: build it with `python mujoco_sim_b200/build.py`")
 olib = C.CDLL(LIB_PATH)
 _vp, _i = C.c_void_p, C.c_int
 for _n in ["omj_kinematics", "omj_comPos", "omj_crb", "omj_factorM", "omj_collision", "omj_makeConstraint",
@@ -35,6 +35,8 @@ olib.omj_tick.restype = None
 olib.omj_tick.argtypes = [_vp, _vp, _vp, _vp, _vp, _i]
 olib.omj_tick_batch.restype = _i
 olib.omj_tick_batch.argtypes = [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]
+olib.omj_tick_batch_pd.restype = _i
+olib.omj_tick_batch_pd.argtypes = [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]
 olib.omj_pair_supported.restype = _i
 olib.omj_pair_supported.argtypes = [_i, _i]
 
@@ -75,11 +77,14 @@ def rne(model, data, flg_acc):
 
 
 def tick_batch(model, pool, nsteps, qpos, qvel, qacc_warmstart=None, qfrc_applied=None, ddq=None, dq=None, controlled=None,
-               do_inverse=False, qfrc_inverse_out=None):
-    """Advance every row of qpos/qvel ([nenv][n] float64, updated in place) nsteps ticks; one thread per pool entry."""
+               do_inverse=False, qfrc_inverse_out=None, pd_kp=None, pd_kd=None):
+    """Advance every row of qpos/qvel ([nenv][n] float64, updated in place) nsteps ticks; one thread per pool entry.
+    pd_kp / pd_kd ([nv] float64): dofs with a non-zero gain read ddq as a position target (PD stage, b2_set_pd)."""
     arr = (C.c_void_p * len(pool))(*[d.ptr for d in pool])
     nenv = qpos.shape[0]
     for a in (qpos, qvel, qacc_warmstart, qfrc_applied, ddq, dq, qfrc_inverse_out):
         assert a is None or (a.dtype == np.float64 and a.flags.c_contiguous)
-    return olib.omj_tick_batch(model.ptr, arr, len(pool), nenv, nsteps, _p(qpos), _p(qvel), _p(qacc_warmstart), _p(qfrc_applied),
-                               _p(ddq), _p(dq), _p(controlled), int(do_inverse), _p(qfrc_inverse_out))
+    for a in (pd_kp, pd_kd):
+        assert a is None or (a.dtype == np.float64 and a.flags.c_contiguous and a.size == model.nv)
+    return olib.omj_tick_batch_pd(model.ptr, arr, len(pool), nenv, nsteps, _p(qpos), _p(qvel), _p(qacc_warmstart), _p(qfrc_applied),
+                                  _p(ddq), _p(dq), _p(controlled), int(do_inverse), _p(qfrc_inverse_out), _p(pd_kp), _p(pd_kd))

@@ -507,3 +507,42 @@ def test_pack_obs_is_the_state_in_native_layout(b2):
     with pytest.raises(b2.B2Error, match="device memory"):
         bt.pack_obs(np.zeros(4, np.float32).ctypes.data)
     bt.close()
+
+
+def test_c4_pr2_like_pd_control_tick_matches_oracle(b2, orc):
+    """C4 (BASELINE configs[3]): PR2-shaped robot — one 49-dof tree, 8 mimic-joint equalities, joint limits, condim-4
+    wheel contacts — dropped onto the floor under device-side PD computed-torque control of the 14 arm joints
+    (b2_set_pd), through the control tick with host buffers.  fp64 batch == fp64 oracle tick (with the oracle's PD
+    stage) on state, efforts, contact counts and row counts; the fp32 product path stays within a written tolerance."""
+    from mujoco_sim_b200 import workloads as w
+    m = b2.Model(b2.asset("pr2_like.xml"))
+    assert (m.nq, m.nv) == (50, 49)
+    nenv, steps = 12, 40
+    hw, ctl, kp, kd = w.control_spec("c4", m)
+    dadr = np.array(m.jnt_dofadr)[hw]
+    q0, v0, _ = w.config_state("c4", m, np.arange(nenv))
+    q0[:, 2] = m.qpos0[2] + 0.01 * np.arange(nenv) / nenv        # close to the floor: wheel contacts within the run
+    tgt = w.commands("c4", m, np.arange(nenv))
+    # oracle
+    rq, rv = np.ascontiguousarray(q0).copy(), np.ascontiguousarray(v0).copy()
+    ws = np.zeros((nenv, m.nv)); ddq = np.zeros((nenv, m.nv)); ddq[:, dadr] = tgt
+    kpv, kdv = np.zeros(m.nv), np.zeros(m.nv); kpv[dadr], kdv[dadr] = kp, kd
+    finv = np.zeros((nenv, m.nv))
+    orc.tick_batch(m, [b2.Data(m)], steps, rq, rv, ws, None, ddq, np.zeros((nenv, m.nv)), ctl, True, finv, pd_kp=kpv, pd_kd=kdv)
+    for prec, tol in [(b2.engine.F64, 1e-7), (b2.engine.F32, 2e-3)]:
+        bt = b2.Batch(m, nenv, precision=prec)
+        bt.set("qpos", q0); bt.set("qvel", v0)
+        bt.set_controlled(ctl); bt.set_hw_joints(hw); bt.set_pd(kp, kd)
+        vel = np.zeros((hw.size, nenv), np.float32); eff = np.ascontiguousarray(tgt.T.astype(np.float32))
+        out = [np.zeros((hw.size, nenv), np.float32) for _ in range(3)]
+        for _ in range(steps):
+            bt.tick_host_raw(vel.ctypes.data, eff.ctypes.data, *[o.ctypes.data for o in out])
+        gq, gv = bt.get("qpos"), bt.get("qvel")
+        assert bt.get("nefc").max() >= 8 + 6 and bt.get("ncon").max() >= 4   # equalities + wheel contacts were active
+        # fp32 targets are rounded once on upload: compare against the same rounding in the tolerance
+        np.testing.assert_allclose(gq, rq, atol=tol * 5 if prec == b2.engine.F64 else tol * 5, err_msg="qpos prec %d" % prec)
+        np.testing.assert_allclose(gv, rv, atol=tol * 200, err_msg="qvel prec %d" % prec)
+        np.testing.assert_allclose(out[0].T, gq[:, np.array(m.jnt_qposadr)[hw]], atol=1e-6)
+        scale = max(1.0, np.abs(finv[:, dadr]).max())
+        np.testing.assert_allclose(out[2].T, finv[:, dadr], atol=(1e-5 if prec == b2.engine.F64 else 2e-2) * scale)
+        bt.close()
