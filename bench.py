@@ -23,7 +23,7 @@ if ROOT not in sys.path:
 import numpy as np  # noqa: E402
 
 METRIC, UNIT = "env_steps_per_sec", "env-steps/s"
-SETTLE_TICKS = {"c1": 0, "c2": 0, "c3": 150, "c4": 150}
+SETTLE_TICKS = {"c1": 0, "c2": 0, "c3": 150, "c4": 150, "c5": 120}
 
 
 def peaks():
@@ -98,6 +98,8 @@ def cpu_reference(cfg, nenv_sample, steps, warmup, threads=None):
     qpos, qvel, frc = w.config_state(cfg, m, np.arange(nenv_sample))
     qpos = np.ascontiguousarray(qpos); qvel = np.ascontiguousarray(qvel)
     ws = np.zeros((nenv_sample, m.nv))
+    if cfg == "c5":
+        return cpu_reference_c5(m, pool, qpos, qvel, steps, warmup)
     hw, ctl, kp, kd = w.control_spec(cfg, m)
     dadr = np.array(m.jnt_dofadr)[hw]
     ddq = np.zeros((nenv_sample, m.nv))
@@ -117,6 +119,53 @@ def cpu_reference(cfg, nenv_sample, steps, warmup, threads=None):
     used = orc.tick_batch(m, pool, steps, qpos, qvel, ws, None, ddq, dq, ctl, True, **pd)
     dt = time.perf_counter() - t0
     return nenv_sample * steps / dt, used, dt
+
+
+def cpu_reference_c5(m, pool, qpos, qvel, steps, warmup):
+    """C5 on the CPU: the same request stream (8 of 20 slots live, one destroy + one spawn per environment every 60
+    ticks) applied to the oracle's state arrays between chunks of ticks; inactive slots are put back to their parking
+    place at every chunk boundary."""
+    from mujoco_sim_b200 import workloads as w
+    from oracle import pyoracle as orc
+    nenv = qpos.shape[0]
+    envs = np.arange(nenv)
+    slots = w.c5_slot_bodies(m)
+    qadr = np.array([m.jnt_qposadr[m.body_jntadr[b]] for b in slots]); dadr = np.array([m.jnt_dofadr[m.body_jntadr[b]] for b in slots])
+    live = np.zeros((nenv, w.NSLOT_C5), bool)
+    ws = np.zeros((nenv, m.nv))
+
+    def park():
+        for s in range(w.NSLOT_C5):
+            off = ~live[:, s]
+            qpos[off, qadr[s]:qadr[s] + 7] = w.park_pose(s); qvel[off, dadr[s]:dadr[s] + 6] = 0; ws[off, dadr[s]:dadr[s] + 6] = 0
+
+    def spawn(k):
+        s = (envs + 3 * k) % w.NSLOT_C5
+        pose = w.c5_spawn_pose(envs, k)
+        for e in range(nenv):
+            qpos[e, qadr[s[e]]:qadr[s[e]] + 7] = pose[e]; qvel[e, dadr[s[e]]:dadr[s[e]] + 6] = 0; live[e, s[e]] = True
+    park()
+    for k in range(w.C5_INITIAL):
+        spawn(k)
+    rnd = 0
+
+    def run(n):
+        nonlocal rnd
+        used = 1
+        done = 0
+        while done < n:
+            c = min(60, n - done)
+            used = orc.tick_batch(m, pool, c, qpos, qvel, ws)
+            done += c
+            if c == 60:
+                live[envs, (envs + 3 * rnd) % w.NSLOT_C5] = False
+                park(); spawn(rnd + w.C5_INITIAL); rnd += 1
+        return used
+    run(SETTLE_TICKS["c5"] + warmup)
+    t0 = time.perf_counter()
+    used = run(steps)
+    dt = time.perf_counter() - t0
+    return nenv * steps / dt, used, dt
 
 
 def drift_report(cfg, nenv=64, horizons=(1, 10, 100, 1000)):
@@ -169,7 +218,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--config", default=os.environ.get("B2_BENCH_CONFIG", "c2"), choices=["c2", "c3", "c4"])
+    ap.add_argument("--config", default=os.environ.get("B2_BENCH_CONFIG", "c2"), choices=["c2", "c3", "c4", "c5"])
     ap.add_argument("--nenv", type=int, default=0, help="environments per GPU (default: the config's)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -226,19 +275,39 @@ def main():
     w.load_config(args.config, bt, env_offset=env_offset)
     # hardware joints, controlled dofs, PD gains and the command buffer of the config (workloads.control_spec)
     hw, ctl, kp, kd = w.control_spec(args.config, m)
-    bt.set_controlled(ctl)
-    bt.set_hw_joints(hw)
-    if kp is not None:
-        bt.set_pd(kp, kd)
     nhw = hw.size
-    cmd = w.commands(args.config, m, np.arange(env_offset, env_offset + nenv))
-    eff_cmd = torch.from_numpy(np.ascontiguousarray(cmd.T.astype(np.float32))).pin_memory()
-    vel_cmd = torch.zeros((nhw, nenv), dtype=torch.float32).pin_memory()
-    pos_o = torch.empty((nhw, nenv), dtype=torch.float32).pin_memory()
-    vel_o = torch.empty_like(pos_o).pin_memory()
-    eff_o = torch.empty_like(pos_o).pin_memory()
-    host_args = (vel_cmd.data_ptr(), eff_cmd.data_ptr(), pos_o.data_ptr(), vel_o.data_ptr(), eff_o.data_ptr())
-    bt.write_commands(vel_cmd.numpy(), eff_cmd.numpy())  # uploads the commands once: they stay resident in HBM for the device-timed loop
+    slots = args.config == "c5"   # no ros_control joints: the host exchange of this config is spawn / destroy requests in, body poses out
+    if not slots:
+        bt.set_controlled(ctl)
+        bt.set_hw_joints(hw)
+        if kp is not None:
+            bt.set_pd(kp, kd)
+        cmd = w.commands(args.config, m, np.arange(env_offset, env_offset + nenv))
+        eff_cmd = torch.from_numpy(np.ascontiguousarray(cmd.T.astype(np.float32))).pin_memory()
+        vel_cmd = torch.zeros((nhw, nenv), dtype=torch.float32).pin_memory()
+        pos_o = torch.empty((nhw, nenv), dtype=torch.float32).pin_memory()
+        vel_o = torch.empty_like(pos_o).pin_memory()
+        eff_o = torch.empty_like(pos_o).pin_memory()
+        host_args = (vel_cmd.data_ptr(), eff_cmd.data_ptr(), pos_o.data_ptr(), vel_o.data_ptr(), eff_o.data_ptr())
+        bt.write_commands(vel_cmd.numpy(), eff_cmd.numpy())  # uploads the commands once: they stay resident in HBM for the device-timed loop
+        tick_resident = bt.tick_resident
+        h2d, d2h = 2 * nhw * nenv * 4, 3 * nhw * nenv * 4
+
+        def tick_e2e(k):
+            bt.tick_host_raw(*host_args)
+    else:
+        w.c5_init(bt, env_offset)
+        churn = {"round": 0}
+        tick_resident = lambda: bt.step(1)   # noqa: E731
+        # per tick: body poses out (what the ROS layer publishes); every 60 ticks one destroy + one spawn per environment in
+        h2d, d2h = (2 * 2 * 4 + 7 * 4) * nenv // 60, 3 * m.nbody * nenv * 4
+
+        def tick_e2e(k):
+            if k % 60 == 0:
+                w.c5_churn(bt, churn["round"], env_offset); churn["round"] += 1
+            bt.step(1)
+            pos_o = bt.get("xpos", dtype=np.float32)   # synchronises
+            return pos_o
 
     stream = torch.cuda.ExternalStream(bt.stream, device=torch.device("cuda", local_rank))
     flush = not args.no_flush
@@ -262,7 +331,7 @@ def main():
 
     # settle (contacts form) + warm-up, untimed
     for _ in range(SETTLE_TICKS[args.config] + args.warmup):
-        bt.tick_resident()
+        tick_resident()
     bt.sync()
     ncon_mean = float(bt.get("ncon").mean()) if m.npair > 0 else 0.0
     nefc_mean = float(bt.get("nefc").mean())
@@ -278,7 +347,7 @@ def main():
     for k in range(K):
         do_flush()
         starts[k].record(stream)
-        bt.tick_resident()          # the tick kernels (one launch for a limit-only chain, else a CUDA-graph replay)
+        tick_resident()             # the tick kernels (one launch for a limit-only chain, else a CUDA-graph replay)
         exchange()
         ends[k].record(stream)
     bt.sync(); torch.cuda.synchronize()
@@ -286,7 +355,7 @@ def main():
     bt.profile_begin(K)
     for k in range(K):
         do_flush()
-        bt.tick_resident()
+        tick_resident()
     bt.sync(); torch.cuda.synchronize()
     nprof, slot_ms = bt.profile_end()
     clocks = sampler.stop()
@@ -305,7 +374,7 @@ def main():
         do_flush()
         bt.sync()
         t0 = time.perf_counter()
-        bt.tick_host_raw(*host_args)
+        last = tick_e2e(k)
         if gather:
             exchange()
             stream.synchronize()
@@ -314,7 +383,7 @@ def main():
     if dist is not None:
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
     e2e_max = float(t2.item())
-    _ = float(pos_o.sum())  # the result is read on the host
+    _ = float(last.sum()) if slots else float(pos_o.sum())  # the result is read on the host
 
     if rank != 0:
         if dist is not None:
@@ -342,7 +411,8 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
         "ms_per_step": max_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "%s: %s" % (args.config, desc), "model": asset, "envs_per_gpu": nenv, "envs_total": total_envs,
-                   "timestep": 0.005, "tick": "write+step1+controller+inverse+step2+read" + (" with device-side PD (kp 200, kd 50) on %d arm joints" % nhw if kp is not None else ""), "mean_ncon": ncon_mean, "mean_nefc": nefc_mean,
+                   "timestep": 0.005, "tick": ("step1+step2 with 8 of 20 object slots live per environment; one destroy + one spawn per environment every 60 ticks in the end-to-end loop" if slots else
+                            "write+step1+controller+inverse+step2+read" + (" with device-side PD (kp 200, kd 50) on %d arm joints" % nhw if kp is not None else "")), "mean_ncon": ncon_mean, "mean_nefc": nefc_mean,
                    "l2": "flushed before every timed step (256 MiB memset)" if flush else "not flushed",
                    "solver": "PGS, %d iterations max" % int(m.int("opt.iterations")), "kernels": bt.path_name,
                    "obs_allgather": ("NCCL all_gather of [qpos|qvel] fp32, %d B per rank per tick, inside the timed region" % (4 * nobs * nenv)) if gather else "none: shards are independent, no data-path collective"},
@@ -351,16 +421,17 @@ def main():
                      "kernel_timing": "CUDA events between the kernels, same K ticks re-run eagerly right after the graph-replayed timed loop",
                      "kernel_ms": dom_ms, "kernel_share_of_step": kern[dom] / max(1e-12, sum(slot_ms.values())),
                      "kernel_ms_all": {k: v / max(1, nprof) for k, v in slot_ms.items()}},
-        "e2e": {"value": total_envs * K / e2e_max, "unit": UNIT, "h2d_bytes_per_step": int(2 * nhw * nenv * 4 * world),
-                "d2h_bytes_per_step": int(3 * nhw * nenv * 4 * world), "ms_per_step": 1e3 * e2e_max / K},
+        "e2e": {"value": total_envs * K / e2e_max, "unit": UNIT, "h2d_bytes_per_step": int(h2d * world),
+                "d2h_bytes_per_step": int(d2h * world), "ms_per_step": 1e3 * e2e_max / K},
         "gpu_launches": int(launches),
         "clocks": clocks,
     }
     if not args.no_cpu_baseline and world == 1:
-        sample = {"c2": 4096, "c3": 2048, "c4": 1024}[args.config]
-        csteps = {"c2": 2000, "c3": 1500, "c4": 1000}[args.config]  # about 10 s of CPU work on 8 cores
+        sample = {"c2": 4096, "c3": 2048, "c4": 1024, "c5": 1024}[args.config]
+        csteps = {"c2": 2000, "c3": 1500, "c4": 1000, "c5": 600}[args.config]  # about 10 s of CPU work on 8 cores
         val, used, dt = cpu_reference(args.config, sample, csteps, 3)
-        out["drift"] = drift_report(args.config)
+        if not slots:
+            out["drift"] = drift_report(args.config)
         out["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": used, "kind": "port",
                                "sample": "%d envs x %d ticks of the same workload in %.1f s; fp64 oracle restatement of MuJoCo 2.3.7 semantics "
                                          "(libmujoco is not available)" % (sample, csteps, dt)}

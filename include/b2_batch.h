@@ -105,6 +105,22 @@ int b2_tick_host(b2_batch* b, const float* vel_cmd_host, const float* effort_cmd
  * HBM: no host<->device traffic, asynchronous (throughput with resident inputs) */
 int b2_tick_resident(b2_batch* b);
 
+/* Runtime spawn / destroy as SLOT ACTIVATION (reference: the spawn_objects / destroy_objects services re-author the
+ * world XML and reload the whole model with the simulation thread blocked, src/mujoco_sim/mj_ros.cpp:906-1428,
+ * mj_sim.cpp:465-558,573-710).  Here the model is compiled once with `nslot` free bodies that serve as object slots;
+ * every environment carries an active flag per slot.  An inactive slot is parked far above the scene at rest (it is
+ * held there after every tick, collides with nothing and produces no constraint rows), spawning writes a pose and a
+ * twist into the slot's free joint of one environment and activates it, destroying parks it again.
+ *   b2_set_slots     body ids of the slot bodies (each must carry exactly one free joint); all slots start ACTIVE
+ *   b2_spawn         n requests: env[i], slot[i], pose7[i] = x y z qw qx qy qz, twist6[i] = v(3) w(3) (NULL: at rest)
+ *   b2_destroy_slots n requests: env[i], slot[i]
+ *   b2_slot_active   read back the flags of environments [env_lo, env_hi) as [env][slot] bytes
+ * Host arrays; the requests are applied in order on the batch's stream before the next tick. */
+int b2_set_slots(b2_batch* b, int nslot, const int* body_ids);
+int b2_spawn(b2_batch* b, int n, const int* env, const int* slot, const float* pose7, const float* twist6);
+int b2_destroy_slots(b2_batch* b, int n, const int* env, const int* slot);
+int b2_slot_active(b2_batch* b, unsigned char* active, int env_lo, int env_hi);
+
 /* observation exchange ("at most one all-gather of observations per control tick"): pack
  * [qpos | qvel] of every environment of this shard as fp32, native layout [nq + nv][nenv], into the DEVICE buffer
  * obs_dev ((nq + nv) * nenv floats) on the batch's stream.  The collective itself is the caller's: one process per GPU,

@@ -297,6 +297,19 @@ int hw_write_async(b2_batch* b);  // k_hw_write from b->io_in
 int hw_read_async(b2_batch* b);   // k_hw_read into b->io_out
 enum { B2_TICK_HW = 1 << 20 };  // internal: run k_hw_write / k_hw_read around the tick kernels
 
+template <typename D>
+__global__ void k_hold_slots(D* qpos, D* qvel, D* qacc, D* qws, const unsigned char* active, const int* qadr, const int* dadr, int nslot, int nenv, int nenvp);
+template <typename T>
+int hold_slots(b2_batch* b) {
+  if (!b->nslot) return 0;
+  const long long tot = (long long)b->nslot * b->nenv;
+  const int th = 256, bl = (int)((tot + th - 1) / th);
+  k_hold_slots<T><<<bl, th, 0, b->stream>>>((T*)b->fields["qpos"].ptr, (T*)b->fields["qvel"].ptr, (T*)b->fields["qacc"].ptr,
+                                            (T*)b->fields["qacc_warmstart"].ptr, b->slot_active, b->slot_qadr, b->slot_dadr, b->nslot, b->nenv, b->nenvp);
+  b->launches++;
+  return 0;
+}
+
 template <typename T>
 int run_tick(b2_batch* b, int flags) {
   int kf = 0;
@@ -369,6 +382,7 @@ int run_tick(b2_batch* b, int flags) {
       b->launches += 2;
     }
   }
+  if (flags & B2_TICK_INTEGRATE) hold_slots<T>(b);   // inactive object slots go back to their parking place
   prof_mark(b, SLOT_HW_READ);
   if (flags & B2_TICK_HW) { if (hw_read_async(b) < 0) return -1; }
   CK(cudaGetLastError());
@@ -571,6 +585,46 @@ __global__ void k_reset(D* qpos, D* qvel, D* qacc, D* qws, D* qapp, D* time, con
     qvel[(long long)i * nenvp + e] = 0; qacc[(long long)i * nenvp + e] = 0; qws[(long long)i * nenvp + e] = 0; qapp[(long long)i * nenvp + e] = 0;
   }
   time[e] = 0;
+}
+
+// ---- object slots: an inactive slot rests at its parking place (x = 3 slot, y = 0, z = 1000 + 3 slot), far from the
+// scene and from the other parked slots, and is put back there after every tick ----
+template <typename D>
+__device__ __forceinline__ void park_slot(D* qpos, D* qvel, D* qacc, D* qws, int qa, int da, int slot, long long S, int e) {
+  const D pose[7] = {D(3 * slot), D(0), D(1000 + 3 * slot), D(1), D(0), D(0), D(0)};
+  for (int k = 0; k < 7; k++) qpos[(long long)(qa + k) * S + e] = pose[k];
+  for (int k = 0; k < 6; k++) { qvel[(long long)(da + k) * S + e] = 0; qacc[(long long)(da + k) * S + e] = 0; qws[(long long)(da + k) * S + e] = 0; }
+}
+template <typename D>
+__global__ void k_hold_slots(D* qpos, D* qvel, D* qacc, D* qws, const unsigned char* active, const int* qadr, const int* dadr, int nslot, int nenv, int nenvp) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)nslot * nenv) return;
+  const int s = (int)(idx / nenv), e = (int)(idx % nenv);
+  if (!active[(long long)s * nenvp + e]) park_slot(qpos, qvel, qacc, qws, qadr[s], dadr[s], s, nenvp, e);
+}
+// apply n spawn (pose != nullptr) or destroy requests in order; one thread, the requests of a control tick are few
+template <typename D>
+__global__ void k_slot_requests(D* qpos, D* qvel, D* qacc, D* qws, unsigned char* active, const int* qadr, const int* dadr, int nenvp,
+                                int n, const int* env, const int* slot, const float* pose7, const float* twist6) {
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {   // distinct (env, slot) per call are independent; duplicates: last writer wins per element
+    const int e = env[i], s = slot[i];
+    if (pose7) {
+      const int qa = qadr[s], da = dadr[s];
+      D q[4] = {(D)pose7[7 * i + 3], (D)pose7[7 * i + 4], (D)pose7[7 * i + 5], (D)pose7[7 * i + 6]};
+      D nrm = sqrt((double)(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]));
+      if (!(nrm > 1e-12)) { q[0] = 1; q[1] = q[2] = q[3] = 0; nrm = 1; }
+      for (int k = 0; k < 3; k++) qpos[(long long)(qa + k) * nenvp + e] = (D)pose7[7 * i + k];
+      for (int k = 0; k < 4; k++) qpos[(long long)(qa + 3 + k) * nenvp + e] = q[k] / nrm;
+      for (int k = 0; k < 6; k++) {
+        qvel[(long long)(da + k) * nenvp + e] = twist6 ? (D)twist6[6 * i + k] : D(0);
+        qacc[(long long)(da + k) * nenvp + e] = 0; qws[(long long)(da + k) * nenvp + e] = 0;
+      }
+      active[(long long)s * nenvp + e] = 1;
+    } else {
+      active[(long long)s * nenvp + e] = 0;
+      park_slot(qpos, qvel, qacc, qws, qadr[s], dadr[s], s, nenvp, e);
+    }
+  }
 }
 
 // observation pack for the per-tick all-gather: dst[(i) * nenv + e] = (i < nq ? qpos[i] : qvel[i - nq]) of environment e
@@ -796,6 +850,9 @@ void b2_destroy(b2_batch* b) {
   if (b->hw_buf) cudaFree(b->hw_buf);
   if (b->hw_kp) cudaFree(b->hw_kp);
   if (b->hw_kd) cudaFree(b->hw_kd);
+  if (b->slot_qadr) cudaFree(b->slot_qadr);
+  if (b->slot_dadr) cudaFree(b->slot_dadr);
+  if (b->slot_active) cudaFree(b->slot_active);
   if (b->flush_buf) cudaFree(b->flush_buf);
   for (auto& kv : b->registered) cudaHostUnregister(const_cast<void*>(kv.first));
   for (cudaEvent_t e : b->prof_ev) cudaEventDestroy(e);
@@ -1108,6 +1165,79 @@ int b2_tick_host(b2_batch* b, const float* vel, const float* eff, float* pos, fl
 int b2_tick_resident(b2_batch* b) {
   if (!b) return fail("b2_tick_resident: null batch");
   return tick_hw(b, nullptr, nullptr, nullptr, nullptr, nullptr, false);
+}
+
+int b2_set_slots(b2_batch* b, int nslot, const int* body_ids) {
+  if (!b || nslot < 0 || (nslot > 0 && !body_ids)) return fail("b2_set_slots: bad argument");
+  CK(cudaSetDevice(b->device));
+  drop_graphs(b);
+  CK(cudaStreamSynchronize(b->stream));
+  for (int** p : {&b->slot_qadr, &b->slot_dadr}) { if (*p) cudaFree(*p); *p = nullptr; }
+  if (b->slot_active) { cudaFree(b->slot_active); b->slot_active = nullptr; }
+  b->nslot = 0;
+  if (nslot == 0) return 0;
+  const mjModel* m = b->m;
+  std::vector<int> qadr(nslot), dadr(nslot);
+  for (int s = 0; s < nslot; s++) {
+    const int id = body_ids[s];
+    if (id < 1 || id >= m->nbody) return fail("b2_set_slots: body id out of range");
+    if (m->body_jntnum[id] != 1 || m->jnt_type[m->body_jntadr[id]] != mjJNT_FREE) return fail("b2_set_slots: a slot body must carry exactly one free joint");
+    qadr[s] = m->jnt_qposadr[m->body_jntadr[id]];
+    dadr[s] = m->jnt_dofadr[m->body_jntadr[id]];
+  }
+  CK(cudaMalloc(&b->slot_qadr, sizeof(int) * nslot));
+  CK(cudaMalloc(&b->slot_dadr, sizeof(int) * nslot));
+  CK(cudaMalloc(&b->slot_active, (size_t)nslot * b->nenvp));
+  CK(cudaMemcpy(b->slot_qadr, qadr.data(), sizeof(int) * nslot, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(b->slot_dadr, dadr.data(), sizeof(int) * nslot, cudaMemcpyHostToDevice));
+  CK(cudaMemset(b->slot_active, 1, (size_t)nslot * b->nenvp));
+  b->nslot = nslot;
+  return 0;
+}
+
+static int slot_requests(b2_batch* b, int n, const int* env, const int* slot, const float* pose7, const float* twist6, bool spawn) {
+  if (!b || n < 0 || (n > 0 && (!env || !slot)) || (spawn && n > 0 && !pose7)) return fail("b2_spawn / b2_destroy_slots: bad argument");
+  CK(cudaSetDevice(b->device));
+  if (!b->nslot) return fail("b2_spawn / b2_destroy_slots: call b2_set_slots first");
+  if (n == 0) return 0;
+  for (int i = 0; i < n; i++)
+    if (env[i] < 0 || env[i] >= b->nenv || slot[i] < 0 || slot[i] >= b->nslot) return fail("b2_spawn / b2_destroy_slots: environment or slot out of range");
+  // one staging block: env | slot | pose7 | twist6
+  const size_t bytes = (size_t)n * (2 * sizeof(int) + 13 * sizeof(float));
+  if (ensure_stage(b, bytes) < 0) return -1;
+  char* base = (char*)b->stage_dev;
+  int* d_env = (int*)base; int* d_slot = d_env + n;
+  float* d_pose = (float*)(d_slot + n); float* d_tw = d_pose + (size_t)7 * n;
+  CK(cudaMemcpyAsync(d_env, env, sizeof(int) * n, cudaMemcpyHostToDevice, b->stream));
+  CK(cudaMemcpyAsync(d_slot, slot, sizeof(int) * n, cudaMemcpyHostToDevice, b->stream));
+  if (spawn) CK(cudaMemcpyAsync(d_pose, pose7, sizeof(float) * 7 * n, cudaMemcpyHostToDevice, b->stream));
+  if (spawn && twist6) CK(cudaMemcpyAsync(d_tw, twist6, sizeof(float) * 6 * n, cudaMemcpyHostToDevice, b->stream));
+  auto P = [&](const char* nm) { return b->fields[nm].ptr; };
+  if (b->prec == 8)
+    k_slot_requests<double><<<1, 256, 0, b->stream>>>((double*)P("qpos"), (double*)P("qvel"), (double*)P("qacc"), (double*)P("qacc_warmstart"), b->slot_active,
+                                                      b->slot_qadr, b->slot_dadr, b->nenvp, n, d_env, d_slot, spawn ? d_pose : nullptr, spawn && twist6 ? d_tw : nullptr);
+  else
+    k_slot_requests<float><<<1, 256, 0, b->stream>>>((float*)P("qpos"), (float*)P("qvel"), (float*)P("qacc"), (float*)P("qacc_warmstart"), b->slot_active,
+                                                     b->slot_qadr, b->slot_dadr, b->nenvp, n, d_env, d_slot, spawn ? d_pose : nullptr, spawn && twist6 ? d_tw : nullptr);
+  b->launches++;
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(b->stream));   // the host arrays may be reused by the caller
+  return 0;
+}
+int b2_spawn(b2_batch* b, int n, const int* env, const int* slot, const float* pose7, const float* twist6) {
+  return slot_requests(b, n, env, slot, pose7, twist6, true);
+}
+int b2_destroy_slots(b2_batch* b, int n, const int* env, const int* slot) { return slot_requests(b, n, env, slot, nullptr, nullptr, false); }
+int b2_slot_active(b2_batch* b, unsigned char* active, int lo, int hi) {
+  if (!b || !active || lo < 0 || hi > b->nenv || lo >= hi) return fail("b2_slot_active: bad argument");
+  CK(cudaSetDevice(b->device));
+  if (!b->nslot) return fail("b2_slot_active: call b2_set_slots first");
+  CK(cudaStreamSynchronize(b->stream));
+  std::vector<unsigned char> tmp((size_t)b->nslot * b->nenvp);
+  CK(cudaMemcpy(tmp.data(), b->slot_active, tmp.size(), cudaMemcpyDeviceToHost));
+  for (int e = lo; e < hi; e++)
+    for (int s = 0; s < b->nslot; s++) active[(size_t)(e - lo) * b->nslot + s] = tmp[(size_t)s * b->nenvp + e];
+  return 0;
 }
 
 int b2_pack_obs(b2_batch* b, float* obs_dev) {

@@ -76,6 +76,10 @@ struct b2_batch {
   b2::KArgs<float> args_f{};
   b2::KArgs<double> args_d{};
   bool args_valid = false;
+  // object slots (b2_set_slots): runtime spawn / destroy as slot activation
+  int nslot = 0;
+  int *slot_qadr = nullptr, *slot_dadr = nullptr;  // [nslot] device: qpos / dof address of each slot's free joint
+  unsigned char* slot_active = nullptr;            // [nslot][nenvp] device
   // per-kernel CUDA-event profiling (b2_profile_begin / b2_profile_end)
   std::vector<cudaEvent_t> prof_ev;  // [max_ticks][B2_NSLOT + 1]
   std::vector<unsigned> prof_mask;   // which boundary events of each tick were recorded

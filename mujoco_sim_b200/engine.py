@@ -88,6 +88,10 @@ _sig = {
     "b2_tick_resident": (_i, [_vp]),
     "b2_pack_obs": (_i, [_vp, _vp]),
     "b2_set_pd": (_i, [_vp, _vp, _vp]),
+    "b2_set_slots": (_i, [_vp, _i, _vp]),
+    "b2_spawn": (_i, [_vp, _i, _vp, _vp, _vp, _vp]),
+    "b2_destroy_slots": (_i, [_vp, _i, _vp, _vp]),
+    "b2_slot_active": (_i, [_vp, _vp, _i, _i]),
     "b2_l2_flush": (_i, [_vp, C.c_longlong]),
     "b2_profile_begin": (_i, [_vp, _i]),
     "b2_profile_end": (_i, [_vp, _vp, _i]),
@@ -341,6 +345,28 @@ class Batch:
         kp = np.ascontiguousarray(np.broadcast_to(np.asarray(kp, np.float32), (self.nhw,)))
         kd = np.ascontiguousarray(np.broadcast_to(np.asarray(kd, np.float32), (self.nhw,)))
         self._ck(lib.b2_set_pd(self.ptr, kp.ctypes.data, kd.ctypes.data), "b2_set_pd")
+
+    # ---- runtime spawn / destroy as slot activation (b2_set_slots) ----
+    def set_slots(self, body_ids):
+        a = np.ascontiguousarray(body_ids, np.int32)
+        self._ck(lib.b2_set_slots(self.ptr, a.size, a.ctypes.data), "b2_set_slots")
+        self.nslot = a.size
+
+    def spawn(self, env, slot, pose7, twist6=None):
+        e = np.ascontiguousarray(env, np.int32); s = np.ascontiguousarray(slot, np.int32)
+        p = np.ascontiguousarray(np.broadcast_to(np.asarray(pose7, np.float32), (e.size, 7)))
+        t = None if twist6 is None else np.ascontiguousarray(np.broadcast_to(np.asarray(twist6, np.float32), (e.size, 6)))
+        self._ck(lib.b2_spawn(self.ptr, e.size, e.ctypes.data, s.ctypes.data, p.ctypes.data, None if t is None else t.ctypes.data), "b2_spawn")
+
+    def destroy_slots(self, env, slot):
+        e = np.ascontiguousarray(env, np.int32); s = np.ascontiguousarray(slot, np.int32)
+        self._ck(lib.b2_destroy_slots(self.ptr, e.size, e.ctypes.data, s.ctypes.data), "b2_destroy_slots")
+
+    def slot_active(self, env_lo=0, env_hi=None):
+        env_hi = self.nenv if env_hi is None else env_hi
+        out = np.zeros((env_hi - env_lo, self.nslot), np.uint8)
+        self._ck(lib.b2_slot_active(self.ptr, out.ctypes.data, env_lo, env_hi), "b2_slot_active")
+        return out
 
     def pack_obs(self, dev_ptr):
         """[qpos | qvel] as fp32 [nq + nv][nenv] into a device buffer (the payload of the per-tick all-gather)."""

@@ -12,6 +12,7 @@ CONFIGS = {
     "c2": ("panda7.xml", 4096, "Franka-Panda-like 7-DoF arm, contact-free forward dynamics"),
     "c3": ("ur5_tabletop.xml", 16384, "UR5-like arm + tabletop objects with contacts, PGS"),
     "c4": ("pr2_like.xml", 8192, "PR2-shaped dual-arm robot (49 dofs, mimic-joint equalities, limits, wheel contacts) + PD computed-torque control"),
+    "c5": ("multi_world.xml", 8192, "multi-robot world: 3 pendulum bobs + 20 object slots, run-time spawn / destroy as slot activation"),
 }
 
 PR2_ARM_JOINTS = ["%s_%s_joint" % (s, j) for s in ("l", "r") for j in
@@ -132,10 +133,64 @@ def config_state(cfg, model, envs, seed=None):
             mid = 0.5 * (rngs[j, 0] + rngs[j, 1]) if model.jnt_limited[j] else 0.0
             q[:, a] = mid + (2 * u[:, a] - 1) * 0.2
         return q, np.zeros((nenv, model.nv)), np.zeros((nenv, model.nv))
+    if cfg == "c5":
+        # bobs slightly off their authored pose (they swing), slots parked (c5_init spawns them)
+        envs = np.asarray(envs)
+        q = np.tile(np.array(model.qpos0), (envs.size, 1))
+        v = np.zeros((envs.size, model.nv))
+        v[:, :9] = (2 * uniform(seed, envs[:, None], np.arange(9)[None, :]) - 1) * 0.5
+        return q, v, np.zeros((envs.size, model.nv))
     if cfg == "c1":
         q = np.tile(np.array(model.qpos0), (np.asarray(envs).size, 1))
         return q, np.zeros((q.shape[0], model.nv)), np.zeros((q.shape[0], model.nv))
     return random_state(model, envs, seed)
+
+
+# ---- C5: object slots ----
+NSLOT_C5, C5_INITIAL = 20, 8
+
+
+def c5_slot_bodies(model):
+    return np.array([model.name2id(engine.OBJ_BODY, "slot_%02d" % s) for s in range(NSLOT_C5)], np.int32)
+
+
+def park_pose(slot):
+    """Where an inactive slot rests (the engine's parking place: csrc/batch.cu park_slot)."""
+    return np.array([3.0 * slot, 0.0, 1000.0 + 3.0 * slot, 1.0, 0.0, 0.0, 0.0])
+
+
+def c5_spawn_pose(envs, rnd):
+    """Spawn pose of round `rnd` for each environment: on a ring r ~ U(0.3, 1.2) around the pendulum anchor, z ~ U(0.3, 1.0),
+    random heading (test/test_spawn_and_destroy.py:28-54 spawns on a ring at z = 5; lower here so that objects land and pile
+    up within a benchmark run)."""
+    envs = np.asarray(envs)
+    u = uniform(0xB205 + 31 * rnd, envs[:, None], np.arange(5)[None, :])
+    r, al, yaw = 0.3 + 0.9 * u[:, 0], (2 * u[:, 1] - 1) * np.pi, (2 * u[:, 3] - 1) * np.pi
+    pose = np.zeros((envs.size, 7), np.float32)
+    pose[:, 0], pose[:, 1], pose[:, 2] = r * np.sin(al), r * np.cos(al), 0.3 + 0.7 * u[:, 2]
+    pose[:, 3], pose[:, 6] = np.cos(yaw / 2), np.sin(yaw / 2)
+    return pose
+
+
+def c5_init(batch, env_offset=0):
+    """All slots destroyed, then C5_INITIAL of them spawned per environment (slot = (env + 3 k) mod 20)."""
+    model = batch.model
+    batch.set_slots(c5_slot_bodies(model))
+    envs = np.arange(batch.nenv)
+    for s in range(NSLOT_C5):
+        batch.destroy_slots(envs, np.full(envs.size, s))
+    for k in range(C5_INITIAL):
+        batch.spawn(envs, (envs + env_offset + 3 * k) % NSLOT_C5, c5_spawn_pose(envs + env_offset, k))
+    return C5_INITIAL
+
+
+def c5_churn(batch, rnd, env_offset=0):
+    """One destroy + one spawn per environment (the reference test does this every 0.3 s: test_spawn_and_destroy.py:86-94):
+    the oldest live slot goes, the next free one in the cycle comes."""
+    envs = np.arange(batch.nenv)
+    g = envs + env_offset
+    batch.destroy_slots(envs, (g + 3 * rnd) % NSLOT_C5)
+    batch.spawn(envs, (g + 3 * (rnd + C5_INITIAL)) % NSLOT_C5, c5_spawn_pose(g, rnd + C5_INITIAL))
 
 
 def load_states(batch, gen, max_depth=0.01, max_rounds=8):

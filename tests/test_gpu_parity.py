@@ -546,3 +546,75 @@ def test_c4_pr2_like_pd_control_tick_matches_oracle(b2, orc):
         scale = max(1.0, np.abs(finv[:, dadr]).max())
         np.testing.assert_allclose(out[2].T, finv[:, dadr], atol=(1e-5 if prec == b2.engine.F64 else 2e-2) * scale)
         bt.close()
+
+
+def test_c5_spawn_destroy_slots_match_oracle(b2, orc):
+    """C5 (BASELINE configs[4]) and SURVEY row f2: run-time spawn / destroy as slot activation.  The fp64 batch, with
+    objects spawned into slots, left to fall and pile up, destroyed and re-spawned per environment, follows the oracle
+    stepping the same model with inactive slots held at their parking place; destroyed slots rest exactly there, produce
+    no contacts, and the flags read back."""
+    from mujoco_sim_b200 import workloads as w
+    m = b2.Model(b2.asset("multi_world.xml"))
+    assert (m.nq, m.nv) == (152, 129)
+    nenv = 10
+    slots = w.c5_slot_bodies(m)
+    qadr = np.array([m.jnt_qposadr[m.body_jntadr[b]] for b in slots]); dadr = np.array([m.jnt_dofadr[m.body_jntadr[b]] for b in slots])
+    q0, v0, _ = w.config_state("c5", m, np.arange(nenv))
+    bt = b2.Batch(m, nenv, precision=b2.engine.F64)
+    bt.set("qpos", q0); bt.set("qvel", v0)
+    w.c5_init(bt)
+    act = bt.slot_active()
+    assert act.sum(axis=1).tolist() == [w.C5_INITIAL] * nenv
+    with pytest.raises(b2.B2Error, match="out of range"):
+        bt.spawn([0], [99], np.zeros(7))
+
+    # oracle mirror of the same request stream
+    D = [b2.Data(m) for _ in range(nenv)]
+    live = np.zeros((nenv, w.NSLOT_C5), bool)
+
+    def hold(e):
+        for s in range(w.NSLOT_C5):
+            if not live[e, s]:
+                D[e].qpos[qadr[s]:qadr[s] + 7] = w.park_pose(s); D[e].qvel[dadr[s]:dadr[s] + 6] = 0
+                D[e].qacc[dadr[s]:dadr[s] + 6] = 0; D[e].qacc_warmstart[dadr[s]:dadr[s] + 6] = 0
+
+    def o_spawn(e, s, pose):
+        D[e].qpos[qadr[s]:qadr[s] + 7] = pose.astype(np.float64); D[e].qvel[dadr[s]:dadr[s] + 6] = 0
+        D[e].qacc[dadr[s]:dadr[s] + 6] = 0; D[e].qacc_warmstart[dadr[s]:dadr[s] + 6] = 0
+        live[e, s] = True
+    envs = np.arange(nenv)
+    for e in range(nenv):
+        D[e].qpos[:] = q0[e]; D[e].qvel[:] = v0[e]
+        hold(e)
+    for k in range(w.C5_INITIAL):
+        pose = w.c5_spawn_pose(envs, k)
+        for e in range(nenv):
+            o_spawn(e, (e + 3 * k) % w.NSLOT_C5, pose[e])
+    assert np.array_equal(live, act.astype(bool))
+
+    def run(nticks):
+        bt.step(nticks); bt.sync()
+        for e in range(nenv):
+            for _ in range(nticks):
+                orc.call("step", m, D[e]); hold(e)
+    run(70)
+    for rnd in range(2):
+        w.c5_churn(bt, rnd)
+        pose = w.c5_spawn_pose(envs, rnd + w.C5_INITIAL)
+        for e in range(nenv):
+            live[e, (e + 3 * rnd) % w.NSLOT_C5] = False; hold(e)
+            o_spawn(e, (e + 3 * (rnd + w.C5_INITIAL)) % w.NSLOT_C5, pose[e])
+        run(40)
+    gq, gv = bt.get("qpos"), bt.get("qvel")
+    rq = np.array([np.array(d.qpos) for d in D]); rv = np.array([np.array(d.qvel) for d in D])
+    assert np.array_equal(bt.slot_active().astype(bool), live)
+    assert bt.get("ncon").max() >= 3                                  # spawned objects did land on the floor / each other
+    # 150 ticks of impacts and piling: rounding differences (~1e-13 per tick) are amplified by the stiff contacts
+    np.testing.assert_allclose(gq, rq, atol=2e-4)
+    np.testing.assert_allclose(gv, rv, atol=2e-2)
+    assert np.median(np.abs(gq - rq)) < 1e-9
+    for e in range(nenv):
+        for s in range(w.NSLOT_C5):
+            if not live[e, s]:
+                assert np.array_equal(gq[e, qadr[s]:qadr[s] + 7], w.park_pose(s)) and not gv[e, dadr[s]:dadr[s] + 6].any()
+    bt.close()
