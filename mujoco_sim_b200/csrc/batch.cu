@@ -214,7 +214,8 @@ KArgs<T> build_args(b2_batch* b) {
   a.efc_id = I("efc_id"); a.efc_tree = I("efc_tree"); a.efc_J = R("efc_J"); a.efc_pos = R("efc_pos"); a.efc_margin = R("efc_margin");
   a.efc_frictionloss = R("efc_frictionloss"); a.efc_diagApprox = R("efc_diagApprox"); a.efc_R = R("efc_R"); a.efc_D = R("efc_D");
   a.efc_KBI = R("efc_KBI"); a.efc_vel = R("efc_vel"); a.efc_aref = R("efc_aref"); a.efc_b = R("efc_b"); a.efc_force = R("efc_force");
-  a.efc_ARdiag = R("efc_ARdiag"); a.efc_blocks = R("efc_blocks"); a.efc_nwords = I("efc_nwords"); a.env_order = I("env_order"); a.solver_iter = I("solver_iter"); a.status = I("status");
+  a.efc_ARdiag = R("efc_ARdiag"); a.efc_blocks = R("efc_blocks"); a.efc_nwords = I("efc_nwords"); a.env_order = I("env_order");
+  a.blk_row0 = I("blk_row0"); a.blk_off = I("blk_off"); a.nblk = I("nblk"); a.maxblk = I("_maxblk"); a.solver_iter = I("solver_iter"); a.status = I("status");
   a.pending = I("_pending");
   return a;
 }
@@ -262,11 +263,11 @@ int configure_constraint_kernels(b2_batch* b) {
     auto SA = [&](const void* fn, int need) { ok &= cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(need, 48 * 1024)) == cudaSuccess; };
     if (b->prec == 8) {
       SA((const void*)k_collide<double, 128>, need1); SA((const void*)k_integrate<double, 128>, need1);
-      SA((const void*)k_make_constraint<double, 128>, need2); SA((const void*)k_make_constraint<double, 32>, need2);
+      SA((const void*)k_make_rows<double, 128>, need1); SA((const void*)k_make_blocks<double, 128>, need2); SA((const void*)k_make_blocks<double, 32>, need2);
       SA((const void*)k_pgs_block<double, 4, 32, PGS_MINB>, need3); SA((const void*)k_pgs_block<double, 8, 32, PGS_MINB>, need3);
     } else {
       SA((const void*)k_collide<float, 128>, need1); SA((const void*)k_integrate<float, 128>, need1);
-      SA((const void*)k_make_constraint<float, 128>, need2); SA((const void*)k_make_constraint<float, 32>, need2);
+      SA((const void*)k_make_rows<float, 128>, need1); SA((const void*)k_make_blocks<float, 128>, need2); SA((const void*)k_make_blocks<float, 32>, need2);
       SA((const void*)k_pgs_block<float, 4, 32, PGS_MINB>, need3); SA((const void*)k_pgs_block<float, 8, 32, PGS_MINB>, need3);
     }
     if (!ok) return fail("cudaFuncSetAttribute failed");
@@ -362,9 +363,16 @@ int run_tick(b2_batch* b, int flags) {
     prof_mark(b, SLOT_COLLIDE);
     if (b->m->npair > 0) { k_collide<T, BL><<<g2, BL, sm, b->stream>>>(a); b->launches++; }
     prof_mark(b, SLOT_MAKE);
-    if (b->make_block == 128) k_make_constraint<T, 128><<<g2, 128, sm + (size_t)b->rec_max * 129 * sizeof(T), b->stream>>>(a);
-    else k_make_constraint<T, 32><<<std::max(1, std::min(b->nenvp / 32, b->nsm * 8)), 32, sm + (size_t)b->rec_max * 33 * sizeof(T), b->stream>>>(a);
-    b->launches += 1;
+    CK(cudaMemsetAsync(a.maxblk, 0, sizeof(int), b->stream));
+    k_make_rows<T, BL><<<g2, BL, sm, b->stream>>>(a);
+    {
+      // one thread per (block, environment); CTAs of block ordinals beyond this tick's largest count exit at once
+      const int mb = b->make_block;
+      const dim3 gb(std::max(1, std::min(b->nenvp / mb, b->nsm * 8)), b->hdr.njmax);
+      if (mb == 128) k_make_blocks<T, 128><<<gb, 128, sm + (size_t)b->rec_max * 129 * sizeof(T), b->stream>>>(a);
+      else k_make_blocks<T, 32><<<gb, 32, sm + (size_t)b->rec_max * 33 * sizeof(T), b->stream>>>(a);
+    }
+    b->launches += 2;
     if (!(flags & B2_TICK_NOSOLVE)) {
       prof_mark(b, SLOT_PGS);
       k_order_envs<256, 1024><<<1, 1024, 0, b->stream>>>(a.nefc, a.efc_nwords, a.env_order, b->nenvp, std::max(4, b->block_capw / 256), a.pending, b->fusable ? 1 : 0);
@@ -769,7 +777,7 @@ b2_batch* b2_create(const mjModel* m, int nenv, int device, int precision) {
         {"efc_type", njmax, 1}, {"efc_id", njmax, 1}, {"efc_tree", 2 * njmax, 1}, {"efc_J", njmax * b->hdr.wmax, 0}, {"efc_pos", njmax, 0}, {"efc_margin", njmax, 0},
         {"efc_frictionloss", njmax, 0}, {"efc_diagApprox", njmax, 0}, {"efc_R", njmax, 0}, {"efc_D", njmax, 0}, {"efc_KBI", 3 * njmax, 0},
         {"efc_vel", njmax, 0}, {"efc_aref", njmax, 0}, {"efc_b", njmax, 0}, {"efc_force", njmax, 0}, {"efc_ARdiag", njmax, 0},
-        {"efc_blocks", b->block_capw, 0}, {"efc_nwords", 1, 1}, {"env_order", 1, 1}};
+        {"efc_blocks", b->block_capw, 0}, {"efc_nwords", 1, 1}, {"env_order", 1, 1}, {"blk_row0", njmax, 1}, {"blk_off", njmax, 1}, {"nblk", 1, 1}, {"_maxblk", 1, 1}};
     specs.insert(specs.end(), more.begin(), more.end());
   }
   for (auto& s : specs)

@@ -63,6 +63,9 @@ struct KArgs {
   T* efc_blocks;          // [nenvp][block_capw] environment-major block records streamed by the solver (k_constraint.cuh)
   int* efc_nwords;        // [nenvp] words of efc_blocks in use
   int* env_order;         // [nenvp] visit order of the solver (k_order_envs)
+  int *blk_row0, *blk_off; // [njmax][nenvp] block table: first row / word offset of block i (k_make_rows -> k_make_blocks)
+  int* nblk;              // [nenvp] blocks of the environment
+  int* maxblk;            // [1] largest block count of this tick (cleared by a memset node in front of k_make_rows)
   int block_capw;         // words of efc_blocks per environment
   int stage_cap;          // words of an environment's records the solver keeps in shared memory
   int wp;                 // (unused) padded compact row width

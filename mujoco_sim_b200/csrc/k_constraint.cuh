@@ -418,17 +418,14 @@ __host__ __device__ inline int block_max_words(int nbmax, int wmax) {
   return s.len;
 }
 
-// K4 + K5 fused: rows, impedance, then per BLOCK: vel, aref, b, B = M^-1 J^T of the base directions by sparse
-// back-substitution inside the block's trees (in shared memory), the local matrix A, diag(AR) per row, and (for
-// mj_inverse) qfrc_inverse -= J^T f(qacc_prev).  A finished record leaves through a shared-memory transpose so that
-// every global store of the slab is a coalesced run.
+// K4: rows, impedance, and per BLOCK the cheap, inherently sequential part — vel, aref, b of every solver row, the
+// primal force of mj_inverse accumulated into qfrc_inverse in row order (deterministic), and the block table
+// (first row, word offset in the slab) that lets k_make_blocks work on all blocks of all environments at once.
+// One thread per environment.
 template <typename T, int BLOCK>
-__global__ void __launch_bounds__(BLOCK) k_make_constraint(const KArgs<T> a) {
+__global__ void __launch_bounds__(BLOCK) k_make_rows(const KArgs<T> a) {
   B2_KERNEL_PROLOGUE
-  constexpr int LDS = BLOCK + 1;  // +1: conflict-free both for per-thread columns and for the transposed reads
-  T* recsh = reinterpret_cast<T*>(smem_raw + 16 + (size_t)nwords * 4);  // [recmax][LDS]: one record per thread (column)
-  const int lane = threadIdx.x & 31, wbase = threadIdx.x & ~31;
-  const int capw = a.block_capw;
+  int wmaxblk = 0;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int env = tile * BLOCK + threadIdx.x;
     Rows<T> rows(m, a, env);
@@ -442,121 +439,174 @@ __global__ void __launch_bounds__(BLOCK) k_make_constraint(const KArgs<T> a) {
     }
     const int ne = rows.nefc, W = h.wmax;
     if (!done) a.nefc[env] = ne;
+    int r = 0, woff = 0, nblk = 0;
+    while (r < ne) {
+      BlockShape bs{};
+      const long long o = (long long)r * S + env;
+      bs.type = a.efc_type[o];
+      const int id = a.efc_id[o];
+      bs.nb = 1; bs.nrow = 1;
+      T fri[5] = {0, 0, 0, 0, 0};
+      if (bs.type == CN_CONTACT_PYRAMIDAL) {
+        bs.nb = a.coni[((long long)CI_DIM * h.nconmax + id) * S + env];
+        bs.nrow = 2 * (bs.nb - 1);
+        for (int k = 0; k < 5; k++) fri[k] = a.con[((long long)(CF_FRICTION + k) * h.nconmax + id) * S + env];
+      }
+      const Seg g = seg_of(m, a.efc_tree[((long long)2 * r) * S + env], a.efc_tree[((long long)2 * r + 1) * S + env]);
+      bs.s1 = g.s1; bs.n1 = g.n1; bs.s2 = g.s2; bs.w = g.n1 + g.n2;
+      bs.layout();
+      const int w = bs.w, nb = bs.nb;
+      T vel[6], js[6], jq[6];
+      for (int k = 0; k < nb; k++) {
+        T v0 = 0, s0 = 0, q0 = 0;
+        for (int e = 0; e < w; e++) {
+          const T j = a.efc_J[((long long)(r + k) * W + e) * S + env];
+          const long long d = (long long)bs.dof(e) * S + env;
+          v0 += j * a.qvel[d]; s0 += j * a.qacc_smooth[d]; q0 += j * a.qacc[d];
+        }
+        vel[k] = v0; js[k] = s0; jq[k] = q0;
+      }
+      const T R = a.efc_R[o], D = 1 / R, fl = a.efc_frictionloss[o];
+      T dsum[6] = {0, 0, 0, 0, 0, 0};
+      for (int rr = 0; rr < bs.nrow; rr++) {
+        const long long orr = (long long)(r + rr) * S + env;
+        const int k = nb > 1 ? rr / 2 + 1 : 0;
+        const T sm = nb > 1 ? ((rr & 1) ? -fri[k - 1] : fri[k - 1]) : T(0);
+        const T velr = vel[0] + sm * vel[k], jsr = js[0] + sm * js[k], jqr = jq[0] + sm * jq[k];
+        const T K = a.efc_KBI[((long long)0 * h.njmax + r + rr) * S + env], Bd = a.efc_KBI[((long long)1 * h.njmax + r + rr) * S + env];
+        const T imp = a.efc_KBI[((long long)2 * h.njmax + r + rr) * S + env];
+        const T aref = -Bd * velr - K * imp * (a.efc_pos[orr] - a.efc_margin[orr]);
+        a.efc_D[orr] = D; a.efc_vel[orr] = velr; a.efc_aref[orr] = aref; a.efc_b[orr] = jsr - aref;
+        if (a.flags & B2F_INVERSE) {
+          const T f = primal_force(bs.type, jqr - aref, D, R, fl);
+          dsum[0] += f;
+          if (nb > 1) dsum[k] += sm * f;
+        }
+      }
+      if (a.flags & B2F_INVERSE) {
+        for (int e = 0; e < w; e++) {
+          T s0 = 0;
+          for (int k = 0; k < nb; k++) s0 += dsum[k] * a.efc_J[((long long)(r + k) * W + e) * S + env];
+          if (s0 != 0) a.qfrc_inverse[(long long)bs.dof(e) * S + env] -= s0;
+        }
+      }
+      a.blk_row0[(long long)nblk * S + env] = r;
+      a.blk_off[(long long)nblk * S + env] = woff;
+      nblk++;
+      woff += bs.len; r += bs.nrow;
+    }
+    if (!done) { a.efc_nwords[env] = woff; a.nblk[env] = nblk; wmaxblk = max(wmaxblk, nblk); }
+    else a.nblk[env] = 0;
+  }
+  for (int o = 16; o > 0; o >>= 1) wmaxblk = max(wmaxblk, __shfl_xor_sync(0xffffffffu, wmaxblk, o));
+  if ((threadIdx.x & 31) == 0 && wmaxblk > 0) atomicMax(a.maxblk, wmaxblk);
+}
+
+// K5: the expensive, embarrassingly parallel part — one thread per (block, environment): B = M^-1 J^T of the block's base
+// directions by sparse back-substitution inside its trees (in shared memory), the local matrix A, the couplings between
+// the pyramid rows, diag(AR) per row, and the finished record, which leaves through a shared-memory transpose so that
+// every global store of the slab is a coalesced run.  grid.y = njmax (the most blocks an environment can have): CTAs
+// beyond the largest block count of this tick (maxblk, found by k_make_rows) exit at once.
+template <typename T, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_make_blocks(const KArgs<T> a) {
+  const int blk = blockIdx.y;
+  if (blk >= a.maxblk[0]) return;
+  B2_KERNEL_PROLOGUE
+  constexpr int LDS = BLOCK + 1;  // +1: conflict-free both for per-thread columns and for the transposed reads
+  T* recsh = reinterpret_cast<T*>(smem_raw + 16 + (size_t)nwords * 4);  // [recmax][LDS]: one record per thread (column)
+  const int lane = threadIdx.x & 31, wbase = threadIdx.x & ~31;
+  const int capw = a.block_capw;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int env = tile * BLOCK + threadIdx.x;
+    const int W = h.wmax;
     SArr<T> LD{a.qLD + env, S}, dinv{a.qLDiagInv + env, S};
     SArr<T> rec{recsh + threadIdx.x, LDS};
-    int r = 0, woff = 0;
-    while (__any_sync(0xffffffffu, r < ne)) {
-      BlockShape bs{};
-      const bool have = r < ne;
-      if (have) {
-        const long long o = (long long)r * S + env;
-        bs.type = a.efc_type[o];
-        const int id = a.efc_id[o];
-        bs.nb = 1; bs.nrow = 1;
-        T fri[5] = {0, 0, 0, 0, 0};
-        if (bs.type == CN_CONTACT_PYRAMIDAL) {
-          bs.nb = a.coni[((long long)CI_DIM * h.nconmax + id) * S + env];
-          bs.nrow = 2 * (bs.nb - 1);
-          for (int k = 0; k < 5; k++) fri[k] = a.con[((long long)(CF_FRICTION + k) * h.nconmax + id) * S + env];
-        }
-        const Seg g = seg_of(m, a.efc_tree[((long long)2 * r) * S + env], a.efc_tree[((long long)2 * r + 1) * S + env]);
-        bs.s1 = g.s1; bs.n1 = g.n1; bs.s2 = g.s2; bs.w = g.n1 + g.n2;
-        bs.layout();
-        const int w = bs.w, wq = bs.wq, nb = bs.nb;
-        T vel[6], js[6], jq[6];
-        for (int k = 0; k < nb; k++) {
-          T v0 = 0, s0 = 0, q0 = 0;
-          for (int e = 0; e < w; e++) {
-            const T j = a.efc_J[((long long)(r + k) * W + e) * S + env];
-            const long long d = (long long)bs.dof(e) * S + env;
-            v0 += j * a.qvel[d]; s0 += j * a.qacc_smooth[d]; q0 += j * a.qacc[d];
-            rec[bs.oJ + k * wq + e] = j;
-            rec[bs.oB + k * wq + e] = j;
-          }
-          for (int e = w; e < wq; e++) { rec[bs.oJ + k * wq + e] = 0; rec[bs.oB + k * wq + e] = 0; }
-          vel[k] = v0; js[k] = s0; jq[k] = q0;
-          // B_k = M^-1 J_k^T, one tree at a time (M is block diagonal over trees)
-          for (int sgm = 0; sgm < 2; sgm++) {
-            const int lo = sgm ? g.s2 : g.s1, n = sgm ? g.n2 : g.n1, base = bs.oB + k * wq + (sgm ? g.n1 : 0);
-            if (n == 0) continue;
-            for (int i = lo + n - 1; i >= lo; i--) {
-              const T xi = rec[base + i - lo];
-              if (xi == 0) continue;
-              int adr = m.i(h.o_dof_Madr, i) + 1;
-              for (int j = m.i(h.o_dof_parentid, i); j >= 0; j = m.i(h.o_dof_parentid, j)) rec[base + j - lo] -= LD[adr++] * xi;
-            }
-            for (int i = lo; i < lo + n; i++) rec[base + i - lo] *= dinv[i];
-            for (int i = lo; i < lo + n; i++) {
-              int adr = m.i(h.o_dof_Madr, i) + 1;
-              T xi = rec[base + i - lo];
-              for (int j = m.i(h.o_dof_parentid, i); j >= 0; j = m.i(h.o_dof_parentid, j)) xi -= LD[adr++] * rec[base + j - lo];
-              rec[base + i - lo] = xi;
-            }
-          }
-        }
-        // local matrix A = J_base B_base^T (symmetric), then the couplings between the pyramid rows
-        T A[6][6];
-        for (int k = 0; k < nb; k++)
-          for (int c = k; c < nb; c++) {
-            T s0 = 0;
-            for (int e = 0; e < w; e++) s0 += rec[bs.oJ + k * wq + e] * rec[bs.oB + c * wq + e];
-            A[k][c] = s0; A[c][k] = s0;
-          }
-        T A0[6], Ad[6];   // A[0][k] and A[k][k]: all the pyramid rows' diagonals need
-        for (int k = 0; k < nb; k++) { A0[k] = A[0][k]; Ad[k] = A[k][k]; }
-        if (nb > 1)
-          for (int r1 = 0; r1 < bs.nrow; r1++)
-            for (int r2 = r1 + 1; r2 < bs.nrow; r2++) {
-              const int k1 = r1 / 2 + 1, k2 = r2 / 2 + 1;
-              const T m1 = (r1 & 1) ? -fri[k1 - 1] : fri[k1 - 1], m2 = (r2 & 1) ? -fri[k2 - 1] : fri[k2 - 1];
-              rec[bs.aru(r1, r2)] = A[0][0] + m2 * A[0][k2] + m1 * (A[k1][0] + m2 * A[k1][k2]);
-            }
-        for (int k = 1; k < nb; k++) rec[bs.oMu + k - 1] = fri[k - 1];
-        const T R = a.efc_R[o], D = 1 / R, fl = a.efc_frictionloss[o];
-        T dsum[6] = {0, 0, 0, 0, 0, 0};
-        for (int rr = 0; rr < bs.nrow; rr++) {
-          const long long orr = (long long)(r + rr) * S + env;
-          const int k = nb > 1 ? rr / 2 + 1 : 0;
-          const T sm = nb > 1 ? ((rr & 1) ? -fri[k - 1] : fri[k - 1]) : T(0);
-          const T velr = vel[0] + sm * vel[k], jsr = js[0] + sm * js[k], jqr = jq[0] + sm * jq[k];
-          const T K = a.efc_KBI[((long long)0 * h.njmax + r + rr) * S + env], Bd = a.efc_KBI[((long long)1 * h.njmax + r + rr) * S + env];
-          const T imp = a.efc_KBI[((long long)2 * h.njmax + r + rr) * S + env];
-          const T aref = -Bd * velr - K * imp * (a.efc_pos[orr] - a.efc_margin[orr]);
-          const T Arr = (nb > 1 ? A0[0] + 2 * sm * A0[k] + sm * sm * Ad[k] : A0[0]) + R;
-          const T bb = jsr - aref;
-          a.efc_D[orr] = D; a.efc_vel[orr] = velr; a.efc_aref[orr] = aref; a.efc_b[orr] = bb; a.efc_ARdiag[orr] = Arr;
-          rec[bs.oAref + rr] = aref; rec[bs.oArr + rr] = Arr; rec[bs.oiA + rr] = 1 / Arr; rec[bs.ob + rr] = bb;
-          if (a.flags & B2F_INVERSE) {
-            const T f = primal_force(bs.type, jqr - aref, D, R, fl);
-            dsum[0] += f;
-            if (nb > 1) dsum[k] += sm * f;
-          }
-        }
-        if (a.flags & B2F_INVERSE) {
-          for (int e = 0; e < w; e++) {
-            T s0 = 0;
-            for (int k = 0; k < nb; k++) s0 += dsum[k] * rec[bs.oJ + k * wq + e];
-            if (s0 != 0) a.qfrc_inverse[(long long)bs.dof(e) * S + env] -= s0;
-          }
-        }
-        for (int q = bs.oA + (nb > 1 ? bs.nrow * (bs.nrow - 1) / 2 : 0); q < bs.oJ; q++) rec[q] = 0;
-        rec[BH_CODE] = enc_int(bs.type + 16 * nb + 256 * bs.nrow, T());
-        rec[BH_S1] = enc_int(bs.s1, T()); rec[BH_N1W] = enc_int(bs.n1 + 1024 * w, T()); rec[BH_S2] = enc_int(bs.s2, T());
-        rec[BH_R] = R; rec[BH_FL] = fl; rec[BH_LEN] = enc_int(bs.len, T()); rec[BH_ROW0] = enc_int(r, T());
+    const bool have = blk < a.nblk[env];
+    BlockShape bs{};
+    int woff = 0;
+    if (have) {
+      const int r = a.blk_row0[(long long)blk * S + env];
+      woff = a.blk_off[(long long)blk * S + env];
+      const long long o = (long long)r * S + env;
+      bs.type = a.efc_type[o];
+      const int id = a.efc_id[o];
+      bs.nb = 1; bs.nrow = 1;
+      T fri[5] = {0, 0, 0, 0, 0};
+      if (bs.type == CN_CONTACT_PYRAMIDAL) {
+        bs.nb = a.coni[((long long)CI_DIM * h.nconmax + id) * S + env];
+        bs.nrow = 2 * (bs.nb - 1);
+        for (int k = 0; k < 5; k++) fri[k] = a.con[((long long)(CF_FRICTION + k) * h.nconmax + id) * S + env];
       }
-      // ---- transpose out: the lanes of the warp write one environment's record at a time (coalesced runs) ----
-      __syncwarp();
-      const int mylen = have ? bs.len : 0;
-      for (unsigned rem = __ballot_sync(0xffffffffu, have); rem; rem &= rem - 1) {
-        const int e = __ffs(rem) - 1;
-        const int len_e = __shfl_sync(0xffffffffu, mylen, e), off_e = __shfl_sync(0xffffffffu, woff, e);
-        T* dst = a.efc_blocks + ((long long)tile * BLOCK + wbase + e) * capw + off_e;
-        for (int q = lane; q < len_e; q += 32) dst[q] = recsh[(size_t)q * LDS + wbase + e];
+      const Seg g = seg_of(m, a.efc_tree[((long long)2 * r) * S + env], a.efc_tree[((long long)2 * r + 1) * S + env]);
+      bs.s1 = g.s1; bs.n1 = g.n1; bs.s2 = g.s2; bs.w = g.n1 + g.n2;
+      bs.layout();
+      const int w = bs.w, wq = bs.wq, nb = bs.nb;
+      for (int k = 0; k < nb; k++) {
+        for (int e = 0; e < w; e++) {
+          const T j = a.efc_J[((long long)(r + k) * W + e) * S + env];
+          rec[bs.oJ + k * wq + e] = j;
+          rec[bs.oB + k * wq + e] = j;
+        }
+        for (int e = w; e < wq; e++) { rec[bs.oJ + k * wq + e] = 0; rec[bs.oB + k * wq + e] = 0; }
+        // B_k = M^-1 J_k^T, one tree at a time (M is block diagonal over trees)
+        for (int sgm = 0; sgm < 2; sgm++) {
+          const int lo = sgm ? g.s2 : g.s1, n = sgm ? g.n2 : g.n1, base = bs.oB + k * wq + (sgm ? g.n1 : 0);
+          if (n == 0) continue;
+          for (int i = lo + n - 1; i >= lo; i--) {
+            const T xi = rec[base + i - lo];
+            if (xi == 0) continue;
+            int adr = m.i(h.o_dof_Madr, i) + 1;
+            for (int j = m.i(h.o_dof_parentid, i); j >= 0; j = m.i(h.o_dof_parentid, j)) rec[base + j - lo] -= LD[adr++] * xi;
+          }
+          for (int i = lo; i < lo + n; i++) rec[base + i - lo] *= dinv[i];
+          for (int i = lo; i < lo + n; i++) {
+            int adr = m.i(h.o_dof_Madr, i) + 1;
+            T xi = rec[base + i - lo];
+            for (int j = m.i(h.o_dof_parentid, i); j >= 0; j = m.i(h.o_dof_parentid, j)) xi -= LD[adr++] * rec[base + j - lo];
+            rec[base + i - lo] = xi;
+          }
+        }
       }
-      __syncwarp();
-      if (have) { woff += bs.len; r += bs.nrow; }
+      // local matrix A = J_base B_base^T (symmetric), then the couplings between the pyramid rows
+      T A[6][6];
+      for (int k = 0; k < nb; k++)
+        for (int c = k; c < nb; c++) {
+          T s0 = 0;
+          for (int e = 0; e < w; e++) s0 += rec[bs.oJ + k * wq + e] * rec[bs.oB + c * wq + e];
+          A[k][c] = s0; A[c][k] = s0;
+        }
+      if (nb > 1)
+        for (int r1 = 0; r1 < bs.nrow; r1++)
+          for (int r2 = r1 + 1; r2 < bs.nrow; r2++) {
+            const int k1 = r1 / 2 + 1, k2 = r2 / 2 + 1;
+            const T m1 = (r1 & 1) ? -fri[k1 - 1] : fri[k1 - 1], m2 = (r2 & 1) ? -fri[k2 - 1] : fri[k2 - 1];
+            rec[bs.aru(r1, r2)] = A[0][0] + m2 * A[0][k2] + m1 * (A[k1][0] + m2 * A[k1][k2]);
+          }
+      for (int k = 1; k < nb; k++) rec[bs.oMu + k - 1] = fri[k - 1];
+      const T R = a.efc_R[o], fl = a.efc_frictionloss[o];
+      for (int rr = 0; rr < bs.nrow; rr++) {
+        const long long orr = (long long)(r + rr) * S + env;
+        const int k = nb > 1 ? rr / 2 + 1 : 0;
+        const T sm = nb > 1 ? ((rr & 1) ? -fri[k - 1] : fri[k - 1]) : T(0);
+        const T Arr = (nb > 1 ? A[0][0] + 2 * sm * A[0][k] + sm * sm * A[k][k] : A[0][0]) + R;
+        a.efc_ARdiag[orr] = Arr;
+        rec[bs.oAref + rr] = a.efc_aref[orr]; rec[bs.oArr + rr] = Arr; rec[bs.oiA + rr] = 1 / Arr; rec[bs.ob + rr] = a.efc_b[orr];
+      }
+      for (int q = bs.oA + (nb > 1 ? bs.nrow * (bs.nrow - 1) / 2 : 0); q < bs.oJ; q++) rec[q] = 0;
+      rec[BH_CODE] = enc_int(bs.type + 16 * nb + 256 * bs.nrow, T());
+      rec[BH_S1] = enc_int(bs.s1, T()); rec[BH_N1W] = enc_int(bs.n1 + 1024 * w, T()); rec[BH_S2] = enc_int(bs.s2, T());
+      rec[BH_R] = R; rec[BH_FL] = fl; rec[BH_LEN] = enc_int(bs.len, T()); rec[BH_ROW0] = enc_int(r, T());
     }
-    if (!done) a.efc_nwords[env] = woff;
+    // ---- transpose out: the lanes of the warp write one environment's record at a time (coalesced runs) ----
+    __syncwarp();
+    const int mylen = have ? bs.len : 0;
+    for (unsigned rem = __ballot_sync(0xffffffffu, have); rem; rem &= rem - 1) {
+      const int e = __ffs(rem) - 1;
+      const int len_e = __shfl_sync(0xffffffffu, mylen, e), off_e = __shfl_sync(0xffffffffu, woff, e);
+      T* dst = a.efc_blocks + ((long long)tile * BLOCK + wbase + e) * capw + off_e;
+      for (int q = lane; q < len_e; q += 32) dst[q] = recsh[(size_t)q * LDS + wbase + e];
+    }
+    __syncwarp();
   }
 }
 
