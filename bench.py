@@ -84,6 +84,23 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def real_mujoco_present():
+    """probe for the real thing before falling back to the oracle port (never found in this image)."""
+    try:
+        import mujoco  # noqa: F401
+        return True
+    except Exception:
+        pass
+    import ctypes
+    for name in ("libmujoco.so.2.3.7", "libmujoco.so"):
+        try:
+            ctypes.CDLL(name)
+            return True
+        except OSError:
+            continue
+    return False
+
+
 def cpu_reference(cfg, nenv_sample, steps, warmup, threads=None):
     """The reference's CPU path for this tick, restated by the fp64 oracle (libmujoco is not available: SURVEY 8c),
     on `threads` host threads (default: all).  Returns (env-steps/s, threads used, description)."""
@@ -249,7 +266,7 @@ def main():
                "config": {"workload": "%s: %s" % (args.config, desc), "model": asset, "envs_per_step": sample, "timestep": 0.005,
                           "tick": "step1+controller+inverse+step2"},
                "cpu_baseline": {"value": val, "unit": UNIT, "cores": used, "kind": "port",
-                                "sample": "%d envs x %d ticks of the same workload; fp64 oracle restatement of MuJoCo 2.3.7 semantics (libmujoco unavailable)" % (sample, args.steps)},
+                                "sample": "%d envs x %d ticks of the same workload; fp64 oracle restatement of MuJoCo 2.3.7 semantics (real MuJoCo present: %s)" % (sample, args.steps, "yes, but not wired in" if real_mujoco_present() else "no")},
                "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(out))
         return
@@ -434,7 +451,7 @@ def main():
             out["drift"] = drift_report(args.config)
         out["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": used, "kind": "port",
                                "sample": "%d envs x %d ticks of the same workload in %.1f s; fp64 oracle restatement of MuJoCo 2.3.7 semantics "
-                                         "(libmujoco is not available)" % (sample, csteps, dt)}
+                                         "(real MuJoCo present: %s)" % (sample, csteps, dt, "yes, but not wired in" if real_mujoco_present() else "no")}
     print(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()
