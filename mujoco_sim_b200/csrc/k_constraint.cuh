@@ -684,8 +684,18 @@ __device__ __forceinline__ void pgs_visit(const T* __restrict__ rec, const Block
     }
   }
   if (any) {
+    {  // lane r stores force r (and r + LANES): select chains, not predicated stores per row (those compile to a jump table)
+      T mine = fo[0];
 #pragma unroll
-    for (int r = 0; r < NROWW; r++) if (r < nrow && l == r % LANES) f[row0 + r] = fo[r];
+      for (int r = 1; r < NROWW && r < LANES; r++) mine = (l == r) ? fo[r] : mine;
+      if (l < nrow && l < LANES) f[row0 + l] = mine;
+      if (NROWW > LANES) {
+        T mine2 = fo[NROWW > LANES ? LANES : 0];
+#pragma unroll
+        for (int r = LANES + 1; r < NROWW; r++) mine2 = (l == r - LANES) ? fo[r] : mine2;
+        if (l + LANES < nrow) f[row0 + l + LANES] = mine2;
+      }
+    }
     T d[NBW];
     d[0] = dl[0];
 #pragma unroll
@@ -698,6 +708,95 @@ __device__ __forceinline__ void pgs_visit(const T* __restrict__ rec, const Block
       for (int k = 0; k < NBW; k++) if (k < nb) s0 += d[k] * rec[bs.oB + k * wq + e];
       acc[bs.dof(e)] += s0;
     }
+  }
+}
+
+// The same visit when every team of the warp that has a block has one with exactly NB base directions (the common case:
+// most contacts of a scene share a condim): all record offsets are compile-time constants, the parameters arrive as
+// 16-byte vector loads and no row is padded or predicated.  `have` masks the teams that only keep the warp company
+// (their rec points at valid memory of their own slab; whatever they compute is discarded).
+template <typename T, int NB, int LANES>
+__device__ __forceinline__ void pgs_visit_exact(const T* __restrict__ rec, bool have, int s1, int n1, int s2, int w, int row0, T R,
+                                                T* acc, T* f, int l, T& improvement) {
+  static_assert(NB == 3 || NB == 4, "pyramidal contacts of condim 3 / 4");
+  constexpr int NROW = 2 * (NB - 1);
+  constexpr int oAref = BH_N, oArr = oAref + NROW, oiA = oArr + NROW, oMu = oiA + 2 * NROW, oA = oMu + NB - 1;
+  constexpr int NCPL = NROW * (NROW - 1) / 2;
+  constexpr int oJ = (oA + NCPL + 3) & ~3;
+  using V4 = VecN<T, 4>;
+  const int wq = (w + 3) & ~3, oB = oJ + NB * wq;
+  // parameters: words [oAref, oJ) as vectors (NB = 3: 24 words, NB = 4: 40 words; both offsets are multiples of 4)
+  constexpr int NPV = (oJ - oAref) / 4;
+  T P[NPV * 4];
+#pragma unroll
+  for (int q = 0; q < NPV; q++) {
+    const V4 v = *reinterpret_cast<const V4*>(rec + oAref + 4 * q);
+#pragma unroll
+    for (int c = 0; c < 4; c++) P[4 * q + c] = v.v[c];
+  }
+  auto PAR = [&](int off) -> T { return P[off - oAref]; };
+  T fo[NROW];
+#pragma unroll
+  for (int r = 0; r < NROW; r++) fo[r] = f[row0 + r];
+  // dot products with the running acceleration: lane l owns elements l and l + LANES (w <= 2 LANES on this path)
+  const int e0 = l, e1 = l + LANES;
+  const bool in0 = e0 < w, in1 = e1 < w;
+  const int d0 = e0 < n1 ? s1 + e0 : s2 + e0 - n1, d1 = e1 < n1 ? s1 + e1 : s2 + e1 - n1;
+  const T x0 = in0 ? acc[d0] : T(0), x1 = in1 ? acc[d1] : T(0);
+  T u[NB];
+#pragma unroll
+  for (int k = 0; k < NB; k++) {
+    const T j0 = in0 ? rec[oJ + k * wq + e0] : T(0), j1 = in1 ? rec[oJ + k * wq + e1] : T(0);
+    u[k] = j0 * x0 + j1 * x1;
+  }
+  T b0[NB], b1[NB];   // this lane's elements of B, fetched early: their latency hides behind the reduction and the rows
+#pragma unroll
+  for (int k = 0; k < NB; k++) { b0[k] = in0 ? rec[oB + k * wq + e0] : T(0); b1[k] = in1 ? rec[oB + k * wq + e1] : T(0); }
+#pragma unroll
+  for (int o = LANES / 2; o > 0; o >>= 1) {
+#pragma unroll
+    for (int k = 0; k < NB; k++) u[k] += __shfl_xor_sync(0xffffffffu, u[k], o, LANES);
+  }
+  T v[NROW], dl[NROW];
+#pragma unroll
+  for (int r = 0; r < NROW; r++) v[r] = u[0] + ((r & 1) ? -PAR(oMu + r / 2) : PAR(oMu + r / 2)) * u[r / 2 + 1];
+  bool any = false;
+  {
+    int q = 0;
+#pragma unroll
+    for (int r = 0; r < NROW; r++) {
+      const T res = v[r] + (R * fo[r] - PAR(oAref + r));
+      const T fn = t_max(T(0), fo[r] - res * PAR(oiA + r));
+      T delta = fn - fo[r];
+      const T change = T(0.5) * delta * delta * PAR(oArr + r) + delta * res;
+      const bool ok = have && delta != 0 && !(change > T(1e-10));
+      delta = ok ? delta : T(0);
+      improvement -= ok ? change : T(0);
+      fo[r] = ok ? fn : fo[r];
+      any |= ok;
+      dl[r] = delta;
+#pragma unroll
+      for (int c = r + 1; c < NROW; c++, q++) v[c] += delta * PAR(oA + q);
+    }
+  }
+  if (any) {
+    {  // lane r stores force r: a select chain instead of NROW predicated stores (which compile to a jump table)
+      T mine = fo[0];
+#pragma unroll
+      for (int r = 1; r < NROW; r++) mine = (l == r) ? fo[r] : mine;
+      if (l < NROW) f[row0 + l] = mine;
+    }
+    T d[NB];
+    d[0] = dl[0];
+#pragma unroll
+    for (int r = 1; r < NROW; r++) d[0] += dl[r];
+#pragma unroll
+    for (int k = 1; k < NB; k++) d[k] = PAR(oMu + k - 1) * (dl[2 * k - 2] - dl[2 * k - 1]);
+    T a0 = 0, a1 = 0;
+#pragma unroll
+    for (int k = 0; k < NB; k++) { a0 += d[k] * b0[k]; a1 += d[k] * b1[k]; }
+    if (in0) acc[d0] = x0 + a0;
+    if (in1) acc[d1] = x1 + a1;
   }
 }
 
@@ -858,6 +957,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_pgs_block(const KArgs<T> a) {
     //      the shuffles use the full mask and the teams never serialise ----
     {
       bool done = ne <= 0;
+      using V4 = VecN<T, 4>;
+      V4 nh0 = *reinterpret_cast<const V4*>(slab), nh1 = *reinterpret_cast<const V4*>(slab + 4);
       for (int it = 0; it < h.iterations; it++) {
         if (__all_sync(0xffffffffu, done)) break;
         T improvement = 0;
@@ -866,21 +967,34 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_pgs_block(const KArgs<T> a) {
           const bool have = !done && off < nw;
           if (!__any_sync(0xffffffffu, have)) break;
           const T* rec = slab + (have ? off : 0);
-          BlockShape bs{};
-          if (have) {
-            bs = block_shape(rec);
-            // pull the next record (or, at the end of a sweep, the first) towards L1 while this one is relaxed
-            const int nxt = off + bs.len < nw ? off + bs.len : 0;
+          // header {code, s1, n1 | w, s2} {R, frictionloss, len, row0}: fetched one visit ahead (nh0 / nh1), so its latency
+          // is never on the critical path
+          const V4 h0 = nh0, h1 = nh1;
+          const int code = dec_int(h0.v[0]), nb = have ? (code >> 4) & 15 : 0, len = have ? dec_int(h1.v[2]) : 0;
+          const int n1w = dec_int(h0.v[2]), w = have ? n1w >> 10 : 0;   // w = 0: a team without a block touches no element
+          if (have) {  // next record (at the end of a sweep: the first again): header into registers, body towards L1
+            const int nxt = off + len < nw ? off + len : 0;
+            nh0 = *reinterpret_cast<const V4*>(slab + nxt); nh1 = *reinterpret_cast<const V4*>(slab + nxt + 4);
             const int pq = nxt + l * (128 / (int)sizeof(T));
             if (pq < nw && l < 5) asm volatile("prefetch.global.L1 [%0];" ::"l"(slab + pq));
           }
-          const int nbw = __reduce_max_sync(0xffffffffu, bs.nb);
-          if (nbw <= 1) pgs_visit<T, 1, LANES>(rec, bs, acc, f, l, improvement);
-          else if (nbw <= 3) pgs_visit<T, 3, LANES>(rec, bs, acc, f, l, improvement);
-          else if (nbw <= 4) pgs_visit<T, 4, LANES>(rec, bs, acc, f, l, improvement);
-          else pgs_visit<T, 6, LANES>(rec, bs, acc, f, l, improvement);
+          // one instruction stream for the whole warp: the exact-shape visit when every team that has a block has the same
+          // condim and fits two elements per lane, else the padded generic visit
+          const bool fits = !have || w <= 2 * LANES;
+          const bool all3 = __all_sync(0xffffffffu, (!have || nb == 3) && fits), all4 = __all_sync(0xffffffffu, (!have || nb == 4) && fits);
+          if (all3) pgs_visit_exact<T, 3, LANES>(rec, have, dec_int(h0.v[1]), n1w & 1023, dec_int(h0.v[3]), w, have ? dec_int(h1.v[3]) : 0, h1.v[0], acc, f, l, improvement);
+          else if (all4) pgs_visit_exact<T, 4, LANES>(rec, have, dec_int(h0.v[1]), n1w & 1023, dec_int(h0.v[3]), w, have ? dec_int(h1.v[3]) : 0, h1.v[0], acc, f, l, improvement);
+          else {
+            BlockShape bs{};
+            if (have) bs = block_shape(rec);
+            const int nbw = __reduce_max_sync(0xffffffffu, bs.nb);
+            if (nbw <= 1) pgs_visit<T, 1, LANES>(rec, bs, acc, f, l, improvement);
+            else if (nbw <= 3) pgs_visit<T, 3, LANES>(rec, bs, acc, f, l, improvement);
+            else if (nbw <= 4) pgs_visit<T, 4, LANES>(rec, bs, acc, f, l, improvement);
+            else pgs_visit<T, 6, LANES>(rec, bs, acc, f, l, improvement);
+          }
           __syncwarp();
-          off += bs.len;
+          off += len;
         }
         if (!done) { iters = it + 1; if (improvement * scale < tol) done = true; }
       }
