@@ -213,7 +213,7 @@ KArgs<T> build_args(b2_batch* b) {
   a.con = R("contact"); a.coni = I("contact_int"); a.ncon = I("ncon"); a.nefc = I("nefc"); a.efc_type = I("efc_type");
   a.efc_id = I("efc_id"); a.efc_tree = I("efc_tree"); a.efc_J = R("efc_J"); a.efc_pos = R("efc_pos"); a.efc_margin = R("efc_margin");
   a.efc_frictionloss = R("efc_frictionloss"); a.efc_diagApprox = R("efc_diagApprox"); a.efc_R = R("efc_R"); a.efc_D = R("efc_D");
-  a.efc_KBI = R("efc_KBI"); a.efc_vel = R("efc_vel"); a.efc_aref = R("efc_aref"); a.efc_b = R("efc_b"); a.efc_force = R("efc_force");
+  a.efc_KBI = R("efc_KBI"); a.efc_vel = R("efc_vel"); a.efc_aref = R("efc_aref"); a.efc_b = R("efc_b"); a.efc_force = R("efc_force"); a.efc_finv = R("efc_finv");
   a.efc_ARdiag = R("efc_ARdiag"); a.efc_blocks = R("efc_blocks"); a.efc_nwords = I("efc_nwords"); a.env_order = I("env_order");
   a.blk_row0 = I("blk_row0"); a.blk_off = I("blk_off"); a.nblk = I("nblk"); a.maxblk = I("_maxblk"); a.solver_iter = I("solver_iter"); a.status = I("status");
   a.pending = I("_pending");
@@ -231,7 +231,7 @@ KArgs<T> make_args(b2_batch* b, int flags) {
   if constexpr (sizeof(T) == 4) a = b->args_f; else a = b->args_d;
   a.model = b->blob_dev; a.model_words = b->hdr.nwords;
   a.flags = flags; a.ws_block = b->smooth_block; a.h = (T)b->h; a.wp = b->wp;
-  a.block_capw = b->block_capw; a.stage_cap = b->stage_cap;
+  a.block_capw = b->block_capw; a.block_npar = b->block_npar; a.stage_cap = b->stage_cap;
   a.hw_vel = b->io_in[0]; a.hw_eff = b->io_in[1];
   a.hw_pos = b->io_out[0]; a.hw_velo = b->io_out[1]; a.hw_effo = b->io_out[2];
   a.hw_kp = b->hw_kp; a.hw_kd = b->hw_kd;
@@ -245,7 +245,7 @@ int configure_constraint_kernels(b2_batch* b) {
     // the constraint-pipeline kernels stage the same blob; row assembly and the solver add their shared vectors
     const int need1 = (int)b->blob_smem;
     // row assembly: one record column per thread; 128-thread CTAs when that fits, else 32
-    b->make_block = b->blob_smem + (size_t)b->rec_max * 129 * b->prec <= 200 * 1024 ? 128 : 32;
+    b->make_block = b->blob_smem + (size_t)b->rec_max * 129 * b->prec <= 56 * 1024 ? 128 : 32;
     const int need2 = (int)(b->blob_smem + (size_t)b->rec_max * (b->make_block + 1) * b->prec);
     // solver: per environment 2 (b->hdr.nv + 4) + njmax words of vectors plus the staged records; sized for ~4 CTAs per SM
     const int epb = 128 / b->pgs_lanes;
@@ -373,6 +373,10 @@ int run_tick(b2_batch* b, int flags) {
       else k_make_blocks<T, 32><<<gb, 32, sm + (size_t)b->rec_max * 33 * sizeof(T), b->stream>>>(a);
     }
     b->launches += 2;
+    if ((flags & B2_TICK_NOSOLVE) && (kf & B2F_INVERSE)) {   // mj_inverse through the shim: no solver pass to fold this into
+      k_inverse_rows<T><<<(b->nenvp + 127) / 128, 128, 0, b->stream>>>(a);
+      b->launches += 1;
+    }
     if (!(flags & B2_TICK_NOSOLVE)) {
       prof_mark(b, SLOT_PGS);
       k_order_envs<256, 1024><<<1, 1024, 0, b->stream>>>(a.nefc, a.efc_nwords, a.env_order, b->nenvp, std::max(4, b->block_capw / 256), a.pending, b->fusable ? 1 : 0);
@@ -753,7 +757,8 @@ b2_batch* b2_create(const mjModel* m, int nenv, int device, int precision) {
     for (int g = 0; g < m->ngeom; g++) nbmax = std::max(nbmax, m->geom_condim[g]);
     nbmax = std::min(nbmax, 6);
     b->block_capw = block_capacity(b->hdr.njmax, b->hdr.wmax);
-    b->rec_max = block_max_words(nbmax, b->hdr.wmax);
+    b->block_npar = block_max_params(nbmax);
+    b->rec_max = b->block_npar + 2 * ((b->hdr.wmax + 3) & ~3);
     b->pgs_lanes = getenv("B2_PGS_LANES") ? atoi(getenv("B2_PGS_LANES")) : 8;
     if (b->pgs_lanes != 4) b->pgs_lanes = 8;
   }
@@ -776,7 +781,7 @@ b2_batch* b2_create(const mjModel* m, int nenv, int device, int precision) {
         {"contact", CF_NFLOAT * ncm, 0}, {"contact_int", CI_NINT * ncm, 1},
         {"efc_type", njmax, 1}, {"efc_id", njmax, 1}, {"efc_tree", 2 * njmax, 1}, {"efc_J", njmax * b->hdr.wmax, 0}, {"efc_pos", njmax, 0}, {"efc_margin", njmax, 0},
         {"efc_frictionloss", njmax, 0}, {"efc_diagApprox", njmax, 0}, {"efc_R", njmax, 0}, {"efc_D", njmax, 0}, {"efc_KBI", 3 * njmax, 0},
-        {"efc_vel", njmax, 0}, {"efc_aref", njmax, 0}, {"efc_b", njmax, 0}, {"efc_force", njmax, 0}, {"efc_ARdiag", njmax, 0},
+        {"efc_vel", njmax, 0}, {"efc_aref", njmax, 0}, {"efc_b", njmax, 0}, {"efc_force", njmax, 0}, {"efc_finv", njmax, 0}, {"efc_ARdiag", njmax, 0},
         {"efc_blocks", b->block_capw, 0}, {"efc_nwords", 1, 1}, {"env_order", 1, 1}, {"blk_row0", njmax, 1}, {"blk_off", njmax, 1}, {"nblk", 1, 1}, {"_maxblk", 1, 1}};
     specs.insert(specs.end(), more.begin(), more.end());
   }

@@ -44,7 +44,8 @@ struct b2_batch {
   int wp = 16, epl = 2;  // (legacy)
   // block records of the constraint pipeline (k_constraint.cuh)
   int block_capw = 0;    // words of efc_blocks per environment
-  int rec_max = 0;       // largest single record (words): sizes the assembly kernel's shared-memory columns
+  int rec_max = 0;       // words per thread of k_make_blocks' shared-memory column: parameters + one base direction (J | B)
+  int block_npar = 0;    // ... of which header + parameters
   int make_block = 128;  // CTA size of k_make_constraint
   int pgs_lanes = 8;     // lanes per environment in k_pgs_block
   int stage_cap = 0;     // words of records per environment staged in shared memory by the solver

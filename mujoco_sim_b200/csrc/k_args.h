@@ -58,7 +58,7 @@ struct KArgs {
   int* efc_tree;          // [njmax][2][nenvp] kinematic trees of the row (-1: none)
   T *efc_J;               // [njmax][wmax][nenvp] compact rows (k_constraint.cuh); a contact's first condim rows hold its base directions
   T *efc_pos, *efc_margin, *efc_frictionloss, *efc_diagApprox, *efc_R, *efc_D, *efc_KBI, *efc_vel, *efc_aref,
-      *efc_b, *efc_force; // [njmax][nenvp] (KBI: [3][njmax][nenvp])
+      *efc_b, *efc_force, *efc_finv; // [njmax][nenvp] (KBI: [3][njmax][nenvp]); efc_finv: primal force of mj_inverse per row
   T* efc_ARdiag;          // [njmax][nenvp] diagonal of J M^-1 J^T + R
   T* efc_blocks;          // [nenvp][block_capw] environment-major block records streamed by the solver (k_constraint.cuh)
   int* efc_nwords;        // [nenvp] words of efc_blocks in use
@@ -67,6 +67,7 @@ struct KArgs {
   int* nblk;              // [nenvp] blocks of the environment
   int* maxblk;            // [1] largest block count of this tick (cleared by a memset node in front of k_make_rows)
   int block_capw;         // words of efc_blocks per environment
+  int block_npar;         // header + parameter words of the largest block (k_make_blocks' shared-memory column layout)
   int stage_cap;          // words of an environment's records the solver keeps in shared memory
   int wp;                 // (unused) padded compact row width
   int* solver_iter;       // [nenvp]

@@ -411,6 +411,13 @@ __device__ __forceinline__ BlockShape block_shape(const T* rec) {
 }
 // words one environment can need: every row as a single-row block is the worst case
 __host__ __device__ inline int block_capacity(int njmax, int wmax) { return njmax * (BH_N + 4 + 2 * ((wmax + 3) & ~3)); }
+// words of header + row parameters (everything in front of J) of the largest block
+__host__ __device__ inline int block_max_params(int nbmax) {
+  BlockShape s{};
+  s.nb = nbmax; s.nrow = nbmax > 1 ? 2 * (nbmax - 1) : 1; s.w = 4;
+  s.layout();
+  return s.oJ;
+}
 __host__ __device__ inline int block_max_words(int nbmax, int wmax) {
   BlockShape s{};
   s.nb = nbmax; s.nrow = nbmax > 1 ? 2 * (nbmax - 1) : 1; s.w = wmax;
@@ -418,10 +425,8 @@ __host__ __device__ inline int block_max_words(int nbmax, int wmax) {
   return s.len;
 }
 
-// K4: rows, impedance, and per BLOCK the cheap, inherently sequential part — vel, aref, b of every solver row, the
-// primal force of mj_inverse accumulated into qfrc_inverse in row order (deterministic), and the block table
-// (first row, word offset in the slab) that lets k_make_blocks work on all blocks of all environments at once.
-// One thread per environment.
+// K4: rows and impedance in MuJoCo's row order — the inherently sequential part — and the block table (first row, word
+// offset in the slab) that lets k_make_blocks work on all blocks of all environments at once.  One thread per environment.
 template <typename T, int BLOCK>
 __global__ void __launch_bounds__(BLOCK) k_make_rows(const KArgs<T> a) {
   B2_KERNEL_PROLOGUE
@@ -437,7 +442,7 @@ __global__ void __launch_bounds__(BLOCK) k_make_rows(const KArgs<T> a) {
       rows.contacts();
       rows.finish();
     }
-    const int ne = rows.nefc, W = h.wmax;
+    const int ne = rows.nefc;
     if (!done) a.nefc[env] = ne;
     int r = 0, woff = 0, nblk = 0;
     while (r < ne) {
@@ -446,50 +451,13 @@ __global__ void __launch_bounds__(BLOCK) k_make_rows(const KArgs<T> a) {
       bs.type = a.efc_type[o];
       const int id = a.efc_id[o];
       bs.nb = 1; bs.nrow = 1;
-      T fri[5] = {0, 0, 0, 0, 0};
       if (bs.type == CN_CONTACT_PYRAMIDAL) {
         bs.nb = a.coni[((long long)CI_DIM * h.nconmax + id) * S + env];
         bs.nrow = 2 * (bs.nb - 1);
-        for (int k = 0; k < 5; k++) fri[k] = a.con[((long long)(CF_FRICTION + k) * h.nconmax + id) * S + env];
       }
       const Seg g = seg_of(m, a.efc_tree[((long long)2 * r) * S + env], a.efc_tree[((long long)2 * r + 1) * S + env]);
       bs.s1 = g.s1; bs.n1 = g.n1; bs.s2 = g.s2; bs.w = g.n1 + g.n2;
       bs.layout();
-      const int w = bs.w, nb = bs.nb;
-      T vel[6], js[6], jq[6];
-      for (int k = 0; k < nb; k++) {
-        T v0 = 0, s0 = 0, q0 = 0;
-        for (int e = 0; e < w; e++) {
-          const T j = a.efc_J[((long long)(r + k) * W + e) * S + env];
-          const long long d = (long long)bs.dof(e) * S + env;
-          v0 += j * a.qvel[d]; s0 += j * a.qacc_smooth[d]; q0 += j * a.qacc[d];
-        }
-        vel[k] = v0; js[k] = s0; jq[k] = q0;
-      }
-      const T R = a.efc_R[o], D = 1 / R, fl = a.efc_frictionloss[o];
-      T dsum[6] = {0, 0, 0, 0, 0, 0};
-      for (int rr = 0; rr < bs.nrow; rr++) {
-        const long long orr = (long long)(r + rr) * S + env;
-        const int k = nb > 1 ? rr / 2 + 1 : 0;
-        const T sm = nb > 1 ? ((rr & 1) ? -fri[k - 1] : fri[k - 1]) : T(0);
-        const T velr = vel[0] + sm * vel[k], jsr = js[0] + sm * js[k], jqr = jq[0] + sm * jq[k];
-        const T K = a.efc_KBI[((long long)0 * h.njmax + r + rr) * S + env], Bd = a.efc_KBI[((long long)1 * h.njmax + r + rr) * S + env];
-        const T imp = a.efc_KBI[((long long)2 * h.njmax + r + rr) * S + env];
-        const T aref = -Bd * velr - K * imp * (a.efc_pos[orr] - a.efc_margin[orr]);
-        a.efc_D[orr] = D; a.efc_vel[orr] = velr; a.efc_aref[orr] = aref; a.efc_b[orr] = jsr - aref;
-        if (a.flags & B2F_INVERSE) {
-          const T f = primal_force(bs.type, jqr - aref, D, R, fl);
-          dsum[0] += f;
-          if (nb > 1) dsum[k] += sm * f;
-        }
-      }
-      if (a.flags & B2F_INVERSE) {
-        for (int e = 0; e < w; e++) {
-          T s0 = 0;
-          for (int k = 0; k < nb; k++) s0 += dsum[k] * a.efc_J[((long long)(r + k) * W + e) * S + env];
-          if (s0 != 0) a.qfrc_inverse[(long long)bs.dof(e) * S + env] -= s0;
-        }
-      }
       a.blk_row0[(long long)nblk * S + env] = r;
       a.blk_off[(long long)nblk * S + env] = woff;
       nblk++;
@@ -502,9 +470,10 @@ __global__ void __launch_bounds__(BLOCK) k_make_rows(const KArgs<T> a) {
   if ((threadIdx.x & 31) == 0 && wmaxblk > 0) atomicMax(a.maxblk, wmaxblk);
 }
 
-// K5: the expensive, embarrassingly parallel part — one thread per (block, environment): B = M^-1 J^T of the block's base
-// directions by sparse back-substitution inside its trees (in shared memory), the local matrix A, the couplings between
-// the pyramid rows, diag(AR) per row, and the finished record, which leaves through a shared-memory transpose so that
+// K5: the expensive, embarrassingly parallel part — one thread per (block, environment): vel, aref, b of the block's solver
+// rows, the primal force of mj_inverse per row, B = M^-1 J^T of the block's base directions by sparse back-substitution
+// inside its trees (in shared memory), the local matrix A, the couplings between the pyramid rows, diag(AR) per row, and
+// the finished record, which leaves through a shared-memory transpose so that
 // every global store of the slab is a coalesced run.  grid.y = njmax (the most blocks an environment can have): CTAs
 // beyond the largest block count of this tick (maxblk, found by k_make_rows) exit at once.
 template <typename T, int BLOCK>
@@ -513,68 +482,101 @@ __global__ void __launch_bounds__(BLOCK) k_make_blocks(const KArgs<T> a) {
   if (blk >= a.maxblk[0]) return;
   B2_KERNEL_PROLOGUE
   constexpr int LDS = BLOCK + 1;  // +1: conflict-free both for per-thread columns and for the transposed reads
-  T* recsh = reinterpret_cast<T*>(smem_raw + 16 + (size_t)nwords * 4);  // [recmax][LDS]: one record per thread (column)
+  // per thread (column): [0, npar) header + row parameters, then one base direction at a time: J_c [wqmax] | B_c [wqmax].
+  // Streaming the base directions keeps the footprint at npar + 2 wq words per thread instead of the whole record
+  // (PR2-sized trees: 156 instead of 468 words -> 4x the resident warps).
+  T* colsh = reinterpret_cast<T*>(smem_raw + 16 + (size_t)nwords * 4);
+  const int npar = a.block_npar, wqmax = (h.wmax + 3) & ~3;
   const int lane = threadIdx.x & 31, wbase = threadIdx.x & ~31;
   const int capw = a.block_capw;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int env = tile * BLOCK + threadIdx.x;
     const int W = h.wmax;
     SArr<T> LD{a.qLD + env, S}, dinv{a.qLDiagInv + env, S};
-    SArr<T> rec{recsh + threadIdx.x, LDS};
+    SArr<T> rec{colsh + threadIdx.x, LDS};
+    SArr<T> Jc{colsh + (size_t)npar * LDS + threadIdx.x, LDS}, Bc{colsh + (size_t)(npar + wqmax) * LDS + threadIdx.x, LDS};
     const bool have = blk < a.nblk[env];
     BlockShape bs{};
-    int woff = 0;
+    int woff = 0, r = 0;
+    Seg g{0, 0, 0, 0};
+    T fri[5] = {0, 0, 0, 0, 0};
     if (have) {
-      const int r = a.blk_row0[(long long)blk * S + env];
+      r = a.blk_row0[(long long)blk * S + env];
       woff = a.blk_off[(long long)blk * S + env];
       const long long o = (long long)r * S + env;
       bs.type = a.efc_type[o];
       const int id = a.efc_id[o];
       bs.nb = 1; bs.nrow = 1;
-      T fri[5] = {0, 0, 0, 0, 0};
       if (bs.type == CN_CONTACT_PYRAMIDAL) {
         bs.nb = a.coni[((long long)CI_DIM * h.nconmax + id) * S + env];
         bs.nrow = 2 * (bs.nb - 1);
         for (int k = 0; k < 5; k++) fri[k] = a.con[((long long)(CF_FRICTION + k) * h.nconmax + id) * S + env];
       }
-      const Seg g = seg_of(m, a.efc_tree[((long long)2 * r) * S + env], a.efc_tree[((long long)2 * r + 1) * S + env]);
+      g = seg_of(m, a.efc_tree[((long long)2 * r) * S + env], a.efc_tree[((long long)2 * r + 1) * S + env]);
       bs.s1 = g.s1; bs.n1 = g.n1; bs.s2 = g.s2; bs.w = g.n1 + g.n2;
       bs.layout();
-      const int w = bs.w, wq = bs.wq, nb = bs.nb;
-      for (int k = 0; k < nb; k++) {
+    }
+    const int w = bs.w, wq = bs.wq, nb = bs.nb;
+    const long long slab_env = ((long long)tile * BLOCK + wbase) * capw;   // slab offset of lane 0's environment
+    T vel[6], js[6], jq[6], A[6][6];
+    const int nbw = __reduce_max_sync(0xffffffffu, nb);
+    for (int c = 0; c < nbw; c++) {
+      const bool on = have && c < nb;
+      if (on) {
+        T v0 = 0, s0 = 0, q0 = 0;
         for (int e = 0; e < w; e++) {
-          const T j = a.efc_J[((long long)(r + k) * W + e) * S + env];
-          rec[bs.oJ + k * wq + e] = j;
-          rec[bs.oB + k * wq + e] = j;
+          const T j = a.efc_J[((long long)(r + c) * W + e) * S + env];
+          Jc[e] = j; Bc[e] = j;
+          if (j != 0) {
+            const long long d = (long long)bs.dof(e) * S + env;
+            v0 += j * a.qvel[d]; s0 += j * a.qacc_smooth[d];
+            if (a.flags & B2F_INVERSE) q0 += j * a.qacc[d];
+          }
         }
-        for (int e = w; e < wq; e++) { rec[bs.oJ + k * wq + e] = 0; rec[bs.oB + k * wq + e] = 0; }
-        // B_k = M^-1 J_k^T, one tree at a time (M is block diagonal over trees)
+        vel[c] = v0; js[c] = s0; jq[c] = q0;
+        for (int e = w; e < wq; e++) { Jc[e] = 0; Bc[e] = 0; }
+        // B_c = M^-1 J_c^T, one tree at a time (M is block diagonal over trees)
         for (int sgm = 0; sgm < 2; sgm++) {
-          const int lo = sgm ? g.s2 : g.s1, n = sgm ? g.n2 : g.n1, base = bs.oB + k * wq + (sgm ? g.n1 : 0);
+          const int lo = sgm ? g.s2 : g.s1, n = sgm ? g.n2 : g.n1, base = sgm ? g.n1 : 0;
           if (n == 0) continue;
           for (int i = lo + n - 1; i >= lo; i--) {
-            const T xi = rec[base + i - lo];
+            const T xi = Bc[base + i - lo];
             if (xi == 0) continue;
             int adr = m.i(h.o_dof_Madr, i) + 1;
-            for (int j = m.i(h.o_dof_parentid, i); j >= 0; j = m.i(h.o_dof_parentid, j)) rec[base + j - lo] -= LD[adr++] * xi;
+            for (int j = m.i(h.o_dof_parentid, i); j >= 0; j = m.i(h.o_dof_parentid, j)) Bc[base + j - lo] -= LD[adr++] * xi;
           }
-          for (int i = lo; i < lo + n; i++) rec[base + i - lo] *= dinv[i];
+          for (int i = lo; i < lo + n; i++) Bc[base + i - lo] *= dinv[i];
           for (int i = lo; i < lo + n; i++) {
             int adr = m.i(h.o_dof_Madr, i) + 1;
-            T xi = rec[base + i - lo];
-            for (int j = m.i(h.o_dof_parentid, i); j >= 0; j = m.i(h.o_dof_parentid, j)) xi -= LD[adr++] * rec[base + j - lo];
-            rec[base + i - lo] = xi;
+            T xi = Bc[base + i - lo];
+            for (int j = m.i(h.o_dof_parentid, i); j >= 0; j = m.i(h.o_dof_parentid, j)) xi -= LD[adr++] * Bc[base + j - lo];
+            Bc[base + i - lo] = xi;
           }
         }
-      }
-      // local matrix A = J_base B_base^T (symmetric), then the couplings between the pyramid rows
-      T A[6][6];
-      for (int k = 0; k < nb; k++)
-        for (int c = k; c < nb; c++) {
-          T s0 = 0;
-          for (int e = 0; e < w; e++) s0 += rec[bs.oJ + k * wq + e] * rec[bs.oB + c * wq + e];
-          A[k][c] = s0; A[c][k] = s0;
+        // column c of the local matrix A = J_base B_base^T (symmetric): rows k < c from efc_J, the diagonal from J_c
+        for (int k = 0; k <= c; k++) {
+          T s0a = 0;
+          if (k == c) { for (int e = 0; e < w; e++) s0a += Jc[e] * Bc[e]; }
+          else { for (int e = 0; e < w; e++) { const T j = a.efc_J[((long long)(r + k) * W + e) * S + env]; if (j != 0) s0a += j * Bc[e]; } }
+          A[k][c] = s0a; A[c][k] = s0a;
         }
+      }
+      // ---- transpose out J_c | B_c: the lanes of the warp write one environment's runs at a time ----
+      __syncwarp();
+      const int myJ = on ? woff + bs.oJ + c * wq : 0, myB = on ? woff + bs.oB + c * wq : 0, mywq = on ? wq : 0;
+      for (unsigned rem = __ballot_sync(0xffffffffu, on); rem; rem &= rem - 1) {
+        const int e = __ffs(rem) - 1;
+        const int wq_e = __shfl_sync(0xffffffffu, mywq, e), oJ_e = __shfl_sync(0xffffffffu, myJ, e), oB_e = __shfl_sync(0xffffffffu, myB, e);
+        T* dst = a.efc_blocks + slab_env + (long long)e * capw;
+        for (int q = lane; q < wq_e; q += 32) {
+          dst[oJ_e + q] = colsh[(size_t)(npar + q) * LDS + wbase + e];
+          dst[oB_e + q] = colsh[(size_t)(npar + wqmax + q) * LDS + wbase + e];
+        }
+      }
+      __syncwarp();
+    }
+    if (have) {
+      const long long o = (long long)r * S + env;
       if (nb > 1)
         for (int r1 = 0; r1 < bs.nrow; r1++)
           for (int r2 = r1 + 1; r2 < bs.nrow; r2++) {
@@ -583,30 +585,70 @@ __global__ void __launch_bounds__(BLOCK) k_make_blocks(const KArgs<T> a) {
             rec[bs.aru(r1, r2)] = A[0][0] + m2 * A[0][k2] + m1 * (A[k1][0] + m2 * A[k1][k2]);
           }
       for (int k = 1; k < nb; k++) rec[bs.oMu + k - 1] = fri[k - 1];
-      const T R = a.efc_R[o], fl = a.efc_frictionloss[o];
+      const T R = a.efc_R[o], D = 1 / R, fl = a.efc_frictionloss[o];
       for (int rr = 0; rr < bs.nrow; rr++) {
         const long long orr = (long long)(r + rr) * S + env;
         const int k = nb > 1 ? rr / 2 + 1 : 0;
         const T sm = nb > 1 ? ((rr & 1) ? -fri[k - 1] : fri[k - 1]) : T(0);
+        const T velr = vel[0] + sm * vel[k], jsr = js[0] + sm * js[k];
+        const T K = a.efc_KBI[((long long)0 * h.njmax + r + rr) * S + env], Bd = a.efc_KBI[((long long)1 * h.njmax + r + rr) * S + env];
+        const T imp = a.efc_KBI[((long long)2 * h.njmax + r + rr) * S + env];
+        const T aref = -Bd * velr - K * imp * (a.efc_pos[orr] - a.efc_margin[orr]);
+        const T bb = jsr - aref;
         const T Arr = (nb > 1 ? A[0][0] + 2 * sm * A[0][k] + sm * sm * A[k][k] : A[0][0]) + R;
-        a.efc_ARdiag[orr] = Arr;
-        rec[bs.oAref + rr] = a.efc_aref[orr]; rec[bs.oArr + rr] = Arr; rec[bs.oiA + rr] = 1 / Arr; rec[bs.ob + rr] = a.efc_b[orr];
+        a.efc_D[orr] = D; a.efc_vel[orr] = velr; a.efc_aref[orr] = aref; a.efc_b[orr] = bb; a.efc_ARdiag[orr] = Arr;
+        // force implied by the previous tick's acceleration (mj_inverse); summed into qfrc_inverse later, in row order
+        if (a.flags & B2F_INVERSE) a.efc_finv[orr] = primal_force(bs.type, jq[0] + sm * jq[k] - aref, D, R, fl);
+        rec[bs.oAref + rr] = aref; rec[bs.oArr + rr] = Arr; rec[bs.oiA + rr] = 1 / Arr; rec[bs.ob + rr] = bb;
       }
       for (int q = bs.oA + (nb > 1 ? bs.nrow * (bs.nrow - 1) / 2 : 0); q < bs.oJ; q++) rec[q] = 0;
       rec[BH_CODE] = enc_int(bs.type + 16 * nb + 256 * bs.nrow, T());
       rec[BH_S1] = enc_int(bs.s1, T()); rec[BH_N1W] = enc_int(bs.n1 + 1024 * w, T()); rec[BH_S2] = enc_int(bs.s2, T());
       rec[BH_R] = R; rec[BH_FL] = fl; rec[BH_LEN] = enc_int(bs.len, T()); rec[BH_ROW0] = enc_int(r, T());
     }
-    // ---- transpose out: the lanes of the warp write one environment's record at a time (coalesced runs) ----
+    // ---- transpose out header + parameters ----
     __syncwarp();
-    const int mylen = have ? bs.len : 0;
+    const int mylen = have ? bs.oJ : 0;
     for (unsigned rem = __ballot_sync(0xffffffffu, have); rem; rem &= rem - 1) {
       const int e = __ffs(rem) - 1;
       const int len_e = __shfl_sync(0xffffffffu, mylen, e), off_e = __shfl_sync(0xffffffffu, woff, e);
-      T* dst = a.efc_blocks + ((long long)tile * BLOCK + wbase + e) * capw + off_e;
-      for (int q = lane; q < len_e; q += 32) dst[q] = recsh[(size_t)q * LDS + wbase + e];
+      T* dst = a.efc_blocks + slab_env + (long long)e * capw + off_e;
+      for (int q = lane; q < len_e; q += 32) dst[q] = colsh[(size_t)q * LDS + wbase + e];
     }
     __syncwarp();
+  }
+}
+
+// mj_inverse without a solve (the MuJoCo-named shim: B2_TICK_INVERSE | B2_TICK_NOSOLVE): qfrc_inverse -= J^T f from the
+// rows' base directions in efc_J and the per-row forces, one thread per environment.
+template <typename T>
+__global__ void k_inverse_rows(const KArgs<T> a) {
+  const DModel* h = reinterpret_cast<const DModel*>(a.model);
+  const int env = blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= a.nenvp) return;
+  if ((a.flags & B2F_FUSABLE) && (a.status[env] & 8)) return;
+  const long long S = a.nenvp;
+  const int ne = a.nefc[env], W = h->wmax;
+  if (ne <= 0) return;
+  const int nw = a.efc_nwords[env];
+  const T* slab = a.efc_blocks + (long long)env * a.block_capw;
+  for (int off = 0; off < nw;) {
+    const T* rec = slab + off;
+    const BlockShape bs = block_shape(rec);
+    const int row0 = dec_int(rec[BH_ROW0]);
+    T d[6] = {0, 0, 0, 0, 0, 0};
+    for (int rr = 0; rr < bs.nrow; rr++) {
+      const T fr = a.efc_finv[(long long)(row0 + rr) * S + env];
+      const int k = bs.nb > 1 ? rr / 2 + 1 : 0;
+      d[0] += fr;
+      if (bs.nb > 1) d[k] += ((rr & 1) ? -rec[bs.oMu + k - 1] : rec[bs.oMu + k - 1]) * fr;
+    }
+    for (int e = 0; e < bs.w; e++) {
+      T s0 = 0;
+      for (int k = 0; k < bs.nb; k++) s0 += d[k] * a.efc_J[((long long)(row0 + k) * W + e) * S + env];
+      if (s0 != 0) a.qfrc_inverse[(long long)bs.dof(e) * S + env] -= s0;
+    }
+    off += bs.len;
   }
 }
 
@@ -1036,6 +1078,31 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_pgs_block(const KArgs<T> a) {
       if (l == 0) a.solver_iter[env] = iters;
     }
     __syncwarp(tmask);
+    // ---- mj_inverse: qfrc_inverse -= J^T f(qacc of the previous tick), forces per row from k_make_blocks ----
+    if ((a.flags & B2F_INVERSE) && ne > 0) {
+      for (int i = l; i < nv; i += LANES) tmp[i] = 0;
+      __syncwarp(tmask);
+      for (int off = 0; off < nw;) {
+        const T* rec = rec_at(off);
+        const BlockShape bs = block_shape(rec);
+        const int row0 = dec_int(rec[BH_ROW0]);
+        T d[6] = {0, 0, 0, 0, 0, 0};
+        bool any = false;
+        for (int rr = 0; rr < bs.nrow; rr++) {
+          const T fr = a.efc_finv[(long long)(row0 + rr) * S + env];
+          if (fr == 0) continue;
+          const int k = bs.nb > 1 ? rr / 2 + 1 : 0;
+          any = true;
+          d[0] += fr;
+          if (bs.nb > 1) d[k] += ((rr & 1) ? -rec[bs.oMu + k - 1] : rec[bs.oMu + k - 1]) * fr;
+        }
+        if (any) base_axpy(rec, bs, bs.oJ, d, tmp);
+        __syncwarp(tmask);
+        off += bs.len;
+      }
+      for (int i = l; i < nv; i += LANES) if (tmp[i] != 0) a.qfrc_inverse[(long long)i * S + env] -= tmp[i];
+      __syncwarp(tmask);
+    }
   }
 }
 
