@@ -112,13 +112,17 @@ int pack_model(b2_batch* b) {
   B2_MODEL_ARRAYS(X)
 #undef X
   h.nwords = (off + 3) & ~3;
+  // mesh vertices live behind the staged part of the blob (HBM only; k_collide's support function reads them in place)
+  h.o_mesh_vert = h.nwords;
+  h.nmeshvert = m->nmeshvert;
+  const int tail_words = ((3 * m->nmeshvert * (rb == 8 ? 2 : 1)) + 3) & ~3;
   int ws = 0;
 #define X(name, count) h.w_##name = ws; ws += (count);
   B2_WS_ARRAYS(X)
 #undef X
   h.ws_slots = ws;
 
-  b->blob.assign(h.nwords, 0u);
+  b->blob.assign(h.nwords + tail_words, 0u);
   std::memcpy(b->blob.data(), &h, sizeof(h));
   // derived tables
   std::vector<int> lastdof(nbody, -1);
@@ -141,6 +145,14 @@ int pack_model(b2_batch* b) {
     if (!std::strcmp(name, "dof_treeid")) { put_int(o, dof_tree.data(), n); return 0; }
     if (!std::strcmp(name, "tree_dofadr")) { put_int(o, tree_adr.data(), n); return 0; }
     if (!std::strcmp(name, "tree_dofnum")) { put_int(o, tree_num.data(), n); return 0; }
+    if (!std::strcmp(name, "geom_vertadr") || !std::strcmp(name, "geom_vertnum")) {
+      const bool adr = name[9] == 'a';
+      for (int g = 0; g < n; g++) {
+        const int id = m->geom_type[g] == mjGEOM_MESH ? m->geom_dataid[g] : -1;
+        b->blob[o + g] = (uint32_t)(id < 0 ? 0 : (adr ? m->mesh_vertadr[id] : m->mesh_vertnum[id]));
+      }
+      return 0;
+    }
     if (!std::strcmp(name, "opt_real")) {
       const double v[8] = {m->opt.gravity[0], m->opt.gravity[1], m->opt.gravity[2], b->opt_tolerance, m->stat.meaninertia, m->opt.impratio, 0, 0};
       put_real(o, v, 8);
@@ -159,6 +171,7 @@ int pack_model(b2_batch* b) {
 #define X(name, kind, count) if (fill(#name, h.o_##name, (count), #kind[0] == 'F') < 0) return -1;
   B2_MODEL_ARRAYS(X)
 #undef X
+  if (m->nmeshvert > 0) put_real(h.o_mesh_vert, m->mesh_vert, 3 * m->nmeshvert);
   (void)neq; (void)npair; (void)nodom; (void)ngeom; (void)ntree;
   return 0;
 }
@@ -245,8 +258,9 @@ int configure_constraint_kernels(b2_batch* b) {
     // the constraint-pipeline kernels stage the same blob; row assembly and the solver add their shared vectors
     const int need1 = (int)b->blob_smem;
     // row assembly: one record column per thread; 128-thread CTAs when that fits, else 32
-    b->make_block = b->blob_smem + (size_t)b->rec_max * 129 * b->prec <= 56 * 1024 ? 128 : 32;
-    const int need2 = (int)(b->blob_smem + (size_t)b->rec_max * (b->make_block + 1) * b->prec);
+    // (k_make_blocks reads the model from HBM: its shared memory is the record columns only)
+    b->make_block = (size_t)b->rec_max * 129 * b->prec <= 56 * 1024 ? 128 : 32;
+    const int need2 = (int)((size_t)b->rec_max * (b->make_block + 1) * b->prec);
     // solver: per environment 2 (b->hdr.nv + 4) + njmax words of vectors plus the staged records; sized for ~4 CTAs per SM
     const int epb = 128 / b->pgs_lanes;
     const long long fixed = (long long)b->blob_smem + ((long long)2 * (b->hdr.nv + 4) + b->hdr.njmax) * epb * b->prec;
@@ -369,8 +383,8 @@ int run_tick(b2_batch* b, int flags) {
       // one thread per (block, environment); CTAs of block ordinals beyond this tick's largest count exit at once
       const int mb = b->make_block;
       const dim3 gb(std::max(1, std::min(b->nenvp / mb, b->nsm * 8)), b->hdr.njmax);
-      if (mb == 128) k_make_blocks<T, 128><<<gb, 128, sm + (size_t)b->rec_max * 129 * sizeof(T), b->stream>>>(a);
-      else k_make_blocks<T, 32><<<gb, 32, sm + (size_t)b->rec_max * 33 * sizeof(T), b->stream>>>(a);
+      if (mb == 128) k_make_blocks<T, 128><<<gb, 128, (size_t)b->rec_max * 129 * sizeof(T), b->stream>>>(a);
+      else k_make_blocks<T, 32><<<gb, 32, (size_t)b->rec_max * 33 * sizeof(T), b->stream>>>(a);
     }
     b->launches += 2;
     if ((flags & B2_TICK_NOSOLVE) && (kf & B2F_INVERSE)) {   // mj_inverse through the shim: no solver pass to fold this into

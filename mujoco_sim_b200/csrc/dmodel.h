@@ -25,6 +25,7 @@ namespace b2 {
   X(geom_size, F, 3 * ngeom) X(geom_rbound, F, ngeom) X(geom_pos, F, 3 * ngeom) X(geom_quat, F, 4 * ngeom)     \
   X(geom_friction, F, 3 * ngeom) X(geom_solmix, F, ngeom) X(geom_solref, F, 2 * ngeom)                         \
   X(geom_solimp, F, 5 * ngeom) X(geom_margin, F, ngeom) X(geom_gap, F, ngeom)                                  \
+  X(geom_vertadr, I, ngeom) X(geom_vertnum, I, ngeom) /* mesh geoms: vertex range in the mesh_vert tail */       \
   X(eq_type, I, neq) X(eq_obj1id, I, neq) X(eq_obj2id, I, neq) X(eq_active, I, neq)                            \
   X(eq_solref, F, 2 * neq) X(eq_solimp, F, 5 * neq) X(eq_data, F, 11 * neq)                                    \
   X(pair_geom1, I, npair) X(pair_geom2, I, npair)                                                              \
@@ -43,7 +44,8 @@ struct DModel {
   // sizes
   int nq, nv, nbody, njnt, ngeom, nM, neq, npair, nconmax, njmax, nmocap, nodom;
   int ntree, wmax;  // kinematic trees with dofs; widest compact constraint row (dofs of the two largest trees)
-  int pad3[2];
+  int o_mesh_vert;  // word offset of the mesh vertices (kind F, 3 per vertex): BEHIND nwords, read from HBM, never staged
+  int nmeshvert;
   int disableflags, enableflags, iterations, nwords;  // nwords: blob size in 32-bit words (multiple of 4)
   int has_damping, has_gravcomp, has_stiffness, has_limits, has_frictionloss, has_controlled, has_xfrc, pad0;
   float gravity[3];

@@ -1,4 +1,5 @@
-// k_collide.cuh — broad + narrow phase for the primitive geom pairs (rows s4 / s5 of SURVEY.md section 8a').
+// k_collide.cuh — broad + narrow phase (rows s4 / s5 of SURVEY.md section 8a'): primitive pair functions and the
+// general convex path (MPR over support functions: cylinder, ellipsoid, mesh and every pair without a primitive).
 // One thread per environment walks the static candidate-pair list in order, so the contact order is the canonical
 // (pair index, emission index) order by construction and geom ids are reproducible bit for bit.
 // Conventions (MuJoCo docs, mjContact): dist < 0 is penetration, pos is the midpoint, frame row 0 is the normal from
@@ -17,7 +18,12 @@ template <typename T>
 struct RawCon { T dist, pos[3], n[3], tan[3]; };
 
 template <typename T>
-struct GeomW { T pos[3], mat[9], size[3]; };
+struct GeomW {
+  T pos[3], mat[9], size[3];
+  int type;         // geom type (general convex path)
+  const T* vert;    // mesh vertices in the geom frame (HBM, behind the staged part of the model blob)
+  int nvert;
+};
 
 template <typename T> __device__ __forceinline__ void mcol(T* r, const T* mat, int k) { r[0] = mat[k]; r[1] = mat[3 + k]; r[2] = mat[6 + k]; }
 
@@ -396,6 +402,293 @@ __device__ int d_box_box(RawCon<T>* out, const GeomW<T>& a, const GeomW<T>& b, T
   return cnt;
 }
 
+// ---- general convex pairs: Minkowski Portal Refinement (what MuJoCo's mjc_Convex runs through libccd) ----
+// One contact per pair: dist = margin - depth, normal = portal direction (geom1 -> geom2), pos = midpoint of the
+// witness points blended by the barycentric coordinates of the origin ray.  mpr_tolerance 1e-6, mpr_iterations 50.
+template <typename T> struct CcdEps;
+template <> struct CcdEps<float> { static __device__ __forceinline__ float v() { return 1.1920929e-7f; } };
+template <> struct CcdEps<double> { static __device__ __forceinline__ double v() { return 2.220446049250313e-16; } };
+template <typename T> __device__ __forceinline__ bool ccd_zero(T x) { return t_abs(x) < CcdEps<T>::v(); }
+template <typename T> __device__ __forceinline__ bool ccd_eq(T a, T b) {
+  const T ab = t_abs(a - b);
+  if (ab < CcdEps<T>::v()) return true;
+  return ab < CcdEps<T>::v() * t_max(t_abs(a), t_abs(b));
+}
+template <typename T> __device__ __forceinline__ T t_sgn(T x) { return x > 0 ? T(1) : (x < 0 ? T(-1) : T(0)); }
+template <typename T> __device__ __forceinline__ void ccd_normalize(T* v) { const T inv = T(1) / norm3(v); v[0] *= inv; v[1] *= inv; v[2] *= inv; }
+
+// geometry as the convex routine sees it: reals of type T, mesh vertices of the batch's storage type V
+template <typename T, typename V>
+struct GeomC {
+  T pos[3], mat[9], size[3];
+  int type;
+  const V* vert;
+  int nvert;
+};
+
+template <typename T, typename G>
+__device__ void d_support_geom(T* res, const G& g, const T* dir, T margin) {
+  T l[3], r[3] = {0, 0, 0};
+  for (int k = 0; k < 3; k++) l[k] = g.mat[k] * dir[0] + g.mat[3 + k] * dir[1] + g.mat[6 + k] * dir[2];
+  switch (g.type) {
+    case GEOM_SPHERE: for (int k = 0; k < 3; k++) r[k] = l[k] * g.size[0]; break;
+    case GEOM_CAPSULE:
+      for (int k = 0; k < 3; k++) r[k] = l[k] * g.size[0];
+      r[2] += t_sgn(l[2]) * g.size[1];
+      break;
+    case GEOM_ELLIPSOID: {
+      const T t[3] = {l[0] * g.size[0], l[1] * g.size[1], l[2] * g.size[2]};
+      const T n = norm3(t);
+      if (n >= Eps<T>::minval()) for (int k = 0; k < 3; k++) r[k] = g.size[k] * t[k] / n;
+      break;
+    }
+    case GEOM_CYLINDER: {
+      const T t = t_sqrt(l[0] * l[0] + l[1] * l[1]);
+      if (t > Eps<T>::minval()) { r[0] = l[0] / t * g.size[0]; r[1] = l[1] / t * g.size[0]; }
+      r[2] = t_sgn(l[2]) * g.size[1];
+      break;
+    }
+    case GEOM_BOX: for (int k = 0; k < 3; k++) r[k] = t_sgn(l[k]) * g.size[k]; break;
+    case GEOM_MESH: {
+      T best = T(-1e30);
+      int ib = 0;
+      for (int i = 0; i < g.nvert; i++) {
+        const T v = (T)g.vert[3 * i] * l[0] + (T)g.vert[3 * i + 1] * l[1] + (T)g.vert[3 * i + 2] * l[2];
+        if (v > best) { best = v; ib = i; }
+      }
+      if (g.nvert) { r[0] = (T)g.vert[3 * ib]; r[1] = (T)g.vert[3 * ib + 1]; r[2] = (T)g.vert[3 * ib + 2]; }
+      break;
+    }
+    default: break;
+  }
+  for (int k = 0; k < 3; k++)
+    res[k] = g.mat[3 * k] * r[0] + g.mat[3 * k + 1] * r[1] + g.mat[3 * k + 2] * r[2] + g.pos[k] + T(0.5) * margin * dir[k];
+}
+
+template <typename T> struct MprV { T v[3], v1[3], v2[3]; };
+
+template <typename T, typename G>
+__device__ __noinline__ void d_mpr_support(MprV<T>& s, const G& a, const G& b, const T* dir, T margin) {
+  const T nd[3] = {-dir[0], -dir[1], -dir[2]};
+  d_support_geom(s.v1, a, dir, margin);
+  d_support_geom(s.v2, b, nd, margin);
+  for (int k = 0; k < 3; k++) s.v[k] = s.v1[k] - s.v2[k];
+}
+
+template <typename T> __device__ __forceinline__ void d_sub3(T* r, const T* a, const T* b) { r[0] = a[0] - b[0]; r[1] = a[1] - b[1]; r[2] = a[2] - b[2]; }
+
+template <typename T>
+__device__ __forceinline__ void d_portal_dir(const MprV<T>* P, T* dir) {
+  T e1[3], e2[3];
+  d_sub3(e1, P[2].v, P[1].v);
+  d_sub3(e2, P[3].v, P[1].v);
+  cross3(dir, e1, e2);
+  ccd_normalize(dir);
+}
+
+template <typename T>
+__device__ __forceinline__ bool d_portal_reach_tol(const MprV<T>* P, const MprV<T>& v4, const T* dir) {
+  const T dv4 = dot3(v4.v, dir);
+  T d = dv4 - dot3(P[1].v, dir);
+  d = t_min(d, dv4 - dot3(P[2].v, dir));
+  d = t_min(d, dv4 - dot3(P[3].v, dir));
+  return ccd_eq(d, T(1e-6)) || d < T(1e-6);
+}
+
+template <typename T>
+__device__ __forceinline__ void d_expand_portal(MprV<T>* P, const MprV<T>& v4) {
+  T v4v0[3];
+  cross3(v4v0, v4.v, P[0].v);
+  int slot;
+  if (dot3(P[1].v, v4v0) > 0) slot = dot3(P[2].v, v4v0) > 0 ? 1 : 3;
+  else slot = dot3(P[3].v, v4v0) > 0 ? 2 : 1;
+  P[slot] = v4;
+}
+
+template <typename T>
+__device__ T d_point_seg_dist2(const T* x0, const T* b, T* wit) {
+  T d[3];
+  d_sub3(d, b, x0);
+  const T t = -dot3(x0, d) / dot3(d, d);
+  if (t < 0 || ccd_zero(t)) { wit[0] = x0[0]; wit[1] = x0[1]; wit[2] = x0[2]; }
+  else if (t > 1 || ccd_eq(t, T(1))) { wit[0] = b[0]; wit[1] = b[1]; wit[2] = b[2]; }
+  else { for (int k = 0; k < 3; k++) wit[k] = x0[k] + t * d[k]; }
+  return dot3(wit, wit);
+}
+
+template <typename T>
+__device__ T d_point_tri_dist2(const T* x0, const T* B, const T* Cc, T* wit) {
+  T d1[3], d2[3];
+  d_sub3(d1, B, x0);
+  d_sub3(d2, Cc, x0);
+  const T v = dot3(d1, d1), w = dot3(d2, d2), p = dot3(x0, d1), q = dot3(x0, d2), r = dot3(d1, d2);
+  const T div = w * v - r * r;
+  T s = -1, t = -1;
+  if (!ccd_zero(div)) { s = (q * r - w * p) / div; t = (-s * r - q) / w; }
+  if ((ccd_zero(s) || s > 0) && (ccd_eq(s, T(1)) || s < 1) && (ccd_zero(t) || t > 0) && (ccd_eq(t, T(1)) || t < 1) &&
+      (ccd_eq(t + s, T(1)) || t + s < 1)) {
+    for (int k = 0; k < 3; k++) wit[k] = x0[k] + s * d1[k] + t * d2[k];
+    return dot3(wit, wit);
+  }
+  T w2[3];
+  T dist = d_point_seg_dist2(x0, B, wit);
+  T d2s = d_point_seg_dist2(x0, Cc, w2);
+  if (d2s < dist) { dist = d2s; wit[0] = w2[0]; wit[1] = w2[1]; wit[2] = w2[2]; }
+  d2s = d_point_seg_dist2(B, Cc, w2);
+  if (d2s < dist) { dist = d2s; wit[0] = w2[0]; wit[1] = w2[1]; wit[2] = w2[2]; }
+  return dist;
+}
+
+template <typename T>
+__device__ void d_mpr_find_pos(const MprV<T>* P, T* pos) {
+  T dir[3], vec[3], b[4];
+  d_portal_dir(P, dir);
+  cross3(vec, P[1].v, P[2].v); b[0] = dot3(vec, P[3].v);
+  cross3(vec, P[3].v, P[2].v); b[1] = dot3(vec, P[0].v);
+  cross3(vec, P[0].v, P[1].v); b[2] = dot3(vec, P[3].v);
+  cross3(vec, P[2].v, P[1].v); b[3] = dot3(vec, P[0].v);
+  T sum = b[0] + b[1] + b[2] + b[3];
+  if (ccd_zero(sum) || sum < 0) {
+    b[0] = 0;
+    cross3(vec, P[2].v, P[3].v); b[1] = dot3(vec, dir);
+    cross3(vec, P[3].v, P[1].v); b[2] = dot3(vec, dir);
+    cross3(vec, P[1].v, P[2].v); b[3] = dot3(vec, dir);
+    sum = b[1] + b[2] + b[3];
+  }
+  const T inv = T(1) / sum;
+  for (int k = 0; k < 3; k++) {
+    T p1 = 0, p2 = 0;
+    for (int i = 0; i < 4; i++) { p1 += b[i] * P[i].v1[k]; p2 += b[i] * P[i].v2[k]; }
+    pos[k] = T(0.5) * (p1 * inv + p2 * inv);
+  }
+}
+
+template <typename T, typename G>
+__device__ __noinline__ int d_convex_convex(RawCon<T>* out, const G& a, const G& b, T margin) {
+  MprV<T> P[4], v4;
+  T dir[3], va[3], vb[3], pos[3], nrm[3], depth;
+  // portal discovery
+  for (int k = 0; k < 3; k++) { P[0].v1[k] = a.pos[k]; P[0].v2[k] = b.pos[k]; P[0].v[k] = a.pos[k] - b.pos[k]; }
+  if (ccd_zero(P[0].v[0]) && ccd_zero(P[0].v[1]) && ccd_zero(P[0].v[2])) P[0].v[0] += 10 * CcdEps<T>::v();
+  for (int k = 0; k < 3; k++) dir[k] = -P[0].v[k];
+  ccd_normalize(dir);
+  d_mpr_support(P[1], a, b, dir, margin);
+  T dt = dot3(P[1].v, dir);
+  if (ccd_zero(dt) || dt < 0) return 0;
+  cross3(dir, P[0].v, P[1].v);
+  if (ccd_zero(dot3(dir, dir))) {
+    if (ccd_zero(P[1].v[0]) && ccd_zero(P[1].v[1]) && ccd_zero(P[1].v[2])) return 0;  // touching: undefined normal
+    for (int k = 0; k < 3; k++) { pos[k] = T(0.5) * (P[1].v1[k] + P[1].v2[k]); nrm[k] = P[1].v[k]; }
+    depth = norm3(nrm);
+    ccd_normalize(nrm);
+    set_raw(out[0], margin - depth, pos, nrm);
+    return 1;
+  }
+  ccd_normalize(dir);
+  d_mpr_support(P[2], a, b, dir, margin);
+  dt = dot3(P[2].v, dir);
+  if (ccd_zero(dt) || dt < 0) return 0;
+  d_sub3(va, P[1].v, P[0].v);
+  d_sub3(vb, P[2].v, P[0].v);
+  cross3(dir, va, vb);
+  ccd_normalize(dir);
+  if (dot3(dir, P[0].v) > 0) {
+    const MprV<T> t = P[1]; P[1] = P[2]; P[2] = t;
+    for (int k = 0; k < 3; k++) dir[k] = -dir[k];
+  }
+  for (int guard = 0;; guard++) {
+    if (guard > 1000) return 0;
+    d_mpr_support(P[3], a, b, dir, margin);
+    dt = dot3(P[3].v, dir);
+    if (ccd_zero(dt) || dt < 0) return 0;
+    bool cont = false;
+    cross3(va, P[1].v, P[3].v);
+    dt = dot3(va, P[0].v);
+    if (dt < 0 && !ccd_zero(dt)) { P[2] = P[3]; cont = true; }
+    if (!cont) {
+      cross3(va, P[3].v, P[2].v);
+      dt = dot3(va, P[0].v);
+      if (dt < 0 && !ccd_zero(dt)) { P[1] = P[3]; cont = true; }
+    }
+    if (!cont) break;
+    d_sub3(va, P[1].v, P[0].v);
+    d_sub3(vb, P[2].v, P[0].v);
+    cross3(dir, va, vb);
+    ccd_normalize(dir);
+  }
+  // refinement
+  for (int guard = 0;; guard++) {
+    if (guard > 1000) return 0;
+    d_portal_dir(P, dir);
+    dt = dot3(dir, P[1].v);
+    if (ccd_zero(dt) || dt > 0) break;
+    d_mpr_support(v4, a, b, dir, margin);
+    dt = dot3(v4.v, dir);
+    if (!(ccd_zero(dt) || dt > 0) || d_portal_reach_tol(P, v4, dir)) return 0;
+    d_expand_portal(P, v4);
+  }
+  // penetration
+  for (int it = 0;; it++) {
+    d_portal_dir(P, dir);
+    d_mpr_support(v4, a, b, dir, margin);
+    if (d_portal_reach_tol(P, v4, dir) || it > 50) {
+      T wit[3];
+      depth = t_sqrt(d_point_tri_dist2(P[1].v, P[2].v, P[3].v, wit));
+      if (ccd_zero(wit[0]) && ccd_zero(wit[1]) && ccd_zero(wit[2])) { nrm[0] = dir[0]; nrm[1] = dir[1]; nrm[2] = dir[2]; }
+      else { nrm[0] = wit[0]; nrm[1] = wit[1]; nrm[2] = wit[2]; ccd_normalize(nrm); }
+      d_mpr_find_pos(P, pos);
+      set_raw(out[0], margin - depth, pos, nrm);
+      return 1;
+    }
+    d_expand_portal(P, v4);
+  }
+}
+
+// plane against ellipsoid / mesh: support point opposite to the normal (+ up to three more mesh vertices within the margin)
+template <typename T>
+__device__ __noinline__ int d_plane_convex(RawCon<T>* out, const GeomW<T>& a, const GeomW<T>& b, T margin) {
+  T n[3], nd[3], s[3], p[3], dif[3];
+  mcol(n, a.mat, 2);
+  for (int k = 0; k < 3; k++) nd[k] = -n[k];
+  d_support_geom(s, b, nd, T(0));
+  d_sub3(dif, s, a.pos);
+  const T dist = dot3(dif, n);
+  if (dist > margin) return 0;
+  for (int k = 0; k < 3; k++) p[k] = s[k] - T(0.5) * dist * n[k];
+  set_raw(out[0], dist, p, n);
+  int cnt = 1;
+  if (b.type == GEOM_MESH) {
+    int used[4] = {-1, -1, -1, -1};
+    {  // the support vertex itself (same argmax as d_support_geom)
+      T l[3];
+      for (int k = 0; k < 3; k++) l[k] = b.mat[k] * nd[0] + b.mat[3 + k] * nd[1] + b.mat[6 + k] * nd[2];
+      T best = T(-1e30);
+      for (int i = 0; i < b.nvert; i++) {
+        const T v = b.vert[3 * i] * l[0] + b.vert[3 * i + 1] * l[1] + b.vert[3 * i + 2] * l[2];
+        if (v > best) { best = v; used[0] = i; }
+      }
+    }
+    while (cnt < 4) {
+      int ib = -1;
+      T best = margin, wb[3] = {0, 0, 0};
+      for (int i = 0; i < b.nvert; i++) {
+        if (i == used[0] || i == used[1] || i == used[2] || i == used[3]) continue;
+        T w[3];
+        for (int k = 0; k < 3; k++) w[k] = b.mat[3 * k] * b.vert[3 * i] + b.mat[3 * k + 1] * b.vert[3 * i + 1] + b.mat[3 * k + 2] * b.vert[3 * i + 2] + b.pos[k];
+        d_sub3(dif, w, a.pos);
+        const T di = dot3(dif, n);
+        if (di < best || (di == best && ib < 0)) { best = di; ib = i; wb[0] = w[0]; wb[1] = w[1]; wb[2] = w[2]; }
+      }
+      if (ib < 0) break;
+      used[cnt] = ib;
+      for (int k = 0; k < 3; k++) p[k] = wb[k] - T(0.5) * best * n[k];
+      set_raw(out[cnt], best, p, n);
+      cnt++;
+    }
+  }
+  return cnt;
+}
+
 template <typename T>
 __device__ int narrow_phase(RawCon<T>* out, int t1, int t2, const GeomW<T>& a, const GeomW<T>& b, T margin) {
   T n[3];
@@ -418,7 +711,30 @@ __device__ int narrow_phase(RawCon<T>* out, int t1, int t2, const GeomW<T>& a, c
     case GEOM_CAPSULE * 8 + GEOM_CAPSULE: return d_capsule_capsule(out, a, b, margin);
     case GEOM_CAPSULE * 8 + GEOM_BOX: return d_capsule_box(out, a, b, margin);
     case GEOM_BOX * 8 + GEOM_BOX: return d_box_box(out, a, b, margin);
-    default: return 0;
+    case GEOM_PLANE * 8 + GEOM_ELLIPSOID: case GEOM_PLANE * 8 + GEOM_MESH: return d_plane_convex(out, a, b, margin);
+    default:
+      if (t1 >= GEOM_SPHERE && t2 <= GEOM_MESH) {
+        if constexpr (sizeof(T) == 4) {
+          // The general convex routine always runs in fp64.  MPR stops on a comparison against mpr_tolerance = 1e-6, which
+          // fp32 rounding (1e-7 on these sizes) moves by whole iterations: at shallow depths the fp32 normal was off by up
+          // to 0.2 (12 degrees) against the fp64 oracle on the same pose, while fp64 arithmetic on fp32-rounded poses stays
+          // within 7e-3.  Convex pairs are a small share of k_collide and B200 runs fp64 at half the fp32 rate.
+          GeomC<double, T> A, B;
+          for (int k = 0; k < 3; k++) { A.pos[k] = a.pos[k]; B.pos[k] = b.pos[k]; A.size[k] = a.size[k]; B.size[k] = b.size[k]; }
+          for (int k = 0; k < 9; k++) { A.mat[k] = a.mat[k]; B.mat[k] = b.mat[k]; }
+          A.type = a.type; A.vert = a.vert; A.nvert = a.nvert; B.type = b.type; B.vert = b.vert; B.nvert = b.nvert;
+          RawCon<double> o;
+          const int n = d_convex_convex<double>(&o, A, B, (double)margin);
+          if (n) {
+            out[0].dist = (T)o.dist;
+            for (int k = 0; k < 3; k++) { out[0].pos[k] = (T)o.pos[k]; out[0].n[k] = (T)o.n[k]; out[0].tan[k] = 0; }
+          }
+          return n;
+        } else {
+          return d_convex_convex<T>(out, a, b, margin);
+        }
+      }
+      return 0;
   }
 }
 
@@ -428,8 +744,9 @@ __host__ __device__ inline bool pair_supported(int t1, int t2) {
     case GEOM_PLANE * 8 + GEOM_BOX: case GEOM_SPHERE * 8 + GEOM_SPHERE: case GEOM_SPHERE * 8 + GEOM_CAPSULE:
     case GEOM_SPHERE * 8 + GEOM_CYLINDER: case GEOM_SPHERE * 8 + GEOM_BOX: case GEOM_CAPSULE * 8 + GEOM_CAPSULE:
     case GEOM_CAPSULE * 8 + GEOM_BOX: case GEOM_BOX * 8 + GEOM_BOX:
+    case GEOM_PLANE * 8 + GEOM_ELLIPSOID: case GEOM_PLANE * 8 + GEOM_MESH:
       return true;
-    default: return false;
+    default: return t1 >= GEOM_SPHERE && t2 <= GEOM_MESH;  // general convex path (MPR)
   }
 }
 
@@ -440,6 +757,9 @@ __device__ void load_geom(GeomW<T>& g, const MV<T>& m, const KArgs<T>& a, int gi
   for (int k = 0; k < 3; k++) g.pos[k] = a.geom_xpos[(3 * gi + k) * S + env];
   for (int k = 0; k < 9; k++) g.mat[k] = a.geom_xmat[(9 * gi + k) * S + env];
   for (int k = 0; k < 3; k++) g.size[k] = m.f(h.o_geom_size, 3 * gi + k);
+  g.type = m.i(h.o_geom_type, gi);
+  g.nvert = m.i(h.o_geom_vertnum, gi);
+  g.vert = reinterpret_cast<const T*>(a.model + h.o_mesh_vert) + 3 * m.i(h.o_geom_vertadr, gi);
 }
 
 template <typename T, int BLOCK>

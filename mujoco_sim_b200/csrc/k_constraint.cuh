@@ -480,12 +480,21 @@ template <typename T, int BLOCK>
 __global__ void __launch_bounds__(BLOCK) k_make_blocks(const KArgs<T> a) {
   const int blk = blockIdx.y;
   if (blk >= a.maxblk[0]) return;
-  B2_KERNEL_PROLOGUE
+  if ((a.flags & B2F_FUSABLE) && a.pending[0] == 0) return;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  // The kernel needs a few integer tables of the model (dof_parentid, dof_Madr, the tree table), warp-uniform or nearly
+  // so: they are read from the blob in HBM through L1 instead of staging a private copy per CTA.  For PR2-sized models
+  // the copy (29 KB) was more than the CTA's own columns (20 KB) and capped the SM at 4 resident warps.
+  const int nwords = 0;
+  MV<T> m{reinterpret_cast<const DModel*>(a.model), a.model};
+  const DModel& h = *m.h;
+  const long long S = a.nenvp;
+  const int ntiles = a.nenvp / BLOCK;
   constexpr int LDS = BLOCK + 1;  // +1: conflict-free both for per-thread columns and for the transposed reads
   // per thread (column): [0, npar) header + row parameters, then one base direction at a time: J_c [wqmax] | B_c [wqmax].
   // Streaming the base directions keeps the footprint at npar + 2 wq words per thread instead of the whole record
   // (PR2-sized trees: 156 instead of 468 words -> 4x the resident warps).
-  T* colsh = reinterpret_cast<T*>(smem_raw + 16 + (size_t)nwords * 4);
+  T* colsh = reinterpret_cast<T*>(smem_raw + (size_t)nwords * 4);
   const int npar = a.block_npar, wqmax = (h.wmax + 3) & ~3;
   const int lane = threadIdx.x & 31, wbase = threadIdx.x & ~31;
   const int capw = a.block_capw;

@@ -1,4 +1,5 @@
-// oracle_collision.cpp — fp64 CPU restatement of broad- and narrow-phase collision for the primitive geom pairs.
+// oracle_collision.cpp — fp64 CPU restatement of broad- and narrow-phase collision: primitive geom pairs and the
+// general convex path (MPR) for every other pair of convex geoms.
 // TEST INFRASTRUCTURE ONLY (see oracle.h).  PARITY UNPINNED: MuJoCo's collision functions are not in
 // /root/reference; conventions follow MuJoCo's docs (mjContact: dist < 0 = penetration, pos = midpoint,
 // frame[0:3] = normal pointing from geom1 to geom2; geom1 has the lower geom TYPE).  Contact order is canonical:
@@ -20,6 +21,9 @@ struct G {  // one geom in the world frame
   const mjtNum* pos;
   const mjtNum* mat;  // row-major; column k is local axis k
   const mjtNum* size;
+  int type = -1;               // mjtGeom (used by the general convex path only)
+  const mjtNum* vert = nullptr;  // mesh vertices in the geom frame, nvert x 3
+  int nvert = 0;
 };
 struct C {  // raw contact before parameter mixing
   mjtNum dist, pos[3], normal[3], tangent[3];
@@ -450,6 +454,298 @@ int box_box(C* out, const G& a, const G& b, mjtNum margin) {
   return cnt;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// General convex pairs (s5: "mjc_Convex").  MuJoCo hands every pair without a primitive function to libccd's
+// Minkowski Portal Refinement (ccdMPRPenetration; G. Snethen, "XenoCollide", Game Programming Gems 7) with its own
+// support functions, mpr_tolerance = 1e-6 and mpr_iterations = 50, and emits ONE contact: dist = margin - depth,
+// normal = MPR direction (from geom1 to geom2), pos = midpoint of the two witness points.  libccd is a third-party
+// dependency of the closed MuJoCo binary and absent here: the published algorithm is restated (portal discovery,
+// refinement until the origin ray crosses the portal, expansion until the support plane is within tolerance of the
+// portal, depth = distance from the origin to the portal triangle, position from the barycentric coordinates of the
+// origin-ray hit).  Parity unpinned like the rest of this file.
+const mjtNum kMprTol = 1e-6;
+const int kMprIter = 50;
+const mjtNum kCcdEps = 2.220446049250313e-16;
+
+inline bool ccd_zero(mjtNum x) { return std::fabs(x) < kCcdEps; }
+inline bool ccd_eq(mjtNum a, mjtNum b) {
+  const mjtNum ab = std::fabs(a - b);
+  if (ab < kCcdEps) return true;
+  const mjtNum fa = std::fabs(a), fb = std::fabs(b);
+  return ab < kCcdEps * (fb > fa ? fb : fa);
+}
+inline mjtNum sgn(mjtNum x) { return x > 0 ? 1.0 : (x < 0 ? -1.0 : 0.0); }
+
+// support point of one geom (world frame) in world direction `dir` (unit), inflated by margin / 2
+void support_geom(mjtNum* res, const G& g, const mjtNum* dir, mjtNum margin) {
+  mjtNum l[3], r[3] = {0, 0, 0};
+  mulMatTVec3(l, g.mat, dir);
+  switch (g.type) {
+    case mjGEOM_SPHERE: for (int k = 0; k < 3; k++) r[k] = l[k] * g.size[0]; break;
+    case mjGEOM_CAPSULE:
+      for (int k = 0; k < 3; k++) r[k] = l[k] * g.size[0];
+      r[2] += sgn(l[2]) * g.size[1];
+      break;
+    case mjGEOM_ELLIPSOID: {
+      const mjtNum t[3] = {l[0] * g.size[0], l[1] * g.size[1], l[2] * g.size[2]};
+      const mjtNum n = norm3(t);
+      if (n >= mjMINVAL) for (int k = 0; k < 3; k++) r[k] = g.size[k] * t[k] / n;
+      break;
+    }
+    case mjGEOM_CYLINDER: {
+      const mjtNum t = std::sqrt(l[0] * l[0] + l[1] * l[1]);
+      if (t > mjMINVAL) { r[0] = l[0] / t * g.size[0]; r[1] = l[1] / t * g.size[0]; }
+      r[2] = sgn(l[2]) * g.size[1];
+      break;
+    }
+    case mjGEOM_BOX: for (int k = 0; k < 3; k++) r[k] = sgn(l[k]) * g.size[k]; break;
+    case mjGEOM_MESH: {
+      mjtNum best = -1e300;
+      int ib = 0;
+      for (int i = 0; i < g.nvert; i++) {
+        const mjtNum v = dot3(g.vert + 3 * i, l);
+        if (v > best) { best = v; ib = i; }
+      }
+      if (g.nvert) copy(r, g.vert + 3 * ib, 3);
+      break;
+    }
+    default: break;
+  }
+  mulMatVec3(res, g.mat, r);
+  for (int k = 0; k < 3; k++) res[k] += g.pos[k] + 0.5 * margin * dir[k];
+}
+
+struct SV { mjtNum v[3], v1[3], v2[3]; };  // point of the Minkowski difference and its two witnesses
+
+void mpr_support(SV& s, const G& a, const G& b, const mjtNum* dir, mjtNum margin) {
+  const mjtNum nd[3] = {-dir[0], -dir[1], -dir[2]};
+  support_geom(s.v1, a, dir, margin);
+  support_geom(s.v2, b, nd, margin);
+  for (int k = 0; k < 3; k++) s.v[k] = s.v1[k] - s.v2[k];
+}
+
+inline void ccd_normalize(mjtNum* v) { const mjtNum n = norm3(v); for (int k = 0; k < 3; k++) v[k] /= n; }
+inline void sub3(mjtNum* r, const mjtNum* a, const mjtNum* b) { for (int k = 0; k < 3; k++) r[k] = a[k] - b[k]; }
+
+void portal_dir(const SV* P, mjtNum* dir) {
+  mjtNum e1[3], e2[3];
+  sub3(e1, P[2].v, P[1].v);
+  sub3(e2, P[3].v, P[1].v);
+  cross(dir, e1, e2);
+  ccd_normalize(dir);
+}
+
+bool portal_reach_tolerance(const SV* P, const SV& v4, const mjtNum* dir) {
+  const mjtNum dv4 = dot3(v4.v, dir);
+  mjtNum d = dv4 - dot3(P[1].v, dir);
+  d = std::min(d, dv4 - dot3(P[2].v, dir));
+  d = std::min(d, dv4 - dot3(P[3].v, dir));
+  return ccd_eq(d, kMprTol) || d < kMprTol;
+}
+
+void expand_portal(SV* P, const SV& v4) {
+  mjtNum v4v0[3];
+  cross(v4v0, v4.v, P[0].v);
+  if (dot3(P[1].v, v4v0) > 0) {
+    if (dot3(P[2].v, v4v0) > 0) P[1] = v4; else P[3] = v4;
+  } else {
+    if (dot3(P[3].v, v4v0) > 0) P[2] = v4; else P[1] = v4;
+  }
+}
+
+mjtNum point_seg_dist2(const mjtNum* x0, const mjtNum* b, mjtNum* wit) {  // from the origin
+  mjtNum d[3];
+  sub3(d, b, x0);
+  mjtNum t = -dot3(x0, d) / dot3(d, d);
+  if (t < 0 || ccd_zero(t)) { copy(wit, x0, 3); }
+  else if (t > 1 || ccd_eq(t, 1)) { copy(wit, b, 3); }
+  else { for (int k = 0; k < 3; k++) wit[k] = x0[k] + t * d[k]; }
+  return dot3(wit, wit);
+}
+
+// squared distance from the origin to triangle (x0, B, C) and the nearest point
+mjtNum point_tri_dist2(const mjtNum* x0, const mjtNum* B, const mjtNum* Cc, mjtNum* wit) {
+  mjtNum d1[3], d2[3];
+  sub3(d1, B, x0);
+  sub3(d2, Cc, x0);
+  const mjtNum v = dot3(d1, d1), w = dot3(d2, d2), p = dot3(x0, d1), q = dot3(x0, d2), r = dot3(d1, d2);
+  const mjtNum div = w * v - r * r;
+  mjtNum s = -1, t = -1;
+  if (!ccd_zero(div)) { s = (q * r - w * p) / div; t = (-s * r - q) / w; }
+  if ((ccd_zero(s) || s > 0) && (ccd_eq(s, 1) || s < 1) && (ccd_zero(t) || t > 0) && (ccd_eq(t, 1) || t < 1) &&
+      (ccd_eq(t + s, 1) || t + s < 1)) {
+    for (int k = 0; k < 3; k++) wit[k] = x0[k] + s * d1[k] + t * d2[k];
+    return dot3(wit, wit);
+  }
+  mjtNum w2[3];
+  mjtNum dist = point_seg_dist2(x0, B, wit);
+  mjtNum d2s = point_seg_dist2(x0, Cc, w2);
+  if (d2s < dist) { dist = d2s; copy(wit, w2, 3); }
+  d2s = point_seg_dist2(B, Cc, w2);
+  if (d2s < dist) { dist = d2s; copy(wit, w2, 3); }
+  return dist;
+}
+
+void mpr_find_pos(const SV* P, mjtNum* pos) {
+  mjtNum dir[3], vec[3], b[4];
+  portal_dir(P, dir);
+  cross(vec, P[1].v, P[2].v); b[0] = dot3(vec, P[3].v);
+  cross(vec, P[3].v, P[2].v); b[1] = dot3(vec, P[0].v);
+  cross(vec, P[0].v, P[1].v); b[2] = dot3(vec, P[3].v);
+  cross(vec, P[2].v, P[1].v); b[3] = dot3(vec, P[0].v);
+  mjtNum sum = b[0] + b[1] + b[2] + b[3];
+  if (ccd_zero(sum) || sum < 0) {
+    b[0] = 0;
+    cross(vec, P[2].v, P[3].v); b[1] = dot3(vec, dir);
+    cross(vec, P[3].v, P[1].v); b[2] = dot3(vec, dir);
+    cross(vec, P[1].v, P[2].v); b[3] = dot3(vec, dir);
+    sum = b[1] + b[2] + b[3];
+  }
+  const mjtNum inv = 1 / sum;
+  for (int k = 0; k < 3; k++) {
+    mjtNum p1 = 0, p2 = 0;
+    for (int i = 0; i < 4; i++) { p1 += b[i] * P[i].v1[k]; p2 += b[i] * P[i].v2[k]; }
+    pos[k] = 0.5 * (p1 * inv + p2 * inv);
+  }
+}
+
+// returns 1 and (depth, dir, pos) when the inflated geoms intersect
+int mpr_penetration(const G& a, const G& b, mjtNum margin, mjtNum& depth, mjtNum* dir_out, mjtNum* pos) {
+  SV P[4], v4;
+  mjtNum dir[3], va[3], vb[3];
+  // --- portal discovery ---
+  copy(P[0].v1, a.pos, 3);
+  copy(P[0].v2, b.pos, 3);
+  sub3(P[0].v, a.pos, b.pos);
+  if (ccd_zero(P[0].v[0]) && ccd_zero(P[0].v[1]) && ccd_zero(P[0].v[2])) P[0].v[0] += 10 * kCcdEps;
+  for (int k = 0; k < 3; k++) dir[k] = -P[0].v[k];
+  ccd_normalize(dir);
+  mpr_support(P[1], a, b, dir, margin);
+  mjtNum dt = dot3(P[1].v, dir);
+  if (ccd_zero(dt) || dt < 0) return 0;
+  cross(dir, P[0].v, P[1].v);
+  if (ccd_zero(dot3(dir, dir))) {
+    for (int k = 0; k < 3; k++) pos[k] = 0.5 * (P[1].v1[k] + P[1].v2[k]);
+    if (ccd_zero(P[1].v[0]) && ccd_zero(P[1].v[1]) && ccd_zero(P[1].v[2])) {  // touching: the normal is undefined, no contact
+      return 0;
+    }
+    depth = norm3(P[1].v);                                                    // origin on the segment v0-v1
+    copy(dir_out, P[1].v, 3);
+    ccd_normalize(dir_out);
+    return 1;
+  }
+  ccd_normalize(dir);
+  mpr_support(P[2], a, b, dir, margin);
+  dt = dot3(P[2].v, dir);
+  if (ccd_zero(dt) || dt < 0) return 0;
+  sub3(va, P[1].v, P[0].v);
+  sub3(vb, P[2].v, P[0].v);
+  cross(dir, va, vb);
+  ccd_normalize(dir);
+  if (dot3(dir, P[0].v) > 0) { std::swap(P[1], P[2]); for (int k = 0; k < 3; k++) dir[k] = -dir[k]; }
+  for (int guard = 0;; guard++) {
+    if (guard > 1000) return 0;
+    mpr_support(P[3], a, b, dir, margin);
+    dt = dot3(P[3].v, dir);
+    if (ccd_zero(dt) || dt < 0) return 0;
+    bool cont = false;
+    cross(va, P[1].v, P[3].v);
+    dt = dot3(va, P[0].v);
+    if (dt < 0 && !ccd_zero(dt)) { P[2] = P[3]; cont = true; }
+    if (!cont) {
+      cross(va, P[3].v, P[2].v);
+      dt = dot3(va, P[0].v);
+      if (dt < 0 && !ccd_zero(dt)) { P[1] = P[3]; cont = true; }
+    }
+    if (!cont) break;
+    sub3(va, P[1].v, P[0].v);
+    sub3(vb, P[2].v, P[0].v);
+    cross(dir, va, vb);
+    ccd_normalize(dir);
+  }
+  // --- refinement: until the portal faces the origin from outside ---
+  for (int guard = 0;; guard++) {
+    if (guard > 1000) return 0;
+    portal_dir(P, dir);
+    dt = dot3(dir, P[1].v);
+    if (ccd_zero(dt) || dt > 0) break;
+    mpr_support(v4, a, b, dir, margin);
+    dt = dot3(v4.v, dir);
+    if (!(ccd_zero(dt) || dt > 0) || portal_reach_tolerance(P, v4, dir)) return 0;
+    expand_portal(P, v4);
+  }
+  // --- penetration: expand until the support plane is within tolerance of the portal ---
+  for (int it = 0;; it++) {
+    portal_dir(P, dir);
+    mpr_support(v4, a, b, dir, margin);
+    if (portal_reach_tolerance(P, v4, dir) || it > kMprIter) {
+      mjtNum wit[3];
+      depth = std::sqrt(point_tri_dist2(P[1].v, P[2].v, P[3].v, wit));
+      if (ccd_zero(wit[0]) && ccd_zero(wit[1]) && ccd_zero(wit[2])) copy(dir_out, dir, 3);
+      else { copy(dir_out, wit, 3); ccd_normalize(dir_out); }
+      mpr_find_pos(P, pos);
+      return 1;
+    }
+    expand_portal(P, v4);
+  }
+}
+
+int convex_convex(C* out, const G& a, const G& b, mjtNum margin) {
+  mjtNum depth = 0, dir[3], pos[3];
+  if (!mpr_penetration(a, b, margin, depth, dir, pos)) return 0;
+  set_c(out[0], margin - depth, pos, dir);
+  return 1;
+}
+
+// plane against a convex geom without a primitive function (ellipsoid, mesh): the support point opposite to the plane
+// normal; a mesh adds up to three more vertices that are within the margin (MuJoCo walks the neighbours of the support
+// vertex in the qhull graph — the hull graph is not available here, so the candidates are all vertices, lowest first).
+int plane_convex(C* out, const G& a, const G& b, mjtNum margin) {
+  mjtNum n[3], nd[3], s[3], p[3];
+  col(n, a.mat, 2);
+  for (int k = 0; k < 3; k++) nd[k] = -n[k];
+  support_geom(s, b, nd, 0);
+  mjtNum dif[3];
+  sub3(dif, s, a.pos);
+  mjtNum dist = dot3(dif, n);
+  if (dist > margin) return 0;
+  axpy3(p, s, -0.5 * dist, n);
+  set_c(out[0], dist, p, n);
+  int cnt = 1;
+  if (b.type == mjGEOM_MESH) {
+    int used[4] = {-1, -1, -1, -1};
+    {  // index of the support vertex (same argmax as support_geom)
+      mjtNum l[3], best = -1e300;
+      mulMatTVec3(l, b.mat, nd);
+      for (int i = 0; i < b.nvert; i++) {
+        const mjtNum v = dot3(b.vert + 3 * i, l);
+        if (v > best) { best = v; used[0] = i; }
+      }
+    }
+    while (cnt < 4) {
+      int ib = -1;
+      mjtNum best = margin;
+      mjtNum wb[3] = {0, 0, 0};
+      for (int i = 0; i < b.nvert; i++) {
+        if (i == used[0] || i == used[1] || i == used[2] || i == used[3]) continue;
+        mjtNum w[3];
+        mulMatVec3(w, b.mat, b.vert + 3 * i);
+        for (int k = 0; k < 3; k++) w[k] += b.pos[k];
+        sub3(dif, w, a.pos);
+        const mjtNum di = dot3(dif, n);
+        if (di < best || (di == best && ib < 0)) { best = di; ib = i; copy(wb, w, 3); }
+      }
+      if (ib < 0) break;
+      used[cnt] = ib;
+      axpy3(p, wb, -0.5 * best, n);
+      set_c(out[cnt], best, p, n);
+      cnt++;
+    }
+  }
+  return cnt;
+}
+
 typedef int (*PairFn)(C*, const G&, const G&, mjtNum);
 PairFn pair_fn(int t1, int t2) {
   if (t1 == mjGEOM_PLANE) {
@@ -468,7 +764,9 @@ PairFn pair_fn(int t1, int t2) {
   } else if (t1 == mjGEOM_BOX && t2 == mjGEOM_BOX) {
     return box_box;
   }
-  return nullptr;  // general convex pairs (mesh, cylinder-box, ...) are not restated yet
+  if (t1 == mjGEOM_PLANE) return (t2 == mjGEOM_ELLIPSOID || t2 == mjGEOM_MESH) ? plane_convex : nullptr;
+  if (t1 >= mjGEOM_SPHERE && t1 != mjGEOM_HFIELD && t2 >= mjGEOM_SPHERE && t2 <= mjGEOM_MESH) return convex_convex;
+  return nullptr;
 }
 
 // complete the contact frame from the normal (and optional first-tangent hint)
@@ -494,6 +792,16 @@ void make_frame(mjtNum* frame, const mjtNum* normal, const mjtNum* hint) {
 
 extern "C" int omj_pair_supported(int t1, int t2) { return pair_fn(t1, t2) != nullptr; }
 
+// test hook: run the general convex path on two explicitly placed primitives; out = {dist, pos[3], normal[3]}
+extern "C" int omj_convex_pair(int t1, const mjtNum* pos1, const mjtNum* mat1, const mjtNum* size1, int t2, const mjtNum* pos2,
+                               const mjtNum* mat2, const mjtNum* size2, mjtNum margin, mjtNum* out) {
+  G a{pos1, mat1, size1, t1}, b{pos2, mat2, size2, t2};
+  C c[1];
+  const int n = convex_convex(c, a, b, margin);
+  if (n) { out[0] = c[0].dist; copy(out + 1, c[0].pos, 3); copy(out + 4, c[0].normal, 3); }
+  return n;
+}
+
 void omj_collision(const mjModel* m, mjData* d) {
   d->ncon = 0;
   if (m->opt.disableflags & (mjDSBL_CONSTRAINT | mjDSBL_CONTACT)) return;
@@ -518,7 +826,9 @@ void omj_collision(const mjModel* m, mjData* d) {
       const mjtNum bound = m->geom_rbound[g1] + m->geom_rbound[g2] + margin;
       if (dot3(dif, dif) > bound * bound) continue;
     }
-    G a{x1, d->geom_xmat + 9 * g1, m->geom_size + 3 * g1}, b{x2, d->geom_xmat + 9 * g2, m->geom_size + 3 * g2};
+    G a{x1, d->geom_xmat + 9 * g1, m->geom_size + 3 * g1, t1}, b{x2, d->geom_xmat + 9 * g2, m->geom_size + 3 * g2, t2};
+    if (t1 == mjGEOM_MESH) { const int id = m->geom_dataid[g1]; a.vert = m->mesh_vert + 3 * m->mesh_vertadr[id]; a.nvert = m->mesh_vertnum[id]; }
+    if (t2 == mjGEOM_MESH) { const int id = m->geom_dataid[g2]; b.vert = m->mesh_vert + 3 * m->mesh_vertadr[id]; b.nvert = m->mesh_vertnum[id]; }
     const int n = fn(raw, a, b, margin);
     for (int i = 0; i < n; i++) {
       if (d->ncon >= m->nconmax) return;  // cap reached: later pairs are dropped (flagged by the caller via ncon == nconmax)

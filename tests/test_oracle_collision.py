@@ -143,3 +143,65 @@ def test_contact_parameter_mixing(b2, orc):
     assert b2.lib.b2_data_contact(d.ptr, 0, C.byref(k)) == 0
     assert k.dim == 4 and list(k.friction) == [2, 2, 0.05, 0.01, 0.01]
     assert list(k.solref) == [0.02, 1] and list(k.solimp) == [0.9, 0.95, 0.001, 0.5, 2]
+
+
+# ---- general convex path (MPR): closed-form placements ----
+
+def test_convex_cylinder_box_face(b2, orc):
+    # upright cylinder (r 0.1, half-height 0.15) pushed 0.01 into the top face of a box whose top is at z = 0.05
+    cyl = free("y", "<geom type='cylinder' size='0.1 0.15'/>", "0.02 0.03 0.19")
+    box = free("b", "<geom type='box' size='0.3 0.3 0.05'/>", "0 0 0")
+    c = contacts(b2, orc, cyl + box)
+    assert len(c) == 1
+    dist, pos, n, g1, g2, dim = c[0]
+    assert abs(dist + 0.01) < 1e-6 and np.allclose(n, [0, 0, -1], atol=1e-6)   # cylinder (type 5) is geom1: normal points to the box
+    # libccd's MPR position is the barycentric blend of the portal witnesses and the geom centres (weight depth / |v0| along
+    # the origin ray), not the exact midpoint: 0.05 * 0.095 + 0.95 * 0.045
+    assert abs(pos[2] - 0.0475) < 1e-6
+    assert (g1, g2) == (0, 1)
+    # separated by 1 mm: no contact
+    assert not contacts(b2, orc, free("y", "<geom type='cylinder' size='0.1 0.15'/>", "0 0 0.201") + box)
+
+
+def test_convex_cylinder_cylinder_side(b2, orc):
+    # two parallel upright cylinders, axes 0.19 apart, radii 0.1: penetration 0.01 along x
+    a = free("a", "<geom type='cylinder' size='0.1 0.2'/>", "0 0 0")
+    b = free("b", "<geom type='cylinder' size='0.1 0.2'/>", "0.19 0 0.05")
+    c = contacts(b2, orc, a + b)
+    assert len(c) == 1
+    dist, pos, n, *_ = c[0]
+    # on curved faces MPR stops when the support plane is within mpr_tolerance (1e-6) of the portal: depth is good to ~1e-6,
+    # the normal only to ~sqrt(tolerance / radius)
+    assert abs(dist + 0.01) < 1e-5 and np.allclose(n, [1, 0, 0], atol=5e-3) and abs(pos[0] - 0.095) < 2e-3
+
+
+def test_convex_capsule_cylinder_and_ellipsoid(b2, orc):
+    # capsule (type 3) lying across the top of an upright cylinder (type 5): geom1 = capsule, normal points down
+    cap = free("c", "<geom type='capsule' size='0.05 0.2' quat='0.7071067811865476 0 0.7071067811865476 0'/>", "0 0 0.24")
+    cyl = free("y", "<geom type='cylinder' size='0.1 0.2'/>", "0 0 0")
+    c = contacts(b2, orc, cap + cyl)
+    assert len(c) == 1 and abs(c[0][0] + 0.01) < 1e-5 and np.allclose(c[0][2], [0, 0, -1], atol=5e-3)
+    # sphere (type 2) against an ellipsoid (type 4) along its long axis
+    s = free("s", "<geom size='0.1'/>", "0.39 0 0")
+    e = free("e", "<geom type='ellipsoid' size='0.3 0.1 0.1'/>", "0 0 0")
+    c = contacts(b2, orc, s + e)
+    assert len(c) == 1 and abs(c[0][0] + 0.01) < 1e-5 and np.allclose(c[0][2], [-1, 0, 0], atol=5e-3)
+    # plane against an ellipsoid: support point
+    c = contacts(b2, orc, "<geom type='plane' size='0 0 1'/>" + free("e", "<geom type='ellipsoid' size='0.3 0.2 0.1'/>", "0 0 0.095"))
+    assert len(c) == 1 and abs(c[0][0] + 0.005) < 1e-12 and np.allclose(c[0][2], [0, 0, 1])
+
+
+def test_convex_matches_primitive_on_box_box_depth(b2, orc):
+    # MPR and the box-box SAT routine must agree on depth and normal for a face-face placement (checked through a
+    # cylinder stand-in is not possible, so compare a rotated box pair via the convex entry point of the oracle)
+    import ctypes as C
+    from oracle import pyoracle as o
+    fn = o.olib.omj_convex_pair
+    fn.restype = C.c_int
+    size = (C.c_double * 3)(0.1, 0.2, 0.05)
+    pos1 = (C.c_double * 3)(0, 0, 0)
+    pos2 = (C.c_double * 3)(0.03, -0.02, 0.09)
+    eye = (C.c_double * 9)(1, 0, 0, 0, 1, 0, 0, 0, 1)
+    out = (C.c_double * 7)()
+    n = fn(6, pos1, eye, size, 6, pos2, eye, size, C.c_double(0.0), out)
+    assert n == 1 and abs(out[0] + 0.01) < 1e-6 and np.allclose(out[4:7], [0, 0, 1], atol=1e-6)
