@@ -352,6 +352,7 @@ def main():
     bt.sync()
     ncon_mean = float(bt.get("ncon").mean()) if m.npair > 0 else 0.0
     nefc_mean = float(bt.get("nefc").mean())
+    iter_mean = float(bt.get("solver_iter").mean()) if m.npair > 0 else 0.0
 
     # ---- device-timed region: K steps, inputs resident in HBM, CUDA events on the launching stream ----
     K = args.steps
@@ -429,7 +430,7 @@ def main():
         "ms_per_step": max_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "%s: %s" % (args.config, desc), "model": asset, "envs_per_gpu": nenv, "envs_total": total_envs,
                    "timestep": 0.005, "tick": ("step1+step2 with 8 of 20 object slots live per environment; one destroy + one spawn per environment every 60 ticks in the end-to-end loop" if slots else
-                            "write+step1+controller+inverse+step2+read" + (" with device-side PD (kp 200, kd 50) on %d arm joints" % nhw if kp is not None else "")), "mean_ncon": ncon_mean, "mean_nefc": nefc_mean,
+                            "write+step1+controller+inverse+step2+read" + (" with device-side PD (kp 200, kd 50) on %d arm joints" % nhw if kp is not None else "")), "mean_ncon": ncon_mean, "mean_nefc": nefc_mean, "mean_solver_iter": iter_mean,
                    "l2": "flushed before every timed step (256 MiB memset)" if flush else "not flushed",
                    "solver": "PGS, %d iterations max" % int(m.int("opt.iterations")), "kernels": bt.path_name,
                    "obs_allgather": ("NCCL all_gather of [qpos|qvel] fp32, %d B per rank per tick, inside the timed region" % (4 * nobs * nenv)) if gather else "none: shards are independent, no data-path collective"},

@@ -279,10 +279,12 @@ int configure_constraint_kernels(b2_batch* b) {
       SA((const void*)k_collide<double, 128>, need1); SA((const void*)k_integrate<double, 128>, need1);
       SA((const void*)k_make_rows<double, 128>, need1); SA((const void*)k_make_blocks<double, 128>, need2); SA((const void*)k_make_blocks<double, 32>, need2);
       SA((const void*)k_pgs_block<double, 4, 32, PGS_MINB>, need3); SA((const void*)k_pgs_block<double, 8, 32, PGS_MINB>, need3);
+      SA((const void*)k_pgs_block<double, 16, 32, PGS_MINB>, need3); SA((const void*)k_pgs_block<double, 32, 32, PGS_MINB>, need3);
     } else {
       SA((const void*)k_collide<float, 128>, need1); SA((const void*)k_integrate<float, 128>, need1);
       SA((const void*)k_make_rows<float, 128>, need1); SA((const void*)k_make_blocks<float, 128>, need2); SA((const void*)k_make_blocks<float, 32>, need2);
       SA((const void*)k_pgs_block<float, 4, 32, PGS_MINB>, need3); SA((const void*)k_pgs_block<float, 8, 32, PGS_MINB>, need3);
+      SA((const void*)k_pgs_block<float, 16, 32, PGS_MINB>, need3); SA((const void*)k_pgs_block<float, 32, 32, PGS_MINB>, need3);
     }
     if (!ok) return fail("cudaFuncSetAttribute failed");
   return 0;
@@ -402,6 +404,8 @@ int run_tick(b2_batch* b, int flags) {
       const size_t smp = ((size_t)2 * (b->hdr.nv + 4) + b->hdr.njmax + b->stage_cap) * epb * sizeof(T);
       const int g3 = b->nenvp / epb;
       if (b->pgs_lanes == 4) k_pgs_block<T, 4, PB, PGS_MINB><<<g3, PB, smp, b->stream>>>(a);
+      else if (b->pgs_lanes == 16) k_pgs_block<T, 16, PB, PGS_MINB><<<g3, PB, smp, b->stream>>>(a);
+      else if (b->pgs_lanes == 32) k_pgs_block<T, 32, PB, PGS_MINB><<<g3, PB, smp, b->stream>>>(a);
       else k_pgs_block<T, 8, PB, PGS_MINB><<<g3, PB, smp, b->stream>>>(a);
       prof_mark(b, SLOT_INTEGRATE);
       k_integrate<T, BL><<<g2, BL, sm, b->stream>>>(a);
@@ -773,8 +777,11 @@ b2_batch* b2_create(const mjModel* m, int nenv, int device, int precision) {
     b->block_capw = block_capacity(b->hdr.njmax, b->hdr.wmax);
     b->block_npar = block_max_params(nbmax);
     b->rec_max = b->block_npar + 2 * ((b->hdr.wmax + 3) & ~3);
-    b->pgs_lanes = getenv("B2_PGS_LANES") ? atoi(getenv("B2_PGS_LANES")) : 8;
-    if (b->pgs_lanes != 4) b->pgs_lanes = 8;
+    // team width of the solver: the narrowest of 8 / 16 / 32 lanes that holds the widest compact row in two elements per
+    // lane (the exact-shape visit's condition); PR2-sized trees (49 dofs) get a whole warp per environment
+    const int wm = b->hdr.wmax;
+    b->pgs_lanes = getenv("B2_PGS_LANES") ? atoi(getenv("B2_PGS_LANES")) : (wm <= 16 ? 8 : (wm <= 32 ? 16 : 32));
+    if (b->pgs_lanes != 4 && b->pgs_lanes != 16 && b->pgs_lanes != 32) b->pgs_lanes = 8;
   }
   struct Spec { const char* name; long long count; int kind; };
   std::vector<Spec> specs = {
