@@ -24,6 +24,7 @@ namespace b2 {
 using namespace hm;
 
 void set_const(ModelStore& S);  // set0.cpp: invweight0, subtreemass, meaninertia
+std::string urdf_to_mjcf(const XmlElem& robot);  // urdf_import.cpp
 
 namespace {
 
@@ -1027,15 +1028,20 @@ mjModel* compile_root(std::unique_ptr<XmlElem> root, const std::string& basedir,
 
 }  // namespace
 
-mjModel* compile_mjcf_string(const std::string& xml, const std::string& basedir) {
-  auto root = XmlParser(xml).parse();
-  return compile_root(std::move(root), basedir, xml);
+// A <robot> root is URDF (the reference's importer hands URDF files to mj_loadXML, src/mujoco_compile.cpp:404): it is
+// translated to MJCF first, and the translation becomes the model's source text (what mj_saveLastXML writes).
+mjModel* compile_text(const std::string& text, const std::string& basedir) {
+  auto root = XmlParser(text).parse();
+  if (root->name == "robot") {
+    const std::string mjcf = urdf_to_mjcf(*root);
+    auto r2 = XmlParser(mjcf).parse();
+    return compile_root(std::move(r2), basedir, mjcf);
+  }
+  return compile_root(std::move(root), basedir, text);
 }
 
-mjModel* compile_mjcf_file(const std::string& path) {
-  std::string text = read_file(path);
-  auto root = XmlParser(text).parse();
-  return compile_root(std::move(root), dir_of(path), text);
-}
+mjModel* compile_mjcf_string(const std::string& xml, const std::string& basedir) { return compile_text(xml, basedir); }
+
+mjModel* compile_mjcf_file(const std::string& path) { return compile_text(read_file(path), dir_of(path)); }
 
 }  // namespace b2

@@ -9,7 +9,7 @@ from . import engine
 CONFIGS = {
     # name: (model asset, default nenv, description)
     "c1": ("pendulum_world.xml", 1, "pendulum world, 1 env (plumbing)"),
-    "c2": ("panda7.xml", 4096, "Franka-Panda-like 7-DoF arm, contact-free forward dynamics"),
+    "c2": ("panda7.urdf", 4096, "Franka-Panda-like 7-DoF arm (URDF import), contact-free forward dynamics"),
     "c3": ("ur5_tabletop.xml", 16384, "UR5-like arm + tabletop objects with contacts, PGS"),
     "c4": ("pr2_like.xml", 8192, "PR2-shaped dual-arm robot (49 dofs, mimic-joint equalities, limits, wheel contacts) + PD computed-torque control"),
     "c5": ("multi_world.xml", 8192, "multi-robot world: 3 pendulum bobs + 20 object slots, run-time spawn / destroy as slot activation"),
