@@ -74,6 +74,11 @@ template <typename T> __device__ __forceinline__ T t_sqrt(T x);
 template <> __device__ __forceinline__ float t_sqrt<float>(float x) { return sqrtf(x); }
 template <> __device__ __forceinline__ double t_sqrt<double>(double x) { return sqrt(x); }
 template <typename T> __device__ __forceinline__ T t_abs(T x) { return x < 0 ? -x : x; }
+// explicit fused multiply-add / unfused product: where two code paths must round identically (shard invariance)
+__device__ __forceinline__ float t_fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+__device__ __forceinline__ double t_fma(double a, double b, double c) { return __fma_rn(a, b, c); }
+__device__ __forceinline__ float t_mul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double t_mul(double a, double b) { return __dmul_rn(a, b); }
 template <typename T> __device__ __forceinline__ T t_min(T a, T b) { return a < b ? a : b; }
 template <typename T> __device__ __forceinline__ T t_max(T a, T b) { return a > b ? a : b; }
 __device__ __forceinline__ void t_sincos(float x, float* s, float* c) { sincosf(x, s, c); }

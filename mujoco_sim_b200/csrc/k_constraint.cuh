@@ -702,7 +702,7 @@ __device__ __forceinline__ void pgs_visit(const T* __restrict__ rec, const Block
   for (int e = l; e < w; e += LANES) {
     const T xv = acc[bs.dof(e)];
 #pragma unroll
-    for (int k = 0; k < NBW; k++) if (k < nb) u[k] += rec[bs.oJ + k * wq + e] * xv;
+    for (int k = 0; k < NBW; k++) if (k < nb) u[k] = t_fma(rec[bs.oJ + k * wq + e], xv, u[k]);
   }
 #pragma unroll
   for (int o = LANES / 2; o > 0; o >>= 1) {
@@ -713,17 +713,18 @@ __device__ __forceinline__ void pgs_visit(const T* __restrict__ rec, const Block
   if (NBW == 1) v[0] = u[0];
   else {
 #pragma unroll
-    for (int r = 0; r < NROWW; r++) v[r] = nb > 1 ? u[0] + ((r & 1) ? -mu[r / 2] : mu[r / 2]) * u[r / 2 + 1] : u[0];
+    for (int r = 0; r < NROWW; r++) v[r] = nb > 1 ? t_fma((r & 1) ? -mu[r / 2] : mu[r / 2], u[r / 2 + 1], u[0]) : u[0];
   }
   bool any = false;
   {
     int q = 0;
 #pragma unroll
     for (int r = 0; r < NROWW; r++) {
-      const T res = v[r] + (R * fo[r] - aref[r]);
-      const T fn = t_min(hi, t_max(lo, fo[r] - res * iA[r]));
+      // (explicit fma / mul: pgs_visit_exact must round every one of these exactly the same way)
+      const T res = v[r] + t_fma(R, fo[r], -aref[r]);
+      const T fn = t_min(hi, t_max(lo, t_fma(-res, iA[r], fo[r])));
       T delta = fn - fo[r];
-      const T change = T(0.5) * delta * delta * Arr[r] + delta * res;
+      const T change = t_fma(t_mul(t_mul(T(0.5), delta), delta), Arr[r], t_mul(delta, res));
       const bool ok = r < nrow && delta != 0 && !(change > T(1e-10));
       delta = ok ? delta : T(0);
       improvement -= ok ? change : T(0);
@@ -731,7 +732,7 @@ __device__ __forceinline__ void pgs_visit(const T* __restrict__ rec, const Block
       any |= ok;
       dl[r] = delta;
 #pragma unroll
-      for (int c = r + 1; c < NROWW; c++, q++) v[c] += delta * cpl[q];
+      for (int c = r + 1; c < NROWW; c++, q++) v[c] = t_fma(delta, cpl[q], v[c]);
     }
   }
   if (any) {
@@ -756,7 +757,7 @@ __device__ __forceinline__ void pgs_visit(const T* __restrict__ rec, const Block
     for (int e = l; e < w; e += LANES) {
       T s0 = 0;
 #pragma unroll
-      for (int k = 0; k < NBW; k++) if (k < nb) s0 += d[k] * rec[bs.oB + k * wq + e];
+      for (int k = 0; k < NBW; k++) if (k < nb) s0 = t_fma(d[k], rec[bs.oB + k * wq + e], s0);
       acc[bs.dof(e)] += s0;
     }
   }
@@ -798,7 +799,9 @@ __device__ __forceinline__ void pgs_visit_exact(const T* __restrict__ rec, bool 
 #pragma unroll
   for (int k = 0; k < NB; k++) {
     const T j0 = in0 ? rec[oJ + k * wq + e0] : T(0), j1 = in1 ? rec[oJ + k * wq + e1] : T(0);
-    u[k] = j0 * x0 + j1 * x1;
+    // rounded exactly like the generic visit's lane-strided loop (u = 0; u = fma(j0, x0, u); u = fma(j1, x1, u)): which of
+    // the two visits a block gets depends on the other teams of the warp, and an environment's result must not
+    u[k] = t_fma(j1, x1, t_mul(j0, x0));
   }
   T b0[NB], b1[NB];   // this lane's elements of B, fetched early: their latency hides behind the reduction and the rows
 #pragma unroll
@@ -810,16 +813,16 @@ __device__ __forceinline__ void pgs_visit_exact(const T* __restrict__ rec, bool 
   }
   T v[NROW], dl[NROW];
 #pragma unroll
-  for (int r = 0; r < NROW; r++) v[r] = u[0] + ((r & 1) ? -PAR(oMu + r / 2) : PAR(oMu + r / 2)) * u[r / 2 + 1];
+  for (int r = 0; r < NROW; r++) v[r] = t_fma((r & 1) ? -PAR(oMu + r / 2) : PAR(oMu + r / 2), u[r / 2 + 1], u[0]);
   bool any = false;
   {
     int q = 0;
 #pragma unroll
     for (int r = 0; r < NROW; r++) {
-      const T res = v[r] + (R * fo[r] - PAR(oAref + r));
-      const T fn = t_max(T(0), fo[r] - res * PAR(oiA + r));
+      const T res = v[r] + t_fma(R, fo[r], -PAR(oAref + r));
+      const T fn = t_max(T(0), t_fma(-res, PAR(oiA + r), fo[r]));
       T delta = fn - fo[r];
-      const T change = T(0.5) * delta * delta * PAR(oArr + r) + delta * res;
+      const T change = t_fma(t_mul(t_mul(T(0.5), delta), delta), PAR(oArr + r), t_mul(delta, res));
       const bool ok = have && delta != 0 && !(change > T(1e-10));
       delta = ok ? delta : T(0);
       improvement -= ok ? change : T(0);
@@ -827,7 +830,7 @@ __device__ __forceinline__ void pgs_visit_exact(const T* __restrict__ rec, bool 
       any |= ok;
       dl[r] = delta;
 #pragma unroll
-      for (int c = r + 1; c < NROW; c++, q++) v[c] += delta * PAR(oA + q);
+      for (int c = r + 1; c < NROW; c++, q++) v[c] = t_fma(delta, PAR(oA + q), v[c]);
     }
   }
   if (any) {
@@ -845,7 +848,7 @@ __device__ __forceinline__ void pgs_visit_exact(const T* __restrict__ rec, bool 
     for (int k = 1; k < NB; k++) d[k] = PAR(oMu + k - 1) * (dl[2 * k - 2] - dl[2 * k - 1]);
     T a0 = 0, a1 = 0;
 #pragma unroll
-    for (int k = 0; k < NB; k++) { a0 += d[k] * b0[k]; a1 += d[k] * b1[k]; }
+    for (int k = 0; k < NB; k++) { a0 = t_fma(d[k], b0[k], a0); a1 = t_fma(d[k], b1[k], a1); }
     if (in0) acc[d0] = x0 + a0;
     if (in1) acc[d1] = x1 + a1;
   }
