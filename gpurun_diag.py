@@ -1,21 +1,47 @@
-import sys, os, time, numpy as np
-sys.path.insert(0, os.getcwd())
+"""where does the C2 end-to-end tick go?  resident+sync vs zero-copy host exchange vs staged copies"""
+import os, sys, time
+import numpy as np
+import torch
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import mujoco_sim_b200 as b2
 from mujoco_sim_b200 import workloads as w
-m = b2.Model(b2.asset("ur5_tabletop.xml"))
-bt = b2.Batch(m, 16384)
-w.load_config("c3", bt, env_offset=0)
-for _ in range(160): bt.step(1)
-bt.sync()
-ne = bt.get("nefc")[:,0]; nc = bt.get("ncon")[:,0]; it = bt.get("solver_iter")[:,0]; nw = bt.get("efc_nwords")[:,0]
-print("nefc mean %.1f max %d p99 %d | ncon mean %.1f max %d | nwords mean %.0f max %d p99 %d" % (ne.mean(), ne.max(), np.percentile(ne,99), nc.mean(), nc.max(), nw.mean(), nw.max(), np.percentile(nw,99)))
-print("iters: mean %.1f, ==100: %.3f, hist" % (it.mean(), (it==100).mean()), np.histogram(it, bins=[0,1,2,5,10,20,50,99,101])[0])
-print("nefc hist", np.histogram(ne, bins=[0,8,16,32,48,64,80,96,128,161])[0])
-for iters in (100, 50, 10, 1):
-    bt.set_option("iterations", iters)
-    bt.step(3); bt.sync()
-    bt.profile_begin(5)
-    for _ in range(5): bt.step(1)
+
+def run(tag):
+    m = b2.Model(b2.asset(w.CONFIGS["c2"][0]))
+    nenv = 4096
+    bt = b2.Batch(m, nenv)
+    w.load_config("c2", bt)
+    hw, ctl, kp, kd = w.control_spec("c2", m)
+    bt.set_controlled(ctl); bt.set_hw_joints(hw)
+    cmd = w.commands("c2", m, np.arange(nenv))
+    eff = torch.from_numpy(np.ascontiguousarray(cmd.T.astype(np.float32))).pin_memory()
+    vel = torch.zeros((hw.size, nenv), dtype=torch.float32).pin_memory()
+    outs = [torch.empty((hw.size, nenv), dtype=torch.float32).pin_memory() for _ in range(3)]
+    args = (vel.data_ptr(), eff.data_ptr(), *[o.data_ptr() for o in outs])
+    bt.write_commands(vel.numpy(), eff.numpy())
+    for _ in range(50):
+        bt.tick_host_raw(*args)
+    K = 2000
+    t0 = time.perf_counter()
+    for _ in range(K):
+        bt.tick_host_raw(*args)
+    t_host = (time.perf_counter() - t0) / K
+    for _ in range(50):
+        bt.tick_resident(); bt.sync()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        bt.tick_resident(); bt.sync()
+    t_res = (time.perf_counter() - t0) / K
+    t0 = time.perf_counter()
+    for _ in range(K):
+        bt.tick_resident()
     bt.sync()
-    n, ms = bt.profile_end()
-    print("iterations", iters, {k: round(v/n,3) for k,v in ms.items() if v>0})
+    t_async = (time.perf_counter() - t0) / K
+    t0 = time.perf_counter()
+    for _ in range(K):
+        bt.sync()
+    t_sync = (time.perf_counter() - t0) / K
+    print("%s: host-exchange tick %.1f us | resident tick + sync %.1f us | resident back-to-back %.1f us | empty sync call %.2f us" % (tag, t_host * 1e6, t_res * 1e6, t_async * 1e6, t_sync * 1e6))
+    bt.close()
+
+run("zero-copy" if os.environ.get("B2_NO_ZEROCOPY") != "1" else "staged copies")

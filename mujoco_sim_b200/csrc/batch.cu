@@ -145,6 +145,18 @@ int pack_model(b2_batch* b) {
     if (!std::strcmp(name, "dof_treeid")) { put_int(o, dof_tree.data(), n); return 0; }
     if (!std::strcmp(name, "tree_dofadr")) { put_int(o, tree_adr.data(), n); return 0; }
     if (!std::strcmp(name, "tree_dofnum")) { put_int(o, tree_num.data(), n); return 0; }
+    if (!std::strcmp(name, "dof_Mcnt") || !std::strcmp(name, "dof_anc")) {
+      // flattened ancestor lists in the layout of qM: the tree recursions index them instead of chasing dof_parentid,
+      // which turns a chain of dependent table loads per hop into independent, pipelinable ones
+      const bool cnt = name[5] == 'c';
+      for (int i = 0; i < nv; i++) {
+        int a = 0;
+        for (int j = i; j >= 0; j = m->dof_parentid[j], a++)
+          if (!cnt) b->blob[o + m->dof_Madr[i] + a] = (uint32_t)j;
+        if (cnt) b->blob[o + i] = (uint32_t)a;
+      }
+      return 0;
+    }
     if (!std::strcmp(name, "geom_vertadr") || !std::strcmp(name, "geom_vertnum")) {
       const bool adr = name[9] == 'a';
       for (int g = 0; g < n; g++) {
@@ -227,7 +239,7 @@ KArgs<T> build_args(b2_batch* b) {
   a.efc_id = I("efc_id"); a.efc_tree = I("efc_tree"); a.efc_J = R("efc_J"); a.efc_pos = R("efc_pos"); a.efc_margin = R("efc_margin");
   a.efc_frictionloss = R("efc_frictionloss"); a.efc_diagApprox = R("efc_diagApprox"); a.efc_R = R("efc_R"); a.efc_D = R("efc_D");
   a.efc_KBI = R("efc_KBI"); a.efc_vel = R("efc_vel"); a.efc_aref = R("efc_aref"); a.efc_b = R("efc_b"); a.efc_force = R("efc_force"); a.efc_finv = R("efc_finv");
-  a.efc_ARdiag = R("efc_ARdiag"); a.efc_blocks = R("efc_blocks"); a.efc_nwords = I("efc_nwords"); a.env_order = I("env_order");
+  a.efc_ARdiag = R("efc_ARdiag"); a.efc_B = R("efc_B"); a.efc_blocks = R("efc_blocks"); a.efc_nwords = I("efc_nwords"); a.env_order = I("env_order");
   a.blk_row0 = I("blk_row0"); a.blk_off = I("blk_off"); a.nblk = I("nblk"); a.maxblk = I("_maxblk"); a.solver_iter = I("solver_iter"); a.status = I("status");
   a.pending = I("_pending");
   return a;
@@ -273,6 +285,14 @@ int configure_constraint_kernels(b2_batch* b) {
     const int need3 = (int)(fixed + cap * epb * b->prec);
     if (need2 > 227 * 1024 || need3 > 227 * 1024) return fail("model too large for the constraint kernels' shared memory");
     b->pgs_ctas_per_sm = std::max(1, std::min(16, (int)(227 * 1024 / std::max(1, need3 + 1024))));
+    // k_solve_rows (wide trees): factor tile + one right-hand-side column per (row-warp, environment)
+    b->solve_rows = 0; b->solve_smem = 0;
+    if (b->make_block == 32 && b->fields.count("efc_B") && !getenv("B2_NO_SOLVE_ROWS")) {
+      for (int rows : {8, 4}) {
+        const size_t need = ((size_t)b->hdr.nM + b->hdr.nv + (size_t)rows * b->hdr.wmax) * 32 * b->prec;
+        if (need <= 200 * 1024) { b->solve_rows = rows; b->solve_smem = need; break; }
+      }
+    }
     bool ok = true;
     auto SA = [&](const void* fn, int need) { ok &= cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(need, 48 * 1024)) == cudaSuccess; };
     if (b->prec == 8) {
@@ -280,11 +300,13 @@ int configure_constraint_kernels(b2_batch* b) {
       SA((const void*)k_make_rows<double, 128>, need1); SA((const void*)k_make_blocks<double, 128>, need2); SA((const void*)k_make_blocks<double, 32>, need2);
       SA((const void*)k_pgs_block<double, 4, 32, PGS_MINB>, need3); SA((const void*)k_pgs_block<double, 8, 32, PGS_MINB>, need3);
       SA((const void*)k_pgs_block<double, 16, 32, PGS_MINB>, need3); SA((const void*)k_pgs_block<double, 32, 32, PGS_MINB>, need3);
+      SA((const void*)k_solve_rows<double, 8>, (int)b->solve_smem); SA((const void*)k_solve_rows<double, 4>, (int)b->solve_smem);
     } else {
       SA((const void*)k_collide<float, 128>, need1); SA((const void*)k_integrate<float, 128>, need1);
       SA((const void*)k_make_rows<float, 128>, need1); SA((const void*)k_make_blocks<float, 128>, need2); SA((const void*)k_make_blocks<float, 32>, need2);
       SA((const void*)k_pgs_block<float, 4, 32, PGS_MINB>, need3); SA((const void*)k_pgs_block<float, 8, 32, PGS_MINB>, need3);
       SA((const void*)k_pgs_block<float, 16, 32, PGS_MINB>, need3); SA((const void*)k_pgs_block<float, 32, 32, PGS_MINB>, need3);
+      SA((const void*)k_solve_rows<float, 8>, (int)b->solve_smem); SA((const void*)k_solve_rows<float, 4>, (int)b->solve_smem);
     }
     if (!ok) return fail("cudaFuncSetAttribute failed");
   return 0;
@@ -381,6 +403,13 @@ int run_tick(b2_batch* b, int flags) {
     prof_mark(b, SLOT_MAKE);
     CK(cudaMemsetAsync(a.maxblk, 0, sizeof(int), b->stream));
     k_make_rows<T, BL><<<g2, BL, sm, b->stream>>>(a);
+    if (b->solve_rows > 0) {
+      // wide trees: M^-1 J^T of all rows up front, the tile's factor shared through shared memory (k_solve_rows)
+      const int gs = std::max(1, std::min(b->nenvp / 32, b->nsm * std::max(1, (int)(227 * 1024 / (b->solve_smem + 1024)))));
+      if (b->solve_rows == 8) k_solve_rows<T, 8><<<gs, 256, b->solve_smem, b->stream>>>(a);
+      else k_solve_rows<T, 4><<<gs, 128, b->solve_smem, b->stream>>>(a);
+      b->launches++;
+    }
     {
       // one thread per (block, environment); CTAs of block ordinals beyond this tick's largest count exit at once
       const int mb = b->make_block;
@@ -804,6 +833,8 @@ b2_batch* b2_create(const mjModel* m, int nenv, int device, int precision) {
         {"efc_frictionloss", njmax, 0}, {"efc_diagApprox", njmax, 0}, {"efc_R", njmax, 0}, {"efc_D", njmax, 0}, {"efc_KBI", 3 * njmax, 0},
         {"efc_vel", njmax, 0}, {"efc_aref", njmax, 0}, {"efc_b", njmax, 0}, {"efc_force", njmax, 0}, {"efc_finv", njmax, 0}, {"efc_ARdiag", njmax, 0},
         {"efc_blocks", b->block_capw, 0}, {"efc_nwords", 1, 1}, {"env_order", 1, 1}, {"blk_row0", njmax, 1}, {"blk_off", njmax, 1}, {"nblk", 1, 1}, {"_maxblk", 1, 1}};
+    // wide trees (the criterion of make_block == 32): M^-1 J^T of every row is produced by k_solve_rows into efc_B
+    if ((size_t)b->rec_max * 129 * b->prec > 56 * 1024 && !getenv("B2_NO_SOLVE_ROWS")) more.push_back({"efc_B", njmax * b->hdr.wmax, 0});
     specs.insert(specs.end(), more.begin(), more.end());
   }
   for (auto& s : specs)

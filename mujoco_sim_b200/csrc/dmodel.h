@@ -19,6 +19,7 @@ namespace b2 {
   X(jnt_range, F, 2 * njnt) X(jnt_margin, F, njnt) X(jnt_solref, F, 2 * njnt) X(jnt_solimp, F, 5 * njnt)       \
   X(qpos0, F, nq) X(qpos_spring, F, nq)                                                                        \
   X(dof_bodyid, I, nv) X(dof_jntid, I, nv) X(dof_parentid, I, nv) X(dof_Madr, I, nv) X(dof_controlled, I, nv)  \
+  X(dof_Mcnt, I, nv) X(dof_anc, I, nM) /* row i of M: dof_Mcnt[i] entries, entry a belongs to dof_anc[dof_Madr[i] + a] */ \
   X(dof_armature, F, nv) X(dof_damping, F, nv) X(dof_frictionloss, F, nv) X(dof_invweight0, F, nv)             \
   X(dof_solref, F, 2 * nv) X(dof_solimp, F, 5 * nv)                                                            \
   X(geom_type, I, ngeom) X(geom_bodyid, I, ngeom) X(geom_condim, I, ngeom) X(geom_priority, I, ngeom)          \

@@ -60,6 +60,7 @@ struct KArgs {
   T *efc_pos, *efc_margin, *efc_frictionloss, *efc_diagApprox, *efc_R, *efc_D, *efc_KBI, *efc_vel, *efc_aref,
       *efc_b, *efc_force, *efc_finv; // [njmax][nenvp] (KBI: [3][njmax][nenvp]); efc_finv: primal force of mj_inverse per row
   T* efc_ARdiag;          // [njmax][nenvp] diagonal of J M^-1 J^T + R
+  T* efc_B;               // [njmax][wmax][nenvp] M^-1 J^T of every row, layout of efc_J; only for wide trees (k_solve_rows), else null
   T* efc_blocks;          // [nenvp][block_capw] environment-major block records streamed by the solver (k_constraint.cuh)
   int* efc_nwords;        // [nenvp] words of efc_blocks in use
   int* env_order;         // [nenvp] visit order of the solver (k_order_envs)

@@ -470,6 +470,62 @@ __global__ void __launch_bounds__(BLOCK) k_make_rows(const KArgs<T> a) {
   if ((threadIdx.x & 31) == 0 && wmaxblk > 0) atomicMax(a.maxblk, wmaxblk);
 }
 
+// K5a (wide trees only, e.g. a PR2: one 49-dof tree, nM = 492): B = M^-1 J^T for every row of every environment as a
+// kernel of its own.  A CTA owns a tile of 32 environments (lane = environment, so every global access is a coalesced
+// 128-byte run) and ROWS warps, one constraint row each per pass.  The tile's factor (qLD, qLDiagInv: what every solve
+// reads ~2 nM times) is loaded into shared memory ONCE and shared by all rows; each thread keeps its right-hand side as a
+// shared-memory column.  In k_make_blocks the same solve re-read the factor from HBM / L2 for every (row, environment):
+// 4.0 of the 12.7 ms of a PR2 tick.  Same loops, same operation order as that solve: results are bit-identical.
+template <typename T, int ROWS>
+__global__ void __launch_bounds__(32 * ROWS) k_solve_rows(const KArgs<T> a) {
+  if ((a.flags & B2F_FUSABLE) && a.pending[0] == 0) return;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  MV<T> m{reinterpret_cast<const DModel*>(a.model), a.model};
+  const DModel& h = *m.h;
+  const long long S = a.nenvp;
+  const int nM = h.nM, nv = h.nv, W = h.wmax;
+  T* LDs = reinterpret_cast<T*>(smem_raw);          // [nM][32]
+  T* dis = LDs + (size_t)nM * 32;                   // [nv][32]
+  T* Xs = dis + (size_t)nv * 32;                    // [ROWS][W][32]
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  const int ntiles = a.nenvp / 32;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int env = tile * 32 + lane;
+    __syncthreads();   // the previous tile's solves are done with the factor
+    for (int i = wrp; i < nM; i += ROWS) LDs[i * 32 + lane] = a.qLD[(long long)i * S + env];
+    for (int i = wrp; i < nv; i += ROWS) dis[i * 32 + lane] = a.qLDiagInv[(long long)i * S + env];
+    __syncthreads();
+    const int ne = a.nefc[env];
+    const int nemax = __reduce_max_sync(0xffffffffu, ne);
+    SArr<T> LD{LDs + lane, 32}, dinv{dis + lane, 32};
+    SArr<T> X{Xs + (size_t)wrp * W * 32 + lane, 32};
+    for (int r = wrp; r < nemax; r += ROWS) {
+      if (r >= ne) continue;
+      const Seg g = seg_of(m, a.efc_tree[((long long)2 * r) * S + env], a.efc_tree[((long long)2 * r + 1) * S + env]);
+      const int w = g.n1 + g.n2;
+      for (int e = 0; e < w; e++) X[e] = a.efc_J[((long long)r * W + e) * S + env];
+      for (int sgm = 0; sgm < 2; sgm++) {
+        const int lo = sgm ? g.s2 : g.s1, n = sgm ? g.n2 : g.n1, base = sgm ? g.n1 : 0;
+        if (n == 0) continue;
+        for (int i = lo + n - 1; i >= lo; i--) {
+          const T xi = X[base + i - lo];
+          if (xi == 0) continue;
+          const int adr = m.i(h.o_dof_Madr, i), cnt = m.i(h.o_dof_Mcnt, i);
+          for (int q = 1; q < cnt; q++) X[base + m.i(h.o_dof_anc, adr + q) - lo] -= LD[adr + q] * xi;
+        }
+        for (int i = lo; i < lo + n; i++) X[base + i - lo] *= dinv[i];
+        for (int i = lo; i < lo + n; i++) {
+          const int adr = m.i(h.o_dof_Madr, i), cnt = m.i(h.o_dof_Mcnt, i);
+          T xi = X[base + i - lo];
+          for (int q = 1; q < cnt; q++) xi -= LD[adr + q] * X[base + m.i(h.o_dof_anc, adr + q) - lo];
+          X[base + i - lo] = xi;
+        }
+      }
+      for (int e = 0; e < w; e++) a.efc_B[((long long)r * W + e) * S + env] = X[e];
+    }
+  }
+}
+
 // K5: the expensive, embarrassingly parallel part — one thread per (block, environment): vel, aref, b of the block's solver
 // rows, the primal force of mj_inverse per row, B = M^-1 J^T of the block's base directions by sparse back-substitution
 // inside its trees (in shared memory), the local matrix A, the couplings between the pyramid rows, diag(AR) per row, and
@@ -544,21 +600,25 @@ __global__ void __launch_bounds__(BLOCK) k_make_blocks(const KArgs<T> a) {
         }
         vel[c] = v0; js[c] = s0; jq[c] = q0;
         for (int e = w; e < wq; e++) { Jc[e] = 0; Bc[e] = 0; }
-        // B_c = M^-1 J_c^T, one tree at a time (M is block diagonal over trees)
+        // B_c = M^-1 J_c^T: precomputed by k_solve_rows for wide trees, else solved here one tree at a time (M is block
+        // diagonal over trees)
+        if (a.efc_B) {
+          for (int e = 0; e < w; e++) Bc[e] = a.efc_B[((long long)(r + c) * W + e) * S + env];
+        } else
         for (int sgm = 0; sgm < 2; sgm++) {
           const int lo = sgm ? g.s2 : g.s1, n = sgm ? g.n2 : g.n1, base = sgm ? g.n1 : 0;
           if (n == 0) continue;
           for (int i = lo + n - 1; i >= lo; i--) {
             const T xi = Bc[base + i - lo];
             if (xi == 0) continue;
-            int adr = m.i(h.o_dof_Madr, i) + 1;
-            for (int j = m.i(h.o_dof_parentid, i); j >= 0; j = m.i(h.o_dof_parentid, j)) Bc[base + j - lo] -= LD[adr++] * xi;
+            const int adr = m.i(h.o_dof_Madr, i), cnt = m.i(h.o_dof_Mcnt, i);
+            for (int q = 1; q < cnt; q++) Bc[base + m.i(h.o_dof_anc, adr + q) - lo] -= LD[adr + q] * xi;
           }
           for (int i = lo; i < lo + n; i++) Bc[base + i - lo] *= dinv[i];
           for (int i = lo; i < lo + n; i++) {
-            int adr = m.i(h.o_dof_Madr, i) + 1;
+            const int adr = m.i(h.o_dof_Madr, i), cnt = m.i(h.o_dof_Mcnt, i);
             T xi = Bc[base + i - lo];
-            for (int j = m.i(h.o_dof_parentid, i); j >= 0; j = m.i(h.o_dof_parentid, j)) xi -= LD[adr++] * Bc[base + j - lo];
+            for (int q = 1; q < cnt; q++) xi -= LD[adr + q] * Bc[base + m.i(h.o_dof_anc, adr + q) - lo];
             Bc[base + i - lo] = xi;
           }
         }

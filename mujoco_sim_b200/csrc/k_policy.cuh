@@ -25,7 +25,7 @@ struct GenericP {
   B2_TAB(body_parentid) B2_TAB(body_rootid) B2_TAB(body_mocapid) B2_TAB(body_jntnum) B2_TAB(body_jntadr)
   B2_TAB(body_dofnum) B2_TAB(body_dofadr) B2_TAB(body_lastdof) B2_TAB(jnt_type) B2_TAB(jnt_qposadr)
   B2_TAB(jnt_dofadr) B2_TAB(jnt_bodyid) B2_TAB(jnt_limited) B2_TAB(dof_bodyid) B2_TAB(dof_parentid) B2_TAB(dof_Madr)
-  B2_TAB(dof_controlled)
+  B2_TAB(dof_controlled) B2_TAB(dof_Mcnt) B2_TAB(dof_anc)
 #undef B2_TAB
   template <typename T> static __device__ __forceinline__ int nbody(const MV<T>& m) { return m.h->nbody; }
   template <typename T> static __device__ __forceinline__ int njnt(const MV<T>& m) { return m.h->njnt; }
@@ -56,6 +56,7 @@ struct ChainP {  // world -> body 1 -> ... -> body N, body b carries scalar join
   template <typename T> static __device__ __forceinline__ int dof_bodyid(const MV<T>&, int i) { return i + 1; }
   template <typename T> static __device__ __forceinline__ int dof_parentid(const MV<T>&, int i) { return i - 1; }
   template <typename T> static __device__ __forceinline__ int dof_Madr(const MV<T>&, int i) { return i * (i + 1) / 2; }
+  template <typename T> static __device__ __forceinline__ int dof_Mcnt(const MV<T>&, int i) { return i + 1; }
   template <typename T> static __device__ __forceinline__ int dof_controlled(const MV<T>& m, int i) { return m.i(m.h->o_dof_controlled, i); }
   template <typename T> static __device__ __forceinline__ int nbody(const MV<T>&) { return NBODY; }
   template <typename T> static __device__ __forceinline__ int njnt(const MV<T>&) { return NJNT; }

@@ -15,6 +15,21 @@ namespace b2 {
 // in-place sparse LtDL factorisation of the matrix stored in LD (tree order), dinv = 1 / D  (mj_factorM, A.4)
 template <typename P, typename T, typename A1, typename A2>
 __device__ __forceinline__ void ld_factor(const MV<T>& m, const A1& LD, const A2& dinv) {
+  if constexpr (!P::STATIC) {
+    // generic trees: the rows of M list a dof and its ancestors in order (dof_anc), so the ancestors of the a-th ancestor
+    // of k are the entries a.. of row k: no dof_parentid chasing, the inner loop is a plain axpy of known length
+    for (int k = P::nv(m) - 1; k >= 0; k--) {
+      const int Mkk = P::dof_Madr(m, k), cnt = P::dof_Mcnt(m, k);
+      const T inv = T(1) / LD[Mkk];
+      for (int a = 1; a < cnt; a++) {
+        const int Mki = Mkk + a, Mij = P::dof_Madr(m, P::dof_anc(m, Mki));
+        const T tmp = LD[Mki] * inv;
+        for (int t = 0; t < cnt - a; t++) LD[Mij + t] -= LD[Mki + t] * tmp;
+        LD[Mki] = tmp;
+      }
+      dinv[k] = inv;
+    }
+  } else {
 #pragma unroll(P::UNROLL)
   for (int k = P::nv(m) - 1; k >= 0; k--) {
     const int Mkk = P::dof_Madr(m, k);
@@ -30,15 +45,30 @@ __device__ __forceinline__ void ld_factor(const MV<T>& m, const A1& LD, const A2
     }
     dinv[k] = inv;
   }
+  }
 }
 // x <- M^-1 x by back / forward substitution on the factor (mj_solveM)
 template <typename P, typename T, typename A1, typename A2, typename A3>
 __device__ __forceinline__ void ld_solve(const MV<T>& m, const A1& LD, const A2& dinv, const A3& x) {
   const int nv = P::nv(m);
+  if constexpr (!P::STATIC) {
+    for (int i = nv - 1; i >= 0; i--) {
+      const T xi = x[i];
+      if (xi == 0) continue;
+      const int adr = P::dof_Madr(m, i), cnt = P::dof_Mcnt(m, i);
+      for (int a = 1; a < cnt; a++) x[P::dof_anc(m, adr + a)] -= LD[adr + a] * xi;
+    }
+    for (int i = 0; i < nv; i++) x[i] *= dinv[i];
+    for (int i = 0; i < nv; i++) {
+      const int adr = P::dof_Madr(m, i), cnt = P::dof_Mcnt(m, i);
+      T xi = x[i];
+      for (int a = 1; a < cnt; a++) xi -= LD[adr + a] * x[P::dof_anc(m, adr + a)];
+      x[i] = xi;
+    }
+  } else {
 #pragma unroll(P::UNROLL)
   for (int i = nv - 1; i >= 0; i--) {
     const T xi = x[i];
-    if (!P::STATIC && xi == 0) continue;
     int adr = P::dof_Madr(m, i) + 1;
 #pragma unroll(P::UNROLL)
     for (int j = P::dof_parentid(m, i); j >= 0; j = P::dof_parentid(m, j)) x[j] -= LD[adr++] * xi;
@@ -52,6 +82,7 @@ __device__ __forceinline__ void ld_solve(const MV<T>& m, const A1& LD, const A2&
 #pragma unroll(P::UNROLL)
     for (int j = P::dof_parentid(m, i); j >= 0; j = P::dof_parentid(m, j)) xi -= LD[adr++] * x[j];
     x[i] = xi;
+  }
   }
 }
 
@@ -332,6 +363,16 @@ struct Smooth {
       ld<T, 6>(cd, cdof, 6 * i);
       mul_inert_vec(buf, ci, cd);
       T v = m.f(h.o_dof_armature, i);
+      if constexpr (!P::STATIC) {
+        const int cnt = P::dof_Mcnt(m, i);
+        for (int a = 0; a < cnt; a++) {   // row i of M over the flattened ancestor list (no dof_parentid chasing)
+          T cj[6];
+          ld<T, 6>(cj, cdof, 6 * P::dof_anc(m, adr + a));
+          v += cj[0] * buf[0] + cj[1] * buf[1] + cj[2] * buf[2] + cj[3] * buf[3] + cj[4] * buf[4] + cj[5] * buf[5];
+          qM[adr + a] = v;
+          v = 0;
+        }
+      } else {
 #pragma unroll(P::UNROLL)
       for (int j = i; j >= 0; j = P::dof_parentid(m, j)) {
         T cj[6];
@@ -339,6 +380,7 @@ struct Smooth {
         v += cj[0] * buf[0] + cj[1] * buf[1] + cj[2] * buf[2] + cj[3] * buf[3] + cj[4] * buf[4] + cj[5] * buf[5];
         qM[adr++] = v;
         v = 0;
+      }
       }
     }
   }
@@ -354,6 +396,16 @@ struct Smooth {
       int adr = P::dof_Madr(m, i);
       const T vi = vec[i];
       T ri = res[i] + qM[adr] * vi;
+      if constexpr (!P::STATIC) {
+        const int cnt = P::dof_Mcnt(m, i);
+        for (int a = 1; a < cnt; a++) {
+          const int j = P::dof_anc(m, adr + a);
+          const T mij = qM[adr + a];
+          ri += mij * vec[j];
+          res[j] += mij * vi;
+        }
+        res[i] = ri;
+      } else {
       adr++;
 #pragma unroll(P::UNROLL)
       for (int j = P::dof_parentid(m, i); j >= 0; j = P::dof_parentid(m, j), adr++) {
@@ -362,6 +414,7 @@ struct Smooth {
         res[j] += mij * vi;
       }
       res[i] = ri;
+      }
     }
   }
 
