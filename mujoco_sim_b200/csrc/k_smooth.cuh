@@ -138,6 +138,7 @@ struct Smooth {
   // state: views of the HBM arrays (GenericP) or thread-private copies loaded once (ChainP)
   typename P::template Arr<T, nq> qpos;
   typename P::template Arr<T, nv> qvel, qacc, qfrc_applied, qfrc_bias;
+  bool aliased = false;  // the exported stage arrays are the working arrays (GenericP with the workspace in HBM)
 #define X(name, count) typename P::template Arr<T, (count)> name;
   B2_WS_ARRAYS(X)
 #undef X
@@ -154,6 +155,18 @@ struct Smooth {
 #define X(name, count) name = SArr<T>{wsbase + (long long)h.w_##name * wsstride, wsstride};
       B2_WS_ARRAYS(X)
 #undef X
+      // workspace in HBM: the stage results the constraint pipeline reads are computed in place in their exported arrays
+      // (same [element][env] layout) instead of in scratch slots that are copied out at the end — the copy was half of the
+      // kernel's DRAM traffic and a third of the scratch footprint that has to stay L2-resident
+      // (only when the constraint pipeline always follows: a kernel that integrates by itself reuses qLD as scratch)
+      aliased = (args.flags & B2F_WS_GLOBAL) && !(args.flags & (B2F_FUSED | B2F_FUSABLE)) && args.xmat != nullptr;
+      if (aliased) {
+        xpos = SArr<T>{args.xpos + env, s}; xquat = SArr<T>{args.xquat + env, s}; xmat = SArr<T>{args.xmat + env, s};
+        subtree_com = SArr<T>{args.subtree_com + env, s}; cdof = SArr<T>{args.cdof + env, s};
+        qM = SArr<T>{args.qM + env, s}; qLD = SArr<T>{args.qLD + env, s}; qLDiagInv = SArr<T>{args.qLDiagInv + env, s};
+        qfrc_passive = SArr<T>{args.qfrc_passive + env, s}; qfrc_smooth = SArr<T>{args.qfrc_smooth + env, s};
+        qacc_smooth = SArr<T>{args.qacc_smooth + env, s};
+      }
     } else {
 #pragma unroll
       for (int i = 0; i < nq; i++) qpos[i] = args.qpos[i * s + env];
@@ -703,10 +716,12 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_smooth(const KArgs<T> a) {
     ld_solve<P>(m, s.qLD, s.qLDiagInv, s.qacc_smooth);
 
     // body poses for the ROS layer (tf / marker publishers read d->xpos, d->xquat: SURVEY.md Appendix C)
+    if (!s.aliased) {
 #pragma unroll(P::UNROLL)
-    for (int i = 0; i < 3 * nb; i++) a.xpos[i * S + env] = s.xpos[i];
+      for (int i = 0; i < 3 * nb; i++) a.xpos[i * S + env] = s.xpos[i];
 #pragma unroll(P::UNROLL)
-    for (int i = 0; i < 4 * nb; i++) a.xquat[i * S + env] = s.xquat[i];
+      for (int i = 0; i < 4 * nb; i++) a.xquat[i * S + env] = s.xquat[i];
+    }
 
     // does this environment need the constraint pipeline this tick?
     bool pipeline = !(a.flags & B2F_FUSED);
@@ -729,20 +744,22 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_smooth(const KArgs<T> a) {
 
     if (pipeline || (a.flags & B2F_EXPORT)) {
       // export the stage results the constraint pipeline (and the legacy mjData mirror) consume
+      if (!s.aliased) {
 #pragma unroll(P::UNROLL)
-      for (int i = 0; i < 9 * nb; i++) a.xmat[i * S + env] = s.xmat[i];
+        for (int i = 0; i < 9 * nb; i++) a.xmat[i * S + env] = s.xmat[i];
 #pragma unroll(P::UNROLL)
-      for (int i = 0; i < 3 * nb; i++) a.subtree_com[i * S + env] = s.subtree_com[i];
+        for (int i = 0; i < 3 * nb; i++) a.subtree_com[i * S + env] = s.subtree_com[i];
 #pragma unroll(P::UNROLL)
-      for (int i = 0; i < 6 * nv; i++) a.cdof[i * S + env] = s.cdof[i];
+        for (int i = 0; i < 6 * nv; i++) a.cdof[i * S + env] = s.cdof[i];
 #pragma unroll(P::UNROLL)
-      for (int i = 0; i < nM; i++) { a.qM[i * S + env] = s.qM[i]; a.qLD[i * S + env] = s.qLD[i]; }
+        for (int i = 0; i < nM; i++) { a.qM[i * S + env] = s.qM[i]; a.qLD[i * S + env] = s.qLD[i]; }
 #pragma unroll(P::UNROLL)
-      for (int i = 0; i < nv; i++) {
-        a.qLDiagInv[i * S + env] = s.qLDiagInv[i];
-        a.qfrc_passive[i * S + env] = s.qfrc_passive[i];
-        a.qfrc_smooth[i * S + env] = s.qfrc_smooth[i];
-        a.qacc_smooth[i * S + env] = s.qacc_smooth[i];
+        for (int i = 0; i < nv; i++) {
+          a.qLDiagInv[i * S + env] = s.qLDiagInv[i];
+          a.qfrc_passive[i * S + env] = s.qfrc_passive[i];
+          a.qfrc_smooth[i * S + env] = s.qfrc_smooth[i];
+          a.qacc_smooth[i * S + env] = s.qacc_smooth[i];
+        }
       }
       s.geoms(env);
       if (P::STATIC && overridden) {

@@ -37,8 +37,8 @@ def main():
             wr = float(r[col["dram__bytes_write.sum"]]) * UNIT.get(units[col["dram__bytes_write.sum"]], 1.0)
             short = name.split("<")[0].replace("void ", "").replace("b2::", "")
             key = {"k_smooth": "smooth", "k_chain": "smooth", "k_chain_team": "smooth", "k_collide": "collide", "k_make_constraint": "make_constraint",
-                   "k_make_rows": "make_constraint", "k_make_blocks": "make_constraint", "k_pgs_block": "pgs", "k_integrate": "integrate"}.get(short, short)
-            traffic[key] = traffic.get(key, 0) + int(rd + wr)   # bench.py's make_constraint slot = k_make_rows + k_make_blocks
+                   "k_make_rows": "make_constraint", "k_make_blocks": "make_constraint", "k_solve_rows": "make_constraint", "k_pgs_block": "pgs", "k_integrate": "integrate"}.get(short, short)
+            traffic[key] = traffic.get(key, 0) + int(rd + wr)   # bench.py's make_constraint slot = k_make_rows (+ k_solve_rows) + k_make_blocks
         except Exception:
             pass
     if "--traffic" in sys.argv:
