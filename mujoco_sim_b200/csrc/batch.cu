@@ -269,6 +269,7 @@ int configure_constraint_kernels(b2_batch* b) {
   if (b->fused) return 0;
     // the constraint-pipeline kernels stage the same blob; row assembly and the solver add their shared vectors
     const int need1 = (int)b->blob_smem;
+    const int need1i = (int)(b->blob_smem + b->ld_smem);
     // row assembly: one record column per thread; 128-thread CTAs when that fits, else 32
     // (k_make_blocks reads the model from HBM: its shared memory is the record columns only)
     b->make_block = (size_t)b->rec_max * 129 * b->prec <= 56 * 1024 ? 128 : 32;
@@ -296,13 +297,15 @@ int configure_constraint_kernels(b2_batch* b) {
     bool ok = true;
     auto SA = [&](const void* fn, int need) { ok &= cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(need, 48 * 1024)) == cudaSuccess; };
     if (b->prec == 8) {
-      SA((const void*)k_collide<double, 128>, need1); SA((const void*)k_integrate<double, 128>, need1);
+      SA((const void*)k_collide<double, 128>, need1); SA((const void*)k_integrate<double, 128>, need1i);
+      SA((const void*)k_integrate<double, 64>, need1i); SA((const void*)k_integrate<double, 32>, need1i);
       SA((const void*)k_make_rows<double, 128>, need1); SA((const void*)k_make_blocks<double, 128>, need2); SA((const void*)k_make_blocks<double, 32>, need2);
       SA((const void*)k_pgs_block<double, 4, 32, PGS_MINB>, need3); SA((const void*)k_pgs_block<double, 8, 32, PGS_MINB>, need3);
       SA((const void*)k_pgs_block<double, 16, 32, PGS_MINB>, need3); SA((const void*)k_pgs_block<double, 32, 32, PGS_MINB>, need3);
       SA((const void*)k_solve_rows<double, 8>, (int)b->solve_smem); SA((const void*)k_solve_rows<double, 4>, (int)b->solve_smem);
     } else {
-      SA((const void*)k_collide<float, 128>, need1); SA((const void*)k_integrate<float, 128>, need1);
+      SA((const void*)k_collide<float, 128>, need1); SA((const void*)k_integrate<float, 128>, need1i);
+      SA((const void*)k_integrate<float, 64>, need1i); SA((const void*)k_integrate<float, 32>, need1i);
       SA((const void*)k_make_rows<float, 128>, need1); SA((const void*)k_make_blocks<float, 128>, need2); SA((const void*)k_make_blocks<float, 32>, need2);
       SA((const void*)k_pgs_block<float, 4, 32, PGS_MINB>, need3); SA((const void*)k_pgs_block<float, 8, 32, PGS_MINB>, need3);
       SA((const void*)k_pgs_block<float, 16, 32, PGS_MINB>, need3); SA((const void*)k_pgs_block<float, 32, 32, PGS_MINB>, need3);
@@ -359,6 +362,7 @@ int run_tick(b2_batch* b, int flags) {
   if (b->fused) kf |= B2F_FUSED;
   if (flags & B2_TICK_NOSOLVE) kf |= B2F_NOSOLVE;
   if (b->ws_global) kf |= B2F_WS_GLOBAL;
+  if (b->ws_global && b->ld_smem) kf |= B2F_LD_SMEM;
   if (b->fusable) kf |= B2F_FUSABLE;
   if (b->tick_flags & (1 << 30)) kf |= B2F_XFRC;  // set once xfrc_applied has been written
   if (b->export_stages) kf |= B2F_EXPORT;
@@ -437,7 +441,15 @@ int run_tick(b2_batch* b, int flags) {
       else if (b->pgs_lanes == 32) k_pgs_block<T, 32, PB, PGS_MINB><<<g3, PB, smp, b->stream>>>(a);
       else k_pgs_block<T, 8, PB, PGS_MINB><<<g3, PB, smp, b->stream>>>(a);
       prof_mark(b, SLOT_INTEGRATE);
-      k_integrate<T, BL><<<g2, BL, sm, b->stream>>>(a);
+      if (kf & B2F_LD_SMEM) {
+        const size_t smi = sm + b->ld_smem;
+        const int bi = b->smooth_block, gi = std::max(1, std::min(b->nenvp / bi, b->nsm * 8));
+        if (bi == 128) k_integrate<T, 128><<<gi, 128, smi, b->stream>>>(a);
+        else if (bi == 64) k_integrate<T, 64><<<gi, 64, smi, b->stream>>>(a);
+        else k_integrate<T, 32><<<gi, 32, smi, b->stream>>>(a);
+      } else {
+        k_integrate<T, BL><<<g2, BL, sm, b->stream>>>(a);
+      }
       b->launches += 2;
     }
   }
@@ -866,6 +878,13 @@ b2_batch* b2_create(const mjModel* m, int nenv, int device, int precision) {
     b->smooth_block = 128;
     b->smooth_smem = b->blob_smem;
     b->ws_global = true;
+    // factor scratch in shared memory (B2F_LD_SMEM): (nM + 2 nv) words per thread, the widest CTA that leaves two CTAs per SM
+    b->ld_smem = 0;
+    if (!getenv("B2_NO_LD_SMEM"))
+      for (int cand : {128, 64, 32}) {
+        const size_t need = b->blob_smem + (size_t)(b->hdr.nM + 2 * b->hdr.nv) * cand * precision;
+        if (need <= 110 * 1024) { b->smooth_block = cand; b->ld_smem = need - b->blob_smem; b->smooth_smem = need; break; }
+      }
     if (alloc_field(b, "_ws", b->hdr.ws_slots, 0, nullptr) < 0) return bail("alloc failed");
   }
   if (configure_constraint_kernels(b) < 0) return bail("constraint kernel configuration failed");
@@ -970,7 +989,7 @@ int b2_set_odom(b2_batch* b, int nrobot, const int* dof, const int* qposadr) {
   }
   b->blob_smem = 16 + (size_t)b->hdr.nwords * 4;
   if (!b->ws_global) b->smooth_smem = b->blob_smem + (size_t)b->hdr.ws_slots * b->smooth_block * b->prec;
-  else b->smooth_smem = b->blob_smem;
+  else b->smooth_smem = b->blob_smem + b->ld_smem;
   if (configure_constraint_kernels(b) < 0) return -1;
   return 0;
 }

@@ -1199,6 +1199,13 @@ __global__ void __launch_bounds__(BLOCK) k_integrate(const KArgs<T> a) {
     if (a.flags & B2F_INTEGRATE) {
       SArr<T> qpos{a.qpos + env, S}, qvel{a.qvel + env, S}, qM{a.qM + env, S}, LD{a.qLD + env, S}, dinv{a.qLDiagInv + env, S};
       SArr<T> frc{a.qfrc_smooth + env, S}, xa{a.qacc_smooth + env, S};
+      if (a.flags & B2F_LD_SMEM) {
+        // scratch of the damped factorisation (M + h D) in per-thread shared-memory columns instead of HBM arrays
+        T* sc = reinterpret_cast<T*>(smem_raw + 16 + (size_t)nwords * 4);
+        LD = SArr<T>{sc + threadIdx.x, BLOCK};
+        dinv = SArr<T>{sc + (size_t)h.nM * BLOCK + threadIdx.x, BLOCK};
+        xa = SArr<T>{sc + (size_t)(h.nM + nv) * BLOCK + threadIdx.x, BLOCK};
+      }
       // qfrc_smooth becomes the total force of the implicit-damping solve; qLD / qLDiagInv / qacc_smooth are dead after
       // the solver and serve as scratch for the damped factorisation
       if (h.has_damping) for (int i = 0; i < nv; i++) frc[i] += a.qfrc_constraint[i * S + env];

@@ -653,9 +653,24 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_smooth(const KArgs<T> a) {
     s.kinematics(env);
     s.com_pos();
     s.crb_mass();
+    // L^T D L.  With the workspace in HBM the O(sum depth^2) read-modify-writes of the elimination would each be an L2
+    // round trip: the factor is built in a per-thread shared-memory column instead and written out once (B2F_LD_SMEM).
+    bool ldsm = false;
+    if constexpr (!P::STATIC) ldsm = (a.flags & B2F_LD_SMEM) != 0;
+    if constexpr (!P::STATIC) {
+      if (ldsm) {
+        SArr<T> LDs{ws_sh + threadIdx.x, BLOCK}, dis{ws_sh + (size_t)nM * BLOCK + threadIdx.x, BLOCK};
+        for (int i = 0; i < nM; i++) LDs[i] = s.qM[i];
+        ld_factor<P>(m, LDs, dis);
+        for (int i = 0; i < nM; i++) s.qLD[i] = LDs[i];
+        for (int i = 0; i < nv; i++) s.qLDiagInv[i] = dis[i];
+      }
+    }
+    if (!ldsm) {
 #pragma unroll(P::UNROLL)
-    for (int i = 0; i < nM; i++) s.qLD[i] = s.qM[i];
-    ld_factor<P>(m, s.qLD, s.qLDiagInv);
+      for (int i = 0; i < nM; i++) s.qLD[i] = s.qM[i];
+      ld_factor<P>(m, s.qLD, s.qLDiagInv);
+    }
     // velocity stage
     s.com_vel();
     s.passive();
@@ -713,7 +728,13 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_smooth(const KArgs<T> a) {
     }
 #pragma unroll(P::UNROLL)
     for (int i = 0; i < nv; i++) s.qacc_smooth[i] = s.qfrc_smooth[i];
-    ld_solve<P>(m, s.qLD, s.qLDiagInv, s.qacc_smooth);
+    if constexpr (!P::STATIC) {
+      if (ldsm) {   // the factor is still in the shared-memory column
+        SArr<T> LDs{ws_sh + threadIdx.x, BLOCK}, dis{ws_sh + (size_t)nM * BLOCK + threadIdx.x, BLOCK};
+        ld_solve<P>(m, LDs, dis, s.qacc_smooth);
+      }
+    }
+    if (!ldsm) ld_solve<P>(m, s.qLD, s.qLDiagInv, s.qacc_smooth);
 
     // body poses for the ROS layer (tf / marker publishers read d->xpos, d->xquat: SURVEY.md Appendix C)
     if (!s.aliased) {
