@@ -415,6 +415,12 @@ def main():
     kern = {k: v for k, v in slot_ms.items() if k not in ("hw_write", "hw_read")}
     dom = max(kern, key=kern.get)
     dom_ms = kern[dom] / max(1, nprof)
+    timing = "CUDA events between the kernels, same K ticks re-run eagerly right after the graph-replayed timed loop"
+    if launches == K and max_ms / K < dom_ms:
+        # the tick IS one kernel launch: the timed region's own event pair brackets exactly that launch (the eager re-run
+        # adds the profiling events' overhead to a ~10 us kernel)
+        dom_ms = max_ms / K
+        timing = "the tick is a single kernel launch: CUDA events of the timed region itself (one pair per launch)"
     balg = b_alg(m, ncon_mean)
     achieved = balg * nenv / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
     traffic = None
@@ -436,7 +442,7 @@ def main():
                    "obs_allgather": ("NCCL all_gather of [qpos|qvel] fp32, %d B per rank per tick, inside the timed region" % (4 * nobs * nenv)) if gather else "none: shards are independent, no data-path collective"},
         "roofline": {"bound": "hbm", "kernel": (bt.path_name.split("+")[0] if dom == "smooth" else {"pgs": "k_pgs_block"}.get(dom, "k_" + dom)), "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_env_step": balg,
-                     "kernel_timing": "CUDA events between the kernels, same K ticks re-run eagerly right after the graph-replayed timed loop",
+                     "kernel_timing": timing,
                      "kernel_ms": dom_ms, "kernel_share_of_step": kern[dom] / max(1e-12, sum(slot_ms.values())),
                      "kernel_ms_all": {k: v / max(1, nprof) for k, v in slot_ms.items()}},
         "e2e": {"value": total_envs * K / e2e_max, "unit": UNIT, "h2d_bytes_per_step": int(h2d * world),

@@ -256,7 +256,7 @@ KArgs<T> make_args(b2_batch* b, int flags) {
   if constexpr (sizeof(T) == 4) a = b->args_f; else a = b->args_d;
   a.model = b->blob_dev; a.model_words = b->hdr.nwords;
   a.flags = flags; a.ws_block = b->smooth_block; a.h = (T)b->h; a.wp = b->wp;
-  a.block_capw = b->block_capw; a.block_npar = b->block_npar; a.stage_cap = b->stage_cap;
+  a.block_capw = b->block_capw; a.block_npar = b->block_npar; a.stage_cap = b->stage_cap; a.row_nb = b->row_nb;
   a.hw_vel = b->io_in[0]; a.hw_eff = b->io_in[1];
   a.hw_pos = b->io_out[0]; a.hw_velo = b->io_out[1]; a.hw_effo = b->io_out[2];
   a.hw_kp = b->hw_kp; a.hw_kd = b->hw_kd;
@@ -270,6 +270,16 @@ int configure_constraint_kernels(b2_batch* b) {
     // the constraint-pipeline kernels stage the same blob; row assembly and the solver add their shared vectors
     const int need1 = (int)b->blob_smem;
     const int need1i = (int)(b->blob_smem + b->ld_smem);
+    // k_make_rows: a shared-memory column per thread for the base rows of the contact being assembled
+    {
+      int nbm = 1;
+      for (int g = 0; g < b->m->ngeom; g++) nbm = std::max(nbm, b->m->geom_condim[g]);
+      nbm = std::min(nbm, 6);
+      const size_t rs = (size_t)nbm * b->hdr.wmax * 128 * b->prec;
+      b->row_nb = (!getenv("B2_NO_ROW_SMEM") && b->blob_smem + rs <= 180 * 1024) ? nbm : 0;
+      b->row_smem = b->row_nb ? rs : 0;
+    }
+    const int need1r = (int)(b->blob_smem + b->row_smem);
     // row assembly: one record column per thread; 128-thread CTAs when that fits, else 32
     // (k_make_blocks reads the model from HBM: its shared memory is the record columns only)
     b->make_block = (size_t)b->rec_max * 129 * b->prec <= 56 * 1024 ? 128 : 32;
@@ -299,14 +309,14 @@ int configure_constraint_kernels(b2_batch* b) {
     if (b->prec == 8) {
       SA((const void*)k_collide<double, 128>, need1); SA((const void*)k_integrate<double, 128>, need1i);
       SA((const void*)k_integrate<double, 64>, need1i); SA((const void*)k_integrate<double, 32>, need1i);
-      SA((const void*)k_make_rows<double, 128>, need1); SA((const void*)k_make_blocks<double, 128>, need2); SA((const void*)k_make_blocks<double, 32>, need2);
+      SA((const void*)k_make_rows<double, 128>, need1r); SA((const void*)k_make_blocks<double, 128>, need2); SA((const void*)k_make_blocks<double, 32>, need2);
       SA((const void*)k_pgs_block<double, 4, 32, PGS_MINB>, need3); SA((const void*)k_pgs_block<double, 8, 32, PGS_MINB>, need3);
       SA((const void*)k_pgs_block<double, 16, 32, PGS_MINB>, need3); SA((const void*)k_pgs_block<double, 32, 32, PGS_MINB>, need3);
       SA((const void*)k_solve_rows<double, 8>, (int)b->solve_smem); SA((const void*)k_solve_rows<double, 4>, (int)b->solve_smem);
     } else {
       SA((const void*)k_collide<float, 128>, need1); SA((const void*)k_integrate<float, 128>, need1i);
       SA((const void*)k_integrate<float, 64>, need1i); SA((const void*)k_integrate<float, 32>, need1i);
-      SA((const void*)k_make_rows<float, 128>, need1); SA((const void*)k_make_blocks<float, 128>, need2); SA((const void*)k_make_blocks<float, 32>, need2);
+      SA((const void*)k_make_rows<float, 128>, need1r); SA((const void*)k_make_blocks<float, 128>, need2); SA((const void*)k_make_blocks<float, 32>, need2);
       SA((const void*)k_pgs_block<float, 4, 32, PGS_MINB>, need3); SA((const void*)k_pgs_block<float, 8, 32, PGS_MINB>, need3);
       SA((const void*)k_pgs_block<float, 16, 32, PGS_MINB>, need3); SA((const void*)k_pgs_block<float, 32, 32, PGS_MINB>, need3);
       SA((const void*)k_solve_rows<float, 8>, (int)b->solve_smem); SA((const void*)k_solve_rows<float, 4>, (int)b->solve_smem);
@@ -406,7 +416,7 @@ int run_tick(b2_batch* b, int flags) {
     if (b->m->npair > 0) { k_collide<T, BL><<<g2, BL, sm, b->stream>>>(a); b->launches++; }
     prof_mark(b, SLOT_MAKE);
     CK(cudaMemsetAsync(a.maxblk, 0, sizeof(int), b->stream));
-    k_make_rows<T, BL><<<g2, BL, sm, b->stream>>>(a);
+    k_make_rows<T, BL><<<g2, BL, sm + b->row_smem, b->stream>>>(a);
     if (b->solve_rows > 0) {
       // wide trees: M^-1 J^T of all rows up front, the tile's factor shared through shared memory (k_solve_rows)
       const int gs = std::max(1, std::min(b->nenvp / 32, b->nsm * std::max(1, (int)(227 * 1024 / (b->solve_smem + 1024)))));

@@ -49,6 +49,8 @@ struct b2_batch {
   int make_block = 128;  // CTA size of k_make_constraint
   int pgs_lanes = 8;     // lanes per environment in k_pgs_block
   size_t ld_smem = 0;    // bytes of the shared-memory factor scratch of k_smooth / k_integrate (workspace in HBM), 0: off
+  int row_nb = 0;        // k_make_rows' shared-memory row column: base rows it holds (0: off)
+  size_t row_smem = 0;
   int solve_rows = 0;    // row-warps per CTA of k_solve_rows (0: rows are solved inside k_make_blocks)
   size_t solve_smem = 0;
   int stage_cap = 0;     // words of records per environment staged in shared memory by the solver

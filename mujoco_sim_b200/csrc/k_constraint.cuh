@@ -62,19 +62,21 @@ struct Rows {
   int env;
   long long S;
   int nefc = 0;
+  T* rowsh = nullptr;   // shared-memory column of this thread for the base rows of the contact being assembled (or null)
+  int rowld = 0;        // its stride (the CTA width)
   __device__ Rows(const MV<T>& mv, const KArgs<T>& args, int e) : m(mv), h(*mv.h), a(args), env(e), S(args.nenvp) {}
   __device__ __forceinline__ T& Jc(int r, int k) const { return a.efc_J[((long long)r * h.wmax + k) * S + env]; }
   __device__ __forceinline__ T cdof(int i, int k) const { return a.cdof[(6 * i + k) * S + env]; }
 
   // start a new zero row over trees (t1, t2); returns its index or -1 when njmax is exhausted
-  __device__ int open(int type, int id, T pos, T margin, T frictionloss, int t1, int t2, Seg* gout) {
+  __device__ int open(int type, int id, T pos, T margin, T frictionloss, int t1, int t2, Seg* gout, bool zero = true) {
     if (nefc >= h.njmax) { a.status[env] |= 2; return -1; }
     if (t1 < 0) { t1 = t2; t2 = -1; }
     if (t1 == t2) t2 = -1;
     if (t2 >= 0 && t2 < t1) { const int t = t1; t1 = t2; t2 = t; }
     const int r = nefc++;
     const Seg g = seg_of(m, t1, t2);
-    for (int k = 0; k < g.n1 + g.n2; k++) Jc(r, k) = 0;
+    if (zero) for (int k = 0; k < g.n1 + g.n2; k++) Jc(r, k) = 0;
     a.efc_tree[((long long)2 * r) * S + env] = t1;
     a.efc_tree[((long long)2 * r + 1) * S + env] = t2;
     a.efc_type[(long long)r * S + env] = type;
@@ -240,8 +242,36 @@ struct Rows {
       if (first + nrow > h.njmax) { a.status[env] |= 2; I(CI_EFC) = -1; continue; }  // kept whole or dropped whole
       Seg g;
       const int t1 = m.i(h.o_body_treeid, b1), t2 = m.i(h.o_body_treeid, b2);
-      for (int k = 0; k < nrow; k++) open(dim == 1 ? CN_CONTACT_FRICTIONLESS : CN_CONTACT_PYRAMIDAL, c, dist, im, 0, t1, t2, &g);
+      // With a shared-memory column the dim base rows are accumulated there and stored once: in HBM every "+=" of a
+      // Jacobian entry is a load behind a store (an L2 round trip), ~100 per contact.  Rows dim .. nrow - 1 of a pyramidal
+      // contact are index space only (never read: k_solve_rows / k_make_blocks work on the base rows) and are left as is.
+      const bool sh = rowsh != nullptr && dim <= a.row_nb;
+      for (int k = 0; k < nrow; k++) open(dim == 1 ? CN_CONTACT_FRICTIONLESS : CN_CONTACT_PYRAMIDAL, c, dist, im, 0, t1, t2, &g, !sh);
       I(CI_EFC) = first;
+      const int wrow = g.n1 + g.n2;
+      auto RS = [&](int k, int e) -> T& { return rowsh[((long long)k * h.wmax + e) * rowld]; };
+      if (sh) {
+        for (int k = 0; k < dim; k++)
+          for (int e = 0; e < wrow; e++) RS(k, e) = 0;
+        for (int side = 0; side < 2; side++) {
+          const int b = side ? b2 : b1;
+          const T sg = side ? T(1) : T(-1);
+          T off[3];
+          point_off(b, pos, off);
+          for (int i = m.i(h.o_body_lastdof, b); i >= 0; i = m.i(h.o_dof_parentid, i)) {
+            T jp[3], jr[3], fp[3], fr[3];
+            jac_col(i, off, jp, jr);
+            mat_vec3(fp, frame, jp);
+            mat_vec3(fr, frame, jr);
+            const int kk = seg_pos(g, i);
+            RS(0, kk) += sg * fp[0];
+            for (int k = 1; k < dim; k++) RS(k, kk) += sg * (k < 3 ? fp[k] : fr[k - 3]);
+          }
+        }
+        for (int k = 0; k < dim; k++)
+          for (int e = 0; e < wrow; e++) Jc(first + k, e) = RS(k, e);
+        continue;
+      }
       for (int side = 0; side < 2; side++) {
         const int b = side ? b2 : b1;
         const T sg = side ? T(1) : T(-1);
@@ -434,6 +464,7 @@ __global__ void __launch_bounds__(BLOCK) k_make_rows(const KArgs<T> a) {
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int env = tile * BLOCK + threadIdx.x;
     Rows<T> rows(m, a, env);
+    if (a.row_nb > 0) { rows.rowsh = reinterpret_cast<T*>(smem_raw + 16 + (size_t)nwords * 4) + threadIdx.x; rows.rowld = BLOCK; }
     const bool done = (a.flags & B2F_FUSABLE) && (a.status[env] & 8);  // already integrated by the smooth kernel
     if (!(h.disableflags & DSBL_CONSTRAINT) && !done) {
       rows.equality();
@@ -501,6 +532,10 @@ __global__ void __launch_bounds__(32 * ROWS) k_solve_rows(const KArgs<T> a) {
     SArr<T> X{Xs + (size_t)wrp * W * 32 + lane, 32};
     for (int r = wrp; r < nemax; r += ROWS) {
       if (r >= ne) continue;
+      if (a.efc_type[(long long)r * S + env] == CN_CONTACT_PYRAMIDAL) {   // only the base rows of a contact carry a Jacobian
+        const int c = a.efc_id[(long long)r * S + env];
+        if (r - a.coni[((long long)CI_EFC * h.nconmax + c) * S + env] >= a.coni[((long long)CI_DIM * h.nconmax + c) * S + env]) continue;
+      }
       const Seg g = seg_of(m, a.efc_tree[((long long)2 * r) * S + env], a.efc_tree[((long long)2 * r + 1) * S + env]);
       const int w = g.n1 + g.n2;
       for (int e = 0; e < w; e++) X[e] = a.efc_J[((long long)r * W + e) * S + env];
