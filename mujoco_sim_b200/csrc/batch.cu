@@ -299,7 +299,7 @@ int configure_constraint_kernels(b2_batch* b) {
     // k_solve_rows (wide trees): factor tile + one right-hand-side column per (row-warp, environment)
     b->solve_rows = 0; b->solve_smem = 0;
     if (b->make_block == 32 && b->fields.count("efc_B") && !getenv("B2_NO_SOLVE_ROWS")) {
-      for (int rows : {8, 4}) {
+      for (int rows : {16, 8, 4}) {
         const size_t need = ((size_t)b->hdr.nM + b->hdr.nv + (size_t)rows * b->hdr.wmax) * 32 * b->prec;
         if (need <= 200 * 1024) { b->solve_rows = rows; b->solve_smem = need; break; }
       }
@@ -312,14 +312,14 @@ int configure_constraint_kernels(b2_batch* b) {
       SA((const void*)k_make_rows<double, 128>, need1r); SA((const void*)k_make_blocks<double, 128>, need2); SA((const void*)k_make_blocks<double, 32>, need2);
       SA((const void*)k_pgs_block<double, 4, 32, PGS_MINB>, need3); SA((const void*)k_pgs_block<double, 8, 32, PGS_MINB>, need3);
       SA((const void*)k_pgs_block<double, 16, 32, PGS_MINB>, need3); SA((const void*)k_pgs_block<double, 32, 32, PGS_MINB>, need3);
-      SA((const void*)k_solve_rows<double, 8>, (int)b->solve_smem); SA((const void*)k_solve_rows<double, 4>, (int)b->solve_smem);
+      SA((const void*)k_solve_rows<double, 16>, (int)b->solve_smem); SA((const void*)k_solve_rows<double, 8>, (int)b->solve_smem); SA((const void*)k_solve_rows<double, 4>, (int)b->solve_smem);
     } else {
       SA((const void*)k_collide<float, 128>, need1); SA((const void*)k_integrate<float, 128>, need1i);
       SA((const void*)k_integrate<float, 64>, need1i); SA((const void*)k_integrate<float, 32>, need1i);
       SA((const void*)k_make_rows<float, 128>, need1r); SA((const void*)k_make_blocks<float, 128>, need2); SA((const void*)k_make_blocks<float, 32>, need2);
       SA((const void*)k_pgs_block<float, 4, 32, PGS_MINB>, need3); SA((const void*)k_pgs_block<float, 8, 32, PGS_MINB>, need3);
       SA((const void*)k_pgs_block<float, 16, 32, PGS_MINB>, need3); SA((const void*)k_pgs_block<float, 32, 32, PGS_MINB>, need3);
-      SA((const void*)k_solve_rows<float, 8>, (int)b->solve_smem); SA((const void*)k_solve_rows<float, 4>, (int)b->solve_smem);
+      SA((const void*)k_solve_rows<float, 16>, (int)b->solve_smem); SA((const void*)k_solve_rows<float, 8>, (int)b->solve_smem); SA((const void*)k_solve_rows<float, 4>, (int)b->solve_smem);
     }
     if (!ok) return fail("cudaFuncSetAttribute failed");
   return 0;
@@ -420,7 +420,8 @@ int run_tick(b2_batch* b, int flags) {
     if (b->solve_rows > 0) {
       // wide trees: M^-1 J^T of all rows up front, the tile's factor shared through shared memory (k_solve_rows)
       const int gs = std::max(1, std::min(b->nenvp / 32, b->nsm * std::max(1, (int)(227 * 1024 / (b->solve_smem + 1024)))));
-      if (b->solve_rows == 8) k_solve_rows<T, 8><<<gs, 256, b->solve_smem, b->stream>>>(a);
+      if (b->solve_rows == 16) k_solve_rows<T, 16><<<gs, 512, b->solve_smem, b->stream>>>(a);
+      else if (b->solve_rows == 8) k_solve_rows<T, 8><<<gs, 256, b->solve_smem, b->stream>>>(a);
       else k_solve_rows<T, 4><<<gs, 128, b->solve_smem, b->stream>>>(a);
       b->launches++;
     }

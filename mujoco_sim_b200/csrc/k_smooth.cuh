@@ -253,9 +253,11 @@ struct Smooth {
       mat_vec3(r, mat, ip);
       r[0] += pos[0]; r[1] += pos[1]; r[2] += pos[2];
       st<T, 3>(xipos, 3 * b, r);
-      mul_quat(qi, quat, iq);
-      quat2mat(imat, qi);
-      st<T, 9>(ximat, 9 * b, imat);
+      if constexpr (P::STATIC) {   // register-resident chains keep the inertial frames; generic trees recompute them in com_pos
+        mul_quat(qi, quat, iq);
+        quat2mat(imat, qi);
+        st<T, 9>(ximat, 9 * b, imat);
+      }
     }
   }
 
@@ -304,7 +306,17 @@ struct Smooth {
       const int root = P::body_rootid(m, b);
       T dif[3], mat[9], inert[3], tmp[6];
       for (int k = 0; k < 3; k++) dif[k] = xipos[3 * b + k] - subtree_com[3 * root + k];
-      ld<T, 9>(mat, ximat, 9 * b);
+      if constexpr (P::STATIC) {
+        ld<T, 9>(mat, ximat, 9 * b);
+      } else {
+        // inertial frame from the body quaternion (4 loads + ~40 flops) instead of a stored 3 x 3 (9 stores + 9 loads
+        // through the HBM / L2-resident workspace): the same operations kinematics() used to do, so the values are identical
+        T bq[4], iq[4], qi[4];
+        ld<T, 4>(bq, xquat, 4 * b);
+        ldm<T, 4>(iq, m, h.o_body_iquat, 4 * b);
+        mul_quat(qi, bq, iq);
+        quat2mat(mat, qi);
+      }
       ldm<T, 3>(inert, m, h.o_body_inertia, 3 * b);
       const T mass = m.f(h.o_body_mass, b);
       // R diag(I) R^T, upper triangle: xx yy zz xy xz yz

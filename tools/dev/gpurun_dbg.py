@@ -1,8 +1,8 @@
 """debug: find convex contacts where the fp64 batch and the oracle disagree; dump inputs"""
 import ctypes as C, json, sys, os
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "tests"))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "tests"))
 import mujoco_sim_b200 as b2
 from oracle import pyoracle as orc
 import test_gpu_parity as tp

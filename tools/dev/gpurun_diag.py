@@ -2,7 +2,7 @@
 import os, sys, time
 import numpy as np
 import torch
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import mujoco_sim_b200 as b2
 from mujoco_sim_b200 import workloads as w
 
