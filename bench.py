@@ -442,6 +442,10 @@ def main():
                    "obs_allgather": ("NCCL all_gather of [qpos|qvel] fp32, %d B per rank per tick, inside the timed region" % (4 * nobs * nenv)) if gather else "none: shards are independent, no data-path collective"},
         "roofline": {"bound": "hbm", "kernel": (bt.path_name.split("+")[0] if dom == "smooth" else {"pgs": "k_pgs_block"}.get(dom, "k_" + dom)), "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_env_step": balg,
+                     "binding": {"c2": "dependent-issue / shuffle latency of one articulated-body chain per 8-lane team (4096 envs = 7 warps per SM); not bandwidth: 2 MB per launch",
+                                 "c3": "aggregate instruction issue of the Gauss-Seidel visits (k_pgs_block: ~360 instructions per block visit, 50 % issue-active)",
+                                 "c4": "aggregate instruction issue of the Gauss-Seidel visits (k_pgs_block, one warp per environment)",
+                                 "c5": "aggregate instruction issue of the Gauss-Seidel visits (k_pgs_block)"}[args.config] + "; evidence: profiles/r01_ncu_%s_summary.txt" % ("c3" if args.config == "c5" else args.config),
                      "kernel_timing": timing,
                      "kernel_ms": dom_ms, "kernel_share_of_step": kern[dom] / max(1e-12, sum(slot_ms.values())),
                      "kernel_ms_all": {k: v / max(1, nprof) for k, v in slot_ms.items()}},
