@@ -708,7 +708,7 @@ void build_pairs(Ctx& c) {
   const int ng = (int)S.geom_type.size();
   std::set<int> excl(S.exclude_signature.begin(), S.exclude_signature.end());
   const bool filterparent = !(S.view.opt.disableflags & mjDSBL_FILTERPARENT);
-  struct Pr { int t1, t2, g1, g2; };
+  struct Pr { int t1, t2, g1, g2, ba = 0, bb = 0, ga = 0, gb = 0; };
   std::vector<Pr> prs;
   for (int a = 0; a < ng; a++)
     for (int b = a + 1; b < ng; b++) {
@@ -727,13 +727,17 @@ void build_pairs(Ctx& c) {
       int g1 = a, g2 = b;
       if (t1 > t2) { std::swap(t1, t2); std::swap(g1, g2); }
       if (t1 == mjGEOM_PLANE && (t2 == mjGEOM_PLANE || t2 == mjGEOM_HFIELD)) continue;
-      prs.push_back({t1, t2, g1, g2});
+      // sort key = MuJoCo's pair-generation order: body pair (lower body id first), then the geoms of the
+      // first body in order, then the geoms of the second; inside a pair geom1 is the one with the lower geom TYPE
+      Pr pr{t1, t2, g1, g2};
+      pr.ba = lo; pr.bb = hi; pr.ga = b1 <= b2 ? a : b; pr.gb = b1 <= b2 ? b : a;
+      prs.push_back(pr);
     }
   std::sort(prs.begin(), prs.end(), [](const Pr& x, const Pr& y) {
-    if (x.t1 != y.t1) return x.t1 < y.t1;
-    if (x.t2 != y.t2) return x.t2 < y.t2;
-    if (x.g1 != y.g1) return x.g1 < y.g1;
-    return x.g2 < y.g2;
+    if (x.ba != y.ba) return x.ba < y.ba;
+    if (x.bb != y.bb) return x.bb < y.bb;
+    if (x.ga != y.ga) return x.ga < y.ga;
+    return x.gb < y.gb;
   });
   for (auto& p : prs) { S.pair_geom1.push_back(p.g1); S.pair_geom2.push_back(p.g2); }
   S.view.npair = (int)prs.size();
