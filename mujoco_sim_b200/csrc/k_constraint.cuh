@@ -297,6 +297,9 @@ struct Rows {
   // diagApprox, impedance -> R, D; K, B, imp; aref; (vel uses the current, possibly overridden, qvel)
   __device__ void finish() {
     const T hs = a.h;
+    // the rows of one contact share its parameters: fetched once per contact (13 HBM loads), not once per row
+    int c_id = -1, c_first = 0;
+    T c_solref[2] = {0, 0}, c_solimp[5] = {0, 0, 0, 0, 0}, c_tran = 0, c_rot = 0;
     for (int r = 0; r < nefc; r++) {
       const int type = a.efc_type[(long long)r * S + env], id = a.efc_id[(long long)r * S + env];
       T solref[2], solimp[5], diag;
@@ -324,14 +327,21 @@ struct Rows {
       } else {
         auto F = [&](int f) -> T { return a.con[((long long)f * h.nconmax + id) * S + env]; };
         auto I = [&](int f) -> int { return a.coni[((long long)f * h.nconmax + id) * S + env]; };
-        for (int k = 0; k < 2; k++) solref[k] = F(CF_SOLREF + k);
-        for (int k = 0; k < 5; k++) solimp[k] = F(CF_SOLIMP + k);
-        const int b1 = m.i(h.o_geom_bodyid, I(CI_GEOM1)), b2 = m.i(h.o_geom_bodyid, I(CI_GEOM2));
-        const T tran = m.f(h.o_body_invweight0, 2 * b1) + m.f(h.o_body_invweight0, 2 * b2);
-        const T rot = m.f(h.o_body_invweight0, 2 * b1 + 1) + m.f(h.o_body_invweight0, 2 * b2 + 1);
+        if (id != c_id) {
+          c_id = id;
+          for (int k = 0; k < 2; k++) c_solref[k] = F(CF_SOLREF + k);
+          for (int k = 0; k < 5; k++) c_solimp[k] = F(CF_SOLIMP + k);
+          const int b1 = m.i(h.o_geom_bodyid, I(CI_GEOM1)), b2 = m.i(h.o_geom_bodyid, I(CI_GEOM2));
+          c_tran = m.f(h.o_body_invweight0, 2 * b1) + m.f(h.o_body_invweight0, 2 * b2);
+          c_rot = m.f(h.o_body_invweight0, 2 * b1 + 1) + m.f(h.o_body_invweight0, 2 * b2 + 1);
+          c_first = I(CI_EFC);
+        }
+        for (int k = 0; k < 2; k++) solref[k] = c_solref[k];
+        for (int k = 0; k < 5; k++) solimp[k] = c_solimp[k];
+        const T tran = c_tran, rot = c_rot;
         if (type == CN_CONTACT_FRICTIONLESS) diag = tran;
         else {
-          const int j = r - I(CI_EFC);
+          const int j = r - c_first;
           const T fr = F(CF_FRICTION + j / 2);
           diag = tran + fr * fr * (j < 4 ? tran : rot);
         }

@@ -2,8 +2,9 @@
 // general convex path (MPR) for every other pair of convex geoms.
 // TEST INFRASTRUCTURE ONLY (see oracle.h).  PARITY UNPINNED: MuJoCo's collision functions are not in
 // /root/reference; conventions follow MuJoCo's docs (mjContact: dist < 0 = penetration, pos = midpoint,
-// frame[0:3] = normal pointing from geom1 to geom2; geom1 has the lower geom TYPE).  Contact order is canonical:
-// static candidate-pair index (mjModel.pair_geom1/2), then emission order inside the pair function.  The reference
+// frame[0:3] = normal pointing from geom1 to geom2; geom1 has the lower geom TYPE).  Contact order: the static
+// candidate-pair list (mjModel.pair_geom1/2, compiled in MuJoCo's pair-generation order: body pair, then geom pair),
+// then emission order inside the pair function.  The reference
 // reaches this only through mj_step1 / mj_forward / mj_inverse (src/mj_main.cpp:83, mj_ros.cpp:608,
 // mj_hw_interface.cpp:61).
 #include <algorithm>
