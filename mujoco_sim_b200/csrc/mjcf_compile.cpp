@@ -88,6 +88,7 @@ struct MeshAsset {
   std::string name;
   std::vector<double> vert;   // unique vertices, xyz
   std::vector<int> face;      // triangle indices (may be empty for point clouds)
+  double center[3] = {0, 0, 0};  // what was subtracted from the file's vertices (see recenter_mesh)
 };
 
 struct Compiler {
@@ -278,6 +279,32 @@ void load_obj(const std::string& path, MeshAsset& ma) {
   }
 }
 
+// MuJoCo stores a mesh about its own centre (its CoM) and moves the geom frame accordingly.  That is not cosmetic for
+// collision: geom_xpos is the interior point the convex routine (MPR) starts its portal from and the centre of the
+// bounding sphere, and a link mesh authored far from its file origin would have neither.  Centre = volume centroid of the
+// closed surface; vertex mean when the surface encloses no volume (point clouds, open sheets).
+void recenter_mesh(MeshAsset& ma) {
+  const size_t nvt = ma.vert.size() / 3;
+  if (nvt == 0) return;
+  double c[3] = {0, 0, 0}, vol = 0;
+  for (size_t f = 0; f + 2 < ma.face.size(); f += 3) {
+    const double *a = &ma.vert[3 * ma.face[f]], *b = &ma.vert[3 * ma.face[f + 1]], *d = &ma.vert[3 * ma.face[f + 2]];
+    const double v6 = a[0] * (b[1] * d[2] - b[2] * d[1]) - a[1] * (b[0] * d[2] - b[2] * d[0]) + a[2] * (b[0] * d[1] - b[1] * d[0]);
+    vol += v6;
+    for (int k = 0; k < 3; k++) c[k] += v6 * (a[k] + b[k] + d[k]) * 0.25;
+  }
+  double ext = 0;
+  for (double x : ma.vert) ext = std::max(ext, std::fabs(x));
+  if (std::fabs(vol) > 1e-9 * ext * ext * ext && ext > 0) {
+    for (int k = 0; k < 3; k++) c[k] /= vol;
+  } else {
+    c[0] = c[1] = c[2] = 0;
+    for (size_t i = 0; i < nvt; i++) for (int k = 0; k < 3; k++) c[k] += ma.vert[3 * i + k] / (double)nvt;
+  }
+  for (size_t i = 0; i < nvt; i++) for (int k = 0; k < 3; k++) ma.vert[3 * i + k] -= c[k];
+  for (int k = 0; k < 3; k++) ma.center[k] = c[k];
+}
+
 // volume, centre of mass and inertia tensor (about the CoM, unit density) of a closed triangle mesh
 void mesh_mass_props(const MeshAsset& ma, double& vol, double* com, double* I) {
   vol = 0;
@@ -418,6 +445,11 @@ GeomTmp parse_geom(Ctx& c, const XmlElem& e, const std::string& cc) {
   zero3(g.pos);
   if (const char* s = L("pos")) { if (parse_nums(s, g.pos, 3) != 3) fail("geom pos needs 3 numbers"); }
   parse_orientation(c, e, "geom", cc, g.quat);
+  if (g.type == mjGEOM_MESH) {   // the mesh was re-centred: the geom frame moves with it
+    double off[3];
+    rot_vec_quat(off, c.meshes[g.dataid].center, g.quat);
+    for (int k = 0; k < 3; k++) g.pos[k] += off[k];
+  }
   if (const char* s = L("fromto")) {
     if (parse_nums(s, v, 6) != 6) fail("fromto needs 6 numbers");
     double d[3] = {v[3] - v[0], v[4] - v[1], v[5] - v[2]};
@@ -837,6 +869,7 @@ mjModel* compile_root(std::unique_ptr<XmlElem> root, const std::string& basedir,
       for (size_t i = 0; i + 2 < ma.vert.size(); i += 3) for (int k = 0; k < 3; k++) ma.vert[i + k] *= sc[k];
       if (sc[0] * sc[1] * sc[2] < 0)
         for (size_t f = 0; f + 2 < ma.face.size(); f += 3) std::swap(ma.face[f + 1], ma.face[f + 2]);
+      recenter_mesh(ma);
       c.meshes.push_back(std::move(ma));
     }
   }

@@ -439,8 +439,9 @@ class ConvexTally:
             assert self.tight[cls] >= need * n, (cls, prec, self.tight[cls], n)
 
 
-def _octahedron_stl(path, r=0.1):
+def _octahedron_stl(path, r=0.1, shift=(0.0, 0.0, 0.0)):
     v = [(r, 0, 0), (-r, 0, 0), (0, r, 0), (0, -r, 0), (0, 0, 1.5 * r), (0, 0, -1.5 * r)]
+    v = [(x + shift[0], y + shift[1], z + shift[2]) for x, y, z in v]
     faces = [(0, 2, 4), (2, 1, 4), (1, 3, 4), (3, 0, 4), (2, 0, 5), (1, 2, 5), (3, 1, 5), (0, 3, 5)]
     with open(path, "w") as f:
         f.write("solid o\n")

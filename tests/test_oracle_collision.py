@@ -205,3 +205,36 @@ def test_convex_matches_primitive_on_box_box_depth(b2, orc):
     out = (C.c_double * 7)()
     n = fn(6, pos1, eye, size, 6, pos2, eye, size, C.c_double(0.0), out)
     assert n == 1 and abs(out[0] + 0.01) < 1e-6 and np.allclose(out[4:7], [0, 0, 1], atol=1e-6)
+
+
+def test_mesh_authored_away_from_its_origin_collides_like_the_centred_one(b2, orc, tmp_path):
+    """MuJoCo stores a mesh about its own centre and moves the geom frame; the convex routine needs that (its portal starts
+    from geom_xpos, which must lie inside the shape).  The same octahedron authored 0.5 m away from its file origin, with
+    the geom placed to compensate, must give the contacts of the centred one — against a plane and through MPR."""
+    from test_gpu_parity import _octahedron_stl
+    shift = (0.5, -0.2, 0.3)
+    _octahedron_stl(str(tmp_path / "a.stl"))
+    _octahedron_stl(str(tmp_path / "b.stl"), shift=shift)
+    res = []
+    for f, gp in (("a.stl", (0.0, 0.0, 0.0)), ("b.stl", tuple(-x for x in shift))):
+        xml = """<mujoco><compiler angle='radian' meshdir='%s'/><option gravity='0 0 0'/><asset><mesh name='o' file='%s'/></asset><worldbody>
+          <geom type='plane' size='0 0 1'/>
+          <body name='m' pos='0 0 0.14'><freejoint/><geom type='mesh' mesh='o' pos='%g %g %g'/><inertial pos='0 0 0' mass='1' diaginertia='0.01 0.01 0.01'/></body>
+          <body name='b' pos='0.12 0.02 0.2'><freejoint/><geom type='box' size='0.05 0.05 0.05'/></body>
+          <body name='y' pos='-0.13 0 0.2' quat='0.9 0.1 0.4 0'><freejoint/><geom type='cylinder' size='0.05 0.08'/></body>
+        </worldbody></mujoco>""" % (str(tmp_path), f, *gp)
+        m = b2.Model(xml=xml)
+        d = b2.Data(m)
+        orc.call("kinematics", m, d); orc.call("collision", m, d)
+        b2.lib.b2_data_contact.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        cs = []
+        for i in range(d.ncon):
+            k = MjContact(); assert b2.lib.b2_data_contact(d.ptr, i, C.byref(k)) == 0
+            cs.append((k.geom1, k.geom2, k.dist, np.array(k.pos), np.array(k.frame[:3])))
+        res.append((cs, np.array(m.geom_rbound), np.array(d.geom_xpos).reshape(-1, 3)))
+    (ca, ra, xa), (cb, rb, xb) = res
+    assert len(ca) == len(cb) >= 3 and {(c[0], c[1]) for c in ca} >= {(0, 1), (2, 1), (3, 1)}     # plane, box and cylinder all touch it
+    np.testing.assert_allclose(rb, ra, rtol=1e-6); np.testing.assert_allclose(xb, xa, atol=1e-6)   # same centre, same bounding sphere
+    for a, b in zip(ca, cb):
+        assert a[:2] == b[:2] and abs(a[2] - b[2]) < 1e-6
+        np.testing.assert_allclose(a[3], b[3], atol=1e-6); np.testing.assert_allclose(a[4], b[4], atol=1e-6)
