@@ -12,11 +12,11 @@
 //   <inertial> origin + mass + ixx..izz -> inertial pos / mass / fullinertia rotated into the link frame;
 //   <collision> box / cylinder / sphere / mesh -> geoms (box extents and cylinder length halved); angles in radians;
 //   <visual> elements are dropped (the reference always sets discardvisual, src/mujoco_compile.cpp:158).
-// The root link is fused into the world body as libmujoco's `fusestatic` does (the reference wraps the result in a named
-// body afterwards, src/mujoco_compile.cpp:197-218).  Difference from libmujoco, by design: links behind fixed joints
-// further down stay separate jointless bodies (fusestatic would fold them into the parent and forget their names).  The
-// dynamics are identical — a jointless body is welded to its parent and its inertia enters the parent's composite —
-// and the link names stay addressable.
+// fusestatic (libmujoco's default for URDF; `<compiler fusestatic="false"/>` in the <mujoco> extension turns it off): a link
+// behind a fixed joint is folded into the body of its parent link — its collision geoms move there with the composed
+// transform, its inertial is combined with the parent's about the common CoM, its movable children attach to the
+// parent — and the root link is the world body (the reference wraps the result in a named body afterwards,
+// src/mujoco_compile.cpp:197-218).  With fusestatic off every non-root link stays a body of its own.
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -96,6 +96,20 @@ void origin_of(const XmlElem* e, double* pos, double* quat) {
   }
 }
 
+struct Frame { double p[3] = {0, 0, 0}, q[4] = {1, 0, 0, 0}; };   // pose of a link frame in the frame of the body that owns it
+inline bool is_identity(const Frame& f) { return f.p[0] == 0 && f.p[1] == 0 && f.p[2] == 0 && f.q[0] == 1 && f.q[1] == 0 && f.q[2] == 0 && f.q[3] == 0; }
+// a o b: b expressed in a's parent
+Frame compose(const Frame& a, const double* bp, const double* bq) {
+  if (is_identity(a)) { Frame r; copy3(r.p, bp); copy4(r.q, bq); return r; }   // (keeps the numbers of the unfused case bit for bit)
+  Frame r;
+  double t[3];
+  rot_vec_quat(t, bp, a.q);
+  for (int k = 0; k < 3; k++) r.p[k] = a.p[k] + t[k];
+  mul_quat(r.q, a.q, bq);
+  normalize4(r.q);
+  return r;
+}
+
 struct Joint {
   const XmlElem* e;
   std::string name, type, parent, child;
@@ -109,6 +123,7 @@ struct Importer {
   std::map<std::string, std::string> mesh_names;  // "file|scale" -> asset name
   std::vector<std::string> mesh_assets;           // <mesh .../> lines
   bool strippath = true;
+  bool fusestatic = true;   // libmujoco's default for URDF: links behind fixed joints are folded into their parent body
   std::ostringstream out;
 
   explicit Importer(const XmlElem& r) : robot(r) {}
@@ -143,13 +158,14 @@ struct Importer {
     return name;
   }
 
-  void emit_geoms(const XmlElem& link, const std::string& ind) {
+  void emit_geoms(const XmlElem& link, const std::string& ind, const Frame& fr = Frame()) {
     for (auto& ch : link.children) {
       if (ch->name != "collision") continue;
       const XmlElem* geo = ch->child("geometry");
       if (!geo || geo->children.empty()) continue;
       double pos[3], quat[4];
       origin_of(ch.get(), pos, quat);
+      { const Frame g = compose(fr, pos, quat); copy3(pos, g.p); copy4(quat, g.q); }
       const XmlElem& sh = *geo->children[0];
       std::string a;
       if (sh.name == "box") {
@@ -182,20 +198,27 @@ struct Importer {
     }
   }
 
-  void emit_inertial(const XmlElem& link, const std::string& ind) {
+  struct Inert { double m = 0, c[3] = {0, 0, 0}, I[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}; bool any = false; };   // about its own CoM, body axes
+
+  // <inertial> of a link, expressed in the frame of the body that owns the link (fr = pose of the link frame in it)
+  Inert read_inertial(const XmlElem& link, const Frame& fr) {
+    Inert r;
     const XmlElem* in = link.child("inertial");
-    if (!in) return;
-    double pos[3], quat[4], mass = 0;
+    if (!in) return r;
+    r.any = true;
+    double pos[3], quat[4];
     origin_of(in, pos, quat);
-    if (const XmlElem* me = in->child("mass")) nums(me->attr("value"), &mass, 1);
+    const Frame f = compose(fr, pos, quat);
+    copy3(r.c, f.p);
+    if (const XmlElem* me = in->child("mass")) nums(me->attr("value"), &r.m, 1);
     double I[6] = {0, 0, 0, 0, 0, 0};  // ixx iyy izz ixy ixz iyz
     if (const XmlElem* ie = in->child("inertia")) {
       const char* keys[6] = {"ixx", "iyy", "izz", "ixy", "ixz", "iyz"};
       for (int k = 0; k < 6; k++) nums(ie->attr(keys[k]), &I[k], 1);
     }
-    // rotate the tensor from the inertial frame into the link frame: R I R^T
-    double R[9], A[9] = {I[0], I[3], I[4], I[3], I[1], I[5], I[4], I[5], I[2]}, T[9], B[9];
-    quat2mat(R, quat);
+    // rotate the tensor from the inertial frame into the body frame: R I R^T
+    double R[9], A[9] = {I[0], I[3], I[4], I[3], I[1], I[5], I[4], I[5], I[2]}, T[9];
+    quat2mat(R, f.q);
     for (int i = 0; i < 3; i++)
       for (int j = 0; j < 3; j++) {
         double s = 0;
@@ -206,10 +229,31 @@ struct Importer {
       for (int j = 0; j < 3; j++) {
         double s = 0;
         for (int k = 0; k < 3; k++) s += T[3 * i + k] * R[3 * j + k];
-        B[3 * i + j] = s;
+        r.I[3 * i + j] = s;
       }
-    const double full[6] = {B[0], B[4], B[8], B[1], B[2], B[5]};
-    out << ind << "<inertial pos=\"" << fmt(pos, 3) << "\" mass=\"" << fmt1(mass) << "\" fullinertia=\"" << fmt(full, 6) << "\"/>\n";
+    return r;
+  }
+
+  // one <inertial> for the body: a single part as it is, several (fused links) combined about the common CoM
+  void emit_inertial(const std::vector<Inert>& parts, const std::string& ind) {
+    std::vector<const Inert*> have;
+    for (auto& p : parts) if (p.any) have.push_back(&p);
+    if (have.empty()) return;
+    Inert t = *have[0];
+    if (have.size() > 1) {
+      t = Inert();
+      for (auto* p : have) { t.m += p->m; for (int k = 0; k < 3; k++) t.c[k] += p->m * p->c[k]; }
+      if (t.m > 0) for (int k = 0; k < 3; k++) t.c[k] /= t.m;
+      else for (int k = 0; k < 3; k++) t.c[k] = have[0]->c[k];
+      for (auto* p : have) {
+        const double d[3] = {p->c[0] - t.c[0], p->c[1] - t.c[1], p->c[2] - t.c[2]};
+        const double d2 = dot3(d, d);
+        for (int i = 0; i < 3; i++)
+          for (int j = 0; j < 3; j++) t.I[3 * i + j] += p->I[3 * i + j] + p->m * ((i == j ? d2 : 0.0) - d[i] * d[j]);
+      }
+    }
+    const double full[6] = {t.I[0], t.I[4], t.I[8], t.I[1], t.I[2], t.I[5]};
+    out << ind << "<inertial pos=\"" << fmt(t.c, 3) << "\" mass=\"" << fmt1(t.m) << "\" fullinertia=\"" << fmt(full, 6) << "\"/>\n";
   }
 
   void emit_joint(const Joint& j, const std::string& ind) {
@@ -241,28 +285,51 @@ struct Importer {
     out << "/>\n";
   }
 
-  void emit_link(const std::string& name, const Joint* via, int depth, std::set<std::string>& open) {
+  struct Part { const XmlElem* link; Frame fr; };
+  struct Kid { const Joint* j; Frame fr; };   // fr: pose of the joint's parent link frame in the owning body
+
+  // the link and, with fusestatic, every link welded to it by fixed joints; the movable joints leaving the group
+  void gather(const std::string& name, const Frame& fr, const Joint* via, std::vector<Part>& parts, std::vector<Kid>& kids, std::set<std::string>& open) {
     auto it = links.find(name);
     if (it == links.end()) ufail("joint '" + (via ? via->name : std::string("?")) + "' refers to unknown link '" + name + "'");
     if (!open.insert(name).second) ufail("kinematic loop through link '" + name + "'");
-    const std::string ind(4 + 2 * depth, ' ');
-    if (!via) {
-      // the root link is welded to the world at the origin: like libmujoco (fusestatic) it IS the world body — its
-      // collision geoms become world geoms, its inertial is irrelevant, its children hang off the world directly
-      emit_geoms(*it->second, ind);
-      for (const Joint* c : children[name]) emit_link(c->child, c, depth, open);
-      open.erase(name);
-      return;
+    parts.push_back({it->second, fr});
+    for (const Joint* c : children[name]) {
+      if (fusestatic && c->type == "fixed") {
+        double p[3], q[4];
+        origin_of(c->e, p, q);
+        gather(c->child, compose(fr, p, q), c, parts, kids, open);
+      } else {
+        kids.push_back({c, fr});
+      }
     }
-    double pos[3] = {0, 0, 0}, quat[4] = {1, 0, 0, 0};
-    origin_of(via->e, pos, quat);
-    out << ind << "<body name=\"" << esc(name) << "\" pos=\"" << fmt(pos, 3) << "\" quat=\"" << fmt(quat, 4) << "\">\n";
-    emit_inertial(*it->second, ind + "  ");
-    emit_joint(*via, ind + "  ");
-    emit_geoms(*it->second, ind + "  ");
-    for (const Joint* c : children[name]) emit_link(c->child, c, depth + 1, open);
-    out << ind << "</body>\n";
-    open.erase(name);
+  }
+
+  // body of link `name` reached through joint `via` (null: the root link, which IS the world body, as with libmujoco's
+  // fusestatic: its collision geoms become world geoms, its inertial is irrelevant, its children hang off the world)
+  void emit_link(const std::string& name, const Joint* via, const Frame& at, int depth, std::set<std::string>& open) {
+    const std::string ind(4 + 2 * depth, ' ');
+    std::vector<Part> parts;
+    std::vector<Kid> kids;
+    std::set<std::string> mine;
+    gather(name, Frame(), via, parts, kids, mine);
+    for (auto& n : mine) if (!open.insert(n).second) ufail("kinematic loop through link '" + n + "'");
+    const std::string in2 = via ? ind + "  " : ind;
+    if (via) {
+      out << ind << "<body name=\"" << esc(name) << "\" pos=\"" << fmt(at.p, 3) << "\" quat=\"" << fmt(at.q, 4) << "\">\n";
+      std::vector<Inert> inert;
+      for (auto& p : parts) inert.push_back(read_inertial(*p.link, p.fr));
+      emit_inertial(inert, in2);
+      emit_joint(*via, in2);
+    }
+    for (auto& p : parts) emit_geoms(*p.link, in2, p.fr);
+    for (auto& k : kids) {
+      double p[3], q[4];
+      origin_of(k.j->e, p, q);
+      emit_link(k.j->child, k.j, compose(k.fr, p, q), via ? depth + 1 : depth, open);
+    }
+    if (via) out << ind << "</body>\n";
+    for (auto& n : mine) open.erase(n);
   }
 
   std::string run() {
@@ -304,7 +371,8 @@ struct Importer {
         if (ch->name == "compiler") {
           for (auto& kv : ch->attrs) {
             if (kv.first == "strippath") { strippath = kv.second == "true"; continue; }
-            if (kv.first == "discardvisual" || kv.first == "fusestatic" || kv.first == "angle") continue;
+            if (kv.first == "fusestatic") { fusestatic = kv.second == "true"; continue; }
+            if (kv.first == "discardvisual" || kv.first == "angle") continue;
             comp.emplace_back(kv.first, kv.second);
           }
         } else {
@@ -315,7 +383,7 @@ struct Importer {
       }
     }
     std::set<std::string> open;
-    emit_link(root, nullptr, 0, open);
+    emit_link(root, nullptr, Frame(), 0, open);
     const std::string bodies = out.str();
 
     std::ostringstream doc;

@@ -54,7 +54,10 @@ URDF = """<?xml version="1.0"?>
     <inertial><origin xyz="0 0 0.25"/><mass value="0.5"/><inertia ixx="0.01" iyy="0.01" izz="0.001" ixy="0" ixz="0" iyz="0"/></inertial>
     <collision><origin xyz="0 0 0.5"/><geometry><sphere radius="0.04"/></geometry></collision>
   </link>
-  <link name="tip"/>
+  <link name="tip">
+    <inertial><origin xyz="0 0.01 0.05" rpy="0.2 0 0.1"/><mass value="0.1"/><inertia ixx="0.0002" iyy="0.0003" izz="0.0004" ixy="0.00001" ixz="0" iyz="0.00002"/></inertial>
+    <collision><origin xyz="0 0 0.05" rpy="0 0.3 0"/><geometry><box size="0.04 0.02 0.06"/></geometry></collision>
+  </link>
   <link name="wheel">
     <inertial><mass value="0.2"/><inertia ixx="0.001" iyy="0.001" izz="0.001" ixy="0" ixz="0" iyz="0"/></inertial>
     <collision><geometry><mesh filename="package://cart/meshes/octa.stl" scale="2 2 2"/></geometry></collision>
@@ -75,8 +78,9 @@ def test_urdf_semantics_and_mjcf_round_trip(b2, orc, tmp_path):
     path = tmp_path / "cart.urdf"
     path.write_text(URDF % str(tmp_path))
     m = b2.Model(str(path))
-    assert (m.nq, m.nv, m.njnt, m.nbody) == (3, 3, 3, 5)
-    assert [m.id2name(1, b) for b in range(1, 5)] == ["slider", "pole", "tip", "wheel"]   # "base" is the world
+    # fusestatic (libmujoco's URDF default): "base" is the world, "tip" (fixed joint) is folded into "pole"
+    assert (m.nq, m.nv, m.njnt, m.nbody) == (3, 3, 3, 4)
+    assert [m.id2name(1, b) for b in range(1, 4)] == ["slider", "pole", "wheel"]
     assert list(m.jnt_type) == [2, 3, 3] and list(m.jnt_limited) == [1, 0, 1]       # slide, hinge, hinge
     np.testing.assert_allclose(m.jnt_range.reshape(-1, 2)[0], [-0.5, 0.7])
     np.testing.assert_allclose(m.dof_damping, [0.3, 0, 0]); np.testing.assert_allclose(m.dof_frictionloss, [0.05, 0, 0])
@@ -89,16 +93,31 @@ def test_urdf_semantics_and_mjcf_round_trip(b2, orc, tmp_path):
     Rq = np.array([[1 - 2 * (yy * yy + z * z), 2 * (x * yy - w * z), 2 * (x * z + w * yy)], [2 * (x * yy + w * z), 1 - 2 * (x * x + z * z), 2 * (yy * z - w * x)],
                    [2 * (x * z - w * yy), 2 * (yy * z + w * x), 1 - 2 * (x * x + yy * yy)]])
     np.testing.assert_allclose(Rq, Rz @ Ry @ Rx, atol=1e-14)
-    # box extents and cylinder length are halved; visuals are dropped; mesh scaled
+    # box extents and cylinder length are halved; visuals are dropped; mesh scaled; the fused link's box now belongs to "pole"
     gs = m.geom_size.reshape(-1, 3); gt = list(m.geom_type)
-    assert gt == [6, 5, 2, 7] and m.geom_bodyid[0] == 0      # the root link's box is a world geom
+    assert gt == [6, 5, 2, 6, 7] and m.geom_bodyid[0] == 0 and list(m.geom_bodyid[2:4]) == [2, 2]
     np.testing.assert_allclose(gs[0], [0.2, 0.1, 0.1]); np.testing.assert_allclose(gs[1][:2], [0.05, 0.15]); assert abs(gs[2][0] - 0.04) < 1e-15
+    np.testing.assert_allclose(gs[3], [0.02, 0.01, 0.03]); np.testing.assert_allclose(m.geom_pos.reshape(-1, 3)[3], [0, 0, 0.55], atol=1e-15)
     assert abs(np.abs(m.mesh_vert).max() - 0.3) < 1e-6                      # octahedron z extent 0.15, scaled by 2
-    # the full inertia tensor given in a rotated inertial frame keeps its principal moments (trace, determinant)
+    # the full inertia tensor given in a rotated inertial frame keeps its principal moments
     I = np.array([[0.02, 0.001, -0.002], [0.001, 0.025, 0.0005], [-0.002, 0.0005, 0.03]])
     np.testing.assert_allclose(np.sort(m.body_inertia.reshape(-1, 3)[1]), np.sort(np.linalg.eigvalsh(I)), rtol=1e-10)
-    # massless link behind a fixed joint: bounded by boundmass, welded to its parent
-    assert abs(m.body_mass[3] - 1e-6) < 1e-18 and m.body_dofnum[3] == 0
+    assert abs(m.body_mass[2] - 0.6) < 1e-15                                 # pole 0.5 + fused tip 0.1
+    # <compiler fusestatic="false"/>: every non-root link stays a body; the two models have the same dynamics, which checks the
+    # composed geom transforms and the combined inertial (mass, CoM, parallel-axis terms) of the fused body
+    path2 = tmp_path / "cart_unfused.urdf"
+    path2.write_text((URDF % str(tmp_path)).replace('<compiler ', '<compiler fusestatic="false" '))
+    mu = b2.Model(str(path2))
+    assert mu.nbody == 5 and [mu.id2name(1, b) for b in range(1, 5)] == ["slider", "pole", "tip", "wheel"] and mu.body_dofnum[3] == 0
+    np.testing.assert_allclose(mu.geom_size, m.geom_size)
+    df, du = b2.Data(m), b2.Data(mu)
+    for q, v, f in [([0.1, 0.4, -0.3], [0.2, -0.5, 0.7], [1.0, -0.2, 0.05]), ([-0.3, 2.0, 0.5], [-1.0, 1.5, 0.2], [0.0, 0.3, -0.1])]:
+        af, Mf = forward_qacc(orc, m, df, np.array(q), np.array(v), np.array(f))
+        au, Mu = forward_qacc(orc, mu, du, np.array(q), np.array(v), np.array(f))
+        np.testing.assert_allclose(Mf, Mu, rtol=1e-10, atol=1e-13)
+        np.testing.assert_allclose(af, au, rtol=1e-9, atol=1e-10)
+        orc.call("kinematics", m, df); orc.call("kinematics", mu, du)
+        np.testing.assert_allclose(np.array(df.geom_xpos).reshape(-1, 3)[3], np.array(du.geom_xpos).reshape(-1, 3)[3], atol=1e-13)
     # mj_saveLastXML writes MJCF (src/mujoco_compile.cpp:470); loading that file reproduces the model
     out = tmp_path / "cart.xml"
     err = C.create_string_buffer(1000)
