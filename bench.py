@@ -200,7 +200,7 @@ def drift_report(cfg, nenv=64, horizons=(1, 10, 100, 1000)):
     ws = np.zeros((nenv, m.nv))
     pool = [b2.Data(m) for _ in range(min(16, os.cpu_count() or 1, nenv))]
     probe = b2.Data(m)
-    out = {"envs": nenv, "ticks": list(horizons), "median": [], "max": [], "ncon_equal_frac": []}
+    out = {"envs": nenv, "ticks": list(horizons), "median": [], "max": [], "frac_below_1e-4": [], "ncon_equal_frac": []}
     done = 0
     for k in horizons:
         bt.step(k - done); bt.sync()
@@ -209,6 +209,7 @@ def drift_report(cfg, nenv=64, horizons=(1, 10, 100, 1000)):
         gq = bt.get("qpos")
         rel = np.linalg.norm(gq - rq, axis=1) / np.maximum(np.linalg.norm(rq, axis=1), 1e-12)
         out["median"].append(float(np.median(rel))); out["max"].append(float(rel.max()))
+        out["frac_below_1e-4"].append(float((rel < 1e-4).mean()))   # the north-star bound, per environment
         if m.npair > 0:
             gn = bt.get("ncon")[:, 0]
             rn = np.zeros(nenv, int)
