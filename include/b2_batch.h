@@ -34,7 +34,10 @@ enum {
   B2_TICK_INVERSE = 1 << 1,
   B2_TICK_INTEGRATE = 1 << 2,
   B2_TICK_ODOM = 1 << 3,
-  B2_TICK_NOSOLVE = 1 << 9  /* stop after constraint assembly (mj_step1) */
+  B2_TICK_NOSOLVE = 1 << 9,  /* stop after constraint assembly (mj_step1) */
+  B2_TICK_READ_POST = 1 << 10 /* b2_tick_host / b2_tick_resident: return the joint positions / velocities AFTER the integration
+                                 of this tick (what read() of the next tick would see) instead of the reference's order, where
+                                 MjHWInterface::read runs between mj_step1 and mj_step2 (src/mj_main.cpp:91-108) */
 };
 enum { B2_F32 = 4, B2_F64 = 8, B2_EXPORT_STAGES = 0x100 /* OR into precision: keep stage arrays (qM, xmat, geom poses ...) readable even for contact-free models */ };
 enum { B2_ENV_MAJOR = 0, /* host buffer is [env][n] */ B2_NATIVE = 1 /* host buffer is [n][env] */ };
@@ -97,9 +100,19 @@ int b2_read_joints(b2_batch* b, float* pos_host, float* vel_host, float* effort_
  * controllers compute on the host for its single environment (gains: model/ontology/box/box.yaml:5-13; the result is
  * read as a desired acceleration, src/mujoco_sim/mj_hw_interface.cpp:73-91). */
 int b2_set_pd(b2_batch* b, const float* kp, const float* kd);
-/* end-to-end tick through host buffers: H2D commands, tick, D2H joint states, synchronised */
+/* end-to-end tick through host buffers: H2D commands, tick, D2H joint states, synchronised.  Order of the reference
+ * (src/mj_main.cpp:82-112, mj_hw_interface.cpp:59-71): the joint states are those read() sees between mj_step1 and
+ * mj_step2: qpos of the tick's start, qvel after the controller's velocity override, qfrc_inverse of this tick
+ * (B2_TICK_READ_POST in b2_set_tick_flags switches to the post-integration positions / velocities). */
 int b2_tick_host(b2_batch* b, const float* vel_cmd_host, const float* effort_cmd_host, float* pos_host, float* vel_host,
                  float* effort_host);
+
+/* Zero-copy exchange: buffers of b2_tick_host that are device memory or host memory the caller pinned (cudaHostAlloc,
+ * cudaHostRegister or b2_register_host below) are read / written in place by the tick kernels; pageable buffers are
+ * staged through HBM with two + three copies.  b2_register_host pins a caller-owned range for that purpose; the caller
+ * keeps it alive and calls b2_unregister_host before freeing it (b2_destroy unregisters what is left). */
+int b2_register_host(b2_batch* b, void* host, long long bytes);
+int b2_unregister_host(b2_batch* b, void* host);
 
 /* the same control tick with the command buffers of the last upload re-issued from HBM and the joint states left in
  * HBM: no host<->device traffic, asynchronous (throughput with resident inputs) */

@@ -4,5 +4,5 @@ The product is the native library (mujoco_sim_b200/lib/libb2sim.so: CUDA kernels
 include/b2_batch.h and include/mujoco/mujoco.h).  This Python package is a thin ctypes mirror of that ABI used by the
 tests and the benchmark; it contains no physics.
 """
-from .engine import Batch, Model, Data, lib, lib_path, asset, B2Error  # noqa: F401
+from .engine import Batch, Model, Data, lib, lib_path, asset, B2Error, data_contacts  # noqa: F401
 from . import engine  # noqa: F401

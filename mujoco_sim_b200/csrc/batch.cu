@@ -12,6 +12,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "b2_batch.h"
@@ -280,6 +281,7 @@ int configure_constraint_kernels(b2_batch* b) {
       b->row_smem = b->row_nb ? rs : 0;
     }
     const int need1r = (int)(b->blob_smem + b->row_smem);
+    if (need1 > 227 * 1024 || need1i > 227 * 1024 || need1r > 227 * 1024) return fail("model too large for the constraint kernels' shared memory");
     // row assembly: one record column per thread; 128-thread CTAs when that fits, else 32
     // (k_make_blocks reads the model from HBM: its shared memory is the record columns only)
     b->make_block = (size_t)b->rec_max * 129 * b->prec <= 56 * 1024 ? 128 : 32;
@@ -304,22 +306,29 @@ int configure_constraint_kernels(b2_batch* b) {
         if (need <= 200 * 1024) { b->solve_rows = rows; b->solve_smem = need; break; }
       }
     }
+    // The opt-in limit is a property of (function, device), not of a batch: raise every kernel to the hardware maximum
+    // once per device and never lower it, so that batches of different models can coexist in one process.
+    static bool attr_done[2][64] = {{false}};
     bool ok = true;
-    auto SA = [&](const void* fn, int need) { ok &= cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(need, 48 * 1024)) == cudaSuccess; };
+    auto SA = [&](const void* fn) { ok &= cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) == cudaSuccess; };
+    const int pi = b->prec == 8 ? 1 : 0, di = b->device & 63;
+    if (!attr_done[pi][di]) {
     if (b->prec == 8) {
-      SA((const void*)k_collide<double, 128>, need1); SA((const void*)k_integrate<double, 128>, need1i);
-      SA((const void*)k_integrate<double, 64>, need1i); SA((const void*)k_integrate<double, 32>, need1i);
-      SA((const void*)k_make_rows<double, 128>, need1r); SA((const void*)k_make_blocks<double, 128>, need2); SA((const void*)k_make_blocks<double, 32>, need2);
-      SA((const void*)k_pgs_block<double, 4, 32, PGS_MINB>, need3); SA((const void*)k_pgs_block<double, 8, 32, PGS_MINB>, need3);
-      SA((const void*)k_pgs_block<double, 16, 32, PGS_MINB>, need3); SA((const void*)k_pgs_block<double, 32, 32, PGS_MINB>, need3);
-      SA((const void*)k_solve_rows<double, 16>, (int)b->solve_smem); SA((const void*)k_solve_rows<double, 8>, (int)b->solve_smem); SA((const void*)k_solve_rows<double, 4>, (int)b->solve_smem);
+      SA((const void*)k_collide<double, 128>); SA((const void*)k_integrate<double, 128>);
+      SA((const void*)k_integrate<double, 64>); SA((const void*)k_integrate<double, 32>);
+      SA((const void*)k_make_rows<double, 128>); SA((const void*)k_make_blocks<double, 128>); SA((const void*)k_make_blocks<double, 32>);
+      SA((const void*)k_pgs_block<double, 4, 32, PGS_MINB>); SA((const void*)k_pgs_block<double, 8, 32, PGS_MINB>);
+      SA((const void*)k_pgs_block<double, 16, 32, PGS_MINB>); SA((const void*)k_pgs_block<double, 32, 32, PGS_MINB>);
+      SA((const void*)k_solve_rows<double, 16>); SA((const void*)k_solve_rows<double, 8>); SA((const void*)k_solve_rows<double, 4>);
     } else {
-      SA((const void*)k_collide<float, 128>, need1); SA((const void*)k_integrate<float, 128>, need1i);
-      SA((const void*)k_integrate<float, 64>, need1i); SA((const void*)k_integrate<float, 32>, need1i);
-      SA((const void*)k_make_rows<float, 128>, need1r); SA((const void*)k_make_blocks<float, 128>, need2); SA((const void*)k_make_blocks<float, 32>, need2);
-      SA((const void*)k_pgs_block<float, 4, 32, PGS_MINB>, need3); SA((const void*)k_pgs_block<float, 8, 32, PGS_MINB>, need3);
-      SA((const void*)k_pgs_block<float, 16, 32, PGS_MINB>, need3); SA((const void*)k_pgs_block<float, 32, 32, PGS_MINB>, need3);
-      SA((const void*)k_solve_rows<float, 16>, (int)b->solve_smem); SA((const void*)k_solve_rows<float, 8>, (int)b->solve_smem); SA((const void*)k_solve_rows<float, 4>, (int)b->solve_smem);
+      SA((const void*)k_collide<float, 128>); SA((const void*)k_integrate<float, 128>);
+      SA((const void*)k_integrate<float, 64>); SA((const void*)k_integrate<float, 32>);
+      SA((const void*)k_make_rows<float, 128>); SA((const void*)k_make_blocks<float, 128>); SA((const void*)k_make_blocks<float, 32>);
+      SA((const void*)k_pgs_block<float, 4, 32, PGS_MINB>); SA((const void*)k_pgs_block<float, 8, 32, PGS_MINB>);
+      SA((const void*)k_pgs_block<float, 16, 32, PGS_MINB>); SA((const void*)k_pgs_block<float, 32, 32, PGS_MINB>);
+      SA((const void*)k_solve_rows<float, 16>); SA((const void*)k_solve_rows<float, 8>); SA((const void*)k_solve_rows<float, 4>);
+    }
+    attr_done[pi][di] = ok;
     }
     if (!ok) return fail("cudaFuncSetAttribute failed");
   return 0;
@@ -345,8 +354,9 @@ int launch_chain(b2_batch* b, const KArgs<T>& a, int grid) {
 }
 
 void io_default(b2_batch* b);
-int hw_write_async(b2_batch* b);  // k_hw_write from b->io_in
-int hw_read_async(b2_batch* b);   // k_hw_read into b->io_out
+void drop_aliases(b2_batch* b);
+int hw_write_async(b2_batch* b, int flags = 0, bool gather = false);  // k_hw_write from b->io_in (+ pre-integration pos / vel gather)
+int hw_read_async(b2_batch* b, bool post = true);   // k_hw_read into b->io_out
 enum { B2_TICK_HW = 1 << 20 };  // internal: run k_hw_write / k_hw_read around the tick kernels
 
 template <typename D>
@@ -371,6 +381,7 @@ int run_tick(b2_batch* b, int flags) {
   if ((flags & B2_TICK_ODOM) && b->hdr.nodom > 0) kf |= B2F_ODOM;
   if (b->fused) kf |= B2F_FUSED;
   if (flags & B2_TICK_NOSOLVE) kf |= B2F_NOSOLVE;
+  if (flags & B2_TICK_READ_POST) kf |= B2F_READ_POST;
   if (b->ws_global) kf |= B2F_WS_GLOBAL;
   if (b->ws_global && b->ld_smem) kf |= B2F_LD_SMEM;
   if (b->fusable) kf |= B2F_FUSABLE;
@@ -386,7 +397,8 @@ int run_tick(b2_batch* b, int flags) {
   if (getenv("B2_SMOOTH_CTAS_PER_SM")) per_sm = std::max(1, atoi(getenv("B2_SMOOTH_CTAS_PER_SM")));
   const int grid = std::max(1, std::min(ntiles, b->nsm * per_sm));
   int rc;
-  if ((flags & B2_TICK_HW) && !hwio) { if (hw_write_async(b) < 0) return -1; }
+  const bool read_post = (flags & B2_TICK_READ_POST) != 0;
+  if ((flags & B2_TICK_HW) && !hwio) { if (hw_write_async(b, flags, !read_post) < 0) return -1; }
   if (single) {
     // limit-only serial chain: one kernel does the whole tick (k_chain.cuh)
     prof_mark(b, SLOT_SMOOTH);
@@ -394,7 +406,7 @@ int run_tick(b2_batch* b, int flags) {
     else if constexpr (sizeof(T) == 4) rc = launch_chain1_f32(b, a, grid); else rc = launch_chain1_f64(b, a, grid);
     if (rc < 0) return rc;
     prof_mark(b, SLOT_HW_READ);
-    if ((flags & B2_TICK_HW) && !hwio) { if (hw_read_async(b) < 0) return -1; }
+    if ((flags & B2_TICK_HW) && !hwio) { if (hw_read_async(b, read_post) < 0) return -1; }
     CK(cudaGetLastError());
     return 0;
   }
@@ -466,7 +478,7 @@ int run_tick(b2_batch* b, int flags) {
   }
   if (flags & B2_TICK_INTEGRATE) hold_slots<T>(b);   // inactive object slots go back to their parking place
   prof_mark(b, SLOT_HW_READ);
-  if (flags & B2_TICK_HW) { if (hw_read_async(b) < 0) return -1; }
+  if (flags & B2_TICK_HW) { if (hw_read_async(b, read_post) < 0) return -1; }
   CK(cudaGetLastError());
   return 0;
 }
@@ -684,12 +696,15 @@ __global__ void k_hold_slots(D* qpos, D* qvel, D* qacc, D* qws, const unsigned c
   const int s = (int)(idx / nenv), e = (int)(idx % nenv);
   if (!active[(long long)s * nenvp + e]) park_slot(qpos, qvel, qacc, qws, qadr[s], dadr[s], s, nenvp, e);
 }
-// apply n spawn (pose != nullptr) or destroy requests in order; one thread, the requests of a control tick are few
+// apply n spawn (pose != nullptr) or destroy requests, one thread per request.  "In order" semantics are established on
+// the host: slot_requests() keeps only the LAST request per (environment, slot) of a call (env[i] < 0 marks a dropped
+// duplicate), so the surviving requests touch disjoint state and run in parallel deterministically.
 template <typename D>
 __global__ void k_slot_requests(D* qpos, D* qvel, D* qacc, D* qws, unsigned char* active, const int* qadr, const int* dadr, int nenvp,
                                 int n, const int* env, const int* slot, const float* pose7, const float* twist6) {
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {   // distinct (env, slot) per call are independent; duplicates: last writer wins per element
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const int e = env[i], s = slot[i];
+    if (e < 0) continue;   // superseded by a later request of the same call
     if (pose7) {
       const int qa = qadr[s], da = dadr[s];
       D q[4] = {(D)pose7[7 * i + 3], (D)pose7[7 * i + 4], (D)pose7[7 * i + 5], (D)pose7[7 * i + 6]};
@@ -721,17 +736,29 @@ __global__ void k_pack_obs(const D* __restrict__ qpos, const D* __restrict__ qve
 // MjHWInterface::write (src/mujoco_sim/mj_hw_interface.cpp:73-91) for every environment
 template <typename D>
 __global__ void k_hw_write(D* ddq, D* dq, const float* vel_cmd, const float* eff_cmd, const int* dadr, const int* ctl, int nhw,
-                           int nenv, int nenvp, const D* qpos, const D* qvel, const int* qadr, const float* kp, const float* kd) {
+                           int nenv, int nenvp, const D* qpos, const D* qvel, const int* qadr, const float* kp, const float* kd,
+                           float* pos_out, float* vel_out, int controller) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)nhw * nenv) return;
   const int j = (int)(idx / nenv), e = (int)(idx % nenv);
-  if (!ctl[j]) return;
-  const float v = vel_cmd[idx];
   const int d = dadr[j];
-  if (fabsf(v) > 1e-15f) { dq[(long long)d * nenvp + e] = (D)v; return; }
-  D cmd = (D)eff_cmd[idx];
-  if (kp) cmd = (D)kp[j] * (cmd - qpos[(long long)qadr[j] * nenvp + e]) - (D)kd[j] * qvel[(long long)d * nenvp + e];  // PD stage (b2_set_pd)
-  ddq[(long long)d * nenvp + e] = cmd;
+  const D qj = qpos[(long long)qadr[j] * nenvp + e], vj = qvel[(long long)d * nenvp + e];
+  if (ctl[j]) {
+    const float v = vel_cmd[idx];
+    if (fabsf(v) > 1e-15f) dq[(long long)d * nenvp + e] = (D)v;
+    else {
+      D cmd = (D)eff_cmd[idx];
+      if (kp) cmd = (D)kp[j] * (cmd - qj) - (D)kd[j] * vj;  // PD stage (b2_set_pd)
+      ddq[(long long)d * nenvp + e] = cmd;
+    }
+  }
+  // MjHWInterface::read runs between mj_step1 and mj_step2 (src/mj_main.cpp:91-108): it sees this tick's starting
+  // position and the velocity AFTER the controller's override by a pending velocity command (mj_sim.cpp:1066-1070)
+  if (pos_out) {
+    const D dqv = dq[(long long)d * nenvp + e];
+    pos_out[idx] = (float)qj;
+    vel_out[idx] = (float)((controller && (dqv < 0 ? -dqv : dqv) > D(1e-15)) ? dqv : vj);
+  }
 }
 // MjHWInterface::read gathers (src/mujoco_sim/mj_hw_interface.cpp:62-70)
 template <typename D>
@@ -740,8 +767,10 @@ __global__ void k_hw_read(const D* qpos, const D* qvel, const D* qfrc_inverse, f
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)nhw * nenv) return;
   const int j = (int)(idx / nenv), e = (int)(idx % nenv);
-  pos[idx] = (float)qpos[(long long)qadr[j] * nenvp + e];
-  vel[idx] = (float)qvel[(long long)dadr[j] * nenvp + e];
+  if (pos) {   // B2_TICK_READ_POST; otherwise k_hw_write has gathered them at the start of the tick
+    pos[idx] = (float)qpos[(long long)qadr[j] * nenvp + e];
+    vel[idx] = (float)qvel[(long long)dadr[j] * nenvp + e];
+  }
   eff[idx] = (float)qfrc_inverse[(long long)dadr[j] * nenvp + e];
 }
 
@@ -1110,6 +1139,7 @@ int b2_set_hw_joints(b2_batch* b, int njoint, const int* jnt_ids) {
   CK(cudaMemcpy(b->hw_dadr, dadr.data(), sizeof(int) * njoint, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(b->hw_ctl, ctl.data(), sizeof(int) * njoint, cudaMemcpyHostToDevice));
   b->nhw = njoint;
+  drop_aliases(b);   // the exchange size changed: every cached alias is re-validated against the new size
   b->hw_identity = njoint == b->m->nv;
   for (int j = 0; j < njoint && b->hw_identity; j++) b->hw_identity = qadr[j] == j && dadr[j] == j;
   io_default(b);
@@ -1123,54 +1153,87 @@ void io_default(b2_batch* b) {  // the exchange runs on the HBM staging buffers
   b->io_in[0] = b->hw_buf; b->io_in[1] = b->hw_buf + n;
   b->io_out[0] = b->hw_buf + 2 * n; b->io_out[1] = b->hw_buf + 3 * n; b->io_out[2] = b->hw_buf + 4 * n;
 }
-int hw_write_async(b2_batch* b) {
+int hw_write_async(b2_batch* b, int flags, bool gather) {
   if (!b->nhw) return fail("b2_write_commands: call b2_set_hw_joints first");
   const size_t n = (size_t)b->nhw * b->nenv;
   const int th = 256, bl = (int)((n + th - 1) / th);
-  if (b->prec == 8) k_hw_write<double><<<bl, th, 0, b->stream>>>((double*)b->fields["ddq"].ptr, (double*)b->fields["dq"].ptr, b->io_in[0], b->io_in[1], b->hw_dadr, b->hw_ctl, b->nhw, b->nenv, b->nenvp, (const double*)b->fields["qpos"].ptr, (const double*)b->fields["qvel"].ptr, b->hw_qadr, b->hw_kp, b->hw_kd);
-  else k_hw_write<float><<<bl, th, 0, b->stream>>>((float*)b->fields["ddq"].ptr, (float*)b->fields["dq"].ptr, b->io_in[0], b->io_in[1], b->hw_dadr, b->hw_ctl, b->nhw, b->nenv, b->nenvp, (const float*)b->fields["qpos"].ptr, (const float*)b->fields["qvel"].ptr, b->hw_qadr, b->hw_kp, b->hw_kd);
+  float* po = gather ? b->io_out[0] : nullptr; float* vo = gather ? b->io_out[1] : nullptr;
+  const int ctlr = (flags & B2_TICK_CONTROLLER) ? 1 : 0;
+  if (b->prec == 8) k_hw_write<double><<<bl, th, 0, b->stream>>>((double*)b->fields["ddq"].ptr, (double*)b->fields["dq"].ptr, b->io_in[0], b->io_in[1], b->hw_dadr, b->hw_ctl, b->nhw, b->nenv, b->nenvp, (const double*)b->fields["qpos"].ptr, (const double*)b->fields["qvel"].ptr, b->hw_qadr, b->hw_kp, b->hw_kd, po, vo, ctlr);
+  else k_hw_write<float><<<bl, th, 0, b->stream>>>((float*)b->fields["ddq"].ptr, (float*)b->fields["dq"].ptr, b->io_in[0], b->io_in[1], b->hw_dadr, b->hw_ctl, b->nhw, b->nenv, b->nenvp, (const float*)b->fields["qpos"].ptr, (const float*)b->fields["qvel"].ptr, b->hw_qadr, b->hw_kp, b->hw_kd, po, vo, ctlr);
   b->launches++;
   CK(cudaGetLastError());
   return 0;
 }
-int hw_read_async(b2_batch* b) {
+int hw_read_async(b2_batch* b, bool post) {
   if (!b->nhw) return fail("b2_read_joints: call b2_set_hw_joints first");
   const size_t n = (size_t)b->nhw * b->nenv;
   const int th = 256, bl = (int)((n + th - 1) / th);
-  if (b->prec == 8) k_hw_read<double><<<bl, th, 0, b->stream>>>((const double*)b->fields["qpos"].ptr, (const double*)b->fields["qvel"].ptr, (const double*)b->fields["qfrc_inverse"].ptr, b->io_out[0], b->io_out[1], b->io_out[2], b->hw_qadr, b->hw_dadr, b->nhw, b->nenv, b->nenvp);
-  else k_hw_read<float><<<bl, th, 0, b->stream>>>((const float*)b->fields["qpos"].ptr, (const float*)b->fields["qvel"].ptr, (const float*)b->fields["qfrc_inverse"].ptr, b->io_out[0], b->io_out[1], b->io_out[2], b->hw_qadr, b->hw_dadr, b->nhw, b->nenv, b->nenvp);
+  float* po = post ? b->io_out[0] : nullptr; float* vo = post ? b->io_out[1] : nullptr;
+  if (b->prec == 8) k_hw_read<double><<<bl, th, 0, b->stream>>>((const double*)b->fields["qpos"].ptr, (const double*)b->fields["qvel"].ptr, (const double*)b->fields["qfrc_inverse"].ptr, po, vo, b->io_out[2], b->hw_qadr, b->hw_dadr, b->nhw, b->nenv, b->nenvp);
+  else k_hw_read<float><<<bl, th, 0, b->stream>>>((const float*)b->fields["qpos"].ptr, (const float*)b->fields["qvel"].ptr, (const float*)b->fields["qfrc_inverse"].ptr, po, vo, b->io_out[2], b->hw_qadr, b->hw_dadr, b->nhw, b->nenv, b->nenvp);
   b->launches++;
   CK(cudaGetLastError());
   return 0;
 }
 
-// Device-accessible alias of a caller buffer, or nullptr when it has to be staged.  Device memory and pinned host memory
-// (cudaHostAlloc / cudaHostRegister) are used in place: the kernels read the commands and write the joint states over
-// PCIe themselves, which removes five staging copies from the control tick.  Pageable host memory is pinned once with
-// cudaHostRegister and remembered (B2_NO_ZEROCOPY=1 turns all of this off).
+// Device-accessible alias of a caller buffer, or nullptr when it has to be staged through hw_buf.  Device memory and
+// host memory the CALLER pinned (cudaHostAlloc / cudaHostRegister, or b2_register_host) are used in place: the kernels
+// read the commands and write the joint states over PCIe themselves, which removes five staging copies from the control
+// tick.  Pageable memory is never pinned behind the caller's back (its lifetime is the caller's): it is staged.
+// (B2_NO_ZEROCOPY=1 stages everything.)
 float* device_alias(b2_batch* b, const void* host, size_t bytes) {
   static const bool off = getenv("B2_NO_ZEROCOPY") != nullptr;
+  (void)b; (void)bytes;
   if (off || !host) return nullptr;
   cudaPointerAttributes at;
   if (cudaPointerGetAttributes(&at, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
   if (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) return (float*)const_cast<void*>(host);
-  if (at.type == cudaMemoryTypeHost) return (float*)at.devicePointer;
-  auto it = b->registered.find(host);
-  if (it == b->registered.end() || it->second < bytes) {
-    if (it != b->registered.end()) { cudaHostUnregister(const_cast<void*>(host)); b->registered.erase(it); }
-    if (cudaHostRegister(const_cast<void*>(host), bytes, cudaHostRegisterMapped | cudaHostRegisterPortable) != cudaSuccess) {
-      cudaGetLastError();
-      return nullptr;
-    }
-    b->registered[host] = bytes;
+  if (at.type == cudaMemoryTypeHost) {
+    // a registered range shorter than the exchange (registered for an earlier, smaller joint set) cannot be used in place
+    auto it = b->registered.find(host);
+    if (it != b->registered.end() && it->second < bytes) return nullptr;
+    return (float*)at.devicePointer;
   }
-  void* dp = nullptr;
-  if (cudaHostGetDevicePointer(&dp, const_cast<void*>(host), 0) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-  return (float*)dp;
+  return nullptr;
+}
+void drop_aliases(b2_batch* b) {
+  for (int k = 0; k < 5; k++) { b->alias_host[k] = nullptr; b->alias_dev[k] = nullptr; b->alias_bytes[k] = 0; }
 }
 
 }  // namespace
 extern "C" {
+
+// Explicit pinning of caller-owned pageable buffers for the in-place (zero-copy) exchange of b2_tick_host.  The caller
+// keeps the buffer alive until b2_unregister_host (or b2_destroy) and must unregister BEFORE freeing it.
+int b2_register_host(b2_batch* b, void* host, long long bytes) {
+  if (!b || !host || bytes <= 0) return fail("b2_register_host: bad argument");
+  CK(cudaSetDevice(b->device));
+  auto it = b->registered.find(host);
+  if (it != b->registered.end()) {
+    if (it->second >= (size_t)bytes) return 0;
+    cudaHostUnregister(host);
+    b->registered.erase(it);
+  }
+  drop_aliases(b);
+  drop_graphs(b);
+  const cudaError_t e = cudaHostRegister(host, (size_t)bytes, cudaHostRegisterMapped | cudaHostRegisterPortable);
+  if (e != cudaSuccess) { cudaGetLastError(); return fail(std::string("b2_register_host: cudaHostRegister: ") + cudaGetErrorString(e)); }
+  b->registered[host] = (size_t)bytes;
+  return 0;
+}
+int b2_unregister_host(b2_batch* b, void* host) {
+  if (!b || !host) return fail("b2_unregister_host: bad argument");
+  CK(cudaSetDevice(b->device));
+  auto it = b->registered.find(host);
+  if (it == b->registered.end()) return fail("b2_unregister_host: not registered through b2_register_host");
+  CK(cudaStreamSynchronize(b->stream));   // no kernel may still be reading / writing the range
+  drop_aliases(b);
+  drop_graphs(b);                          // captured ticks hold the device alias in their kernel arguments
+  cudaHostUnregister(host);
+  b->registered.erase(it);
+  return 0;
+}
 
 int b2_set_pd(b2_batch* b, const float* kp, const float* kd) {
   if (!b) return fail("b2_set_pd: null batch");
@@ -1218,9 +1281,9 @@ int b2_read_joints(b2_batch* b, float* pos, float* vel, float* eff) {
 
 // One control tick as the reference's loop body sees it (src/mj_main.cpp:82-112):
 // write(commands) -> step1 + controller -> read (mj_inverse) -> step2 -> odom; joint states out.
-// Note on order: the reference reads the joint state between mj_step1 and mj_step2 (pre-integration qpos/qvel,
-// qfrc_inverse of this tick); the gather here returns qfrc_inverse of this tick and the post-integration qpos/qvel,
-// i.e. exactly what read() of the NEXT tick would return for positions and velocities.
+// Order: the reference reads the joint state between mj_step1 and mj_step2 (qpos of the tick's start, qvel after the
+// controller's override, qfrc_inverse of this tick) and so does this tick; B2_TICK_READ_POST (b2_set_tick_flags) returns
+// the post-integration qpos / qvel instead, i.e. what read() of the NEXT tick would see.
 static int tick_hw(b2_batch* b, const float* vel, const float* eff, float* pos, float* velo, float* effo, bool sync) {
   CK(cudaSetDevice(b->device));
   if (!b->nhw) return fail("b2_tick_host: call b2_set_hw_joints first");
@@ -1232,7 +1295,9 @@ static int tick_hw(b2_batch* b, const float* vel, const float* eff, float* pos, 
   float* out[3] = {pos, velo, effo};
   float* stage_out[3] = {nullptr, nullptr, nullptr};
   auto alias = [&](int slot, const void* host) -> float* {
-    if (b->alias_host[slot] != host) { b->alias_host[slot] = host; b->alias_dev[slot] = device_alias(b, host, n * 4); }
+    if (b->alias_host[slot] != host || b->alias_bytes[slot] != n * 4) {
+      b->alias_host[slot] = host; b->alias_bytes[slot] = n * 4; b->alias_dev[slot] = device_alias(b, host, n * 4);
+    }
     return b->alias_dev[slot];
   };
   for (int k = 0; k < 2; k++) {
@@ -1297,6 +1362,18 @@ static int slot_requests(b2_batch* b, int n, const int* env, const int* slot, co
   if (n == 0) return 0;
   for (int i = 0; i < n; i++)
     if (env[i] < 0 || env[i] >= b->nenv || slot[i] < 0 || slot[i] >= b->nslot) return fail("b2_spawn / b2_destroy_slots: environment or slot out of range");
+  // requests are applied in order: of several requests for one (environment, slot) only the last one has an effect
+  std::vector<int> env_last(env, env + n);
+  {
+    std::unordered_map<long long, int> last;
+    last.reserve((size_t)n * 2);
+    for (int i = 0; i < n; i++) {
+      const long long key = (long long)env[i] * b->nslot + slot[i];
+      auto it = last.find(key);
+      if (it != last.end()) { env_last[it->second] = -1; it->second = i; } else last.emplace(key, i);
+    }
+  }
+  env = env_last.data();
   // one staging block: env | slot | pose7 | twist6
   const size_t bytes = (size_t)n * (2 * sizeof(int) + 13 * sizeof(float));
   if (ensure_stage(b, bytes) < 0) return -1;
@@ -1309,10 +1386,10 @@ static int slot_requests(b2_batch* b, int n, const int* env, const int* slot, co
   if (spawn && twist6) CK(cudaMemcpyAsync(d_tw, twist6, sizeof(float) * 6 * n, cudaMemcpyHostToDevice, b->stream));
   auto P = [&](const char* nm) { return b->fields[nm].ptr; };
   if (b->prec == 8)
-    k_slot_requests<double><<<1, 256, 0, b->stream>>>((double*)P("qpos"), (double*)P("qvel"), (double*)P("qacc"), (double*)P("qacc_warmstart"), b->slot_active,
+    k_slot_requests<double><<<std::min(64, (n + 255) / 256), 256, 0, b->stream>>>((double*)P("qpos"), (double*)P("qvel"), (double*)P("qacc"), (double*)P("qacc_warmstart"), b->slot_active,
                                                       b->slot_qadr, b->slot_dadr, b->nenvp, n, d_env, d_slot, spawn ? d_pose : nullptr, spawn && twist6 ? d_tw : nullptr);
   else
-    k_slot_requests<float><<<1, 256, 0, b->stream>>>((float*)P("qpos"), (float*)P("qvel"), (float*)P("qacc"), (float*)P("qacc_warmstart"), b->slot_active,
+    k_slot_requests<float><<<std::min(64, (n + 255) / 256), 256, 0, b->stream>>>((float*)P("qpos"), (float*)P("qvel"), (float*)P("qacc"), (float*)P("qacc_warmstart"), b->slot_active,
                                                      b->slot_qadr, b->slot_dadr, b->nenvp, n, d_env, d_slot, spawn ? d_pose : nullptr, spawn && twist6 ? d_tw : nullptr);
   b->launches++;
   CK(cudaGetLastError());

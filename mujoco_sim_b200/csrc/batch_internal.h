@@ -74,10 +74,11 @@ struct b2_batch {
   // caller's host buffers (pinned / registered memory is read and written in place over PCIe, no staging copies)
   const float* io_in[2] = {nullptr, nullptr};
   float* io_out[3] = {nullptr, nullptr, nullptr};
-  std::map<const void*, size_t> registered;  // host ranges this batch pinned with cudaHostRegister
+  std::map<const void*, size_t> registered;  // host ranges pinned through b2_register_host (the caller owns their lifetime)
   // device aliases of the caller buffers seen by the last b2_tick_host (the control loop passes the same ones every tick)
   const void* alias_host[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   float* alias_dev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  size_t alias_bytes[5] = {0, 0, 0, 0, 0};   // the cache key is (pointer, exchange bytes)
   // kernel argument block, rebuilt only after a field (re)allocation
   b2::KArgs<float> args_f{};
   b2::KArgs<double> args_d{};

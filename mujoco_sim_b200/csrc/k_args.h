@@ -19,6 +19,7 @@ enum TickFlags : int {
   B2F_FUSABLE = 1 << 9,      // joint limits are the only constraint source: environments without an active limit are
                              // integrated by the smooth kernel (status bit 8) and skipped by the constraint pipeline
   B2F_LD_SMEM = 1 << 11,     // k_smooth (workspace in HBM) factorises M in a shared-memory scratch column per thread
+  B2F_READ_POST = 1 << 12,   // hardware read returns post-integration qpos / qvel (default: the reference's pre-integration order)
   B2F_HWIO = 1 << 10,        // k_chain also does MjHWInterface::write / read (hardware joint j == dof j): commands are read
                              // from, and joint states written to, the hw_* buffers (HBM or mapped host memory)
 };

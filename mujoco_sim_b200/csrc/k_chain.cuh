@@ -451,6 +451,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_chain(const KArgs<T> a) {
     }
 #pragma unroll
     for (int i = 0; i < N; i++) { a.qacc[i * S + env] = acc[i]; a.qacc_warmstart[i * S + env] = acc[i]; }
+    // MjHWInterface::read sits between mj_step1 and mj_step2 (src/mj_main.cpp:91-108): joint states before the integration
+    if (!(a.flags & B2F_READ_POST)) hw_out(q, v, finv);
     if (a.flags & B2F_INTEGRATE) {
       LArr<T, N> xa;
       if (h.has_damping && !(h.disableflags & DSBL_EULERDAMP)) {
@@ -477,7 +479,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_chain(const KArgs<T> a) {
 #pragma unroll
       for (int i = 0; i < N; i++) a.qvel[i * S + env] = v[i];
     }
-    hw_out(q, v, finv);
+    if (a.flags & B2F_READ_POST) hw_out(q, v, finv);
   }
 }
 

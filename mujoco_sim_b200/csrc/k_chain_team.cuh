@@ -521,6 +521,8 @@ __global__ void __launch_bounds__(BLOCK) k_chain_team(const KArgs<T> a) {
     }
     const bool live = !(stat & 16);
     if (on && live) { a.qacc[at] = acc; a.qacc_warmstart[at] = acc; }
+    // MjHWInterface::read sits between mj_step1 and mj_step2 (src/mj_main.cpp:91-108): joint states before the integration
+    if (live && !(a.flags & B2F_READ_POST)) hw_out(q, v, finv);
     if (a.flags & B2F_INTEGRATE) {
       T xa = acc;
       if (h.has_damping && !(h.disableflags & DSBL_EULERDAMP)) {
@@ -539,7 +541,7 @@ __global__ void __launch_bounds__(BLOCK) k_chain_team(const KArgs<T> a) {
     } else if (ov_team && on && live) {
       a.qvel[at] = v;
     }
-    if (live) hw_out(q, v, finv);
+    if (live && (a.flags & B2F_READ_POST)) hw_out(q, v, finv);
     prefetch(tile + gridDim.x);
     if (hwio) {
       __syncthreads();

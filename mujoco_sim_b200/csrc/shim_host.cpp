@@ -207,6 +207,15 @@ int b2_model_set_opt(mjModel* m, const char* name, double value) {
   else return -1;
   return 0;
 }
+/* bulk view of the contact list of an mjData: geom ids and distances of the first min(n, ncon) contacts; returns ncon */
+int b2_data_contacts(const mjData* d, int n, int* geom1, int* geom2, double* dist) {
+  for (int i = 0; i < n && i < d->ncon; i++) {
+    if (geom1) geom1[i] = d->contact[i].geom1;
+    if (geom2) geom2[i] = d->contact[i].geom2;
+    if (dist) dist[i] = d->contact[i].dist;
+  }
+  return d->ncon;
+}
 int b2_data_contact(const mjData* d, int i, mjContact* out) {
   if (i < 0 || i >= d->ncon) return -1;
   *out = d->contact[i];

@@ -26,7 +26,7 @@ if not os.path.exists(lib_path()):
                       "(there is no Python or CPU fallback for the CUDA engine)" % lib_path())
 lib = C.CDLL(lib_path(), mode=C.RTLD_GLOBAL)
 
-TICK_CONTROLLER, TICK_INVERSE, TICK_INTEGRATE, TICK_ODOM, TICK_NOSOLVE = 1, 2, 4, 8, 1 << 9
+TICK_CONTROLLER, TICK_INVERSE, TICK_INTEGRATE, TICK_ODOM, TICK_NOSOLVE, TICK_READ_POST = 1, 2, 4, 8, 1 << 9, 1 << 10
 F32, F64, EXPORT_STAGES = 4, 8, 0x100
 ENV_MAJOR, NATIVE = 0, 1
 OBJ_BODY, OBJ_JOINT, OBJ_GEOM, OBJ_MESH = 1, 3, 5, 9
@@ -54,6 +54,7 @@ _sig = {
     "b2_model_array": (_i, [_vp, _cp, C.POINTER(_vp), C.POINTER(_i)]),
     "b2_data_array": (_i, [_vp, _vp, _cp, C.POINTER(_vp), C.POINTER(_i)]),
     "b2_model_set_opt": (_i, [_vp, _cp, C.c_double]),
+    "b2_data_contacts": (_i, [_vp, _i, _vp, _vp, _vp]),
     "b2_last_error": (_cp, []),
     "b2_device_count": (_i, []),
     "b2_create": (_vp, [_vp, _i, _i, _i]),
@@ -86,6 +87,8 @@ _sig = {
     "b2_read_joints": (_i, [_vp, _vp, _vp, _vp]),
     "b2_tick_host": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "b2_tick_resident": (_i, [_vp]),
+    "b2_register_host": (_i, [_vp, _vp, C.c_longlong]),
+    "b2_unregister_host": (_i, [_vp, _vp]),
     "b2_pack_obs": (_i, [_vp, _vp]),
     "b2_set_pd": (_i, [_vp, _vp, _vp]),
     "b2_set_slots": (_i, [_vp, _i, _vp]),
@@ -209,6 +212,15 @@ class Data:
         if name in ("time", "ncon", "nefc", "solver_iter"):
             return a[0]
         return a
+
+
+def data_contacts(data, nmax=None):
+    """(geom1, geom2, dist) arrays of the contact list held by an mjData (the legacy single-environment view)."""
+    n = int(data.ncon) if nmax is None else int(nmax)
+    g1, g2, dist = np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n, np.float64)
+    if n:
+        lib.b2_data_contacts(data.ptr, n, g1.ctypes.data, g2.ctypes.data, dist.ctypes.data)
+    return g1, g2, dist
 
 
 class Batch:
@@ -336,6 +348,13 @@ class Batch:
 
     def tick_host_raw(self, vel_ptr, eff_ptr, pos_ptr, velo_ptr, effo_ptr):
         self._ck(lib.b2_tick_host(self.ptr, vel_ptr, eff_ptr, pos_ptr, velo_ptr, effo_ptr), "b2_tick_host")
+
+    def register_host(self, arr):
+        """Pin a caller-owned numpy buffer for the zero-copy exchange of tick_host (b2_register_host)."""
+        self._ck(lib.b2_register_host(self.ptr, arr.ctypes.data, arr.nbytes), "b2_register_host")
+
+    def unregister_host(self, arr):
+        self._ck(lib.b2_unregister_host(self.ptr, arr.ctypes.data), "b2_unregister_host")
 
     def set_pd(self, kp=None, kd=None):
         """Device-side PD stage: the effort-command buffer then carries position targets (b2_set_pd)."""

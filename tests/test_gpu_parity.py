@@ -271,10 +271,74 @@ def test_hw_interface_roundtrip(b2):
     assert np.all(dq[::2, 3] == 0.5) and np.all(ddq[::2, 3] == 0)      # velocity command wins
     assert np.all(ddq[1::2, 3] == 4) and np.all(ddq[:, 0] == 1)
     pos = np.empty((7, nenv), np.float32); velo = np.empty_like(pos); effo = np.empty_like(pos)
+    q_before = bt.get("qpos", layout=b2.engine.NATIVE, dtype=np.float32)
+    bt.tick_host_raw(vel.ctypes.data, eff.ctypes.data, pos.ctypes.data, velo.ctypes.data, effo.ctypes.data)
+    # the reference's order: read() runs between mj_step1 and mj_step2 (mj_main.cpp:91-108): positions of the tick's start,
+    # velocities after the controller's override, this tick's inverse dynamics
+    np.testing.assert_array_equal(pos, q_before)
+    assert np.all(velo[3, ::2] == 0.5) and np.all(velo[3, 1::2] == 0)
+    np.testing.assert_array_equal(effo, bt.get("qfrc_inverse", layout=b2.engine.NATIVE, dtype=np.float32))
+    assert np.all(np.isfinite(effo)) and np.abs(bt.get("qvel")).max() > 0
+    # B2_TICK_READ_POST: what read() of the next tick would see
+    bt.set_tick_flags(b2.engine.TICK_INTEGRATE | b2.engine.TICK_READ_POST)
     bt.tick_host_raw(vel.ctypes.data, eff.ctypes.data, pos.ctypes.data, velo.ctypes.data, effo.ctypes.data)
     np.testing.assert_array_equal(pos, bt.get("qpos", layout=b2.engine.NATIVE, dtype=np.float32))
-    np.testing.assert_array_equal(effo, bt.get("qfrc_inverse", layout=b2.engine.NATIVE, dtype=np.float32))
-    assert np.all(np.isfinite(effo)) and np.abs(velo).max() > 0
+    np.testing.assert_array_equal(velo, bt.get("qvel", layout=b2.engine.NATIVE, dtype=np.float32))
+
+
+@pytest.mark.parametrize("name", ["panda7.xml", "ur5_tabletop.xml", "mobile_arm.xml"])
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_tick_host_read_order_matches_reference_loop(b2, orc, name, prec):
+    """b2_tick_host against the reference's loop body restated with the oracle (src/mj_main.cpp:82-112): write -> mj_step1 ->
+    controller -> read() = mj_inverse + gathers of d->qpos / d->qvel / d->qfrc_inverse (mj_hw_interface.cpp:59-71) -> mj_step2.
+    Every tick's joint position, velocity and effort must be the ones read() sees BEFORE the integration.  Single-kernel
+    chain path (panda7), the generic pipeline with contacts (ur5_tabletop) and a fusable generic tree (mobile_arm)."""
+    m = b2.Model(b2.asset(name))
+    nenv, nv, ticks = 12, m.nv, 6
+    qpos, qvel, _ = states_for(m, name, nenv, 4242)
+    jt = np.array(m.jnt_type)
+    hw = np.where(jt >= 2)[0].astype(np.int32)
+    dadr = np.array(m.jnt_dofadr)[hw]; qadr = np.array(m.jnt_qposadr)[hw]
+    ctl = np.zeros(nv, np.uint8); ctl[dadr] = 1
+    if hw.size > 2:
+        ctl[dadr[-1]] = 0   # one uncontrolled hardware joint
+    rng = np.random.default_rng(9)
+    eff = rng.uniform(-2, 2, (hw.size, nenv)).astype(np.float32)
+    vel = np.zeros((hw.size, nenv), np.float32); vel[1, ::3] = 0.25
+    f64 = prec == "f64"
+    bt = b2.Batch(m, nenv, precision=b2.engine.F64 if f64 else b2.engine.F32)
+    bt.set("qpos", qpos); bt.set("qvel", qvel)
+    bt.set_controlled(ctl); bt.set_hw_joints(hw)
+    got = []
+    out = [np.zeros((hw.size, nenv), np.float32) for _ in range(3)]
+    for s in range(ticks):
+        bt.tick_host_raw(vel.ctypes.data, eff.ctypes.data, *[o.ctypes.data for o in out])
+        got.append([o.copy() for o in out])
+    d = b2.Data(m)
+    ref = np.zeros((ticks, 3, hw.size, nenv))
+    for e in range(nenv):
+        d.qpos[:] = qpos[e]; d.qvel[:] = qvel[e]; d.qacc[:] = 0; d.qacc_warmstart[:] = 0; d.qfrc_applied[:] = 0
+        for s in range(ticks):
+            ddq = np.zeros(nv); dq = np.zeros(nv)
+            for j in range(hw.size):                       # MjHWInterface::write
+                if not ctl[dadr[j]]:
+                    continue
+                if abs(vel[j, e]) > 1e-15:
+                    dq[dadr[j]] = vel[j, e]
+                else:
+                    ddq[dadr[j]] = eff[j, e]
+            orc.call("step1", m, d)
+            orc.controller(m, d, ddq, dq, ctl)
+            orc.call("inverse", m, d)                      # MjHWInterface::read
+            ref[s, 0, :, e] = d.qpos[qadr]; ref[s, 1, :, e] = d.qvel[dadr]; ref[s, 2, :, e] = d.qfrc_inverse[dadr]
+            orc.call("step2", m, d)
+    ptol, ftol = (2e-6, 2e-5) if f64 else (2e-3, 2e-2)     # fp32 host buffers bound the fp64 batch at ~1e-6
+    for s in range(ticks):
+        np.testing.assert_allclose(got[s][0], ref[s, 0], atol=ptol, err_msg="pos tick %d" % s)
+        np.testing.assert_allclose(got[s][1], ref[s, 1], atol=ptol * 10, err_msg="vel tick %d" % s)
+        scale = max(1.0, np.abs(ref[s, 2]).max())
+        np.testing.assert_allclose(got[s][2], ref[s, 2], atol=ftol * scale, err_msg="effort tick %d" % s)
+    bt.close()
 
 
 def test_mujoco_named_shim_steps_like_the_oracle(b2, orc):
@@ -550,7 +614,9 @@ def test_limit_only_chain_runs_as_one_kernel_per_tick(b2):
 def test_hw_exchange_fused_zero_copy_equals_staged_kernels(b2):
     """The control tick through host buffers gives bit-identical joint states whether k_chain does the hardware
     exchange itself on the caller's pinned buffers (zero-copy) or k_hw_write / k_hw_read run around it on the HBM
-    staging area (B2_NO_HWIO=1), with pinned (torch) and pageable (numpy, registered on first use) host memory."""
+    staging area (B2_NO_HWIO=1), with pinned (torch), pageable (numpy: staged through HBM by memcpy, never pinned behind the
+    caller's back) and explicitly registered (b2_register_host) host memory; a registered buffer can be unregistered and the
+    tick then falls back to staging with the same results."""
     import os
     import torch
     m = b2.Model(b2.asset("panda7.xml"))
@@ -571,11 +637,17 @@ def test_hw_exchange_fused_zero_copy_equals_staged_kernels(b2):
         else:
             bufs = [vel.copy(), eff.copy()] + [np.zeros((7, nenv), np.float32) for _ in range(3)]
             ptrs = [t.ctypes.data for t in bufs]; outs = bufs[2:]
+        if mode == "registered":
+            for t in bufs:
+                bt.register_host(t)
         if mode == "staged":
             os.environ["B2_NO_HWIO"] = "1"
         try:
             l0 = bt.launch_count
-            for _ in range(6):
+            for k in range(6):
+                if mode == "registered" and k == 3:   # mid-run: back to staged copies, same numbers
+                    for t in bufs:
+                        bt.unregister_host(t)
                 bt.tick_host_raw(*ptrs)
             n = bt.launch_count - l0
         finally:
@@ -583,10 +655,10 @@ def test_hw_exchange_fused_zero_copy_equals_staged_kernels(b2):
         res = [o.copy() for o in outs] + [bt.get("qpos"), bt.get("qacc")]
         bt.close()
         return n, res
-    n_p, r_p = run("pinned"); n_g, r_g = run("pageable"); n_s, r_s = run("staged")
-    assert n_p == 6 and n_g == 6 and n_s == 18
-    for x, y, z in zip(r_p, r_g, r_s):
-        assert np.array_equal(x, z) and np.array_equal(y, z)
+    n_p, r_p = run("pinned"); n_g, r_g = run("pageable"); n_s, r_s = run("staged"); n_r, r_r = run("registered")
+    assert n_p == 6 and n_g == 6 and n_s == 18 and n_r == 6
+    for x, y, z, u in zip(r_p, r_g, r_s, r_r):
+        assert np.array_equal(x, z) and np.array_equal(y, z) and np.array_equal(u, z)
     assert np.abs(r_p[0]).max() > 0 and np.all(np.isfinite(r_p[2]))
 
 
