@@ -39,6 +39,9 @@ int fail(const std::string& msg) { return b2::set_error(msg); }
   } while (0)
 }  // namespace
 
+#ifndef PGS_ISL_MINB
+#define PGS_ISL_MINB 8
+#endif
 #ifndef PGS_MINB
 #define PGS_MINB 16
 #endif
@@ -243,6 +246,7 @@ KArgs<T> build_args(b2_batch* b) {
   a.efc_ARdiag = R("efc_ARdiag"); a.efc_B = R("efc_B"); a.efc_blocks = R("efc_blocks"); a.efc_nwords = I("efc_nwords"); a.env_order = I("env_order");
   a.blk_row0 = I("blk_row0"); a.blk_off = I("blk_off"); a.nblk = I("nblk"); a.maxblk = I("_maxblk"); a.solver_iter = I("solver_iter"); a.status = I("status");
   a.pending = I("_pending");
+  a.isl_off = I("isl_off"); a.isl_end = I("isl_end"); a.nisl = I("nisl");
   return a;
 }
 // the field pointers are looked up by name once per (re)allocation, not once per tick
@@ -257,7 +261,7 @@ KArgs<T> make_args(b2_batch* b, int flags) {
   if constexpr (sizeof(T) == 4) a = b->args_f; else a = b->args_d;
   a.model = b->blob_dev; a.model_words = b->hdr.nwords;
   a.flags = flags; a.ws_block = b->smooth_block; a.h = (T)b->h; a.wp = b->wp;
-  a.block_capw = b->block_capw; a.block_npar = b->block_npar; a.stage_cap = b->stage_cap; a.row_nb = b->row_nb;
+  a.block_capw = b->block_capw; a.block_npar = b->block_npar; a.stage_cap = b->isl_cap ? b->isl_stage : b->stage_cap; a.row_nb = b->row_nb; a.isl_cap = b->isl_cap;
   a.hw_vel = b->io_in[0]; a.hw_eff = b->io_in[1];
   a.hw_pos = b->io_out[0]; a.hw_velo = b->io_out[1]; a.hw_effo = b->io_out[2];
   a.hw_kp = b->hw_kp; a.hw_kd = b->hw_kd;
@@ -280,7 +284,18 @@ int configure_constraint_kernels(b2_batch* b) {
       b->row_nb = (!getenv("B2_NO_ROW_SMEM") && b->blob_smem + rs <= 180 * 1024) ? nbm : 0;
       b->row_smem = b->row_nb ? rs : 0;
     }
-    const int need1r = (int)(b->blob_smem + b->row_smem);
+    // k_make_rows with island ordering: two int columns of ntree entries per thread behind the row column
+    b->isl_smem = b->isl_cap ? (size_t)2 * b->hdr.ntree * 128 * sizeof(int) : 0;
+    const int need1r = (int)(b->blob_smem + b->row_smem + b->isl_smem);
+    if (b->isl_cap) {
+      // k_pgs_island: EPB environments per one-warp CTA, each with its vectors and its staged records; the stage is sized
+      // for eight resident CTAs per SM
+      const int epbi = 32 / b->pgs_isl;
+      const long long fixedi = ((long long)2 * (b->hdr.nv + 4) + ((b->hdr.njmax + 3) & ~3)) * b->prec + (long long)b->isl_cap * 4;
+      long long capi = getenv("B2_PGS_STAGE") ? atoi(getenv("B2_PGS_STAGE")) : (long long)((220 * 1024 / 8) / epbi - fixedi) / b->prec;
+      capi = std::max(0LL, std::min<long long>(capi, b->block_capw)) & ~3LL;
+      b->isl_stage = (int)capi;
+    }
     if (need1 > 227 * 1024 || need1i > 227 * 1024 || need1r > 227 * 1024) return fail("model too large for the constraint kernels' shared memory");
     // row assembly: one record column per thread; 128-thread CTAs when that fits, else 32
     // (k_make_blocks reads the model from HBM: its shared memory is the record columns only)
@@ -314,19 +329,21 @@ int configure_constraint_kernels(b2_batch* b) {
     const int pi = b->prec == 8 ? 1 : 0, di = b->device & 63;
     if (!attr_done[pi][di]) {
     if (b->prec == 8) {
-      SA((const void*)k_collide<double, 128>); SA((const void*)k_integrate<double, 128>);
+      SA((const void*)k_collide<double, 128, 8>); SA((const void*)k_integrate<double, 128>);
       SA((const void*)k_integrate<double, 64>); SA((const void*)k_integrate<double, 32>);
-      SA((const void*)k_make_rows<double, 128>); SA((const void*)k_make_blocks<double, 128>); SA((const void*)k_make_blocks<double, 32>);
+      SA((const void*)k_make_rows<double, 128, 8>); SA((const void*)k_make_blocks<double, 128>); SA((const void*)k_make_blocks<double, 32>);
       SA((const void*)k_pgs_block<double, 4, 32, PGS_MINB>); SA((const void*)k_pgs_block<double, 8, 32, PGS_MINB>);
       SA((const void*)k_pgs_block<double, 16, 32, PGS_MINB>); SA((const void*)k_pgs_block<double, 32, 32, PGS_MINB>);
       SA((const void*)k_solve_rows<double, 16>); SA((const void*)k_solve_rows<double, 8>); SA((const void*)k_solve_rows<double, 4>);
+      SA((const void*)k_pgs_island<double, 4, PGS_ISL_MINB>); SA((const void*)k_pgs_island<double, 8, PGS_ISL_MINB>); SA((const void*)k_pgs_island<double, 16, PGS_ISL_MINB>);
     } else {
-      SA((const void*)k_collide<float, 128>); SA((const void*)k_integrate<float, 128>);
+      SA((const void*)k_collide<float, 128, 8>); SA((const void*)k_integrate<float, 128>);
       SA((const void*)k_integrate<float, 64>); SA((const void*)k_integrate<float, 32>);
-      SA((const void*)k_make_rows<float, 128>); SA((const void*)k_make_blocks<float, 128>); SA((const void*)k_make_blocks<float, 32>);
+      SA((const void*)k_make_rows<float, 128, 8>); SA((const void*)k_make_blocks<float, 128>); SA((const void*)k_make_blocks<float, 32>);
       SA((const void*)k_pgs_block<float, 4, 32, PGS_MINB>); SA((const void*)k_pgs_block<float, 8, 32, PGS_MINB>);
       SA((const void*)k_pgs_block<float, 16, 32, PGS_MINB>); SA((const void*)k_pgs_block<float, 32, 32, PGS_MINB>);
       SA((const void*)k_solve_rows<float, 16>); SA((const void*)k_solve_rows<float, 8>); SA((const void*)k_solve_rows<float, 4>);
+      SA((const void*)k_pgs_island<float, 4, PGS_ISL_MINB>); SA((const void*)k_pgs_island<float, 8, PGS_ISL_MINB>); SA((const void*)k_pgs_island<float, 16, PGS_ISL_MINB>);
     }
     attr_done[pi][di] = ok;
     }
@@ -425,10 +442,21 @@ int run_tick(b2_batch* b, int flags) {
     const int g2 = std::max(1, std::min(nt, b->nsm * 4));
     const size_t sm = b->blob_smem;
     prof_mark(b, SLOT_COLLIDE);
-    if (b->m->npair > 0) { k_collide<T, BL><<<g2, BL, sm, b->stream>>>(a); b->launches++; }
+    if (b->m->npair > 0) {
+      // a team of 8 lanes per environment: 16 environments per CTA, the candidate list of each behind the model blob
+      constexpr int CL = 8;
+      const size_t smc = 16 + (((size_t)b->hdr.nwords * 4 + 15) & ~(size_t)15) + (size_t)(BL / CL) * ((b->m->npair + 1) & ~1) * sizeof(uint16_t);
+      const int gc = std::max(1, std::min(b->nenvp / (BL / CL), b->nsm * std::max(1, std::min(8, (int)(200 * 1024 / smc)))));
+      k_collide<T, BL, CL><<<gc, BL, smc, b->stream>>>(a);
+      b->launches++;
+    }
     prof_mark(b, SLOT_MAKE);
     CK(cudaMemsetAsync(a.maxblk, 0, sizeof(int), b->stream));
-    k_make_rows<T, BL><<<g2, BL, sm + b->row_smem, b->stream>>>(a);
+    {
+      constexpr int RL = 8;   // lanes per environment
+      const int gr = std::max(1, std::min(b->nenvp / (BL / RL), b->nsm * std::max(1, std::min(8, (int)(220 * 1024 / (sm + b->row_smem + b->isl_smem + 1024))))));
+      k_make_rows<T, BL, RL><<<gr, BL, sm + b->row_smem + b->isl_smem, b->stream>>>(a);
+    }
     if (b->solve_rows > 0) {
       // wide trees: M^-1 J^T of all rows up front, the tile's factor shared through shared memory (k_solve_rows)
       const int gs = std::max(1, std::min(b->nenvp / 32, b->nsm * std::max(1, (int)(227 * 1024 / (b->solve_smem + 1024)))));
@@ -456,6 +484,15 @@ int run_tick(b2_batch* b, int flags) {
       // one warp per CTA and one CTA per group of environments: the hardware scheduler balances the very uneven
       // per-environment work (contact counts) dynamically
       constexpr int PB = 32;
+      if (b->isl_cap) {
+        // several small trees: one lane per constraint island (k_pgs_island)
+        const int epbi = 32 / b->pgs_isl;
+        const size_t smi = ((size_t)2 * (b->hdr.nv + 4) + ((b->hdr.njmax + 3) & ~3) + b->isl_stage) * epbi * sizeof(T) + (size_t)epbi * b->isl_cap * sizeof(int);
+        const int gi = b->nenvp / epbi;
+        if (b->pgs_isl == 4) k_pgs_island<T, 4, PGS_ISL_MINB><<<gi, 32, smi, b->stream>>>(a);
+        else if (b->pgs_isl == 16) k_pgs_island<T, 16, PGS_ISL_MINB><<<gi, 32, smi, b->stream>>>(a);
+        else k_pgs_island<T, 8, PGS_ISL_MINB><<<gi, 32, smi, b->stream>>>(a);
+      } else {
       const int epb = PB / b->pgs_lanes;
       const size_t smp = ((size_t)2 * (b->hdr.nv + 4) + b->hdr.njmax + b->stage_cap) * epb * sizeof(T);
       const int g3 = b->nenvp / epb;
@@ -463,6 +500,7 @@ int run_tick(b2_batch* b, int flags) {
       else if (b->pgs_lanes == 16) k_pgs_block<T, 16, PB, PGS_MINB><<<g3, PB, smp, b->stream>>>(a);
       else if (b->pgs_lanes == 32) k_pgs_block<T, 32, PB, PGS_MINB><<<g3, PB, smp, b->stream>>>(a);
       else k_pgs_block<T, 8, PB, PGS_MINB><<<g3, PB, smp, b->stream>>>(a);
+      }
       prof_mark(b, SLOT_INTEGRATE);
       if (kf & B2F_LD_SMEM) {
         const size_t smi = sm + b->ld_smem;
@@ -863,6 +901,10 @@ b2_batch* b2_create(const mjModel* m, int nenv, int device, int precision) {
     const int wm = b->hdr.wmax;
     b->pgs_lanes = getenv("B2_PGS_LANES") ? atoi(getenv("B2_PGS_LANES")) : (wm <= 16 ? 8 : (wm <= 32 ? 16 : 32));
     if (b->pgs_lanes != 4 && b->pgs_lanes != 16 && b->pgs_lanes != 32) b->pgs_lanes = 8;
+    // models made of several small kinematic trees (arm + free objects, object slots): island-parallel solver
+    b->isl_cap = (b->hdr.ntree >= 2 && b->hdr.ntree <= 32 && wm <= 16 && !getenv("B2_NO_ISLANDS")) ? b->hdr.ntree : 0;
+    b->pgs_isl = getenv("B2_PGS_ISL") ? atoi(getenv("B2_PGS_ISL")) : 8;
+    if (b->pgs_isl != 4 && b->pgs_isl != 16) b->pgs_isl = 8;
   }
   struct Spec { const char* name; long long count; int kind; };
   std::vector<Spec> specs = {
@@ -885,6 +927,7 @@ b2_batch* b2_create(const mjModel* m, int nenv, int device, int precision) {
         {"efc_frictionloss", njmax, 0}, {"efc_diagApprox", njmax, 0}, {"efc_R", njmax, 0}, {"efc_D", njmax, 0}, {"efc_KBI", 3 * njmax, 0},
         {"efc_vel", njmax, 0}, {"efc_aref", njmax, 0}, {"efc_b", njmax, 0}, {"efc_force", njmax, 0}, {"efc_finv", njmax, 0}, {"efc_ARdiag", njmax, 0},
         {"efc_blocks", b->block_capw, 0}, {"efc_nwords", 1, 1}, {"env_order", 1, 1}, {"blk_row0", njmax, 1}, {"blk_off", njmax, 1}, {"nblk", 1, 1}, {"_maxblk", 1, 1}};
+    if (b->isl_cap) { more.push_back({"isl_off", b->isl_cap, 1}); more.push_back({"isl_end", b->isl_cap, 1}); more.push_back({"nisl", 1, 1}); }
     // wide trees (the criterion of make_block == 32): M^-1 J^T of every row is produced by k_solve_rows into efc_B
     if ((size_t)b->rec_max * 129 * b->prec > 56 * 1024 && !getenv("B2_NO_SOLVE_ROWS")) more.push_back({"efc_B", njmax * b->hdr.wmax, 0});
     specs.insert(specs.end(), more.begin(), more.end());

@@ -48,6 +48,10 @@ struct b2_batch {
   int block_npar = 0;    // ... of which header + parameters
   int make_block = 128;  // CTA size of k_make_constraint
   int pgs_lanes = 8;     // lanes per environment in k_pgs_block
+  int isl_cap = 0;       // island slots per environment (k_pgs_island: models made of several small trees); 0: k_pgs_block
+  int pgs_isl = 8;       // lanes (= islands relaxed side by side) per environment in k_pgs_island
+  int isl_stage = 0;     // words of records k_pgs_island stages per environment
+  size_t isl_smem = 0;   // k_make_rows: island label columns
   size_t ld_smem = 0;    // bytes of the shared-memory factor scratch of k_smooth / k_integrate (workspace in HBM), 0: off
   int row_nb = 0;        // k_make_rows' shared-memory row column: base rows it holds (0: off)
   size_t row_smem = 0;

@@ -68,6 +68,11 @@ struct KArgs {
   int* env_order;         // [nenvp] visit order of the solver (k_order_envs)
   int *blk_row0, *blk_off; // [njmax][nenvp] block table: first row / word offset of block i (k_make_rows -> k_make_blocks)
   int* nblk;              // [nenvp] blocks of the environment
+  // constraint islands (k_make_rows -> k_pgs_island): connected components of the graph "kinematic trees joined by the
+  // blocks that touch two of them".  The blocks of an island are contiguous in the slab (original order kept inside it).
+  int *isl_off, *isl_end; // [isl_cap][nenvp] word range of island i in the environment's slab
+  int* nisl;              // [nenvp] islands of the environment
+  int isl_cap;            // island slots allocated per environment (0: no island ordering, the slab is in row order)
   int* maxblk;            // [1] largest block count of this tick (cleared by a memset node in front of k_make_rows)
   int block_capw;         // words of efc_blocks per environment
   int block_npar;         // header + parameter words of the largest block (k_make_blocks' shared-memory column layout)

@@ -762,7 +762,67 @@ __device__ void load_geom(GeomW<T>& g, const MV<T>& m, const KArgs<T>& a, int gi
   g.vert = reinterpret_cast<const T*>(a.model + h.o_mesh_vert) + 3 * m.i(h.o_geom_vertadr, gi);
 }
 
-template <typename T, int BLOCK>
+// complete contact c of the environment from a raw narrow-phase result: frame, margins, parameter mixing, ids
+template <typename T>
+__device__ void emit_contact(const MV<T>& m, const KArgs<T>& a, int env, int c, const RawCon<T>& raw, int g1, int g2, int p, T margin) {
+  const DModel& h = *m.h;
+  const long long S = a.nenvp;
+  auto F = [&](int f) -> T& { return a.con[((long long)f * h.nconmax + c) * S + env]; };
+  auto I = [&](int f) -> int& { return a.coni[((long long)f * h.nconmax + c) * S + env]; };
+  F(CF_DIST) = raw.dist;
+  for (int k = 0; k < 3; k++) F(CF_POS + k) = raw.pos[k];
+  // complete the frame: normal, tangent hint (Gram-Schmidt) or a fixed pick, then their cross product
+  T x[3] = {raw.n[0], raw.n[1], raw.n[2]}, y[3] = {raw.tan[0], raw.tan[1], raw.tan[2]}, z[3];
+  normalize3(x);
+  if (norm3(y) < T(0.5)) {
+    y[0] = 0; y[1] = 0; y[2] = 0;
+    if (x[1] < T(0.5) && x[1] > T(-0.5)) y[1] = 1; else y[2] = 1;
+  }
+  const T dd = dot3(x, y);
+  y[0] -= dd * x[0]; y[1] -= dd * x[1]; y[2] -= dd * x[2];
+  normalize3(y);
+  cross3(z, x, y);
+  for (int k = 0; k < 3; k++) { F(CF_FRAME + k) = x[k]; F(CF_FRAME + 3 + k) = y[k]; F(CF_FRAME + 6 + k) = z[k]; }
+  const T gap = t_max(m.f(h.o_geom_gap, g1), m.f(h.o_geom_gap, g2));
+  F(CF_INCLUDEMARGIN) = margin - gap;
+  // parameter mixing
+  const int pr1 = m.i(h.o_geom_priority, g1), pr2 = m.i(h.o_geom_priority, g2);
+  T fr[3];
+  int dim;
+  if (pr1 != pr2) {
+    const int g = pr1 > pr2 ? g1 : g2;
+    dim = m.i(h.o_geom_condim, g);
+    for (int k = 0; k < 3; k++) fr[k] = m.f(h.o_geom_friction, 3 * g + k);
+    for (int k = 0; k < 2; k++) F(CF_SOLREF + k) = m.f(h.o_geom_solref, 2 * g + k);
+    for (int k = 0; k < 5; k++) F(CF_SOLIMP + k) = m.f(h.o_geom_solimp, 5 * g + k);
+  } else {
+    dim = max(m.i(h.o_geom_condim, g1), m.i(h.o_geom_condim, g2));
+    for (int k = 0; k < 3; k++) fr[k] = t_max(m.f(h.o_geom_friction, 3 * g1 + k), m.f(h.o_geom_friction, 3 * g2 + k));
+    const T s1 = m.f(h.o_geom_solmix, g1), s2 = m.f(h.o_geom_solmix, g2);
+    T mix;
+    if (s1 >= Eps<T>::minval() && s2 >= Eps<T>::minval()) mix = s1 / (s1 + s2);
+    else if (s1 < Eps<T>::minval() && s2 < Eps<T>::minval()) mix = T(0.5);
+    else mix = s1 < Eps<T>::minval() ? T(0) : T(1);
+    const T r10 = m.f(h.o_geom_solref, 2 * g1), r20 = m.f(h.o_geom_solref, 2 * g2);
+    for (int k = 0; k < 2; k++) {
+      const T r1 = m.f(h.o_geom_solref, 2 * g1 + k), r2 = m.f(h.o_geom_solref, 2 * g2 + k);
+      F(CF_SOLREF + k) = (r10 > 0 && r20 > 0) ? mix * r1 + (1 - mix) * r2 : t_min(r1, r2);
+    }
+    for (int k = 0; k < 5; k++) F(CF_SOLIMP + k) = mix * m.f(h.o_geom_solimp, 5 * g1 + k) + (1 - mix) * m.f(h.o_geom_solimp, 5 * g2 + k);
+  }
+  const T minmu = T(1e-5);
+  F(CF_FRICTION) = F(CF_FRICTION + 1) = t_max(minmu, fr[0]);
+  F(CF_FRICTION + 2) = t_max(minmu, fr[1]);
+  F(CF_FRICTION + 3) = F(CF_FRICTION + 4) = t_max(minmu, fr[2]);
+  I(CI_GEOM1) = g1; I(CI_GEOM2) = g2; I(CI_DIM) = dim; I(CI_PAIR) = p; I(CI_EFC) = -1;
+}
+
+// K2 + K3: a team of L lanes per environment.  Phase 1: the lanes cull the static pair list side by side (bounding
+// spheres; planes by signed centre distance) and compact the survivors, in pair order, into a shared-memory candidate
+// list (ballot + popcount).  Phase 2: L candidates at a time go through the narrow phase, one per lane; an exclusive
+// scan of the contact counts over the team gives every lane its output slots, so the contact list comes out in
+// MuJoCo's pair order whatever the team width (geom ids and pair indices are bit-exact against the sequential oracle).
+template <typename T, int BLOCK, int L>
 __global__ void __launch_bounds__(BLOCK) k_collide(const KArgs<T> a) {
   if ((a.flags & B2F_FUSABLE) && a.pending[0] == 0) return;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -773,85 +833,68 @@ __global__ void __launch_bounds__(BLOCK) k_collide(const KArgs<T> a) {
   MV<T> m{reinterpret_cast<const DModel*>(blob), blob};
   const DModel& h = *m.h;
   const long long S = a.nenvp;
-  const int ntiles = a.nenvp / BLOCK;
+  constexpr int EPB = BLOCK / L;
+  const int ntiles = a.nenvp / EPB;
   const bool off = h.disableflags & (DSBL_CONSTRAINT | DSBL_CONTACT);
+  const int team = threadIdx.x / L, l = threadIdx.x % L;
+  const int tshift = (threadIdx.x & 31) & ~(L - 1);
+  const unsigned tmask = (L == 32 ? 0xffffffffu : ((1u << L) - 1u)) << tshift;
+  const int npp = (h.npair + 1) & ~1;
+  uint16_t* cand = reinterpret_cast<uint16_t*>(smem_raw + 16 + (((size_t)nwords * 4 + 15) & ~(size_t)15)) + (size_t)team * npp;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int env = tile * BLOCK + threadIdx.x;
-    int ncon = 0;
-    for (int p = 0; p < h.npair && !off; p++) {
-      const int g1 = m.i(h.o_pair_geom1, p), g2 = m.i(h.o_pair_geom2, p);
-      const int t1 = m.i(h.o_geom_type, g1), t2 = m.i(h.o_geom_type, g2);
-      const T margin = t_max(m.f(h.o_geom_margin, g1), m.f(h.o_geom_margin, g2));
-      // broad phase: bounding spheres (planes: signed centre distance)
-      T x1[3], x2[3];
-      for (int k = 0; k < 3; k++) { x1[k] = a.geom_xpos[(3 * g1 + k) * S + env]; x2[k] = a.geom_xpos[(3 * g2 + k) * S + env]; }
-      const T dif[3] = {x2[0] - x1[0], x2[1] - x1[1], x2[2] - x1[2]};
-      if (t1 == GEOM_PLANE) {
-        const T n[3] = {a.geom_xmat[(9 * g1 + 2) * S + env], a.geom_xmat[(9 * g1 + 5) * S + env], a.geom_xmat[(9 * g1 + 8) * S + env]};
-        if (dot3(dif, n) > m.f(h.o_geom_rbound, g2) + margin) continue;
-      } else {
-        const T bound = m.f(h.o_geom_rbound, g1) + m.f(h.o_geom_rbound, g2) + margin;
-        if (dot3(dif, dif) > bound * bound) continue;
-      }
-      GeomW<T> ga, gb;
-      load_geom(ga, m, a, g1, env);
-      load_geom(gb, m, a, g2, env);
-      RawCon<T> raw[B2_MAXCONPAIR];
-      const int n = narrow_phase(raw, t1, t2, ga, gb, margin);
-      for (int i = 0; i < n; i++) {
-        if (ncon >= h.nconmax) { a.status[env] |= 1; break; }
-        const int c = ncon++;
-        auto F = [&](int f) -> T& { return a.con[((long long)f * h.nconmax + c) * S + env]; };
-        auto I = [&](int f) -> int& { return a.coni[((long long)f * h.nconmax + c) * S + env]; };
-        F(CF_DIST) = raw[i].dist;
-        for (int k = 0; k < 3; k++) F(CF_POS + k) = raw[i].pos[k];
-        // complete the frame: normal, tangent hint (Gram-Schmidt) or a fixed pick, then their cross product
-        T x[3] = {raw[i].n[0], raw[i].n[1], raw[i].n[2]}, y[3] = {raw[i].tan[0], raw[i].tan[1], raw[i].tan[2]}, z[3];
-        normalize3(x);
-        if (norm3(y) < T(0.5)) {
-          y[0] = 0; y[1] = 0; y[2] = 0;
-          if (x[1] < T(0.5) && x[1] > T(-0.5)) y[1] = 1; else y[2] = 1;
-        }
-        const T dd = dot3(x, y);
-        y[0] -= dd * x[0]; y[1] -= dd * x[1]; y[2] -= dd * x[2];
-        normalize3(y);
-        cross3(z, x, y);
-        for (int k = 0; k < 3; k++) { F(CF_FRAME + k) = x[k]; F(CF_FRAME + 3 + k) = y[k]; F(CF_FRAME + 6 + k) = z[k]; }
-        const T gap = t_max(m.f(h.o_geom_gap, g1), m.f(h.o_geom_gap, g2));
-        F(CF_INCLUDEMARGIN) = margin - gap;
-        // parameter mixing
-        const int pr1 = m.i(h.o_geom_priority, g1), pr2 = m.i(h.o_geom_priority, g2);
-        T fr[3];
-        int dim;
-        if (pr1 != pr2) {
-          const int g = pr1 > pr2 ? g1 : g2;
-          dim = m.i(h.o_geom_condim, g);
-          for (int k = 0; k < 3; k++) fr[k] = m.f(h.o_geom_friction, 3 * g + k);
-          for (int k = 0; k < 2; k++) F(CF_SOLREF + k) = m.f(h.o_geom_solref, 2 * g + k);
-          for (int k = 0; k < 5; k++) F(CF_SOLIMP + k) = m.f(h.o_geom_solimp, 5 * g + k);
+    const int env = tile * EPB + team;
+    int ncand = 0;
+    __syncwarp(tmask);
+    for (int base = 0; base < h.npair && !off; base += L) {
+      const int p = base + l;
+      bool pass = false;
+      if (p < h.npair) {
+        const int g1 = m.i(h.o_pair_geom1, p), g2 = m.i(h.o_pair_geom2, p);
+        const int t1 = m.i(h.o_geom_type, g1);
+        const T margin = t_max(m.f(h.o_geom_margin, g1), m.f(h.o_geom_margin, g2));
+        T x1[3], x2[3];
+        for (int k = 0; k < 3; k++) { x1[k] = a.geom_xpos[(3 * g1 + k) * S + env]; x2[k] = a.geom_xpos[(3 * g2 + k) * S + env]; }
+        const T dif[3] = {x2[0] - x1[0], x2[1] - x1[1], x2[2] - x1[2]};
+        if (t1 == GEOM_PLANE) {
+          const T n[3] = {a.geom_xmat[(9 * g1 + 2) * S + env], a.geom_xmat[(9 * g1 + 5) * S + env], a.geom_xmat[(9 * g1 + 8) * S + env]};
+          pass = !(dot3(dif, n) > m.f(h.o_geom_rbound, g2) + margin);
         } else {
-          dim = max(m.i(h.o_geom_condim, g1), m.i(h.o_geom_condim, g2));
-          for (int k = 0; k < 3; k++) fr[k] = t_max(m.f(h.o_geom_friction, 3 * g1 + k), m.f(h.o_geom_friction, 3 * g2 + k));
-          const T s1 = m.f(h.o_geom_solmix, g1), s2 = m.f(h.o_geom_solmix, g2);
-          T mix;
-          if (s1 >= Eps<T>::minval() && s2 >= Eps<T>::minval()) mix = s1 / (s1 + s2);
-          else if (s1 < Eps<T>::minval() && s2 < Eps<T>::minval()) mix = T(0.5);
-          else mix = s1 < Eps<T>::minval() ? T(0) : T(1);
-          const T r10 = m.f(h.o_geom_solref, 2 * g1), r20 = m.f(h.o_geom_solref, 2 * g2);
-          for (int k = 0; k < 2; k++) {
-            const T r1 = m.f(h.o_geom_solref, 2 * g1 + k), r2 = m.f(h.o_geom_solref, 2 * g2 + k);
-            F(CF_SOLREF + k) = (r10 > 0 && r20 > 0) ? mix * r1 + (1 - mix) * r2 : t_min(r1, r2);
-          }
-          for (int k = 0; k < 5; k++) F(CF_SOLIMP + k) = mix * m.f(h.o_geom_solimp, 5 * g1 + k) + (1 - mix) * m.f(h.o_geom_solimp, 5 * g2 + k);
+          const T bound = m.f(h.o_geom_rbound, g1) + m.f(h.o_geom_rbound, g2) + margin;
+          pass = !(dot3(dif, dif) > bound * bound);
         }
-        const T minmu = T(1e-5);
-        F(CF_FRICTION) = F(CF_FRICTION + 1) = t_max(minmu, fr[0]);
-        F(CF_FRICTION + 2) = t_max(minmu, fr[1]);
-        F(CF_FRICTION + 3) = F(CF_FRICTION + 4) = t_max(minmu, fr[2]);
-        I(CI_GEOM1) = g1; I(CI_GEOM2) = g2; I(CI_DIM) = dim; I(CI_PAIR) = p; I(CI_EFC) = -1;
       }
+      const unsigned bal = (__ballot_sync(tmask, pass) >> tshift) & (L == 32 ? 0xffffffffu : ((1u << L) - 1u));
+      if (pass) cand[ncand + __popc(bal & ((1u << l) - 1u))] = (uint16_t)p;
+      ncand += __popc(bal);
     }
-    a.ncon[env] = ncon;
+    __syncwarp(tmask);
+    int ncon = 0;
+    for (int base = 0; base < ncand; base += L) {
+      const int i = base + l;
+      int n = 0, g1 = 0, g2 = 0, p = 0;
+      T margin = 0;
+      RawCon<T> raw[B2_MAXCONPAIR];
+      if (i < ncand) {
+        p = cand[i];
+        g1 = m.i(h.o_pair_geom1, p); g2 = m.i(h.o_pair_geom2, p);
+        margin = t_max(m.f(h.o_geom_margin, g1), m.f(h.o_geom_margin, g2));
+        GeomW<T> ga, gb;
+        load_geom(ga, m, a, g1, env);
+        load_geom(gb, m, a, g2, env);
+        n = narrow_phase(raw, ga.type, gb.type, ga, gb, margin);
+      }
+      int incl = n;
+#pragma unroll
+      for (int o = 1; o < L; o <<= 1) { const int v = __shfl_up_sync(tmask, incl, o, L); if (l >= o) incl += v; }
+      const int total = __shfl_sync(tmask, incl, L - 1, L);
+      const int first = ncon + incl - n;
+      for (int j = 0; j < n; j++) {
+        if (first + j >= h.nconmax) { a.status[env] |= 1; break; }
+        emit_contact(m, a, env, first + j, raw[j], g1, g2, p, margin);
+      }
+      ncon = min(ncon + total, h.nconmax);
+    }
+    if (l == 0) a.ncon[env] = ncon;
   }
 }
 

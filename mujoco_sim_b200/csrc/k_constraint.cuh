@@ -71,10 +71,13 @@ struct Rows {
   // start a new zero row over trees (t1, t2); returns its index or -1 when njmax is exhausted
   __device__ int open(int type, int id, T pos, T margin, T frictionloss, int t1, int t2, Seg* gout, bool zero = true) {
     if (nefc >= h.njmax) { a.status[env] |= 2; return -1; }
+    return open_at(nefc++, type, id, pos, margin, frictionloss, t1, t2, gout, zero);
+  }
+  // the same for a row whose index is already known (contacts assembled side by side by the lanes of a team)
+  __device__ int open_at(int r, int type, int id, T pos, T margin, T frictionloss, int t1, int t2, Seg* gout, bool zero = true) {
     if (t1 < 0) { t1 = t2; t2 = -1; }
     if (t1 == t2) t2 = -1;
     if (t2 >= 0 && t2 < t1) { const int t = t1; t1 = t2; t2 = t; }
-    const int r = nefc++;
     const Seg g = seg_of(m, t1, t2);
     if (zero) for (int k = 0; k < g.n1 + g.n2; k++) Jc(r, k) = 0;
     a.efc_tree[((long long)2 * r) * S + env] = t1;
@@ -224,53 +227,47 @@ struct Rows {
     }
   }
 
-  __device__ void contacts() {
-    if (h.disableflags & DSBL_CONTACT) return;
+  // first row of every contact, in contact order (sequential: a contact that does not fit is dropped whole, later and
+  // smaller ones may still fit).  Returns the row count after the contacts.
+  __device__ int contact_offsets(int ne0) {
+    if (h.disableflags & DSBL_CONTACT) return ne0;
     const int ncon = a.ncon[env];
+    int r = ne0;
     for (int c = 0; c < ncon; c++) {
+      const int dim = a.coni[((long long)CI_DIM * h.nconmax + c) * S + env];
+      const int nrow = dim == 1 ? 1 : 2 * (dim - 1);
+      int& efc = a.coni[((long long)CI_EFC * h.nconmax + c) * S + env];
+      if (r + nrow > h.njmax) { a.status[env] |= 2; efc = -1; }
+      else { efc = r; r += nrow; }
+    }
+    return r;
+  }
+
+  // rows of contact c (first row from contact_offsets): headers, the base directions' Jacobians, impedance, cone R
+  __device__ void contact_one(int c) {
       auto F = [&](int f) -> T { return a.con[((long long)f * h.nconmax + c) * S + env]; };
       auto I = [&](int f) -> int& { return a.coni[((long long)f * h.nconmax + c) * S + env]; };
+      const int first = I(CI_EFC);
+      if (first < 0) return;
       const int dim = I(CI_DIM);
       const int b1 = m.i(h.o_geom_bodyid, I(CI_GEOM1)), b2 = m.i(h.o_geom_bodyid, I(CI_GEOM2));
-      T pos[3], frame[9], fri[5];
+      T pos[3], frame[9];
       for (int k = 0; k < 3; k++) pos[k] = F(CF_POS + k);
       for (int k = 0; k < 9; k++) frame[k] = F(CF_FRAME + k);
-      for (int k = 0; k < 5; k++) fri[k] = F(CF_FRICTION + k);
       const T dist = F(CF_DIST), im = F(CF_INCLUDEMARGIN);
       const int nrow = dim == 1 ? 1 : 2 * (dim - 1);
-      const int first = nefc;
-      if (first + nrow > h.njmax) { a.status[env] |= 2; I(CI_EFC) = -1; continue; }  // kept whole or dropped whole
       Seg g;
       const int t1 = m.i(h.o_body_treeid, b1), t2 = m.i(h.o_body_treeid, b2);
       // With a shared-memory column the dim base rows are accumulated there and stored once: in HBM every "+=" of a
       // Jacobian entry is a load behind a store (an L2 round trip), ~100 per contact.  Rows dim .. nrow - 1 of a pyramidal
       // contact are index space only (never read: k_solve_rows / k_make_blocks work on the base rows) and are left as is.
       const bool sh = rowsh != nullptr && dim <= a.row_nb;
-      for (int k = 0; k < nrow; k++) open(dim == 1 ? CN_CONTACT_FRICTIONLESS : CN_CONTACT_PYRAMIDAL, c, dist, im, 0, t1, t2, &g, !sh);
-      I(CI_EFC) = first;
+      for (int k = 0; k < nrow; k++) open_at(first + k, dim == 1 ? CN_CONTACT_FRICTIONLESS : CN_CONTACT_PYRAMIDAL, c, dist, im, 0, t1, t2, &g, !sh);
       const int wrow = g.n1 + g.n2;
       auto RS = [&](int k, int e) -> T& { return rowsh[((long long)k * h.wmax + e) * rowld]; };
       if (sh) {
         for (int k = 0; k < dim; k++)
           for (int e = 0; e < wrow; e++) RS(k, e) = 0;
-        for (int side = 0; side < 2; side++) {
-          const int b = side ? b2 : b1;
-          const T sg = side ? T(1) : T(-1);
-          T off[3];
-          point_off(b, pos, off);
-          for (int i = m.i(h.o_body_lastdof, b); i >= 0; i = m.i(h.o_dof_parentid, i)) {
-            T jp[3], jr[3], fp[3], fr[3];
-            jac_col(i, off, jp, jr);
-            mat_vec3(fp, frame, jp);
-            mat_vec3(fr, frame, jr);
-            const int kk = seg_pos(g, i);
-            RS(0, kk) += sg * fp[0];
-            for (int k = 1; k < dim; k++) RS(k, kk) += sg * (k < 3 ? fp[k] : fr[k - 3]);
-          }
-        }
-        for (int k = 0; k < dim; k++)
-          for (int e = 0; e < wrow; e++) Jc(first + k, e) = RS(k, e);
-        continue;
       }
       for (int side = 0; side < 2; side++) {
         const int b = side ? b2 : b1;
@@ -285,22 +282,34 @@ struct Rows {
           const int kk = seg_pos(g, i);
           // rows first .. first + dim - 1 hold the BASE directions of the contact: normal, tangent 1, tangent 2, torsion,
           // rolling 1, rolling 2 (unscaled); pyramid row 2 (k - 1) + s is base 0 +/- friction[k - 1] * base k and is never
-          // materialised on the hot path (k_make_constraint works on the dim base rows, the legacy efc_J view is expanded
-          // on demand)
-          Jc(first, kk) += sg * fp[0];
-          for (int k = 1; k < dim; k++) Jc(first + k, kk) += sg * (k < 3 ? fp[k] : fr[k - 3]);
+          // materialised on the hot path (the legacy efc_J view is expanded on demand)
+          if (sh) {
+            RS(0, kk) += sg * fp[0];
+            for (int k = 1; k < dim; k++) RS(k, kk) += sg * (k < 3 ? fp[k] : fr[k - 3]);
+          } else {
+            Jc(first, kk) += sg * fp[0];
+            for (int k = 1; k < dim; k++) Jc(first + k, kk) += sg * (k < 3 ? fp[k] : fr[k - 3]);
+          }
         }
       }
-    }
+      if (sh)
+        for (int k = 0; k < dim; k++)
+          for (int e = 0; e < wrow; e++) Jc(first + k, e) = RS(k, e);
+      finish_range(first, first + nrow, 1);
+      if (dim > 1) {   // pyramidal cones share R = 2 mu^2 R_first
+        const T mu = F(CF_FRICTION) / t_sqrt(t_max(Eps<T>::minval(), m.f(h.o_opt_real, 5)));
+        const T Rpy = t_max(Eps<T>::minval(), 2 * mu * mu * a.efc_R[(long long)first * S + env]);
+        for (int j = 0; j < nrow; j++) a.efc_R[(long long)(first + j) * S + env] = Rpy;
+      }
   }
 
   // diagApprox, impedance -> R, D; K, B, imp; aref; (vel uses the current, possibly overridden, qvel)
-  __device__ void finish() {
+  __device__ void finish_range(int r0, int r1, int step) {
     const T hs = a.h;
     // the rows of one contact share its parameters: fetched once per contact (13 HBM loads), not once per row
     int c_id = -1, c_first = 0;
     T c_solref[2] = {0, 0}, c_solimp[5] = {0, 0, 0, 0, 0}, c_tran = 0, c_rot = 0;
-    for (int r = 0; r < nefc; r++) {
+    for (int r = r0; r < r1; r += step) {
       const int type = a.efc_type[(long long)r * S + env], id = a.efc_id[(long long)r * S + env];
       T solref[2], solimp[5], diag;
       if (type == CN_EQUALITY) {
@@ -368,16 +377,6 @@ struct Rows {
       a.efc_KBI[((long long)1 * h.njmax + r) * S + env] = B;
       a.efc_KBI[((long long)2 * h.njmax + r) * S + env] = imp;
     }
-    // pyramidal cones share R = 2 mu^2 R_first
-    const int ncon = a.ncon[env];
-    for (int c = 0; c < ncon; c++) {
-      const int adr = a.coni[((long long)CI_EFC * h.nconmax + c) * S + env];
-      const int dim = a.coni[((long long)CI_DIM * h.nconmax + c) * S + env];
-      if (adr < 0 || dim == 1) continue;
-      const T mu = a.con[((long long)CF_FRICTION * h.nconmax + c) * S + env] / t_sqrt(t_max(Eps<T>::minval(), m.f(h.o_opt_real, 5)));
-      const T Rpy = t_max(Eps<T>::minval(), 2 * mu * mu * a.efc_R[(long long)adr * S + env]);
-      for (int j = 0; j < 2 * (dim - 1); j++) a.efc_R[(long long)(adr + j) * S + env] = Rpy;
-    }
   }
 };
 
@@ -429,7 +428,9 @@ struct BlockShape {
     oA = oMu + (nb > 1 ? nb - 1 : 0);
     oJ = (oA + (nb > 1 ? nrow * (nrow - 1) / 2 : 0) + 3) & ~3;
     oB = oJ + nb * wq;
-    len = oB + nb * wq;
+    // records are whole 128-byte lines: the lanes of k_pgs_island keep the bank alignment they were staged with while they
+    // walk from record to record
+    len = (oB + nb * wq + 31) & ~31;
   }
   __host__ __device__ int dof(int e) const { return e < n1 ? s1 + e : s2 + e - n1; }
   // position of (r, s), r < s, in the packed strict upper triangle
@@ -450,7 +451,7 @@ __device__ __forceinline__ BlockShape block_shape(const T* rec) {
   return s;
 }
 // words one environment can need: every row as a single-row block is the worst case
-__host__ __device__ inline int block_capacity(int njmax, int wmax) { return njmax * (BH_N + 4 + 2 * ((wmax + 3) & ~3)); }
+__host__ __device__ inline int block_capacity(int njmax, int wmax) { return njmax * ((BH_N + 4 + 2 * ((wmax + 3) & ~3) + 31) & ~31); }
 // words of header + row parameters (everything in front of J) of the largest block
 __host__ __device__ inline int block_max_params(int nbmax) {
   BlockShape s{};
@@ -465,27 +466,58 @@ __host__ __device__ inline int block_max_words(int nbmax, int wmax) {
   return s.len;
 }
 
-// K4: rows and impedance in MuJoCo's row order — the inherently sequential part — and the block table (first row, word
-// offset in the slab) that lets k_make_blocks work on all blocks of all environments at once.  One thread per environment.
-template <typename T, int BLOCK>
+// K4: rows and impedance in MuJoCo's row order, and the block table (first row, word offset in the slab) that lets
+// k_make_blocks work on all blocks of all environments at once.  A team of L lanes per environment: lane 0 opens the
+// scalar rows (equalities, friction loss, limits) and fixes every contact's first row — the inherently sequential part —
+// then the lanes assemble the contacts side by side (headers, base-direction Jacobians, impedance, cone R: a contact is
+// independent of the others once its first row is known) and share the impedance pass over the scalar rows; lane 0
+// finishes with the block table and the island ordering.
+template <typename T, int BLOCK, int L>
 __global__ void __launch_bounds__(BLOCK) k_make_rows(const KArgs<T> a) {
   B2_KERNEL_PROLOGUE
+  (void)ntiles;
+  constexpr int EPB = BLOCK / L;
+  const int nteams = a.nenvp / EPB;
+  const int team = threadIdx.x / L, l = threadIdx.x % L;
+  const int tshift = (threadIdx.x & 31) & ~(L - 1);
+  const unsigned tmask = (L == 32 ? 0xffffffffu : ((1u << L) - 1u)) << tshift;
   int wmaxblk = 0;
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int env = tile * BLOCK + threadIdx.x;
+  for (int tile = blockIdx.x; tile < nteams; tile += gridDim.x) {
+    const int env = tile * EPB + team;
     Rows<T> rows(m, a, env);
     if (a.row_nb > 0) { rows.rowsh = reinterpret_cast<T*>(smem_raw + 16 + (size_t)nwords * 4) + threadIdx.x; rows.rowld = BLOCK; }
     const bool done = (a.flags & B2F_FUSABLE) && (a.status[env] & 8);  // already integrated by the smooth kernel
-    if (!(h.disableflags & DSBL_CONSTRAINT) && !done) {
+    const bool active = !(h.disableflags & DSBL_CONSTRAINT) && !done;
+    int ne0 = 0, ne = 0;
+    if (active && l == 0) {
       rows.equality();
       rows.friction_loss();
       rows.limits();
-      rows.contacts();
-      rows.finish();
+      ne0 = rows.nefc;
+      ne = rows.contact_offsets(ne0);
     }
-    const int ne = rows.nefc;
+    __syncwarp(tmask);
+    ne0 = __shfl_sync(tmask, ne0, 0, L);
+    ne = __shfl_sync(tmask, ne, 0, L);
+    if (active) {
+      rows.finish_range(l, ne0, L);
+      if (!(h.disableflags & DSBL_CONTACT)) {
+        const int ncon = a.ncon[env];
+        for (int c = l; c < ncon; c += L) rows.contact_one(c);
+      }
+    }
+    __syncwarp(tmask);
+    if (l != 0) continue;
     if (!done) a.nefc[env] = ne;
     int r = 0, woff = 0, nblk = 0;
+    // island labels: union-find over the kinematic trees (root = smallest tree id of the component), in a per-thread
+    // shared-memory column behind the row column
+    const int nt = a.isl_cap > 0 ? h.ntree : 0;
+    int* lab = reinterpret_cast<int*>(smem_raw + 16 + (size_t)nwords * 4 + (size_t)a.row_nb * h.wmax * BLOCK * sizeof(T)) + threadIdx.x;
+    auto LAB = [&](int t) -> int& { return lab[(size_t)t * BLOCK]; };
+    auto CNT = [&](int t) -> int& { return lab[(size_t)(nt + t) * BLOCK]; };
+    auto find = [&](int t) { if (t < 0) return 0; while (LAB(t) != t) t = LAB(t); return t; };
+    for (int t = 0; t < nt; t++) { LAB(t) = t; CNT(t) = 0; }
     while (r < ne) {
       BlockShape bs{};
       const long long o = (long long)r * S + env;
@@ -496,13 +528,43 @@ __global__ void __launch_bounds__(BLOCK) k_make_rows(const KArgs<T> a) {
         bs.nb = a.coni[((long long)CI_DIM * h.nconmax + id) * S + env];
         bs.nrow = 2 * (bs.nb - 1);
       }
-      const Seg g = seg_of(m, a.efc_tree[((long long)2 * r) * S + env], a.efc_tree[((long long)2 * r + 1) * S + env]);
+      const int t1 = a.efc_tree[((long long)2 * r) * S + env], t2 = a.efc_tree[((long long)2 * r + 1) * S + env];
+      const Seg g = seg_of(m, t1, t2);
       bs.s1 = g.s1; bs.n1 = g.n1; bs.s2 = g.s2; bs.w = g.n1 + g.n2;
       bs.layout();
       a.blk_row0[(long long)nblk * S + env] = r;
-      a.blk_off[(long long)nblk * S + env] = woff;
+      a.blk_off[(long long)nblk * S + env] = nt ? bs.len : woff;   // islands: the length for now, the offset below
+      if (nt && t2 >= 0) {
+        const int ra = find(t1), rb = find(t2);
+        if (ra != rb) LAB(ra > rb ? ra : rb) = ra < rb ? ra : rb;
+      }
       nblk++;
       woff += bs.len; r += bs.nrow;
+    }
+    if (nt) {
+      // words per island, islands numbered by ascending root; then every block's offset inside its island (row order kept)
+      for (int q = 0; q < nblk; q++) {
+        const int row = a.blk_row0[(long long)q * S + env];
+        CNT(find(a.efc_tree[((long long)2 * row) * S + env])) += a.blk_off[(long long)q * S + env];
+      }
+      int start = 0, ni = 0;
+      for (int t = 0; t < nt; t++) {
+        const int c = CNT(t);
+        if (c <= 0) continue;
+        if (ni < a.isl_cap) { a.isl_off[(long long)ni * S + env] = start; a.isl_end[(long long)ni * S + env] = start + c; }
+        else a.isl_end[(long long)(a.isl_cap - 1) * S + env] = start + c;   // more islands than slots: the last slot takes the rest (still one contiguous range)
+        CNT(t) = start;
+        start += c;
+        ni++;
+      }
+      for (int q = 0; q < nblk; q++) {
+        const int row = a.blk_row0[(long long)q * S + env];
+        const int root = find(a.efc_tree[((long long)2 * row) * S + env]);
+        const int len = a.blk_off[(long long)q * S + env];
+        a.blk_off[(long long)q * S + env] = CNT(root);
+        CNT(root) += len;
+      }
+      if (!done) a.nisl[env] = ni < a.isl_cap ? ni : a.isl_cap; else a.nisl[env] = 0;
     }
     if (!done) { a.efc_nwords[env] = woff; a.nblk[env] = nblk; wmaxblk = max(wmaxblk, nblk); }
     else a.nblk[env] = 0;
@@ -841,6 +903,10 @@ __device__ __forceinline__ void pgs_visit(const T* __restrict__ rec, const Block
     }
   }
   if (any) {
+    if constexpr (LANES == 1) {   // one lane per block (k_pgs_island): it stores every row itself
+#pragma unroll
+      for (int r = 0; r < NROWW; r++) if (r < nrow) f[row0 + r] = fo[r];
+    } else
     {  // lane r stores force r (and r + LANES): select chains, not predicated stores per row (those compile to a jump table)
       T mine = fo[0];
 #pragma unroll
@@ -864,6 +930,138 @@ __device__ __forceinline__ void pgs_visit(const T* __restrict__ rec, const Block
 #pragma unroll
       for (int k = 0; k < NBW; k++) if (k < nb) s0 = t_fma(d[k], rec[bs.oB + k * wq + e], s0);
       acc[bs.dof(e)] += s0;
+    }
+  }
+}
+
+// The visit of k_pgs_island: ONE lane relaxes one block, every lane of the warp a block of its own (different
+// environments / islands, possibly different shapes).  NBW is the warp-uniform bound of the base directions (1, 3 or 4).
+// Everything is fetched up front with 16-byte loads in fixed-trip, predicated loops (the header, the parameter words, the
+// <= 16 elements of the acceleration, J and B), so the loads are in flight together and the dependent chain is
+// "dot products -> rows -> one update".  The parameter words sit at offsets that depend on the block's own shape; they
+// are picked out of the loaded vectors by select chains over the shapes NBW admits (register indices stay static).
+// Same operation order as pgs_visit with LANES = 1.
+__host__ __device__ constexpr int lv_nrow(int nb) { return nb > 1 ? 2 * (nb - 1) : 1; }
+__host__ __device__ constexpr int lv_arr(int nb, int r) { return r < lv_nrow(nb) ? lv_nrow(nb) + r : 0; }
+__host__ __device__ constexpr int lv_ia(int nb, int r) { return r < lv_nrow(nb) ? 2 * lv_nrow(nb) + r : 0; }
+__host__ __device__ constexpr int lv_mu(int nb, int k) { return k < nb - 1 ? 4 * lv_nrow(nb) + k : 0; }
+__host__ __device__ constexpr int lv_cpl(int nb, int r, int c) {
+  return c < lv_nrow(nb) ? 4 * lv_nrow(nb) + nb - 1 + r * (2 * lv_nrow(nb) - r - 1) / 2 + (c - r - 1) : 0;
+}
+__host__ __device__ constexpr int lv_np(int nb) { return (4 * lv_nrow(nb) + (nb > 1 ? nb - 1 + lv_nrow(nb) * (lv_nrow(nb) - 1) / 2 : 0) + 3) & ~3; }
+template <typename T, int NBW>
+__device__ __forceinline__ void pgs_visit_lane(const T* __restrict__ rec, bool have, T* __restrict__ acc, T* __restrict__ f, T& improvement) {
+  static_assert(NBW == 1 || NBW == 3 || NBW == 4, "scalar rows and pyramidal contacts of condim 3 / 4");
+  constexpr int NROWW = lv_nrow(NBW), WCAP = 16, NPV = lv_np(NBW) / 4;
+  using V4 = VecN<T, 4>;
+  V4 h0, h1;
+  if (have) { h0 = *reinterpret_cast<const V4*>(rec); h1 = *reinterpret_cast<const V4*>(rec + 4); }
+  else {
+#pragma unroll
+    for (int c = 0; c < 4; c++) { h0.v[c] = enc_int(0, T()); h1.v[c] = enc_int(0, T()); }
+  }
+  const int code = dec_int(h0.v[0]), type = code & 15, nb = have ? (code >> 4) & 15 : 0, nrow = have ? code >> 8 : 0;
+  const int s1 = dec_int(h0.v[1]), n1w = dec_int(h0.v[2]), n1 = n1w & 1023, w = have ? n1w >> 10 : 0, s2 = dec_int(h0.v[3]);
+  const T R = h1.v[0], flv = h1.v[1];
+  const int row0 = dec_int(h1.v[3]);
+  const int wq = (w + 3) & ~3;
+  const int np = nb == 1 ? lv_np(1) : (nb == 3 ? lv_np(3) : lv_np(4));
+  const int oJ = BH_N + np, oB = oJ + nb * wq;
+  T P[NPV * 4];
+#pragma unroll
+  for (int q = 0; q < NPV; q++) {
+    V4 v;
+    if (have && 4 * q < np) v = *reinterpret_cast<const V4*>(rec + BH_N + 4 * q);
+    else { v.v[0] = 0; v.v[1] = 0; v.v[2] = 0; v.v[3] = 0; }
+#pragma unroll
+    for (int c = 0; c < 4; c++) P[4 * q + c] = v.v[c];
+  }
+  // pick a parameter whose offset depends on the shape: i1 / i3 / i4 are its offsets for nb = 1 / 3 / 4
+  auto pick = [&](int i1, int i3, int i4) -> T {
+    T v = P[i1 < NPV * 4 ? i1 : 0];
+    if (NBW >= 3) v = nb == 3 ? P[i3 < NPV * 4 ? i3 : 0] : v;
+    if (NBW >= 4) v = nb == 4 ? P[i4 < NPV * 4 ? i4 : 0] : v;
+    return v;
+  };
+  const T big = T(3.0e38);
+  const T lo = type == CN_EQUALITY ? -big : (type == CN_FRICTION_DOF ? -flv : T(0));
+  const T hi = type == CN_FRICTION_DOF ? flv : big;
+  T fo[NROWW];
+#pragma unroll
+  for (int r = 0; r < NROWW; r++) fo[r] = r < nrow ? f[row0 + r] : T(0);
+  // elements of the running acceleration this block touches
+  T x[WCAP];
+  int dofs[WCAP];
+#pragma unroll
+  for (int e = 0; e < WCAP; e++) {
+    dofs[e] = e < n1 ? s1 + e : s2 + e - n1;
+    x[e] = e < w ? acc[dofs[e]] : T(0);
+  }
+  T u[NBW];
+#pragma unroll
+  for (int k = 0; k < NBW; k++) {
+    u[k] = 0;
+#pragma unroll
+    for (int q = 0; q < WCAP / 4; q++) {
+      if (k < nb && 4 * q < w) {   // (the pad elements of a row are zero in the record)
+        const V4 j = *reinterpret_cast<const V4*>(rec + oJ + k * wq + 4 * q);
+#pragma unroll
+        for (int c = 0; c < 4; c++) u[k] = t_fma(j.v[c], x[4 * q + c], u[k]);
+      }
+    }
+  }
+  T Bv[NBW][WCAP];
+#pragma unroll
+  for (int k = 0; k < NBW; k++)
+#pragma unroll
+    for (int q = 0; q < WCAP / 4; q++) {
+      V4 b;
+      if (k < nb && 4 * q < w) b = *reinterpret_cast<const V4*>(rec + oB + k * wq + 4 * q);
+      else { b.v[0] = 0; b.v[1] = 0; b.v[2] = 0; b.v[3] = 0; }
+#pragma unroll
+      for (int c = 0; c < 4; c++) Bv[k][4 * q + c] = b.v[c];
+    }
+  T mu[NBW > 1 ? NBW - 1 : 1];
+#pragma unroll
+  for (int k = 0; k < NBW - 1; k++) mu[k] = k < nb - 1 ? pick(0, lv_mu(3, k), lv_mu(4, k)) : T(0);
+  T v[NROWW], dl[NROWW];
+  if (NBW == 1) v[0] = u[0];
+  else {
+#pragma unroll
+    for (int r = 0; r < NROWW; r++) v[r] = nb > 1 ? t_fma((r & 1) ? -mu[r / 2] : mu[r / 2], u[r / 2 + 1], u[0]) : u[0];
+  }
+  bool any = false;
+#pragma unroll
+  for (int r = 0; r < NROWW; r++) {
+    const T aref = P[r], Arr = pick(lv_arr(1, r), lv_arr(3, r), lv_arr(4, r)), iA = pick(lv_ia(1, r), lv_ia(3, r), lv_ia(4, r));
+    const T res = v[r] + t_fma(R, fo[r], -aref);
+    const T fn = t_min(hi, t_max(lo, t_fma(-res, iA, fo[r])));
+    T delta = fn - fo[r];
+    const T change = t_fma(t_mul(t_mul(T(0.5), delta), delta), Arr, t_mul(delta, res));
+    const bool ok = r < nrow && delta != 0 && !(change > T(1e-10));
+    delta = ok ? delta : T(0);
+    improvement -= ok ? change : T(0);
+    fo[r] = ok ? fn : fo[r];
+    any |= ok;
+    dl[r] = delta;
+#pragma unroll
+    for (int c = r + 1; c < NROWW; c++) v[c] = t_fma(delta, c < nrow ? pick(0, lv_cpl(3, r, c), lv_cpl(4, r, c)) : T(0), v[c]);
+  }
+  if (any) {
+#pragma unroll
+    for (int r = 0; r < NROWW; r++) if (r < nrow) f[row0 + r] = fo[r];
+    T d[NBW];
+    d[0] = dl[0];
+#pragma unroll
+    for (int r = 1; r < NROWW; r++) d[0] += dl[r];
+#pragma unroll
+    for (int k = 1; k < NBW; k++) d[k] = mu[k - 1] * (dl[2 * k - 2] - dl[2 * k - 1]);
+#pragma unroll
+    for (int e = 0; e < WCAP; e++) {
+      T s0 = 0;
+#pragma unroll
+      for (int k = 0; k < NBW; k++) s0 = t_fma(d[k], Bv[k][e], s0);
+      if (e < w) acc[dofs[e]] = x[e] + s0;
     }
   }
 }
@@ -1219,6 +1417,258 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_pgs_block(const KArgs<T> a) {
       }
       for (int i = l; i < nv; i += LANES) if (tmp[i] != 0) a.qfrc_inverse[(long long)i * S + env] -= tmp[i];
       __syncwarp(tmask);
+    }
+  }
+}
+
+// K6': the same solver for models made of many small kinematic trees (an arm and free objects, a field of object slots):
+// one LANE per constraint ISLAND.  Blocks that share no tree commute exactly — they read and write disjoint entries of
+// the acceleration and of the forces — so relaxing the islands of an environment side by side produces the iterates of
+// the row-ordered sweep bit for bit, while the serial chain of an iteration shrinks from "all blocks of the environment"
+// to "the blocks of its largest island" (C3: ~14 -> ~4).  A team of ISL lanes owns an environment (islands i = lane,
+// lane + ISL, ...); every lane runs the scalar visit (pgs_visit with LANES = 1: no shuffles, no redundant copies of the
+// row relaxation in eight lanes), the teams of a warp step through their blocks in lockstep so that one padded
+// instruction stream serves all 32 lanes.  The environment's records are staged in shared memory once (16-byte
+// coalesced copies) and read from there every iteration; only the iteration's convergence test is a team reduction.
+template <typename T, int ISL, int MINB>
+__global__ void __launch_bounds__(32, MINB) k_pgs_island(const KArgs<T> a) {
+  if ((a.flags & B2F_FUSABLE) && a.pending[0] == 0) return;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const DModel& h = *reinterpret_cast<const DModel*>(a.model);
+  MV<T> m{&h, a.model};
+  const long long S = a.nenvp;
+  constexpr int EPB = 32 / ISL;
+  const int nv = h.nv, njmax = h.njmax, capw = a.block_capw, cap = a.stage_cap;
+  const int nvs = nv + 4;
+  T* accsh = reinterpret_cast<T*>(smem_raw);
+  T* tmpsh = accsh + (size_t)EPB * nvs;
+  T* fsh = tmpsh + (size_t)EPB * nvs;
+  T* stsh = fsh + (size_t)EPB * ((njmax + 3) & ~3);
+  int* stosh = reinterpret_cast<int*>(stsh + (size_t)EPB * cap);   // [EPB][isl_cap] where island i was staged (-1: not staged)
+  const int team = threadIdx.x / ISL, l = threadIdx.x % ISL;
+  const unsigned tmask = (ISL == 32 ? 0xffffffffu : ((1u << ISL) - 1u)) << (threadIdx.x & ~(ISL - 1));
+  T* acc = accsh + (size_t)team * nvs;
+  T* tmp = tmpsh + (size_t)team * nvs;
+  T* f = fsh + (size_t)team * ((njmax + 3) & ~3);
+  T* st = stsh + (size_t)team * cap;
+  int* sto = stosh + (size_t)team * a.isl_cap;
+  const int ngroups = (a.nenvp + EPB - 1) / EPB;
+  const T tol = m.f(h.o_opt_real, 3), scale = 1 / (m.f(h.o_opt_real, 4) * T(nv > 1 ? nv : 1));
+  auto team_sum = [&](T v) {
+#pragma unroll
+    for (int o = ISL / 2; o > 0; o >>= 1) v += __shfl_xor_sync(tmask, v, o, ISL);
+    return v;
+  };
+  for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+    const long long env = a.env_order[(long long)grp * EPB + team];
+    const bool skip = (a.flags & B2F_FUSABLE) && (a.status[env] & 8);
+    const int ne = skip ? 0 : a.nefc[env], nw = ne > 0 ? a.efc_nwords[env] : 0, nisl = ne > 0 ? a.nisl[env] : 0;
+    const T* slab = a.efc_blocks + env * capw;
+    int iters = 0;
+    __syncwarp();   // the previous group's readers are done with the shared vectors
+    {
+      // stage the records island by island: island i starts on the bank group of the lane that will walk it (records
+      // are whole 128-byte lines, so the lanes of a quarter-warp keep reading disjoint banks while their blocks have
+      // the same shape)
+      constexpr int VW = 16 / (int)sizeof(T);
+      using V = VecN<T, VW>;
+      int pos = 0;
+      for (int i = 0; i < nisl; i++) {
+        const int o = a.isl_off[(long long)i * S + env], len = a.isl_end[(long long)i * S + env] - o;
+        const int start = ((pos + 31) & ~31) + 4 * ((team * ISL + (i % ISL)) & 7);
+        const bool fits = start + len <= cap;
+        if (fits) {
+          for (int q = l * VW; q < len; q += ISL * VW) *reinterpret_cast<V*>(st + start + q) = *reinterpret_cast<const V*>(slab + o + q);
+          pos = start + len;
+        }
+        if (l == 0) sto[i] = fits ? start : -1;
+      }
+    }
+    for (int i = l; i < nv; i += ISL) { acc[i] = a.qacc_warmstart[(long long)i * S + env]; tmp[i] = 0; }
+    __syncwarp();
+    // this lane's blocks: islands l, l + ISL, ... one after the other
+    struct Cursor { int isl, off, end; const T* base; };   // the record at slab offset off is base + off
+    auto cur_load = [&](Cursor& c) {
+      c.base = slab;
+      if (c.isl < nisl) {
+        c.off = a.isl_off[(long long)c.isl * S + env]; c.end = a.isl_end[(long long)c.isl * S + env];
+        const int so = sto[c.isl];
+        if (so >= 0) c.base = st + so - c.off;
+      } else { c.off = 0; c.end = 0; }
+    };
+    auto cur_init = [&](Cursor& c) { c.isl = l; cur_load(c); };
+    auto cur_next = [&](Cursor& c, int len) {
+      c.off += len;
+      if (c.off >= c.end) { c.isl += ISL; cur_load(c); }
+    };
+    auto base_dots = [&](const T* rec, const BlockShape& bs, const T* x, T* u) {
+#pragma unroll
+      for (int k = 0; k < 6; k++) u[k] = 0;
+      for (int e = 0; e < bs.w; e++) {
+        const T xv = x[bs.dof(e)];
+#pragma unroll
+        for (int k = 0; k < 6; k++) if (k < bs.nb) u[k] += rec[bs.oJ + k * bs.wq + e] * xv;
+      }
+    };
+    auto base_axpy = [&](const T* rec, const BlockShape& bs, int oX, const T* d, T* x) {
+      for (int e = 0; e < bs.w; e++) {
+        T s0 = 0;
+#pragma unroll
+        for (int k = 0; k < 6; k++) if (k < bs.nb) s0 += d[k] * rec[oX + k * bs.wq + e];
+        x[bs.dof(e)] += s0;
+      }
+    };
+    {
+      // ---- warm start: forces implied by qacc_warmstart (held in acc), kept only if their dual cost is negative ----
+      bool warm = ne > 0 && !(h.disableflags & DSBL_WARMSTART);
+      T cost = 0;
+      if (warm) {
+        Cursor c;
+        for (cur_init(c); c.off < c.end;) {
+          const T* rec = c.base + c.off;
+          const BlockShape bs = block_shape(rec);
+          T u[6], d[6] = {0, 0, 0, 0, 0, 0};
+          base_dots(rec, bs, acc, u);
+          const int row0 = dec_int(rec[BH_ROW0]);
+          const T R = rec[BH_R];
+          bool any = false;
+          for (int rr = 0; rr < bs.nrow; rr++) {
+            const int k = bs.nb > 1 ? rr / 2 + 1 : 0;
+            const T sm = bs.nb > 1 ? ((rr & 1) ? -rec[bs.oMu + k - 1] : rec[bs.oMu + k - 1]) : T(0);
+            const T fr = primal_force(bs.type, u[0] + sm * u[k] - rec[bs.oAref + rr], 1 / R, R, rec[BH_FL]);
+            f[row0 + rr] = fr;
+            if (fr != 0) { any = true; d[0] += fr; if (bs.nb > 1) d[k] += sm * fr; }
+          }
+          if (any) base_axpy(rec, bs, bs.oB, d, tmp);
+          cur_next(c, bs.len);
+        }
+        // (tmp is complete for this lane's islands: the cost of an island needs only its own entries)
+        for (cur_init(c); c.off < c.end;) {
+          const T* rec = c.base + c.off;
+          const BlockShape bs = block_shape(rec);
+          const int row0 = dec_int(rec[BH_ROW0]);
+          bool any = false;
+          for (int rr = 0; rr < bs.nrow; rr++) any |= f[row0 + rr] != 0;
+          if (any) {
+            T u[6];
+            base_dots(rec, bs, tmp, u);
+            for (int rr = 0; rr < bs.nrow; rr++) {
+              const T fr = f[row0 + rr];
+              if (fr == 0) continue;
+              const int k = bs.nb > 1 ? rr / 2 + 1 : 0;
+              const T sm = bs.nb > 1 ? ((rr & 1) ? -rec[bs.oMu + k - 1] : rec[bs.oMu + k - 1]) : T(0);
+              const T Af = u[0] + sm * u[k] + rec[BH_R] * fr;
+              cost += fr * (T(0.5) * Af + rec[bs.ob + rr]);
+            }
+          }
+          cur_next(c, bs.len);
+        }
+      }
+      __syncwarp(tmask);
+      cost = team_sum(cost);
+      if (cost > 0) warm = false;
+      if (ne > 0) {
+        if (warm) {
+          for (int i = l; i < nv; i += ISL) acc[i] = a.qacc_smooth[(long long)i * S + env] + tmp[i];
+        } else {
+          for (int i = l; i < nv; i += ISL) acc[i] = a.qacc_smooth[(long long)i * S + env];
+          for (int r = l; r < ne; r += ISL) f[r] = 0;
+        }
+      }
+    }
+    __syncwarp();
+    // ---- Gauss-Seidel sweeps: the lanes of the warp step through their own blocks in lockstep ----
+    {
+      bool done = ne <= 0;
+      for (int it = 0; it < h.iterations; it++) {
+        if (__all_sync(0xffffffffu, done)) break;
+        T improvement = 0;
+        Cursor c;
+        cur_init(c);
+        if (done) { c.off = 0; c.end = 0; }
+        while (true) {
+          const bool have = c.off < c.end;
+          if (!__any_sync(0xffffffffu, have)) break;
+          const T* rec = have ? c.base + c.off : slab;
+          const int code = have ? dec_int(rec[BH_CODE]) : 0, len = have ? dec_int(rec[BH_LEN]) : 0;
+          const int nbw = __reduce_max_sync(0xffffffffu, (code >> 4) & 15);
+          if (nbw <= 1) pgs_visit_lane<T, 1>(rec, have, acc, f, improvement);
+          else if (nbw <= 3) pgs_visit_lane<T, 3>(rec, have, acc, f, improvement);
+          else if (nbw <= 4) pgs_visit_lane<T, 4>(rec, have, acc, f, improvement);
+          else {
+            BlockShape bs{};
+            if (have) bs = block_shape(rec);
+            pgs_visit<T, 6, 1>(rec, bs, acc, f, 0, improvement);
+          }
+          if (have) cur_next(c, len);
+        }
+        __syncwarp();
+        improvement = team_sum(improvement);
+        if (!done) { iters = it + 1; if (improvement * scale < tol) done = true; }
+      }
+    }
+    __syncwarp();
+    if (ne > 0) {
+      // ---- qfrc_constraint = J^T f ----
+      for (int i = l; i < nv; i += ISL) tmp[i] = 0;
+      __syncwarp(tmask);
+      Cursor c;
+      for (cur_init(c); c.off < c.end;) {
+        const T* rec = c.base + c.off;
+        const BlockShape bs = block_shape(rec);
+        const int row0 = dec_int(rec[BH_ROW0]);
+        T d[6] = {0, 0, 0, 0, 0, 0};
+        bool any = false;
+        for (int rr = 0; rr < bs.nrow; rr++) {
+          const T fr = f[row0 + rr];
+          a.efc_force[(long long)(row0 + rr) * S + env] = fr;
+          if (fr == 0) continue;
+          const int k = bs.nb > 1 ? rr / 2 + 1 : 0;
+          any = true;
+          d[0] += fr;
+          if (bs.nb > 1) d[k] += ((rr & 1) ? -rec[bs.oMu + k - 1] : rec[bs.oMu + k - 1]) * fr;
+        }
+        if (any) base_axpy(rec, bs, bs.oJ, d, tmp);
+        cur_next(c, bs.len);
+      }
+    } else {
+      for (int i = l; i < nv; i += ISL) acc[i] = a.qacc_smooth[(long long)i * S + env];
+    }
+    __syncwarp();
+    if (!skip) {
+      for (int i = l; i < nv; i += ISL) {
+        const T v = acc[i];
+        a.qacc[(long long)i * S + env] = v;
+        a.qacc_warmstart[(long long)i * S + env] = v;
+        a.qfrc_constraint[(long long)i * S + env] = tmp[i];
+      }
+      if (l == 0) a.solver_iter[env] = iters;
+    }
+    __syncwarp();
+    // ---- mj_inverse: qfrc_inverse -= J^T f(qacc of the previous tick), forces per row from k_make_blocks ----
+    if ((a.flags & B2F_INVERSE) && ne > 0) {
+      for (int i = l; i < nv; i += ISL) tmp[i] = 0;
+      __syncwarp(tmask);
+      Cursor c;
+      for (cur_init(c); c.off < c.end;) {
+        const T* rec = c.base + c.off;
+        const BlockShape bs = block_shape(rec);
+        const int row0 = dec_int(rec[BH_ROW0]);
+        T d[6] = {0, 0, 0, 0, 0, 0};
+        bool any = false;
+        for (int rr = 0; rr < bs.nrow; rr++) {
+          const T fr = a.efc_finv[(long long)(row0 + rr) * S + env];
+          if (fr == 0) continue;
+          const int k = bs.nb > 1 ? rr / 2 + 1 : 0;
+          any = true;
+          d[0] += fr;
+          if (bs.nb > 1) d[k] += ((rr & 1) ? -rec[bs.oMu + k - 1] : rec[bs.oMu + k - 1]) * fr;
+        }
+        if (any) base_axpy(rec, bs, bs.oJ, d, tmp);
+        cur_next(c, bs.len);
+      }
+      __syncwarp(tmask);
+      for (int i = l; i < nv; i += ISL) if (tmp[i] != 0) a.qfrc_inverse[(long long)i * S + env] -= tmp[i];
     }
   }
 }

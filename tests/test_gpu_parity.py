@@ -749,14 +749,16 @@ def test_c4_pr2_like_pd_control_tick_matches_oracle(b2, orc):
         bt.set_controlled(ctl); bt.set_hw_joints(hw); bt.set_pd(kp, kd)
         vel = np.zeros((hw.size, nenv), np.float32); eff = np.ascontiguousarray(tgt.T.astype(np.float32))
         out = [np.zeros((hw.size, nenv), np.float32) for _ in range(3)]
-        for _ in range(steps):
+        for k in range(steps):
+            if k == steps - 1: q_before = bt.get("qpos")
             bt.tick_host_raw(vel.ctypes.data, eff.ctypes.data, *[o.ctypes.data for o in out])
         gq, gv = bt.get("qpos"), bt.get("qvel")
         assert bt.get("nefc").max() >= 8 + 6 and bt.get("ncon").max() >= 4   # equalities + wheel contacts were active
         # fp32 targets are rounded once on upload: compare against the same rounding in the tolerance
         np.testing.assert_allclose(gq, rq, atol=tol * 5 if prec == b2.engine.F64 else tol * 5, err_msg="qpos prec %d" % prec)
         np.testing.assert_allclose(gv, rv, atol=tol * 200, err_msg="qvel prec %d" % prec)
-        np.testing.assert_allclose(out[0].T, gq[:, np.array(m.jnt_qposadr)[hw]], atol=1e-6)
+        # read() gathers the joint state between mj_step1 and mj_step2 (mj_main.cpp:91-108): positions of the tick's start
+        np.testing.assert_allclose(out[0].T, q_before[:, np.array(m.jnt_qposadr)[hw]], atol=1e-6)
         scale = max(1.0, np.abs(finv[:, dadr]).max())
         np.testing.assert_allclose(out[2].T, finv[:, dadr], atol=(1e-5 if prec == b2.engine.F64 else 2e-2) * scale)
         bt.close()
