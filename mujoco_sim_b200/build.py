@@ -52,6 +52,8 @@ def build_lib(force=False, verbose_ptxas=False):
             cmd = [NVCC, "-c", "-Xcompiler", "-fPIC", "-O3", "-std=c++17", "-lineinfo",
                    "-gencode", "arch=compute_100a,code=sm_100a",
                    "-I" + os.path.join(ROOT, "include"), "-I" + CSRC, "-o", obj, src]
+            if os.environ.get("B2_EXTRA_NVCC") and s.endswith(".cu"):
+                cmd[1:1] = os.environ["B2_EXTRA_NVCC"].split()
             if verbose_ptxas and s.endswith(".cu"):
                 cmd.insert(1, "-Xptxas=-v")
             jobs.append(cmd)

@@ -949,10 +949,11 @@ __host__ __device__ constexpr int lv_cpl(int nb, int r, int c) {
   return c < lv_nrow(nb) ? 4 * lv_nrow(nb) + nb - 1 + r * (2 * lv_nrow(nb) - r - 1) / 2 + (c - r - 1) : 0;
 }
 __host__ __device__ constexpr int lv_np(int nb) { return (4 * lv_nrow(nb) + (nb > 1 ? nb - 1 + lv_nrow(nb) * (lv_nrow(nb) - 1) / 2 : 0) + 3) & ~3; }
-template <typename T, int NBW>
-__device__ __forceinline__ void pgs_visit_lane(const T* __restrict__ rec, bool have, T* __restrict__ acc, T* __restrict__ f, T& improvement) {
+template <typename T, int NBW, int WCAP>
+__device__ __noinline__ void pgs_visit_lane(const T* __restrict__ rec, bool have, T* __restrict__ acc, T* __restrict__ f, T& improvement) {
   static_assert(NBW == 1 || NBW == 3 || NBW == 4, "scalar rows and pyramidal contacts of condim 3 / 4");
-  constexpr int NROWW = lv_nrow(NBW), WCAP = 16, NPV = lv_np(NBW) / 4;
+  static_assert(WCAP % 4 == 0 && WCAP <= 16, "compact rows of at most 16 elements");
+  constexpr int NROWW = lv_nrow(NBW), NPV = lv_np(NBW) / 4;
   using V4 = VecN<T, 4>;
   V4 h0, h1;
   if (have) { h0 = *reinterpret_cast<const V4*>(rec); h1 = *reinterpret_cast<const V4*>(rec + 4); }
@@ -1591,11 +1592,24 @@ __global__ void __launch_bounds__(32, MINB) k_pgs_island(const KArgs<T> a) {
           if (!__any_sync(0xffffffffu, have)) break;
           const T* rec = have ? c.base + c.off : slab;
           const int code = have ? dec_int(rec[BH_CODE]) : 0, len = have ? dec_int(rec[BH_LEN]) : 0;
+          // one instruction stream for the warp, sized by the largest block of this step (base directions, row width)
           const int nbw = __reduce_max_sync(0xffffffffu, (code >> 4) & 15);
-          if (nbw <= 1) pgs_visit_lane<T, 1>(rec, have, acc, f, improvement);
-          else if (nbw <= 3) pgs_visit_lane<T, 3>(rec, have, acc, f, improvement);
-          else if (nbw <= 4) pgs_visit_lane<T, 4>(rec, have, acc, f, improvement);
-          else {
+          const int ww = __reduce_max_sync(0xffffffffu, have ? dec_int(rec[BH_N1W]) >> 10 : 0);
+          if (nbw <= 4) {
+            if (ww <= 8) {
+              if (nbw <= 1) pgs_visit_lane<T, 1, 8>(rec, have, acc, f, improvement);
+              else if (nbw <= 3) pgs_visit_lane<T, 3, 8>(rec, have, acc, f, improvement);
+              else pgs_visit_lane<T, 4, 8>(rec, have, acc, f, improvement);
+            } else if (ww <= 12) {
+              if (nbw <= 1) pgs_visit_lane<T, 1, 12>(rec, have, acc, f, improvement);
+              else if (nbw <= 3) pgs_visit_lane<T, 3, 12>(rec, have, acc, f, improvement);
+              else pgs_visit_lane<T, 4, 12>(rec, have, acc, f, improvement);
+            } else {
+              if (nbw <= 1) pgs_visit_lane<T, 1, 16>(rec, have, acc, f, improvement);
+              else if (nbw <= 3) pgs_visit_lane<T, 3, 16>(rec, have, acc, f, improvement);
+              else pgs_visit_lane<T, 4, 16>(rec, have, acc, f, improvement);
+            }
+          } else {
             BlockShape bs{};
             if (have) bs = block_shape(rec);
             pgs_visit<T, 6, 1>(rec, bs, acc, f, 0, improvement);
@@ -1605,6 +1619,9 @@ __global__ void __launch_bounds__(32, MINB) k_pgs_island(const KArgs<T> a) {
         __syncwarp();
         improvement = team_sum(improvement);
         if (!done) { iters = it + 1; if (improvement * scale < tol) done = true; }
+#ifdef B2_DEBUG_PGS
+        if (l == 0 && ne > 0 && (it & 7) == 7 && it / 8 < 12) a.efc_vel[(long long)(it / 8) * S + env] = improvement * scale;
+#endif
       }
     }
     __syncwarp();
