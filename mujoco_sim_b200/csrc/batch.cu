@@ -19,6 +19,7 @@
 #include "batch_internal.h"
 #include "k_args.h"
 #include "k_collide.cuh"
+#include "k_project_tc.cuh"
 #include "k_common.cuh"
 #include "k_constraint.cuh"
 #include "k_smooth.cuh"
@@ -247,6 +248,7 @@ KArgs<T> build_args(b2_batch* b) {
   a.blk_row0 = I("blk_row0"); a.blk_off = I("blk_off"); a.nblk = I("nblk"); a.maxblk = I("_maxblk"); a.solver_iter = I("solver_iter"); a.status = I("status");
   a.pending = I("_pending");
   a.isl_off = I("isl_off"); a.isl_end = I("isl_end"); a.nisl = I("nisl");
+  a.efc_Jem = R("efc_Jem"); a.efc_Bem = R("efc_Bem"); a.minv_em = R("minv_em");
   return a;
 }
 // the field pointers are looked up by name once per (re)allocation, not once per tick
@@ -261,7 +263,7 @@ KArgs<T> make_args(b2_batch* b, int flags) {
   if constexpr (sizeof(T) == 4) a = b->args_f; else a = b->args_d;
   a.model = b->blob_dev; a.model_words = b->hdr.nwords;
   a.flags = flags; a.ws_block = b->smooth_block; a.h = (T)b->h; a.wp = b->wp;
-  a.block_capw = b->block_capw; a.block_npar = b->block_npar; a.stage_cap = b->isl_cap ? b->isl_stage : b->stage_cap; a.row_nb = b->row_nb; a.isl_cap = b->isl_cap;
+  a.block_capw = b->block_capw; a.block_npar = b->block_npar; a.stage_cap = b->isl_cap ? b->isl_stage : b->stage_cap; a.row_nb = b->row_nb; a.isl_cap = b->isl_cap; a.em_rows = b->tc_rows;
   a.hw_vel = b->io_in[0]; a.hw_eff = b->io_in[1];
   a.hw_pos = b->io_out[0]; a.hw_velo = b->io_out[1]; a.hw_effo = b->io_out[2];
   a.hw_kp = b->hw_kp; a.hw_kd = b->hw_kd;
@@ -344,6 +346,11 @@ int configure_constraint_kernels(b2_batch* b) {
       SA((const void*)k_pgs_block<float, 16, 32, PGS_MINB>); SA((const void*)k_pgs_block<float, 32, 32, PGS_MINB>);
       SA((const void*)k_solve_rows<float, 16>); SA((const void*)k_solve_rows<float, 8>); SA((const void*)k_solve_rows<float, 4>);
       SA((const void*)k_pgs_island<float, 4, PGS_ISL_MINB>); SA((const void*)k_pgs_island<float, 8, PGS_ISL_MINB>); SA((const void*)k_pgs_island<float, 16, PGS_ISL_MINB>);
+    }
+    if (b->prec == 4) {
+      SA((const void*)k_dense_minv<float, 8>);
+      // (this kernel also has static shared memory: ask for what it uses, not for the whole SM)
+      ok &= cudaFuncSetAttribute((const void*)k_project_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * tc::A_BYTES + 2 * tc::B_BYTES)) == cudaSuccess;
     }
     attr_done[pi][di] = ok;
     }
@@ -457,7 +464,18 @@ int run_tick(b2_batch* b, int flags) {
       const int gr = std::max(1, std::min(b->nenvp / (BL / RL), b->nsm * std::max(1, std::min(8, (int)(220 * 1024 / (sm + b->row_smem + b->isl_smem + 1024))))));
       k_make_rows<T, BL, RL><<<gr, BL, sm + b->row_smem + b->isl_smem, b->stream>>>(a);
     }
-    if (b->solve_rows > 0) {
+    if (b->tc_rows > 0) {
+      // one-tree model, fp32: dense M^-1 per environment, then B = J M^-1 on the tensor cores (k_project_tc.cuh)
+      if constexpr (sizeof(T) == 4) {
+        constexpr int MR = 8;
+        const size_t smm = 16 + (((size_t)b->hdr.nwords * 4 + 15) & ~(size_t)15) + ((size_t)2 * b->hdr.nM + b->hdr.nv + (size_t)MR * b->hdr.nv) * 32 * sizeof(T);
+        const int gm = std::max(1, std::min(b->nenvp / 32, b->nsm * std::max(1, (int)(227 * 1024 / (smm + 1024)))));
+        k_dense_minv<T, MR><<<gm, 32 * MR, smm, b->stream>>>(a);
+        const size_t smt = 2 * tc::A_BYTES + 2 * tc::B_BYTES;
+        k_project_tc<<<std::min(b->nenvp, 2 * b->nsm), 128, smt, b->stream>>>(a.efc_Jem, a.minv_em, a.efc_Bem, a.nefc, b->nenvp, b->tc_rows / tc::TM, b->tc_rows, b->tc_passes);
+        b->launches += 2;
+      }
+    } else if (b->solve_rows > 0) {
       // wide trees: M^-1 J^T of all rows up front, the tile's factor shared through shared memory (k_solve_rows)
       const int gs = std::max(1, std::min(b->nenvp / 32, b->nsm * std::max(1, (int)(227 * 1024 / (b->solve_smem + 1024)))));
       if (b->solve_rows == 16) k_solve_rows<T, 16><<<gs, 512, b->solve_smem, b->stream>>>(a);
@@ -927,6 +945,14 @@ b2_batch* b2_create(const mjModel* m, int nenv, int device, int precision) {
         {"efc_frictionloss", njmax, 0}, {"efc_diagApprox", njmax, 0}, {"efc_R", njmax, 0}, {"efc_D", njmax, 0}, {"efc_KBI", 3 * njmax, 0},
         {"efc_vel", njmax, 0}, {"efc_aref", njmax, 0}, {"efc_b", njmax, 0}, {"efc_force", njmax, 0}, {"efc_finv", njmax, 0}, {"efc_ARdiag", njmax, 0},
         {"efc_blocks", b->block_capw, 0}, {"efc_nwords", 1, 1}, {"env_order", 1, 1}, {"blk_row0", njmax, 1}, {"blk_off", njmax, 1}, {"nblk", 1, 1}, {"_maxblk", 1, 1}};
+    // tensor-core projection: one tree whose compact row is every dof, fp32, nv <= 56 (the GEMM's padded K), opt-in
+    b->tc_rows = 0;
+    if (getenv("B2_TC_PROJECT") && atoi(getenv("B2_TC_PROJECT")) > 0 && precision == 4 && b->hdr.ntree == 1 && b->hdr.wmax == nv && nv <= tc::TK &&
+        (size_t)b->rec_max * 129 * b->prec > 56 * 1024) {
+      b->tc_rows = (int)((njmax + tc::TM - 1) / tc::TM) * tc::TM;
+      b->tc_passes = atoi(getenv("B2_TC_PROJECT")) == 1 ? 3 : 1;   // B2_TC_PROJECT=1: 3xTF32, =2: single-pass TF32 (accuracy experiment)
+      more.push_back({"efc_Jem", (long long)b->tc_rows * 64, 0}); more.push_back({"efc_Bem", (long long)b->tc_rows * 64, 0}); more.push_back({"minv_em", 64 * 64, 0});
+    }
     if (b->isl_cap) { more.push_back({"isl_off", b->isl_cap, 1}); more.push_back({"isl_end", b->isl_cap, 1}); more.push_back({"nisl", 1, 1}); }
     // wide trees (the criterion of make_block == 32): M^-1 J^T of every row is produced by k_solve_rows into efc_B
     if ((size_t)b->rec_max * 129 * b->prec > 56 * 1024 && !getenv("B2_NO_SOLVE_ROWS")) more.push_back({"efc_B", njmax * b->hdr.wmax, 0});

@@ -48,6 +48,8 @@ struct b2_batch {
   int block_npar = 0;    // ... of which header + parameters
   int make_block = 128;  // CTA size of k_make_constraint
   int pgs_lanes = 8;     // lanes per environment in k_pgs_block
+  int tc_rows = 0;       // tensor-core projection (k_project_tc): rows per environment of the environment-major arrays; 0: off
+  int tc_passes = 3;     // 3: 3xTF32 (fp32-level accuracy), 1: plain TF32
   int isl_cap = 0;       // island slots per environment (k_pgs_island: models made of several small trees); 0: k_pgs_block
   int pgs_isl = 8;       // lanes (= islands relaxed side by side) per environment in k_pgs_island
   int isl_stage = 0;     // words of records k_pgs_island stages per environment

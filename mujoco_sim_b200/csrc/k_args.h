@@ -63,6 +63,11 @@ struct KArgs {
       *efc_b, *efc_force, *efc_finv; // [njmax][nenvp] (KBI: [3][njmax][nenvp]); efc_finv: primal force of mj_inverse per row
   T* efc_ARdiag;          // [njmax][nenvp] diagonal of J M^-1 J^T + R
   T* efc_B;               // [njmax][wmax][nenvp] M^-1 J^T of every row, layout of efc_J; only for wide trees (k_solve_rows), else null
+  // tensor-core projection (k_project_tc.cuh; one-tree models, fp32): environment-major copies, rows of 64 floats
+  T* efc_Jem;             // [nenvp][em_rows][64] J of every row (written next to efc_J by k_make_rows)
+  T* efc_Bem;             // [nenvp][em_rows][64] B = J M^-1 from the tcgen05 kernel (read by k_make_blocks instead of efc_B)
+  T* minv_em;             // [nenvp][64][64] dense M^-1 (k_dense_minv)
+  int em_rows;            // rows per environment in the two arrays above (a multiple of 128 >= njmax); 0: path off
   T* efc_blocks;          // [nenvp][block_capw] environment-major block records streamed by the solver (k_constraint.cuh)
   int* efc_nwords;        // [nenvp] words of efc_blocks in use
   int* env_order;         // [nenvp] visit order of the solver (k_order_envs)

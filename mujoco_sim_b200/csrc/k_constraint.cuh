@@ -65,7 +65,17 @@ struct Rows {
   T* rowsh = nullptr;   // shared-memory column of this thread for the base rows of the contact being assembled (or null)
   int rowld = 0;        // its stride (the CTA width)
   __device__ Rows(const MV<T>& mv, const KArgs<T>& args, int e) : m(mv), h(*mv.h), a(args), env(e), S(args.nenvp) {}
-  __device__ __forceinline__ T& Jc(int r, int k) const { return a.efc_J[((long long)r * h.wmax + k) * S + env]; }
+  // element (r, k) of the compact Jacobian; with the tensor-core projection on, every write also goes to the
+  // environment-major copy the GEMM reads
+  struct JRef {
+    T* p; T* q;
+    __device__ __forceinline__ void operator=(T v) const { *p = v; if (q) *q = v; }
+    __device__ __forceinline__ void operator+=(T v) const { const T nv = *p + v; *p = nv; if (q) *q = nv; }
+  };
+  __device__ __forceinline__ JRef Jc(int r, int k) const {
+    return JRef{a.efc_J + ((long long)r * h.wmax + k) * S + env,
+                a.em_rows ? a.efc_Jem + ((long long)env * a.em_rows + r) * 64 + k : nullptr};
+  }
   __device__ __forceinline__ T cdof(int i, int k) const { return a.cdof[(6 * i + k) * S + env]; }
 
   // start a new zero row over trees (t1, t2); returns its index or -1 when njmax is exhausted
@@ -709,7 +719,10 @@ __global__ void __launch_bounds__(BLOCK) k_make_blocks(const KArgs<T> a) {
         for (int e = w; e < wq; e++) { Jc[e] = 0; Bc[e] = 0; }
         // B_c = M^-1 J_c^T: precomputed by k_solve_rows for wide trees, else solved here one tree at a time (M is block
         // diagonal over trees)
-        if (a.efc_B) {
+        if (a.em_rows) {
+          const T* brow = a.efc_Bem + ((long long)env * a.em_rows + (r + c)) * 64;
+          for (int e = 0; e < w; e++) Bc[e] = brow[e];
+        } else if (a.efc_B) {
           for (int e = 0; e < w; e++) Bc[e] = a.efc_B[((long long)(r + c) * W + e) * S + env];
         } else
         for (int sgm = 0; sgm < 2; sgm++) {

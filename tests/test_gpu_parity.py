@@ -850,3 +850,41 @@ def test_c5_spawn_destroy_slots_match_oracle(b2, orc):
             if not live[e, s]:
                 assert np.array_equal(gq[e, qadr[s]:qadr[s] + 7], w.park_pose(s)) and not gv[e, dadr[s]:dadr[s] + 6].any()
     bt.close()
+
+
+def test_tensor_core_projection_matches_ffma(b2):
+    """B = J M^-1 of a one-tree model (PR2-shaped, 49 dofs) on the 5th-generation tensor cores
+    (k_project_tc: tcgen05.mma kind::tf32 with the 3xTF32 split, accumulator in TMEM) against the FFMA path
+    (k_solve_rows).  Same contacts and rows, forces and accelerations to fp32 rounding; a single TF32 pass (10-bit
+    mantissa) is measurably worse, which is why the split is needed."""
+    import os
+    from mujoco_sim_b200 import workloads as w
+    m = b2.Model(b2.asset("pr2_like.xml"))
+    nenv = 64
+    q0, v0, _ = w.config_state("c4", m, np.arange(nenv))
+    q0[:, 2] = m.qpos0[2] + 0.01 * np.arange(nenv) / nenv
+    out = {}
+    for tag, val in (("ffma", None), ("tf32x3", "1"), ("tf32x1", "2")):
+        if val is None:
+            os.environ.pop("B2_TC_PROJECT", None)
+        else:
+            os.environ["B2_TC_PROJECT"] = val
+        try:
+            bt = b2.Batch(m, nenv)
+        finally:
+            os.environ.pop("B2_TC_PROJECT", None)
+        bt.set("qpos", q0); bt.set("qvel", v0)
+        bt.step(30)
+        out[tag] = (bt.get("nefc").copy(), bt.get("qacc"), bt.get("efc_force"), bt.get("qpos"))
+        bt.close()
+    ref = out["ffma"]
+    assert ref[0].max() >= 14
+    got = out["tf32x3"]
+    assert np.array_equal(ref[0], got[0])
+    for k in (1, 2, 3):
+        scale = max(1.0, float(np.abs(ref[k]).max()))
+        assert np.abs(ref[k] - got[k]).max() <= 2e-4 * scale, (k, np.abs(ref[k] - got[k]).max(), scale)
+    # one TF32 pass: an order of magnitude (or more) further from the FFMA result than the split
+    e3 = np.abs(ref[1] - got[1]).max()
+    e1 = np.abs(ref[1] - out["tf32x1"][1]).max()
+    assert e1 > 5 * e3, (e1, e3)
