@@ -230,6 +230,8 @@ extern mjfGeneric mjcb_control;
 
 /* ---- model / data lifecycle ---- */
 mjModel* mj_loadXML(const char* filename, const mjVFS* vfs, char* error, int error_sz);
+void mj_saveModel(const mjModel* m, const char* filename, void* buffer, int buffer_sz);  /* binary model image (.mjb) */
+mjModel* mj_loadModel(const char* filename, const mjVFS* vfs);
 mjModel* mj_loadXMLString(const char* xml, const char* basedir, char* error, int error_sz); /* extension */
 int mj_saveLastXML(const char* filename, const mjModel* m, char* error, int error_sz);
 mjData* mj_makeData(const mjModel* m);

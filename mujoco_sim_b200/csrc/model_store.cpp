@@ -1,7 +1,11 @@
 // model_store.cpp — storage, mjData allocation and string-keyed field access.
 #include "model_store.h"
 
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <stdexcept>
 
 namespace b2 {
 
@@ -35,6 +39,64 @@ void ModelStore::finalize() {
   }
   v.jnt_qposadr = jnt_qposadr_padded.data() + 1;
   v.jnt_dofadr = jnt_dofadr_padded.data() + 1;
+}
+
+// ---- binary model image ------------------------------------------------------------------------------------------
+// [magic "B2MJB001"][sizeof(mjModel)][mjModel bytes (pointers are rebuilt by finalize)] then, in one fixed order, every
+// vector as [element size][count][bytes], then the source text and directory.
+#define B2_MODEL_VECTORS(X)                                                                                            \
+  X(qpos0) X(qpos_spring) X(body_parentid) X(body_rootid) X(body_weldid) X(body_mocapid) X(body_jntnum) X(body_jntadr) \
+  X(body_dofnum) X(body_dofadr) X(body_geomnum) X(body_geomadr) X(body_pos) X(body_quat) X(body_ipos) X(body_iquat)    \
+  X(body_mass) X(body_subtreemass) X(body_inertia) X(body_invweight0) X(body_gravcomp) X(jnt_type) X(jnt_qposadr)      \
+  X(jnt_dofadr) X(jnt_bodyid) X(jnt_limited) X(jnt_solref) X(jnt_solimp) X(jnt_pos) X(jnt_axis) X(jnt_stiffness)       \
+  X(jnt_range) X(jnt_margin) X(dof_bodyid) X(dof_jntid) X(dof_parentid) X(dof_Madr) X(dof_solref) X(dof_solimp)        \
+  X(dof_frictionloss) X(dof_armature) X(dof_damping) X(dof_invweight0) X(geom_type) X(geom_contype)                    \
+  X(geom_conaffinity) X(geom_condim) X(geom_bodyid) X(geom_dataid) X(geom_priority) X(geom_size) X(geom_rbound)        \
+  X(geom_pos) X(geom_quat) X(geom_friction) X(geom_solmix) X(geom_solref) X(geom_solimp) X(geom_margin) X(geom_gap)    \
+  X(geom_rgba) X(mesh_vertadr) X(mesh_vertnum) X(mesh_vert) X(eq_type) X(eq_obj1id) X(eq_obj2id) X(eq_active)          \
+  X(eq_solref) X(eq_solimp) X(eq_data) X(pair_geom1) X(pair_geom2) X(sensor_type) X(sensor_objid) X(sensor_adr)        \
+  X(name_bodyadr) X(name_jntadr) X(name_geomadr) X(name_meshadr) X(names) X(exclude_signature)
+
+static const char kMagic[8] = {'B', '2', 'M', 'J', 'B', '0', '0', '1'};
+
+void ModelStore::save(const std::string& path) const {
+  FILE* f = std::fopen(path.c_str(), "wb");
+  if (!f) throw std::runtime_error("cannot write '" + path + "'");
+  auto W = [&](const void* p, size_t n) { if (n && std::fwrite(p, 1, n, f) != n) { std::fclose(f); throw std::runtime_error("short write to '" + path + "'"); } };
+  W(kMagic, 8);
+  const uint64_t vs = sizeof(mjModel);
+  W(&vs, 8);
+  W(&view, sizeof(mjModel));
+#define X(v) { const uint64_t es = sizeof(v[0]), n = v.size(); W(&es, 8); W(&n, 8); W(v.data(), (size_t)(es * n)); }
+  B2_MODEL_VECTORS(X)
+#undef X
+  // the MJCF source text travels only on request (B2_MJB_WITH_SOURCE=1): an image is a compiled artefact
+  const std::string none;
+  const bool with_src = std::getenv("B2_MJB_WITH_SOURCE") != nullptr;
+  for (const std::string* t : {with_src ? &source_xml : &none, with_src ? &source_dir : &none}) { const uint64_t n = t->size(); W(&n, 8); W(t->data(), (size_t)n); }
+  std::fclose(f);
+}
+
+ModelStore* ModelStore::load(const std::string& path) {
+  FILE* f = std::fopen(path.c_str(), "rb");
+  if (!f) throw std::runtime_error("cannot open '" + path + "'");
+  auto* s = new ModelStore();
+  auto bad = [&](const char* why) { std::fclose(f); delete s; throw std::runtime_error("'" + path + "': " + why); };
+  auto R = [&](void* p, size_t n) { if (n && std::fread(p, 1, n, f) != n) bad("truncated model image"); };
+  char magic[8];
+  uint64_t vs = 0;
+  R(magic, 8);
+  if (std::memcmp(magic, kMagic, 8)) bad("not a model image of this library (magic)");
+  R(&vs, 8);
+  if (vs != sizeof(mjModel)) bad("model image of a different library version (mjModel size)");
+  R(&s->view, sizeof(mjModel));
+#define X(v) { uint64_t es = 0, n = 0; R(&es, 8); R(&n, 8); if (es != sizeof(s->v[0]) || n > (1ull << 32)) bad("corrupt array header"); s->v.resize((size_t)n); R(s->v.data(), (size_t)(es * n)); }
+  B2_MODEL_VECTORS(X)
+#undef X
+  for (std::string* t : {&s->source_xml, &s->source_dir}) { uint64_t n = 0; R(&n, 8); if (n > (1ull << 32)) bad("corrupt text header"); t->resize((size_t)n); R(&(*t)[0], (size_t)n); }
+  std::fclose(f);
+  s->finalize();
+  return s;
 }
 
 namespace {

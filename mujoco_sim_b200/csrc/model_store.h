@@ -41,6 +41,9 @@ struct ModelStore {
   // jnt_qposadr / jnt_dofadr arrays because the reference indexes them with -1 when an odom joint
   // is absent (src/mujoco_sim/mj_sim.cpp:1083-1091).
   void finalize();
+  // binary image of a compiled model (mj_saveModel / mj_loadModel): header + every array above + the source text
+  void save(const std::string& path) const;
+  static ModelStore* load(const std::string& path);
   std::vector<int> jnt_qposadr_padded, jnt_dofadr_padded;
 };
 

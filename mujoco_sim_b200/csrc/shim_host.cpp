@@ -48,6 +48,24 @@ mjModel* mj_loadXML(const char* filename, const mjVFS*, char* error, int error_s
   }
 }
 
+// MuJoCo's binary model I/O (mj_saveModel / mj_loadModel): a compiled model travels without its MJCF and mesh files
+// (the C4 workload ships as such an image of the reference's pr2.xml, its meshes reduced to their hull vertices).
+void mj_saveModel(const mjModel* m, const char* filename, void* buffer, int buffer_sz) {
+  (void)buffer; (void)buffer_sz;
+  if (!m || !m->owner_ || !filename) return;
+  try { static_cast<const b2::ModelStore*>(m->owner_)->save(filename); }
+  catch (const std::exception& e) { mju_warning(e.what()); }
+}
+mjModel* mj_loadModel(const char* filename, const mjVFS*) {
+  try {
+    b2::ModelStore* s = b2::ModelStore::load(filename ? filename : "");
+    return &s->view;
+  } catch (const std::exception& e) {
+    mju_warning(e.what());
+    return nullptr;
+  }
+}
+
 mjModel* mj_loadXMLString(const char* xml, const char* basedir, char* error, int error_sz) {
   if (error && error_sz > 0) error[0] = 0;
   try {

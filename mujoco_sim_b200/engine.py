@@ -36,6 +36,8 @@ _sig = {
     "mj_loadXML": (_vp, [_cp, _vp, _cp, _i]),
     "mj_loadXMLString": (_vp, [_cp, _cp, _cp, _i]),
     "mj_saveLastXML": (_i, [_cp, _vp, _cp, _i]),
+    "mj_saveModel": (None, [_vp, _cp, _vp, _i]),
+    "mj_loadModel": (_vp, [_cp, _vp]),
     "mj_makeData": (_vp, [_vp]),
     "mj_deleteData": (None, [_vp]),
     "mj_deleteModel": (None, [_vp]),
@@ -122,7 +124,11 @@ class Model:
 
     def __init__(self, path=None, xml=None, basedir="."):
         err = C.create_string_buffer(1000)
-        if path is not None:
+        if path is not None and path.endswith(".mjb"):     # binary image of a compiled model (mj_loadModel)
+            self.ptr = lib.mj_loadModel(path.encode(), None)
+            if not self.ptr:
+                raise B2Error("mj_loadModel: cannot load " + path)
+        elif path is not None:
             self.ptr = lib.mj_loadXML(path.encode(), None, err, 1000)
         else:
             self.ptr = lib.mj_loadXMLString(xml.encode(), basedir.encode(), err, 1000)
@@ -133,6 +139,12 @@ class Model:
         if getattr(self, "ptr", None):
             lib.mj_deleteModel(self.ptr)
             self.ptr = None
+
+    def save(self, path):
+        """mj_saveModel: binary image of the compiled model."""
+        lib.mj_saveModel(self.ptr, path.encode(), None, 0)
+        if not os.path.exists(path):
+            raise B2Error("mj_saveModel: cannot write " + path)
 
     def int(self, name):
         v = _i(0)

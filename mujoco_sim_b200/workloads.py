@@ -11,7 +11,7 @@ CONFIGS = {
     "c1": ("pendulum_world.xml", 1, "pendulum world, 1 env (plumbing)"),
     "c2": ("panda7.urdf", 4096, "Franka-Panda-like 7-DoF arm (URDF import), contact-free forward dynamics"),
     "c3": ("ur5_tabletop.xml", 16384, "UR5-like arm + tabletop objects with contacts, PGS"),
-    "c4": ("pr2_like.xml", 8192, "PR2-shaped dual-arm robot (49 dofs, mimic-joint equalities, limits, wheel contacts) + PD computed-torque control"),
+    "c4": ("pr2_real.mjb", 8192, "PR2 of the reference (model/test/pr2/pr2.xml: 49 dofs, 45 bodies, 37 mesh geoms as convex hulls, 6 mimic equalities, 105 excludes -> 1284 candidate pairs) on the floor of world/empty.xml + PD computed-torque control of the 14 arm joints"),
     "c5": ("multi_world.xml", 8192, "multi-robot world: 3 pendulum bobs + 20 object slots, run-time spawn / destroy as slot activation"),
 }
 

@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 
-CASES = [("c2", 8, 50), ("c3", 6, 60), ("c4", 3, 40)]
+CASES = [("c2", 256, 50), ("c3", 256, 60), ("c4", 256, 40)]
 
 
 def rollout(cfg, nenv, ticks):
@@ -34,7 +34,7 @@ def rollout(cfg, nenv, ticks):
         pd = {"pd_kp": kpv, "pd_kd": kdv}
     q, v = np.ascontiguousarray(q0).copy(), np.ascontiguousarray(v0).copy()
     ws = np.zeros((nenv, m.nv)); finv = np.zeros((nenv, m.nv))
-    orc.tick_batch(m, [b2.Data(m)], ticks, q, v, ws, None, ddq, np.zeros((nenv, m.nv)), ctl, True, finv, **pd)
+    orc.tick_batch(m, [b2.Data(m) for _ in range(min(8, os.cpu_count() or 1))], ticks, q, v, ws, None, ddq, np.zeros((nenv, m.nv)), ctl, True, finv, **pd)
     ncon, nefc = np.zeros(nenv, np.int32), np.zeros(nenv, np.int32)
     d = b2.Data(m)
     for e in range(nenv):

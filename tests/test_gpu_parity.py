@@ -217,7 +217,12 @@ def test_odom_override(b2, orc):
     <joint name="r_ang_odom_z_joint" type="hinge" axis="0 0 1"/><geom type="box" size="0.3 0.2 0.1"/></body></worldbody></mujoco>"""
     m = b2.Model(xml=xml)
     nenv = 8
-    bt = b2.Batch(m, nenv, precision=b2.engine.F64)
+    for prec, tol in [(b2.engine.F64, 1e-12), (b2.engine.F32, 2e-6)]:   # the product path is fp32: sin / cos of the yaw in fp32
+        _odom_case(b2, orc, m, nenv, prec, tol)
+
+
+def _odom_case(b2, orc, m, nenv, prec, tol):
+    bt = b2.Batch(m, nenv, precision=prec)
     bt.set_odom([0, 1, -1, -1, -1, 2], [-1, -1, 2])
     yaw = np.linspace(-3, 3, nenv)
     qpos = np.zeros((nenv, 3)); qpos[:, 2] = yaw
@@ -231,8 +236,9 @@ def test_odom_override(b2, orc):
         d.qpos[:] = qpos[e]; d.qvel[:] = 0; d.qacc_warmstart[:] = 0
         orc.call("step", m, d)
         orc.set_odom_vels(m, d, [0, 1, -1], [-1, -1, 2], [-1, -1, 2], tw[e])
-        np.testing.assert_allclose(qv[e], d.qvel, atol=1e-12)
-        np.testing.assert_allclose(q1[e], d.qpos, atol=1e-12)
+        np.testing.assert_allclose(qv[e], d.qvel, atol=tol)
+        np.testing.assert_allclose(q1[e], d.qpos, atol=tol)
+    bt.close()
 
 
 @pytest.mark.parametrize("name", ["panda7.xml", "ur5_tabletop.xml"])
@@ -341,10 +347,12 @@ def test_tick_host_read_order_matches_reference_loop(b2, orc, name, prec):
     bt.close()
 
 
-def test_mujoco_named_shim_steps_like_the_oracle(b2, orc):
-    """mj_step1 / mjcb_control / mj_inverse / mj_step2 through the MuJoCo-named C API == oracle tick (C1 plumbing)."""
+@pytest.mark.parametrize("prec,tol", [("8", 1e-9), ("4", 2e-5)])
+def test_mujoco_named_shim_steps_like_the_oracle(b2, orc, prec, tol):
+    """mj_step1 / mjcb_control / mj_inverse / mj_step2 through the MuJoCo-named C API == oracle tick (C1 plumbing), with
+    the shim's batch in fp64 and in fp32 (the product precision; B2_PRECISION selects it)."""
     import os
-    os.environ["B2_PRECISION"] = "8"
+    os.environ["B2_PRECISION"] = prec
     m = b2.Model(b2.asset("pendulum_world.xml"))
     d = b2.Data(m); dr = b2.Data(m)
     qpos, qvel, _ = random_state(m, 1, 606)
@@ -370,17 +378,27 @@ def test_mujoco_named_shim_steps_like_the_oracle(b2, orc):
         C.c_void_p.in_dll(b2.lib, "mjcb_control").value = None
         os.environ.pop("B2_PRECISION")
     assert len(calls) == 20
-    np.testing.assert_allclose(d.qpos, dr.qpos, atol=1e-9)
-    np.testing.assert_allclose(d.qvel, dr.qvel, atol=1e-9)
-    np.testing.assert_allclose(d.qfrc_inverse, dr.qfrc_inverse, atol=1e-8)
-    np.testing.assert_allclose(d.xpos, dr.xpos, atol=1e-9)
-    assert abs(d.time - dr.time) < 1e-9
+    np.testing.assert_allclose(d.qpos, dr.qpos, atol=tol)
+    np.testing.assert_allclose(d.qvel, dr.qvel, atol=tol * 10)
+    np.testing.assert_allclose(d.qfrc_inverse, dr.qfrc_inverse, atol=tol * 10)
+    np.testing.assert_allclose(d.xpos, dr.xpos, atol=tol)
+    assert abs(d.time - dr.time) < 1e-6
     y = np.zeros(m.nv); v = np.linspace(-1, 1, m.nv).copy(); yr = np.zeros(m.nv)
     b2.lib.mj_mulM(m.ptr, d.ptr, y.ctypes.data, v.ctypes.data)
     orc.call("fwdPosition", m, dr)
     orc.olib.omj_mulM(m.ptr, dr.ptr, yr.ctypes.data, v.ctypes.data)
-    # d->qM was mirrored before the last integration step; compare against the oracle at the same configuration
-    assert np.all(np.isfinite(y))
+    # d->qM was mirrored before the last integration step: the oracle's matrix at that configuration is the one of its own
+    # last mj_step1, still in dr->qM (mj_step2 does not touch it)
+    os.environ["B2_PRECISION"] = prec
+    try:
+        b2.lib.mj_forward(m.ptr, d.ptr)
+        b2.lib.mj_mulM(m.ptr, d.ptr, y.ctypes.data, v.ctypes.data)
+    finally:
+        os.environ.pop("B2_PRECISION")
+    dr.qpos[:] = d.qpos
+    orc.call("fwdPosition", m, dr)
+    orc.olib.omj_mulM(m.ptr, dr.ptr, yr.ctypes.data, v.ctypes.data)
+    np.testing.assert_allclose(y, yr, atol=max(tol, 1e-9) * 10 * max(1.0, np.abs(yr).max()))
 
 
 ZOO = """<mujoco><compiler angle="radian"/><option timestep="0.005" gravity="0 0 -9.81"/><size nconmax="96" njmax="320"/>
@@ -723,14 +741,17 @@ def test_pack_obs_is_the_state_in_native_layout(b2):
     bt.close()
 
 
-def test_c4_pr2_like_pd_control_tick_matches_oracle(b2, orc):
-    """C4 (BASELINE configs[3]): PR2-shaped robot — one 49-dof tree, 8 mimic-joint equalities, joint limits, condim-4
-    wheel contacts — dropped onto the floor under device-side PD computed-torque control of the 14 arm joints
-    (b2_set_pd), through the control tick with host buffers.  fp64 batch == fp64 oracle tick (with the oracle's PD
-    stage) on state, efforts, contact counts and row counts; the fp32 product path stays within a written tolerance."""
+@pytest.mark.parametrize("asset_name,neq", [("pr2_real.mjb", 6), ("pr2_like.xml", 8)])
+def test_c4_pr2_like_pd_control_tick_matches_oracle(b2, orc, asset_name, neq):
+    """C4 (BASELINE configs[3]): the reference's PR2 (compiled image of model/test/pr2/pr2.xml, mesh geoms as convex
+    hulls, 1284 candidate pairs) and the primitive-shaped stand-in of round 1 — one 49-dof tree, mimic-joint equalities,
+    joint limits, condim-4 wheel contacts — dropped onto the floor under device-side PD computed-torque control of the 14
+    arm joints (b2_set_pd), through the control tick with host buffers.  fp64 batch == fp64 oracle tick (with the
+    oracle's PD stage) on state, efforts, contact counts and row counts; the fp32 product path stays within a written
+    tolerance."""
     from mujoco_sim_b200 import workloads as w
-    m = b2.Model(b2.asset("pr2_like.xml"))
-    assert (m.nq, m.nv) == (50, 49)
+    m = b2.Model(b2.asset(asset_name))
+    assert (m.nq, m.nv) == (50, 49) and m.neq == neq
     nenv, steps = 12, 40
     hw, ctl, kp, kd = w.control_spec("c4", m)
     dadr = np.array(m.jnt_dofadr)[hw]
@@ -753,7 +774,7 @@ def test_c4_pr2_like_pd_control_tick_matches_oracle(b2, orc):
             if k == steps - 1: q_before = bt.get("qpos")
             bt.tick_host_raw(vel.ctypes.data, eff.ctypes.data, *[o.ctypes.data for o in out])
         gq, gv = bt.get("qpos"), bt.get("qvel")
-        assert bt.get("nefc").max() >= 8 + 6 and bt.get("ncon").max() >= 4   # equalities + wheel contacts were active
+        assert bt.get("nefc").max() >= neq + 6 and bt.get("ncon").max() >= 4   # equalities + wheel contacts were active
         # fp32 targets are rounded once on upload: compare against the same rounding in the tolerance
         np.testing.assert_allclose(gq, rq, atol=tol * 5 if prec == b2.engine.F64 else tol * 5, err_msg="qpos prec %d" % prec)
         np.testing.assert_allclose(gv, rv, atol=tol * 200, err_msg="qvel prec %d" % prec)
@@ -764,8 +785,10 @@ def test_c4_pr2_like_pd_control_tick_matches_oracle(b2, orc):
         bt.close()
 
 
-def test_c5_spawn_destroy_slots_match_oracle(b2, orc):
-    """C5 (BASELINE configs[4]) and SURVEY row f2: run-time spawn / destroy as slot activation.  The fp64 batch, with
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_c5_spawn_destroy_slots_match_oracle(b2, orc, prec):
+    """C5 (BASELINE configs[4]) and SURVEY row f2: run-time spawn / destroy as slot activation.  The fp64 batch (and the
+    fp32 product path, to written tolerances), with
     objects spawned into slots, left to fall and pile up, destroyed and re-spawned per environment, follows the oracle
     stepping the same model with inactive slots held at their parking place; destroyed slots rest exactly there, produce
     no contacts, and the flags read back."""
@@ -776,7 +799,7 @@ def test_c5_spawn_destroy_slots_match_oracle(b2, orc):
     slots = w.c5_slot_bodies(m)
     qadr = np.array([m.jnt_qposadr[m.body_jntadr[b]] for b in slots]); dadr = np.array([m.jnt_dofadr[m.body_jntadr[b]] for b in slots])
     q0, v0, _ = w.config_state("c5", m, np.arange(nenv))
-    bt = b2.Batch(m, nenv, precision=b2.engine.F64)
+    bt = b2.Batch(m, nenv, precision=b2.engine.F64 if prec == "f64" else b2.engine.F32)
     bt.set("qpos", q0); bt.set("qvel", v0)
     w.c5_init(bt)
     act = bt.slot_active()
@@ -839,6 +862,17 @@ def test_c5_spawn_destroy_slots_match_oracle(b2, orc):
     err = np.abs(gq - rq).max(axis=1)
     verr = np.abs(gv - rv).max(axis=1)
     clean = ~touched
+    if prec == "f32":
+        # the product path: same slot bookkeeping bit for bit; 150 ticks of impacts in fp32 against the fp64 oracle: the bulk
+        # of the state within 1e-4, every environment physically close, parked slots exactly at their parking place
+        assert np.median(np.abs(gq - rq)) < 1e-4 and (err < 0.3).all(), err
+        assert (err[clean] < 5e-2).all(), (touched, err)
+        for e in range(nenv):
+            for s_ in range(w.NSLOT_C5):
+                if not live[e, s_]:
+                    assert np.array_equal(gq[e, qadr[s_]:qadr[s_] + 7], w.park_pose(s_).astype(np.float32).astype(np.float64)) and not gv[e, dadr[s_]:dadr[s_] + 6].any()
+        bt.close()
+        return
     assert (err[clean] < 2e-4).all() and (verr[clean] < 2e-2).all(), (touched, err)
     # with cylinders among the slots and the pendulum bobs nearly every environment sees a flat-faced pair within 150 ticks;
     # the ones whose MPR iterates happened to coincide still follow the oracle to rounding, the others stay physically close
@@ -888,3 +922,47 @@ def test_tensor_core_projection_matches_ffma(b2):
     e3 = np.abs(ref[1] - got[1]).max()
     e1 = np.abs(ref[1] - out["tf32x1"][1]).max()
     assert e1 > 5 * e3, (e1, e3)
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_contact_lists_match_oracle_every_tick(b2, orc, prec):
+    """north_star: "bit-exact for contact-pair indices and body ids" on every compared tick.  The tabletop scene (C3) is
+    stepped tick by tick next to the oracle; after EVERY tick the contact lists (geom1, geom2, pair index, condim, in
+    order) are compared.  fp64: identical on every tick of every environment.  fp32: an environment's list may change a
+    tick earlier or later than the oracle's when a contact forms within rounding of the margin; the lists must agree on
+    >= 97 % of the environment-ticks and an environment that differs must agree again within a few ticks."""
+    from mujoco_sim_b200 import workloads as w
+    m = b2.Model(b2.asset("ur5_tabletop.xml"))
+    nenv, ticks = 48, 80
+    bt = b2.Batch(m, nenv, precision=b2.engine.F64 if prec == "f64" else b2.engine.F32)
+    qpos, qvel, frc, _ = w.load_config("c3", bt)
+    ds = [b2.Data(m) for _ in range(nenv)]
+    for e in range(nenv):
+        ds[e].qpos[:] = qpos[e]; ds[e].qvel[:] = qvel[e]; ds[e].qfrc_applied[:] = frc[e]; ds[e].qacc[:] = 0; ds[e].qacc_warmstart[:] = 0
+    ncm = m.nconmax
+    same = np.zeros((ticks, nenv), bool)
+    for k in range(ticks):
+        bt.step(1)
+        for e in range(nenv):
+            orc.call("step", m, ds[e])
+        gi = bt.get("contact_int")   # [env][5 * nconmax]: geom1 | geom2 | dim | pair | efc
+        gn = bt.get("ncon")[:, 0]
+        for e in range(nenv):
+            nc = int(ds[e].ncon)
+            ok = nc == int(gn[e])
+            if ok and nc:
+                ref = np.array([[contact_of(b2, ds[e], c)[f] for f in ("geom1", "geom2", "dim")] for c in range(nc)])
+                ok = np.array_equal(ref[:, 0], gi[e, :nc]) and np.array_equal(ref[:, 1], gi[e, ncm:ncm + nc]) and \
+                    np.array_equal(ref[:, 2], gi[e, 2 * ncm:2 * ncm + nc])
+                if ok:   # the pair index names the same two geoms
+                    pr = gi[e, 3 * ncm:3 * ncm + nc]
+                    ok = np.array_equal(np.array(m.pair_geom1)[pr], ref[:, 0]) and np.array_equal(np.array(m.pair_geom2)[pr], ref[:, 1])
+            same[k, e] = ok
+    assert int(np.array([d.ncon for d in ds]).max()) >= 8     # the props did land
+    if prec == "f64":
+        assert same.all(), np.argwhere(~same)[:10]
+    else:
+        assert same.mean() >= 0.97, same.mean()
+        # a difference does not persist: every environment agrees again on most of the last 10 ticks
+        assert (same[-10:].mean(axis=0) >= 0.5).mean() >= 0.9, same[-10:].mean(axis=0)
+    bt.close()
