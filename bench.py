@@ -97,7 +97,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", os.environ.get("B2_BENCH_SMI_MS", "100")],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, bufsize=1)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -370,6 +370,81 @@ def drift_report(cfg, nenv=64, horizons=(1, 10, 100, 1000)):
     return out
 
 
+def measure_exchange(bt, m, nenv, K, ctx, tick_resident, do_flush, starts, ends, stream, allmax, barrier, blocks=5):
+    """Per-tick observation exchange: device time of K-step blocks with (a) the fused peer-store epilogue and (b) for
+    N > 1 the pack kernel + NCCL all-gather; the fused buffer is verified against the ranks' own states."""
+    import torch
+    rank, world, dist = ctx["rank"], ctx["world"], ctx["dist"]
+    nobs = m.nq + m.nv
+    _, handle = bt.obs_create(world, rank)
+    if dist is not None:
+        hs = [None] * world
+        dist.all_gather_object(hs, handle)
+        bt.obs_attach(handles=b"".join(hs))
+    else:
+        bt.obs_attach(handles=handle)
+
+    def timed():
+        out = []
+        for _ in range(blocks):
+            barrier(); torch.cuda.synchronize(); bt.sync()
+            for k in range(K):
+                do_flush()
+                starts[k].record(stream)
+                tick_resident()
+                ends[k].record(stream)
+            bt.sync(); torch.cuda.synchronize(); barrier()
+            out.append(allmax(sum(s.elapsed_time(e) for s, e in zip(starts, ends))))
+        return float(np.median(out)) / K
+    # the tick time depends on the (evolving) contact state: the exchange-free reference is measured around the
+    # exchange blocks, in the same phase of the simulation
+    bt.obs_enable(False)
+    for _ in range(3):
+        tick_resident()
+    ref_a = timed()
+    bt.obs_enable(True)
+    for _ in range(3):
+        tick_resident()
+    fused_ms = timed()
+    # verification: after a barrier every rank's buffer holds every rank's state
+    bt.sync(); barrier()
+    got = bt.obs_read(world)
+    mine = np.concatenate([bt.get("qpos", layout=1, dtype=np.float32), bt.get("qvel", layout=1, dtype=np.float32)])
+    ok = bool(np.array_equal(got[rank], mine))
+    if dist is not None:
+        allst = torch.empty((world, nobs, nenv), dtype=torch.float32, device="cuda")
+        dist.all_gather_into_tensor(allst, torch.from_numpy(mine).cuda())
+        ok = ok and bool(np.array_equal(got, allst.cpu().numpy()))
+        flag = torch.tensor([1.0 if ok else 0.0], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        ok = bool(flag.item() > 0.5)
+    bt.obs_enable(False)
+    for _ in range(3):
+        tick_resident()
+    ref_b = timed()
+    res = {"no_exchange_ms_per_step_same_phase": 0.5 * (ref_a + ref_b), "fused_peer_store_ms_per_step": fused_ms, "verified_equal_to_all_ranks_state": ok, "bytes_per_rank_per_tick": int(4 * nobs * nenv),
+           "how": "stores from k_integrate's epilogue into every GPU's buffer through NVLink peer mappings (CUDA IPC); no pack kernel, no collective"}
+    if dist is not None:
+        obs_local = torch.empty((nobs, nenv), dtype=torch.float32, device="cuda")
+        obs_all = torch.empty((world, nobs, nenv), dtype=torch.float32, device="cuda")
+        out = []
+        for _ in range(blocks):
+            barrier(); torch.cuda.synchronize(); bt.sync()
+            for k in range(K):
+                do_flush()
+                starts[k].record(stream)
+                tick_resident()
+                bt.pack_obs(obs_local.data_ptr())
+                with torch.cuda.stream(stream):
+                    dist.all_gather_into_tensor(obs_all, obs_local)
+                ends[k].record(stream)
+            bt.sync(); torch.cuda.synchronize(); barrier()
+            out.append(allmax(sum(s.elapsed_time(e) for s, e in zip(starts, ends))))
+        res["nccl_allgather_ms_per_step"] = float(np.median(out)) / K
+        res["no_exchange_ms_per_step_after_nccl"] = timed()
+    return res
+
+
 def measure(cfg, nenv, K, W, ctx, min_dev_s=0.5, detail=True, max_repeats=400):
     """Settle + warm up, then timed K-step blocks (device events, max over ranks, median block) and the end-to-end loop
     through host buffers.  Returns a dict with everything the JSON line needs for this configuration."""
@@ -458,7 +533,7 @@ def measure(cfg, nenv, K, W, ctx, min_dev_s=0.5, detail=True, max_repeats=400):
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
     ends = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
     blocks, total_ms, launches = [], 0.0, 0
-    sampler = ClockSampler(local_rank) if detail else None
+    sampler = ClockSampler(local_rank) if (detail and not os.environ.get("B2_BENCH_NO_SAMPLER")) else None
     if sampler:
         sampler.start()
     t_wall = time.perf_counter()
@@ -511,6 +586,16 @@ def measure(cfg, nenv, K, W, ctx, min_dev_s=0.5, detail=True, max_repeats=400):
     clocks = sampler.stop() if sampler else None
     wall = time.perf_counter() - t_wall
 
+    # ---- observation exchange, measured next to the exchange-free number: the fused peer-store epilogue
+    #      (every rank writes its [qpos | qvel] into every GPU's buffer from inside the integrate kernel; no pack kernel, no
+    #      collective call) and, for N > 1, the pack + NCCL all-gather baseline ----
+    exch = None
+    if detail and not slots:
+        try:
+            exch = measure_exchange(bt, m, nenv, K, ctx, tick_resident, do_flush, starts, ends, stream, allmax, barrier)
+        except Exception as e:   # never take the bench line down
+            exch = {"error": repr(e)[:300]}
+
     total_envs = nenv * world
     value = total_envs * K / (max_ms * 1e-3)
     peak, peak_src = peaks()
@@ -549,7 +634,7 @@ def measure(cfg, nenv, K, W, ctx, min_dev_s=0.5, detail=True, max_repeats=400):
         "e2e": {"value": total_envs * K / e2e_max, "unit": UNIT, "h2d_bytes_per_step": int(h2d * world),
                 "d2h_bytes_per_step": int(d2h * world), "ms_per_step": 1e3 * e2e_max / K, "repeats": len(e2e_blocks)},
         "gpu_launches": int(launches),
-        "clocks": clocks, "wall_s": wall,
+        "clocks": clocks, "wall_s": wall, "obs_exchange": exch,
     }
     del keep
     bt.close()
@@ -639,7 +724,7 @@ def main():
         "ms_per_step": res["ms_per_step"], "repeats": res["repeats"], "block_ms_min_med_max": res["block_ms_min_med_max"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": res["config"], "stats": res["stats"], "roofline": res["roofline"], "e2e": res["e2e"],
-        "gpu_launches": res["gpu_launches"], "clocks": res["clocks"],
+        "gpu_launches": res["gpu_launches"], "clocks": res["clocks"], "obs_exchange": res["obs_exchange"],
     }
     if not args.no_cpu_baseline and world == 1:
         sample = {"c2": 4096, "c3": 2048, "c4": 512, "c5": 512}[args.config]

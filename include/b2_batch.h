@@ -140,6 +140,33 @@ int b2_slot_active(b2_batch* b, unsigned char* active, int env_lo, int env_hi);
  * ncclAllGather / torch.distributed.all_gather_into_tensor of that buffer on the same stream (bench.py does exactly that). */
 int b2_pack_obs(b2_batch* b, float* obs_dev);
 
+/* The same exchange fused into the tick (no pack kernel, no collective call): every GPU owns a buffer
+ * [world][nq + nv][nenv] fp32 and each tick's integrate epilogue stores the new state of its environments into slice
+ * `rank` of EVERY GPU's buffer through NVLink peer mappings.
+ *   b2_obs_create   allocate this GPU's buffer for `world` shards of nenv environments; returns its device pointer
+ *   b2_obs_handle   64-byte CUDA IPC handle of the buffer (one process per GPU: all-gather the handles once, at setup)
+ *   b2_obs_attach   open the peers: `handles` = world x 64 bytes (IPC, other processes) or `ptrs` = world device
+ *                   pointers (one process driving several devices, peer access is enabled here); switches the exchange on
+ *   b2_obs_enable   switch the exchange on / off for the following ticks
+ * A reader of the buffer synchronises with the writers' streams first (a barrier after the tick). */
+float* b2_obs_create(b2_batch* b, int world, int rank);
+int b2_obs_handle(b2_batch* b, void* handle64);
+int b2_obs_attach(b2_batch* b, const void* handles, float* const* ptrs);
+int b2_obs_enable(b2_batch* b, int on);
+int b2_obs_read(b2_batch* b, float* host);   /* copy this GPU's whole buffer to the host (after synchronising its stream) */
+
+/* One host process driving several devices (b2_create(m, nenv, devices, ndev)): contiguous shards of
+ * nenv environments, one batch and stream per device; b2_multi_tick launches the tick on every device before it returns
+ * (the devices run concurrently), b2_multi_sync waits for all of them.  With obs != 0 the fused observation exchange is
+ * set up between the shards (peer access).  b2_multi_shard gives access to shard i for state I/O. */
+typedef struct b2_multi b2_multi;
+b2_multi* b2_create_multi(const mjModel* m, int nenv, const int* devices, int ndev, int precision, int obs);
+void b2_multi_destroy(b2_multi* mb);
+int b2_multi_count(const b2_multi* mb);
+b2_batch* b2_multi_shard(b2_multi* mb, int i);
+int b2_multi_tick(b2_multi* mb, int flags);
+int b2_multi_sync(b2_multi* mb);
+
 /* benchmarking aid: write `bytes` of scratch on the batch's stream so that the state leaves the L2 between timed steps */
 int b2_l2_flush(b2_batch* b, long long bytes);
 

@@ -264,6 +264,7 @@ KArgs<T> make_args(b2_batch* b, int flags) {
   a.model = b->blob_dev; a.model_words = b->hdr.nwords;
   a.flags = flags; a.ws_block = b->smooth_block; a.h = (T)b->h; a.wp = b->wp;
   a.block_capw = b->block_capw; a.block_npar = b->block_npar; a.stage_cap = b->isl_cap ? b->isl_stage : b->stage_cap; a.row_nb = b->row_nb; a.isl_cap = b->isl_cap; a.em_rows = b->tc_rows;
+  a.obs_peers = b->obs_peers_dev; a.obs_world = b->obs_world; a.obs_rank = b->obs_rank; a.obs_nenv = b->nenv;
   a.hw_vel = b->io_in[0]; a.hw_eff = b->io_in[1];
   a.hw_pos = b->io_out[0]; a.hw_velo = b->io_out[1]; a.hw_effo = b->io_out[2];
   a.hw_kp = b->hw_kp; a.hw_kd = b->hw_kd;
@@ -411,6 +412,12 @@ int run_tick(b2_batch* b, int flags) {
   if (b->fusable) kf |= B2F_FUSABLE;
   if (b->tick_flags & (1 << 30)) kf |= B2F_XFRC;  // set once xfrc_applied has been written
   if (b->export_stages) kf |= B2F_EXPORT;
+  // observation exchange: fused into k_integrate's epilogue when the tick ends there for every environment; a tick
+  // that ends elsewhere (single-kernel chain, self-integrating smooth kernel, slot parking after the integration)
+  // publishes with one small kernel at its end
+  const bool obs = b->obs_on && b->obs_peers_dev && (flags & B2_TICK_INTEGRATE);
+  const bool obs_fused = obs && !b->fused && !b->fusable && !b->nslot && !(flags & B2_TICK_NOSOLVE) && !(b->chain_single && !(kf & B2F_XFRC));
+  if (obs_fused) kf |= B2F_OBS;
   const bool single = b->chain_single && !(kf & B2F_XFRC);
   // k_chain does the hardware-interface exchange itself when the hardware joints are exactly the chain's dofs
   const bool hwio = single && (flags & B2_TICK_HW) && b->hw_identity && (kf & B2F_CONTROLLER) && !(kf & B2F_ODOM) && !getenv("B2_NO_HWIO");
@@ -429,6 +436,7 @@ int run_tick(b2_batch* b, int flags) {
     if (b->chain_team) { if constexpr (sizeof(T) == 4) rc = launch_chain_team_f32(b, a); else rc = launch_chain_team_f64(b, a); }
     else if constexpr (sizeof(T) == 4) rc = launch_chain1_f32(b, a, grid); else rc = launch_chain1_f64(b, a, grid);
     if (rc < 0) return rc;
+    if (obs) { k_publish_obs<T><<<(b->nenv + 127) / 128, 128, 0, b->stream>>>(a); b->launches++; }
     prof_mark(b, SLOT_HW_READ);
     if ((flags & B2_TICK_HW) && !hwio) { if (hw_read_async(b, read_post) < 0) return -1; }
     CK(cudaGetLastError());
@@ -533,6 +541,7 @@ int run_tick(b2_batch* b, int flags) {
     }
   }
   if (flags & B2_TICK_INTEGRATE) hold_slots<T>(b);   // inactive object slots go back to their parking place
+  if (obs && !obs_fused) { k_publish_obs<T><<<(b->nenv + 127) / 128, 128, 0, b->stream>>>(a); b->launches++; }
   prof_mark(b, SLOT_HW_READ);
   if (flags & B2_TICK_HW) { if (hw_read_async(b, read_post) < 0) return -1; }
   CK(cudaGetLastError());
@@ -1047,6 +1056,10 @@ void b2_destroy(b2_batch* b) {
   if (b->slot_dadr) cudaFree(b->slot_dadr);
   if (b->slot_active) cudaFree(b->slot_active);
   if (b->flush_buf) cudaFree(b->flush_buf);
+  for (size_t p = 0; p < b->obs_peers_host.size(); p++)
+    if (b->obs_peer_ipc[p] && b->obs_peers_host[p]) cudaIpcCloseMemHandle(b->obs_peers_host[p]);
+  if (b->obs_peers_dev) cudaFree(b->obs_peers_dev);
+  if (b->obs_buf) cudaFree(b->obs_buf);
   for (auto& kv : b->registered) cudaHostUnregister(const_cast<void*>(kv.first));
   for (cudaEvent_t e : b->prof_ev) cudaEventDestroy(e);
   drop_graphs(b);
@@ -1496,6 +1509,108 @@ int b2_pack_obs(b2_batch* b, float* obs_dev) {
   else k_pack_obs<float><<<bl, th, 0, b->stream>>>((const float*)b->fields["qpos"].ptr, (const float*)b->fields["qvel"].ptr, obs_dev, nq, nv, b->nenv, b->nenvp);
   b->launches++;
   CK(cudaGetLastError());
+  return 0;
+}
+
+// ---- fused observation exchange (include/b2_batch.h) ----
+float* b2_obs_create(b2_batch* b, int world, int rank) {
+  if (!b || world < 1 || rank < 0 || rank >= world) { fail("b2_obs_create: bad argument"); return nullptr; }
+  if (cudaSetDevice(b->device) != cudaSuccess) { fail("b2_obs_create: cudaSetDevice"); return nullptr; }
+  if (b->obs_buf) { fail("b2_obs_create: already created"); return nullptr; }
+  const size_t bytes = (size_t)world * (b->m->nq + b->m->nv) * b->nenv * sizeof(float);
+  if (cudaMalloc(&b->obs_buf, bytes) != cudaSuccess) { fail("b2_obs_create: cudaMalloc"); return nullptr; }
+  cudaMemsetAsync(b->obs_buf, 0, bytes, b->stream);
+  b->obs_world = world; b->obs_rank = rank;
+  return b->obs_buf;
+}
+int b2_obs_handle(b2_batch* b, void* handle64) {
+  if (!b || !b->obs_buf || !handle64) return fail("b2_obs_handle: call b2_obs_create first");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+  CK(cudaSetDevice(b->device));
+  cudaIpcMemHandle_t h;
+  CK(cudaIpcGetMemHandle(&h, b->obs_buf));
+  std::memcpy(handle64, &h, 64);
+  return 0;
+}
+int b2_obs_attach(b2_batch* b, const void* handles, float* const* ptrs) {
+  if (!b || !b->obs_buf || (!handles && !ptrs)) return fail("b2_obs_attach: call b2_obs_create first and pass handles or pointers");
+  CK(cudaSetDevice(b->device));
+  drop_graphs(b);
+  b->obs_peers_host.assign(b->obs_world, nullptr);
+  b->obs_peer_ipc.assign(b->obs_world, false);
+  for (int p = 0; p < b->obs_world; p++) {
+    if (p == b->obs_rank) { b->obs_peers_host[p] = b->obs_buf; continue; }
+    if (ptrs) {
+      cudaPointerAttributes at;
+      CK(cudaPointerGetAttributes(&at, ptrs[p]));
+      if (at.device != b->device) {
+        const cudaError_t e = cudaDeviceEnablePeerAccess(at.device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(std::string("b2_obs_attach: no peer access to device ") + std::to_string(at.device));
+        cudaGetLastError();
+      }
+      b->obs_peers_host[p] = ptrs[p];
+    } else {
+      cudaIpcMemHandle_t h;
+      std::memcpy(&h, (const char*)handles + (size_t)64 * p, 64);
+      void* q = nullptr;
+      CK(cudaIpcOpenMemHandle(&q, h, cudaIpcMemLazyEnablePeerAccess));
+      b->obs_peers_host[p] = (float*)q;
+      b->obs_peer_ipc[p] = true;
+    }
+  }
+  if (!b->obs_peers_dev) CK(cudaMalloc(&b->obs_peers_dev, sizeof(float*) * b->obs_world));
+  CK(cudaMemcpy(b->obs_peers_dev, b->obs_peers_host.data(), sizeof(float*) * b->obs_world, cudaMemcpyHostToDevice));
+  b->obs_on = true;
+  return 0;
+}
+int b2_obs_read(b2_batch* b, float* host) {
+  if (!b || !b->obs_buf || !host) return fail("b2_obs_read: call b2_obs_create first");
+  CK(cudaSetDevice(b->device));
+  CK(cudaStreamSynchronize(b->stream));
+  CK(cudaMemcpy(host, b->obs_buf, (size_t)b->obs_world * (b->m->nq + b->m->nv) * b->nenv * sizeof(float), cudaMemcpyDeviceToHost));
+  return 0;
+}
+int b2_obs_enable(b2_batch* b, int on) {
+  if (!b) return fail("b2_obs_enable: null batch");
+  if (on && !b->obs_peers_dev) return fail("b2_obs_enable: call b2_obs_attach first");
+  if (b->obs_on != (on != 0)) drop_graphs(b);   // the flag is baked into the captured kernel arguments
+  b->obs_on = on != 0;
+  return 0;
+}
+
+// ---- one process, several devices ----
+struct b2_multi { std::vector<b2_batch*> shard; };
+b2_multi* b2_create_multi(const mjModel* m, int nenv, const int* devices, int ndev, int precision, int obs) {
+  if (!m || nenv < 1 || !devices || ndev < 1 || nenv % ndev) { fail("b2_create_multi: bad argument (nenv must divide by ndev)"); return nullptr; }
+  auto* mb = new b2_multi();
+  for (int i = 0; i < ndev; i++) {
+    b2_batch* b = b2_create(m, nenv / ndev, devices[i], precision);
+    if (!b) { b2_multi_destroy(mb); return nullptr; }
+    mb->shard.push_back(b);
+  }
+  if (obs) {
+    std::vector<float*> ptrs(ndev, nullptr);
+    for (int i = 0; i < ndev; i++) { ptrs[i] = b2_obs_create(mb->shard[i], ndev, i); if (!ptrs[i]) { b2_multi_destroy(mb); return nullptr; } }
+    for (int i = 0; i < ndev; i++) if (b2_obs_attach(mb->shard[i], nullptr, ptrs.data()) < 0) { b2_multi_destroy(mb); return nullptr; }
+  }
+  return mb;
+}
+void b2_multi_destroy(b2_multi* mb) {
+  if (!mb) return;
+  for (b2_batch* b : mb->shard) b2_sync(b);   // nobody writes into a buffer that is about to be freed
+  for (b2_batch* b : mb->shard) b2_destroy(b);
+  delete mb;
+}
+int b2_multi_count(const b2_multi* mb) { return mb ? (int)mb->shard.size() : 0; }
+b2_batch* b2_multi_shard(b2_multi* mb, int i) { return (mb && i >= 0 && i < (int)mb->shard.size()) ? mb->shard[i] : nullptr; }
+int b2_multi_tick(b2_multi* mb, int flags) {
+  if (!mb) return fail("b2_multi_tick: null");
+  for (b2_batch* b : mb->shard) if (b2_tick(b, flags) < 0) return -1;   // asynchronous launches: the devices run side by side
+  return 0;
+}
+int b2_multi_sync(b2_multi* mb) {
+  if (!mb) return fail("b2_multi_sync: null");
+  for (b2_batch* b : mb->shard) if (b2_sync(b) < 0) return -1;
   return 0;
 }
 

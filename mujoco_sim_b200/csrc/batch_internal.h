@@ -48,6 +48,13 @@ struct b2_batch {
   int block_npar = 0;    // ... of which header + parameters
   int make_block = 128;  // CTA size of k_make_constraint
   int pgs_lanes = 8;     // lanes per environment in k_pgs_block
+  // observation exchange: this GPU's buffer, the peers' mappings (device array of world pointers), slice geometry
+  float* obs_buf = nullptr;
+  float** obs_peers_dev = nullptr;
+  std::vector<float*> obs_peers_host;
+  std::vector<bool> obs_peer_ipc;
+  int obs_world = 0, obs_rank = 0;
+  bool obs_on = false;
   int tc_rows = 0;       // tensor-core projection (k_project_tc): rows per environment of the environment-major arrays; 0: off
   int tc_passes = 3;     // 3: 3xTF32 (fp32-level accuracy), 1: plain TF32
   int isl_cap = 0;       // island slots per environment (k_pgs_island: models made of several small trees); 0: k_pgs_block

@@ -20,6 +20,7 @@ enum TickFlags : int {
                              // integrated by the smooth kernel (status bit 8) and skipped by the constraint pipeline
   B2F_LD_SMEM = 1 << 11,     // k_smooth (workspace in HBM) factorises M in a shared-memory scratch column per thread
   B2F_READ_POST = 1 << 12,   // hardware read returns post-integration qpos / qvel (default: the reference's pre-integration order)
+  B2F_OBS = 1 << 13,         // publish [qpos | qvel] of every environment into the observation buffer of every GPU (peer stores)
   B2F_HWIO = 1 << 10,        // k_chain also does MjHWInterface::write / read (hardware joint j == dof j): commands are read
                              // from, and joint states written to, the hw_* buffers (HBM or mapped host memory)
 };
@@ -91,6 +92,10 @@ struct KArgs {
   const float *hw_vel, *hw_eff;
   float *hw_pos, *hw_velo, *hw_effo;
   const float *hw_kp, *hw_kd;   // [nhw] PD gains (b2_set_pd): hw_eff holds position targets when non-null
+  // observation exchange: obs_peers[p] is GPU p's buffer [world][nq + nv][obs_nenv] fp32 (own memory for
+  // p == obs_rank, NVLink peer mappings otherwise); this GPU fills slice obs_rank of every one of them
+  float* const* obs_peers;
+  int obs_world, obs_rank, obs_nenv;
   int* pending;           // [1] environments that need the constraint pipeline this tick (B2F_FUSABLE); cleared by a
                           //     memset node in front of the smooth kernel
 };

@@ -1703,6 +1703,24 @@ __global__ void __launch_bounds__(32, MINB) k_pgs_island(const KArgs<T> a) {
   }
 }
 
+template <typename T>
+__device__ __forceinline__ void publish_obs(const KArgs<T>& a, int env) {
+  const DModel* hd = reinterpret_cast<const DModel*>(a.model);
+  const int nq = hd->nq, nv = hd->nv;
+  const long long S = a.nenvp;
+  const long long base = (long long)a.obs_rank * (nq + nv) * a.obs_nenv + env;
+  for (int i = 0; i < nq + nv; i++) {
+    const float v = (float)(i < nq ? a.qpos[(long long)i * S + env] : a.qvel[(long long)(i - nq) * S + env]);
+    for (int p = 0; p < a.obs_world; p++) a.obs_peers[p][base + (long long)i * a.obs_nenv] = v;
+  }
+}
+// the same as a kernel of its own, for the ticks that do not end in k_integrate (single-kernel chains)
+template <typename T>
+__global__ void k_publish_obs(const KArgs<T> a) {
+  const int env = blockIdx.x * blockDim.x + threadIdx.x;
+  if (env < a.nenv) publish_obs(a, env);
+}
+
 // G7: mj_checkAcc, semi-implicit Euler with implicit damping, odom override (one thread per environment)
 template <typename T, int BLOCK>
 __global__ void __launch_bounds__(BLOCK) k_integrate(const KArgs<T> a) {
@@ -1737,6 +1755,10 @@ __global__ void __launch_bounds__(BLOCK) k_integrate(const KArgs<T> a) {
       euler_step<GenericP>(m, qpos, qvel, qM, qacc, frc, a.h, LD, dinv, xa);
       a.time[env] += a.h;
       if (a.flags & B2F_ODOM) odom_override(m, a, env);
+      // observation exchange fused into the integrate epilogue: the new state goes straight into slice `rank` of every
+      // GPU's observation buffer (plain stores through the NVLink peer mappings: fire-and-forget, one 128-byte line per
+      // element and warp).  No pack kernel, no collective call.
+      if ((a.flags & B2F_OBS) && env < a.nenv) publish_obs(a, env);
     }
   }
 }

@@ -92,6 +92,17 @@ _sig = {
     "b2_register_host": (_i, [_vp, _vp, C.c_longlong]),
     "b2_unregister_host": (_i, [_vp, _vp]),
     "b2_pack_obs": (_i, [_vp, _vp]),
+    "b2_obs_create": (_vp, [_vp, _i, _i]),
+    "b2_obs_handle": (_i, [_vp, _vp]),
+    "b2_obs_attach": (_i, [_vp, _vp, _vp]),
+    "b2_obs_enable": (_i, [_vp, _i]),
+    "b2_obs_read": (_i, [_vp, _vp]),
+    "b2_create_multi": (_vp, [_vp, _i, _vp, _i, _i, _i]),
+    "b2_multi_destroy": (None, [_vp]),
+    "b2_multi_count": (_i, [_vp]),
+    "b2_multi_shard": (_vp, [_vp, _i]),
+    "b2_multi_tick": (_i, [_vp, _i]),
+    "b2_multi_sync": (_i, [_vp]),
     "b2_set_pd": (_i, [_vp, _vp, _vp]),
     "b2_set_slots": (_i, [_vp, _i, _vp]),
     "b2_spawn": (_i, [_vp, _i, _vp, _vp, _vp, _vp]),
@@ -402,6 +413,35 @@ class Batch:
     def pack_obs(self, dev_ptr):
         """[qpos | qvel] as fp32 [nq + nv][nenv] into a device buffer (the payload of the per-tick all-gather)."""
         self._ck(lib.b2_pack_obs(self.ptr, dev_ptr), "b2_pack_obs")
+
+    # ---- fused observation exchange (include/b2_batch.h) ----
+    def obs_create(self, world, rank):
+        """Allocate this GPU's observation buffer [world][nq + nv][nenv] fp32; returns (device pointer, 64-byte IPC handle)."""
+        p = lib.b2_obs_create(self.ptr, world, rank)
+        if not p:
+            raise B2Error("b2_obs_create: " + _err())
+        h = C.create_string_buffer(64)
+        self._ck(lib.b2_obs_handle(self.ptr, h), "b2_obs_handle")
+        return p, h.raw
+
+    def obs_attach(self, handles=None, ptrs=None):
+        """Open the peers' buffers (handles: world x 64 bytes from the other processes, or ptrs: device pointers of a
+        single process driving several devices) and switch the exchange on."""
+        if handles is not None:
+            buf = C.create_string_buffer(bytes(handles), len(handles))
+            self._ck(lib.b2_obs_attach(self.ptr, buf, None), "b2_obs_attach")
+        else:
+            arr = (C.c_void_p * len(ptrs))(*ptrs)
+            self._ck(lib.b2_obs_attach(self.ptr, None, arr), "b2_obs_attach")
+
+    def obs_read(self, world):
+        """This GPU's observation buffer as a host array [world][nq + nv][nenv] (synchronises the batch's stream only)."""
+        out = np.zeros((world, self.model.nq + self.model.nv, self.nenv), np.float32)
+        self._ck(lib.b2_obs_read(self.ptr, out.ctypes.data), "b2_obs_read")
+        return out
+
+    def obs_enable(self, on=True):
+        self._ck(lib.b2_obs_enable(self.ptr, int(bool(on))), "b2_obs_enable")
 
     def tick_resident(self):
         self._ck(lib.b2_tick_resident(self.ptr), "b2_tick_resident")

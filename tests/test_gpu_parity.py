@@ -966,3 +966,40 @@ def test_contact_lists_match_oracle_every_tick(b2, orc, prec):
         # a difference does not persist: every environment agrees again on most of the last 10 ticks
         assert (same[-10:].mean(axis=0) >= 0.5).mean() >= 0.9, same[-10:].mean(axis=0)
     bt.close()
+
+
+def test_multi_device_host_and_fused_observation_exchange(b2):
+    """b2_create_multi (one host process, contiguous shards, one batch + stream per device; here two
+    shards on device 0) with the fused observation exchange: every tick's integrate epilogue stores [qpos | qvel] of its
+    environments into slice `rank` of every shard's buffer.  Each shard's buffer must hold both shards' states exactly,
+    and the shards must reproduce the single batch bit for bit (shard invariance)."""
+    from mujoco_sim_b200 import workloads as w
+    m = b2.Model(b2.asset("ur5_tabletop.xml"))
+    nenv = 256
+    q0, v0, f0 = w.config_state("c3", m, np.arange(nenv))
+    devs = (C.c_int * 2)(0, 0)
+    mb = b2.lib.b2_create_multi(m.ptr, nenv, devs, 2, b2.engine.F32, 1)
+    assert mb and b2.lib.b2_multi_count(mb) == 2
+    half = nenv // 2
+    shards = []
+    for i in range(2):
+        bt = b2.Batch.__new__(b2.Batch)
+        bt.model, bt.ptr, bt.nenv, bt.precision = m, b2.lib.b2_multi_shard(mb, i), half, b2.engine.F32
+        bt.set("qpos", q0[i * half:(i + 1) * half]); bt.set("qvel", v0[i * half:(i + 1) * half]); bt.set("qfrc_applied", f0[i * half:(i + 1) * half])
+        shards.append(bt)
+    for _ in range(25):
+        assert b2.lib.b2_multi_tick(mb, b2.engine.TICK_INTEGRATE) == 0
+    assert b2.lib.b2_multi_sync(mb) == 0
+    one = b2.Batch(m, nenv)
+    one.set("qpos", q0); one.set("qvel", v0); one.set("qfrc_applied", f0)
+    one.step(25); one.sync()
+    ref = np.concatenate([one.get("qpos", layout=b2.engine.NATIVE, dtype=np.float32), one.get("qvel", layout=b2.engine.NATIVE, dtype=np.float32)])
+    for i, bt in enumerate(shards):
+        obs = bt.obs_read(2)                                   # [2][nq + nv][half]
+        for r in range(2):
+            assert np.array_equal(obs[r], ref[:, r * half:(r + 1) * half]), (i, r)
+    assert one.get("ncon").max() >= 4
+    one.close()
+    for bt in shards:
+        bt.ptr = None                                          # owned by the multi handle
+    b2.lib.b2_multi_destroy(mb)
