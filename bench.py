@@ -301,7 +301,7 @@ def cpu_reference_c5(m, pool, qpos, qvel, steps, warmup, min_seconds=0.0):
     return nenv * steps / med, used, med, len(blocks)
 
 
-def drift_report(cfg, nenv=64, horizons=(1, 10, 100, 1000)):
+def drift_report(cfg, nenv=64, horizons=(1, 10, 100, 1000), precision=None):
     """BASELINE metric, second part: relative L2 drift of qpos (fp32 CUDA tick vs the fp64 CPU oracle) from identical
     states.  Both sides advance tick by tick; after every tick the contact lists (geom1, geom2 in order) of the two are
     compared, and an environment leaves the drift statistics at the first tick where they differ (drift
@@ -311,7 +311,7 @@ def drift_report(cfg, nenv=64, horizons=(1, 10, 100, 1000)):
     from mujoco_sim_b200 import workloads as w
     from oracle import pyoracle as orc
     m = b2.Model(b2.asset(w.CONFIGS[cfg][0]))
-    bt = b2.Batch(m, nenv)
+    bt = b2.Batch(m, nenv, precision=precision or b2.engine.F32)
     qpos, qvel, frc, _ = w.load_config(cfg, bt)
     rq, rv, rf = (np.ascontiguousarray(x, np.float64).copy() for x in (qpos, qvel, frc))
     contacts = m.npair > 0
@@ -445,7 +445,7 @@ def measure_exchange(bt, m, nenv, K, ctx, tick_resident, do_flush, starts, ends,
     return res
 
 
-def measure(cfg, nenv, K, W, ctx, min_dev_s=0.5, detail=True, max_repeats=400):
+def measure(cfg, nenv, K, W, ctx, min_dev_s=0.5, detail=True, max_repeats=400, precision=None):
     """Settle + warm up, then timed K-step blocks (device events, max over ranks, median block) and the end-to-end loop
     through host buffers.  Returns a dict with everything the JSON line needs for this configuration."""
     import torch
@@ -465,7 +465,7 @@ def measure(cfg, nenv, K, W, ctx, min_dev_s=0.5, detail=True, max_repeats=400):
         return float(t.item())
 
     m = b2.Model(b2.asset(asset))
-    bt = b2.Batch(m, nenv, device=local_rank, precision=b2.engine.F32)
+    bt = b2.Batch(m, nenv, device=local_rank, precision=precision or b2.engine.F32)
     env_offset = rank * nenv  # contiguous shards of one global batch
     w.load_config(cfg, bt, env_offset=env_offset)
     hw, ctl, kp, kd = w.control_spec(cfg, m)
@@ -714,6 +714,13 @@ def main():
                          "kernel_ms_all": r["roofline"]["kernel_ms_all"], "mean_ncon": r["stats"]["mean_ncon"], "mean_nefc": r["stats"]["mean_nefc"],
                          "mean_solver_iter": r["stats"]["mean_solver_iter"], "kernels": r["stats"]["kernels"], "gpu_launches": r["gpu_launches"], "repeats": r["repeats"]}
 
+        # the contact-free chain once more with fp64 arithmetic: what the north star's drift bound (< 1e-4 over 1000 ticks)
+        # costs on a chaotic arm, where fp32 rounding is amplified exponentially whatever the integrator does
+        if "c2" in others:
+            r = measure("c2", w.CONFIGS["c2"][1], min(args.steps, 20), 3, ctx, min_dev_s=0.25, detail=False, max_repeats=100, precision=b2.engine.F64)
+            others["c2_f64"] = {"workload": r["config"]["workload"] + " — fp64 state and arithmetic (b2_create precision = B2_F64)", "envs_per_gpu": r["config"]["envs_per_gpu"],
+                                "value": r["value"], "e2e": r["e2e"]["value"], "ms_per_step": r["ms_per_step"], "kernels": r["stats"]["kernels"], "gpu_launches": r["gpu_launches"], "repeats": r["repeats"]}
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -740,7 +747,8 @@ def main():
                 if c == "c5":
                     continue
                 try:
-                    d = drift_report(c, nenv=16 if c == "c4" else 64, horizons=(1, 10, 100, 1000) if c == "c2" else (1, 10, 100, 300))
+                    d = drift_report(c[:2], nenv=16 if c == "c4" else 64, horizons=(1, 10, 100, 1000) if c.startswith("c2") else (1, 10, 100, 300),
+                                     precision=b2.engine.F64 if c.endswith("_f64") else None)
                     others[c]["drift_frac_below_1e-4"] = dict(zip([str(t) for t in d["ticks"]], d["frac_below_1e-4"]))
                     others[c]["drift_max"] = dict(zip([str(t) for t in d["ticks"]], d["max"]))
                     if "first_contact_set_mismatch_tick" in d:
