@@ -1021,3 +1021,64 @@ def test_drift_f64_contact_free_1000_steps_meets_north_star(b2, orc):
     rel = np.linalg.norm(bt.get("qpos") - rq, axis=1) / np.maximum(np.linalg.norm(rq, axis=1), 1e-12)
     assert rel.max() < 1e-8, rel.max()
     bt.close()
+
+
+REWRITE_CASES = [
+    # (asset, robot root body, pose_init, odom joints, received bodies)
+    # (the arm's own first joint is a z hinge: a yaw odom joint on the same body would make the mass matrix singular)
+    ("panda7.xml", "link1", (0.2, 0.1, 0.4, 0.0, 0.0, 0.5), ("lin_odom_x_joint", "lin_odom_y_joint", "ang_odom_x_joint"), ()),
+    ("mobile_arm.xml", "robot", (0.0, 0.3, 0.25, 0.0, 0.0, -0.4), (), ()),
+    ("ur5_tabletop.xml", "shoulder_link", None, (), ("ball", "cube1")),
+]
+
+
+@pytest.mark.parametrize("asset_name,robot,pose,odom,receive", REWRITE_CASES, ids=[c[0] for c in REWRITE_CASES])
+def test_reference_xml_rewrites_run_on_gpu_like_oracle(b2, orc, asset_name, robot, pose, odom, receive):
+    """the products of the reference's XML rewrites — gravcomp = 1 on every body and pose_init on the robot
+    root (mj_sim.cpp:301-335), injected odom joints (mj_sim.cpp:338-420), mocap "_ref" clones welded to received bodies with
+    torquescale 0.9 plus their excludes (mj_sim.cpp:847-960) — compiled and stepped on the GPU against the oracle, fp64
+    tight and fp32 to a written tolerance; mocap targets are moved while the simulation runs."""
+    from rewrites import rewrite
+    txt = open(b2.asset(asset_name)).read()
+    if receive and "cube1" not in txt:
+        receive = receive[:1]
+    xml = rewrite(txt, robot, True, pose, odom, receive)
+    m = b2.Model(xml=xml, basedir=b2.asset(""))
+    assert np.array(m.body_gravcomp)[1:].min() == 1.0                      # every body compensated (disable_gravity)
+    if odom:
+        names = [m.id2name(b2.engine.OBJ_JOINT, j) for j in range(m.njnt)]
+        assert all("%s_%s" % (robot, o) in names for o in odom)
+    if receive:
+        assert m.nmocap == len(receive) and m.neq == len(receive)
+    nenv, ticks = 8, 60
+    rng = np.random.default_rng(11)
+    q0 = np.tile(np.array(m.qpos0), (nenv, 1))
+    jt, qa = np.array(m.jnt_type), np.array(m.jnt_qposadr)
+    for j in range(m.njnt):
+        if jt[j] >= 2:
+            q0[:, qa[j]] += rng.uniform(-0.2, 0.2, nenv)
+    v0 = rng.uniform(-0.3, 0.3, (nenv, m.nv))
+    if m.npair > 0:   # a scene with contacts: the seeded, redrawn states of the other contact tests (no deep starts)
+        q0, v0, _ = states_for(m, asset_name, nenv, 909)
+    mp = np.tile(np.array([0.45, -0.2, 0.62, 0.3, 0.2, 0.62])[:3 * max(1, m.nmocap)], (nenv, 1)) + rng.uniform(-0.05, 0.05, (nenv, 3 * max(1, m.nmocap)))
+    for prec, tol in [(b2.engine.F64, 1e-7), (b2.engine.F32, 3e-3)]:
+        bt = b2.Batch(m, nenv, precision=prec)
+        bt.set("qpos", q0); bt.set("qvel", v0)
+        ds = [b2.Data(m) for _ in range(nenv)]
+        for e in range(nenv):
+            ds[e].qpos[:] = q0[e]; ds[e].qvel[:] = v0[e]
+        for k in range(ticks):
+            if m.nmocap and k % 20 == 0:                                   # the reference moves the targets from its subscriber
+                tgt = mp + 0.02 * (k // 20)
+                bt.set("mocap_pos", tgt)
+                for e in range(nenv):
+                    ds[e].mocap_pos[:] = tgt[e]
+            bt.step(1)
+            for e in range(nenv):
+                orc.call("step", m, ds[e])
+        rq = np.array([np.array(d.qpos) for d in ds]); rv = np.array([np.array(d.qvel) for d in ds])
+        np.testing.assert_allclose(bt.get("qpos"), rq, atol=tol, err_msg="%s prec %d" % (asset_name, prec))
+        np.testing.assert_allclose(bt.get("qvel"), rv, atol=tol * 50)
+        if receive:   # the welds were doing work: the received bodies follow their targets
+            assert bt.get("nefc").min() >= 6 * len(receive)
+        bt.close()
