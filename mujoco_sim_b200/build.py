@@ -16,7 +16,7 @@ ORACLE_LIB = os.path.join(ORACLE_DIR, "liboracle.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 CXX = os.environ.get("CXX", "g++")
 
-LIB_SOURCES = ["batch.cu", "chain_f32.cu", "chain_f64.cu", "chain1_f32.cu", "chain1_f64.cu", "shim_step.cpp", "shim_host.cpp", "mjcf_compile.cpp", "urdf_import.cpp", "set0.cpp", "model_store.cpp"]
+LIB_SOURCES = ["batch.cu", "chain_f32.cu", "chain_f64.cu", "chain1_f32.cu", "chain1_f64.cu", "shim_step.cpp", "shim_host.cpp", "mjcf_compile.cpp", "urdf_import.cpp", "set0.cpp", "model_store.cpp", "mirror_post.cpp"]
 ORACLE_SOURCES = ["oracle_smooth.cpp", "oracle_collision.cpp", "oracle_constraint.cpp", "oracle_top.cpp"]
 
 

@@ -20,6 +20,7 @@
 #include "k_args.h"
 #include "k_collide.cuh"
 #include "k_project_tc.cuh"
+namespace b2 { void mirror_post(const mjModel* m, mjData* d, const double* xfrc_applied); }
 #include "k_common.cuh"
 #include "k_constraint.cuh"
 #include "k_smooth.cuh"
@@ -1736,6 +1737,13 @@ int b2_mirror_env(b2_batch* b, int env, mjData* d) {
     std::copy(it.begin(), it.begin() + d->nefc, d->efc_type);
     if (get_field<int>(b, "efc_id", it.data(), env, env + 1, B2_ENV_MAJOR, 1) < 0) return -1;
     std::copy(it.begin(), it.begin() + d->nefc, d->efc_id);
+  }
+  // derived quantities the publishers / viewer read (cacc, cfrc_int, energy, ...): computed on the host for this one
+  // environment (mirror_post.cpp)
+  if (b->fields.count("subtree_com") && b->fields.count("cdof") && b->fields.count("qM")) {
+    std::vector<double> xf((size_t)6 * nb, 0.0);
+    if (b->tick_flags & (1 << 30)) { if (G("xfrc_applied", xf.data(), 6 * nb) < 0) return -1; }
+    b2::mirror_post(m, d, xf.data());
   }
   return 0;
 }

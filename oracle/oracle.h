@@ -38,6 +38,7 @@ void omj_fwdAcceleration(const mjModel* m, mjData* d);
 void omj_fwdConstraint(const mjModel* m, mjData* d);
 void omj_Euler(const mjModel* m, mjData* d);
 void omj_energy(const mjModel* m, mjData* d);
+void omj_rnePostConstraint(const mjModel* m, mjData* d);  /* cacc, cfrc_int with applied wrenches and contact forces */
 /* top level (mirror mj_step1 / mj_step2 / mj_forward / mj_inverse / mj_mulM) */
 void omj_step1(const mjModel* m, mjData* d);
 void omj_step2(const mjModel* m, mjData* d);

@@ -373,6 +373,60 @@ void omj_rne(const mjModel* m, mjData* d, int flg_acc, mjtNum* result) {
   copy(d->cfrc_int, cfrc.data(), 6 * nb);
 }
 
+// mj_rnePostConstraint (MuJoCo "Computation": RNE with the final acceleration and all external forces): body
+// accelerations cacc and interaction forces cfrc_int, in the c-frame ([rotational; translational] about the subtree CoM of
+// the tree root).  External forces: xfrc_applied at the body's inertial frame origin and the contact forces of the
+// current solution (pyramid multipliers -> contact-frame force -> world wrench at the contact point; geom2's body
+// receives it, geom1's body its opposite).  What force / torque sensors read (reference mj_ros.cpp:1940-1966).
+void omj_rnePostConstraint(const mjModel* m, mjData* d) {
+  const int nb = m->nbody;
+  std::vector<mjtNum> ext(6 * (size_t)nb, 0.0);
+  auto wrench = [&](int body, const mjtNum* point, const mjtNum* f, const mjtNum* t, mjtNum sgn) {
+    if (body <= 0) return;
+    const mjtNum* com = d->subtree_com + 3 * m->body_rootid[body];
+    mjtNum arm[3] = {point[0] - com[0], point[1] - com[1], point[2] - com[2]}, mom[3];
+    cross(mom, arm, f);
+    for (int k = 0; k < 3; k++) { ext[6 * body + k] += sgn * (mom[k] + (t ? t[k] : 0)); ext[6 * body + 3 + k] += sgn * f[k]; }
+  };
+  for (int i = 1; i < nb; i++) {
+    const mjtNum* w = d->xfrc_applied + 6 * i;
+    if (w[0] || w[1] || w[2] || w[3] || w[4] || w[5]) wrench(i, d->xipos + 3 * i, w, w + 3, 1);
+  }
+  for (int c = 0; c < d->ncon; c++) {
+    const mjContact& con = d->contact[c];
+    if (con.efc_address < 0) continue;
+    mjtNum cf[6] = {0, 0, 0, 0, 0, 0};
+    const mjtNum* lam = d->efc_force + con.efc_address;
+    if (con.dim == 1) cf[0] = lam[0];
+    else {
+      for (int i = 0; i < 2 * (con.dim - 1); i++) cf[0] += lam[i];
+      for (int i = 1; i < con.dim; i++) cf[i] = con.friction[i - 1] * (lam[2 * i - 2] - lam[2 * i - 1]);
+    }
+    mjtNum fw[3], tw[3];
+    for (int k = 0; k < 3; k++) {
+      fw[k] = con.frame[k] * cf[0] + con.frame[3 + k] * cf[1] + con.frame[6 + k] * cf[2];
+      tw[k] = con.frame[k] * cf[3] + con.frame[3 + k] * cf[4] + con.frame[6 + k] * cf[5];
+    }
+    wrench(m->geom_bodyid[con.geom1], con.pos, fw, tw, -1);
+    wrench(m->geom_bodyid[con.geom2], con.pos, fw, tw, 1);
+  }
+  zero(d->cacc, 6); zero(d->cfrc_int, 6);
+  if (!(m->opt.disableflags & mjDSBL_GRAVITY)) for (int k = 0; k < 3; k++) d->cacc[3 + k] = -m->opt.gravity[k];
+  for (int i = 1; i < nb; i++) {
+    mjtNum* a = d->cacc + 6 * i;
+    copy(a, d->cacc + 6 * m->body_parentid[i], 6);
+    for (int j = m->body_dofadr[i]; j < m->body_dofadr[i] + m->body_dofnum[i]; j++)
+      for (int r = 0; r < 6; r++) a[r] += d->cdof_dot[6 * j + r] * d->qvel[j] + d->cdof[6 * j + r] * d->qacc[j];
+    mjtNum Ia[6], Iv[6], vIv[6];
+    mulInertVec(Ia, d->cinert + 10 * i, a);
+    mulInertVec(Iv, d->cinert + 10 * i, d->cvel + 6 * i);
+    crossForce(vIv, d->cvel + 6 * i, Iv);
+    for (int r = 0; r < 6; r++) d->cfrc_int[6 * i + r] = Ia[r] + vIv[r] - ext[6 * (size_t)i + r];
+  }
+  for (int i = nb - 1; i > 0; i--)
+    for (int r = 0; r < 6; r++) d->cfrc_int[6 * m->body_parentid[i] + r] += d->cfrc_int[6 * i + r];
+}
+
 void omj_fwdVelocity(const mjModel* m, mjData* d) {
   omj_comVel(m, d);
   omj_passive(m, d);

@@ -14,7 +14,7 @@ _vp, _i = C.c_void_p, C.c_int
 for _n in ["omj_kinematics", "omj_comPos", "omj_crb", "omj_factorM", "omj_collision", "omj_makeConstraint",
            "omj_projectConstraint", "omj_fwdPosition", "omj_comVel", "omj_passive", "omj_referenceConstraint",
            "omj_fwdVelocity", "omj_fwdAcceleration", "omj_fwdConstraint", "omj_Euler", "omj_energy", "omj_step1",
-           "omj_step2", "omj_step", "omj_forward", "omj_inverse", "omj_invConstraint"]:
+           "omj_step2", "omj_step", "omj_forward", "omj_inverse", "omj_invConstraint", "omj_rnePostConstraint"]:
     getattr(olib, _n).restype = None
     getattr(olib, _n).argtypes = [_vp, _vp]
 olib.omj_rne.restype = None

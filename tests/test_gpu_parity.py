@@ -1082,3 +1082,37 @@ def test_reference_xml_rewrites_run_on_gpu_like_oracle(b2, orc, asset_name, robo
         if receive:   # the welds were doing work: the received bodies follow their targets
             assert bt.get("nefc").min() >= 6 * len(receive)
         bt.close()
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_mirror_derives_cacc_cfrc_int_and_energy(b2, orc, prec):
+    """b2_mirror_env fills the legacy mjData view of one environment including what the reference's
+    publishers / viewer read beyond the state — body accelerations and interaction forces (mj_rnePostConstraint: what
+    force / torque sensors report, mj_ros.cpp:1940-1966) and d->energy (mj_visual.cpp:176) — computed on the host from the
+    mirrored tick.  Against the oracle's own rnePostConstraint / energy on the tabletop scene with contacts."""
+    m = b2.Model(b2.asset("ur5_tabletop.xml"))
+    nenv = 6
+    qpos, qvel, frc = states_for(m, "ur5_tabletop.xml", nenv, 515)
+    bt = b2.Batch(m, nenv, precision=b2.engine.F64 if prec == "f64" else b2.engine.F32)
+    bt.set("qpos", qpos); bt.set("qvel", qvel); bt.set("qfrc_applied", frc)
+    bt.step(40); bt.sync()
+    q40, v40 = bt.get("qpos"), bt.get("qvel")
+    ws = bt.get("qacc_warmstart")
+    bt.forward(); bt.sync()
+    tol = 1e-6 if prec == "f64" else 5e-3
+    d, dr = b2.Data(m), b2.Data(m)
+    seen = 0
+    for e in range(nenv):
+        bt.mirror_env(e, d)
+        dr.qpos[:] = q40[e]; dr.qvel[:] = v40[e]; dr.qfrc_applied[:] = frc[e]; dr.qacc_warmstart[:] = ws[e]
+        orc.call("forward", m, dr)
+        orc.call("rnePostConstraint", m, dr)
+        orc.call("energy", m, dr)
+        seen += int(dr.ncon)
+        scale = max(1.0, np.abs(np.array(dr.cfrc_int)).max())
+        np.testing.assert_allclose(d.cacc, dr.cacc, atol=tol * max(1.0, np.abs(np.array(dr.cacc)).max()), err_msg="cacc env %d" % e)
+        np.testing.assert_allclose(d.cfrc_int, dr.cfrc_int, atol=tol * scale, err_msg="cfrc_int env %d" % e)
+        np.testing.assert_allclose(d.energy, dr.energy, rtol=tol, atol=tol)
+        np.testing.assert_allclose(d.cvel, dr.cvel, atol=tol * max(1.0, np.abs(np.array(dr.cvel)).max()))
+    assert seen >= 8     # contact forces were part of the comparison
+    bt.close()

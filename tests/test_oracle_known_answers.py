@@ -234,3 +234,38 @@ def test_oracle_is_deterministic(b2, orc):
         d = b2.Data(m)
         outs.append(oracle_rollout(orc, m, d, qpos[0], qvel[0], frc[0], 50))
     assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+
+
+def test_rne_post_constraint_known_answers(b2, orc):
+    """mj_rnePostConstraint (what force / torque sensors read), pinned by statics:
+    (1) a two-link arm hanging at rest under gravity: the interaction force at the first joint carries the weight of both
+        links, at the second joint the weight of the second link (c-frame translational part, +z);
+    (2) a box at rest on the floor: its weight is carried by the contact forces, so the interaction force across its free
+        joint vanishes; with the contacts disabled (free fall) it vanishes too (cacc cancels the pseudo-gravity)."""
+    xml = """<mujoco><compiler angle="radian"/><option timestep="0.002" gravity="0 0 -9.81"/><worldbody>
+    <body name="l1" pos="0 0 1"><joint type="hinge" axis="0 1 0" damping="5"/><geom type="capsule" size="0.03" fromto="0 0 0 0 0 -0.4"/>
+      <body name="l2" pos="0 0 -0.4"><joint type="hinge" axis="0 1 0" damping="5"/><geom type="capsule" size="0.02" fromto="0 0 0 0 0 -0.3"/></body>
+    </body></worldbody></mujoco>"""
+    m = b2.Model(xml=xml); d = b2.Data(m)
+    orc.call("forward", m, d)
+    orc.call("rnePostConstraint", m, d)
+    mass = np.array(m.body_mass)
+    cf = np.array(d.cfrc_int).reshape(-1, 6)
+    assert np.allclose(cf[1, 3:], [0, 0, (mass[1] + mass[2]) * 9.81], atol=1e-9)
+    assert np.allclose(cf[2, 3:], [0, 0, mass[2] * 9.81], atol=1e-9)
+    assert np.allclose(np.array(d.cacc).reshape(-1, 6)[1:, 3:], [[0, 0, 9.81]] * 2, atol=1e-9)
+    xml2 = """<mujoco><option timestep="0.002"/><worldbody><geom type="plane" size="0 0 1"/>
+    <body name="box" pos="0 0 0.0995"><freejoint/><geom type="box" size="0.1 0.1 0.1"/></body></worldbody></mujoco>"""
+    m2 = b2.Model(xml=xml2); d2 = b2.Data(m2)
+    for _ in range(600):
+        orc.call("step", m2, d2)
+    orc.call("forward", m2, d2)
+    orc.call("rnePostConstraint", m2, d2)
+    w = float(m2.body_mass[1]) * 9.81
+    assert d2.ncon == 4 and abs(np.array(d2.qacc)).max() < 1e-3
+    assert np.abs(np.array(d2.cfrc_int).reshape(-1, 6)[1]).max() < 2e-3 * w
+    m2.set_opt("disableflags", 16)   # contacts off: free fall
+    orc.call("forward", m2, d2)
+    orc.call("rnePostConstraint", m2, d2)
+    assert np.abs(np.array(d2.cfrc_int).reshape(-1, 6)[1]).max() < 1e-9 * w
+    assert np.allclose(np.array(d2.cacc).reshape(-1, 6)[1, 3:], 0, atol=1e-9)
