@@ -788,7 +788,7 @@ mjModel* compile_root(std::unique_ptr<XmlElem> root, const std::string& basedir,
   mjOption& o = S.view.opt;
   o.timestep = 0.002; o.impratio = 1; o.tolerance = 1e-8; o.noslip_tolerance = 1e-6;
   o.gravity[0] = 0; o.gravity[1] = 0; o.gravity[2] = -9.81;
-  o.integrator = mjINT_EULER; o.cone = mjCONE_PYRAMIDAL; o.solver = mjSOL_PGS; o.iterations = 100;
+  o.integrator = mjINT_EULER; o.cone = mjCONE_PYRAMIDAL; o.solver = mjSOL_NEWTON; o.iterations = 100;   // MuJoCo 2.3.7's defaults (the engine's substitution is reported by mj_loadXML)
   o.noslip_iterations = 0; o.disableflags = 0; o.enableflags = 0;
   int nconmax = -1, njmax = -1;
 

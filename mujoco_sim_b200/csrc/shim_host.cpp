@@ -33,12 +33,31 @@ extern "C" {
 
 mjfGeneric mjcb_control = nullptr;
 
+namespace b2 {
+// What this engine does differently from the options a model asks for, said once per load instead of silently:
+// m->opt keeps the authored values (MuJoCo's default solver is Newton), the constraint solve is always PGS with
+// opt.iterations sweeps, and the noslip post-pass and RK4 are not run (BASELINE.json configs name PGS).
+// B2_QUIET=1 silences the notes.
+void report_substitutions(const mjModel* m) {
+  if (!m || std::getenv("B2_QUIET")) return;
+  static bool said[3] = {false, false, false};   // once per process and kind
+  if (m->opt.solver != mjSOL_PGS && !said[0] && (said[0] = true))
+    std::fprintf(stderr, "b2: note: solver %s requested (or defaulted); this engine solves constraints with PGS (%d iterations, tolerance %g)\n",
+                 m->opt.solver == mjSOL_CG ? "CG" : "Newton", m->opt.iterations, m->opt.tolerance);
+  if (m->opt.noslip_iterations > 0 && !said[1] && (said[1] = true))
+    std::fprintf(stderr, "b2: note: noslip_iterations = %d requested; the noslip post-pass is not run\n", m->opt.noslip_iterations);
+  if (m->opt.integrator != mjINT_EULER && !said[2] && (said[2] = true))
+    std::fprintf(stderr, "b2: note: integrator %d requested; mj_step1 / mj_step2 integrate with semi-implicit Euler (as MuJoCo's split step does)\n", m->opt.integrator);
+}
+}  // namespace b2
+
 // Replaces libmujoco's mj_loadXML as called from include/mujoco_sim/mj_util.h:190 and
 // src/mujoco_compile.cpp:404. Error contract kept: NULL + message in `error`.
 mjModel* mj_loadXML(const char* filename, const mjVFS*, char* error, int error_sz) {
   if (error && error_sz > 0) error[0] = 0;
   try {
     mjModel* m = b2::compile_mjcf_file(filename ? filename : "");
+    b2::report_substitutions(m);
     std::lock_guard<std::mutex> lk(g_last_mtx);
     g_last_xml = static_cast<b2::ModelStore*>(m->owner_)->source_xml;
     return m;
@@ -70,6 +89,7 @@ mjModel* mj_loadXMLString(const char* xml, const char* basedir, char* error, int
   if (error && error_sz > 0) error[0] = 0;
   try {
     mjModel* m = b2::compile_mjcf_string(xml ? xml : "", basedir ? basedir : ".");
+    b2::report_substitutions(m);
     std::lock_guard<std::mutex> lk(g_last_mtx);
     g_last_xml = static_cast<b2::ModelStore*>(m->owner_)->source_xml;
     return m;
