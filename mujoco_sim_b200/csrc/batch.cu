@@ -151,6 +151,49 @@ int pack_model(b2_batch* b) {
     if (!std::strcmp(name, "dof_treeid")) { put_int(o, dof_tree.data(), n); return 0; }
     if (!std::strcmp(name, "tree_dofadr")) { put_int(o, tree_adr.data(), n); return 0; }
     if (!std::strcmp(name, "tree_dofnum")) { put_int(o, tree_num.data(), n); return 0; }
+    if (!std::strncmp(name, "lane_", 5)) {
+      // per-lane item lists of the tree-parallel kernels: tree t belongs to lane t % L, static bodies (and the geoms on
+      // them) to lane 0; ascending inside a lane, the lanes one after the other; lane_off[9 * kind + lane] = first position
+      const int L = std::max(1, b->tree_lanes);
+      // trees to lanes by longest-processing-time-first on a cost proxy (dofs + 2 bodies of the tree: an articulated arm
+      // costs about twice a free body of the same dof count), so that the lanes of an environment finish together
+      std::vector<int> tree_lane(std::max(1, ntree), 0);
+      {
+        std::vector<long long> w(std::max(1, ntree), 0), load(L, 0);
+        for (int t = 0; t < ntree; t++) w[t] = tree_num[t];
+        for (int i = 1; i < nbody; i++) if (body_tree[i] >= 0) w[body_tree[i]] += 2;
+        std::vector<int> order(ntree);
+        for (int t = 0; t < ntree; t++) order[t] = t;
+        std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return w[x] > w[y]; });
+        for (int t : order) {
+          int best = 0;
+          for (int l = 1; l < L; l++) if (load[l] < load[best]) best = l;
+          tree_lane[t] = best; load[best] += w[t];
+        }
+      }
+      auto lane_of_body = [&](int i) { return body_tree[i] < 0 ? 0 : tree_lane[body_tree[i]]; };
+      std::vector<std::vector<int>> lb(L), ld(L), lj(L), lg(L);
+      for (int i = 1; i < nbody; i++) lb[lane_of_body(i)].push_back(i);
+      for (int i = 0; i < nv; i++) ld[tree_lane[dof_tree[i]]].push_back(i);
+      for (int j = 0; j < njnt; j++) lj[lane_of_body(m->jnt_bodyid[j])].push_back(j);
+      for (int g = 0; g < ngeom; g++) lg[lane_of_body(m->geom_bodyid[g])].push_back(g);
+      std::vector<int> offs(36, 0), flat;
+      const std::vector<std::vector<int>>* kinds[4] = {&lb, &ld, &lj, &lg};
+      const int which = !std::strcmp(name, "lane_body") ? 0 : !std::strcmp(name, "lane_dof") ? 1 : !std::strcmp(name, "lane_jnt") ? 2 : !std::strcmp(name, "lane_geom") ? 3 : -1;
+      for (int k = 0; k < 4; k++) {
+        int pos = k == 0 ? 1 : 0;   // (positions of the body list start at 1: position 0 is the world body)
+        std::vector<int> fl(pos, 0);
+        for (int l = 0; l < 8; l++) {
+          offs[9 * k + l] = pos;
+          if (l < L) { for (int v : (*kinds[k])[l]) fl.push_back(v); pos += (int)(*kinds[k])[l].size(); }
+        }
+        offs[9 * k + 8] = pos;
+        if (k == which) flat = fl;
+      }
+      if (which < 0) put_int(o, offs.data(), 36);
+      else put_int(o, flat.data(), std::min(n, (int)flat.size()));
+      return 0;
+    }
     if (!std::strcmp(name, "dof_Mcnt") || !std::strcmp(name, "dof_anc")) {
       // flattened ancestor lists in the layout of qM: the tree recursions index them instead of chasing dof_parentid,
       // which turns a chain of dependent table loads per hop into independent, pipelinable ones
@@ -335,6 +378,7 @@ int configure_constraint_kernels(b2_batch* b) {
     if (b->prec == 8) {
       SA((const void*)k_collide<double, 128, 8>); SA((const void*)k_integrate<double, 128>);
       SA((const void*)k_integrate<double, 64>); SA((const void*)k_integrate<double, 32>);
+      SA((const void*)k_integrate<double, 128, 8>); SA((const void*)k_integrate<double, 128, 4>); SA((const void*)k_integrate<double, 128, 2>);
       SA((const void*)k_make_rows<double, 128, 8>); SA((const void*)k_make_blocks<double, 128>); SA((const void*)k_make_blocks<double, 32>);
       SA((const void*)k_pgs_block<double, 4, 32, PGS_MINB>); SA((const void*)k_pgs_block<double, 8, 32, PGS_MINB>);
       SA((const void*)k_pgs_block<double, 16, 32, PGS_MINB>); SA((const void*)k_pgs_block<double, 32, 32, PGS_MINB>);
@@ -343,6 +387,7 @@ int configure_constraint_kernels(b2_batch* b) {
     } else {
       SA((const void*)k_collide<float, 128, 8>); SA((const void*)k_integrate<float, 128>);
       SA((const void*)k_integrate<float, 64>); SA((const void*)k_integrate<float, 32>);
+      SA((const void*)k_integrate<float, 128, 8>); SA((const void*)k_integrate<float, 128, 4>); SA((const void*)k_integrate<float, 128, 2>);
       SA((const void*)k_make_rows<float, 128, 8>); SA((const void*)k_make_blocks<float, 128>); SA((const void*)k_make_blocks<float, 32>);
       SA((const void*)k_pgs_block<float, 4, 32, PGS_MINB>); SA((const void*)k_pgs_block<float, 8, 32, PGS_MINB>);
       SA((const void*)k_pgs_block<float, 16, 32, PGS_MINB>); SA((const void*)k_pgs_block<float, 32, 32, PGS_MINB>);
@@ -360,15 +405,16 @@ int configure_constraint_kernels(b2_batch* b) {
   return 0;
 }
 
-template <typename T, int BLOCK, typename P>
+template <typename T, int BLOCK, typename P, int L = 1>
 int launch_smooth(b2_batch* b, const KArgs<T>& a, int grid) {
   static bool attr_set[8] = {false};
   int dev = b->device & 7;
   if (!attr_set[dev]) {
-    CK(cudaFuncSetAttribute(k_smooth<T, BLOCK, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    constexpr int MB = L > 1 ? 3 : 1;   // tree-parallel form: three CTAs per SM (170 registers)
+    CK(cudaFuncSetAttribute(k_smooth<T, BLOCK, P, MB, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set[dev] = true;
   }
-  k_smooth<T, BLOCK, P><<<grid, BLOCK, b->smooth_smem, b->stream>>>(a);
+  k_smooth<T, BLOCK, P, (L > 1 ? 3 : 1), L><<<grid, BLOCK, b->smooth_smem, b->stream>>>(a);
   b->launches++;
   return 0;
 }
@@ -424,7 +470,7 @@ int run_tick(b2_batch* b, int flags) {
   const bool hwio = single && (flags & B2_TICK_HW) && b->hw_identity && (kf & B2F_CONTROLLER) && !(kf & B2F_ODOM) && !getenv("B2_NO_HWIO");
   if (hwio) kf |= B2F_HWIO;
   KArgs<T> a = make_args<T>(b, kf);
-  const int ntiles = b->nenvp / b->smooth_block;
+  const int ntiles = b->nenvp / (b->smooth_block / (b->chain_n > 0 ? 1 : b->tree_lanes));
   int per_sm = (int)std::max<size_t>(1, (227 * 1024) / std::max<size_t>(1, b->smooth_smem));
   if (getenv("B2_SMOOTH_CTAS_PER_SM")) per_sm = std::max(1, atoi(getenv("B2_SMOOTH_CTAS_PER_SM")));
   const int grid = std::max(1, std::min(ntiles, b->nsm * per_sm));
@@ -447,7 +493,12 @@ int run_tick(b2_batch* b, int flags) {
   prof_mark(b, SLOT_SMOOTH);
   if (b->chain_n > 0) rc = launch_chain<T>(b, a, grid);
   else switch (b->smooth_block) {
-    case 128: rc = launch_smooth<T, 128, GenericP>(b, a, grid); break;
+    case 128:
+      if (b->tree_lanes == 8) rc = launch_smooth<T, 128, GenericP, 8>(b, a, grid);
+      else if (b->tree_lanes == 4) rc = launch_smooth<T, 128, GenericP, 4>(b, a, grid);
+      else if (b->tree_lanes == 2) rc = launch_smooth<T, 128, GenericP, 2>(b, a, grid);
+      else rc = launch_smooth<T, 128, GenericP>(b, a, grid);
+      break;
     case 64: rc = launch_smooth<T, 64, GenericP>(b, a, grid); break;
     default: rc = launch_smooth<T, 32, GenericP>(b, a, grid); break;
   }
@@ -529,7 +580,15 @@ int run_tick(b2_batch* b, int flags) {
       else k_pgs_block<T, 8, PB, PGS_MINB><<<g3, PB, smp, b->stream>>>(a);
       }
       prof_mark(b, SLOT_INTEGRATE);
-      if (kf & B2F_LD_SMEM) {
+      const int TL = b->chain_n > 0 ? 1 : b->tree_lanes;
+      if (TL > 1) {
+        // tree-parallel: 128 threads = 128 / TL environments per CTA
+        const size_t smi = sm + ((kf & B2F_LD_SMEM) ? b->ld_smem : 0);
+        const int gi = std::max(1, std::min(b->nenvp / (128 / TL), b->nsm * 8));
+        if (TL == 8) k_integrate<T, 128, 8><<<gi, 128, smi, b->stream>>>(a);
+        else if (TL == 4) k_integrate<T, 128, 4><<<gi, 128, smi, b->stream>>>(a);
+        else k_integrate<T, 128, 2><<<gi, 128, smi, b->stream>>>(a);
+      } else if (kf & B2F_LD_SMEM) {
         const size_t smi = sm + b->ld_smem;
         const int bi = b->smooth_block, gi = std::max(1, std::min(b->nenvp / bi, b->nsm * 8));
         if (bi == 128) k_integrate<T, 128><<<gi, 128, smi, b->stream>>>(a);
@@ -974,7 +1033,42 @@ b2_batch* b2_create(const mjModel* m, int nenv, int device, int precision) {
   // shared-memory budget of the smooth kernel: 16 B barrier + model blob + workspace[ws_slots][BLOCK]
   b->blob_smem = 16 + (size_t)b->hdr.nwords * 4;
   const size_t budget = 200 * 1024;
+  // tree-parallel form of k_smooth / k_integrate: lanes per environment from the number of kinematic trees (an arm and four
+  // free props: 8 lanes, one tree each); single-tree models and register-resident chains stay one thread per environment
+  b->tree_lanes = 1;
+  if (b->chain_n == 0 && !getenv("B2_NO_TREE_LANES")) {
+    // lanes: enough to bring the heaviest lane down to about the heaviest tree (same cost proxy as the assignment in
+    // pack_model), a power of two <= 8
+    const int nt = b->hdr.ntree;
+    std::vector<long long> w(std::max(1, nt), 0);
+    long long tot = 0, mx = 1;
+    {
+      std::vector<int> root_tree(m->nbody, -1);
+      int ntr = 0;
+      for (int d = 0; d < m->nv; d++) { const int root = m->body_rootid[m->dof_bodyid[d]]; if (root_tree[root] < 0) root_tree[root] = ntr++; w[root_tree[root]] += 1; }
+      for (int i = 1; i < m->nbody; i++) if (lastdof_of(m, i) >= 0) w[root_tree[m->body_rootid[i]]] += 2;
+      for (int t = 0; t < nt; t++) { tot += w[t]; mx = std::max(mx, w[t]); }
+    }
+    const long long want = (tot + mx - 1) / mx;
+    // measured (B200, tools/gpurun_r2l.sh): the smooth kernel is register-bound (three 128-thread CTAs per SM), so more
+    // lanes mean more waves; 2 lanes for an arm + a few props (C3: smooth + integrate 0.49 -> 0.38 ms), 4 for a field of
+    // free bodies (C5: 1.95 -> 0.84 ms), never 8
+    b->tree_lanes = want >= 8 ? 4 : (want >= 2 ? 2 : 1);
+    if (getenv("B2_TREE_LANES")) { const int v = atoi(getenv("B2_TREE_LANES")); if (v == 1 || v == 2 || v == 4 || v == 8) b->tree_lanes = v; }
+  }
+  // (a kinematic tree standing on a static pedestal body would read a frame another lane computes: one lane then)
+  for (int i = 1; i < m->nbody && b->tree_lanes > 1; i++) {
+    const int pa = m->body_parentid[i];
+    if (pa > 0 && lastdof_of(m, i) >= 0 && lastdof_of(m, pa) < 0) b->tree_lanes = 1;
+  }
+  if (b->tree_lanes > 1 && upload_model(b) < 0) return bail("upload_model failed");   // the blob carries the per-lane item lists
+  const int TL = b->tree_lanes;
   int block = 0;
+  if (TL > 1) {
+    // 128 threads = 128 / TL environments per CTA: the workspace shrinks with it
+    const size_t need = b->blob_smem + (size_t)b->hdr.ws_slots * (128 / TL) * precision;
+    if (need <= budget) block = 128;
+  } else
   // a shared-memory workspace pays off only when at least two warps fit on an SM; below that the L2-resident HBM
   // workspace with four warps per SM is faster (measured on C3: 0.63 ms vs 0.95 ms, profiles/r01_ncu_c3_summary.txt)
   for (int cand : {128, 64}) {
@@ -991,17 +1085,18 @@ b2_batch* b2_create(const mjModel* m, int nenv, int device, int precision) {
     b->ws_global = false;
   } else if (block) {
     b->smooth_block = block;
-    b->smooth_smem = b->blob_smem + (size_t)b->hdr.ws_slots * block * precision;
+    b->smooth_smem = b->blob_smem + (size_t)b->hdr.ws_slots * (block / TL) * precision;
     b->ws_global = false;
   } else {
     b->smooth_block = 128;
     b->smooth_smem = b->blob_smem;
     b->ws_global = true;
-    // factor scratch in shared memory (B2F_LD_SMEM): (nM + 2 nv) words per thread, the widest CTA that leaves two CTAs per SM
+    // factor scratch in shared memory (B2F_LD_SMEM): (nM + 2 nv) words per environment, the widest CTA that leaves two CTAs per SM
     b->ld_smem = 0;
     if (!getenv("B2_NO_LD_SMEM"))
       for (int cand : {128, 64, 32}) {
-        const size_t need = b->blob_smem + (size_t)(b->hdr.nM + 2 * b->hdr.nv) * cand * precision;
+        if (TL > 1 && cand != 128) break;
+        const size_t need = b->blob_smem + (size_t)(b->hdr.nM + 2 * b->hdr.nv) * (cand / TL) * precision;
         if (need <= 110 * 1024) { b->smooth_block = cand; b->ld_smem = need - b->blob_smem; b->smooth_smem = need; break; }
       }
     if (alloc_field(b, "_ws", b->hdr.ws_slots, 0, nullptr) < 0) return bail("alloc failed");

@@ -32,6 +32,8 @@ namespace b2 {
   X(pair_geom1, I, npair) X(pair_geom2, I, npair)                                                              \
   X(odom_dof, I, 6 * nodom) X(odom_qpos, I, 3 * nodom)                                                          \
   X(body_treeid, I, nbody) X(dof_treeid, I, nv) X(tree_dofadr, I, ntree) X(tree_dofnum, I, ntree)              \
+  /* tree-parallel kernels: per-lane item lists (kind 0 body, 1 dof, 2 joint, 3 geom; lane_off[9 * kind + lane] .. [+ 1]) */ \
+  X(lane_off, I, 36) X(lane_body, I, nbody) X(lane_dof, I, nv) X(lane_jnt, I, njnt) X(lane_geom, I, ngeom)     \
   X(opt_real, F, 8) /* gravity[3], tolerance, meaninertia, impratio, 0, 0 in batch precision */
 
 // Workspace arrays (per environment, strided by the workspace stride): name, count expression

@@ -28,6 +28,9 @@ template <typename T>
 struct MV {
   const DModel* h;
   const uint32_t* w;
+  // tree-parallel kernels (k_smooth / k_integrate with several lanes per environment): this thread works on the
+  // kinematic trees t with t % nlanes == lane (static bodies: lane 0); nlanes == 1 is the thread-per-environment form
+  int lane = 0, nlanes = 1;
   __device__ __forceinline__ int i(int off, int k) const { return (int)w[off + k]; }
   __device__ __forceinline__ T f(int off, int k) const { return reinterpret_cast<const T*>(w + off)[k]; }
   __device__ __forceinline__ const T* fp(int off) const { return reinterpret_cast<const T*>(w + off); }

@@ -1704,12 +1704,12 @@ __global__ void __launch_bounds__(32, MINB) k_pgs_island(const KArgs<T> a) {
 }
 
 template <typename T>
-__device__ __forceinline__ void publish_obs(const KArgs<T>& a, int env) {
+__device__ __forceinline__ void publish_obs(const KArgs<T>& a, int env, int lane = 0, int nlanes = 1) {
   const DModel* hd = reinterpret_cast<const DModel*>(a.model);
   const int nq = hd->nq, nv = hd->nv;
   const long long S = a.nenvp;
   const long long base = (long long)a.obs_rank * (nq + nv) * a.obs_nenv + env;
-  for (int i = 0; i < nq + nv; i++) {
+  for (int i = lane; i < nq + nv; i += nlanes) {
     const float v = (float)(i < nq ? a.qpos[(long long)i * S + env] : a.qvel[(long long)(i - nq) * S + env]);
     for (int p = 0; p < a.obs_world; p++) a.obs_peers[p][base + (long long)i * a.obs_nenv] = v;
   }
@@ -1721,44 +1721,61 @@ __global__ void k_publish_obs(const KArgs<T> a) {
   if (env < a.nenv) publish_obs(a, env);
 }
 
-// G7: mj_checkAcc, semi-implicit Euler with implicit damping, odom override (one thread per environment)
-template <typename T, int BLOCK>
+// G7: mj_checkAcc, semi-implicit Euler with implicit damping, odom override, observation publish.  L lanes per
+// environment: lane l integrates the kinematic trees t with t % L == l (the damped factorisation M + h D is block
+// diagonal over trees like M itself); L = 1 is the thread-per-environment form.
+template <typename T, int BLOCK, int L = 1>
 __global__ void __launch_bounds__(BLOCK) k_integrate(const KArgs<T> a) {
   B2_KERNEL_PROLOGUE
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int env = tile * BLOCK + threadIdx.x;
+  (void)ntiles;
+  constexpr int EPB = BLOCK / L;
+  const int nteams = a.nenvp / EPB;
+  const int envl = threadIdx.x / L, lane = threadIdx.x % L;
+  const unsigned tmask = (L >= 32 ? 0xffffffffu : ((1u << L) - 1u)) << ((threadIdx.x & 31) & ~(L - 1));
+  m.lane = lane; m.nlanes = L;
+  for (int tile = blockIdx.x; tile < nteams; tile += gridDim.x) {
+    const int env = tile * EPB + envl;
     const int nv = h.nv;
     if ((a.flags & B2F_FUSABLE) && (a.status[env] & 8)) continue;
     SArr<T> qacc{a.qacc + env, S};
     bool bad = false;
-    for (int i = 0; i < nv; i++) bad |= !(t_abs(qacc[i]) < T(1e10));
+    for (int i = 0; i < nv; i++) bad |= !(t_abs(qacc[i]) < T(1e10));   // (every lane looks at the whole vector: one decision per environment)
     if (bad) {  // reset instead of integrating garbage
-      for (int i = 0; i < h.nq; i++) a.qpos[i * S + env] = m.f(h.o_qpos0, i);
-      for (int i = 0; i < nv; i++) { a.qvel[i * S + env] = 0; qacc[i] = 0; a.qacc_warmstart[i * S + env] = 0; a.qfrc_applied[i * S + env] = 0; }
-      a.time[env] = 0;
-      a.status[env] |= 4;
+      if (L > 1) __syncwarp(tmask);   // every lane has read qacc before anybody clears it
+      if (lane == 0) {
+        for (int i = 0; i < h.nq; i++) a.qpos[i * S + env] = m.f(h.o_qpos0, i);
+        for (int i = 0; i < nv; i++) { a.qvel[i * S + env] = 0; qacc[i] = 0; a.qacc_warmstart[i * S + env] = 0; a.qfrc_applied[i * S + env] = 0; }
+        a.time[env] = 0;
+        a.status[env] |= 4;
+      }
       continue;
     }
     if (a.flags & B2F_INTEGRATE) {
       SArr<T> qpos{a.qpos + env, S}, qvel{a.qvel + env, S}, qM{a.qM + env, S}, LD{a.qLD + env, S}, dinv{a.qLDiagInv + env, S};
       SArr<T> frc{a.qfrc_smooth + env, S}, xa{a.qacc_smooth + env, S};
       if (a.flags & B2F_LD_SMEM) {
-        // scratch of the damped factorisation (M + h D) in per-thread shared-memory columns instead of HBM arrays
+        // scratch of the damped factorisation (M + h D) in per-environment shared-memory columns instead of HBM arrays
         T* sc = reinterpret_cast<T*>(smem_raw + 16 + (size_t)nwords * 4);
-        LD = SArr<T>{sc + threadIdx.x, BLOCK};
-        dinv = SArr<T>{sc + (size_t)h.nM * BLOCK + threadIdx.x, BLOCK};
-        xa = SArr<T>{sc + (size_t)(h.nM + nv) * BLOCK + threadIdx.x, BLOCK};
+        LD = SArr<T>{sc + envl, EPB};
+        dinv = SArr<T>{sc + (size_t)h.nM * EPB + envl, EPB};
+        xa = SArr<T>{sc + (size_t)(h.nM + nv) * EPB + envl, EPB};
       }
       // qfrc_smooth becomes the total force of the implicit-damping solve; qLD / qLDiagInv / qacc_smooth are dead after
       // the solver and serve as scratch for the damped factorisation
-      if (h.has_damping) for (int i = 0; i < nv; i++) frc[i] += a.qfrc_constraint[i * S + env];
+      if (h.has_damping) for (int k_ = GenericP::dof_lo(m); k_ < GenericP::dof_hi(m); k_++) { const int i = GenericP::dof_at(m, k_); frc[i] += a.qfrc_constraint[i * S + env]; }
       euler_step<GenericP>(m, qpos, qvel, qM, qacc, frc, a.h, LD, dinv, xa);
-      a.time[env] += a.h;
-      if (a.flags & B2F_ODOM) odom_override(m, a, env);
+      if (L > 1) __syncwarp(tmask);
+      if (lane == 0) {
+        a.time[env] += a.h;
+        if (a.flags & B2F_ODOM) odom_override(m, a, env);
+      }
       // observation exchange fused into the integrate epilogue: the new state goes straight into slice `rank` of every
       // GPU's observation buffer (plain stores through the NVLink peer mappings: fire-and-forget, one 128-byte line per
-      // element and warp).  No pack kernel, no collective call.
-      if ((a.flags & B2F_OBS) && env < a.nenv) publish_obs(a, env);
+      // element and warp in the thread-per-environment form).  No pack kernel, no collective call.
+      if ((a.flags & B2F_OBS) && env < a.nenv) {
+        if (L > 1 && (a.flags & B2F_ODOM)) __syncwarp(tmask);
+        publish_obs(a, env, lane, L);
+      }
     }
   }
 }

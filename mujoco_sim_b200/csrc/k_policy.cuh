@@ -27,6 +27,14 @@ struct GenericP {
   B2_TAB(jnt_dofadr) B2_TAB(jnt_bodyid) B2_TAB(jnt_limited) B2_TAB(dof_bodyid) B2_TAB(dof_parentid) B2_TAB(dof_Madr)
   B2_TAB(dof_controlled) B2_TAB(dof_Mcnt) B2_TAB(dof_anc)
 #undef B2_TAB
+  // this lane's bodies (>= 1; static bodies belong to lane 0) / dofs / joints / geoms: positions [lo, hi) of the per-lane
+  // lists of the model blob, ascending (parents before children).  One lane per environment: the identity.
+#define B2_LANE(kind, idx, first, count, list)                                                                              \
+  template <typename T> static __device__ __forceinline__ int kind##_lo(const MV<T>& m) { return m.nlanes == 1 ? (first) : m.i(m.h->o_lane_off, 9 * (idx) + m.lane); } \
+  template <typename T> static __device__ __forceinline__ int kind##_hi(const MV<T>& m) { return m.nlanes == 1 ? m.h->count : m.i(m.h->o_lane_off, 9 * (idx) + m.lane + 1); } \
+  template <typename T> static __device__ __forceinline__ int kind##_at(const MV<T>& m, int k) { return m.nlanes == 1 ? k : m.i(m.h->o_##list, k); }
+  B2_LANE(body, 0, 1, nbody, lane_body) B2_LANE(dof, 1, 0, nv, lane_dof) B2_LANE(jnt, 2, 0, njnt, lane_jnt) B2_LANE(geom, 3, 0, ngeom, lane_geom)
+#undef B2_LANE
   template <typename T> static __device__ __forceinline__ int nbody(const MV<T>& m) { return m.h->nbody; }
   template <typename T> static __device__ __forceinline__ int njnt(const MV<T>& m) { return m.h->njnt; }
   template <typename T> static __device__ __forceinline__ int nv(const MV<T>& m) { return m.h->nv; }
@@ -58,6 +66,18 @@ struct ChainP {  // world -> body 1 -> ... -> body N, body b carries scalar join
   template <typename T> static __device__ __forceinline__ int dof_Madr(const MV<T>&, int i) { return i * (i + 1) / 2; }
   template <typename T> static __device__ __forceinline__ int dof_Mcnt(const MV<T>&, int i) { return i + 1; }
   template <typename T> static __device__ __forceinline__ int dof_controlled(const MV<T>& m, int i) { return m.i(m.h->o_dof_controlled, i); }
+  template <typename T> static __device__ __forceinline__ int body_lo(const MV<T>&) { return 1; }
+  template <typename T> static __device__ __forceinline__ int body_hi(const MV<T>&) { return NBODY; }
+  template <typename T> static __device__ __forceinline__ int body_at(const MV<T>&, int k) { return k; }
+  template <typename T> static __device__ __forceinline__ int dof_lo(const MV<T>&) { return 0; }
+  template <typename T> static __device__ __forceinline__ int dof_hi(const MV<T>&) { return NV; }
+  template <typename T> static __device__ __forceinline__ int dof_at(const MV<T>&, int k) { return k; }
+  template <typename T> static __device__ __forceinline__ int jnt_lo(const MV<T>&) { return 0; }
+  template <typename T> static __device__ __forceinline__ int jnt_hi(const MV<T>&) { return NJNT; }
+  template <typename T> static __device__ __forceinline__ int jnt_at(const MV<T>&, int k) { return k; }
+  template <typename T> static __device__ __forceinline__ int geom_lo(const MV<T>&) { return 0; }
+  template <typename T> static __device__ __forceinline__ int geom_hi(const MV<T>& m) { return m.h->ngeom; }
+  template <typename T> static __device__ __forceinline__ int geom_at(const MV<T>&, int k) { return k; }
   template <typename T> static __device__ __forceinline__ int nbody(const MV<T>&) { return NBODY; }
   template <typename T> static __device__ __forceinline__ int njnt(const MV<T>&) { return NJNT; }
   template <typename T> static __device__ __forceinline__ int nv(const MV<T>&) { return NV; }

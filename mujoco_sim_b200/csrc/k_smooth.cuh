@@ -12,13 +12,48 @@
 
 namespace b2 {
 
+// Which lane of an environment's team works on a dof / body / joint (see MV::lane): kinematic trees are independent
+// in every stage of the smooth dynamics (M is block diagonal over them), so the lanes never exchange data.
+template <typename P, typename T>
+__device__ __forceinline__ bool own_tree(const MV<T>& m, int t) {
+  if constexpr (P::STATIC) return true;
+  else return m.nlanes == 1 || (t < 0 ? 0 : t % m.nlanes) == m.lane;
+}
+template <typename P, typename T>
+__device__ __forceinline__ bool own_dof(const MV<T>& m, int i) {
+  if constexpr (P::STATIC) return true;
+  else return m.nlanes == 1 || own_tree<P>(m, m.i(m.h->o_dof_treeid, i));
+}
+template <typename P, typename T>
+__device__ __forceinline__ bool own_body(const MV<T>& m, int b) {
+  if constexpr (P::STATIC) return true;
+  else return m.nlanes == 1 || own_tree<P>(m, m.i(m.h->o_body_treeid, b));
+}
+// forward kinematics only: static bodies (no tree) are placed by EVERY lane, redundantly and identically, because a tree
+// rooted on a static pedestal reads its parent's frame and the lanes do not synchronise inside the position stage
+template <typename P, typename T>
+__device__ __forceinline__ bool own_body_kin(const MV<T>& m, int b) {
+  if constexpr (P::STATIC) return true;
+  else {
+    if (m.nlanes == 1) return true;
+    const int t = m.i(m.h->o_body_treeid, b);
+    return t < 0 || t % m.nlanes == m.lane;
+  }
+}
+template <typename P, typename T>
+__device__ __forceinline__ bool own_jnt(const MV<T>& m, int j) {
+  if constexpr (P::STATIC) return true;
+  else return m.nlanes == 1 || own_body<P>(m, P::jnt_bodyid(m, j));
+}
+
 // in-place sparse LtDL factorisation of the matrix stored in LD (tree order), dinv = 1 / D  (mj_factorM, A.4)
 template <typename P, typename T, typename A1, typename A2>
 __device__ __forceinline__ void ld_factor(const MV<T>& m, const A1& LD, const A2& dinv) {
   if constexpr (!P::STATIC) {
     // generic trees: the rows of M list a dof and its ancestors in order (dof_anc), so the ancestors of the a-th ancestor
     // of k are the entries a.. of row k: no dof_parentid chasing, the inner loop is a plain axpy of known length
-    for (int k = P::nv(m) - 1; k >= 0; k--) {
+    for (int k_ = P::dof_hi(m) - 1; k_ >= P::dof_lo(m); k_--) {
+      const int k = P::dof_at(m, k_);
       const int Mkk = P::dof_Madr(m, k), cnt = P::dof_Mcnt(m, k);
       const T inv = T(1) / LD[Mkk];
       for (int a = 1; a < cnt; a++) {
@@ -52,14 +87,16 @@ template <typename P, typename T, typename A1, typename A2, typename A3>
 __device__ __forceinline__ void ld_solve(const MV<T>& m, const A1& LD, const A2& dinv, const A3& x) {
   const int nv = P::nv(m);
   if constexpr (!P::STATIC) {
-    for (int i = nv - 1; i >= 0; i--) {
+    for (int k_ = P::dof_hi(m) - 1; k_ >= P::dof_lo(m); k_--) {
+      const int i = P::dof_at(m, k_);
       const T xi = x[i];
       if (xi == 0) continue;
       const int adr = P::dof_Madr(m, i), cnt = P::dof_Mcnt(m, i);
       for (int a = 1; a < cnt; a++) x[P::dof_anc(m, adr + a)] -= LD[adr + a] * xi;
     }
-    for (int i = 0; i < nv; i++) x[i] *= dinv[i];
-    for (int i = 0; i < nv; i++) {
+    for (int k_ = P::dof_lo(m); k_ < P::dof_hi(m); k_++) { const int i = P::dof_at(m, k_); x[i] *= dinv[i]; }
+    for (int k_ = P::dof_lo(m); k_ < P::dof_hi(m); k_++) {
+      const int i = P::dof_at(m, k_);
       const int adr = P::dof_Madr(m, i), cnt = P::dof_Mcnt(m, i);
       T xi = x[i];
       for (int a = 1; a < cnt; a++) xi -= LD[adr + a] * x[P::dof_anc(m, adr + a)];
@@ -96,21 +133,33 @@ __device__ __forceinline__ void euler_step(const MV<T>& m, const AQ& qpos, const
   const bool damp = h.has_damping && !(h.disableflags & DSBL_EULERDAMP);
   if (damp) {
 #pragma unroll(P::UNROLL)
-    for (int i = 0; i < P::nM(m); i++) LDtmp[i] = qM[i];
+    for (int i = 0; i < P::nM(m); i++) {
+      if constexpr (P::STATIC) LDtmp[i] = qM[i];
+      else if (m.nlanes == 1) LDtmp[i] = qM[i];
+    }
+    if constexpr (!P::STATIC) {
+      if (m.nlanes > 1)
+        for (int k_ = P::dof_lo(m); k_ < P::dof_hi(m); k_++) {   // this lane's rows of M only
+          const int i = P::dof_at(m, k_);
+          const int adr = P::dof_Madr(m, i), cnt = P::dof_Mcnt(m, i);
+          for (int a = 0; a < cnt; a++) LDtmp[adr + a] = qM[adr + a];
+        }
+    }
 #pragma unroll(P::UNROLL)
-    for (int i = 0; i < nv; i++) LDtmp[P::dof_Madr(m, i)] += hs * m.f(h.o_dof_damping, i);
+    for (int k_ = P::dof_lo(m); k_ < P::dof_hi(m); k_++) { const int i = P::dof_at(m, k_); LDtmp[P::dof_Madr(m, i)] += hs * m.f(h.o_dof_damping, i); }
     ld_factor<P>(m, LDtmp, dinvtmp);
 #pragma unroll(P::UNROLL)
-    for (int i = 0; i < nv; i++) xa[i] = frc[i];
+    for (int k_ = P::dof_lo(m); k_ < P::dof_hi(m); k_++) { const int i = P::dof_at(m, k_); xa[i] = frc[i]; }
     ld_solve<P>(m, LDtmp, dinvtmp, xa);
   } else {
 #pragma unroll(P::UNROLL)
-    for (int i = 0; i < nv; i++) xa[i] = qacc_in[i];
+    for (int k_ = P::dof_lo(m); k_ < P::dof_hi(m); k_++) { const int i = P::dof_at(m, k_); xa[i] = qacc_in[i]; }
   }
 #pragma unroll(P::UNROLL)
-  for (int i = 0; i < nv; i++) qvel[i] += hs * xa[i];
+  for (int k_ = P::dof_lo(m); k_ < P::dof_hi(m); k_++) { const int i = P::dof_at(m, k_); qvel[i] += hs * xa[i]; }
 #pragma unroll(P::UNROLL)
-  for (int j = 0; j < P::njnt(m); j++) {
+  for (int k_ = P::jnt_lo(m); k_ < P::jnt_hi(m); k_++) {
+    const int j = P::jnt_at(m, k_);
     const int qa = P::jnt_qposadr(m, j), da = P::jnt_dofadr(m, j), jt = P::jnt_type(m, j);
     if (!P::STATIC && (jt == JNT_FREE || jt == JNT_BALL)) {
       int qo = qa, dofo = da;
@@ -187,7 +236,8 @@ struct Smooth {
       st<T, 3>(xpos, 0, z3); st<T, 4>(xquat, 0, q1); st<T, 9>(xmat, 0, I); st<T, 3>(xipos, 0, z3); st<T, 9>(ximat, 0, I);
     }
 #pragma unroll(P::UNROLL)
-    for (int b = 1; b < nb; b++) {
+    for (int k_ = P::body_lo(m); k_ < P::body_hi(m); k_++) {
+      const int b = P::body_at(m, k_);
       const int p = P::body_parentid(m, b), jn = P::body_jntnum(m, b), ja = P::body_jntadr(m, b);
       T pos[3], quat[4];
       if (!P::STATIC && jn == 1 && P::jnt_type(m, ja) == JNT_FREE) {
@@ -265,7 +315,8 @@ struct Smooth {
   // are re-read from their exported HBM copies because the body index of a geom is a run-time value
   __device__ void geoms(int env) {
     const long long S = a.nenvp;
-    for (int g = 0; g < h.ngeom; g++) {
+    for (int k_ = P::geom_lo(m); k_ < P::geom_hi(m); k_++) {
+      const int g = P::geom_at(m, k_);
       const int b = m.i(h.o_geom_bodyid, g);
       T gp[3], gq[4], bm[9], bp[3], bq[4], r[3], q[4], gm[9];
       ldm<T, 3>(gp, m, h.o_geom_pos, 3 * g);
@@ -284,25 +335,34 @@ struct Smooth {
   // ---- CoM-based quantities (A.3) ----
   __device__ __forceinline__ void com_pos() {
     const int nb = P::nbody(m);
+    const bool team = !P::STATIC && m.nlanes > 1;
+    // (tree-parallel form: the world body's total is not needed by any stage and would be a cross-lane sum; the kernel
+    //  fills it in afterwards, for the exported array)
+    if (!team) { const T mass = m.f(h.o_body_mass, 0); for (int k = 0; k < 3; k++) subtree_com[k] = mass * xipos[k]; }
 #pragma unroll(P::UNROLL)
-    for (int b = 0; b < nb; b++) {
+    for (int k_ = P::body_lo(m); k_ < P::body_hi(m); k_++) {
+      const int b = P::body_at(m, k_);
       const T mass = m.f(h.o_body_mass, b);
       for (int k = 0; k < 3; k++) subtree_com[3 * b + k] = mass * xipos[3 * b + k];
     }
 #pragma unroll(P::UNROLL)
-    for (int b = nb - 1; b > 0; b--) {
+    for (int k_ = P::body_hi(m) - 1; k_ >= P::body_lo(m); k_--) {
+      const int b = P::body_at(m, k_);
       const int p = P::body_parentid(m, b);
+      if (team && p == 0) continue;
       for (int k = 0; k < 3; k++) subtree_com[3 * p + k] += subtree_com[3 * b + k];
     }
 #pragma unroll(P::UNROLL)
-    for (int b = 0; b < nb; b++) {
+    for (int k_ = P::body_lo(m) - (team ? 0 : 1); k_ < P::body_hi(m); k_++) {
+      const int b = k_ < P::body_lo(m) ? 0 : P::body_at(m, k_);
       const T sm = m.f(h.o_body_subtreemass, b);
       if (sm < Eps<T>::minval()) { for (int k = 0; k < 3; k++) subtree_com[3 * b + k] = xipos[3 * b + k]; }
       else { const T inv = T(1) / sm; for (int k = 0; k < 3; k++) subtree_com[3 * b + k] *= inv; }
     }
     for (int k = 0; k < 10; k++) cinert[k] = 0;
 #pragma unroll(P::UNROLL)
-    for (int b = 1; b < nb; b++) {
+    for (int k_ = P::body_lo(m); k_ < P::body_hi(m); k_++) {
+      const int b = P::body_at(m, k_);
       const int root = P::body_rootid(m, b);
       T dif[3], mat[9], inert[3], tmp[6];
       for (int k = 0; k < 3; k++) dif[k] = xipos[3 * b + k] - subtree_com[3 * root + k];
@@ -338,7 +398,8 @@ struct Smooth {
       st<T, 10>(cinert, 10 * b, ci);
     }
 #pragma unroll(P::UNROLL)
-    for (int j = 0; j < P::njnt(m); j++) {
+    for (int k_ = P::jnt_lo(m); k_ < P::jnt_hi(m); k_++) {
+      const int j = P::jnt_at(m, k_);
       const int bi = P::jnt_bodyid(m, j), da = P::jnt_dofadr(m, j), jt = P::jnt_type(m, j);
       const int root = P::body_rootid(m, bi);
       T off[3];
@@ -374,14 +435,19 @@ struct Smooth {
   __device__ __forceinline__ void crb_mass() {
     const int nb = P::nbody(m), nvv = P::nv(m);
 #pragma unroll(P::UNROLL)
-    for (int i = 0; i < 10 * nb; i++) crb[i] = cinert[i];
+    for (int k_ = P::body_lo(m) - 1; k_ < P::body_hi(m); k_++) {
+      const int b = k_ < P::body_lo(m) ? 0 : P::body_at(m, k_);
+      for (int k = 0; k < 10; k++) crb[10 * b + k] = cinert[10 * b + k];
+    }
 #pragma unroll(P::UNROLL)
-    for (int b = nb - 1; b > 0; b--) {
+    for (int k_ = P::body_hi(m) - 1; k_ >= P::body_lo(m); k_--) {
+      const int b = P::body_at(m, k_);
       const int p = P::body_parentid(m, b);
       if (p > 0) for (int k = 0; k < 10; k++) crb[10 * p + k] += crb[10 * b + k];
     }
 #pragma unroll(P::UNROLL)
-    for (int i = 0; i < nvv; i++) {
+    for (int k_ = P::dof_lo(m); k_ < P::dof_hi(m); k_++) {
+      const int i = P::dof_at(m, k_);
       int adr = P::dof_Madr(m, i);
       T ci[10], cd[6], buf[6];
       ld<T, 10>(ci, crb, 10 * P::dof_bodyid(m, i));
@@ -415,9 +481,10 @@ struct Smooth {
   __device__ __forceinline__ void mul_M(const AR& res, const AV& vec) {
     const int nvv = P::nv(m);
 #pragma unroll(P::UNROLL)
-    for (int i = 0; i < nvv; i++) res[i] = 0;
+    for (int k_ = P::dof_lo(m); k_ < P::dof_hi(m); k_++) { const int i = P::dof_at(m, k_); res[i] = 0; }
 #pragma unroll(P::UNROLL)
-    for (int i = 0; i < nvv; i++) {
+    for (int k_ = P::dof_lo(m); k_ < P::dof_hi(m); k_++) {
+      const int i = P::dof_at(m, k_);
       int adr = P::dof_Madr(m, i);
       const T vi = vec[i];
       T ri = res[i] + qM[adr] * vi;
@@ -447,7 +514,8 @@ struct Smooth {
   __device__ __forceinline__ void com_vel() {
     for (int k = 0; k < 6; k++) cvel[k] = 0;
 #pragma unroll(P::UNROLL)
-    for (int b = 1; b < P::nbody(m); b++) {
+    for (int k_ = P::body_lo(m); k_ < P::body_hi(m); k_++) {
+      const int b = P::body_at(m, k_);
       T cv[6];
       ld<T, 6>(cv, cvel, 6 * P::body_parentid(m, b));
       const int ja = P::body_jntadr(m, b), jn = P::body_jntnum(m, b);
@@ -507,11 +575,12 @@ struct Smooth {
   __device__ __forceinline__ void passive() {
     const int nvv = P::nv(m);
 #pragma unroll(P::UNROLL)
-    for (int i = 0; i < nvv; i++) qfrc_passive[i] = 0;
+    for (int k_ = P::dof_lo(m); k_ < P::dof_hi(m); k_++) { const int i = P::dof_at(m, k_); qfrc_passive[i] = 0; }
     if (h.disableflags & DSBL_PASSIVE) return;
     if (h.has_stiffness) {
 #pragma unroll(P::UNROLL)
-      for (int j = 0; j < P::njnt(m); j++) {
+      for (int k_ = P::jnt_lo(m); k_ < P::jnt_hi(m); k_++) {
+        const int j = P::jnt_at(m, k_);
         const T k = m.f(h.o_jnt_stiffness, j);
         if (k == 0) continue;
         const int qa = P::jnt_qposadr(m, j), da = P::jnt_dofadr(m, j), jt = P::jnt_type(m, j);
@@ -534,13 +603,14 @@ struct Smooth {
     }
     if (h.has_damping) {
 #pragma unroll(P::UNROLL)
-      for (int i = 0; i < nvv; i++) qfrc_passive[i] -= m.f(h.o_dof_damping, i) * qvel[i];
+      for (int k_ = P::dof_lo(m); k_ < P::dof_hi(m); k_++) { const int i = P::dof_at(m, k_); qfrc_passive[i] -= m.f(h.o_dof_damping, i) * qvel[i]; }
     }
     // gravity compensation: the reference sets gravcomp="1" on every robot body by default
     // (src/mujoco_sim/mj_sim.cpp:301-310, src/config/robot.yaml:19)
     if (h.has_gravcomp && !(h.disableflags & DSBL_GRAVITY)) {
 #pragma unroll(P::UNROLL)
-      for (int b = 1; b < P::nbody(m); b++) {
+      for (int k_ = P::body_lo(m); k_ < P::body_hi(m); k_++) {
+        const int b = P::body_at(m, k_);
         const T gc = m.f(h.o_body_gravcomp, b);
         if (gc == 0) continue;
         const T s = -m.f(h.o_body_mass, b) * gc;
@@ -560,7 +630,8 @@ struct Smooth {
     cacc[3] = grav ? -m.f(h.o_opt_real, 0) : T(0); cacc[4] = grav ? -m.f(h.o_opt_real, 1) : T(0); cacc[5] = grav ? -m.f(h.o_opt_real, 2) : T(0);
     for (int k = 0; k < 6; k++) cfrc[k] = 0;
 #pragma unroll(P::UNROLL)
-    for (int b = 1; b < nb; b++) {
+    for (int k_ = P::body_lo(m); k_ < P::body_hi(m); k_++) {
+      const int b = P::body_at(m, k_);
       T ac[6], ci[10], cv[6], Ia[6], Iv[6], x[6];
       ld<T, 6>(ac, cacc, 6 * P::body_parentid(m, b));
       const int da = P::body_dofadr(m, b), dn = P::body_dofnum(m, b);
@@ -582,12 +653,14 @@ struct Smooth {
       for (int r = 0; r < 6; r++) cfrc[6 * b + r] = Ia[r] + x[r];
     }
 #pragma unroll(P::UNROLL)
-    for (int b = nb - 1; b > 0; b--) {
+    for (int k_ = P::body_hi(m) - 1; k_ >= P::body_lo(m); k_--) {
+      const int b = P::body_at(m, k_);
       const int p = P::body_parentid(m, b);
       if (p > 0) for (int r = 0; r < 6; r++) cfrc[6 * p + r] += cfrc[6 * b + r];
     }
 #pragma unroll(P::UNROLL)
-    for (int i = 0; i < nvv; i++) {
+    for (int k_ = P::dof_lo(m); k_ < P::dof_hi(m); k_++) {
+      const int i = P::dof_at(m, k_);
       const int b = P::dof_bodyid(m, i);
       T s = 0;
       for (int r = 0; r < 6; r++) s += cdof[6 * i + r] * cfrc[6 * b + r];
@@ -619,8 +692,11 @@ __device__ void odom_override(const MV<T>& m, const KArgs<T>& a, int env) {
   }
 }
 
-// ---- the kernel: persistent CTAs, one thread per environment ----
-template <typename T, int BLOCK, typename P, int MINB = 1>
+// ---- the kernel: persistent CTAs; L lanes per environment (L = 1: one thread per environment).  With L > 1 lane l works
+//      on the kinematic trees t with t % L == l (own_tree): the trees of an environment are independent in every stage,
+//      so an arm and the free objects around it are processed side by side and the per-environment serial chain shrinks
+//      to its largest tree ----
+template <typename T, int BLOCK, typename P, int MINB = 1, int L = 1>
 __global__ void __launch_bounds__(BLOCK, MINB) k_smooth(const KArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
@@ -632,12 +708,17 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_smooth(const KArgs<T> a) {
   T* ws_sh = reinterpret_cast<T*>(smem_raw + 16 + (size_t)nwords * 4);
   const int nv = P::nv(m), nb = P::nbody(m), nq = P::nq(m), nM = P::nM(m);
   const long long S = a.nenvp;
-  const int ntiles = a.nenvp / BLOCK;
+  static_assert(L == 1 || !P::STATIC, "the register-resident chain policy is one thread per environment");
+  constexpr int EPB = BLOCK / L;
+  const int ntiles = a.nenvp / EPB;
+  const int envl = threadIdx.x / L, lane = threadIdx.x % L;
+  const unsigned tmask = (L >= 32 ? 0xffffffffu : ((1u << L) - 1u)) << ((threadIdx.x & 31) & ~(L - 1));
+  m.lane = lane; m.nlanes = L;
 
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int env = tile * BLOCK + threadIdx.x;
-    T* wsbase = (a.flags & B2F_WS_GLOBAL) ? a.ws + env : ws_sh + threadIdx.x;
-    const long long wss = (a.flags & B2F_WS_GLOBAL) ? S : BLOCK;
+    const int env = tile * EPB + envl;
+    T* wsbase = (a.flags & B2F_WS_GLOBAL) ? a.ws + env : ws_sh + envl;
+    const long long wss = (a.flags & B2F_WS_GLOBAL) ? S : EPB;
     Smooth<T, P> s(m, a, wsbase, wss, env);
     SArr<T> qfrc_inverse{a.qfrc_inverse + env, S};
 
@@ -664,6 +745,17 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_smooth(const KArgs<T> a) {
     // position stage
     s.kinematics(env);
     s.com_pos();
+    if (L > 1) {
+      // the world body's subtree centre of mass (exported only): the one cross-tree sum, by lane 0 once every lane's
+      // inertial frame positions are in the workspace
+      __syncwarp(tmask);
+      if (lane == 0) {
+        T c[3] = {0, 0, 0};
+        for (int b = 0; b < nb; b++) { const T mass = m.f(h.o_body_mass, b); for (int k2 = 0; k2 < 3; k2++) c[k2] += mass * s.xipos[3 * b + k2]; }
+        const T sm = m.f(h.o_body_subtreemass, 0);
+        for (int k2 = 0; k2 < 3; k2++) s.subtree_com[k2] = sm < Eps<T>::minval() ? s.xipos[k2] : c[k2] / sm;
+      }
+    }
     s.crb_mass();
     // L^T D L.  With the workspace in HBM the O(sum depth^2) read-modify-writes of the elimination would each be an L2
     // round trip: the factor is built in a per-thread shared-memory column instead and written out once (B2F_LD_SMEM).
@@ -671,16 +763,32 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_smooth(const KArgs<T> a) {
     if constexpr (!P::STATIC) ldsm = (a.flags & B2F_LD_SMEM) != 0;
     if constexpr (!P::STATIC) {
       if (ldsm) {
-        SArr<T> LDs{ws_sh + threadIdx.x, BLOCK}, dis{ws_sh + (size_t)nM * BLOCK + threadIdx.x, BLOCK};
-        for (int i = 0; i < nM; i++) LDs[i] = s.qM[i];
+        SArr<T> LDs{ws_sh + envl, EPB}, dis{ws_sh + (size_t)nM * EPB + envl, EPB};
+        for (int k_ = P::dof_lo(m); k_ < P::dof_hi(m); k_++) {
+          const int i = P::dof_at(m, k_);
+          const int adr = P::dof_Madr(m, i), cnt = P::dof_Mcnt(m, i);
+          for (int q2 = 0; q2 < cnt; q2++) LDs[adr + q2] = s.qM[adr + q2];
+        }
         ld_factor<P>(m, LDs, dis);
-        for (int i = 0; i < nM; i++) s.qLD[i] = LDs[i];
-        for (int i = 0; i < nv; i++) s.qLDiagInv[i] = dis[i];
+        for (int k_ = P::dof_lo(m); k_ < P::dof_hi(m); k_++) {
+          const int i = P::dof_at(m, k_);
+          const int adr = P::dof_Madr(m, i), cnt = P::dof_Mcnt(m, i);
+          for (int q2 = 0; q2 < cnt; q2++) s.qLD[adr + q2] = LDs[adr + q2];
+          s.qLDiagInv[i] = dis[i];
+        }
       }
     }
     if (!ldsm) {
+      if constexpr (P::STATIC) {
 #pragma unroll(P::UNROLL)
-      for (int i = 0; i < nM; i++) s.qLD[i] = s.qM[i];
+        for (int i = 0; i < nM; i++) s.qLD[i] = s.qM[i];
+      } else {
+        for (int k_ = P::dof_lo(m); k_ < P::dof_hi(m); k_++) {
+          const int i = P::dof_at(m, k_);
+          const int adr = P::dof_Madr(m, i), cnt = P::dof_Mcnt(m, i);
+          for (int q2 = 0; q2 < cnt; q2++) s.qLD[adr + q2] = s.qM[adr + q2];
+        }
+      }
       ld_factor<P>(m, s.qLD, s.qLDiagInv);
     }
     // velocity stage
@@ -699,7 +807,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_smooth(const KArgs<T> a) {
       }
       s.mul_M(s.tmpv, ddq);
 #pragma unroll(P::UNROLL)
-      for (int i = 0; i < nv; i++) {
+      for (int k_ = P::dof_lo(m); k_ < P::dof_hi(m); k_++) {
+        const int i = P::dof_at(m, k_);
         T tau = s.tmpv[i];
         if (P::dof_controlled(m, i)) tau += s.qfrc_bias[i];
         s.qfrc_applied[i] = tau;
@@ -717,7 +826,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_smooth(const KArgs<T> a) {
       // mj_inverse collapses to one sparse mat-vec with the CRBA matrix already at hand
       s.mul_M(s.tmpv, s.qacc);
 #pragma unroll(P::UNROLL)
-      for (int i = 0; i < nv; i++) qfrc_inverse[i] = s.tmpv[i] + s.qfrc_bias[i] - s.qfrc_passive[i];
+      for (int k_ = P::dof_lo(m); k_ < P::dof_hi(m); k_++) { const int i = P::dof_at(m, k_); qfrc_inverse[i] = s.tmpv[i] + s.qfrc_bias[i] - s.qfrc_passive[i]; }
     }
     if (P::STATIC) {
 #pragma unroll(P::UNROLL)
@@ -726,11 +835,12 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_smooth(const KArgs<T> a) {
 
     // smooth acceleration
 #pragma unroll(P::UNROLL)
-    for (int i = 0; i < nv; i++) s.qfrc_smooth[i] = s.qfrc_passive[i] - s.qfrc_bias[i] + s.qfrc_applied[i];
+    for (int k_ = P::dof_lo(m); k_ < P::dof_hi(m); k_++) { const int i = P::dof_at(m, k_); s.qfrc_smooth[i] = s.qfrc_passive[i] - s.qfrc_bias[i] + s.qfrc_applied[i]; }
     if (a.flags & B2F_XFRC) {
       SArr<T> xf{a.xfrc_applied + env, S};
 #pragma unroll(P::UNROLL)
-      for (int b = 1; b < nb; b++) {
+      for (int k_ = P::body_lo(m); k_ < P::body_hi(m); k_++) {
+        const int b = P::body_at(m, k_);
         T w[6], pt[3];
         ld<T, 6>(w, xf, 6 * b);
         if (w[0] == 0 && w[1] == 0 && w[2] == 0 && w[3] == 0 && w[4] == 0 && w[5] == 0) continue;
@@ -739,10 +849,10 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_smooth(const KArgs<T> a) {
       }
     }
 #pragma unroll(P::UNROLL)
-    for (int i = 0; i < nv; i++) s.qacc_smooth[i] = s.qfrc_smooth[i];
+    for (int k_ = P::dof_lo(m); k_ < P::dof_hi(m); k_++) { const int i = P::dof_at(m, k_); s.qacc_smooth[i] = s.qfrc_smooth[i]; }
     if constexpr (!P::STATIC) {
       if (ldsm) {   // the factor is still in the shared-memory column
-        SArr<T> LDs{ws_sh + threadIdx.x, BLOCK}, dis{ws_sh + (size_t)nM * BLOCK + threadIdx.x, BLOCK};
+        SArr<T> LDs{ws_sh + envl, EPB}, dis{ws_sh + (size_t)nM * EPB + envl, EPB};
         ld_solve<P>(m, LDs, dis, s.qacc_smooth);
       }
     }
@@ -751,9 +861,11 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_smooth(const KArgs<T> a) {
     // body poses for the ROS layer (tf / marker publishers read d->xpos, d->xquat: SURVEY.md Appendix C)
     if (!s.aliased) {
 #pragma unroll(P::UNROLL)
-      for (int i = 0; i < 3 * nb; i++) a.xpos[i * S + env] = s.xpos[i];
-#pragma unroll(P::UNROLL)
-      for (int i = 0; i < 4 * nb; i++) a.xquat[i * S + env] = s.xquat[i];
+      for (int k_ = P::body_lo(m) - 1; k_ < P::body_hi(m); k_++) {
+        const int b = k_ < P::body_lo(m) ? 0 : P::body_at(m, k_);   // (the world body: written by every lane, identically)
+        for (int k = 0; k < 3; k++) a.xpos[(long long)(3 * b + k) * S + env] = s.xpos[3 * b + k];
+        for (int k = 0; k < 4; k++) a.xquat[(long long)(4 * b + k) * S + env] = s.xquat[4 * b + k];
+      }
     }
 
     // does this environment need the constraint pipeline this tick?
@@ -769,9 +881,11 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_smooth(const KArgs<T> a) {
           pipeline |= (q - m.f(h.o_jnt_range, 2 * j) < mg) || (m.f(h.o_jnt_range, 2 * j + 1) - q < mg);
         }
       }
-      a.nefc[env] = 0;
-      a.status[env] = (a.status[env] & 7) | (pipeline ? 0 : 8);
-      const unsigned vote = __ballot_sync(__activemask(), pipeline);
+      if (lane == 0) {
+        a.nefc[env] = 0;
+        a.status[env] = (a.status[env] & 7) | (pipeline ? 0 : 8);
+      }
+      const unsigned vote = __ballot_sync(__activemask(), pipeline && lane == 0);
       if (vote && (int)(threadIdx.x & 31) == __ffs(vote) - 1) atomicAdd(&a.pending[0], __popc(vote));
     }
 
@@ -779,15 +893,30 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_smooth(const KArgs<T> a) {
       // export the stage results the constraint pipeline (and the legacy mjData mirror) consume
       if (!s.aliased) {
 #pragma unroll(P::UNROLL)
-        for (int i = 0; i < 9 * nb; i++) a.xmat[i * S + env] = s.xmat[i];
+        for (int k_ = P::body_lo(m) - 1; k_ < P::body_hi(m); k_++) {
+          const int b = k_ < P::body_lo(m) ? 0 : P::body_at(m, k_);
+          if (b == 0 && L > 1 && lane != 0) continue;   // the world's subtree_com was summed by lane 0
+          for (int k = 0; k < 9; k++) a.xmat[(long long)(9 * b + k) * S + env] = s.xmat[9 * b + k];
+          for (int k = 0; k < 3; k++) a.subtree_com[(long long)(3 * b + k) * S + env] = s.subtree_com[3 * b + k];
+        }
 #pragma unroll(P::UNROLL)
-        for (int i = 0; i < 3 * nb; i++) a.subtree_com[i * S + env] = s.subtree_com[i];
+        for (int k_ = P::dof_lo(m); k_ < P::dof_hi(m); k_++) {
+          const int i = P::dof_at(m, k_);
+          for (int k = 0; k < 6; k++) a.cdof[(long long)(6 * i + k) * S + env] = s.cdof[6 * i + k];
+        }
+        if constexpr (P::STATIC) {
 #pragma unroll(P::UNROLL)
-        for (int i = 0; i < 6 * nv; i++) a.cdof[i * S + env] = s.cdof[i];
+          for (int i = 0; i < nM; i++) { a.qM[i * S + env] = s.qM[i]; a.qLD[i * S + env] = s.qLD[i]; }
+        } else {
+          for (int k_ = P::dof_lo(m); k_ < P::dof_hi(m); k_++) {
+            const int i = P::dof_at(m, k_);
+            const int adr = P::dof_Madr(m, i), cnt = P::dof_Mcnt(m, i);
+            for (int q2 = 0; q2 < cnt; q2++) { a.qM[(long long)(adr + q2) * S + env] = s.qM[adr + q2]; a.qLD[(long long)(adr + q2) * S + env] = s.qLD[adr + q2]; }
+          }
+        }
 #pragma unroll(P::UNROLL)
-        for (int i = 0; i < nM; i++) { a.qM[i * S + env] = s.qM[i]; a.qLD[i * S + env] = s.qLD[i]; }
-#pragma unroll(P::UNROLL)
-        for (int i = 0; i < nv; i++) {
+        for (int k_ = P::dof_lo(m); k_ < P::dof_hi(m); k_++) {
+          const int i = P::dof_at(m, k_);
           a.qLDiagInv[i * S + env] = s.qLDiagInv[i];
           a.qfrc_passive[i * S + env] = s.qfrc_passive[i];
           a.qfrc_smooth[i * S + env] = s.qfrc_smooth[i];
@@ -809,7 +938,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_smooth(const KArgs<T> a) {
     } else if (!pipeline) {
       // no active constraint: qacc = qacc_smooth, integrate right here
 #pragma unroll(P::UNROLL)
-      for (int i = 0; i < nv; i++) {
+      for (int k_ = P::dof_lo(m); k_ < P::dof_hi(m); k_++) {
+        const int i = P::dof_at(m, k_);
         const T v = s.qacc_smooth[i];
         a.qacc[i * S + env] = v;
         a.qacc_warmstart[i * S + env] = v;
@@ -817,14 +947,17 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_smooth(const KArgs<T> a) {
       if (a.flags & B2F_INTEGRATE) {
         // qLD / qLDiagInv are dead by now: reuse them as scratch for the damped factorisation
         euler_step<P>(m, s.qpos, s.qvel, s.qM, s.qacc_smooth, s.qfrc_smooth, a.h, s.qLD, s.qLDiagInv, s.tmpv);
+        if (L > 1) __syncwarp(tmask);   // the odom override below reads joints of other lanes' trees
         if (P::STATIC) {
 #pragma unroll(P::UNROLL)
           for (int i = 0; i < nq; i++) a.qpos[i * S + env] = s.qpos[i];
 #pragma unroll(P::UNROLL)
           for (int i = 0; i < nv; i++) a.qvel[i * S + env] = s.qvel[i];
         }
-        a.time[env] += a.h;
-        if (a.flags & B2F_ODOM) odom_override(m, a, env);
+        if (lane == 0) {
+          a.time[env] += a.h;
+          if (a.flags & B2F_ODOM) odom_override(m, a, env);
+        }
       } else if (P::STATIC && overridden) {
 #pragma unroll(P::UNROLL)
         for (int i = 0; i < nv; i++) a.qvel[i * S + env] = s.qvel[i];
