@@ -37,10 +37,11 @@ def main():
             wr = float(r[col["dram__bytes_write.sum"]]) * UNIT.get(units[col["dram__bytes_write.sum"]], 1.0)
             short = name.split("<")[0].replace("void ", "").replace("b2::", "")
             key = {"k_smooth": "smooth", "k_chain": "smooth", "k_chain_team": "smooth", "k_collide": "collide", "k_make_constraint": "make_constraint",
-                   "k_make_rows": "make_constraint", "k_make_blocks": "make_constraint", "k_solve_rows": "make_constraint", "k_pgs_block": "pgs", "k_integrate": "integrate"}.get(short, short)
+                   "k_make_rows": "make_constraint", "k_make_blocks": "make_constraint", "k_solve_rows": "make_constraint", "k_pgs_block": "pgs", "k_pgs_island": "pgs", "k_order_envs": "pgs", "k_integrate": "integrate", "k_dense_minv": "make_constraint", "k_project_tc": "make_constraint"}.get(short, short)
             traffic[key] = traffic.get(key, 0) + int(rd + wr)   # bench.py's make_constraint slot = k_make_rows (+ k_solve_rows) + k_make_blocks
         except Exception:
             pass
+    traffic["tick_total"] = sum(v for k, v in traffic.items() if k != "tick_total")
     if "--traffic" in sys.argv:
         with open(sys.argv[sys.argv.index("--traffic") + 1], "w") as f:
             json.dump(traffic, f, indent=1)
