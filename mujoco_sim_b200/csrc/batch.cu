@@ -546,7 +546,8 @@ int run_tick(b2_batch* b, int flags) {
     {
       // one thread per (block, environment); CTAs of block ordinals beyond this tick's largest count exit at once
       const int mb = b->make_block;
-      const dim3 gb(std::max(1, std::min(b->nenvp / mb, b->nsm * 8)), b->hdr.njmax);
+      // (block ordinals beyond grid.y are covered by a loop inside the kernel: a grid of njmax rows was mostly CTAs that exit at once)
+      const dim3 gb(std::max(1, std::min(b->nenvp / mb, b->nsm * 8)), std::min(b->hdr.njmax, 32));
       if (mb == 128) k_make_blocks<T, 128><<<gb, 128, (size_t)b->rec_max * 129 * sizeof(T), b->stream>>>(a);
       else k_make_blocks<T, 32><<<gb, 32, (size_t)b->rec_max * 33 * sizeof(T), b->stream>>>(a);
     }

@@ -643,6 +643,7 @@ __global__ void __launch_bounds__(32 * ROWS) k_solve_rows(const KArgs<T> a) {
   }
 }
 
+template <typename T, int BLOCK> __device__ __forceinline__ void make_blocks_pass(const KArgs<T>& a, const int blk);
 // K5: the expensive, embarrassingly parallel part — one thread per (block, environment): vel, aref, b of the block's solver
 // rows, the primal force of mj_inverse per row, B = M^-1 J^T of the block's base directions by sparse back-substitution
 // inside its trees (in shared memory), the local matrix A, the couplings between the pyramid rows, diag(AR) per row, and
@@ -651,9 +652,12 @@ __global__ void __launch_bounds__(32 * ROWS) k_solve_rows(const KArgs<T> a) {
 // beyond the largest block count of this tick (maxblk, found by k_make_rows) exit at once.
 template <typename T, int BLOCK>
 __global__ void __launch_bounds__(BLOCK) k_make_blocks(const KArgs<T> a) {
-  const int blk = blockIdx.y;
-  if (blk >= a.maxblk[0]) return;
   if ((a.flags & B2F_FUSABLE) && a.pending[0] == 0) return;
+  const int maxblk = a.maxblk[0];
+  for (int blk = blockIdx.y; blk < maxblk; blk += gridDim.y) make_blocks_pass<T, BLOCK>(a, blk);
+}
+template <typename T, int BLOCK>
+__device__ __forceinline__ void make_blocks_pass(const KArgs<T>& a, const int blk) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // The kernel needs a few integer tables of the model (dof_parentid, dof_Madr, the tree table), warp-uniform or nearly
   // so: they are read from the blob in HBM through L1 instead of staging a private copy per CTA.  For PR2-sized models
@@ -963,17 +967,13 @@ __host__ __device__ constexpr int lv_cpl(int nb, int r, int c) {
 }
 __host__ __device__ constexpr int lv_np(int nb) { return (4 * lv_nrow(nb) + (nb > 1 ? nb - 1 + lv_nrow(nb) * (lv_nrow(nb) - 1) / 2 : 0) + 3) & ~3; }
 template <typename T, int NBW, int WCAP>
-__device__ __noinline__ void pgs_visit_lane(const T* __restrict__ rec, bool have, T* __restrict__ acc, T* __restrict__ f, T& improvement) {
+__device__ __forceinline__ void pgs_visit_lane(const T* __restrict__ rec, bool have, const VecN<T, 4>& h0, const VecN<T, 4>& h1,
+                                               T* __restrict__ acc, T* __restrict__ f, T& improvement) {
   static_assert(NBW == 1 || NBW == 3 || NBW == 4, "scalar rows and pyramidal contacts of condim 3 / 4");
   static_assert(WCAP % 4 == 0 && WCAP <= 16, "compact rows of at most 16 elements");
   constexpr int NROWW = lv_nrow(NBW), NPV = lv_np(NBW) / 4;
   using V4 = VecN<T, 4>;
-  V4 h0, h1;
-  if (have) { h0 = *reinterpret_cast<const V4*>(rec); h1 = *reinterpret_cast<const V4*>(rec + 4); }
-  else {
-#pragma unroll
-    for (int c = 0; c < 4; c++) { h0.v[c] = enc_int(0, T()); h1.v[c] = enc_int(0, T()); }
-  }
+  // (h0 / h1: the record's header words, loaded by the caller — zeros for a lane without a block)
   const int code = dec_int(h0.v[0]), type = code & 15, nb = have ? (code >> 4) & 15 : 0, nrow = have ? code >> 8 : 0;
   const int s1 = dec_int(h0.v[1]), n1w = dec_int(h0.v[2]), n1 = n1w & 1023, w = have ? n1w >> 10 : 0, s2 = dec_int(h0.v[3]);
   const T R = h1.v[0], flv = h1.v[1];
@@ -1602,25 +1602,33 @@ __global__ void __launch_bounds__(32, MINB) k_pgs_island(const KArgs<T> a) {
         if (done) { c.off = 0; c.end = 0; }
         while (true) {
           const bool have = c.off < c.end;
-          if (!__any_sync(0xffffffffu, have)) break;
           const T* rec = have ? c.base + c.off : slab;
-          const int code = have ? dec_int(rec[BH_CODE]) : 0, len = have ? dec_int(rec[BH_LEN]) : 0;
-          // one instruction stream for the warp, sized by the largest block of this step (base directions, row width)
+          using V4 = VecN<T, 4>;
+          V4 h0, h1;
+          if (have) { h0 = *reinterpret_cast<const V4*>(rec); h1 = *reinterpret_cast<const V4*>(rec + 4); }
+          else {
+#pragma unroll
+            for (int q2 = 0; q2 < 4; q2++) { h0.v[q2] = enc_int(0, T()); h1.v[q2] = enc_int(0, T()); }
+          }
+          const int code = dec_int(h0.v[0]), len = dec_int(h1.v[2]);
+          // one instruction stream for the warp, sized by the largest block of this step (base directions, row width):
+          // both maxima in one warp reduction
           const int nbw = __reduce_max_sync(0xffffffffu, (code >> 4) & 15);
-          const int ww = __reduce_max_sync(0xffffffffu, have ? dec_int(rec[BH_N1W]) >> 10 : 0);
+          if (nbw == 0) break;   // no lane of the warp has a block left in this sweep
+          const int ww = __reduce_max_sync(0xffffffffu, dec_int(h0.v[2]) >> 10);
           if (nbw <= 4) {
             if (ww <= 8) {
-              if (nbw <= 1) pgs_visit_lane<T, 1, 8>(rec, have, acc, f, improvement);
-              else if (nbw <= 3) pgs_visit_lane<T, 3, 8>(rec, have, acc, f, improvement);
-              else pgs_visit_lane<T, 4, 8>(rec, have, acc, f, improvement);
+              if (nbw <= 1) pgs_visit_lane<T, 1, 8>(rec, have, h0, h1, acc, f, improvement);
+              else if (nbw <= 3) pgs_visit_lane<T, 3, 8>(rec, have, h0, h1, acc, f, improvement);
+              else pgs_visit_lane<T, 4, 8>(rec, have, h0, h1, acc, f, improvement);
             } else if (ww <= 12) {
-              if (nbw <= 1) pgs_visit_lane<T, 1, 12>(rec, have, acc, f, improvement);
-              else if (nbw <= 3) pgs_visit_lane<T, 3, 12>(rec, have, acc, f, improvement);
-              else pgs_visit_lane<T, 4, 12>(rec, have, acc, f, improvement);
+              if (nbw <= 1) pgs_visit_lane<T, 1, 12>(rec, have, h0, h1, acc, f, improvement);
+              else if (nbw <= 3) pgs_visit_lane<T, 3, 12>(rec, have, h0, h1, acc, f, improvement);
+              else pgs_visit_lane<T, 4, 12>(rec, have, h0, h1, acc, f, improvement);
             } else {
-              if (nbw <= 1) pgs_visit_lane<T, 1, 16>(rec, have, acc, f, improvement);
-              else if (nbw <= 3) pgs_visit_lane<T, 3, 16>(rec, have, acc, f, improvement);
-              else pgs_visit_lane<T, 4, 16>(rec, have, acc, f, improvement);
+              if (nbw <= 1) pgs_visit_lane<T, 1, 16>(rec, have, h0, h1, acc, f, improvement);
+              else if (nbw <= 3) pgs_visit_lane<T, 3, 16>(rec, have, h0, h1, acc, f, improvement);
+              else pgs_visit_lane<T, 4, 16>(rec, have, h0, h1, acc, f, improvement);
             }
           } else {
             BlockShape bs{};
