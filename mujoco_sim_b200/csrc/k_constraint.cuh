@@ -1730,7 +1730,7 @@ __global__ void k_publish_obs(const KArgs<T> a) {
 }
 
 // G7: mj_checkAcc, semi-implicit Euler with implicit damping, odom override, observation publish.  L lanes per
-// environment: lane l integrates the kinematic trees t with t % L == l (the damped factorisation M + h D is block
+// environment: lane l integrates the kinematic trees of its item lists (the damped factorisation M + h D is block
 // diagonal over trees like M itself); L = 1 is the thread-per-environment form.
 template <typename T, int BLOCK, int L = 1>
 __global__ void __launch_bounds__(BLOCK) k_integrate(const KArgs<T> a) {
@@ -1744,10 +1744,10 @@ __global__ void __launch_bounds__(BLOCK) k_integrate(const KArgs<T> a) {
   for (int tile = blockIdx.x; tile < nteams; tile += gridDim.x) {
     const int env = tile * EPB + envl;
     const int nv = h.nv;
-    if ((a.flags & B2F_FUSABLE) && (a.status[env] & 8)) continue;
+    const bool skip = (a.flags & B2F_FUSABLE) && (a.status[env] & 8);   // integrated by the smooth kernel already
     SArr<T> qacc{a.qacc + env, S};
     bool bad = false;
-    for (int i = 0; i < nv; i++) bad |= !(t_abs(qacc[i]) < T(1e10));   // (every lane looks at the whole vector: one decision per environment)
+    if (!skip) for (int i = 0; i < nv; i++) bad |= !(t_abs(qacc[i]) < T(1e10));   // (every lane looks at the whole vector: one decision per environment)
     if (bad) {  // reset instead of integrating garbage
       if (L > 1) __syncwarp(tmask);   // every lane has read qacc before anybody clears it
       if (lane == 0) {
@@ -1756,9 +1756,7 @@ __global__ void __launch_bounds__(BLOCK) k_integrate(const KArgs<T> a) {
         a.time[env] = 0;
         a.status[env] |= 4;
       }
-      continue;
-    }
-    if (a.flags & B2F_INTEGRATE) {
+    } else if (!skip && (a.flags & B2F_INTEGRATE)) {
       SArr<T> qpos{a.qpos + env, S}, qvel{a.qvel + env, S}, qM{a.qM + env, S}, LD{a.qLD + env, S}, dinv{a.qLDiagInv + env, S};
       SArr<T> frc{a.qfrc_smooth + env, S}, xa{a.qacc_smooth + env, S};
       if (a.flags & B2F_LD_SMEM) {
@@ -1777,12 +1775,21 @@ __global__ void __launch_bounds__(BLOCK) k_integrate(const KArgs<T> a) {
         a.time[env] += a.h;
         if (a.flags & B2F_ODOM) odom_override(m, a, env);
       }
-      // observation exchange fused into the integrate epilogue: the new state goes straight into slice `rank` of every
-      // GPU's observation buffer (plain stores through the NVLink peer mappings: fire-and-forget, one 128-byte line per
-      // element and warp in the thread-per-environment form).  No pack kernel, no collective call.
-      if ((a.flags & B2F_OBS) && env < a.nenv) {
-        if (L > 1 && (a.flags & B2F_ODOM)) __syncwarp(tmask);
-        publish_obs(a, env, lane, L);
+    }
+    // observation exchange fused into the integrate epilogue: once the CTA's environments are integrated, its threads
+    // store their new state into slice `rank` of every GPU's observation buffer — a warp writes one element of 32
+    // consecutive environments, i.e. whole 128-byte lines through the NVLink peer mappings (plain posted stores).
+    // No pack kernel, no collective call.
+    if (a.flags & B2F_OBS) {
+      __syncthreads();
+      const DModel* hd = reinterpret_cast<const DModel*>(a.model);
+      const int nobs = hd->nq + hd->nv, nq = hd->nq;
+      const long long base = (long long)a.obs_rank * nobs * a.obs_nenv;
+      for (int idx = threadIdx.x; idx < nobs * EPB; idx += BLOCK) {
+        const int i = idx / EPB, e = tile * EPB + idx % EPB;
+        if (e >= a.nenv) continue;
+        const float v = (float)(i < nq ? a.qpos[(long long)i * S + e] : a.qvel[(long long)(i - nq) * S + e]);
+        for (int p = 0; p < a.obs_world; p++) a.obs_peers[p][base + (long long)i * a.obs_nenv + e] = v;
       }
     }
   }
