@@ -307,6 +307,7 @@ KArgs<T> make_args(b2_batch* b, int flags) {
   if constexpr (sizeof(T) == 4) a = b->args_f; else a = b->args_d;
   a.model = b->blob_dev; a.model_words = b->hdr.nwords;
   a.flags = flags; a.ws_block = b->smooth_block; a.h = (T)b->h; a.wp = b->wp;
+  a.hp = b->h_dev ? (sizeof(T) == 8 ? (const T*)b->h_dev : (const T*)((const char*)b->h_dev + 8)) : nullptr;
   a.block_capw = b->block_capw; a.block_npar = b->block_npar; a.stage_cap = b->isl_cap ? b->isl_stage : b->stage_cap; a.row_nb = b->row_nb; a.isl_cap = b->isl_cap; a.em_rows = b->tc_rows;
   a.obs_peers = b->obs_peers_dev; a.obs_world = b->obs_world; a.obs_rank = b->obs_rank; a.obs_nenv = b->nenv;
   a.hw_vel = b->io_in[0]; a.hw_eff = b->io_in[1];
@@ -638,9 +639,7 @@ int tick_dispatch(b2_batch* b, int flags) {
     if (mine) prof_close(b);
     return rc;
   }
-  float hf = (float)b->h;
-  uint32_t hb;
-  std::memcpy(&hb, &hf, 4);
+  const uint32_t hb = 0;   // (the timestep is read from device memory: not part of the graph key)
   // a tick that is a single kernel gains nothing from a graph
   if ((flags & B2_TICK_HW) && b->chain_single && b->hw_identity && !(b->tick_flags & (1 << 30))) return tick_eager(b, flags);
   unsigned long long ph = 0;  // the exchange buffers are baked into the captured kernel arguments
@@ -942,6 +941,11 @@ b2_batch* b2_create(const mjModel* m, int nenv, int device, int precision) {
     return nullptr;
   };
   if (cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess) return bail("cudaStreamCreate failed");
+  {
+    if (cudaMalloc(&b->h_dev, 16) != cudaSuccess) return bail("cudaMalloc(h_dev) failed");
+    struct { double d; float f; float pad; } hv{b->h, (float)b->h, 0.f};
+    if (cudaMemcpyAsync(b->h_dev, &hv, 16, cudaMemcpyHostToDevice, b->stream) != cudaSuccess) return bail("timestep upload failed");
+  }
   if (upload_model(b) < 0) return bail("upload_model failed");
 
   const int nq = m->nq, nv = m->nv, nb = m->nbody, ng = m->ngeom, nM = m->nM;
@@ -1153,6 +1157,7 @@ void b2_destroy(b2_batch* b) {
   if (b->slot_dadr) cudaFree(b->slot_dadr);
   if (b->slot_active) cudaFree(b->slot_active);
   if (b->flush_buf) cudaFree(b->flush_buf);
+  if (b->h_dev) cudaFree(b->h_dev);
   for (size_t p = 0; p < b->obs_peers_host.size(); p++)
     if (b->obs_peer_ipc[p] && b->obs_peers_host[p]) cudaIpcCloseMemHandle(b->obs_peers_host[p]);
   if (b->obs_peers_dev) cudaFree(b->obs_peers_dev);
@@ -1215,7 +1220,14 @@ int b2_set_odom(b2_batch* b, int nrobot, const int* dof, const int* qposadr) {
 
 int b2_set_timestep(b2_batch* b, double h) {
   if (!b || !(h > 0)) return fail("b2_set_timestep: bad argument");
+  if (h == b->h && b->h_dev) return 0;
   b->h = h;
+  // the kernels read the timestep from device memory (KArgs::hp), so captured CUDA graphs follow it: the reference
+  // changes m->opt.timestep on every tick (src/mj_main.cpp:150-163) and a graph per value would never be reused
+  CK(cudaSetDevice(b->device));
+  if (!b->h_dev) CK(cudaMalloc(&b->h_dev, 16));
+  struct { double d; float f; float pad; } hv{h, (float)h, 0.f};
+  CK(cudaMemcpyAsync(b->h_dev, &hv, 16, cudaMemcpyHostToDevice, b->stream));   // pageable source: staged before the call returns
   return 0;
 }
 

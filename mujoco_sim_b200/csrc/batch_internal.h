@@ -55,6 +55,7 @@ struct b2_batch {
   std::vector<bool> obs_peer_ipc;
   int obs_world = 0, obs_rank = 0;
   bool obs_on = false;
+  void* h_dev = nullptr; // {double h, float h}: the timestep in device memory (KArgs::hp)
   int tree_lanes = 1;    // lanes per environment in k_smooth / k_integrate (tree-parallel form; 1: thread per environment)
   int tc_rows = 0;       // tensor-core projection (k_project_tc): rows per environment of the environment-major arrays; 0: off
   int tc_passes = 3;     // 3: 3xTF32 (fp32-level accuracy), 1: plain TF32

@@ -40,6 +40,10 @@ struct KArgs {
   int flags;
   int ws_block;           // CTA size the shared workspace was sized for
   T h;                    // timestep of this call (the reference mutates m->opt.timestep every tick, mj_main.cpp:150-163)
+  const T* hp;            // the same value in device memory: a captured CUDA graph keeps following b2_set_timestep
+#ifdef __CUDACC__
+  __device__ __forceinline__ T dt() const { return hp ? *hp : h; }
+#endif
 
   // persistent state, SoA [element][nenvp]
   T *qpos, *qvel, *qacc, *qacc_warmstart, *qfrc_applied, *xfrc_applied, *mocap_pos, *mocap_quat;

@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_chain(const KArgs<T> a) {
         T K, Bd;
         if (solref[0] > 0) {
           T tc = solref[0];
-          if (!(h.disableflags & DSBL_REFSAFE)) tc = t_max(tc, 2 * a.h);
+          if (!(h.disableflags & DSBL_REFSAFE)) tc = t_max(tc, 2 * a.dt());
           K = 1 / t_max(Eps<T>::minval(), dmax * dmax * tc * tc * solref[1] * solref[1]);
           Bd = 2 / t_max(Eps<T>::minval(), dmax * tc);
         } else {
@@ -459,7 +459,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_chain(const KArgs<T> a) {
 #pragma unroll
         for (int i = 0; i < NM; i++) LD[i] = qM[i];
 #pragma unroll
-        for (int i = 0; i < N; i++) { LD[i * (i + 1) / 2] += a.h * m.f(h.o_dof_damping, i); xa[i] = fsm[i] + qfc[i]; }
+        for (int i = 0; i < N; i++) { LD[i * (i + 1) / 2] += a.dt() * m.f(h.o_dof_damping, i); xa[i] = fsm[i] + qfc[i]; }
         ld_factor<P>(m, LD, dinv);
         ld_solve<P>(m, LD, dinv, xa);
       } else {
@@ -468,12 +468,12 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_chain(const KArgs<T> a) {
       }
 #pragma unroll
       for (int i = 0; i < N; i++) {
-        v[i] += a.h * xa[i];
-        q[i] += a.h * v[i];
+        v[i] += a.dt() * xa[i];
+        q[i] += a.dt() * v[i];
         a.qvel[i * S + env] = v[i];
         a.qpos[i * S + env] = q[i];
       }
-      a.time[env] += a.h;
+      a.time[env] += a.dt();
       if (a.flags & B2F_ODOM) odom_override(m, a, env);
     } else if (overridden) {
 #pragma unroll

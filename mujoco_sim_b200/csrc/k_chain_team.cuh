@@ -412,7 +412,7 @@ __global__ void __launch_bounds__(BLOCK) k_chain_team(const KArgs<T> a) {
         T K, Bd;
         if (solref[0] > 0) {
           T tc = solref[0];
-          if (!(h.disableflags & DSBL_REFSAFE)) tc = t_max(tc, 2 * a.h);
+          if (!(h.disableflags & DSBL_REFSAFE)) tc = t_max(tc, 2 * a.dt());
           K = 1 / t_max(Eps<T>::minval(), dmax * dmax * tc * tc * solref[1] * solref[1]);
           Bd = 2 / t_max(Eps<T>::minval(), dmax * tc);
         } else {
@@ -527,17 +527,17 @@ __global__ void __launch_bounds__(BLOCK) k_chain_team(const KArgs<T> a) {
       T xa = acc;
       if (h.has_damping && !(h.disableflags & DSBL_EULERDAMP)) {
 #pragma unroll
-        for (int c = 0; c < N; c++) W[c] = Mr[c] + ((c == l) ? a.h * damp : T(0));
+        for (int c = 0; c < N; c++) W[c] = Mr[c] + ((c == l) ? a.dt() * damp : T(0));
         factor(W);
         xa = solve(on ? fsm + qfc : T(0));
       }
       if (on && live) {
-        v += a.h * xa;
-        q += a.h * v;
+        v += a.dt() * xa;
+        q += a.dt() * v;
         a.qvel[at] = v;
         a.qpos[at] = q;
       }
-      if (l == 0 && live) a.time[env] += a.h;
+      if (l == 0 && live) a.time[env] += a.dt();
     } else if (ov_team && on && live) {
       a.qvel[at] = v;
     }

@@ -315,7 +315,7 @@ struct Rows {
 
   // diagApprox, impedance -> R, D; K, B, imp; aref; (vel uses the current, possibly overridden, qvel)
   __device__ void finish_range(int r0, int r1, int step) {
-    const T hs = a.h;
+    const T hs = a.dt();
     // the rows of one contact share its parameters: fetched once per contact (13 HBM loads), not once per row
     int c_id = -1, c_first = 0;
     T c_solref[2] = {0, 0}, c_solimp[5] = {0, 0, 0, 0, 0}, c_tran = 0, c_rot = 0;
@@ -1769,10 +1769,10 @@ __global__ void __launch_bounds__(BLOCK) k_integrate(const KArgs<T> a) {
       // qfrc_smooth becomes the total force of the implicit-damping solve; qLD / qLDiagInv / qacc_smooth are dead after
       // the solver and serve as scratch for the damped factorisation
       if (h.has_damping) for (int k_ = GenericP::dof_lo(m); k_ < GenericP::dof_hi(m); k_++) { const int i = GenericP::dof_at(m, k_); frc[i] += a.qfrc_constraint[i * S + env]; }
-      euler_step<GenericP>(m, qpos, qvel, qM, qacc, frc, a.h, LD, dinv, xa);
+      euler_step<GenericP>(m, qpos, qvel, qM, qacc, frc, a.dt(), LD, dinv, xa);
       if (L > 1) __syncwarp(tmask);
       if (lane == 0) {
-        a.time[env] += a.h;
+        a.time[env] += a.dt();
         if (a.flags & B2F_ODOM) odom_override(m, a, env);
       }
     }

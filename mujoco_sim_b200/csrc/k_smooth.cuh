@@ -946,7 +946,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_smooth(const KArgs<T> a) {
       }
       if (a.flags & B2F_INTEGRATE) {
         // qLD / qLDiagInv are dead by now: reuse them as scratch for the damped factorisation
-        euler_step<P>(m, s.qpos, s.qvel, s.qM, s.qacc_smooth, s.qfrc_smooth, a.h, s.qLD, s.qLDiagInv, s.tmpv);
+        euler_step<P>(m, s.qpos, s.qvel, s.qM, s.qacc_smooth, s.qfrc_smooth, a.dt(), s.qLD, s.qLDiagInv, s.tmpv);
         if (L > 1) __syncwarp(tmask);   // the odom override below reads joints of other lanes' trees
         if (P::STATIC) {
 #pragma unroll(P::UNROLL)
@@ -955,7 +955,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_smooth(const KArgs<T> a) {
           for (int i = 0; i < nv; i++) a.qvel[i * S + env] = s.qvel[i];
         }
         if (lane == 0) {
-          a.time[env] += a.h;
+          a.time[env] += a.dt();
           if (a.flags & B2F_ODOM) odom_override(m, a, env);
         }
       } else if (P::STATIC && overridden) {
