@@ -134,6 +134,14 @@ int b2_spawn(b2_batch* b, int n, const int* env, const int* slot, const float* p
 int b2_destroy_slots(b2_batch* b, int n, const int* env, const int* slot);
 int b2_slot_active(b2_batch* b, unsigned char* active, int env_lo, int env_hi);
 
+/* Full-recompile fallback for topology changes the slots cannot express (MESH / whole-robot spawn, mj_ros.cpp:941-1325):
+ * the caller compiles the new world (mj_loadXML), creates a batch for it and carries the old state over as the
+ * reference's add_old_state does (src/mujoco_sim/mj_sim.cpp:465-558): for every body NAME present in both models with
+ * the same joint / dof counts, qpos, qvel, qacc, qacc_warmstart, qfrc_applied of its joints are copied for every
+ * environment (device to device), and the simulation time; bodies only in the new model keep their qpos0.  Both batches
+ * must have the same environment count and precision.  Returns the number of bodies carried over, < 0 on error. */
+int b2_transfer_state(b2_batch* src, b2_batch* dst);
+
 /* observation exchange ("at most one all-gather of observations per control tick"): pack
  * [qpos | qvel] of every environment of this shard as fp32, native layout [nq + nv][nenv], into the DEVICE buffer
  * obs_dev ((nq + nv) * nenv floats) on the batch's stream.  The collective itself is the caller's: one process per GPU,

@@ -1621,6 +1621,54 @@ int b2_pack_obs(b2_batch* b, float* obs_dev) {
   return 0;
 }
 
+// the reference's add_old_state (src/mujoco_sim/mj_sim.cpp:465-558) for whole batches
+int b2_transfer_state(b2_batch* src, b2_batch* dst) {
+  if (!src || !dst || src == dst) return fail("b2_transfer_state: bad argument");
+  if (src->nenv != dst->nenv || src->prec != dst->prec || src->device != dst->device) return fail("b2_transfer_state: the batches must agree in environments, precision and device");
+  CK(cudaSetDevice(dst->device));
+  CK(cudaStreamSynchronize(src->stream));
+  const mjModel* ma = src->m;
+  const mjModel* mb = dst->m;
+  const size_t row = (size_t)dst->prec, na = src->nenvp, nb_ = dst->nenvp;
+  auto copy_rows = [&](const char* field, int ia, int ib, int n) -> int {
+    auto fa = src->fields.find(field), fb = dst->fields.find(field);
+    if (fa == src->fields.end() || fb == dst->fields.end()) return 0;
+    for (int k = 0; k < n; k++)
+      CK(cudaMemcpyAsync((char*)fb->second.ptr + (size_t)(ib + k) * nb_ * row, (const char*)fa->second.ptr + (size_t)(ia + k) * na * row,
+                         (size_t)src->nenv * row, cudaMemcpyDeviceToDevice, dst->stream));
+    return 0;
+  };
+  int carried = 0;
+  for (int i = 1; i < ma->nbody; i++) {
+    const char* name = mj_id2name(ma, mjOBJ_BODY, i);
+    if (!name || !*name) continue;
+    const int j = mj_name2id(mb, mjOBJ_BODY, name);
+    if (j < 0) continue;
+    if (ma->body_jntnum[i] != mb->body_jntnum[j] || ma->body_dofnum[i] != mb->body_dofnum[j]) continue;   // (the reference warns and skips)
+    if (ma->body_jntnum[i] > 0) {
+      // qpos width of the body's joints (free 7, ball 4, scalar 1); the joint types must agree as well
+      int wa = 0, wb = 0;
+      bool same = true;
+      for (int k = 0; k < ma->body_jntnum[i]; k++) {
+        const int ta = ma->jnt_type[ma->body_jntadr[i] + k], tb = mb->jnt_type[mb->body_jntadr[j] + k];
+        same &= ta == tb;
+        wa += ta == mjJNT_FREE ? 7 : (ta == mjJNT_BALL ? 4 : 1);
+        wb += tb == mjJNT_FREE ? 7 : (tb == mjJNT_BALL ? 4 : 1);
+      }
+      if (!same || wa != wb) continue;
+      const int qa = ma->jnt_qposadr[ma->body_jntadr[i]], qb = mb->jnt_qposadr[mb->body_jntadr[j]];
+      const int da = ma->body_dofadr[i], db = mb->body_dofadr[j], nd = ma->body_dofnum[i];
+      if (copy_rows("qpos", qa, qb, wa) < 0) return -1;
+      for (const char* f : {"qvel", "qacc", "qacc_warmstart", "qfrc_applied"})
+        if (copy_rows(f, da, db, nd) < 0) return -1;
+    }
+    carried++;
+  }
+  if (copy_rows("time", 0, 0, 1) < 0) return -1;
+  CK(cudaStreamSynchronize(dst->stream));
+  return carried;
+}
+
 // ---- fused observation exchange (include/b2_batch.h) ----
 float* b2_obs_create(b2_batch* b, int world, int rank) {
   if (!b || world < 1 || rank < 0 || rank >= world) { fail("b2_obs_create: bad argument"); return nullptr; }

@@ -92,6 +92,7 @@ _sig = {
     "b2_register_host": (_i, [_vp, _vp, C.c_longlong]),
     "b2_unregister_host": (_i, [_vp, _vp]),
     "b2_pack_obs": (_i, [_vp, _vp]),
+    "b2_transfer_state": (_i, [_vp, _vp]),
     "b2_obs_create": (_vp, [_vp, _i, _i]),
     "b2_obs_handle": (_i, [_vp, _vp]),
     "b2_obs_attach": (_i, [_vp, _vp, _vp]),
@@ -413,6 +414,14 @@ class Batch:
     def pack_obs(self, dev_ptr):
         """[qpos | qvel] as fp32 [nq + nv][nenv] into a device buffer (the payload of the per-tick all-gather)."""
         self._ck(lib.b2_pack_obs(self.ptr, dev_ptr), "b2_pack_obs")
+
+    def transfer_state_to(self, other):
+        """The reference's add_old_state for whole batches: carry the state of every body that exists (by name) in both
+        models over to `other` (a batch of the re-compiled world); returns the number of bodies carried."""
+        n = lib.b2_transfer_state(self.ptr, other.ptr)
+        if n < 0:
+            raise B2Error("b2_transfer_state: " + _err())
+        return n
 
     # ---- fused observation exchange (include/b2_batch.h) ----
     def obs_create(self, world, rank):

@@ -1147,3 +1147,38 @@ def test_timestep_changes_every_tick_follow_without_new_graphs(b2, orc):
     m.set_opt("timestep", 0.005)
     assert per_tick <= 12, per_tick      # replayed graph: the tick's own kernels, no re-capture bookkeeping
     bt.close()
+
+
+def test_full_recompile_fallback_carries_the_state_over(b2):
+    """SURVEY row f2, the fallback for spawns the slots cannot express (a MESH object or a whole robot,
+    mj_ros.cpp:941-1325): the world is re-compiled with the new body and the state of every body that exists in both
+    models is carried over by name (the reference's add_old_state, mj_sim.cpp:465-558), for all environments on the
+    device.  The carried bodies continue bit for bit where they were; the new body starts at its authored pose."""
+    import xml.etree.ElementTree as ET
+    txt = open(b2.asset("ur5_tabletop.xml")).read()
+    root = ET.fromstring(txt)
+    wb = root.find("worldbody")
+    newb = ET.SubElement(wb, "body", {"name": "spawned_robot_part", "pos": "0.1 0.3 1.2"})
+    ET.SubElement(newb, "freejoint")
+    ET.SubElement(newb, "geom", {"type": "capsule", "size": "0.03 0.08"})
+    m_old = b2.Model(b2.asset("ur5_tabletop.xml"))
+    m_new = b2.Model(xml=ET.tostring(root, encoding="unicode"), basedir=b2.asset(""))
+    assert m_new.nbody == m_old.nbody + 1 and m_new.nq == m_old.nq + 7
+    nenv = 64
+    qpos, qvel, frc = states_for(m_old, "ur5_tabletop.xml", nenv, 818)
+    a = b2.Batch(m_old, nenv)
+    a.set("qpos", qpos); a.set("qvel", qvel); a.set("qfrc_applied", frc)
+    a.step(30); a.sync()
+    b = b2.Batch(m_new, nenv)
+    carried = a.transfer_state_to(b)
+    assert carried == m_old.nbody - 1
+    qa, qb = a.get("qpos"), b.get("qpos")
+    va, vb = a.get("qvel"), b.get("qvel")
+    # the old bodies come first in both models (the new one was appended): same addresses
+    assert np.array_equal(qb[:, :m_old.nq], qa) and np.array_equal(vb[:, :m_old.nv], va)
+    assert np.array_equal(b.get("qacc_warmstart")[:, :m_old.nv], a.get("qacc_warmstart"))
+    assert np.allclose(qb[:, m_old.nq:], np.array(m_new.qpos0)[m_old.nq:]) and not vb[:, m_old.nv:].any()
+    assert np.array_equal(b.get("time"), a.get("time"))
+    b.step(5); b.sync()
+    assert np.isfinite(b.get("qpos")).all()
+    a.close(); b.close()
