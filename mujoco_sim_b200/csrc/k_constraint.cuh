@@ -1080,6 +1080,102 @@ __device__ __forceinline__ void pgs_visit_lane(const T* __restrict__ rec, bool h
   }
 }
 
+// The lane visit when every lane of the warp that has a block has a pyramidal contact with exactly NB base directions
+// (the common case: most contacts of a scene share a condim) — record offsets are compile-time constants, no parameter
+// picks, no row padding, contact bounds only (f >= 0).  SH: every such record is staged in shared memory (the loads
+// become LDS instead of generic loads).  Same operation order as pgs_visit_lane.
+template <typename T, int NB, int WCAP, bool SH>
+__device__ __forceinline__ void pgs_visit_lane_exact(const T* __restrict__ rec, bool have, const VecN<T, 4>& h0, const VecN<T, 4>& h1,
+                                                     T* __restrict__ acc, T* __restrict__ f, T& improvement) {
+  static_assert(NB == 3 || NB == 4, "pyramidal contacts of condim 3 / 4");
+  constexpr int NROW = 2 * (NB - 1), NP = lv_np(NB), NPV = NP / 4, oJ = BH_N + NP;
+  using V4 = VecN<T, 4>;
+  if (SH) __builtin_assume(__isShared(rec));
+  const int s1 = dec_int(h0.v[1]), n1w = dec_int(h0.v[2]), n1 = n1w & 1023, w = have ? n1w >> 10 : 0, s2 = dec_int(h0.v[3]);
+  const T R = h1.v[0];
+  const int row0 = dec_int(h1.v[3]);
+  const int wq = (w + 3) & ~3, oB = oJ + NB * wq;
+  T P[NPV * 4];
+#pragma unroll
+  for (int q = 0; q < NPV; q++) {
+    V4 v;
+    if (have) v = *reinterpret_cast<const V4*>(rec + BH_N + 4 * q);
+    else { v.v[0] = 0; v.v[1] = 0; v.v[2] = 0; v.v[3] = 0; }
+#pragma unroll
+    for (int c = 0; c < 4; c++) P[4 * q + c] = v.v[c];
+  }
+  T fo[NROW];
+#pragma unroll
+  for (int r = 0; r < NROW; r++) fo[r] = have ? f[row0 + r] : T(0);
+  T x[WCAP];
+  int dofs[WCAP];
+#pragma unroll
+  for (int e = 0; e < WCAP; e++) {
+    dofs[e] = e < n1 ? s1 + e : s2 + e - n1;
+    x[e] = e < w ? acc[dofs[e]] : T(0);
+  }
+  T u[NB];
+#pragma unroll
+  for (int k = 0; k < NB; k++) {
+    u[k] = 0;
+#pragma unroll
+    for (int q = 0; q < WCAP / 4; q++) {
+      if (4 * q < w) {
+        const V4 j = *reinterpret_cast<const V4*>(rec + oJ + k * wq + 4 * q);
+#pragma unroll
+        for (int c = 0; c < 4; c++) u[k] = t_fma(j.v[c], x[4 * q + c], u[k]);
+      }
+    }
+  }
+  T Bv[NB][WCAP];
+#pragma unroll
+  for (int k = 0; k < NB; k++)
+#pragma unroll
+    for (int q = 0; q < WCAP / 4; q++) {
+      V4 b;
+      if (4 * q < w) b = *reinterpret_cast<const V4*>(rec + oB + k * wq + 4 * q);
+      else { b.v[0] = 0; b.v[1] = 0; b.v[2] = 0; b.v[3] = 0; }
+#pragma unroll
+      for (int c = 0; c < 4; c++) Bv[k][4 * q + c] = b.v[c];
+    }
+  T v[NROW], dl[NROW];
+#pragma unroll
+  for (int r = 0; r < NROW; r++) v[r] = t_fma((r & 1) ? -P[lv_mu(NB, r / 2)] : P[lv_mu(NB, r / 2)], u[r / 2 + 1], u[0]);
+  bool any = false;
+#pragma unroll
+  for (int r = 0; r < NROW; r++) {
+    const T res = v[r] + t_fma(R, fo[r], -P[r]);
+    const T fn = t_min(T(3.0e38), t_max(T(0), t_fma(-res, P[lv_ia(NB, r)], fo[r])));
+    T delta = fn - fo[r];
+    const T change = t_fma(t_mul(t_mul(T(0.5), delta), delta), P[lv_arr(NB, r)], t_mul(delta, res));
+    const bool ok = have && delta != 0 && !(change > T(1e-10));
+    delta = ok ? delta : T(0);
+    improvement -= ok ? change : T(0);
+    fo[r] = ok ? fn : fo[r];
+    any |= ok;
+    dl[r] = delta;
+#pragma unroll
+    for (int c = r + 1; c < NROW; c++) v[c] = t_fma(delta, P[lv_cpl(NB, r, c)], v[c]);
+  }
+  if (any) {
+#pragma unroll
+    for (int r = 0; r < NROW; r++) f[row0 + r] = fo[r];
+    T d[NB];
+    d[0] = dl[0];
+#pragma unroll
+    for (int r = 1; r < NROW; r++) d[0] += dl[r];
+#pragma unroll
+    for (int k = 1; k < NB; k++) d[k] = P[lv_mu(NB, k - 1)] * (dl[2 * k - 2] - dl[2 * k - 1]);
+#pragma unroll
+    for (int e = 0; e < WCAP; e++) {
+      T s0 = 0;
+#pragma unroll
+      for (int k = 0; k < NB; k++) s0 = t_fma(d[k], Bv[k][e], s0);
+      if (e < w) acc[dofs[e]] = x[e] + s0;
+    }
+  }
+}
+
 // The same visit when every team of the warp that has a block has one with exactly NB base directions (the common case:
 // most contacts of a scene share a condim): all record offsets are compile-time constants, the parameters arrive as
 // 16-byte vector loads and no row is padded or predicated.  `have` masks the teams that only keep the warp company
@@ -1515,6 +1611,8 @@ __global__ void __launch_bounds__(32, MINB) k_pgs_island(const KArgs<T> a) {
       c.off += len;
       if (c.off >= c.end) { c.isl += ISL; cur_load(c); }
     };
+    // (measured: 16-byte loads in fixed-trip, predicated loops made these four per-solve walks slower than the plain
+    //  loops — more registers and code for work that runs once per solve, profiles/r02_pgs_analysis.txt)
     auto base_dots = [&](const T* rec, const BlockShape& bs, const T* x, T* u) {
 #pragma unroll
       for (int k = 0; k < 6; k++) u[k] = 0;
@@ -1602,7 +1700,7 @@ __global__ void __launch_bounds__(32, MINB) k_pgs_island(const KArgs<T> a) {
         if (done) { c.off = 0; c.end = 0; }
         while (true) {
           const bool have = c.off < c.end;
-          const T* rec = have ? c.base + c.off : slab;
+          const T* rec = have ? c.base + c.off : st;   // (a lane without a block: any valid shared address, never read)
           using V4 = VecN<T, 4>;
           V4 h0, h1;
           if (have) { h0 = *reinterpret_cast<const V4*>(rec); h1 = *reinterpret_cast<const V4*>(rec + 4); }
@@ -1616,7 +1714,13 @@ __global__ void __launch_bounds__(32, MINB) k_pgs_island(const KArgs<T> a) {
           const int nbw = __reduce_max_sync(0xffffffffu, (code >> 4) & 15);
           if (nbw == 0) break;   // no lane of the warp has a block left in this sweep
           const int ww = __reduce_max_sync(0xffffffffu, dec_int(h0.v[2]) >> 10);
-          if (nbw <= 4) {
+          // every lane with a block has a condim-3 contact staged in shared memory (the common step): exact-shape visit
+          const bool ex3 = __all_sync(0xffffffffu, !have || (((code >> 4) & 15) == 3 && c.base != slab));
+          // (an exact visit for condim 4 as well was measured and lost: the extra vote per step costs the tail more than
+          //  the shorter visit gains where condim-4 steps are the minority, profiles/r02_pgs_analysis.txt)
+          if (ex3 && ww <= 8) pgs_visit_lane_exact<T, 3, 8, true>(rec, have, h0, h1, acc, f, improvement);
+          else if (ex3 && ww <= 12) pgs_visit_lane_exact<T, 3, 12, true>(rec, have, h0, h1, acc, f, improvement);
+          else if (nbw <= 4) {
             if (ww <= 8) {
               if (nbw <= 1) pgs_visit_lane<T, 1, 8>(rec, have, h0, h1, acc, f, improvement);
               else if (nbw <= 3) pgs_visit_lane<T, 3, 8>(rec, have, h0, h1, acc, f, improvement);
