@@ -754,19 +754,21 @@ __device__ __forceinline__ void make_blocks_pass(const KArgs<T>& a, const int bl
           A[k][c] = s0a; A[c][k] = s0a;
         }
       }
-      // ---- transpose out J_c | B_c: the lanes of the warp write one environment's runs at a time ----
-      __syncwarp();
-      const int myJ = on ? woff + bs.oJ + c * wq : 0, myB = on ? woff + bs.oB + c * wq : 0, mywq = on ? wq : 0;
-      for (unsigned rem = __ballot_sync(0xffffffffu, on); rem; rem &= rem - 1) {
-        const int e = __ffs(rem) - 1;
-        const int wq_e = __shfl_sync(0xffffffffu, mywq, e), oJ_e = __shfl_sync(0xffffffffu, myJ, e), oB_e = __shfl_sync(0xffffffffu, myB, e);
-        T* dst = a.efc_blocks + slab_env + (long long)e * capw;
-        for (int q = lane; q < wq_e; q += 32) {
-          dst[oJ_e + q] = colsh[(size_t)(npar + q) * LDS + wbase + e];
-          dst[oB_e + q] = colsh[(size_t)(npar + wqmax + q) * LDS + wbase + e];
+      // ---- J_c | B_c leave as 16-byte stores from the thread's own column: every thread writes a contiguous run of its
+      //      environment's slab (whole 32-byte sectors after two stores).  The round-1 form — the warp writing one
+      //      environment's run at a time for 128-byte coalescing — spent ~2500 instructions per block on the ballot / shuffle
+      //      loop for 32-byte runs; the sector writes are the same ----
+      if (on) {
+        using V4 = VecN<T, 4>;
+        T* dst = a.efc_blocks + slab_env + (long long)lane * capw + woff;
+        for (int q = 0; q < wq; q += 4) {
+          V4 vj, vb;
+#pragma unroll
+          for (int c2 = 0; c2 < 4; c2++) { vj.v[c2] = Jc[q + c2]; vb.v[c2] = Bc[q + c2]; }
+          *reinterpret_cast<V4*>(dst + bs.oJ + c * wq + q) = vj;
+          *reinterpret_cast<V4*>(dst + bs.oB + c * wq + q) = vb;
         }
       }
-      __syncwarp();
     }
     if (have) {
       const long long o = (long long)r * S + env;
@@ -799,16 +801,17 @@ __device__ __forceinline__ void make_blocks_pass(const KArgs<T>& a, const int bl
       rec[BH_S1] = enc_int(bs.s1, T()); rec[BH_N1W] = enc_int(bs.n1 + 1024 * w, T()); rec[BH_S2] = enc_int(bs.s2, T());
       rec[BH_R] = R; rec[BH_FL] = fl; rec[BH_LEN] = enc_int(bs.len, T()); rec[BH_ROW0] = enc_int(r, T());
     }
-    // ---- transpose out header + parameters ----
-    __syncwarp();
-    const int mylen = have ? bs.oJ : 0;
-    for (unsigned rem = __ballot_sync(0xffffffffu, have); rem; rem &= rem - 1) {
-      const int e = __ffs(rem) - 1;
-      const int len_e = __shfl_sync(0xffffffffu, mylen, e), off_e = __shfl_sync(0xffffffffu, woff, e);
-      T* dst = a.efc_blocks + slab_env + (long long)e * capw + off_e;
-      for (int q = lane; q < len_e; q += 32) dst[q] = colsh[(size_t)q * LDS + wbase + e];
+    // ---- header + parameters: 16-byte stores from the thread's column ----
+    if (have) {
+      using V4 = VecN<T, 4>;
+      T* dst = a.efc_blocks + slab_env + (long long)lane * capw + woff;
+      for (int q = 0; q < bs.oJ; q += 4) {
+        V4 v;
+#pragma unroll
+        for (int c2 = 0; c2 < 4; c2++) v.v[c2] = rec[q + c2];
+        *reinterpret_cast<V4*>(dst + q) = v;
+      }
     }
-    __syncwarp();
   }
 }
 
