@@ -1583,19 +1583,25 @@ __global__ void __launch_bounds__(32, MINB) k_pgs_island(const KArgs<T> a) {
       // stage the records island by island: island i starts on the bank group of the lane that will walk it (records
       // are whole 128-byte lines, so the lanes of a quarter-warp keep reading disjoint banks while their blocks have
       // the same shape)
-      constexpr int VW = 16 / (int)sizeof(T);
-      using V = VecN<T, VW>;
+      // (asynchronous 16-byte copies, cp.async: no register round trip, every load of the environment in flight at once —
+      //  a load -> store loop serialised on the L2 latency, ~40 k cycles per environment group)
       int pos = 0;
       for (int i = 0; i < nisl; i++) {
         const int o = a.isl_off[(long long)i * S + env], len = a.isl_end[(long long)i * S + env] - o;
         const int start = ((pos + 31) & ~31) + 4 * ((team * ISL + (i % ISL)) & 7);
         const bool fits = start + len <= cap;
         if (fits) {
-          for (int q = l * VW; q < len; q += ISL * VW) *reinterpret_cast<V*>(st + start + q) = *reinterpret_cast<const V*>(slab + o + q);
+          const char* src = reinterpret_cast<const char*>(slab + o);
+          const uint32_t dst = smem_u32(st + start);
+          const int bytes = len * (int)sizeof(T);
+          for (int q = l * 16; q < bytes; q += ISL * 16)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)q), "l"(src + q) : "memory");
           pos = start + len;
         }
         if (l == 0) sto[i] = fits ? start : -1;
       }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     for (int i = l; i < nv; i += ISL) { acc[i] = a.qacc_warmstart[(long long)i * S + env]; tmp[i] = 0; }
     __syncwarp();

@@ -31,6 +31,7 @@ print("work = iters*blocks: mean %.0f p99 %.0f max %d" % (work.mean(), np.quanti
 order = bt.get("env_order")[:, 0]
 wk = work[order[: (nenv // 4) * 4]].reshape(-1, 4)
 print("sum of warp-max work / sum of mean work: %.2f" % (wk.max(1).sum() / wk.mean(1).sum()))
+if os.environ.get('EXP_DISABLE'): bt.set_option('disableflags', int(os.environ['EXP_DISABLE']))
 for cap in [int(x) for x in os.environ.get('EXP_CAPS', '100,20,5').split(',')]:
     bt.set_option("iterations", cap)
     for _ in range(3): tick()
