@@ -314,21 +314,24 @@ struct Importer {
     std::set<std::string> mine;
     gather(name, Frame(), via, parts, kids, mine);
     for (auto& n : mine) if (!open.insert(n).second) ufail("kinematic loop through link '" + n + "'");
-    const std::string in2 = via ? ind + "  " : ind;
-    if (via) {
+    // libmujoco keeps the root link as a body of its own under the world unless it is called "world"; only fusestatic
+    // folds it into the world body
+    const bool as_body = via || (!fusestatic && name != "world");
+    const std::string in2 = as_body ? ind + "  " : ind;
+    if (as_body) {
       out << ind << "<body name=\"" << esc(name) << "\" pos=\"" << fmt(at.p, 3) << "\" quat=\"" << fmt(at.q, 4) << "\">\n";
       std::vector<Inert> inert;
       for (auto& p : parts) inert.push_back(read_inertial(*p.link, p.fr));
       emit_inertial(inert, in2);
-      emit_joint(*via, in2);
+      if (via) emit_joint(*via, in2);
     }
     for (auto& p : parts) emit_geoms(*p.link, in2, p.fr);
     for (auto& k : kids) {
       double p[3], q[4];
       origin_of(k.j->e, p, q);
-      emit_link(k.j->child, k.j, compose(k.fr, p, q), via ? depth + 1 : depth, open);
+      emit_link(k.j->child, k.j, compose(k.fr, p, q), as_body ? depth + 1 : depth, open);
     }
-    if (via) out << ind << "</body>\n";
+    if (as_body) out << ind << "</body>\n";
     for (auto& n : mine) open.erase(n);
   }
 

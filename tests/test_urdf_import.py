@@ -108,7 +108,10 @@ def test_urdf_semantics_and_mjcf_round_trip(b2, orc, tmp_path):
     path2 = tmp_path / "cart_unfused.urdf"
     path2.write_text((URDF % str(tmp_path)).replace('<compiler ', '<compiler fusestatic="false" '))
     mu = b2.Model(str(path2))
-    assert mu.nbody == 5 and [mu.id2name(1, b) for b in range(1, 5)] == ["slider", "pole", "tip", "wheel"] and mu.body_dofnum[3] == 0
+    # (as in libmujoco, the root link is then a body of its own under the world — it would only be the world body if it were
+    #  called "world")
+    assert mu.nbody == 6 and [mu.id2name(1, b) for b in range(1, 6)] == ["base", "slider", "pole", "tip", "wheel"] and mu.body_dofnum[4] == 0
+    assert mu.body_dofnum[1] == 0 and mu.body_parentid[1] == 0 and mu.geom_bodyid[0] == 1
     np.testing.assert_allclose(mu.geom_size, m.geom_size)
     df, du = b2.Data(m), b2.Data(mu)
     for q, v, f in [([0.1, 0.4, -0.3], [0.2, -0.5, 0.7], [1.0, -0.2, 0.05]), ([-0.3, 2.0, 0.5], [-1.0, 1.5, 0.2], [0.0, 0.3, -0.1])]:
