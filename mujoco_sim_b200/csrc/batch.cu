@@ -339,7 +339,7 @@ int configure_constraint_kernels(b2_batch* b) {
       // k_pgs_island: EPB environments per one-warp CTA, each with its vectors and its staged records; the stage is sized
       // for eight resident CTAs per SM
       const int epbi = 32 / b->pgs_isl;
-      const long long fixedi = ((long long)2 * (b->hdr.nv + 4) + ((b->hdr.njmax + 3) & ~3)) * b->prec + (long long)b->isl_cap * 4;
+      const long long fixedi = ((long long)2 * ((b->hdr.nv + 7) & ~3) + ((b->hdr.njmax + 3) & ~3)) * b->prec + (long long)b->isl_cap * 4;
       long long capi = getenv("B2_PGS_STAGE") ? atoi(getenv("B2_PGS_STAGE")) : (long long)((220 * 1024 / 8) / epbi - fixedi) / b->prec;
       capi = std::max(0LL, std::min<long long>(capi, b->block_capw)) & ~3LL;
       b->isl_stage = (int)capi;
@@ -349,9 +349,9 @@ int configure_constraint_kernels(b2_batch* b) {
     // (k_make_blocks reads the model from HBM: its shared memory is the record columns only)
     b->make_block = (size_t)b->rec_max * 129 * b->prec <= 56 * 1024 ? 128 : 32;
     const int need2 = (int)((size_t)b->rec_max * (b->make_block + 1) * b->prec);
-    // solver: per environment 2 (b->hdr.nv + 4) + njmax words of vectors plus the staged records; sized for ~4 CTAs per SM
+    // solver: per environment 2 ((b->hdr.nv + 7) & ~3) + njmax words of vectors plus the staged records; sized for ~4 CTAs per SM
     const int epb = 128 / b->pgs_lanes;
-    const long long fixed = (long long)b->blob_smem + ((long long)2 * (b->hdr.nv + 4) + b->hdr.njmax) * epb * b->prec;
+    const long long fixed = (long long)b->blob_smem + ((long long)2 * ((b->hdr.nv + 7) & ~3) + ((b->hdr.njmax + 3) & ~3)) * epb * b->prec;
     // staging an environment's records in shared memory lost to plain L1-cached streaming once the records became compact
     // (profiles/r01_pgs_variants.txt): off unless asked for
     long long cap = getenv("B2_PGS_STAGE") ? atoi(getenv("B2_PGS_STAGE")) : 0;
@@ -567,14 +567,14 @@ int run_tick(b2_batch* b, int flags) {
       if (b->isl_cap) {
         // several small trees: one lane per constraint island (k_pgs_island)
         const int epbi = 32 / b->pgs_isl;
-        const size_t smi = ((size_t)2 * (b->hdr.nv + 4) + ((b->hdr.njmax + 3) & ~3) + b->isl_stage) * epbi * sizeof(T) + (size_t)epbi * b->isl_cap * sizeof(int);
+        const size_t smi = ((size_t)2 * ((b->hdr.nv + 7) & ~3) + ((b->hdr.njmax + 3) & ~3) + b->isl_stage) * epbi * sizeof(T) + (size_t)epbi * b->isl_cap * sizeof(int);
         const int gi = b->nenvp / epbi;
         if (b->pgs_isl == 4) k_pgs_island<T, 4, PGS_ISL_MINB><<<gi, 32, smi, b->stream>>>(a);
         else if (b->pgs_isl == 16) k_pgs_island<T, 16, PGS_ISL_MINB><<<gi, 32, smi, b->stream>>>(a);
         else k_pgs_island<T, 8, PGS_ISL_MINB><<<gi, 32, smi, b->stream>>>(a);
       } else {
       const int epb = PB / b->pgs_lanes;
-      const size_t smp = ((size_t)2 * (b->hdr.nv + 4) + b->hdr.njmax + b->stage_cap) * epb * sizeof(T);
+      const size_t smp = ((size_t)2 * ((b->hdr.nv + 7) & ~3) + ((b->hdr.njmax + 3) & ~3) + b->stage_cap) * epb * sizeof(T);
       const int g3 = b->nenvp / epb;
       if (b->pgs_lanes == 4) k_pgs_block<T, 4, PB, PGS_MINB><<<g3, PB, smp, b->stream>>>(a);
       else if (b->pgs_lanes == 16) k_pgs_block<T, 16, PB, PGS_MINB><<<g3, PB, smp, b->stream>>>(a);

@@ -1304,16 +1304,16 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_pgs_block(const KArgs<T> a) {
   const long long S = a.nenvp;
   constexpr int EPB = BLOCK / LANES;  // environments per CTA
   const int nv = h.nv, njmax = h.njmax, capw = a.block_capw, cap = a.stage_cap;
-  const int nvs = nv + 4;  // stride of the per-environment vectors (skews the teams over the banks)
+  const int nvs = (nv + 7) & ~3;  // stride of the per-environment vectors: nv + 4 (skews the teams over the banks), rounded so that the staged records behind them stay 16 / 32-byte aligned
   T* accsh = reinterpret_cast<T*>(smem_raw);                             // [EPB][nvs] running acceleration
   T* tmpsh = accsh + (size_t)EPB * nvs;                                   // [EPB][nvs] M^-1 J^T f, later qfrc_constraint
   T* fsh = tmpsh + (size_t)EPB * nvs;                                     // [EPB][njmax] forces
-  T* stsh = fsh + (size_t)EPB * njmax;                                    // [EPB][cap] staged records
+  T* stsh = fsh + (size_t)EPB * ((njmax + 3) & ~3);                       // [EPB][cap] staged records
   const int team = threadIdx.x / LANES, l = threadIdx.x % LANES;
   const unsigned tmask = (LANES == 32 ? 0xffffffffu : ((1u << LANES) - 1u)) << ((threadIdx.x & 31) & ~(LANES - 1));
   T* acc = accsh + (size_t)team * nvs;
   T* tmp = tmpsh + (size_t)team * nvs;
-  T* f = fsh + (size_t)team * njmax;
+  T* f = fsh + (size_t)team * ((njmax + 3) & ~3);
   T* st = stsh + (size_t)team * cap;
   const int ngroups = (a.nenvp + EPB - 1) / EPB;
   const T tol = m.f(h.o_opt_real, 3), scale = 1 / (m.f(h.o_opt_real, 4) * T(nv > 1 ? nv : 1));
@@ -1446,7 +1446,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_pgs_block(const KArgs<T> a) {
             const int nxt = off + len < nw ? off + len : 0;
             nh0 = *reinterpret_cast<const V4*>(slab + nxt); nh1 = *reinterpret_cast<const V4*>(slab + nxt + 4);
             const int pq = nxt + l * (128 / (int)sizeof(T));
-            if (pq < nw && l < 5) asm volatile("prefetch.global.L1 [%0];" ::"l"(slab + pq));
+            if (pq < nw && l < 16) asm volatile("prefetch.global.L1 [%0];" ::"l"(slab + pq));
           }
           // one instruction stream for the whole warp: the exact-shape visit when every team that has a block has the same
           // condim and fits two elements per lane, else the padded generic visit
@@ -1552,7 +1552,7 @@ __global__ void __launch_bounds__(32, MINB) k_pgs_island(const KArgs<T> a) {
   const long long S = a.nenvp;
   constexpr int EPB = 32 / ISL;
   const int nv = h.nv, njmax = h.njmax, capw = a.block_capw, cap = a.stage_cap;
-  const int nvs = nv + 4;
+  const int nvs = (nv + 7) & ~3;   // (nv + 4 rounded up to a multiple of 4: the staged records behind stay aligned)
   T* accsh = reinterpret_cast<T*>(smem_raw);
   T* tmpsh = accsh + (size_t)EPB * nvs;
   T* fsh = tmpsh + (size_t)EPB * nvs;
