@@ -340,7 +340,14 @@ int configure_constraint_kernels(b2_batch* b) {
       // for eight resident CTAs per SM
       const int epbi = 32 / b->pgs_isl;
       const long long fixedi = ((long long)2 * ((b->hdr.nv + 7) & ~3) + ((b->hdr.njmax + 3) & ~3)) * b->prec + (long long)b->isl_cap * 4;
-      long long capi = getenv("B2_PGS_STAGE") ? atoi(getenv("B2_PGS_STAGE")) : (long long)((220 * 1024 / 8) / epbi - fixedi) / b->prec;
+      // what fits eight resident CTAs per SM, raised — down to four CTAs — towards the record volume a busy environment
+      // has (a quarter of the contact cap, each a largest-shape record): measured on C5, whose environments carry 2200
+      // words on average: 2304 staged words 1.84 ms, 1232 (eight CTAs) 2.34 ms, 3328 2.07 ms
+      int nbmx = 1;
+      for (int g = 0; g < b->m->ngeom; g++) nbmx = std::max(nbmx, b->m->geom_condim[g]);
+      const long long fit8 = (long long)((220 * 1024 / 8) / epbi - fixedi) / b->prec, fit4 = (long long)((220 * 1024 / 4) / epbi - fixedi) / b->prec;
+      const long long busy = (long long)(b->hdr.nconmax / 4) * block_max_words(std::min(nbmx, 6), b->hdr.wmax);
+      long long capi = getenv("B2_PGS_STAGE") ? atoi(getenv("B2_PGS_STAGE")) : std::max(fit8, std::min(busy, fit4));
       capi = std::max(0LL, std::min<long long>(capi, b->block_capw)) & ~3LL;
       b->isl_stage = (int)capi;
     }
