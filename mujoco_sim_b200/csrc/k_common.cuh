@@ -72,6 +72,20 @@ __device__ __forceinline__ void stage_model(uint32_t* dst, const uint32_t* src, 
   stage_model_wait(bar);
 }
 
+// The CTA's threads put rows [0, nrows) of an [element][env] array in flight towards L1 for its `nenvs` consecutive
+// environments starting at env0 (one prefetch per 128-byte line): the thread-per-environment stages walk these arrays
+// element by element inside dependent chains, so without this every first touch is a serialised L2 / HBM round trip.
+template <typename T>
+__device__ __forceinline__ void prefetch_rows(const T* base, int nrows, long long S, int env0, int nenvs) {
+  if (!base) return;
+  constexpr int PER_LINE = 128 / (int)sizeof(T);
+  const int nlines = (nenvs + PER_LINE - 1) / PER_LINE;
+  for (int idx = threadIdx.x; idx < nrows * nlines; idx += blockDim.x) {
+    const int r = idx / nlines, ln = idx % nlines;
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(base + (long long)r * S + env0 + ln * PER_LINE));
+  }
+}
+
 // ---------- small math (registers) ----------
 template <typename T> __device__ __forceinline__ T t_sqrt(T x);
 template <> __device__ __forceinline__ float t_sqrt<float>(float x) { return sqrtf(x); }

@@ -1857,6 +1857,12 @@ __global__ void __launch_bounds__(BLOCK) k_integrate(const KArgs<T> a) {
   for (int tile = blockIdx.x; tile < nteams; tile += gridDim.x) {
     const int env = tile * EPB + envl;
     const int nv = h.nv;
+    prefetch_rows(a.qacc, nv, S, tile * EPB, EPB);
+    if (a.flags & B2F_INTEGRATE) {
+      prefetch_rows(a.qvel, nv, S, tile * EPB, EPB);
+      prefetch_rows(a.qpos, h.nq, S, tile * EPB, EPB);
+      if (h.has_damping) { prefetch_rows(a.qM, h.nM, S, tile * EPB, EPB); prefetch_rows(a.qfrc_smooth, nv, S, tile * EPB, EPB); prefetch_rows(a.qfrc_constraint, nv, S, tile * EPB, EPB); }
+    }
     const bool skip = (a.flags & B2F_FUSABLE) && (a.status[env] & 8);   // integrated by the smooth kernel already
     SArr<T> qacc{a.qacc + env, S};
     bool bad = false;

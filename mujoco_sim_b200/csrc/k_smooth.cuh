@@ -717,6 +717,14 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_smooth(const KArgs<T> a) {
 
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int env = tile * EPB + envl;
+    if constexpr (!P::STATIC) {
+      // the state this tile reads, in flight at once
+      prefetch_rows(a.qpos, nq, S, tile * EPB, EPB);
+      prefetch_rows(a.qvel, nv, S, tile * EPB, EPB);
+      prefetch_rows(a.qfrc_applied, nv, S, tile * EPB, EPB);
+      if (a.flags & B2F_INVERSE) prefetch_rows(a.qacc, nv, S, tile * EPB, EPB);
+      if (a.flags & B2F_CONTROLLER) { prefetch_rows(a.ddq, nv, S, tile * EPB, EPB); prefetch_rows(a.dq, nv, S, tile * EPB, EPB); }
+    }
     T* wsbase = (a.flags & B2F_WS_GLOBAL) ? a.ws + env : ws_sh + envl;
     const long long wss = (a.flags & B2F_WS_GLOBAL) ? S : EPB;
     Smooth<T, P> s(m, a, wsbase, wss, env);
