@@ -60,7 +60,10 @@ int b2_set_controlled(b2_batch* b, const unsigned char* mask);
  * qposadr[3*r+k] = qpos address of the angular x,y,z odom joints (-1: absent -> angle 0) */
 int b2_set_odom(b2_batch* b, int nrobot, const int* dof, const int* qposadr);
 int b2_set_timestep(b2_batch* b, double h);
-int b2_set_option(b2_batch* b, const char* name, double value); /* iterations, tolerance, disableflags */
+/* iterations, tolerance, disableflags (mjOption); scheduling only, results do not depend on them: subbatches (1..8,
+ * default 4: windows of the batch that run the tick's kernels side by side on their own streams) and subbatch_min
+ * (smallest window in environments, default 2048; a batch too small for two such windows is one window) */
+int b2_set_option(b2_batch* b, const char* name, double value);
 
 /* field access by MuJoCo name: qpos qvel qacc qacc_warmstart qfrc_applied xfrc_applied mocap_pos mocap_quat ddq dq
  * odom_vels time qfrc_bias qfrc_inverse xpos xquat xmat geom_xpos geom_xmat subtree_com cdof qM qLD qLDiagInv

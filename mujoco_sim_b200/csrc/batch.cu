@@ -273,7 +273,7 @@ KArgs<T> build_args(b2_batch* b) {
   std::memset(&a, 0, sizeof(a));
   a.model = b->blob_dev;
   a.model_words = b->hdr.nwords;
-  a.nenv = b->nenv; a.nenvp = b->nenvp;
+  a.nenv = b->nenv; a.nenvp = b->nenvp; a.ncount = b->nenvp; a.env_base = 0;
   auto R = [&](const char* n) { auto it = b->fields.find(n); return it == b->fields.end() ? (T*)nullptr : (T*)it->second.ptr; };
   auto I = [&](const char* n) { auto it = b->fields.find(n); return it == b->fields.end() ? (int*)nullptr : (int*)it->second.ptr; };
   a.qpos = R("qpos"); a.qvel = R("qvel"); a.qacc = R("qacc"); a.qacc_warmstart = R("qacc_warmstart");
@@ -313,6 +313,31 @@ KArgs<T> make_args(b2_batch* b, int flags) {
   a.hw_vel = b->io_in[0]; a.hw_eff = b->io_in[1];
   a.hw_pos = b->io_out[0]; a.hw_velo = b->io_out[1]; a.hw_effo = b->io_out[2];
   a.hw_kp = b->hw_kp; a.hw_kd = b->hw_kd;
+  return a;
+}
+
+// Sub-batch window [lo, lo + n) of the batch: every pointer advanced to the window's first environment (SoA arrays keep
+// the batch's environment stride nenvp, environment-major slabs move by whole slabs), counters get the window's own
+// word.  The kernels index environments from 0 and cover `ncount` of them, so a window is launched exactly like a batch.
+template <typename T>
+KArgs<T> window_args(KArgs<T> a, int s, int lo, int n) {
+  auto adv = [&](auto*& p, long long per_env = 1) { if (p) p += (long long)lo * per_env; };
+  adv(a.qpos); adv(a.qvel); adv(a.qacc); adv(a.qacc_warmstart); adv(a.qfrc_applied); adv(a.xfrc_applied); adv(a.mocap_pos); adv(a.mocap_quat);
+  adv(a.ddq); adv(a.dq); adv(a.odom_vels); adv(a.time); adv(a.qfrc_bias); adv(a.qfrc_inverse); adv(a.xpos); adv(a.xquat);
+  adv(a.xmat); adv(a.geom_xpos); adv(a.geom_xmat); adv(a.subtree_com); adv(a.cdof); adv(a.qM); adv(a.qLD); adv(a.qLDiagInv);
+  adv(a.qfrc_passive); adv(a.qfrc_smooth); adv(a.qacc_smooth); adv(a.qfrc_constraint); adv(a.ws);
+  adv(a.con); adv(a.coni); adv(a.ncon); adv(a.nefc); adv(a.efc_type); adv(a.efc_id); adv(a.efc_tree); adv(a.efc_J);
+  adv(a.efc_pos); adv(a.efc_margin); adv(a.efc_frictionloss); adv(a.efc_diagApprox); adv(a.efc_R); adv(a.efc_D); adv(a.efc_KBI);
+  adv(a.efc_vel); adv(a.efc_aref); adv(a.efc_b); adv(a.efc_force); adv(a.efc_finv); adv(a.efc_ARdiag); adv(a.efc_B);
+  adv(a.efc_Jem, (long long)a.em_rows * 64); adv(a.efc_Bem, (long long)a.em_rows * 64); adv(a.minv_em, 64 * 64);
+  adv(a.efc_blocks, a.block_capw);
+  adv(a.efc_nwords); adv(a.env_order); adv(a.blk_row0); adv(a.blk_off); adv(a.nblk); adv(a.isl_off); adv(a.isl_end); adv(a.nisl);
+  adv(a.solver_iter); adv(a.status);
+  if (a.maxblk) a.maxblk += s;
+  if (a.pending) a.pending += s;
+  a.env_base = lo;
+  a.ncount = n;
+  a.nenv = std::max(0, std::min(n, a.nenv - lo));
   return a;
 }
 
@@ -414,15 +439,15 @@ int configure_constraint_kernels(b2_batch* b) {
 }
 
 template <typename T, int BLOCK, typename P, int L = 1>
-int launch_smooth(b2_batch* b, const KArgs<T>& a, int grid) {
+int launch_smooth(b2_batch* b, const KArgs<T>& a, int grid, cudaStream_t st) {
   static bool attr_set[8] = {false};
   int dev = b->device & 7;
   if (!attr_set[dev]) {
-    constexpr int MB = L > 1 ? 3 : 1;   // tree-parallel form: three CTAs per SM (170 registers)
+    constexpr int MB = L > 1 ? 2 : 1;   // tree-parallel form: two CTAs per SM (255 registers: no spills; one wave at the BASELINE batch sizes)
     CK(cudaFuncSetAttribute(k_smooth<T, BLOCK, P, MB, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set[dev] = true;
   }
-  k_smooth<T, BLOCK, P, (L > 1 ? 3 : 1), L><<<grid, BLOCK, b->smooth_smem, b->stream>>>(a);
+  k_smooth<T, BLOCK, P, (L > 1 ? 2 : 1), L><<<grid, BLOCK, b->smooth_smem, st>>>(a);
   b->launches++;
   return 0;
 }
@@ -452,6 +477,17 @@ int hold_slots(b2_batch* b) {
   return 0;
 }
 
+int ensure_sub_streams(b2_batch* b, int nsub) {
+  if (!b->sub_fork) CK(cudaEventCreateWithFlags(&b->sub_fork, cudaEventDisableTiming));
+  while ((int)b->sub_stream.size() < nsub - 1) {
+    cudaStream_t st; cudaEvent_t ev;
+    CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    b->sub_stream.push_back(st); b->sub_join.push_back(ev);
+  }
+  return 0;
+}
+
 template <typename T>
 int run_tick(b2_batch* b, int flags) {
   int kf = 0;
@@ -478,15 +514,19 @@ int run_tick(b2_batch* b, int flags) {
   const bool hwio = single && (flags & B2_TICK_HW) && b->hw_identity && (kf & B2F_CONTROLLER) && !(kf & B2F_ODOM) && !getenv("B2_NO_HWIO");
   if (hwio) kf |= B2F_HWIO;
   KArgs<T> a = make_args<T>(b, kf);
-  const int ntiles = b->nenvp / (b->smooth_block / (b->chain_n > 0 ? 1 : b->tree_lanes));
   int per_sm = (int)std::max<size_t>(1, (227 * 1024) / std::max<size_t>(1, b->smooth_smem));
+  if (b->chain_n == 0 && b->tree_lanes > 1) per_sm = std::min(per_sm, 2);   // (its launch bounds: two resident CTAs per SM)
   if (getenv("B2_SMOOTH_CTAS_PER_SM")) per_sm = std::max(1, atoi(getenv("B2_SMOOTH_CTAS_PER_SM")));
-  const int grid = std::max(1, std::min(ntiles, b->nsm * per_sm));
+  auto smooth_grid = [&](int n) {
+    const int ntiles = n / (b->smooth_block / (b->chain_n > 0 ? 1 : b->tree_lanes));
+    return std::max(1, std::min(ntiles, b->nsm * per_sm));
+  };
   int rc;
   const bool read_post = (flags & B2_TICK_READ_POST) != 0;
   if ((flags & B2_TICK_HW) && !hwio) { if (hw_write_async(b, flags, !read_post) < 0) return -1; }
   if (single) {
     // limit-only serial chain: one kernel does the whole tick (k_chain.cuh)
+    const int grid = smooth_grid(b->nenvp);
     prof_mark(b, SLOT_SMOOTH);
     if (b->chain_team) { if constexpr (sizeof(T) == 4) rc = launch_chain_team_f32(b, a); else rc = launch_chain_team_f64(b, a); }
     else if constexpr (sizeof(T) == 4) rc = launch_chain1_f32(b, a, grid); else rc = launch_chain1_f64(b, a, grid);
@@ -497,23 +537,27 @@ int run_tick(b2_batch* b, int flags) {
     CK(cudaGetLastError());
     return 0;
   }
-  if (b->fusable) CK(cudaMemsetAsync(a.pending, 0, sizeof(int), b->stream));
+  // The kernels of the pipeline for the environments of one window, on one stream.  (prof_mark records on the batch's
+  // stream: per-kernel profiling runs the batch as a single window.)
+  auto pipeline = [&](const KArgs<T>& a, cudaStream_t st, int n) -> int {
+  if (b->fusable) CK(cudaMemsetAsync(a.pending, 0, sizeof(int), st));
   prof_mark(b, SLOT_SMOOTH);
+  const int grid = smooth_grid(n);
   if (b->chain_n > 0) rc = launch_chain<T>(b, a, grid);
   else switch (b->smooth_block) {
     case 128:
-      if (b->tree_lanes == 8) rc = launch_smooth<T, 128, GenericP, 8>(b, a, grid);
-      else if (b->tree_lanes == 4) rc = launch_smooth<T, 128, GenericP, 4>(b, a, grid);
-      else if (b->tree_lanes == 2) rc = launch_smooth<T, 128, GenericP, 2>(b, a, grid);
-      else rc = launch_smooth<T, 128, GenericP>(b, a, grid);
+      if (b->tree_lanes == 8) rc = launch_smooth<T, 128, GenericP, 8>(b, a, grid, st);
+      else if (b->tree_lanes == 4) rc = launch_smooth<T, 128, GenericP, 4>(b, a, grid, st);
+      else if (b->tree_lanes == 2) rc = launch_smooth<T, 128, GenericP, 2>(b, a, grid, st);
+      else rc = launch_smooth<T, 128, GenericP>(b, a, grid, st);
       break;
-    case 64: rc = launch_smooth<T, 64, GenericP>(b, a, grid); break;
-    default: rc = launch_smooth<T, 32, GenericP>(b, a, grid); break;
+    case 64: rc = launch_smooth<T, 64, GenericP>(b, a, grid, st); break;
+    default: rc = launch_smooth<T, 32, GenericP>(b, a, grid, st); break;
   }
   if (rc < 0) return rc;
   if (!b->fused) {
     constexpr int BL = 128;
-    const int nt = b->nenvp / BL;
+    const int nt = n / BL;
     const int g2 = std::max(1, std::min(nt, b->nsm * 4));
     const size_t sm = b->blob_smem;
     prof_mark(b, SLOT_COLLIDE);
@@ -521,52 +565,62 @@ int run_tick(b2_batch* b, int flags) {
       // a team of 8 lanes per environment: 16 environments per CTA, the candidate list of each behind the model blob
       constexpr int CL = 8;
       const size_t smc = 16 + (((size_t)b->hdr.nwords * 4 + 15) & ~(size_t)15) + (size_t)(BL / CL) * ((b->m->npair + 1) & ~1) * sizeof(uint16_t);
-      const int gc = std::max(1, std::min(b->nenvp / (BL / CL), b->nsm * std::max(1, std::min(8, (int)(200 * 1024 / smc)))));
-      k_collide<T, BL, CL><<<gc, BL, smc, b->stream>>>(a);
+      const int gc = std::max(1, std::min(n / (BL / CL), b->nsm * std::max(1, std::min(8, (int)(200 * 1024 / smc)))));
+      k_collide<T, BL, CL><<<gc, BL, smc, st>>>(a);
       b->launches++;
     }
     prof_mark(b, SLOT_MAKE);
-    CK(cudaMemsetAsync(a.maxblk, 0, sizeof(int), b->stream));
+    CK(cudaMemsetAsync(a.maxblk, 0, sizeof(int), st));
     {
       constexpr int RL = 8;   // lanes per environment
-      const int gr = std::max(1, std::min(b->nenvp / (BL / RL), b->nsm * std::max(1, std::min(8, (int)(220 * 1024 / (sm + b->row_smem + b->isl_smem + 1024))))));
-      k_make_rows<T, BL, RL><<<gr, BL, sm + b->row_smem + b->isl_smem, b->stream>>>(a);
+      // persistent CTAs: as many as are resident at once (registers or shared memory, whichever binds)
+      static int occ_cache[2] = {0, 0};
+      static size_t occ_smem[2] = {0, 0};
+      const int oi = sizeof(T) == 8;
+      const size_t smr = sm + b->row_smem + b->isl_smem;
+      if (!occ_cache[oi] || occ_smem[oi] != smr) {
+        int occ = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_make_rows<T, BL, RL>, BL, smr) != cudaSuccess || occ < 1) { occ = 1; cudaGetLastError(); }
+        occ_cache[oi] = occ; occ_smem[oi] = smr;
+      }
+      const int gr = std::max(1, std::min(n / (BL / RL), b->nsm * occ_cache[oi]));
+      k_make_rows<T, BL, RL><<<gr, BL, smr, st>>>(a);
     }
     if (b->tc_rows > 0) {
       // one-tree model, fp32: dense M^-1 per environment, then B = J M^-1 on the tensor cores (k_project_tc.cuh)
       if constexpr (sizeof(T) == 4) {
         constexpr int MR = 8;
         const size_t smm = 16 + (((size_t)b->hdr.nwords * 4 + 15) & ~(size_t)15) + ((size_t)2 * b->hdr.nM + b->hdr.nv + (size_t)MR * b->hdr.nv) * 32 * sizeof(T);
-        const int gm = std::max(1, std::min(b->nenvp / 32, b->nsm * std::max(1, (int)(227 * 1024 / (smm + 1024)))));
-        k_dense_minv<T, MR><<<gm, 32 * MR, smm, b->stream>>>(a);
+        const int gm = std::max(1, std::min(n / 32, b->nsm * std::max(1, (int)(227 * 1024 / (smm + 1024)))));
+        k_dense_minv<T, MR><<<gm, 32 * MR, smm, st>>>(a);
         const size_t smt = 2 * tc::A_BYTES + 2 * tc::B_BYTES;
-        k_project_tc<<<std::min(b->nenvp, 2 * b->nsm), 128, smt, b->stream>>>(a.efc_Jem, a.minv_em, a.efc_Bem, a.nefc, b->nenvp, b->tc_rows / tc::TM, b->tc_rows, b->tc_passes);
+        k_project_tc<<<std::min(n, 2 * b->nsm), 128, smt, st>>>(a.efc_Jem, a.minv_em, a.efc_Bem, a.nefc, n, b->tc_rows / tc::TM, b->tc_rows, b->tc_passes);
         b->launches += 2;
       }
     } else if (b->solve_rows > 0) {
       // wide trees: M^-1 J^T of all rows up front, the tile's factor shared through shared memory (k_solve_rows)
-      const int gs = std::max(1, std::min(b->nenvp / 32, b->nsm * std::max(1, (int)(227 * 1024 / (b->solve_smem + 1024)))));
-      if (b->solve_rows == 16) k_solve_rows<T, 16><<<gs, 512, b->solve_smem, b->stream>>>(a);
-      else if (b->solve_rows == 8) k_solve_rows<T, 8><<<gs, 256, b->solve_smem, b->stream>>>(a);
-      else k_solve_rows<T, 4><<<gs, 128, b->solve_smem, b->stream>>>(a);
+      const int gs = std::max(1, std::min(n / 32, b->nsm * std::max(1, (int)(227 * 1024 / (b->solve_smem + 1024)))));
+      if (b->solve_rows == 16) k_solve_rows<T, 16><<<gs, 512, b->solve_smem, st>>>(a);
+      else if (b->solve_rows == 8) k_solve_rows<T, 8><<<gs, 256, b->solve_smem, st>>>(a);
+      else k_solve_rows<T, 4><<<gs, 128, b->solve_smem, st>>>(a);
       b->launches++;
     }
     {
       // one thread per (block, environment); CTAs of block ordinals beyond this tick's largest count exit at once
       const int mb = b->make_block;
       // (block ordinals beyond grid.y are covered by a loop inside the kernel: a grid of njmax rows was mostly CTAs that exit at once)
-      const dim3 gb(std::max(1, std::min(b->nenvp / mb, b->nsm * 8)), std::min(b->hdr.njmax, 32));
-      if (mb == 128) k_make_blocks<T, 128><<<gb, 128, (size_t)b->rec_max * 129 * sizeof(T), b->stream>>>(a);
-      else k_make_blocks<T, 32><<<gb, 32, (size_t)b->rec_max * 33 * sizeof(T), b->stream>>>(a);
+      const dim3 gb(std::max(1, std::min(n / mb, b->nsm * 8)), std::min(b->hdr.njmax, 32));
+      if (mb == 128) k_make_blocks<T, 128><<<gb, 128, (size_t)b->rec_max * 129 * sizeof(T), st>>>(a);
+      else k_make_blocks<T, 32><<<gb, 32, (size_t)b->rec_max * 33 * sizeof(T), st>>>(a);
     }
     b->launches += 2;
     if ((flags & B2_TICK_NOSOLVE) && (kf & B2F_INVERSE)) {   // mj_inverse through the shim: no solver pass to fold this into
-      k_inverse_rows<T><<<(b->nenvp + 127) / 128, 128, 0, b->stream>>>(a);
+      k_inverse_rows<T><<<(n + 127) / 128, 128, 0, st>>>(a);
       b->launches += 1;
     }
     if (!(flags & B2_TICK_NOSOLVE)) {
       prof_mark(b, SLOT_PGS);
-      k_order_envs<256, 1024><<<1, 1024, 0, b->stream>>>(a.nefc, a.efc_nwords, a.env_order, b->nenvp, std::max(4, b->block_capw / 256), a.pending, b->fusable ? 1 : 0);
+      k_order_envs<256, 1024><<<1, 1024, 0, st>>>(a.nefc, a.efc_nwords, a.env_order, n, std::max(4, b->block_capw / 256), a.pending, b->fusable ? 1 : 0);
       b->launches += 1;
       // one warp per CTA and one CTA per group of environments: the hardware scheduler balances the very uneven
       // per-environment work (contact counts) dynamically
@@ -575,38 +629,61 @@ int run_tick(b2_batch* b, int flags) {
         // several small trees: one lane per constraint island (k_pgs_island)
         const int epbi = 32 / b->pgs_isl;
         const size_t smi = ((size_t)2 * ((b->hdr.nv + 7) & ~3) + ((b->hdr.njmax + 3) & ~3) + b->isl_stage) * epbi * sizeof(T) + (size_t)epbi * b->isl_cap * sizeof(int);
-        const int gi = b->nenvp / epbi;
-        if (b->pgs_isl == 4) k_pgs_island<T, 4, PGS_ISL_MINB><<<gi, 32, smi, b->stream>>>(a);
-        else if (b->pgs_isl == 16) k_pgs_island<T, 16, PGS_ISL_MINB><<<gi, 32, smi, b->stream>>>(a);
-        else k_pgs_island<T, 8, PGS_ISL_MINB><<<gi, 32, smi, b->stream>>>(a);
+        const int gi = n / epbi;
+        if (b->pgs_isl == 4) k_pgs_island<T, 4, PGS_ISL_MINB><<<gi, 32, smi, st>>>(a);
+        else if (b->pgs_isl == 16) k_pgs_island<T, 16, PGS_ISL_MINB><<<gi, 32, smi, st>>>(a);
+        else k_pgs_island<T, 8, PGS_ISL_MINB><<<gi, 32, smi, st>>>(a);
       } else {
       const int epb = PB / b->pgs_lanes;
       const size_t smp = ((size_t)2 * ((b->hdr.nv + 7) & ~3) + ((b->hdr.njmax + 3) & ~3) + b->stage_cap) * epb * sizeof(T);
-      const int g3 = b->nenvp / epb;
-      if (b->pgs_lanes == 4) k_pgs_block<T, 4, PB, PGS_MINB><<<g3, PB, smp, b->stream>>>(a);
-      else if (b->pgs_lanes == 16) k_pgs_block<T, 16, PB, PGS_MINB><<<g3, PB, smp, b->stream>>>(a);
-      else if (b->pgs_lanes == 32) k_pgs_block<T, 32, PB, PGS_MINB><<<g3, PB, smp, b->stream>>>(a);
-      else k_pgs_block<T, 8, PB, PGS_MINB><<<g3, PB, smp, b->stream>>>(a);
+      const int g3 = n / epb;
+      if (b->pgs_lanes == 4) k_pgs_block<T, 4, PB, PGS_MINB><<<g3, PB, smp, st>>>(a);
+      else if (b->pgs_lanes == 16) k_pgs_block<T, 16, PB, PGS_MINB><<<g3, PB, smp, st>>>(a);
+      else if (b->pgs_lanes == 32) k_pgs_block<T, 32, PB, PGS_MINB><<<g3, PB, smp, st>>>(a);
+      else k_pgs_block<T, 8, PB, PGS_MINB><<<g3, PB, smp, st>>>(a);
       }
       prof_mark(b, SLOT_INTEGRATE);
       const int TL = b->chain_n > 0 ? 1 : b->tree_lanes;
       if (TL > 1) {
         // tree-parallel: 128 threads = 128 / TL environments per CTA
         const size_t smi = sm + ((kf & B2F_LD_SMEM) ? b->ld_smem : 0);
-        const int gi = std::max(1, std::min(b->nenvp / (128 / TL), b->nsm * 8));
-        if (TL == 8) k_integrate<T, 128, 8><<<gi, 128, smi, b->stream>>>(a);
-        else if (TL == 4) k_integrate<T, 128, 4><<<gi, 128, smi, b->stream>>>(a);
-        else k_integrate<T, 128, 2><<<gi, 128, smi, b->stream>>>(a);
+        const int gi = std::max(1, std::min(n / (128 / TL), b->nsm * 8));
+        if (TL == 8) k_integrate<T, 128, 8><<<gi, 128, smi, st>>>(a);
+        else if (TL == 4) k_integrate<T, 128, 4><<<gi, 128, smi, st>>>(a);
+        else k_integrate<T, 128, 2><<<gi, 128, smi, st>>>(a);
       } else if (kf & B2F_LD_SMEM) {
         const size_t smi = sm + b->ld_smem;
-        const int bi = b->smooth_block, gi = std::max(1, std::min(b->nenvp / bi, b->nsm * 8));
-        if (bi == 128) k_integrate<T, 128><<<gi, 128, smi, b->stream>>>(a);
-        else if (bi == 64) k_integrate<T, 64><<<gi, 64, smi, b->stream>>>(a);
-        else k_integrate<T, 32><<<gi, 32, smi, b->stream>>>(a);
+        const int bi = b->smooth_block, gi = std::max(1, std::min(n / bi, b->nsm * 8));
+        if (bi == 128) k_integrate<T, 128><<<gi, 128, smi, st>>>(a);
+        else if (bi == 64) k_integrate<T, 64><<<gi, 64, smi, st>>>(a);
+        else k_integrate<T, 32><<<gi, 32, smi, st>>>(a);
       } else {
-        k_integrate<T, BL><<<g2, BL, sm, b->stream>>>(a);
+        k_integrate<T, BL><<<g2, BL, sm, st>>>(a);
       }
       b->launches += 2;
+    }
+  }
+  return 0;
+  };
+  // Sub-batches: the batch is cut into nsub windows of whole 128-environment tiles that run the pipeline side by side
+  // on their own streams (forked from and joined back into the batch's stream, also inside a graph capture).  Every
+  // kernel of the tick is bound by per-environment latency at 10-25 % of the SM's warp slots, and the solver ends in a
+  // tail of a few slow environments: windows in different stages fill each other's gaps.  Results do not depend on the
+  // cut (an environment never looks at another one).
+  int nsub = b->nsub;
+  if (b->prof_on || b->chain_n > 0 || b->fused || b->tc_rows > 0) nsub = 1;
+  while (nsub > 1 && (b->nenvp % (128 * nsub) != 0 || b->nenvp / nsub < b->sub_min_envs)) nsub /= 2;
+  if (nsub <= 1) {
+    if (pipeline(a, b->stream, b->nenvp) < 0) return -1;
+  } else {
+    if (ensure_sub_streams(b, nsub) < 0) return -1;
+    const int n = b->nenvp / nsub;
+    CK(cudaEventRecord(b->sub_fork, b->stream));
+    for (int s = 0; s < nsub; s++) {
+      cudaStream_t st = s == 0 ? b->stream : b->sub_stream[s - 1];
+      if (s > 0) CK(cudaStreamWaitEvent(st, b->sub_fork, 0));
+      if (pipeline(window_args(a, s, s * n, n), st, n) < 0) return -1;
+      if (s > 0) { CK(cudaEventRecord(b->sub_join[s - 1], st)); CK(cudaStreamWaitEvent(b->stream, b->sub_join[s - 1], 0)); }
     }
   }
   if (flags & B2_TICK_INTEGRATE) hold_slots<T>(b);   // inactive object slots go back to their parking place
@@ -940,6 +1017,8 @@ b2_batch* b2_create(const mjModel* m, int nenv, int device, int precision) {
   b->controlled.assign(m->nv, 0);
   b->export_stages = export_stages;
   b->use_graph = !getenv("B2_NO_GRAPH");
+  if (getenv("B2_SUBBATCH")) b->nsub = std::max(1, std::min(8, atoi(getenv("B2_SUBBATCH"))));
+  if (getenv("B2_SUBBATCH_MIN")) b->sub_min_envs = std::max(128, atoi(getenv("B2_SUBBATCH_MIN")));
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) b->nsm = prop.multiProcessorCount;
   auto bail = [&](const char* what) -> b2_batch* {
@@ -1165,6 +1244,9 @@ void b2_destroy(b2_batch* b) {
   if (b->slot_active) cudaFree(b->slot_active);
   if (b->flush_buf) cudaFree(b->flush_buf);
   if (b->h_dev) cudaFree(b->h_dev);
+  for (cudaStream_t st : b->sub_stream) cudaStreamDestroy(st);
+  for (cudaEvent_t ev : b->sub_join) cudaEventDestroy(ev);
+  if (b->sub_fork) cudaEventDestroy(b->sub_fork);
   for (size_t p = 0; p < b->obs_peers_host.size(); p++)
     if (b->obs_peer_ipc[p] && b->obs_peers_host[p]) cudaIpcCloseMemHandle(b->obs_peers_host[p]);
   if (b->obs_peers_dev) cudaFree(b->obs_peers_dev);
@@ -1241,6 +1323,14 @@ int b2_set_timestep(b2_batch* b, double h) {
 int b2_set_option(b2_batch* b, const char* name, double value) {
   if (!b || !name) return fail("b2_set_option: null argument");
   CK(cudaSetDevice(b->device));
+  if (!std::strcmp(name, "subbatches") || !std::strcmp(name, "subbatch_min")) {
+    // scheduling only (run_tick): how many windows of the batch run the pipeline side by side, and their smallest size
+    if (value < 1) return fail("b2_set_option: subbatches / subbatch_min must be >= 1");
+    CK(cudaStreamSynchronize(b->stream));
+    drop_graphs(b);
+    if (name[8] == 'e') b->nsub = std::min(8, (int)value); else b->sub_min_envs = (int)value;
+    return 0;
+  }
   if (!std::strcmp(name, "iterations")) b->opt_iterations = (int)value;
   else if (!std::strcmp(name, "tolerance")) b->opt_tolerance = value;
   else if (!std::strcmp(name, "disableflags")) b->opt_disableflags = (int)value;

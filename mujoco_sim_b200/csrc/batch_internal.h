@@ -56,6 +56,12 @@ struct b2_batch {
   int obs_world = 0, obs_rank = 0;
   bool obs_on = false;
   void* h_dev = nullptr; // {double h, float h}: the timestep in device memory (KArgs::hp)
+  // sub-batches: windows of the batch that run the pipeline side by side on their own streams (batch.cu: run_tick)
+  int nsub = 4;            // windows asked for (b2_set_option "subbatches", B2_SUBBATCH); halved until they are whole tiles
+  int sub_min_envs = 2048; // ... of at least this many environments (b2_set_option "subbatch_min")
+  std::vector<cudaStream_t> sub_stream;
+  std::vector<cudaEvent_t> sub_join;
+  cudaEvent_t sub_fork = nullptr;
   int tree_lanes = 1;    // lanes per environment in k_smooth / k_integrate (tree-parallel form; 1: thread per environment)
   int tc_rows = 0;       // tensor-core projection (k_project_tc): rows per environment of the environment-major arrays; 0: off
   int tc_passes = 3;     // 3: 3xTF32 (fp32-level accuracy), 1: plain TF32

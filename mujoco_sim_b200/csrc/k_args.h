@@ -36,7 +36,10 @@ template <typename T>
 struct KArgs {
   const uint32_t* model;  // packed DModel blob in HBM
   int model_words;        // its size in 32-bit words (so that the TMA staging copy needs no dependent header load)
-  int nenv, nenvp;        // environments, padded to a multiple of the CTA size
+  int nenv, nenvp;        // environments, padded to a multiple of the CTA size (nenvp is the env stride of every SoA array)
+  int ncount;             // environments THIS launch covers (a multiple of 128): nenvp, or a sub-batch window of it whose
+                          // pointers were advanced to its first environment (batch.cu: window_args)
+  int env_base;           // first environment of the window in the whole batch (0 without windows): observation slices
   int flags;
   int ws_block;           // CTA size the shared workspace was sized for
   T h;                    // timestep of this call (the reference mutates m->opt.timestep every tick, mj_main.cpp:150-163)

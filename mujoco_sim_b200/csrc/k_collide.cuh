@@ -834,7 +834,7 @@ __global__ void __launch_bounds__(BLOCK) k_collide(const KArgs<T> a) {
   const DModel& h = *m.h;
   const long long S = a.nenvp;
   constexpr int EPB = BLOCK / L;
-  const int ntiles = a.nenvp / EPB;
+  const int ntiles = a.ncount / EPB;
   const bool off = h.disableflags & (DSBL_CONSTRAINT | DSBL_CONTACT);
   const int team = threadIdx.x / L, l = threadIdx.x % L;
   const int tshift = (threadIdx.x & 31) & ~(L - 1);

@@ -243,12 +243,21 @@ struct Rows {
     if (h.disableflags & DSBL_CONTACT) return ne0;
     const int ncon = a.ncon[env];
     int r = ne0;
-    for (int c = 0; c < ncon; c++) {
-      const int dim = a.coni[((long long)CI_DIM * h.nconmax + c) * S + env];
-      const int nrow = dim == 1 ? 1 : 2 * (dim - 1);
-      int& efc = a.coni[((long long)CI_EFC * h.nconmax + c) * S + env];
-      if (r + nrow > h.njmax) { a.status[env] |= 2; efc = -1; }
-      else { efc = r; r += nrow; }
+    // (the dims of eight contacts are fetched before the first offset is stored: a store into contact_int orders every
+    //  later load of the same array behind it, one L2 round trip per contact)
+    for (int c0 = 0; c0 < ncon; c0 += 8) {
+      int dims[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++) dims[k] = c0 + k < ncon ? a.coni[((long long)CI_DIM * h.nconmax + c0 + k) * S + env] : 1;
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const int c = c0 + k;
+        if (c >= ncon) break;
+        const int nrow = dims[k] == 1 ? 1 : 2 * (dims[k] - 1);
+        int& efc = a.coni[((long long)CI_EFC * h.nconmax + c) * S + env];
+        if (r + nrow > h.njmax) { a.status[env] |= 2; efc = -1; }
+        else { efc = r; r += nrow; }
+      }
     }
     return r;
   }
@@ -284,9 +293,26 @@ struct Rows {
         const T sg = side ? T(1) : T(-1);
         T off[3];
         point_off(b, pos, off);
-        for (int i = m.i(h.o_body_lastdof, b); i >= 0; i = m.i(h.o_dof_parentid, i)) {
-          T jp[3], jr[3], fp[3], fr[3];
-          jac_col(i, off, jp, jr);
+        // (the spatial axes of six dofs of the chain are fetched before the first one is used: one dof per L2 round trip
+        //  otherwise, twelve per arm - prop contact)
+        for (int i0 = m.i(h.o_body_lastdof, b); i0 >= 0;) {
+          int id6[6];
+          T cd6[6][6];
+          int nd = 0, inext = i0;
+#pragma unroll
+          for (int q = 0; q < 6; q++) {
+            id6[q] = inext;
+            if (inext >= 0) { nd = q + 1; for (int k = 0; k < 6; k++) cd6[q][k] = cdof(inext, k); inext = m.i(h.o_dof_parentid, inext); }
+          }
+          i0 = inext;
+#pragma unroll
+          for (int q = 0; q < 6; q++) {
+          if (q >= nd) break;
+          const int i = id6[q];
+          T jp[3], jr[3], fp[3], fr[3], t[3];
+          cross3(t, cd6[q], off);
+          jp[0] = cd6[q][3] + t[0]; jp[1] = cd6[q][4] + t[1]; jp[2] = cd6[q][5] + t[2];
+          jr[0] = cd6[q][0]; jr[1] = cd6[q][1]; jr[2] = cd6[q][2];
           mat_vec3(fp, frame, jp);  // rows of frame: normal, tangent1, tangent2
           mat_vec3(fr, frame, jr);
           const int kk = seg_pos(g, i);
@@ -300,22 +326,64 @@ struct Rows {
             Jc(first, kk) += sg * fp[0];
             for (int k = 1; k < dim; k++) Jc(first + k, kk) += sg * (k < 3 ? fp[k] : fr[k - 3]);
           }
+          }
         }
       }
       if (sh)
         for (int k = 0; k < dim; k++)
           for (int e = 0; e < wrow; e++) Jc(first + k, e) = RS(k, e);
-      finish_range(first, first + nrow, 1);
-      if (dim > 1) {   // pyramidal cones share R = 2 mu^2 R_first
-        const T mu = F(CF_FRICTION) / t_sqrt(t_max(Eps<T>::minval(), m.f(h.o_opt_real, 5)));
-        const T Rpy = t_max(Eps<T>::minval(), 2 * mu * mu * a.efc_R[(long long)first * S + env]);
-        for (int j = 0; j < nrow; j++) a.efc_R[(long long)(first + j) * S + env] = Rpy;
+      // diagApprox, impedance, R, K, B of the contact's rows (finish_range for one contact): its rows share type, id,
+      // pos and margin, all at hand here, so nothing is read back from the row arrays just written (each such load is an
+      // L2 round trip behind a store), and the impedance and the reference spring are evaluated once
+      {
+        T solref[2], solimp[5], fric[5];
+        for (int k = 0; k < 2; k++) solref[k] = F(CF_SOLREF + k);
+        for (int k = 0; k < 5; k++) solimp[k] = F(CF_SOLIMP + k);
+        for (int k = 0; k < 5; k++) fric[k] = F(CF_FRICTION + k);
+        const T tran = m.f(h.o_body_invweight0, 2 * b1) + m.f(h.o_body_invweight0, 2 * b2);
+        const T rot = m.f(h.o_body_invweight0, 2 * b1 + 1) + m.f(h.o_body_invweight0, 2 * b2 + 1);
+        const T imp = impedance(solimp, dist, im);
+        T K, B;
+        spring(solref, solimp, K, B);
+        T R0 = 0;
+        for (int j = 0; j < nrow; j++) {
+          const int r = first + j;
+          T diag = tran;
+          if (dim > 1) { const T fr = fric[j / 2]; diag = tran + fr * fr * (j < 4 ? tran : rot); }
+          const T R = t_max(Eps<T>::minval(), (1 - imp) * diag / imp);
+          if (j == 0) R0 = R;
+          a.efc_diagApprox[(long long)r * S + env] = diag;
+          a.efc_KBI[((long long)0 * h.njmax + r) * S + env] = K;
+          a.efc_KBI[((long long)1 * h.njmax + r) * S + env] = B;
+          a.efc_KBI[((long long)2 * h.njmax + r) * S + env] = imp;
+          if (dim == 1) a.efc_R[(long long)r * S + env] = R;
+        }
+        if (dim > 1) {   // pyramidal cones share R = 2 mu^2 R_first
+          const T mu = fric[0] / t_sqrt(t_max(Eps<T>::minval(), m.f(h.o_opt_real, 5)));
+          const T Rpy = t_max(Eps<T>::minval(), 2 * mu * mu * R0);
+          for (int j = 0; j < nrow; j++) a.efc_R[(long long)(first + j) * S + env] = Rpy;
+        }
       }
+  }
+
+  // reference spring of a row: stiffness K and damping B from solref / solimp (mj_makeImpedance)
+  __device__ __forceinline__ void spring(const T* solref, const T* solimp, T& K, T& B) const {
+    const T hs = a.dt();
+    const T dmax = t_min(T(0.9999), t_max(T(0.0001), solimp[1]));
+    if (solref[0] > 0) {
+      T tc = solref[0];
+      const T dr = solref[1];
+      if (!(h.disableflags & DSBL_REFSAFE)) tc = t_max(tc, 2 * hs);
+      K = 1 / t_max(Eps<T>::minval(), dmax * dmax * tc * tc * dr * dr);
+      B = 2 / t_max(Eps<T>::minval(), dmax * tc);
+    } else {
+      K = -solref[0] / t_max(Eps<T>::minval(), dmax * dmax);
+      B = -solref[1] / t_max(Eps<T>::minval(), dmax);
+    }
   }
 
   // diagApprox, impedance -> R, D; K, B, imp; aref; (vel uses the current, possibly overridden, qvel)
   __device__ void finish_range(int r0, int r1, int step) {
-    const T hs = a.dt();
     // the rows of one contact share its parameters: fetched once per contact (13 HBM loads), not once per row
     int c_id = -1, c_first = 0;
     T c_solref[2] = {0, 0}, c_solimp[5] = {0, 0, 0, 0, 0}, c_tran = 0, c_rot = 0;
@@ -370,18 +438,8 @@ struct Rows {
       T R = t_max(Eps<T>::minval(), (1 - imp) * diag / imp);
       a.efc_diagApprox[(long long)r * S + env] = diag;
       a.efc_R[(long long)r * S + env] = R;
-      const T dmax = t_min(T(0.9999), t_max(T(0.0001), solimp[1]));
       T K, B;
-      if (solref[0] > 0) {
-        T tc = solref[0];
-        const T dr = solref[1];
-        if (!(h.disableflags & DSBL_REFSAFE)) tc = t_max(tc, 2 * hs);
-        K = 1 / t_max(Eps<T>::minval(), dmax * dmax * tc * tc * dr * dr);
-        B = 2 / t_max(Eps<T>::minval(), dmax * tc);
-      } else {
-        K = -solref[0] / t_max(Eps<T>::minval(), dmax * dmax);
-        B = -solref[1] / t_max(Eps<T>::minval(), dmax);
-      }
+      spring(solref, solimp, K, B);
       if (type == CN_FRICTION_DOF) K = 0;
       a.efc_KBI[((long long)0 * h.njmax + r) * S + env] = K;
       a.efc_KBI[((long long)1 * h.njmax + r) * S + env] = B;
@@ -412,7 +470,7 @@ __device__ __forceinline__ T primal_force(int type, T jar, T D, T R, T fl) {
   MV<T> m{reinterpret_cast<const DModel*>(blob), blob};                              \
   const DModel& h = *m.h;                                                            \
   const long long S = a.nenvp;                                                       \
-  const int ntiles = a.nenvp / BLOCK;                                                \
+  const int ntiles = a.ncount / BLOCK;                                               \
   (void)S; (void)h;
 
 template <typename T, int N> struct alignas(sizeof(T) * N) VecN { T v[N]; };
@@ -487,7 +545,7 @@ __global__ void __launch_bounds__(BLOCK) k_make_rows(const KArgs<T> a) {
   B2_KERNEL_PROLOGUE
   (void)ntiles;
   constexpr int EPB = BLOCK / L;
-  const int nteams = a.nenvp / EPB;
+  const int nteams = a.ncount / EPB;
   const int team = threadIdx.x / L, l = threadIdx.x % L;
   const int tshift = (threadIdx.x & 31) & ~(L - 1);
   const unsigned tmask = (L == 32 ? 0xffffffffu : ((1u << L) - 1u)) << tshift;
@@ -601,7 +659,7 @@ __global__ void __launch_bounds__(32 * ROWS) k_solve_rows(const KArgs<T> a) {
   T* dis = LDs + (size_t)nM * 32;                   // [nv][32]
   T* Xs = dis + (size_t)nv * 32;                    // [ROWS][W][32]
   const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
-  const int ntiles = a.nenvp / 32;
+  const int ntiles = a.ncount / 32;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int env = tile * 32 + lane;
     __syncthreads();   // the previous tile's solves are done with the factor
@@ -666,7 +724,7 @@ __device__ __forceinline__ void make_blocks_pass(const KArgs<T>& a, const int bl
   MV<T> m{reinterpret_cast<const DModel*>(a.model), a.model};
   const DModel& h = *m.h;
   const long long S = a.nenvp;
-  const int ntiles = a.nenvp / BLOCK;
+  const int ntiles = a.ncount / BLOCK;
   constexpr int LDS = BLOCK + 1;  // +1: conflict-free both for per-thread columns and for the transposed reads
   // per thread (column): [0, npar) header + row parameters, then one base direction at a time: J_c [wqmax] | B_c [wqmax].
   // Streaming the base directions keeps the footprint at npar + 2 wq words per thread instead of the whole record
@@ -710,13 +768,22 @@ __device__ __forceinline__ void make_blocks_pass(const KArgs<T>& a, const int bl
       const bool on = have && c < nb;
       if (on) {
         T v0 = 0, s0 = 0, q0 = 0;
-        for (int e = 0; e < w; e++) {
-          const T j = a.efc_J[((long long)(r + c) * W + e) * S + env];
-          Jc[e] = j; Bc[e] = j;
-          if (j != 0) {
-            const long long d = (long long)bs.dof(e) * S + env;
-            v0 += j * a.qvel[d]; s0 += j * a.qacc_smooth[d];
-            if (a.flags & B2F_INVERSE) q0 += j * a.qacc[d];
+        // (four elements at a time, every load of the chunk in flight before the first use: the row and the three state
+        //  vectors come from L2, and a load -> test -> load chain per element was two round trips each)
+        const bool inv = (a.flags & B2F_INVERSE) != 0;
+        for (int e0 = 0; e0 < w; e0 += 4) {
+          T j[4], qv[4], qs[4], qa[4];
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const bool in = e0 + k < w;
+            const long long d = (long long)bs.dof(in ? e0 + k : 0) * S + env;
+            j[k] = in ? a.efc_J[((long long)(r + c) * W + e0 + k) * S + env] : T(0);
+            qv[k] = in ? a.qvel[d] : T(0); qs[k] = in ? a.qacc_smooth[d] : T(0); qa[k] = (in && inv) ? a.qacc[d] : T(0);
+          }
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            if (e0 + k < w) { Jc[e0 + k] = j[k]; Bc[e0 + k] = j[k]; }
+            if (j[k] != 0) { v0 += j[k] * qv[k]; s0 += j[k] * qs[k]; if (inv) q0 += j[k] * qa[k]; }
           }
         }
         vel[c] = v0; js[c] = s0; jq[c] = q0;
@@ -732,17 +799,37 @@ __device__ __forceinline__ void make_blocks_pass(const KArgs<T>& a, const int bl
         for (int sgm = 0; sgm < 2; sgm++) {
           const int lo = sgm ? g.s2 : g.s1, n = sgm ? g.n2 : g.n1, base = sgm ? g.n1 : 0;
           if (n == 0) continue;
+          // (a row of the factor is fetched eight entries at a time before it is used: the entries come from L2, and one
+          //  load per update of the shared-memory column was one round trip per entry)
           for (int i = lo + n - 1; i >= lo; i--) {
             const T xi = Bc[base + i - lo];
             if (xi == 0) continue;
             const int adr = m.i(h.o_dof_Madr, i), cnt = m.i(h.o_dof_Mcnt, i);
-            for (int q = 1; q < cnt; q++) Bc[base + m.i(h.o_dof_anc, adr + q) - lo] -= LD[adr + q] * xi;
+            for (int q0 = 1; q0 < cnt; q0 += 8) {
+              T l[8]; int an[8];
+#pragma unroll
+              for (int k = 0; k < 8; k++) { const bool in = q0 + k < cnt; l[k] = in ? LD[adr + q0 + k] : T(0); an[k] = in ? m.i(h.o_dof_anc, adr + q0 + k) : lo; }
+#pragma unroll
+              for (int k = 0; k < 8; k++) if (q0 + k < cnt) Bc[base + an[k] - lo] -= l[k] * xi;
+            }
           }
-          for (int i = lo; i < lo + n; i++) Bc[base + i - lo] *= dinv[i];
+          for (int i0 = lo; i0 < lo + n; i0 += 8) {
+            T dv[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) dv[k] = i0 + k < lo + n ? dinv[i0 + k] : T(0);
+#pragma unroll
+            for (int k = 0; k < 8; k++) if (i0 + k < lo + n) Bc[base + i0 + k - lo] *= dv[k];
+          }
           for (int i = lo; i < lo + n; i++) {
             const int adr = m.i(h.o_dof_Madr, i), cnt = m.i(h.o_dof_Mcnt, i);
             T xi = Bc[base + i - lo];
-            for (int q = 1; q < cnt; q++) xi -= LD[adr + q] * Bc[base + m.i(h.o_dof_anc, adr + q) - lo];
+            for (int q0 = 1; q0 < cnt; q0 += 8) {
+              T l[8]; int an[8];
+#pragma unroll
+              for (int k = 0; k < 8; k++) { const bool in = q0 + k < cnt; l[k] = in ? LD[adr + q0 + k] : T(0); an[k] = in ? m.i(h.o_dof_anc, adr + q0 + k) : lo; }
+#pragma unroll
+              for (int k = 0; k < 8; k++) if (q0 + k < cnt) xi -= l[k] * Bc[base + an[k] - lo];
+            }
             Bc[base + i - lo] = xi;
           }
         }
@@ -750,7 +837,15 @@ __device__ __forceinline__ void make_blocks_pass(const KArgs<T>& a, const int bl
         for (int k = 0; k <= c; k++) {
           T s0a = 0;
           if (k == c) { for (int e = 0; e < w; e++) s0a += Jc[e] * Bc[e]; }
-          else { for (int e = 0; e < w; e++) { const T j = a.efc_J[((long long)(r + k) * W + e) * S + env]; if (j != 0) s0a += j * Bc[e]; } }
+          else {
+            for (int e0 = 0; e0 < w; e0 += 4) {
+              T j[4];
+#pragma unroll
+              for (int k2 = 0; k2 < 4; k2++) j[k2] = e0 + k2 < w ? a.efc_J[((long long)(r + k) * W + e0 + k2) * S + env] : T(0);
+#pragma unroll
+              for (int k2 = 0; k2 < 4; k2++) if (j[k2] != 0) s0a += j[k2] * Bc[e0 + k2];
+            }
+          }
           A[k][c] = s0a; A[c][k] = s0a;
         }
       }
@@ -781,20 +876,34 @@ __device__ __forceinline__ void make_blocks_pass(const KArgs<T>& a, const int bl
           }
       for (int k = 1; k < nb; k++) rec[bs.oMu + k - 1] = fri[k - 1];
       const T R = a.efc_R[o], D = 1 / R, fl = a.efc_frictionloss[o];
-      for (int rr = 0; rr < bs.nrow; rr++) {
+      for (int rr0 = 0; rr0 < bs.nrow; rr0 += 4) {
+      // (the row parameters of four rows are fetched before the first row's results are stored: a store to the row arrays
+      //  orders every later load behind it)
+      T Kq[4], Bq[4], Iq[4], Pq[4], Mq[4];
+#pragma unroll
+      for (int k2 = 0; k2 < 4; k2++) {
+        const int rr = rr0 + k2 < bs.nrow ? rr0 + k2 : rr0;
+        const long long orr = (long long)(r + rr) * S + env;
+        Kq[k2] = a.efc_KBI[((long long)0 * h.njmax + r + rr) * S + env]; Bq[k2] = a.efc_KBI[((long long)1 * h.njmax + r + rr) * S + env];
+        Iq[k2] = a.efc_KBI[((long long)2 * h.njmax + r + rr) * S + env]; Pq[k2] = a.efc_pos[orr]; Mq[k2] = a.efc_margin[orr];
+      }
+#pragma unroll
+      for (int k2 = 0; k2 < 4; k2++) {
+        const int rr = rr0 + k2;
+        if (rr >= bs.nrow) break;
         const long long orr = (long long)(r + rr) * S + env;
         const int k = nb > 1 ? rr / 2 + 1 : 0;
         const T sm = nb > 1 ? ((rr & 1) ? -fri[k - 1] : fri[k - 1]) : T(0);
         const T velr = vel[0] + sm * vel[k], jsr = js[0] + sm * js[k];
-        const T K = a.efc_KBI[((long long)0 * h.njmax + r + rr) * S + env], Bd = a.efc_KBI[((long long)1 * h.njmax + r + rr) * S + env];
-        const T imp = a.efc_KBI[((long long)2 * h.njmax + r + rr) * S + env];
-        const T aref = -Bd * velr - K * imp * (a.efc_pos[orr] - a.efc_margin[orr]);
+        const T K = Kq[k2], Bd = Bq[k2], imp = Iq[k2];
+        const T aref = -Bd * velr - K * imp * (Pq[k2] - Mq[k2]);
         const T bb = jsr - aref;
         const T Arr = (nb > 1 ? A[0][0] + 2 * sm * A[0][k] + sm * sm * A[k][k] : A[0][0]) + R;
         a.efc_D[orr] = D; a.efc_vel[orr] = velr; a.efc_aref[orr] = aref; a.efc_b[orr] = bb; a.efc_ARdiag[orr] = Arr;
         // force implied by the previous tick's acceleration (mj_inverse); summed into qfrc_inverse later, in row order
         if (a.flags & B2F_INVERSE) a.efc_finv[orr] = primal_force(bs.type, jq[0] + sm * jq[k] - aref, D, R, fl);
         rec[bs.oAref + rr] = aref; rec[bs.oArr + rr] = Arr; rec[bs.oiA + rr] = 1 / Arr; rec[bs.ob + rr] = bb;
+      }
       }
       for (int q = bs.oA + (nb > 1 ? bs.nrow * (bs.nrow - 1) / 2 : 0); q < bs.oJ; q++) rec[q] = 0;
       rec[BH_CODE] = enc_int(bs.type + 16 * nb + 256 * bs.nrow, T());
@@ -821,7 +930,7 @@ template <typename T>
 __global__ void k_inverse_rows(const KArgs<T> a) {
   const DModel* h = reinterpret_cast<const DModel*>(a.model);
   const int env = blockIdx.x * blockDim.x + threadIdx.x;
-  if (env >= a.nenvp) return;
+  if (env >= a.ncount) return;
   if ((a.flags & B2F_FUSABLE) && (a.status[env] & 8)) return;
   const long long S = a.nenvp;
   const int ne = a.nefc[env], W = h->wmax;
@@ -1315,7 +1424,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_pgs_block(const KArgs<T> a) {
   T* tmp = tmpsh + (size_t)team * nvs;
   T* f = fsh + (size_t)team * ((njmax + 3) & ~3);
   T* st = stsh + (size_t)team * cap;
-  const int ngroups = (a.nenvp + EPB - 1) / EPB;
+  const int ngroups = (a.ncount + EPB - 1) / EPB;
   const T tol = m.f(h.o_opt_real, 3), scale = 1 / (m.f(h.o_opt_real, 4) * T(nv > 1 ? nv : 1));
 
   auto team_sum = [&](T v) {
@@ -1565,7 +1674,7 @@ __global__ void __launch_bounds__(32, MINB) k_pgs_island(const KArgs<T> a) {
   T* f = fsh + (size_t)team * ((njmax + 3) & ~3);
   T* st = stsh + (size_t)team * cap;
   int* sto = stosh + (size_t)team * a.isl_cap;
-  const int ngroups = (a.nenvp + EPB - 1) / EPB;
+  const int ngroups = (a.ncount + EPB - 1) / EPB;
   const T tol = m.f(h.o_opt_real, 3), scale = 1 / (m.f(h.o_opt_real, 4) * T(nv > 1 ? nv : 1));
   auto team_sum = [&](T v) {
 #pragma unroll
@@ -1829,7 +1938,7 @@ __device__ __forceinline__ void publish_obs(const KArgs<T>& a, int env, int lane
   const DModel* hd = reinterpret_cast<const DModel*>(a.model);
   const int nq = hd->nq, nv = hd->nv;
   const long long S = a.nenvp;
-  const long long base = (long long)a.obs_rank * (nq + nv) * a.obs_nenv + env;
+  const long long base = (long long)a.obs_rank * (nq + nv) * a.obs_nenv + a.env_base + env;
   for (int i = lane; i < nq + nv; i += nlanes) {
     const float v = (float)(i < nq ? a.qpos[(long long)i * S + env] : a.qvel[(long long)(i - nq) * S + env]);
     for (int p = 0; p < a.obs_world; p++) a.obs_peers[p][base + (long long)i * a.obs_nenv] = v;
@@ -1850,7 +1959,7 @@ __global__ void __launch_bounds__(BLOCK) k_integrate(const KArgs<T> a) {
   B2_KERNEL_PROLOGUE
   (void)ntiles;
   constexpr int EPB = BLOCK / L;
-  const int nteams = a.nenvp / EPB;
+  const int nteams = a.ncount / EPB;
   const int envl = threadIdx.x / L, lane = threadIdx.x % L;
   const unsigned tmask = (L >= 32 ? 0xffffffffu : ((1u << L) - 1u)) << ((threadIdx.x & 31) & ~(L - 1));
   m.lane = lane; m.nlanes = L;
@@ -1903,7 +2012,7 @@ __global__ void __launch_bounds__(BLOCK) k_integrate(const KArgs<T> a) {
       __syncthreads();
       const DModel* hd = reinterpret_cast<const DModel*>(a.model);
       const int nobs = hd->nq + hd->nv, nq = hd->nq;
-      const long long base = (long long)a.obs_rank * nobs * a.obs_nenv;
+      const long long base = (long long)a.obs_rank * nobs * a.obs_nenv + a.env_base;
       for (int idx = threadIdx.x; idx < nobs * EPB; idx += BLOCK) {
         const int i = idx / EPB, e = tile * EPB + idx % EPB;
         if (e >= a.nenv) continue;

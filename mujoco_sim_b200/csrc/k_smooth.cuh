@@ -437,13 +437,21 @@ struct Smooth {
 #pragma unroll(P::UNROLL)
     for (int k_ = P::body_lo(m) - 1; k_ < P::body_hi(m); k_++) {
       const int b = k_ < P::body_lo(m) ? 0 : P::body_at(m, k_);
-      for (int k = 0; k < 10; k++) crb[10 * b + k] = cinert[10 * b + k];
+      T ci[10];
+      ld<T, 10>(ci, cinert, 10 * b);   // (all ten loads before the first store: the arrays may alias for the compiler)
+      st<T, 10>(crb, 10 * b, ci);
     }
 #pragma unroll(P::UNROLL)
     for (int k_ = P::body_hi(m) - 1; k_ >= P::body_lo(m); k_--) {
       const int b = P::body_at(m, k_);
       const int p = P::body_parentid(m, b);
-      if (p > 0) for (int k = 0; k < 10; k++) crb[10 * p + k] += crb[10 * b + k];
+      if (p > 0) {
+        T cp[10], cb[10];
+        ld<T, 10>(cp, crb, 10 * p);
+        ld<T, 10>(cb, crb, 10 * b);
+        for (int k = 0; k < 10; k++) cp[k] += cb[k];
+        st<T, 10>(crb, 10 * p, cp);
+      }
     }
 #pragma unroll(P::UNROLL)
     for (int k_ = P::dof_lo(m); k_ < P::dof_hi(m); k_++) {
@@ -456,12 +464,19 @@ struct Smooth {
       T v = m.f(h.o_dof_armature, i);
       if constexpr (!P::STATIC) {
         const int cnt = P::dof_Mcnt(m, i);
-        for (int a = 0; a < cnt; a++) {   // row i of M over the flattened ancestor list (no dof_parentid chasing)
-          T cj[6];
-          ld<T, 6>(cj, cdof, 6 * P::dof_anc(m, adr + a));
-          v += cj[0] * buf[0] + cj[1] * buf[1] + cj[2] * buf[2] + cj[3] * buf[3] + cj[4] * buf[4] + cj[5] * buf[5];
-          qM[adr + a] = v;
-          v = 0;
+        // row i of M over the flattened ancestor list (no dof_parentid chasing); the axes of four ancestors are fetched
+        // before the first entry is stored
+        for (int a0 = 0; a0 < cnt; a0 += 4) {
+          T cj[4][6];
+#pragma unroll
+          for (int q = 0; q < 4; q++) if (a0 + q < cnt) ld<T, 6>(cj[q], cdof, 6 * P::dof_anc(m, adr + a0 + q));
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            if (a0 + q >= cnt) break;
+            v += cj[q][0] * buf[0] + cj[q][1] * buf[1] + cj[q][2] * buf[2] + cj[q][3] * buf[3] + cj[q][4] * buf[4] + cj[q][5] * buf[5];
+            qM[adr + a0 + q] = v;
+            v = 0;
+          }
         }
       } else {
 #pragma unroll(P::UNROLL)
@@ -490,11 +505,21 @@ struct Smooth {
       T ri = res[i] + qM[adr] * vi;
       if constexpr (!P::STATIC) {
         const int cnt = P::dof_Mcnt(m, i);
-        for (int a = 1; a < cnt; a++) {
-          const int j = P::dof_anc(m, adr + a);
-          const T mij = qM[adr + a];
-          ri += mij * vec[j];
-          res[j] += mij * vi;
+        // (the row's entries and the ancestors' vector elements, four at a time, before the first update is stored)
+        for (int a0 = 1; a0 < cnt; a0 += 4) {
+          T mij[4], vj[4], rj[4]; int jj[4];
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            const bool in = a0 + q < cnt;
+            jj[q] = in ? P::dof_anc(m, adr + a0 + q) : i;
+            mij[q] = in ? qM[adr + a0 + q] : T(0); vj[q] = in ? vec[jj[q]] : T(0); rj[q] = in ? res[jj[q]] : T(0);
+          }
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            if (a0 + q >= cnt) break;
+            ri += mij[q] * vj[q];
+            res[jj[q]] = rj[q] + mij[q] * vi;   // (the ancestors of a row are distinct dofs: no entry is updated twice here)
+          }
         }
         res[i] = ri;
       } else {
@@ -603,7 +628,16 @@ struct Smooth {
     }
     if (h.has_damping) {
 #pragma unroll(P::UNROLL)
-      for (int k_ = P::dof_lo(m); k_ < P::dof_hi(m); k_++) { const int i = P::dof_at(m, k_); qfrc_passive[i] -= m.f(h.o_dof_damping, i) * qvel[i]; }
+      for (int k0 = P::dof_lo(m); k0 < P::dof_hi(m); k0 += 4) {   // (four dofs' loads before the first store)
+        T fp[4], vq[4]; int ii[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          ii[q] = P::dof_at(m, k0 + q < P::dof_hi(m) ? k0 + q : k0);
+          fp[q] = qfrc_passive[ii[q]]; vq[q] = qvel[ii[q]];
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) if (k0 + q < P::dof_hi(m)) qfrc_passive[ii[q]] = fp[q] - m.f(h.o_dof_damping, ii[q]) * vq[q];
+      }
     }
     // gravity compensation: the reference sets gravcomp="1" on every robot body by default
     // (src/mujoco_sim/mj_sim.cpp:301-310, src/config/robot.yaml:19)
@@ -635,6 +669,10 @@ struct Smooth {
       T ac[6], ci[10], cv[6], Ia[6], Iv[6], x[6];
       ld<T, 6>(ac, cacc, 6 * P::body_parentid(m, b));
       const int da = P::body_dofadr(m, b), dn = P::body_dofnum(m, b);
+      // (the body's inertia and velocity are fetched together with its dofs' terms, before cacc is stored)
+      ld<T, 10>(ci, cinert, 10 * b);
+      ld<T, 6>(cv, cvel, 6 * b);
+      if constexpr (P::STATIC) {
 #pragma unroll(P::UNROLL)
       for (int j = 0; j < dn; j++) {
         const T v = qvel[da + j];
@@ -644,9 +682,26 @@ struct Smooth {
           for (int r = 0; r < 6; r++) ac[r] += cdof[6 * (da + j) + r] * q2;
         }
       }
+      } else {
+      for (int j0 = 0; j0 < dn; j0 += 3) {
+        T v[3], dd[3][6], q2[3] = {0, 0, 0}, cd[3][6];
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+          if (j0 + q < dn) {
+            v[q] = qvel[da + j0 + q];
+            ld<T, 6>(dd[q], cdof_dot, 6 * (da + j0 + q));
+            if (with_acc) { q2[q] = qacc[da + j0 + q]; ld<T, 6>(cd[q], cdof, 6 * (da + j0 + q)); }
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+          if (j0 + q >= dn) break;
+          for (int r = 0; r < 6; r++) ac[r] += dd[q][r] * v[q];
+          if (with_acc) for (int r = 0; r < 6; r++) ac[r] += cd[q][r] * q2[q];
+        }
+      }
+      }
       st<T, 6>(cacc, 6 * b, ac);
-      ld<T, 10>(ci, cinert, 10 * b);
-      ld<T, 6>(cv, cvel, 6 * b);
       mul_inert_vec(Ia, ci, ac);
       mul_inert_vec(Iv, ci, cv);
       cross_force(x, cv, Iv);
@@ -656,7 +711,13 @@ struct Smooth {
     for (int k_ = P::body_hi(m) - 1; k_ >= P::body_lo(m); k_--) {
       const int b = P::body_at(m, k_);
       const int p = P::body_parentid(m, b);
-      if (p > 0) for (int r = 0; r < 6; r++) cfrc[6 * p + r] += cfrc[6 * b + r];
+      if (p > 0) {
+        T fp[6], fb[6];
+        ld<T, 6>(fp, cfrc, 6 * p);
+        ld<T, 6>(fb, cfrc, 6 * b);
+        for (int r = 0; r < 6; r++) fp[r] += fb[r];
+        st<T, 6>(cfrc, 6 * p, fp);
+      }
     }
 #pragma unroll(P::UNROLL)
     for (int k_ = P::dof_lo(m); k_ < P::dof_hi(m); k_++) {
@@ -710,7 +771,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_smooth(const KArgs<T> a) {
   const long long S = a.nenvp;
   static_assert(L == 1 || !P::STATIC, "the register-resident chain policy is one thread per environment");
   constexpr int EPB = BLOCK / L;
-  const int ntiles = a.nenvp / EPB;
+  const int ntiles = a.ncount / EPB;
   const int envl = threadIdx.x / L, lane = threadIdx.x % L;
   const unsigned tmask = (L >= 32 ? 0xffffffffu : ((1u << L) - 1u)) << ((threadIdx.x & 31) & ~(L - 1));
   m.lane = lane; m.nlanes = L;
@@ -729,14 +790,37 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_smooth(const KArgs<T> a) {
     const long long wss = (a.flags & B2F_WS_GLOBAL) ? S : EPB;
     Smooth<T, P> s(m, a, wsbase, wss, env);
     SArr<T> qfrc_inverse{a.qfrc_inverse + env, S};
+    if constexpr (!P::STATIC) {
+      // workspace in HBM with the factor scratch in shared memory: its third vector (free in this kernel) is the scratch
+      // vector of the controller's and mj_inverse's M x products and, at the end, of the solve for qacc_smooth
+      if (a.flags & B2F_LD_SMEM) s.tmpv = SArr<T>{ws_sh + (size_t)(nM + nv) * EPB + envl, EPB};
+    }
 
     // mj_checkPos / mj_checkVel: reset an environment whose state went non-finite
     {
       bool bad = false;
+      if constexpr (P::STATIC) {
 #pragma unroll(P::UNROLL)
-      for (int i = 0; i < nq; i++) { const T v = s.qpos[i]; bad |= !(t_abs(v) < T(1e10)); }
+        for (int i = 0; i < nq; i++) { const T v = s.qpos[i]; bad |= !(t_abs(v) < T(1e10)); }
 #pragma unroll(P::UNROLL)
-      for (int i = 0; i < nv; i++) { const T v = s.qvel[i]; bad |= !(t_abs(v) < T(1e10)); }
+        for (int i = 0; i < nv; i++) { const T v = s.qvel[i]; bad |= !(t_abs(v) < T(1e10)); }
+      } else {
+        // (eight loads in flight per step: this is the first touch of the state, an HBM round trip per element otherwise)
+        for (int i0 = 0; i0 < nq; i0 += 8) {
+          T v[8];
+#pragma unroll
+          for (int k = 0; k < 8; k++) v[k] = i0 + k < nq ? s.qpos[i0 + k] : T(0);
+#pragma unroll
+          for (int k = 0; k < 8; k++) bad |= !(t_abs(v[k]) < T(1e10));
+        }
+        for (int i0 = 0; i0 < nv; i0 += 8) {
+          T v[8];
+#pragma unroll
+          for (int k = 0; k < 8; k++) v[k] = i0 + k < nv ? s.qvel[i0 + k] : T(0);
+#pragma unroll
+          for (int k = 0; k < 8; k++) bad |= !(t_abs(v[k]) < T(1e10));
+        }
+      }
       if (bad) {
 #pragma unroll(P::UNROLL)
         for (int i = 0; i < nq; i++) { const T q0 = m.f(h.o_qpos0, i); s.qpos[i] = q0; a.qpos[i * S + env] = q0; }
@@ -775,7 +859,13 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_smooth(const KArgs<T> a) {
         for (int k_ = P::dof_lo(m); k_ < P::dof_hi(m); k_++) {
           const int i = P::dof_at(m, k_);
           const int adr = P::dof_Madr(m, i), cnt = P::dof_Mcnt(m, i);
-          for (int q2 = 0; q2 < cnt; q2++) LDs[adr + q2] = s.qM[adr + q2];
+          for (int q0 = 0; q0 < cnt; q0 += 8) {   // (eight loads in flight per step)
+            T v[8];
+#pragma unroll
+            for (int q2 = 0; q2 < 8; q2++) v[q2] = q0 + q2 < cnt ? s.qM[adr + q0 + q2] : T(0);
+#pragma unroll
+            for (int q2 = 0; q2 < 8; q2++) if (q0 + q2 < cnt) LDs[adr + q0 + q2] = v[q2];
+          }
         }
         ld_factor<P>(m, LDs, dis);
         for (int k_ = P::dof_lo(m); k_ < P::dof_hi(m); k_++) {
@@ -814,6 +904,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_smooth(const KArgs<T> a) {
         for (int i = 0; i < P::NV; i++) ddq[i] = a.ddq[i * S + env];
       }
       s.mul_M(s.tmpv, ddq);
+      if constexpr (P::STATIC) {
 #pragma unroll(P::UNROLL)
       for (int k_ = P::dof_lo(m); k_ < P::dof_hi(m); k_++) {
         const int i = P::dof_at(m, k_);
@@ -826,6 +917,27 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_smooth(const KArgs<T> a) {
         a.ddq[i * S + env] = 0;
         a.dq[i * S + env] = 0;
       }
+      } else {
+      for (int k0 = P::dof_lo(m); k0 < P::dof_hi(m); k0 += 4) {   // (four dofs' loads before the first store)
+        T tq[4], bq[4], vq[4]; int ii[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          ii[q] = P::dof_at(m, k0 + q < P::dof_hi(m) ? k0 + q : k0);
+          tq[q] = s.tmpv[ii[q]]; bq[q] = s.qfrc_bias[ii[q]]; vq[q] = a.dq[ii[q] * S + env];
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          if (k0 + q >= P::dof_hi(m)) break;
+          const int i = ii[q];
+          T tau = tq[q];
+          if (P::dof_controlled(m, i)) tau += bq[q];
+          s.qfrc_applied[i] = tau;
+          if (t_abs(vq[q]) > Eps<T>::minval()) { s.qvel[i] = vq[q]; overridden = true; }
+          a.ddq[i * S + env] = 0;
+          a.dq[i * S + env] = 0;
+        }
+      }
+      }
     }
     // MjHWInterface::read -> mj_inverse: velocity stage again for the overridden qvel, then RNE with the stored qacc
     if (a.flags & B2F_INVERSE) {
@@ -833,8 +945,21 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_smooth(const KArgs<T> a) {
       // RNE is affine in the acceleration: RNE(q, v, a) + armature a = M a + bias, so the second tree pass of
       // mj_inverse collapses to one sparse mat-vec with the CRBA matrix already at hand
       s.mul_M(s.tmpv, s.qacc);
+      if constexpr (P::STATIC) {
 #pragma unroll(P::UNROLL)
       for (int k_ = P::dof_lo(m); k_ < P::dof_hi(m); k_++) { const int i = P::dof_at(m, k_); qfrc_inverse[i] = s.tmpv[i] + s.qfrc_bias[i] - s.qfrc_passive[i]; }
+      } else {
+      for (int k0 = P::dof_lo(m); k0 < P::dof_hi(m); k0 += 4) {
+        T tq[4], bq[4], pq[4]; int ii[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          ii[q] = P::dof_at(m, k0 + q < P::dof_hi(m) ? k0 + q : k0);
+          tq[q] = s.tmpv[ii[q]]; bq[q] = s.qfrc_bias[ii[q]]; pq[q] = s.qfrc_passive[ii[q]];
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) if (k0 + q < P::dof_hi(m)) qfrc_inverse[ii[q]] = tq[q] + bq[q] - pq[q];
+      }
+      }
     }
     if (P::STATIC) {
 #pragma unroll(P::UNROLL)
@@ -842,8 +967,28 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_smooth(const KArgs<T> a) {
     }
 
     // smooth acceleration
+    bool rhs_ready = false;   // the solve's right-hand side is already in the shared-memory vector
+    if constexpr (P::STATIC) {
 #pragma unroll(P::UNROLL)
     for (int k_ = P::dof_lo(m); k_ < P::dof_hi(m); k_++) { const int i = P::dof_at(m, k_); s.qfrc_smooth[i] = s.qfrc_passive[i] - s.qfrc_bias[i] + s.qfrc_applied[i]; }
+    } else {
+      rhs_ready = ldsm && !(a.flags & B2F_XFRC);
+      for (int k0 = P::dof_lo(m); k0 < P::dof_hi(m); k0 += 4) {   // (four dofs' loads before the first store)
+        T fp[4], fb[4], fa[4]; int ii[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          ii[q] = P::dof_at(m, k0 + q < P::dof_hi(m) ? k0 + q : k0);
+          fp[q] = s.qfrc_passive[ii[q]]; fb[q] = s.qfrc_bias[ii[q]]; fa[q] = s.qfrc_applied[ii[q]];
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          if (k0 + q >= P::dof_hi(m)) break;
+          const T v = fp[q] - fb[q] + fa[q];
+          s.qfrc_smooth[ii[q]] = v;
+          if (rhs_ready) s.tmpv[ii[q]] = v;
+        }
+      }
+    }
     if (a.flags & B2F_XFRC) {
       SArr<T> xf{a.xfrc_applied + env, S};
 #pragma unroll(P::UNROLL)
@@ -856,12 +1001,16 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_smooth(const KArgs<T> a) {
         s.apply_ft(s.qfrc_smooth, b, pt, w, w + 3);
       }
     }
+    if (!ldsm) {
 #pragma unroll(P::UNROLL)
     for (int k_ = P::dof_lo(m); k_ < P::dof_hi(m); k_++) { const int i = P::dof_at(m, k_); s.qacc_smooth[i] = s.qfrc_smooth[i]; }
+    }
     if constexpr (!P::STATIC) {
-      if (ldsm) {   // the factor is still in the shared-memory column
+      if (ldsm) {   // the factor is still in the shared-memory column; the right-hand side joins it (tmpv)
         SArr<T> LDs{ws_sh + envl, EPB}, dis{ws_sh + (size_t)nM * EPB + envl, EPB};
-        ld_solve<P>(m, LDs, dis, s.qacc_smooth);
+        if (!rhs_ready) for (int k_ = P::dof_lo(m); k_ < P::dof_hi(m); k_++) { const int i = P::dof_at(m, k_); s.tmpv[i] = s.qfrc_smooth[i]; }
+        ld_solve<P>(m, LDs, dis, s.tmpv);
+        for (int k_ = P::dof_lo(m); k_ < P::dof_hi(m); k_++) { const int i = P::dof_at(m, k_); s.qacc_smooth[i] = s.tmpv[i]; }
       }
     }
     if (!ldsm) ld_solve<P>(m, s.qLD, s.qLDiagInv, s.qacc_smooth);

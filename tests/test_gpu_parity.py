@@ -1005,6 +1005,52 @@ def test_multi_device_host_and_fused_observation_exchange(b2):
     b2.lib.b2_multi_destroy(mb)
 
 
+@pytest.mark.parametrize("cfg", ["c3", "c5"])
+def test_sub_batches_reproduce_the_single_window_tick(b2, cfg):
+    """run_tick cuts large batches into windows that run the kernel pipeline side by side on their own streams (scheduling
+    only: an environment never looks at another one).  With the minimum window lowered to one tile, 1, 2 and 4 windows must
+    give bit-identical states, contact lists, solver iteration counts, joint read-back and observation buffers, through
+    the eager first tick, the capture and the graph replays."""
+    from mujoco_sim_b200 import workloads as w
+    asset = w.CONFIGS[cfg][0]
+    m = b2.Model(b2.asset(asset))
+    nenv = 1000          # padded to 1024: 4 windows of 256, 2 of 512; the last window holds the 24 pad environments
+
+    def run(nsub):
+        bt = b2.Batch(m, nenv)
+        bt.set_option("subbatch_min", 128); bt.set_option("subbatches", nsub)
+        w.load_config(cfg, bt)
+        out = []
+        if cfg == "c5":
+            w.c5_init(bt, 0)
+            for k in range(12):
+                if k == 6:
+                    w.c5_churn(bt, 0, 0)
+                bt.step(1)
+        else:
+            hw, ctl, kp, kd = w.control_spec(cfg, m)
+            bt.set_controlled(ctl); bt.set_hw_joints(hw)
+            optr, _ = bt.obs_create(1, 0)
+            bt.obs_attach(ptrs=[optr])       # fused exchange, world of one: the epilogue of k_integrate fills slice 0
+            cmd = np.ascontiguousarray(w.commands(cfg, m, np.arange(nenv)).T.astype(np.float32))
+            vel = np.zeros_like(cmd)
+            pos, velo, eff = (np.zeros_like(cmd) for _ in range(3))
+            for k in range(12):
+                bt.tick_host_raw(vel.ctypes.data, cmd.ctypes.data, pos.ctypes.data, velo.ctypes.data, eff.ctypes.data)
+            out += [pos.copy(), velo.copy(), eff.copy(), bt.obs_read(1)]
+        bt.sync()
+        out += [bt.get(f, layout=b2.engine.NATIVE, dtype=np.float32) for f in ("qpos", "qvel", "qacc", "qfrc_inverse", "xpos")]
+        out += [bt.get("ncon"), bt.get("nefc"), bt.get("solver_iter"), bt.get("contact_int")]
+        bt.close()
+        return out
+    one = run(1)
+    assert one[-4].max() >= 4 and one[-2].max() >= 2
+    for nsub in (2, 4):
+        got = run(nsub)
+        for k, (x, y) in enumerate(zip(one, got)):
+            assert np.array_equal(x, y), (nsub, k)
+
+
 def test_drift_f64_contact_free_1000_steps_meets_north_star(b2, orc):
     """BASELINE north star: "qpos L2 drift vs CPU < 1e-4 relative over 1000 steps".  The driven 7-dof arm is chaotic over
     5 s, so fp32 rounding is amplified exponentially whatever the integrator does (test above: 83 % of the environments
