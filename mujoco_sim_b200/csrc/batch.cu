@@ -364,7 +364,7 @@ int configure_constraint_kernels(b2_batch* b) {
       // k_pgs_island: EPB environments per one-warp CTA, each with its vectors and its staged records; the stage is sized
       // for eight resident CTAs per SM
       const int epbi = 32 / b->pgs_isl;
-      const long long fixedi = ((long long)2 * ((b->hdr.nv + 7) & ~3) + ((b->hdr.njmax + 3) & ~3)) * b->prec + (long long)b->isl_cap * 4;
+      const long long fixedi = ((long long)2 * ((b->hdr.nv + 7) & ~3) + (long long)2 * ((b->hdr.njmax + 3) & ~3)) * b->prec + (long long)3 * b->isl_cap * 4;
       // what fits eight resident CTAs per SM, raised — down to four CTAs — towards the record volume a busy environment
       // has (a quarter of the contact cap, each a largest-shape record): measured on C5, whose environments carry 2200
       // words on average: 2304 staged words 1.84 ms, 1232 (eight CTAs) 2.34 ms, 3328 2.07 ms
@@ -565,6 +565,8 @@ int run_tick(b2_batch* b, int flags) {
       // a team of 8 lanes per environment: 16 environments per CTA, the candidate list of each behind the model blob
       constexpr int CL = 8;
       const size_t smc = 16 + (((size_t)b->hdr.nwords * 4 + 15) & ~(size_t)15) + (size_t)(BL / CL) * ((b->m->npair + 1) & ~1) * sizeof(uint16_t);
+      // (measured and dropped: staging the tile's geom frames in shared memory for the cull — the pair walk re-reads them
+      //  from L1 already: C3 0.140 -> 0.154 ms, C5 0.180 -> 0.191 ms)
       const int gc = std::max(1, std::min(n / (BL / CL), b->nsm * std::max(1, std::min(8, (int)(200 * 1024 / smc)))));
       k_collide<T, BL, CL><<<gc, BL, smc, st>>>(a);
       b->launches++;
@@ -577,14 +579,19 @@ int run_tick(b2_batch* b, int flags) {
       static int occ_cache[2] = {0, 0};
       static size_t occ_smem[2] = {0, 0};
       const int oi = sizeof(T) == 8;
-      const size_t smr = sm + b->row_smem + b->isl_smem;
+      // (+ the row table of the epilogue, one word per row and environment, when it fits)
+      const size_t rtb = (size_t)(BL / RL) * b->hdr.njmax * sizeof(int);
+      const bool rtab = !getenv("B2_NO_ROW_TAB") && b->hdr.ntree < 4095 && sm + b->row_smem + b->isl_smem + rtb <= 100 * 1024;
+      const size_t smr = sm + b->row_smem + b->isl_smem + (rtab ? rtb : 0);
+      KArgs<T> ar = a;
+      ar.row_tab = rtab ? 1 : 0;
       if (!occ_cache[oi] || occ_smem[oi] != smr) {
         int occ = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_make_rows<T, BL, RL>, BL, smr) != cudaSuccess || occ < 1) { occ = 1; cudaGetLastError(); }
         occ_cache[oi] = occ; occ_smem[oi] = smr;
       }
       const int gr = std::max(1, std::min(n / (BL / RL), b->nsm * occ_cache[oi]));
-      k_make_rows<T, BL, RL><<<gr, BL, smr, st>>>(a);
+      k_make_rows<T, BL, RL><<<gr, BL, smr, st>>>(ar);
     }
     if (b->tc_rows > 0) {
       // one-tree model, fp32: dense M^-1 per environment, then B = J M^-1 on the tensor cores (k_project_tc.cuh)
@@ -628,7 +635,7 @@ int run_tick(b2_batch* b, int flags) {
       if (b->isl_cap) {
         // several small trees: one lane per constraint island (k_pgs_island)
         const int epbi = 32 / b->pgs_isl;
-        const size_t smi = ((size_t)2 * ((b->hdr.nv + 7) & ~3) + ((b->hdr.njmax + 3) & ~3) + b->isl_stage) * epbi * sizeof(T) + (size_t)epbi * b->isl_cap * sizeof(int);
+        const size_t smi = ((size_t)2 * ((b->hdr.nv + 7) & ~3) + (size_t)2 * ((b->hdr.njmax + 3) & ~3) + b->isl_stage) * epbi * sizeof(T) + (size_t)epbi * 3 * b->isl_cap * sizeof(int);
         const int gi = n / epbi;
         if (b->pgs_isl == 4) k_pgs_island<T, 4, PGS_ISL_MINB><<<gi, 32, smi, st>>>(a);
         else if (b->pgs_isl == 16) k_pgs_island<T, 16, PGS_ISL_MINB><<<gi, 32, smi, st>>>(a);

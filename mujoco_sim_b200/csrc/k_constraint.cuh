@@ -64,6 +64,8 @@ struct Rows {
   int nefc = 0;
   T* rowsh = nullptr;   // shared-memory column of this thread for the base rows of the contact being assembled (or null)
   int rowld = 0;        // its stride (the CTA width)
+  int* rowtab = nullptr; // shared-memory table of the environment, one word per row: type | nb << 4 | (t1 + 1) << 8 | (t2 + 1) << 20
+                         // (what the block table and the island ordering need of a block's first row; or null)
   __device__ Rows(const MV<T>& mv, const KArgs<T>& args, int e) : m(mv), h(*mv.h), a(args), env(e), S(args.nenvp) {}
   // element (r, k) of the compact Jacobian; with the tensor-core projection on, every write also goes to the
   // environment-major copy the GEMM reads
@@ -84,11 +86,12 @@ struct Rows {
     return open_at(nefc++, type, id, pos, margin, frictionloss, t1, t2, gout, zero);
   }
   // the same for a row whose index is already known (contacts assembled side by side by the lanes of a team)
-  __device__ int open_at(int r, int type, int id, T pos, T margin, T frictionloss, int t1, int t2, Seg* gout, bool zero = true) {
+  __device__ int open_at(int r, int type, int id, T pos, T margin, T frictionloss, int t1, int t2, Seg* gout, bool zero = true, int nb = 1) {
     if (t1 < 0) { t1 = t2; t2 = -1; }
     if (t1 == t2) t2 = -1;
     if (t2 >= 0 && t2 < t1) { const int t = t1; t1 = t2; t2 = t; }
     const Seg g = seg_of(m, t1, t2);
+    if (rowtab) rowtab[r] = type | (nb << 4) | ((t1 + 1) << 8) | ((t2 + 1) << 20);
     if (zero) for (int k = 0; k < g.n1 + g.n2; k++) Jc(r, k) = 0;
     a.efc_tree[((long long)2 * r) * S + env] = t1;
     a.efc_tree[((long long)2 * r + 1) * S + env] = t2;
@@ -281,7 +284,7 @@ struct Rows {
       // Jacobian entry is a load behind a store (an L2 round trip), ~100 per contact.  Rows dim .. nrow - 1 of a pyramidal
       // contact are index space only (never read: k_solve_rows / k_make_blocks work on the base rows) and are left as is.
       const bool sh = rowsh != nullptr && dim <= a.row_nb;
-      for (int k = 0; k < nrow; k++) open_at(first + k, dim == 1 ? CN_CONTACT_FRICTIONLESS : CN_CONTACT_PYRAMIDAL, c, dist, im, 0, t1, t2, &g, !sh);
+      for (int k = 0; k < nrow; k++) open_at(first + k, dim == 1 ? CN_CONTACT_FRICTIONLESS : CN_CONTACT_PYRAMIDAL, c, dist, im, 0, t1, t2, &g, !sh, dim);
       const int wrow = g.n1 + g.n2;
       auto RS = [&](int k, int e) -> T& { return rowsh[((long long)k * h.wmax + e) * rowld]; };
       if (sh) {
@@ -554,6 +557,9 @@ __global__ void __launch_bounds__(BLOCK) k_make_rows(const KArgs<T> a) {
     const int env = tile * EPB + team;
     Rows<T> rows(m, a, env);
     if (a.row_nb > 0) { rows.rowsh = reinterpret_cast<T*>(smem_raw + 16 + (size_t)nwords * 4) + threadIdx.x; rows.rowld = BLOCK; }
+    int* const rowtab = a.row_tab ? reinterpret_cast<int*>(smem_raw + 16 + (size_t)nwords * 4 + (size_t)a.row_nb * h.wmax * BLOCK * sizeof(T) +
+                                                           (a.isl_cap > 0 ? (size_t)2 * h.ntree * BLOCK * sizeof(int) : 0)) + (size_t)team * h.njmax : nullptr;
+    rows.rowtab = rowtab;
     const bool done = (a.flags & B2F_FUSABLE) && (a.status[env] & 8);  // already integrated by the smooth kernel
     const bool active = !(h.disableflags & DSBL_CONSTRAINT) && !done;
     int ne0 = 0, ne = 0;
@@ -586,22 +592,30 @@ __global__ void __launch_bounds__(BLOCK) k_make_rows(const KArgs<T> a) {
     auto CNT = [&](int t) -> int& { return lab[(size_t)(nt + t) * BLOCK]; };
     auto find = [&](int t) { if (t < 0) return 0; while (LAB(t) != t) t = LAB(t); return t; };
     for (int t = 0; t < nt; t++) { LAB(t) = t; CNT(t) = 0; }
-    while (r < ne) {
-      BlockShape bs{};
-      const long long o = (long long)r * S + env;
-      bs.type = a.efc_type[o];
-      const int id = a.efc_id[o];
-      bs.nb = 1; bs.nrow = 1;
-      if (bs.type == CN_CONTACT_PYRAMIDAL) {
-        bs.nb = a.coni[((long long)CI_DIM * h.nconmax + id) * S + env];
-        bs.nrow = 2 * (bs.nb - 1);
+    // shape and trees of the block that starts at row r: from the shared-memory row table the lanes filled while they
+    // opened the rows, else read back from the row arrays in HBM (an L2 round trip per block and per pass below)
+    auto block_at = [&](int r, BlockShape& bs, int& t1, int& t2) {
+      if (rowtab) {
+        const int pk = rowtab[r];
+        bs.type = pk & 15; bs.nb = (pk >> 4) & 15;
+        t1 = ((pk >> 8) & 4095) - 1; t2 = ((pk >> 20) & 4095) - 1;
+      } else {
+        const long long o = (long long)r * S + env;
+        bs.type = a.efc_type[o];
+        bs.nb = bs.type == CN_CONTACT_PYRAMIDAL ? a.coni[((long long)CI_DIM * h.nconmax + a.efc_id[o]) * S + env] : 1;
+        t1 = a.efc_tree[((long long)2 * r) * S + env]; t2 = a.efc_tree[((long long)2 * r + 1) * S + env];
       }
-      const int t1 = a.efc_tree[((long long)2 * r) * S + env], t2 = a.efc_tree[((long long)2 * r + 1) * S + env];
+      bs.nrow = bs.type == CN_CONTACT_PYRAMIDAL ? 2 * (bs.nb - 1) : 1;
       const Seg g = seg_of(m, t1, t2);
       bs.s1 = g.s1; bs.n1 = g.n1; bs.s2 = g.s2; bs.w = g.n1 + g.n2;
       bs.layout();
+    };
+    while (r < ne) {
+      BlockShape bs{};
+      int t1, t2;
+      block_at(r, bs, t1, t2);
       a.blk_row0[(long long)nblk * S + env] = r;
-      a.blk_off[(long long)nblk * S + env] = nt ? bs.len : woff;   // islands: the length for now, the offset below
+      if (!nt) a.blk_off[(long long)nblk * S + env] = woff;   // (islands: the offsets follow below)
       if (nt && t2 >= 0) {
         const int ra = find(t1), rb = find(t2);
         if (ra != rb) LAB(ra > rb ? ra : rb) = ra < rb ? ra : rb;
@@ -611,9 +625,12 @@ __global__ void __launch_bounds__(BLOCK) k_make_rows(const KArgs<T> a) {
     }
     if (nt) {
       // words per island, islands numbered by ascending root; then every block's offset inside its island (row order kept)
-      for (int q = 0; q < nblk; q++) {
-        const int row = a.blk_row0[(long long)q * S + env];
-        CNT(find(a.efc_tree[((long long)2 * row) * S + env])) += a.blk_off[(long long)q * S + env];
+      for (int r2 = 0; r2 < ne;) {
+        BlockShape bs{};
+        int t1, t2;
+        block_at(r2, bs, t1, t2);
+        CNT(find(t1)) += bs.len;
+        r2 += bs.nrow;
       }
       int start = 0, ni = 0;
       for (int t = 0; t < nt; t++) {
@@ -625,12 +642,15 @@ __global__ void __launch_bounds__(BLOCK) k_make_rows(const KArgs<T> a) {
         start += c;
         ni++;
       }
-      for (int q = 0; q < nblk; q++) {
-        const int row = a.blk_row0[(long long)q * S + env];
-        const int root = find(a.efc_tree[((long long)2 * row) * S + env]);
-        const int len = a.blk_off[(long long)q * S + env];
+      int q = 0;
+      for (int r2 = 0; r2 < ne; q++) {
+        BlockShape bs{};
+        int t1, t2;
+        block_at(r2, bs, t1, t2);
+        const int root = find(t1);
         a.blk_off[(long long)q * S + env] = CNT(root);
-        CNT(root) += len;
+        CNT(root) += bs.len;
+        r2 += bs.nrow;
       }
       if (!done) a.nisl[env] = ni < a.isl_cap ? ni : a.isl_cap; else a.nisl[env] = 0;
     }
@@ -1665,15 +1685,21 @@ __global__ void __launch_bounds__(32, MINB) k_pgs_island(const KArgs<T> a) {
   T* accsh = reinterpret_cast<T*>(smem_raw);
   T* tmpsh = accsh + (size_t)EPB * nvs;
   T* fsh = tmpsh + (size_t)EPB * nvs;
-  T* stsh = fsh + (size_t)EPB * ((njmax + 3) & ~3);
-  int* stosh = reinterpret_cast<int*>(stsh + (size_t)EPB * cap);   // [EPB][isl_cap] where island i was staged (-1: not staged)
+  T* finvsh = fsh + (size_t)EPB * ((njmax + 3) & ~3);   // per-row forces of mj_inverse (efc_finv), fetched with the prologue
+  T* stsh = finvsh + (size_t)EPB * ((njmax + 3) & ~3);
+  // [EPB][3][isl_cap]: where island i was staged (-1: not staged), and the island table of the environment (word range
+  // of island i in the slab) — read by every walk and every sweep, so kept next to the records
+  int* stosh = reinterpret_cast<int*>(stsh + (size_t)EPB * cap);
   const int team = threadIdx.x / ISL, l = threadIdx.x % ISL;
   const unsigned tmask = (ISL == 32 ? 0xffffffffu : ((1u << ISL) - 1u)) << (threadIdx.x & ~(ISL - 1));
   T* acc = accsh + (size_t)team * nvs;
   T* tmp = tmpsh + (size_t)team * nvs;
   T* f = fsh + (size_t)team * ((njmax + 3) & ~3);
+  T* finv = finvsh + (size_t)team * ((njmax + 3) & ~3);
   T* st = stsh + (size_t)team * cap;
-  int* sto = stosh + (size_t)team * a.isl_cap;
+  int* sto = stosh + (size_t)team * 3 * a.isl_cap;
+  int* iso = sto + a.isl_cap;
+  int* ise = iso + a.isl_cap;
   const int ngroups = (a.ncount + EPB - 1) / EPB;
   const T tol = m.f(h.o_opt_real, 3), scale = 1 / (m.f(h.o_opt_real, 4) * T(nv > 1 ? nv : 1));
   auto team_sum = [&](T v) {
@@ -1688,6 +1714,18 @@ __global__ void __launch_bounds__(32, MINB) k_pgs_island(const KArgs<T> a) {
     const T* slab = a.efc_blocks + env * capw;
     int iters = 0;
     __syncwarp();   // the previous group's readers are done with the shared vectors
+    // everything the solve reads once per environment, in flight together: the island table, the warm-start acceleration
+    // and mj_inverse's row forces (one L2 / HBM round trip each when they were fetched where they are used)
+    const bool invf = (a.flags & B2F_INVERSE) && ne > 0;
+#pragma unroll 2
+    for (int i = l; i < nisl; i += ISL) { iso[i] = a.isl_off[(long long)i * S + env]; ise[i] = a.isl_end[(long long)i * S + env]; }
+#pragma unroll 4
+    for (int i = l; i < nv; i += ISL) { acc[i] = a.qacc_warmstart[(long long)i * S + env]; tmp[i] = 0; }
+    if (invf) {
+#pragma unroll 4
+      for (int r = l; r < ne; r += ISL) finv[r] = a.efc_finv[(long long)r * S + env];
+    }
+    __syncwarp(tmask);
     {
       // stage the records island by island: island i starts on the bank group of the lane that will walk it (records
       // are whole 128-byte lines, so the lanes of a quarter-warp keep reading disjoint banks while their blocks have
@@ -1696,7 +1734,7 @@ __global__ void __launch_bounds__(32, MINB) k_pgs_island(const KArgs<T> a) {
       //  a load -> store loop serialised on the L2 latency, ~40 k cycles per environment group)
       int pos = 0;
       for (int i = 0; i < nisl; i++) {
-        const int o = a.isl_off[(long long)i * S + env], len = a.isl_end[(long long)i * S + env] - o;
+        const int o = iso[i], len = ise[i] - o;
         const int start = ((pos + 31) & ~31) + 4 * ((team * ISL + (i % ISL)) & 7);
         const bool fits = start + len <= cap;
         if (fits) {
@@ -1712,14 +1750,13 @@ __global__ void __launch_bounds__(32, MINB) k_pgs_island(const KArgs<T> a) {
       asm volatile("cp.async.commit_group;" ::: "memory");
       asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
-    for (int i = l; i < nv; i += ISL) { acc[i] = a.qacc_warmstart[(long long)i * S + env]; tmp[i] = 0; }
     __syncwarp();
     // this lane's blocks: islands l, l + ISL, ... one after the other
     struct Cursor { int isl, off, end; const T* base; };   // the record at slab offset off is base + off
     auto cur_load = [&](Cursor& c) {
       c.base = slab;
       if (c.isl < nisl) {
-        c.off = a.isl_off[(long long)c.isl * S + env]; c.end = a.isl_end[(long long)c.isl * S + env];
+        c.off = iso[c.isl]; c.end = ise[c.isl];
         const int so = sto[c.isl];
         if (so >= 0) c.base = st + so - c.off;
       } else { c.off = 0; c.end = 0; }
@@ -1799,8 +1836,10 @@ __global__ void __launch_bounds__(32, MINB) k_pgs_island(const KArgs<T> a) {
       if (cost > 0) warm = false;
       if (ne > 0) {
         if (warm) {
+#pragma unroll 4
           for (int i = l; i < nv; i += ISL) acc[i] = a.qacc_smooth[(long long)i * S + env] + tmp[i];
         } else {
+#pragma unroll 4
           for (int i = l; i < nv; i += ISL) acc[i] = a.qacc_smooth[(long long)i * S + env];
           for (int r = l; r < ne; r += ISL) f[r] = 0;
         }
@@ -1917,7 +1956,7 @@ __global__ void __launch_bounds__(32, MINB) k_pgs_island(const KArgs<T> a) {
         T d[6] = {0, 0, 0, 0, 0, 0};
         bool any = false;
         for (int rr = 0; rr < bs.nrow; rr++) {
-          const T fr = a.efc_finv[(long long)(row0 + rr) * S + env];
+          const T fr = finv[row0 + rr];
           if (fr == 0) continue;
           const int k = bs.nb > 1 ? rr / 2 + 1 : 0;
           any = true;
@@ -1928,6 +1967,7 @@ __global__ void __launch_bounds__(32, MINB) k_pgs_island(const KArgs<T> a) {
         cur_next(c, bs.len);
       }
       __syncwarp(tmask);
+#pragma unroll 4
       for (int i = l; i < nv; i += ISL) if (tmp[i] != 0) a.qfrc_inverse[(long long)i * S + env] -= tmp[i];
     }
   }
@@ -1975,7 +2015,14 @@ __global__ void __launch_bounds__(BLOCK) k_integrate(const KArgs<T> a) {
     const bool skip = (a.flags & B2F_FUSABLE) && (a.status[env] & 8);   // integrated by the smooth kernel already
     SArr<T> qacc{a.qacc + env, S};
     bool bad = false;
-    if (!skip) for (int i = 0; i < nv; i++) bad |= !(t_abs(qacc[i]) < T(1e10));   // (every lane looks at the whole vector: one decision per environment)
+    if (!skip)   // (every lane looks at the whole vector: one decision per environment; eight loads in flight per step)
+      for (int i0 = 0; i0 < nv; i0 += 8) {
+        T v[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) v[q] = i0 + q < nv ? qacc[i0 + q] : T(0);
+#pragma unroll
+        for (int q = 0; q < 8; q++) bad |= !(t_abs(v[q]) < T(1e10));
+      }
     if (bad) {  // reset instead of integrating garbage
       if (L > 1) __syncwarp(tmask);   // every lane has read qacc before anybody clears it
       if (lane == 0) {
@@ -1996,7 +2043,14 @@ __global__ void __launch_bounds__(BLOCK) k_integrate(const KArgs<T> a) {
       }
       // qfrc_smooth becomes the total force of the implicit-damping solve; qLD / qLDiagInv / qacc_smooth are dead after
       // the solver and serve as scratch for the damped factorisation
-      if (h.has_damping) for (int k_ = GenericP::dof_lo(m); k_ < GenericP::dof_hi(m); k_++) { const int i = GenericP::dof_at(m, k_); frc[i] += a.qfrc_constraint[i * S + env]; }
+      if (h.has_damping)
+        for (int k0 = GenericP::dof_lo(m); k0 < GenericP::dof_hi(m); k0 += 8) {   // (eight dofs' loads before the first store)
+          T f[8], c[8]; int ii[8];
+#pragma unroll
+          for (int q = 0; q < 8; q++) { ii[q] = GenericP::dof_at(m, k0 + q < GenericP::dof_hi(m) ? k0 + q : k0); f[q] = frc[ii[q]]; c[q] = a.qfrc_constraint[ii[q] * S + env]; }
+#pragma unroll
+          for (int q = 0; q < 8; q++) if (k0 + q < GenericP::dof_hi(m)) frc[ii[q]] = f[q] + c[q];
+        }
       euler_step<GenericP>(m, qpos, qvel, qM, qacc, frc, a.dt(), LD, dinv, xa);
       if (L > 1) __syncwarp(tmask);
       if (lane == 0) {

@@ -131,6 +131,61 @@ __device__ __forceinline__ void euler_step(const MV<T>& m, const AQ& qpos, const
   const DModel& h = *m.h;
   const int nv = P::nv(m);
   const bool damp = h.has_damping && !(h.disableflags & DSBL_EULERDAMP);
+  if constexpr (!P::STATIC) {
+    // generic trees: the arrays live in HBM / L2 (or shared-memory scratch), every loop fetches a group of elements before
+    // it stores the first result — a store orders the later loads of possibly aliasing arrays behind it, one L2 round
+    // trip per element otherwise
+    if (damp) {
+      for (int k_ = P::dof_lo(m); k_ < P::dof_hi(m); k_++) {   // this lane's rows of M
+        const int i = P::dof_at(m, k_);
+        const int adr = P::dof_Madr(m, i), cnt = P::dof_Mcnt(m, i);
+        const T dmp = hs * m.f(h.o_dof_damping, i);
+        for (int a0 = 0; a0 < cnt; a0 += 8) {
+          T v[8];
+#pragma unroll
+          for (int q = 0; q < 8; q++) v[q] = a0 + q < cnt ? qM[adr + a0 + q] : T(0);
+          if (a0 == 0) v[0] += dmp;
+#pragma unroll
+          for (int q = 0; q < 8; q++) if (a0 + q < cnt) LDtmp[adr + a0 + q] = v[q];
+        }
+      }
+      ld_factor<P>(m, LDtmp, dinvtmp);
+    }
+    for (int k0 = P::dof_lo(m); k0 < P::dof_hi(m); k0 += 8) {
+      T v[8]; int ii[8];
+#pragma unroll
+      for (int q = 0; q < 8; q++) { ii[q] = P::dof_at(m, k0 + q < P::dof_hi(m) ? k0 + q : k0); v[q] = damp ? frc[ii[q]] : qacc_in[ii[q]]; }
+#pragma unroll
+      for (int q = 0; q < 8; q++) if (k0 + q < P::dof_hi(m)) xa[ii[q]] = v[q];
+    }
+    if (damp) ld_solve<P>(m, LDtmp, dinvtmp, xa);
+    // velocity and position of a joint together: its dofs' qvel, acceleration and its qpos are fetched at once
+    for (int k_ = P::jnt_lo(m); k_ < P::jnt_hi(m); k_++) {
+      const int j = P::jnt_at(m, k_);
+      const int qa = P::jnt_qposadr(m, j), da = P::jnt_dofadr(m, j), jt = P::jnt_type(m, j);
+      if (jt == JNT_FREE) {
+        T q[7], v[6], ac[6];
+        ld<T, 7>(q, qpos, qa); ld<T, 6>(v, qvel, da); ld<T, 6>(ac, xa, da);
+        for (int k = 0; k < 6; k++) v[k] += hs * ac[k];
+        for (int k = 0; k < 3; k++) q[k] += hs * v[k];
+        quat_integrate(q + 3, v + 3, hs);
+        st<T, 6>(qvel, da, v); st<T, 7>(qpos, qa, q);
+      } else if (jt == JNT_BALL) {
+        T q[4], v[3], ac[3];
+        ld<T, 4>(q, qpos, qa); ld<T, 3>(v, qvel, da); ld<T, 3>(ac, xa, da);
+        for (int k = 0; k < 3; k++) v[k] += hs * ac[k];
+        quat_integrate(q, v, hs);
+        st<T, 3>(qvel, da, v); st<T, 4>(qpos, qa, q);
+      } else {
+        T q = qpos[qa], v = qvel[da];
+        const T ac = xa[da];
+        v += hs * ac;
+        q += hs * v;
+        qvel[da] = v; qpos[qa] = q;
+      }
+    }
+    return;
+  }
   if (damp) {
 #pragma unroll(P::UNROLL)
     for (int i = 0; i < P::nM(m); i++) {
