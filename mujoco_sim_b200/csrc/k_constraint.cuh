@@ -784,6 +784,42 @@ __device__ __forceinline__ void make_blocks_pass(const KArgs<T>& a, const int bl
     const long long slab_env = ((long long)tile * BLOCK + wbase) * capw;   // slab offset of lane 0's environment
     T vel[6], js[6], jq[6], A[6][6];
     const int nbw = __reduce_max_sync(0xffffffffu, nb);
+    // The rows of the factor the block's trees need (off-diagonal entries of L in row order, then 1 / D), fetched ONCE
+    // per block into the head of the thread's column — free until the parameters are written at the end — when they fit
+    // there: the solves of the block's base directions then read them from shared memory (a row fetched inside the solve
+    // is one L2 round trip per dof, per pass and per base direction).
+    bool ldc = false;
+    if (have && !a.em_rows && !a.efc_B) {
+      int tot = g.n1 + g.n2;
+      for (int i = g.s1; i < g.s1 + g.n1; i++) tot += m.i(h.o_dof_Mcnt, i) - 1;
+      for (int i = g.s2; i < g.s2 + g.n2; i++) tot += m.i(h.o_dof_Mcnt, i) - 1;
+      ldc = tot <= npar;
+      if (ldc) {
+        int k = 0;
+        for (int sgm = 0; sgm < 2; sgm++) {
+          const int lo = sgm ? g.s2 : g.s1, n = sgm ? g.n2 : g.n1;
+          for (int i = lo; i < lo + n; i++) {
+            const int adr = m.i(h.o_dof_Madr, i), cnt = m.i(h.o_dof_Mcnt, i);
+            for (int q0 = 1; q0 < cnt; q0 += 8) {
+              T l[8];
+#pragma unroll
+              for (int q = 0; q < 8; q++) l[q] = q0 + q < cnt ? LD[adr + q0 + q] : T(0);
+#pragma unroll
+              for (int q = 0; q < 8; q++) if (q0 + q < cnt) rec[k + q0 - 1 + q] = l[q];
+            }
+            k += cnt - 1;
+          }
+          for (int i0 = lo; i0 < lo + n; i0 += 8) {
+            T dv[8];
+#pragma unroll
+            for (int q = 0; q < 8; q++) dv[q] = i0 + q < lo + n ? dinv[i0 + q] : T(0);
+#pragma unroll
+            for (int q = 0; q < 8; q++) if (i0 + q < lo + n) rec[k + i0 - lo + q] = dv[q];
+          }
+          k += n;
+        }
+      }
+    }
     for (int c = 0; c < nbw; c++) {
       const bool on = have && c < nb;
       if (on) {
@@ -815,6 +851,33 @@ __device__ __forceinline__ void make_blocks_pass(const KArgs<T>& a, const int bl
           for (int e = 0; e < w; e++) Bc[e] = brow[e];
         } else if (a.efc_B) {
           for (int e = 0; e < w; e++) Bc[e] = a.efc_B[((long long)(r + c) * W + e) * S + env];
+        } else if (ldc) {
+          // same loops, same operation order as below, the factor's rows from the column head
+          int k0 = 0;
+          for (int sgm = 0; sgm < 2; sgm++) {
+            const int lo = sgm ? g.s2 : g.s1, n = sgm ? g.n2 : g.n1, base = sgm ? g.n1 : 0;
+            if (n == 0) continue;
+            int nl = 0;
+            for (int i = lo; i < lo + n; i++) nl += m.i(h.o_dof_Mcnt, i) - 1;
+            int k = k0 + nl;
+            for (int i = lo + n - 1; i >= lo; i--) {
+              const int adr = m.i(h.o_dof_Madr, i), cnt = m.i(h.o_dof_Mcnt, i);
+              k -= cnt - 1;
+              const T xi = Bc[base + i - lo];
+              if (xi == 0) continue;
+              for (int q = 1; q < cnt; q++) Bc[base + m.i(h.o_dof_anc, adr + q) - lo] -= rec[k + q - 1] * xi;
+            }
+            for (int i = lo; i < lo + n; i++) Bc[base + i - lo] *= rec[k0 + nl + i - lo];
+            k = k0;
+            for (int i = lo; i < lo + n; i++) {
+              const int adr = m.i(h.o_dof_Madr, i), cnt = m.i(h.o_dof_Mcnt, i);
+              T xi = Bc[base + i - lo];
+              for (int q = 1; q < cnt; q++) xi -= rec[k + q - 1] * Bc[base + m.i(h.o_dof_anc, adr + q) - lo];
+              Bc[base + i - lo] = xi;
+              k += cnt - 1;
+            }
+            k0 += nl + n;
+          }
         } else
         for (int sgm = 0; sgm < 2; sgm++) {
           const int lo = sgm ? g.s2 : g.s1, n = sgm ? g.n2 : g.n1, base = sgm ? g.n1 : 0;
