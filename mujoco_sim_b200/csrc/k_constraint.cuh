@@ -207,13 +207,25 @@ struct Rows {
 
   __device__ void limits() {
     if (!h.has_limits || (h.disableflags & DSBL_LIMIT)) return;
-    for (int j = 0; j < h.njnt; j++) {
+    for (int j0 = 0; j0 < h.njnt; j0 += 8) {
+    // (the positions of eight joints are fetched before the first row is opened: its stores order later loads behind them)
+    T val8[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const int j = j0 + k;
+      const bool scalar = j < h.njnt && m.i(h.o_jnt_limited, j) && (m.i(h.o_jnt_type, j) == JNT_SLIDE || m.i(h.o_jnt_type, j) == JNT_HINGE);
+      val8[k] = scalar ? a.qpos[m.i(h.o_jnt_qposadr, j) * S + env] : T(0);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const int j = j0 + k;
+      if (j >= h.njnt) break;
       if (!m.i(h.o_jnt_limited, j)) continue;
       const int qa = m.i(h.o_jnt_qposadr, j), da = m.i(h.o_jnt_dofadr, j), jt = m.i(h.o_jnt_type, j);
       const T margin = m.f(h.o_jnt_margin, j);
       Seg g;
       if (jt == JNT_SLIDE || jt == JNT_HINGE) {
-        const T value = a.qpos[qa * S + env];
+        const T value = val8[k];
         for (int side = -1; side <= 1; side += 2) {
           const T dist = side * (m.f(h.o_jnt_range, 2 * j + (side + 1) / 2) - value);
           if (dist < margin) {
@@ -223,7 +235,7 @@ struct Rows {
         }
       } else if (jt == JNT_BALL) {
         T q[4];
-        for (int k = 0; k < 4; k++) q[k] = a.qpos[(qa + k) * S + env];
+        for (int k4 = 0; k4 < 4; k4++) q[k4] = a.qpos[(qa + k4) * S + env];
         normalize4(q);
         T ax[3] = {q[1], q[2], q[3]};
         const T s = normalize3(ax);
@@ -234,9 +246,10 @@ struct Rows {
         const T dist = t_max(m.f(h.o_jnt_range, 2 * j), m.f(h.o_jnt_range, 2 * j + 1)) - angle;
         if (dist < margin) {
           const int r = open(CN_LIMIT_JOINT, j, dist, margin, 0, m.i(h.o_dof_treeid, da), -1, &g);
-          if (r >= 0) for (int k = 0; k < 3; k++) Jc(r, seg_pos(g, da + k)) = -ax[k];
+          if (r >= 0) for (int k2 = 0; k2 < 3; k2++) Jc(r, seg_pos(g, da + k2)) = -ax[k2];
         }
       }
+    }
     }
   }
 
@@ -1279,7 +1292,9 @@ __device__ __forceinline__ void pgs_visit_lane(const T* __restrict__ rec, bool h
 // (the common case: most contacts of a scene share a condim) — record offsets are compile-time constants, no parameter
 // picks, no row padding, contact bounds only (f >= 0).  SH: every such record is staged in shared memory (the loads
 // become LDS instead of generic loads).  Same operation order as pgs_visit_lane.
-template <typename T, int NB, int WCAP, bool SH>
+// SEG1: every such block lies in ONE kinematic tree (a prop on the table, the arm against the table): its elements of the
+// acceleration are acc[s1 + e] — one address, immediate offsets — instead of a pick between two segments per element.
+template <typename T, int NB, int WCAP, bool SH, bool SEG1 = false>
 __device__ __forceinline__ void pgs_visit_lane_exact(const T* __restrict__ rec, bool have, const VecN<T, 4>& h0, const VecN<T, 4>& h1,
                                                      T* __restrict__ acc, T* __restrict__ f, T& improvement) {
   static_assert(NB == 3 || NB == 4, "pyramidal contacts of condim 3 / 4");
@@ -1304,10 +1319,14 @@ __device__ __forceinline__ void pgs_visit_lane_exact(const T* __restrict__ rec, 
   for (int r = 0; r < NROW; r++) fo[r] = have ? f[row0 + r] : T(0);
   T x[WCAP];
   int dofs[WCAP];
+  T* const acc1 = acc + (have ? s1 : 0);
 #pragma unroll
   for (int e = 0; e < WCAP; e++) {
+    if constexpr (SEG1) { dofs[e] = 0; x[e] = e < w ? acc1[e] : T(0); }
+    else {
     dofs[e] = e < n1 ? s1 + e : s2 + e - n1;
     x[e] = e < w ? acc[dofs[e]] : T(0);
+    }
   }
   T u[NB];
 #pragma unroll
@@ -1366,7 +1385,8 @@ __device__ __forceinline__ void pgs_visit_lane_exact(const T* __restrict__ rec, 
       T s0 = 0;
 #pragma unroll
       for (int k = 0; k < NB; k++) s0 = t_fma(d[k], Bv[k][e], s0);
-      if (e < w) acc[dofs[e]] = x[e] + s0;
+      if constexpr (SEG1) { if (e < w) acc1[e] = x[e] + s0; }
+      else if (e < w) acc[dofs[e]] = x[e] + s0;
     }
   }
 }
@@ -1936,9 +1956,12 @@ __global__ void __launch_bounds__(32, MINB) k_pgs_island(const KArgs<T> a) {
           const int ww = __reduce_max_sync(0xffffffffu, dec_int(h0.v[2]) >> 10);
           // every lane with a block has a condim-3 contact staged in shared memory (the common step): exact-shape visit
           const bool ex3 = __all_sync(0xffffffffu, !have || (((code >> 4) & 15) == 3 && c.base != slab));
+          // ... and each of them lies in one kinematic tree (props on the table: the common step of the common step)
+          const bool seg1 = ex3 && ww <= 8 && __all_sync(0xffffffffu, !have || (dec_int(h0.v[2]) & 1023) == (dec_int(h0.v[2]) >> 10));
           // (an exact visit for condim 4 as well was measured and lost: the extra vote per step costs the tail more than
           //  the shorter visit gains where condim-4 steps are the minority, profiles/r02_pgs_analysis.txt)
-          if (ex3 && ww <= 8) pgs_visit_lane_exact<T, 3, 8, true>(rec, have, h0, h1, acc, f, improvement);
+          if (seg1) pgs_visit_lane_exact<T, 3, 8, true, true>(rec, have, h0, h1, acc, f, improvement);
+          else if (ex3 && ww <= 8) pgs_visit_lane_exact<T, 3, 8, true>(rec, have, h0, h1, acc, f, improvement);
           else if (ex3 && ww <= 12) pgs_visit_lane_exact<T, 3, 12, true>(rec, have, h0, h1, acc, f, improvement);
           else if (nbw <= 4) {
             if (ww <= 8) {

@@ -556,12 +556,12 @@ struct Smooth {
     for (int k_ = P::dof_lo(m); k_ < P::dof_hi(m); k_++) {
       const int i = P::dof_at(m, k_);
       int adr = P::dof_Madr(m, i);
-      const T vi = vec[i];
-      T ri = res[i] + qM[adr] * vi;
       if constexpr (!P::STATIC) {
         const int cnt = P::dof_Mcnt(m, i);
-        // (the row's entries and the ancestors' vector elements, four at a time, before the first update is stored)
-        for (int a0 = 1; a0 < cnt; a0 += 4) {
+        // (the row's entries and the vector elements of the dof and its ancestors, four at a time, before the first
+        //  update is stored; entry 0 of a row is the diagonal and its "ancestor" the dof itself)
+        T vi = 0, ri = 0;
+        for (int a0 = 0; a0 < cnt; a0 += 4) {
           T mij[4], vj[4], rj[4]; int jj[4];
 #pragma unroll
           for (int q = 0; q < 4; q++) {
@@ -572,12 +572,15 @@ struct Smooth {
 #pragma unroll
           for (int q = 0; q < 4; q++) {
             if (a0 + q >= cnt) break;
+            if (a0 + q == 0) { vi = vj[0]; ri = rj[0] + mij[0] * vi; continue; }
             ri += mij[q] * vj[q];
             res[jj[q]] = rj[q] + mij[q] * vi;   // (the ancestors of a row are distinct dofs: no entry is updated twice here)
           }
         }
         res[i] = ri;
       } else {
+      const T vi = vec[i];
+      T ri = res[i] + qM[adr] * vi;
       adr++;
 #pragma unroll(P::UNROLL)
       for (int j = P::dof_parentid(m, i); j >= 0; j = P::dof_parentid(m, j), adr++) {

@@ -121,7 +121,7 @@ for _n, (_r, _a) in _sig.items():
     _f.restype = _r
     _f.argtypes = _a
 
-INT_FIELDS = {"ncon", "nefc", "efc_type", "efc_id", "contact_int", "solver_iter", "status", "efc_nwords", "env_order"}
+INT_FIELDS = {"ncon", "nefc", "efc_type", "efc_id", "contact_int", "solver_iter", "status", "efc_nwords", "env_order", "nisl", "isl_off", "isl_end", "nblk", "blk_row0", "blk_off", "efc_tree"}
 
 
 def _err():
