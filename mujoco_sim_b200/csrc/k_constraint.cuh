@@ -1486,12 +1486,24 @@ __device__ __forceinline__ void pgs_visit_exact(const T* __restrict__ rec, bool 
 // words / BINW, one CTA; the order inside a bin is whatever the atomics give, which affects scheduling only).
 template <int NBIN, int THREADS>
 __global__ void __launch_bounds__(THREADS) k_order_envs(const int* __restrict__ nefc, const int* __restrict__ nwords, int* __restrict__ order,
-                                                        int nenvp, int binw, const int* pending, int use_pending) {
+                                                        int nenvp, int binw, const int* pending, int use_pending, const int* __restrict__ iters, int) {
   if (use_pending && pending[0] == 0) return;
   __shared__ int hist[NBIN], start[NBIN];
   for (int i = threadIdx.x; i < NBIN; i += THREADS) hist[i] = 0;
   __syncthreads();
-  auto bin_of = [&](int e) { const int w = nefc[e] > 0 ? nwords[e] : 0; const int b = w / binw; return NBIN - 1 - (b < NBIN ? b : NBIN - 1); };
+  // predicted work (island solver; iters == null: record volume only): the iterations the environment's solve took LAST
+  // tick first (contact states persist from tick to tick), the record volume second — the few environments that use all
+  // 100 iterations set the kernel's duration: they must start first, and together, because a warp steps its four
+  // environments in lockstep
+  auto bin_of = [&](int e) {
+    const int w = nefc[e] > 0 ? nwords[e] : 0;
+    int b = w / binw;
+    if (iters) {
+      const int it = nefc[e] > 0 ? (iters[e] < 100 ? iters[e] : 100) : 0;
+      b = 2 * it + (b / 5 < 54 ? b / 5 : 54);
+    }
+    return NBIN - 1 - (b < NBIN ? b : NBIN - 1);
+  };
   for (int e = threadIdx.x; e < nenvp; e += THREADS) atomicAdd(&hist[bin_of(e)], 1);
   __syncthreads();
   if (threadIdx.x == 0) { int s0 = 0; for (int i = 0; i < NBIN; i++) { start[i] = s0; s0 += hist[i]; } }
