@@ -308,6 +308,7 @@ KArgs<T> make_args(b2_batch* b, int flags) {
   a.model = b->blob_dev; a.model_words = b->hdr.nwords;
   a.flags = flags; a.ws_block = b->smooth_block; a.h = (T)b->h; a.wp = b->wp;
   a.hp = b->h_dev ? (sizeof(T) == 8 ? (const T*)b->h_dev : (const T*)((const char*)b->h_dev + 8)) : nullptr;
+  a.ld_extra = b->ld_extra;
   a.block_capw = b->block_capw; a.block_npar = b->block_npar; a.stage_cap = b->isl_cap ? b->isl_stage : b->stage_cap; a.row_nb = b->row_nb; a.isl_cap = b->isl_cap; a.em_rows = b->tc_rows;
   a.obs_peers = b->obs_peers_dev; a.obs_world = b->obs_world; a.obs_rank = b->obs_rank; a.obs_nenv = b->nenv;
   a.hw_vel = b->io_in[0]; a.hw_eff = b->io_in[1];
@@ -1192,13 +1193,19 @@ b2_batch* b2_create(const mjModel* m, int nenv, int device, int precision) {
     b->smooth_block = 128;
     b->smooth_smem = b->blob_smem;
     b->ws_global = true;
-    // factor scratch in shared memory (B2F_LD_SMEM): (nM + 2 nv) words per environment, the widest CTA that leaves two CTAs per SM
+    // factor scratch in shared memory (B2F_LD_SMEM): (nM + 3 nv) words per environment (factor, 1 / D, two vectors), the widest CTA that leaves two CTAs per SM
     b->ld_smem = 0;
     if (!getenv("B2_NO_LD_SMEM"))
       for (int cand : {128, 64, 32}) {
         if (TL > 1 && cand != 128) break;
-        const size_t need = b->blob_smem + (size_t)(b->hdr.nM + 2 * b->hdr.nv) * (cand / TL) * precision;
-        if (need <= 110 * 1024) { b->smooth_block = cand; b->ld_smem = need - b->blob_smem; b->smooth_smem = need; break; }
+        // (the fourth vector — the second product of the fused M x pass — only when it does not cost the CTA width)
+        const size_t need3 = b->blob_smem + (size_t)(b->hdr.nM + 3 * b->hdr.nv) * (cand / TL) * precision;
+        const size_t need2 = b->blob_smem + (size_t)(b->hdr.nM + 2 * b->hdr.nv) * (cand / TL) * precision;
+        if (need2 > 110 * 1024) continue;
+        b->ld_extra = need3 <= 110 * 1024 ? 1 : 0;
+        const size_t need = b->ld_extra ? need3 : need2;
+        b->smooth_block = cand; b->ld_smem = need - b->blob_smem; b->smooth_smem = need;
+        break;
       }
     if (alloc_field(b, "_ws", b->hdr.ws_slots, 0, nullptr) < 0) return bail("alloc failed");
   }

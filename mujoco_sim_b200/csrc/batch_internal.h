@@ -69,6 +69,7 @@ struct b2_batch {
   int pgs_isl = 8;       // lanes (= islands relaxed side by side) per environment in k_pgs_island
   int isl_stage = 0;     // words of records k_pgs_island stages per environment
   size_t isl_smem = 0;   // k_make_rows: island label columns
+  int ld_extra = 0;      // ... with a fourth vector (second product of k_smooth's fused M x pass)
   size_t ld_smem = 0;    // bytes of the shared-memory factor scratch of k_smooth / k_integrate (workspace in HBM), 0: off
   int row_nb = 0;        // k_make_rows' shared-memory row column: base rows it holds (0: off)
   size_t row_smem = 0;

@@ -91,6 +91,7 @@ struct KArgs {
   int block_npar;         // header + parameter words of the largest block (k_make_blocks' shared-memory column layout)
   int stage_cap;          // words of an environment's records the solver keeps in shared memory
   int wp;                 // (unused) padded compact row width
+  int ld_extra;           // k_smooth: the shared-memory factor scratch has a fourth vector (B2F_LD_SMEM)
   int row_tab;            // k_make_rows: a shared-memory row table (one word per row and environment) sits behind its other columns
   int row_nb;             // k_make_rows: base rows its per-thread shared-memory column holds (0: rows are accumulated in HBM)
   int* solver_iter;       // [nenvp]

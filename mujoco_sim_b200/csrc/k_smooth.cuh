@@ -546,6 +546,39 @@ struct Smooth {
     }
   }
 
+  // res = M vec and res2 = M vec2 in ONE pass over the rows of M (generic trees): the controller's M ddq and mj_inverse's
+  // M qacc of the reference tick.  Every row costs one L2 round trip whatever the number of right-hand sides.  Same
+  // operation order per product as mul_M.
+  template <typename AR, typename AV, typename AR2, typename AV2>
+  __device__ __forceinline__ void mul_M2(const AR& res, const AV& vec, const AR2& res2, const AV2& vec2) {
+    for (int k_ = P::dof_lo(m); k_ < P::dof_hi(m); k_++) { const int i = P::dof_at(m, k_); res[i] = 0; res2[i] = 0; }
+    for (int k_ = P::dof_lo(m); k_ < P::dof_hi(m); k_++) {
+      const int i = P::dof_at(m, k_);
+      const int adr = P::dof_Madr(m, i), cnt = P::dof_Mcnt(m, i);
+      T vi = 0, ri = 0, vi2 = 0, ri2 = 0;
+      for (int a0 = 0; a0 < cnt; a0 += 4) {
+        T mij[4], vj[4], rj[4], vj2[4], rj2[4]; int jj[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const bool in = a0 + q < cnt;
+          jj[q] = in ? P::dof_anc(m, adr + a0 + q) : i;
+          mij[q] = in ? qM[adr + a0 + q] : T(0);
+          vj[q] = in ? vec[jj[q]] : T(0); rj[q] = in ? res[jj[q]] : T(0);
+          vj2[q] = in ? vec2[jj[q]] : T(0); rj2[q] = in ? res2[jj[q]] : T(0);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          if (a0 + q >= cnt) break;
+          if (a0 + q == 0) { vi = vj[0]; ri = rj[0] + mij[0] * vi; vi2 = vj2[0]; ri2 = rj2[0] + mij[0] * vi2; continue; }
+          ri += mij[q] * vj[q]; ri2 += mij[q] * vj2[q];
+          res[jj[q]] = rj[q] + mij[q] * vi;
+          res2[jj[q]] = rj2[q] + mij[q] * vi2;
+        }
+      }
+      res[i] = ri; res2[i] = ri2;
+    }
+  }
+
   // res = M vec (mj_mulM, reference call site src/mujoco_sim/mj_sim.cpp:1057)
   template <typename AR, typename AV>
   __device__ __forceinline__ void mul_M(const AR& res, const AV& vec) {
@@ -853,6 +886,12 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_smooth(const KArgs<T> a) {
       // vector of the controller's and mj_inverse's M x products and, at the end, of the solve for qacc_smooth
       if (a.flags & B2F_LD_SMEM) s.tmpv = SArr<T>{ws_sh + (size_t)(nM + nv) * EPB + envl, EPB};
     }
+    // the reference tick needs M ddq (controller) and M qacc (mj_inverse): one pass over M for both, the second product in
+    // the scratch's fourth vector
+    bool both = false;
+    if constexpr (!P::STATIC) both = (a.flags & B2F_LD_SMEM) && a.ld_extra && (a.flags & B2F_CONTROLLER) && (a.flags & B2F_INVERSE);
+    auto tmpv2 = s.tmpv;
+    if constexpr (!P::STATIC) { if (both) tmpv2 = SArr<T>{ws_sh + (size_t)(nM + 2 * nv) * EPB + envl, EPB}; }
 
     // mj_checkPos / mj_checkVel: reset an environment whose state went non-finite
     {
@@ -961,7 +1000,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_smooth(const KArgs<T> a) {
 #pragma unroll
         for (int i = 0; i < P::NV; i++) ddq[i] = a.ddq[i * S + env];
       }
-      s.mul_M(s.tmpv, ddq);
+      if constexpr (!P::STATIC) { if (both) s.mul_M2(s.tmpv, ddq, tmpv2, s.qacc); else s.mul_M(s.tmpv, ddq); }
+      else s.mul_M(s.tmpv, ddq);
       if constexpr (P::STATIC) {
 #pragma unroll(P::UNROLL)
       for (int k_ = P::dof_lo(m); k_ < P::dof_hi(m); k_++) {
@@ -1002,7 +1042,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_smooth(const KArgs<T> a) {
       if (overridden) { s.com_vel(); s.passive(); s.rne(s.qfrc_bias, false); }
       // RNE is affine in the acceleration: RNE(q, v, a) + armature a = M a + bias, so the second tree pass of
       // mj_inverse collapses to one sparse mat-vec with the CRBA matrix already at hand
-      s.mul_M(s.tmpv, s.qacc);
+      if (!both) s.mul_M(s.tmpv, s.qacc);
       if constexpr (P::STATIC) {
 #pragma unroll(P::UNROLL)
       for (int k_ = P::dof_lo(m); k_ < P::dof_hi(m); k_++) { const int i = P::dof_at(m, k_); qfrc_inverse[i] = s.tmpv[i] + s.qfrc_bias[i] - s.qfrc_passive[i]; }
@@ -1012,7 +1052,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_smooth(const KArgs<T> a) {
 #pragma unroll
         for (int q = 0; q < 4; q++) {
           ii[q] = P::dof_at(m, k0 + q < P::dof_hi(m) ? k0 + q : k0);
-          tq[q] = s.tmpv[ii[q]]; bq[q] = s.qfrc_bias[ii[q]]; pq[q] = s.qfrc_passive[ii[q]];
+          tq[q] = tmpv2[ii[q]]; bq[q] = s.qfrc_bias[ii[q]]; pq[q] = s.qfrc_passive[ii[q]];
         }
 #pragma unroll
         for (int q = 0; q < 4; q++) if (k0 + q < P::dof_hi(m)) qfrc_inverse[ii[q]] = tq[q] + bq[q] - pq[q];
