@@ -1292,9 +1292,7 @@ __device__ __forceinline__ void pgs_visit_lane(const T* __restrict__ rec, bool h
 // (the common case: most contacts of a scene share a condim) — record offsets are compile-time constants, no parameter
 // picks, no row padding, contact bounds only (f >= 0).  SH: every such record is staged in shared memory (the loads
 // become LDS instead of generic loads).  Same operation order as pgs_visit_lane.
-// SEG1: every such block lies in ONE kinematic tree (a prop on the table, the arm against the table): its elements of the
-// acceleration are acc[s1 + e] — one address, immediate offsets — instead of a pick between two segments per element.
-template <typename T, int NB, int WCAP, bool SH, bool SEG1 = false>
+template <typename T, int NB, int WCAP, bool SH>
 __device__ __forceinline__ void pgs_visit_lane_exact(const T* __restrict__ rec, bool have, const VecN<T, 4>& h0, const VecN<T, 4>& h1,
                                                      T* __restrict__ acc, T* __restrict__ f, T& improvement) {
   static_assert(NB == 3 || NB == 4, "pyramidal contacts of condim 3 / 4");
@@ -1319,14 +1317,10 @@ __device__ __forceinline__ void pgs_visit_lane_exact(const T* __restrict__ rec, 
   for (int r = 0; r < NROW; r++) fo[r] = have ? f[row0 + r] : T(0);
   T x[WCAP];
   int dofs[WCAP];
-  T* const acc1 = acc + (have ? s1 : 0);
 #pragma unroll
   for (int e = 0; e < WCAP; e++) {
-    if constexpr (SEG1) { dofs[e] = 0; x[e] = e < w ? acc1[e] : T(0); }
-    else {
     dofs[e] = e < n1 ? s1 + e : s2 + e - n1;
     x[e] = e < w ? acc[dofs[e]] : T(0);
-    }
   }
   T u[NB];
 #pragma unroll
@@ -1385,8 +1379,7 @@ __device__ __forceinline__ void pgs_visit_lane_exact(const T* __restrict__ rec, 
       T s0 = 0;
 #pragma unroll
       for (int k = 0; k < NB; k++) s0 = t_fma(d[k], Bv[k][e], s0);
-      if constexpr (SEG1) { if (e < w) acc1[e] = x[e] + s0; }
-      else if (e < w) acc[dofs[e]] = x[e] + s0;
+      if (e < w) acc[dofs[e]] = x[e] + s0;
     }
   }
 }
@@ -1968,12 +1961,11 @@ __global__ void __launch_bounds__(32, MINB) k_pgs_island(const KArgs<T> a) {
           const int ww = __reduce_max_sync(0xffffffffu, dec_int(h0.v[2]) >> 10);
           // every lane with a block has a condim-3 contact staged in shared memory (the common step): exact-shape visit
           const bool ex3 = __all_sync(0xffffffffu, !have || (((code >> 4) & 15) == 3 && c.base != slab));
-          // ... and each of them lies in one kinematic tree (props on the table: the common step of the common step)
-          const bool seg1 = ex3 && ww <= 8 && __all_sync(0xffffffffu, !have || (dec_int(h0.v[2]) & 1023) == (dec_int(h0.v[2]) >> 10));
           // (an exact visit for condim 4 as well was measured and lost: the extra vote per step costs the tail more than
           //  the shorter visit gains where condim-4 steps are the minority, profiles/r02_pgs_analysis.txt)
-          if (seg1) pgs_visit_lane_exact<T, 3, 8, true, true>(rec, have, h0, h1, acc, f, improvement);
-          else if (ex3 && ww <= 8) pgs_visit_lane_exact<T, 3, 8, true>(rec, have, h0, h1, acc, f, improvement);
+          // (an exact visit for blocks that lie in one kinematic tree — one base address, immediate offsets — was measured
+          //  and lost as well: C5 PGS 1.79 -> 1.98 ms)
+          if (ex3 && ww <= 8) pgs_visit_lane_exact<T, 3, 8, true>(rec, have, h0, h1, acc, f, improvement);
           else if (ex3 && ww <= 12) pgs_visit_lane_exact<T, 3, 12, true>(rec, have, h0, h1, acc, f, improvement);
           else if (nbw <= 4) {
             if (ww <= 8) {
