@@ -825,10 +825,11 @@ __device__ void emit_contact(const MV<T>& m, const KArgs<T>& a, int env, int c, 
 template <typename T, int BLOCK, int L>
 // (measured: a 72-register build, seven CTAs per SM = one wave for 16384 environments: C3 0.141 -> 0.137 ms, PR2 0.87 -> 0.77,
 //  but the 20-slot world 0.18 -> 0.33 ms; the 128-register build stays)
-#ifndef B2_COLLIDE_MINB
-#define B2_COLLIDE_MINB 1
-#endif
+#ifdef B2_COLLIDE_MINB
 __global__ void __launch_bounds__(BLOCK, B2_COLLIDE_MINB) k_collide(const KArgs<T> a) {
+#else
+__global__ void __launch_bounds__(BLOCK) k_collide(const KArgs<T> a) {
+#endif
   if ((a.flags & B2F_FUSABLE) && a.pending[0] == 0) return;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
