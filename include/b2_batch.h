@@ -61,7 +61,7 @@ int b2_set_controlled(b2_batch* b, const unsigned char* mask);
 int b2_set_odom(b2_batch* b, int nrobot, const int* dof, const int* qposadr);
 int b2_set_timestep(b2_batch* b, double h);
 /* iterations, tolerance, disableflags (mjOption); scheduling only, results do not depend on them: subbatches (1..8,
- * default 4: windows of the batch that run the tick's kernels side by side on their own streams) and subbatch_min
+ * default 1: windows of the batch that run the tick's kernels side by side on their own streams) and subbatch_min
  * (smallest window in environments, default 2048; a batch too small for two such windows is one window) */
 int b2_set_option(b2_batch* b, const char* name, double value);
 

@@ -57,7 +57,9 @@ struct b2_batch {
   bool obs_on = false;
   void* h_dev = nullptr; // {double h, float h}: the timestep in device memory (KArgs::hp)
   // sub-batches: windows of the batch that run the pipeline side by side on their own streams (batch.cu: run_tick)
-  int nsub = 4;            // windows asked for (b2_set_option "subbatches", B2_SUBBATCH); halved until they are whole tiles
+  int nsub = 1;            // windows asked for (b2_set_option "subbatches", B2_SUBBATCH); halved until they are whole tiles.
+                           // Default 1: worth 2-3 % before the solver visited environments by last tick's iterations, nothing since
+                           // (C3 1.420 / 1.412 / 1.439 / 1.457 ms per tick with 1 / 2 / 4 / 8 windows, C5 3.22 / 3.34 with 1 / 4)
   int sub_min_envs = 2048; // ... of at least this many environments (b2_set_option "subbatch_min")
   std::vector<cudaStream_t> sub_stream;
   std::vector<cudaEvent_t> sub_join;
