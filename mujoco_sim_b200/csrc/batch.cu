@@ -540,6 +540,9 @@ int run_tick(b2_batch* b, int flags) {
   }
   // The kernels of the pipeline for the environments of one window, on one stream.  (prof_mark records on the batch's
   // stream: per-kernel profiling runs the batch as a single window.)
+  int nsub_now = b->nsub;
+  if (b->prof_on || b->chain_n > 0 || b->fused || b->tc_rows > 0) nsub_now = 1;
+  while (nsub_now > 1 && (b->nenvp % (128 * nsub_now) != 0 || b->nenvp / nsub_now < b->sub_min_envs)) nsub_now /= 2;
   auto pipeline = [&](const KArgs<T>& a, cudaStream_t st, int n) -> int {
   if (b->fusable) CK(cudaMemsetAsync(a.pending, 0, sizeof(int), st));
   prof_mark(b, SLOT_SMOOTH);
@@ -594,6 +597,16 @@ int run_tick(b2_batch* b, int flags) {
       const int gr = std::max(1, std::min(n / (BL / RL), b->nsm * occ_cache[oi]));
       k_make_rows<T, BL, RL><<<gr, BL, smr, st>>>(ar);
     }
+    // the solver's visit order needs only the row counts (k_make_rows) and last tick's iteration counts: its one-CTA sort
+    // runs on a side stream next to k_make_blocks (forked here, joined in front of the solver; also inside the graph)
+    cudaStream_t ost = st;
+    const bool fork_order = !(flags & B2_TICK_NOSOLVE) && nsub_now <= 1 && !b->prof_on && !getenv("B2_NO_ORDER_FORK");
+    if (fork_order) {
+      if (ensure_sub_streams(b, 2) < 0) return -1;
+      ost = b->sub_stream[0];
+      CK(cudaEventRecord(b->sub_fork, st));
+      CK(cudaStreamWaitEvent(ost, b->sub_fork, 0));
+    }
     if (b->tc_rows > 0) {
       // one-tree model, fp32: dense M^-1 per environment, then B = J M^-1 on the tensor cores (k_project_tc.cuh)
       if constexpr (sizeof(T) == 4) {
@@ -628,8 +641,9 @@ int run_tick(b2_batch* b, int flags) {
     }
     if (!(flags & B2_TICK_NOSOLVE)) {
       prof_mark(b, SLOT_PGS);
-      k_order_envs<256, 1024><<<1, 1024, 0, st>>>(a.nefc, a.efc_nwords, a.env_order, n, std::max(4, b->block_capw / 256), a.pending, b->fusable ? 1 : 0,
+      k_order_envs<256, 1024><<<1, 1024, 0, ost>>>(a.nefc, a.efc_nwords, a.env_order, n, std::max(4, b->block_capw / 256), a.pending, b->fusable ? 1 : 0,
                                               (b->isl_cap && !getenv("B2_ORDER_BY_WORDS")) ? a.solver_iter : nullptr, 1);
+      if (fork_order) { CK(cudaEventRecord(b->sub_join[0], ost)); CK(cudaStreamWaitEvent(st, b->sub_join[0], 0)); }
       // (measured: the one-environment-per-team block solver is fastest with the volume-only order — PR2 5.66 ms against
       //  6.2 / 6.4 ms with last tick's iterations in the key)
       b->launches += 1;
@@ -681,9 +695,7 @@ int run_tick(b2_batch* b, int flags) {
   // kernel of the tick is bound by per-environment latency at 10-25 % of the SM's warp slots, and the solver ends in a
   // tail of a few slow environments: windows in different stages fill each other's gaps.  Results do not depend on the
   // cut (an environment never looks at another one).
-  int nsub = b->nsub;
-  if (b->prof_on || b->chain_n > 0 || b->fused || b->tc_rows > 0) nsub = 1;
-  while (nsub > 1 && (b->nenvp % (128 * nsub) != 0 || b->nenvp / nsub < b->sub_min_envs)) nsub /= 2;
+  const int nsub = nsub_now;
   if (nsub <= 1) {
     if (pipeline(a, b->stream, b->nenvp) < 0) return -1;
   } else {
