@@ -462,7 +462,7 @@ int launch_chain(b2_batch* b, const KArgs<T>& a, int grid) {
 void io_default(b2_batch* b);
 void drop_aliases(b2_batch* b);
 int hw_write_async(b2_batch* b, int flags = 0, bool gather = false);  // k_hw_write from b->io_in (+ pre-integration pos / vel gather)
-int hw_read_async(b2_batch* b, bool post = true);   // k_hw_read into b->io_out
+int hw_read_async(b2_batch* b, bool post = true, cudaStream_t st = nullptr);   // k_hw_read into b->io_out (st: default the batch's stream)
 enum { B2_TICK_HW = 1 << 20 };  // internal: run k_hw_write / k_hw_read around the tick kernels
 
 template <typename D>
@@ -540,9 +540,13 @@ int run_tick(b2_batch* b, int flags) {
   }
   // The kernels of the pipeline for the environments of one window, on one stream.  (prof_mark records on the batch's
   // stream: per-kernel profiling runs the batch as a single window.)
+  bool hw_read_early = false;
   int nsub_now = b->nsub;
   if (b->prof_on || b->chain_n > 0 || b->fused || b->tc_rows > 0) nsub_now = 1;
   while (nsub_now > 1 && (b->nenvp % (128 * nsub_now) != 0 || b->nenvp / nsub_now < b->sub_min_envs)) nsub_now /= 2;
+  hw_read_early = (flags & B2_TICK_HW) && !read_post && !(flags & B2_TICK_NOSOLVE) && !b->fused && nsub_now <= 1 && !b->prof_on &&
+                  !getenv("B2_NO_ORDER_FORK");
+  if (hw_read_early && ensure_sub_streams(b, 2) < 0) return -1;
   auto pipeline = [&](const KArgs<T>& a, cudaStream_t st, int n) -> int {
   if (b->fusable) CK(cudaMemsetAsync(a.pending, 0, sizeof(int), st));
   prof_mark(b, SLOT_SMOOTH);
@@ -667,6 +671,15 @@ int run_tick(b2_batch* b, int flags) {
       else if (b->pgs_lanes == 32) k_pgs_block<T, 32, PB, PGS_MINB><<<g3, PB, smp, st>>>(a);
       else k_pgs_block<T, 8, PB, PGS_MINB><<<g3, PB, smp, st>>>(a);
       }
+      // the joint read-back of the reference's order (effort = qfrc_inverse, complete once the solver has subtracted its
+      // J^T f; positions / velocities were gathered before the step) does not wait for the integration: side stream
+      if (hw_read_early) {
+        cudaStream_t rst = b->sub_stream[0];
+        CK(cudaEventRecord(b->sub_fork, st));
+        CK(cudaStreamWaitEvent(rst, b->sub_fork, 0));
+        if (hw_read_async(b, false, rst) < 0) return -1;
+        CK(cudaEventRecord(b->sub_join[0], rst));
+      }
       prof_mark(b, SLOT_INTEGRATE);
       const int TL = b->chain_n > 0 ? 1 : b->tree_lanes;
       if (TL > 1) {
@@ -712,7 +725,8 @@ int run_tick(b2_batch* b, int flags) {
   if (flags & B2_TICK_INTEGRATE) hold_slots<T>(b);   // inactive object slots go back to their parking place
   if (obs && !obs_fused) { k_publish_obs<T><<<(b->nenv + 127) / 128, 128, 0, b->stream>>>(a); b->launches++; }
   prof_mark(b, SLOT_HW_READ);
-  if (flags & B2_TICK_HW) { if (hw_read_async(b, read_post) < 0) return -1; }
+  if (hw_read_early) CK(cudaStreamWaitEvent(b->stream, b->sub_join[0], 0));
+  else if (flags & B2_TICK_HW) { if (hw_read_async(b, read_post) < 0) return -1; }
   CK(cudaGetLastError());
   return 0;
 }
@@ -1482,13 +1496,14 @@ int hw_write_async(b2_batch* b, int flags, bool gather) {
   CK(cudaGetLastError());
   return 0;
 }
-int hw_read_async(b2_batch* b, bool post) {
+int hw_read_async(b2_batch* b, bool post, cudaStream_t st) {
+  if (!st) st = b->stream;
   if (!b->nhw) return fail("b2_read_joints: call b2_set_hw_joints first");
   const size_t n = (size_t)b->nhw * b->nenv;
   const int th = 256, bl = (int)((n + th - 1) / th);
   float* po = post ? b->io_out[0] : nullptr; float* vo = post ? b->io_out[1] : nullptr;
-  if (b->prec == 8) k_hw_read<double><<<bl, th, 0, b->stream>>>((const double*)b->fields["qpos"].ptr, (const double*)b->fields["qvel"].ptr, (const double*)b->fields["qfrc_inverse"].ptr, po, vo, b->io_out[2], b->hw_qadr, b->hw_dadr, b->nhw, b->nenv, b->nenvp);
-  else k_hw_read<float><<<bl, th, 0, b->stream>>>((const float*)b->fields["qpos"].ptr, (const float*)b->fields["qvel"].ptr, (const float*)b->fields["qfrc_inverse"].ptr, po, vo, b->io_out[2], b->hw_qadr, b->hw_dadr, b->nhw, b->nenv, b->nenvp);
+  if (b->prec == 8) k_hw_read<double><<<bl, th, 0, st>>>((const double*)b->fields["qpos"].ptr, (const double*)b->fields["qvel"].ptr, (const double*)b->fields["qfrc_inverse"].ptr, po, vo, b->io_out[2], b->hw_qadr, b->hw_dadr, b->nhw, b->nenv, b->nenvp);
+  else k_hw_read<float><<<bl, th, 0, st>>>((const float*)b->fields["qpos"].ptr, (const float*)b->fields["qvel"].ptr, (const float*)b->fields["qfrc_inverse"].ptr, po, vo, b->io_out[2], b->hw_qadr, b->hw_dadr, b->nhw, b->nenv, b->nenvp);
   b->launches++;
   CK(cudaGetLastError());
   return 0;
